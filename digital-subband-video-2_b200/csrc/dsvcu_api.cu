@@ -1,0 +1,1081 @@
+/*
+ * dsvcu_api.cu -- implementation of the C ABI declared in include/dsv_cuda.h.
+ *
+ * Owns device memory (frames, coefficient planes, scratch), builds the per-level
+ * launch plans and launches the kernels in k_*.cuh.  Host-side scalar math that
+ * the reference evaluates once per band/frame (lfquant, hfquant,
+ * dsv_spatial_psy_factor, compute_filter_q, level/filter selection) lives here.
+ */
+#include "dsvcu_rt.h"
+#include "k_sbt.cuh"
+#include "k_quant.cuh"
+#include "k_bmc.cuh"
+#include "k_filter.cuh"
+#include "k_frame.cuh"
+#include "../../include/dsv_cuda.h"
+
+#ifdef DSVCU_EMU
+dsvcu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+unsigned char *dsvcu_emu_smem = 0;
+size_t dsvcu_emu_smem_size = 0;
+#endif
+
+#define RSHIFT_UP(x, s) (((x) + (1 << (s)) - 1) >> (s))
+#define FMT_HSHIFT(f) (((f) >> 2) & 3)
+#define FMT_VSHIFT(f) ((f) & 3)
+#define PSY_I_VISUAL_MASKING 4
+#define PSY_P_VISUAL_MASKING 8
+
+static char g_err[256] = "";
+
+static int
+fail(const char *what, int code)
+{
+#ifndef DSVCU_EMU
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString((cudaError_t) code));
+#else
+    snprintf(g_err, sizeof(g_err), "%s: error %d", what, code);
+#endif
+    return -1;
+}
+
+#define CK(call)                                  \
+    do {                                          \
+        int e_ = (int) (call);                    \
+        if (e_ != 0) return fail(#call, e_);      \
+    } while (0)
+
+#ifndef DSVCU_EMU
+#define CK_LAUNCH(ctx)                                             \
+    do {                                                           \
+        (ctx)->launches++;                                         \
+        cudaError_t e_ = cudaGetLastError();                       \
+        if (e_ != cudaSuccess) return fail("kernel launch", e_);   \
+    } while (0)
+#else
+#define CK_LAUNCH(ctx) ((ctx)->launches++)
+#endif
+
+struct dsvcu_plane_t {
+    uint8_t *base; /* first byte of the bordered plane */
+    uint8_t *data; /* pixel (0,0) */
+    int w, h, stride;
+};
+
+struct dsvcu_frame {
+    uint8_t *alloc;
+    size_t bytes;
+    int nplanes;
+    dsvcu_plane_t p[3];
+};
+
+struct dsvcu_coefs {
+    int32_t *alloc;
+    int32_t *data[3];
+    int w[3], h[3];
+};
+
+struct dsvcu_ctx {
+    int device;
+    dsvcu_stream_t stream;
+    int width, height, subsamp;
+    int cw[3], ch[3]; /* coefficient plane dims */
+    long long launches;
+    /* side information */
+    uint8_t *d_blockdata;
+    dsvcu_mv *d_mvs;
+    int nblk_cap;
+    /* transform scratch: two planes of the largest coefficient plane */
+    int32_t *scratch[2];
+    /* quantiser outputs */
+    int32_t *d_qv;
+    int *d_chunk;
+    int *d_meta;          /* [0..2] nsyms, [3..5] dc */
+    int *h_meta;          /* pinned mirror */
+    dsvcu_sym *d_syms[3];
+    dsvcu_sym *h_syms[3]; /* pinned */
+    int sym_cap[3];
+    int *d_progress;
+    int progress_cap;
+#ifndef DSVCU_EMU
+    cudaEvent_t ev0, ev1;
+#endif
+};
+
+static int
+ilb2(unsigned n) /* dsv_lb2, dsv.c:449-459: ceil(log2(n)) */
+{
+    unsigned i = 1;
+    int l = 0;
+    while (i < n) {
+        i <<= 1;
+        l++;
+    }
+    return l;
+}
+
+static int
+grid_for(int total, int threads)
+{
+    int g = (total + threads - 1) / threads;
+    if (g < 1) g = 1;
+    if (g > 148 * 16) g = 148 * 16;
+    return g;
+}
+
+/* ------------------------------------------------------------------ context */
+
+extern "C" const char *
+dsvcu_last_error(void)
+{
+    return g_err;
+}
+
+extern "C" int
+dsvcu_device_count(void)
+{
+#ifndef DSVCU_EMU
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+#else
+    return 1;
+#endif
+}
+
+static void
+coef_dims(int subsamp, int w, int h, int cw[3], int ch[3])
+{
+    /* dsv_mk_coefs, frame.c:29-60: chroma dims rounded up to even */
+    int cwid = RSHIFT_UP(w, FMT_HSHIFT(subsamp));
+    int chei = RSHIFT_UP(h, FMT_VSHIFT(subsamp));
+    cwid = (cwid + 1) & ~1;
+    chei = (chei + 1) & ~1;
+    cw[0] = w;
+    ch[0] = h;
+    cw[1] = cw[2] = cwid;
+    ch[1] = ch[2] = chei;
+}
+
+extern "C" int
+dsvcu_ctx_create(dsvcu_ctx **out, int device, int width, int height, int subsamp)
+{
+    dsvcu_ctx *c;
+    int i;
+    size_t maxplane;
+    *out = NULL;
+#ifndef DSVCU_EMU
+    {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n <= 0) {
+            snprintf(g_err, sizeof(g_err), "no CUDA device available (%s); this library has no CPU path",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+            return -1;
+        }
+        if (device < 0 || device >= n) {
+            snprintf(g_err, sizeof(g_err), "device %d out of range (have %d)", device, n);
+            return -1;
+        }
+        CK(cudaSetDevice(device));
+    }
+#endif
+    c = (dsvcu_ctx *) calloc(1, sizeof(*c));
+    if (!c) return -1;
+    c->device = device;
+    c->width = width;
+    c->height = height;
+    c->subsamp = subsamp;
+    coef_dims(subsamp, width, height, c->cw, c->ch);
+#ifndef DSVCU_EMU
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+#endif
+    maxplane = (size_t) c->cw[0] * c->ch[0];
+    if ((size_t) c->cw[1] * c->ch[1] > maxplane) maxplane = (size_t) c->cw[1] * c->ch[1];
+    CK(dsvcu_malloc(&c->scratch[0], maxplane * sizeof(int32_t)));
+    CK(dsvcu_malloc(&c->scratch[1], maxplane * sizeof(int32_t)));
+    CK(dsvcu_malloc(&c->d_qv, (maxplane + CMP_CHUNK) * sizeof(int32_t)));
+    CK(dsvcu_malloc(&c->d_chunk, (maxplane / CMP_CHUNK + 2) * sizeof(int)));
+    CK(dsvcu_malloc(&c->d_meta, 8 * sizeof(int)));
+    CK(dsvcu_malloc_host(&c->h_meta, 8 * sizeof(int)));
+    for (i = 0; i < 3; i++) {
+        c->sym_cap[i] = c->cw[i] * c->ch[i] + 8;
+        CK(dsvcu_malloc(&c->d_syms[i], (size_t) c->sym_cap[i] * sizeof(dsvcu_sym)));
+        CK(dsvcu_malloc_host(&c->h_syms[i], (size_t) c->sym_cap[i] * sizeof(dsvcu_sym)));
+    }
+    c->progress_cap = height / 4 + 64;
+    CK(dsvcu_malloc(&c->d_progress, (size_t) c->progress_cap * sizeof(int)));
+    *out = c;
+    return 0;
+}
+
+extern "C" void
+dsvcu_ctx_destroy(dsvcu_ctx *c)
+{
+    int i;
+    if (!c) return;
+#ifndef DSVCU_EMU
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+#endif
+    dsvcu_free_dev(c->scratch[0]);
+    dsvcu_free_dev(c->scratch[1]);
+    dsvcu_free_dev(c->d_qv);
+    dsvcu_free_dev(c->d_chunk);
+    dsvcu_free_dev(c->d_meta);
+    dsvcu_free_host(c->h_meta);
+    for (i = 0; i < 3; i++) {
+        dsvcu_free_dev(c->d_syms[i]);
+        dsvcu_free_host(c->h_syms[i]);
+    }
+    dsvcu_free_dev(c->d_progress);
+    if (c->d_blockdata) dsvcu_free_dev(c->d_blockdata);
+    if (c->d_mvs) dsvcu_free_dev(c->d_mvs);
+#ifndef DSVCU_EMU
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+#endif
+    free(c);
+}
+
+extern "C" void *
+dsvcu_ctx_stream(dsvcu_ctx *c)
+{
+#ifndef DSVCU_EMU
+    return (void *) c->stream;
+#else
+    (void) c;
+    return NULL;
+#endif
+}
+
+extern "C" int
+dsvcu_sync(dsvcu_ctx *c)
+{
+    (void) c;
+    CK(dsvcu_stream_sync(c->stream));
+    return 0;
+}
+
+extern "C" long long
+dsvcu_launch_count(dsvcu_ctx *c)
+{
+    return c->launches;
+}
+
+extern "C" int
+dsvcu_timer_start(dsvcu_ctx *c)
+{
+#ifndef DSVCU_EMU
+    CK(cudaEventRecord(c->ev0, c->stream));
+#else
+    (void) c;
+#endif
+    return 0;
+}
+
+extern "C" int
+dsvcu_timer_stop_ms(dsvcu_ctx *c, float *ms)
+{
+#ifndef DSVCU_EMU
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+#else
+    (void) c;
+    *ms = 0.f;
+#endif
+    return 0;
+}
+
+/* ------------------------------------------------------------------- frames */
+
+static int
+frame_alloc(dsvcu_frame **out, int nplanes, const int w[3], const int h[3])
+{
+    /* geometry of dsv_mk_frame with border, frame.c:62-113: stride =
+     * round16(w + 64), 32 rows above and below; 8 spare rows keep the clamped
+     * +3 sub-pel window inside the allocation */
+    dsvcu_frame *f = (dsvcu_frame *) calloc(1, sizeof(*f));
+    size_t off[3], total = 0;
+    int i;
+    if (!f) return -1;
+    f->nplanes = nplanes;
+    for (i = 0; i < nplanes; i++) {
+        f->p[i].w = w[i];
+        f->p[i].h = h[i];
+        f->p[i].stride = (w[i] + 2 * FR_BORDER + 15) & ~15;
+        off[i] = total;
+        total += (size_t) f->p[i].stride * (h[i] + 2 * FR_BORDER + 8);
+        total = (total + 255) & ~(size_t) 255;
+    }
+    f->bytes = total;
+    CK(dsvcu_malloc(&f->alloc, total));
+    for (i = 0; i < nplanes; i++) {
+        f->p[i].base = f->alloc + off[i];
+        f->p[i].data = f->p[i].base + (size_t) f->p[i].stride * FR_BORDER + FR_BORDER;
+    }
+    *out = f;
+    return 0;
+}
+
+extern "C" int
+dsvcu_frame_create(dsvcu_ctx *c, dsvcu_frame **out)
+{
+    int w[3], h[3], r;
+    w[0] = c->width;
+    h[0] = c->height;
+    w[1] = w[2] = RSHIFT_UP(c->width, FMT_HSHIFT(c->subsamp));
+    h[1] = h[2] = RSHIFT_UP(c->height, FMT_VSHIFT(c->subsamp));
+    r = frame_alloc(out, 3, w, h);
+    if (r == 0) {
+        CK(dsvcu_memset_async((*out)->alloc, 0, (*out)->bytes, c->stream));
+    }
+    return r;
+}
+
+extern "C" int
+dsvcu_frame_create_luma(dsvcu_ctx *c, dsvcu_frame **out, int w, int h)
+{
+    int ww[3] = { w, 0, 0 }, hh[3] = { h, 0, 0 }, r;
+    r = frame_alloc(out, 1, ww, hh);
+    if (r == 0) {
+        CK(dsvcu_memset_async((*out)->alloc, 0, (*out)->bytes, c->stream));
+    }
+    return r;
+}
+
+extern "C" void
+dsvcu_frame_destroy(dsvcu_ctx *c, dsvcu_frame *f)
+{
+    (void) c;
+    if (!f) return;
+    dsvcu_free_dev(f->alloc);
+    free(f);
+}
+
+extern "C" int
+dsvcu_frame_plane_dims(dsvcu_frame *f, int plane, int *w, int *h, int *stride)
+{
+    if (plane < 0 || plane >= f->nplanes) return -1;
+    if (w) *w = f->p[plane].w;
+    if (h) *h = f->p[plane].h;
+    if (stride) *stride = f->p[plane].stride;
+    return 0;
+}
+
+extern "C" int
+dsvcu_frame_upload(dsvcu_ctx *c, dsvcu_frame *f, int plane, const uint8_t *src, int hstride)
+{
+    dsvcu_plane_t *p = &f->p[plane];
+    CK(dsvcu_h2d_2d_async(p->data, p->stride, src, hstride, p->w, p->h, c->stream));
+    return 0;
+}
+
+extern "C" int
+dsvcu_frame_download(dsvcu_ctx *c, dsvcu_frame *f, int plane, uint8_t *dst, int hstride)
+{
+    dsvcu_plane_t *p = &f->p[plane];
+    CK(dsvcu_d2h_2d_async(dst, hstride, p->data, p->stride, p->w, p->h, c->stream));
+    return 0;
+}
+
+extern "C" int
+dsvcu_frame_clear_plane(dsvcu_ctx *c, dsvcu_frame *f, int plane, int value)
+{
+    dsvcu_plane_t *p = &f->p[plane];
+    CK(dsvcu_memset_2d_async(p->data, p->stride, value, p->w, p->h, c->stream));
+    return 0;
+}
+
+extern "C" int
+dsvcu_frame_upload_bordered(dsvcu_ctx *c, dsvcu_frame *f, int plane, const uint8_t *src)
+{
+    dsvcu_plane_t *p = &f->p[plane];
+    CK(dsvcu_h2d_async(p->base, src, (size_t) p->stride * (p->h + 2 * FR_BORDER), c->stream));
+    return 0;
+}
+
+extern "C" int
+dsvcu_frame_download_bordered(dsvcu_ctx *c, dsvcu_frame *f, int plane, uint8_t *dst)
+{
+    dsvcu_plane_t *p = &f->p[plane];
+    CK(dsvcu_d2h_async(dst, p->base, (size_t) p->stride * (p->h + 2 * FR_BORDER), c->stream));
+    return 0;
+}
+
+/* ------------------------------------------------------------- coefficients */
+
+extern "C" int
+dsvcu_coefs_create(dsvcu_ctx *c, dsvcu_coefs **out)
+{
+    dsvcu_coefs *k = (dsvcu_coefs *) calloc(1, sizeof(*k));
+    size_t n = 0;
+    int i;
+    if (!k) return -1;
+    for (i = 0; i < 3; i++) {
+        k->w[i] = c->cw[i];
+        k->h[i] = c->ch[i];
+        n += (size_t) k->w[i] * k->h[i];
+    }
+    CK(dsvcu_malloc(&k->alloc, n * sizeof(int32_t)));
+    CK(dsvcu_memset_async(k->alloc, 0, n * sizeof(int32_t), c->stream));
+    k->data[0] = k->alloc;
+    k->data[1] = k->data[0] + (size_t) k->w[0] * k->h[0];
+    k->data[2] = k->data[1] + (size_t) k->w[1] * k->h[1];
+    *out = k;
+    return 0;
+}
+
+extern "C" void
+dsvcu_coefs_destroy(dsvcu_ctx *c, dsvcu_coefs *k)
+{
+    (void) c;
+    if (!k) return;
+    dsvcu_free_dev(k->alloc);
+    free(k);
+}
+
+extern "C" int
+dsvcu_coefs_plane_dims(dsvcu_coefs *k, int plane, int *w, int *h)
+{
+    if (w) *w = k->w[plane];
+    if (h) *h = k->h[plane];
+    return 0;
+}
+
+extern "C" int
+dsvcu_coefs_upload(dsvcu_ctx *c, dsvcu_coefs *k, int plane, const int32_t *src)
+{
+    CK(dsvcu_h2d_async(k->data[plane], src, (size_t) k->w[plane] * k->h[plane] * sizeof(int32_t), c->stream));
+    return 0;
+}
+
+extern "C" int
+dsvcu_coefs_download(dsvcu_ctx *c, dsvcu_coefs *k, int plane, int32_t *dst)
+{
+    CK(dsvcu_d2h_async(dst, k->data[plane], (size_t) k->w[plane] * k->h[plane] * sizeof(int32_t), c->stream));
+    return 0;
+}
+
+/* --------------------------------------------------------- side information */
+
+static int
+ensure_blocks(dsvcu_ctx *c, int n)
+{
+    if (n <= c->nblk_cap) return 0;
+    if (c->d_blockdata) dsvcu_free_dev(c->d_blockdata);
+    if (c->d_mvs) dsvcu_free_dev(c->d_mvs);
+    c->d_blockdata = NULL;
+    c->d_mvs = NULL;
+    CK(dsvcu_malloc(&c->d_blockdata, (size_t) n + 64));
+    CK(dsvcu_malloc(&c->d_mvs, ((size_t) n + 4) * sizeof(dsvcu_mv)));
+    CK(dsvcu_memset_async(c->d_blockdata, 0, (size_t) n + 64, c->stream));
+    CK(dsvcu_memset_async(c->d_mvs, 0, ((size_t) n + 4) * sizeof(dsvcu_mv), c->stream));
+    c->nblk_cap = n;
+    return 0;
+}
+
+extern "C" int
+dsvcu_set_blockdata(dsvcu_ctx *c, const uint8_t *bd, int n)
+{
+    if (ensure_blocks(c, n)) return -1;
+    CK(dsvcu_h2d_async(c->d_blockdata, bd, (size_t) n, c->stream));
+    return 0;
+}
+
+extern "C" int
+dsvcu_set_mvs(dsvcu_ctx *c, const void *mvs, int n)
+{
+    if (ensure_blocks(c, n)) return -1;
+    CK(dsvcu_h2d_async(c->d_mvs, mvs, (size_t) n * sizeof(dsvcu_mv), c->stream));
+    return 0;
+}
+
+/* ---------------------------------------------------------------- transforms */
+
+static int
+sbt_nlevels(int w, int h) /* sbt.c:834-845 */
+{
+    return ilb2((unsigned) (w > h ? w : h));
+}
+
+/* which 1-D filter family a level uses (sbt.c:19-29, :862-930) */
+static int
+sbt_pick(int l, int lvls, int luma, int isP, int lossless)
+{
+    if (lossless) {
+        return (l >= 1 && l <= lvls - 2) ? SBT_F_LOSSLESS : SBT_F_HAAR_SIMPLE;
+    }
+    if (luma && !isP && l == 4) return SBT_F_LLI;
+    if (luma && isP && l == 4) return SBT_F_LLP;
+    if (!luma && !isP && l >= 1 && l <= lvls - 2) return SBT_F_CC;
+    if (luma && !isP && l == 2) return SBT_F_L2A;
+    if (luma && !isP && l == 1) return SBT_F_L1;
+    return (luma || !isP) ? SBT_F_HAAR : SBT_F_HAAR_SIMPLE;
+}
+
+static void
+sbt_level_geom(SbtLevel *L, int w, int h, int l, const dsvcu_fmeta *fm, const uint8_t *bd)
+{
+    memset(L, 0, sizeof(*L));
+    L->fw = w;
+    L->sw = RSHIFT_UP(w, l - 1);
+    L->sh = RSHIFT_UP(h, l - 1);
+    L->cw = RSHIFT_UP(w, l);
+    L->ch = RSHIFT_UP(h, l);
+    L->blockdata = bd;
+    L->nbh = fm->nblocks_h;
+    L->dbx = (fm->nblocks_h << BLOCK_INTERP_P) / L->sw;
+    L->dby = (fm->nblocks_v << BLOCK_INTERP_P) / L->sh;
+}
+
+extern "C" int
+dsvcu_inv_sbt(dsvcu_ctx *c, dsvcu_frame *dst, int plane, dsvcu_coefs *src, int q, const dsvcu_fmeta *fm)
+{
+    const int w = src->w[plane], h = src->h[plane];
+    const int lvls = sbt_nlevels(w, h);
+    const int luma = (plane == 0);
+    int l;
+    for (l = lvls; l > 0; l--) {
+        SbtLevel L;
+        int f = sbt_pick(l, lvls, luma, fm->isP, fm->lossless);
+        dim3 tg;
+        sbt_level_geom(&L, w, h, l, fm, c->d_blockdata);
+        L.hqp = luma ? (q / (fm->isP ? 14 : (l > 4 ? 2 : 8))) : (q / 2);
+        L.ovf = (l >= 6 && l >= lvls - 3 && !fm->lossless);
+        L.ll = (l == lvls) ? src->data[plane] : c->scratch[(l + 1) & 1];
+        L.bands = src->data[plane];
+        if (l == 1) {
+            L.px = dst->p[plane].data;
+            L.px_stride = dst->p[plane].stride;
+            L.px_w = dst->p[plane].w;
+            L.px_h = dst->p[plane].h;
+        } else {
+            L.dst = c->scratch[l & 1];
+        }
+        tg = dim3((L.sw + SBT_TW - 1) / SBT_TW, (L.sh + SBT_TH - 1) / SBT_TH, 1);
+        switch (f) {
+            case SBT_F_LLI: DSVCU_LAUNCH(k_inv_lift<SBT_F_LLI>, tg, SBT_THREADS, 0, c->stream, L); break;
+            case SBT_F_LLP: DSVCU_LAUNCH(k_inv_lift<SBT_F_LLP>, tg, SBT_THREADS, 0, c->stream, L); break;
+            case SBT_F_CC: DSVCU_LAUNCH(k_inv_lift<SBT_F_CC>, tg, SBT_THREADS, 0, c->stream, L); break;
+            case SBT_F_L2A: DSVCU_LAUNCH(k_inv_lift<SBT_F_L2A>, tg, SBT_THREADS, 0, c->stream, L); break;
+            case SBT_F_L1: DSVCU_LAUNCH(k_inv_lift<SBT_F_L1>, tg, SBT_THREADS, 0, c->stream, L); break;
+            case SBT_F_LOSSLESS: DSVCU_LAUNCH(k_inv_lift<SBT_F_LOSSLESS>, tg, SBT_THREADS, 0, c->stream, L); break;
+            case SBT_F_HAAR:
+                DSVCU_LAUNCH(k_inv_haar<true>, grid_for(L.cw * L.ch, 256), 256, 0, c->stream, L);
+                break;
+            default:
+                DSVCU_LAUNCH(k_inv_haar<false>, grid_for(L.cw * L.ch, 256), 256, 0, c->stream, L);
+                break;
+        }
+        CK_LAUNCH(c);
+    }
+    return 0;
+}
+
+extern "C" int
+dsvcu_fwd_sbt(dsvcu_ctx *c, dsvcu_frame *src, int plane, dsvcu_coefs *dst, const dsvcu_fmeta *fm)
+{
+    const int w = dst->w[plane], h = dst->h[plane];
+    const int lvls = sbt_nlevels(w, h);
+    const int luma = (plane == 0);
+    int l;
+    for (l = 1; l <= lvls; l++) {
+        SbtLevel L;
+        int f = sbt_pick(l, lvls, luma, fm->isP, fm->lossless);
+        dim3 tg;
+        sbt_level_geom(&L, w, h, l, fm, c->d_blockdata);
+        L.ovf = (l >= 6 && l >= lvls - 3 && !fm->lossless);
+        if (l == 1) {
+            L.px = src->p[plane].data;
+            L.px_stride = src->p[plane].stride;
+            L.px_w = src->p[plane].w;
+            L.px_h = src->p[plane].h;
+        } else {
+            L.src = c->scratch[(l - 1) & 1];
+        }
+        L.out_ll = (l == lvls) ? dst->data[plane] : c->scratch[l & 1];
+        L.out_bands = dst->data[plane];
+        tg = dim3((L.sw + SBT_TW - 1) / SBT_TW, (L.sh + SBT_TH - 1) / SBT_TH, 1);
+        switch (f) {
+            case SBT_F_LLI: DSVCU_LAUNCH(k_fwd_lift<SBT_F_LLI>, tg, SBT_THREADS, 0, c->stream, L); break;
+            case SBT_F_LLP: DSVCU_LAUNCH(k_fwd_lift<SBT_F_LLP>, tg, SBT_THREADS, 0, c->stream, L); break;
+            case SBT_F_CC: DSVCU_LAUNCH(k_fwd_lift<SBT_F_CC>, tg, SBT_THREADS, 0, c->stream, L); break;
+            case SBT_F_L2A: DSVCU_LAUNCH(k_fwd_lift<SBT_F_L2A>, tg, SBT_THREADS, 0, c->stream, L); break;
+            case SBT_F_L1: DSVCU_LAUNCH(k_fwd_l1, tg, SBT_THREADS, 0, c->stream, L); break;
+            case SBT_F_LOSSLESS: DSVCU_LAUNCH(k_fwd_lift<SBT_F_LOSSLESS>, tg, SBT_THREADS, 0, c->stream, L); break;
+            default:
+                DSVCU_LAUNCH(k_fwd_haar, grid_for(L.cw * L.ch, 256), 256, 0, c->stream, L);
+                break;
+        }
+        CK_LAUNCH(c);
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------- quantisation */
+
+static int
+psy_factor(const dsvcu_fmeta *fm, int subband) /* dsv_spatial_psy_factor, hzcc.c:66-86 */
+{
+    int scale, lo, hi;
+    int bw = fm->blk_w, bh = fm->blk_h;
+    if (subband == 1) {
+        lo = (352 + bw - 1) / bw;
+        hi = (1920 + bw - 1) / bw;
+        scale = fm->nblocks_h;
+    } else if (subband == 2) {
+        lo = (288 + bh - 1) / bh;
+        hi = (1080 + bh - 1) / bh;
+        scale = fm->nblocks_v;
+    } else {
+        lo = ((352 + bw - 1) / bw) * ((288 + bh - 1) / bh);
+        hi = ((1920 + bw - 1) / bw) * ((1080 + bh - 1) / bh);
+        scale = fm->nblocks_h * fm->nblocks_v;
+    }
+    scale = scale - lo > 0 ? scale - lo : 0;
+    return (scale << 7) / (hi - lo);
+}
+
+static int
+lfquant(int q, int plane, const dsvcu_fmeta *fm) /* hzcc.c:88-105 */
+{
+    int psyfac = psy_factor(fm, 3);
+    q -= (q * psyfac >> (7 + 3));
+    if (q < 8) q = 8;
+    if (plane) {
+        if (q > 256) q = 256 + q / 4;
+        return q < 768 ? q : 768;
+    }
+    return q < 3072 ? q : 3072;
+}
+
+static int
+hfquant(const dsvcu_fmeta *fm, int plane, int subsamp, int q, int s, int l) /* hzcc.c:107-162 */
+{
+    int chroma = (plane != 0);
+    int psyfac = psy_factor(fm, s);
+    q /= 2;
+    psyfac = q * psyfac >> (7 + (fm->isP ? 0 : 1));
+    if (chroma) {
+        int tl = l - 2;
+        if (s == 1) {
+            tl += FMT_HSHIFT(subsamp);
+        } else if (s == 2) {
+            tl += FMT_VSHIFT(subsamp);
+        }
+        q = (q * 6) / (4 - tl);
+    } else {
+        if (l == 1) {
+            q += psyfac / 2;
+        } else if (l == 2) {
+            q += psyfac;
+        }
+    }
+    if (fm->isP) {
+        if (l != 2) {
+            if (l == 0) {
+                q *= 2;
+                q -= psyfac;
+            } else {
+                q -= psyfac / 2;
+            }
+        }
+        return (q / 4) > 8 ? (q / 4) : 8;
+    }
+    q = q * (15 + 3 * l) / 16;
+    if (!chroma) {
+        if (l == 0) {
+            q = (q * 3) / 8;
+        } else if (s == 3) {
+            q *= 2;
+        }
+    } else {
+        q /= 4;
+        if (s == 3) q *= 2;
+    }
+    return q > 8 ? q : 8;
+}
+
+extern "C" int
+dsvcu_scan_layout(int w, int h, int part_start[5])
+{
+    int l, pos;
+    pos = RSHIFT_UP(w, 3) * RSHIFT_UP(h, 3);
+    part_start[0] = 0;
+    for (l = 0; l < 3; l++) {
+        part_start[1 + l] = pos;
+        pos += 3 * RSHIFT_UP(w, 3 - l) * RSHIFT_UP(h, 3 - l);
+    }
+    part_start[4] = pos;
+    return pos;
+}
+
+static void
+quant_level_geom(QuantLevel *Q, dsvcu_ctx *c, dsvcu_coefs *k, int plane, int q, const dsvcu_fmeta *fm, int l,
+                 const int part_start[5])
+{
+    const int w = k->w[plane], h = k->h[plane];
+    int s;
+    memset(Q, 0, sizeof(*Q));
+    Q->coefs = k->data[plane];
+    Q->fw = w;
+    Q->l = l;
+    Q->w = RSHIFT_UP(w, 3 - (l < 0 ? 0 : l));
+    Q->h = RSHIFT_UP(h, 3 - (l < 0 ? 0 : l));
+    Q->isP = fm->isP;
+    Q->luma = (plane == 0);
+    Q->lossless = fm->lossless;
+    Q->psy = (plane == 0) && (fm->do_psy & (fm->isP ? PSY_P_VISUAL_MASKING : PSY_I_VISUAL_MASKING));
+    Q->nbh = fm->nblocks_h;
+    Q->dbx = (fm->nblocks_h << 14) / Q->w;
+    Q->dby = (fm->nblocks_v << 14) / Q->h;
+    Q->blockdata = c->d_blockdata;
+    Q->mvs = c->d_mvs;
+    if (l < 0) return;
+    for (s = 1; s <= 3; s++) {
+        QuantBand *B = &Q->band[s - 1];
+        B->ox = (s & 1) ? Q->w : 0;
+        B->oy = (s & 2) ? Q->h : 0;
+        B->pox = (s & 1) ? RSHIFT_UP(w, 4 - l) : 0;
+        B->poy = (s & 2) ? RSHIFT_UP(h, 4 - l) : 0;
+        B->gox = (s & 1) ? RSHIFT_UP(w, 5 - l) : 0;
+        B->goy = (s & 2) ? RSHIFT_UP(h, 5 - l) : 0;
+        B->qp = fm->lossless ? 1 : hfquant(fm, plane, c->subsamp, q, s, l);
+        B->scan_base = part_start[1 + l] + (s - 1) * Q->w * Q->h;
+    }
+}
+
+extern "C" int
+dsvcu_quant_plane(dsvcu_ctx *c, dsvcu_coefs *k, int plane, int q, const dsvcu_fmeta *fm)
+{
+    const int w = k->w[plane], h = k->h[plane];
+    int part[5], total, l, nchunks;
+    QuantLevel Q;
+    int qf = q * 3 / 2; /* fix_quant, hzcc.c:59-63 */
+
+    total = dsvcu_scan_layout(w, h, part);
+    /* the DC coefficient is sent raw */
+    CK(dsvcu_d2d_async(c->d_meta + 3 + plane, k->data[plane], sizeof(int), c->stream));
+    quant_level_geom(&Q, c, k, plane, qf, fm, -1, part);
+    Q.qv = c->d_qv;
+    DSVCU_LAUNCH(k_quant_ll, grid_for(Q.w * Q.h, 256), 256, 0, c->stream, Q, fm->lossless ? 1 : lfquant(qf, plane, fm));
+    CK_LAUNCH(c);
+    for (l = 0; l < 3; l++) {
+        quant_level_geom(&Q, c, k, plane, qf, fm, l, part);
+        Q.qv = c->d_qv;
+        DSVCU_LAUNCH(k_quant_hf, dim3(grid_for(Q.w * Q.h, 256), 3, 1), 256, 0, c->stream, Q);
+        CK_LAUNCH(c);
+        if (!fm->lossless) {
+            DSVCU_LAUNCH(k_quant_hf_edge, dim3(grid_for(Q.w + Q.h, 256), 3, 1), 256, 0, c->stream, Q);
+            CK_LAUNCH(c);
+        }
+    }
+    nchunks = (total + CMP_CHUNK - 1) / CMP_CHUNK;
+    DSVCU_LAUNCH(k_compact_count, nchunks, CMP_THREADS, 0, c->stream, c->d_qv, total, c->d_chunk);
+    CK_LAUNCH(c);
+    DSVCU_LAUNCH(k_compact_scan, 1, 1024, 0, c->stream, c->d_chunk, nchunks, c->d_meta + plane);
+    CK_LAUNCH(c);
+    DSVCU_LAUNCH(k_compact_scatter, nchunks, CMP_THREADS, 0, c->stream, c->d_qv, total, c->d_chunk, c->d_syms[plane]);
+    CK_LAUNCH(c);
+    return 0;
+}
+
+extern "C" int
+dsvcu_fetch_symbols(dsvcu_ctx *c, int plane, const dsvcu_symbol **syms, int *nsyms, int *dc)
+{
+    int n;
+    CK(dsvcu_d2h_async(c->h_meta, c->d_meta, 6 * sizeof(int), c->stream));
+    CK(dsvcu_stream_sync(c->stream));
+    n = c->h_meta[plane];
+    if (n > 0) {
+        CK(dsvcu_d2h_async(c->h_syms[plane], c->d_syms[plane], (size_t) n * sizeof(dsvcu_sym), c->stream));
+        CK(dsvcu_stream_sync(c->stream));
+    }
+    *syms = (const dsvcu_symbol *) c->h_syms[plane];
+    *nsyms = n;
+    *dc = c->h_meta[3 + plane];
+    return 0;
+}
+
+extern "C" dsvcu_symbol *
+dsvcu_symbol_staging(dsvcu_ctx *c, int plane, int *capacity)
+{
+    if (capacity) *capacity = c->sym_cap[plane];
+    return (dsvcu_symbol *) c->h_syms[plane];
+}
+
+extern "C" int
+dsvcu_dequant_plane(dsvcu_ctx *c, dsvcu_coefs *k, int plane, int q, const dsvcu_fmeta *fm,
+                    int nsyms, const int level_start[5], int dc)
+{
+    const int w = k->w[plane], h = k->h[plane];
+    int part[5], l;
+    QuantLevel Q;
+    int qf = q * 3 / 2;
+
+    dsvcu_scan_layout(w, h, part);
+    CK(dsvcu_memset_async(k->data[plane], 0, (size_t) w * h * sizeof(int32_t), c->stream));
+    /* the raw DC rides behind the last symbol of the staging buffer */
+    c->h_syms[plane][nsyms].pos = 0;
+    c->h_syms[plane][nsyms].v = dc;
+    CK(dsvcu_h2d_async(c->d_syms[plane], c->h_syms[plane], (size_t) (nsyms + 1) * sizeof(dsvcu_sym), c->stream));
+    if (nsyms > 0) {
+        quant_level_geom(&Q, c, k, plane, qf, fm, -1, part);
+        Q.syms = c->d_syms[plane];
+        Q.sym_begin = level_start[0];
+        Q.sym_end = level_start[1];
+        if (Q.sym_end > Q.sym_begin) {
+            DSVCU_LAUNCH(k_dequant_ll, grid_for(Q.sym_end - Q.sym_begin, 256), 256, 0, c->stream, Q,
+                         fm->lossless ? 1 : lfquant(qf, plane, fm));
+            CK_LAUNCH(c);
+        }
+        for (l = 0; l < 3; l++) {
+            int wave;
+            quant_level_geom(&Q, c, k, plane, qf, fm, l, part);
+            Q.syms = c->d_syms[plane];
+            Q.sym_begin = level_start[1 + l];
+            Q.sym_end = level_start[2 + l];
+            if (Q.sym_end <= Q.sym_begin) continue;
+            for (wave = 0; wave < (fm->lossless ? 1 : 2); wave++) {
+                Q.wave = wave;
+                DSVCU_LAUNCH(k_dequant_hf, grid_for(Q.sym_end - Q.sym_begin, 256), 256, 0, c->stream, Q);
+                CK_LAUNCH(c);
+            }
+        }
+    }
+    /* dst->data[0] = LL (hzcc.c:634) */
+    CK(dsvcu_d2d_async(k->data[plane], &c->d_syms[plane][nsyms].v, sizeof(int), c->stream));
+    return 0;
+}
+
+/* ----------------------------------------------- motion compensation, filters */
+
+static void
+bmc_fill(BmcArgs *A, dsvcu_ctx *c, const dsvcu_fmeta *fm, dsvcu_frame *ref, dsvcu_frame *pred, dsvcu_frame *res,
+         dsvcu_frame *out, int mode)
+{
+    int i;
+    memset(A, 0, sizeof(*A));
+    for (i = 0; i < 3; i++) {
+        BmcPlane *P = &A->pl[i];
+        if (ref) {
+            P->ref = ref->p[i].data;
+            P->ref_stride = ref->p[i].stride;
+        }
+        if (pred) {
+            P->pred = pred->p[i].data;
+            P->pred_stride = pred->p[i].stride;
+        }
+        if (res) {
+            P->res = res->p[i].data;
+            P->res_stride = res->p[i].stride;
+            P->w = res->p[i].w;
+            P->h = res->p[i].h;
+        }
+        if (out) {
+            P->out = out->p[i].data;
+            P->out_stride = out->p[i].stride;
+        }
+        P->sh = i ? FMT_HSHIFT(c->subsamp) : 0;
+        P->sv = i ? FMT_VSHIFT(c->subsamp) : 0;
+    }
+    A->mvs = c->d_mvs;
+    A->nbh = fm->nblocks_h;
+    A->nbv = fm->nblocks_v;
+    A->blk_w = fm->blk_w;
+    A->blk_h = fm->blk_h;
+    A->tmc = fm->temporal_mc;
+    A->lossless = fm->lossless;
+    A->mode = mode;
+}
+
+static int
+filter_q(const dsvcu_fmeta *fm, int q) /* compute_filter_q, bmc.c:376-388 */
+{
+    int psyf = psy_factor(fm, -1);
+    if (q > 1536) q = 1536;
+    q += q * psyf >> (7 + 3);
+    if (q < 1024) q = 512 + q / 2;
+    return q;
+}
+
+static int
+run_wavefront(dsvcu_ctx *c, FiltArgs *F)
+{
+    int ctas;
+    if (F->nrows <= 0 || F->ncols <= 0) return 0;
+    if (F->nrows > c->progress_cap) {
+        dsvcu_free_dev(c->d_progress);
+        c->progress_cap = F->nrows + 64;
+        CK(dsvcu_malloc(&c->d_progress, (size_t) c->progress_cap * sizeof(int)));
+    }
+    CK(dsvcu_memset_async(c->d_progress, 0, (size_t) F->nrows * sizeof(int), c->stream));
+    F->progress = c->d_progress;
+#ifdef DSVCU_EMU
+    ctas = 1;
+#else
+    ctas = (F->nrows + FILT_WARPS_PER_CTA - 1) / FILT_WARPS_PER_CTA;
+    if (ctas > 148 * 4) ctas = 148 * 4; /* all CTAs must be co-resident */
+#endif
+    DSVCU_LAUNCH(k_filter_wavefront, ctas, FILT_WARPS_PER_CTA * 32, 0, c->stream, *F);
+    CK_LAUNCH(c);
+    return 0;
+}
+
+static int
+loop_filters(dsvcu_ctx *c, const dsvcu_fmeta *fm, int q, dsvcu_frame *f, int do_filter)
+{
+    /* luma_filter + chroma_filter, bmc.c:459-659 */
+    FiltArgs F;
+    int i;
+    if (fm->lossless) return 0;
+    memset(&F, 0, sizeof(F));
+    F.mvs = c->d_mvs;
+    F.blockdata = c->d_blockdata;
+    F.nbh = fm->nblocks_h;
+    F.nbv = fm->nblocks_v;
+    F.blk_w = fm->blk_w;
+    F.blk_h = fm->blk_h;
+    F.data = f->p[0].data;
+    F.stride = f->p[0].stride;
+    F.w = f->p[0].w;
+    F.h = f->p[0].h;
+    F.q = filter_q(fm, q);
+    F.fthresh = 32 * (14 - ilb2((unsigned) F.q));
+    F.do_filter = do_filter;
+    F.sharpen = fm->inter_sharpen ? fm->temporal_mc : 0;
+    F.ncols = F.w / 4;
+    F.nrows = F.h / 4;
+    F.mode = FILT_MODE_LUMA;
+    if (run_wavefront(c, &F)) return -1;
+    for (i = 1; i < 3; i++) {
+        F.data = f->p[i].data;
+        F.stride = f->p[i].stride;
+        F.w = f->p[i].w;
+        F.h = f->p[i].h;
+        F.q = q;
+        F.bw = fm->blk_w >> FMT_HSHIFT(c->subsamp);
+        F.bh = fm->blk_h >> FMT_VSHIFT(c->subsamp);
+        F.ncols = fm->nblocks_h;
+        F.nrows = fm->nblocks_v;
+        F.mode = FILT_MODE_CHROMA;
+        if (run_wavefront(c, &F)) return -1;
+    }
+    return 0;
+}
+
+extern "C" int
+dsvcu_sub_pred(dsvcu_ctx *c, const dsvcu_fmeta *fm, dsvcu_frame *pred, dsvcu_frame *resd, dsvcu_frame *ref)
+{
+    BmcArgs A;
+    bmc_fill(&A, c, fm, ref, pred, resd, NULL, 0);
+    DSVCU_LAUNCH(k_predict, dim3(fm->nblocks_h * fm->nblocks_v, 3, 1), BMC_THREADS, 0, c->stream, A);
+    CK_LAUNCH(c);
+    return 0;
+}
+
+extern "C" int
+dsvcu_add_pred(dsvcu_ctx *c, const dsvcu_fmeta *fm, int q, dsvcu_frame *resd, dsvcu_frame *out, dsvcu_frame *ref,
+               int do_filter)
+{
+    BmcArgs A;
+    bmc_fill(&A, c, fm, ref, NULL, resd, out, 1);
+    DSVCU_LAUNCH(k_predict, dim3(fm->nblocks_h * fm->nblocks_v, 3, 1), BMC_THREADS, 0, c->stream, A);
+    CK_LAUNCH(c);
+    return loop_filters(c, fm, q, out, do_filter);
+}
+
+extern "C" int
+dsvcu_add_res(dsvcu_ctx *c, const dsvcu_fmeta *fm, int q, dsvcu_frame *resd, dsvcu_frame *pred, int do_filter)
+{
+    BmcArgs A;
+    bmc_fill(&A, c, fm, NULL, pred, resd, NULL, 0);
+    DSVCU_LAUNCH(k_reconstruct, dim3(fm->nblocks_h * fm->nblocks_v, 3, 1), BMC_THREADS, 0, c->stream, A);
+    CK_LAUNCH(c);
+    return loop_filters(c, fm, q, resd, do_filter);
+}
+
+extern "C" int
+dsvcu_intra_filter(dsvcu_ctx *c, int q, const dsvcu_fmeta *fm, int plane, dsvcu_frame *f, int do_filter)
+{
+    FiltArgs F;
+    if (fm->lossless || plane != 0 || !do_filter) return 0;
+    memset(&F, 0, sizeof(F));
+    F.mvs = c->d_mvs;
+    F.blockdata = c->d_blockdata;
+    F.nbh = fm->nblocks_h;
+    F.nbv = fm->nblocks_v;
+    F.blk_w = fm->blk_w;
+    F.blk_h = fm->blk_h;
+    F.data = f->p[0].data;
+    F.stride = f->p[0].stride;
+    F.w = f->p[0].w;
+    F.h = f->p[0].h;
+    F.q = filter_q(fm, q);
+    F.fthresh = 32 * (14 - ilb2((unsigned) F.q));
+    F.do_filter = 1;
+    F.ncols = F.w / 4;
+    F.nrows = F.h / 4;
+    F.mode = FILT_MODE_INTRA;
+    return run_wavefront(c, &F);
+}
+
+extern "C" int
+dsvcu_post_process(dsvcu_ctx *c, dsvcu_frame *f)
+{
+    dsvcu_plane_t *p = &f->p[0];
+    DSVCU_LAUNCH(k_post_sharpen, grid_for((p->w / 4) * (p->h / 4), 256), 256, 0, c->stream, p->data, p->stride, p->w,
+                 p->h);
+    CK_LAUNCH(c);
+    return 0;
+}
+
+/* ------------------------------------------------------------ frame helpers */
+
+extern "C" int
+dsvcu_extend_frame(dsvcu_ctx *c, dsvcu_frame *f, int luma_only)
+{
+    ExtArgs A;
+    int i, n = luma_only ? 1 : f->nplanes, maxitems = 0;
+    memset(&A, 0, sizeof(A));
+    for (i = 0; i < n; i++) {
+        int items = f->p[i].h + (f->p[i].w + 3) / 4 + 4;
+        A.pl[i].data = f->p[i].data;
+        A.pl[i].stride = f->p[i].stride;
+        A.pl[i].w = f->p[i].w;
+        A.pl[i].h = f->p[i].h;
+        if (items > maxitems) maxitems = items;
+    }
+    DSVCU_LAUNCH(k_extend, dim3(grid_for(maxitems, 64), n, 1), 64, 0, c->stream, A);
+    CK_LAUNCH(c);
+    return 0;
+}
+
+extern "C" int
+dsvcu_ds2x_luma(dsvcu_ctx *c, dsvcu_frame *dst, dsvcu_frame *src)
+{
+    dsvcu_plane_t *d = &dst->p[0], *s = &src->p[0];
+    DSVCU_LAUNCH(k_ds2x, grid_for(d->w * d->h, 256), 256, 0, c->stream, d->data, d->stride, d->w, d->h, s->data,
+                 s->stride);
+    CK_LAUNCH(c);
+    return 0;
+}
+
+extern "C" int
+dsvcu_frame_copy(dsvcu_ctx *c, dsvcu_frame *dst, dsvcu_frame *src)
+{
+    int i;
+    for (i = 0; i < dst->nplanes; i++) {
+        CK(dsvcu_d2d_2d_async(dst->p[i].data, dst->p[i].stride, src->p[i].data, src->p[i].stride, src->p[i].w,
+                              dst->p[i].h, c->stream));
+    }
+    return dsvcu_extend_frame(c, dst, 0);
+}

@@ -1,0 +1,265 @@
+/*
+ * k_bmc.cuh -- block motion compensation, residual subtract / reconstruct.
+ *
+ * Replaces reference src/bmc.c: predict (:814-923), luma_qp (:661-769),
+ * bilinear_sp (:772-812), avgval/cpyblk (:25-49), subtract (:989-1055) and
+ * reconstruct (:925-987).
+ *
+ * One CTA per (motion block, plane).  The reference-window (+3 px for the
+ * 4-tap luma filter) is staged once in shared memory, the separable filter
+ * runs out of shared memory, and the residual arithmetic is fused into the
+ * same launch: the encoder variant writes prediction + residual (dsv_sub_pred,
+ * bmc.c:1057-1070); the decoder variant writes the reconstructed pixel
+ * directly (predict + reconstruct of dsv_add_pred, bmc.c:1093-1111) so the
+ * prediction never round-trips through HBM.
+ */
+#ifndef K_BMC_CUH
+#define K_BMC_CUH
+
+#include "dsvcu_rt.h"
+#include "k_quant.cuh" /* dsvcu_mv + flag bits */
+
+#define BMC_BORDER 32
+#define BMC_MAXB 32
+#define BMC_THREADS 128
+
+struct BmcPlane {
+    const uint8_t *ref; /* pixel (0,0) of the extended reference plane */
+    int ref_stride;
+    uint8_t *pred;      /* encoder: prediction plane (written); decoder: unused */
+    int pred_stride;
+    uint8_t *res;       /* residual plane: encoder in/out; decoder input */
+    int res_stride;
+    uint8_t *out;       /* decoder: reconstructed output plane */
+    int out_stride;
+    int w, h;           /* plane size */
+    int sh, sv;         /* chroma shifts (0 for luma) */
+};
+
+struct BmcArgs {
+    BmcPlane pl[3];
+    const dsvcu_mv *mvs;
+    int nbh, nbv;
+    int blk_w, blk_h;
+    int tmc;      /* temporal MC flag (fnum % 2) */
+    int lossless;
+    int mode;     /* 0 = encoder sub_pred, 1 = decoder add_pred */
+};
+
+DSVCU_HD int bmc_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+DSVCU_HD int bmc_u8(int v) { return v > 255 ? 255 : (v < 0 ? 0 : v); }
+DSVCU_HD int bmc_sar(int v, int s) { return v >> s; }
+
+#define HPF_A(a, b, c, d) ((19 * ((b) + (c))) - (3 * ((a) + (d))))
+#define HPF_B(a, b, c, d) ((20 * ((b) + (c))) - (4 * ((a) + (d))))
+
+DSVCU_HD int
+bmc_blend(int f, int b, int c, int frac) /* bmc.c:701-714, BF_SHIFT 6, BF_MULADD 32 */
+{
+    switch (frac) {
+        case 0: return (32 * 2 * b + 32) >> 6;
+        case 1: return (f + 32 * b + 32) >> 6;
+        case 2: return (f * 2 + 32) >> 6;
+        default: return (f + 32 * c + 32) >> 6;
+    }
+}
+
+DSVCU_KERNEL void __launch_bounds__(BMC_THREADS)
+k_predict(BmcArgs A)
+{
+    DSVCU_SHARED uint8_t win[(BMC_MAXB + 3) * (BMC_MAXB + 4)];
+    DSVCU_SHARED int16_t tmp[(BMC_MAXB + 3) * BMC_MAXB];
+    DSVCU_SHARED uint8_t prd[BMC_MAXB * BMC_MAXB];
+    DSVCU_SHARED int sums[4];
+
+    const int c = (int) blockIdx.y;
+    const BmcPlane P = A.pl[c];
+    const int bi = (int) blockIdx.x % A.nbh, bj = (int) blockIdx.x / A.nbh;
+    const dsvcu_mv mv = A.mvs[bi + bj * A.nbh];
+    const int bw = A.blk_w >> P.sh, bh = A.blk_h >> P.sv;
+    const int x = bi * bw, y = bj * bh;
+    const int limx = (P.w - bw) + BMC_BORDER - 1;
+    const int limy = (P.h - bh) + BMC_BORDER - 1;
+    const int WS = BMC_MAXB + 4; /* window row pitch */
+    int px = x + bmc_sar(mv.x, 2 + P.sh);
+    int py = y + bmc_sar(mv.y, 2 + P.sv);
+    const int intra = mv.flags & MVF_INTRA;
+
+    if (intra) {
+        /* D.2: DC fill of the whole block or of masked quadrants */
+        px = bmc_clampi(px, -BMC_BORDER, limx);
+        py = bmc_clampi(py, -BMC_BORDER, limy);
+        PAR_FOR(k, bw * bh) {
+            int r = k / bw, q = k - r * bw;
+            win[r * WS + q] = P.ref[(py + r) * P.ref_stride + px + q];
+        }
+        PAR_FOR(k, 4) { sums[k] = 0; }
+        DSVCU_SYNC();
+        const int whole = (mv.submask == 15);
+        const int sbw = bw / 2, sbh = bh / 2;
+        const int use_dc = (c == 0 && mv.dc);
+        if (!use_dc) {
+            /* per-quadrant (or whole-block) sums; integer sums are order-free */
+            int part[4] = { 0, 0, 0, 0 };
+            PAR_FOR(k, bw * bh) {
+                int r = k / bw, q = k - r * bw;
+                int qi = whole ? 0 : ((r >= sbh) * 2 + (q >= sbw));
+                part[qi] += win[r * WS + q];
+            }
+            for (int i = 0; i < 4; i++) {
+                if (part[i]) atomicAdd(&sums[i], part[i]);
+            }
+        }
+        DSVCU_SYNC();
+        PAR_FOR(k, bw * bh) {
+            int r = k / bw, q = k - r * bw;
+            int qi = (r >= sbh) * 2 + (q >= sbw);
+            int v;
+            if (whole) {
+                v = use_dc ? mv.dc : sums[0] / (bw * bh);
+            } else if (mv.submask & (1 << qi)) {
+                v = use_dc ? mv.dc : sums[qi] / (sbw * sbh);
+            } else {
+                v = win[r * WS + q];
+            }
+            prd[r * BMC_MAXB + q] = (uint8_t) v; /* memset semantics: low 8 bits */
+        }
+    } else if (c == 0) {
+        if (!((mv.x | mv.y) & 3)) {
+            px = bmc_clampi(px, -BMC_BORDER, limx);
+            py = bmc_clampi(py, -BMC_BORDER, limy);
+            PAR_FOR(k, bw * bh) {
+                int r = k / bw, q = k - r * bw;
+                prd[r * BMC_MAXB + q] = P.ref[(py + r) * P.ref_stride + px + q];
+            }
+        } else {
+            /* D.1 separable 4-tap, two sharpnesses (bmc.c:661-769) */
+            px = bmc_clampi(px - 1, -BMC_BORDER, limx);
+            py = bmc_clampi(py - 1, -BMC_BORDER, limy);
+            int adx = mv.x < 0 ? -mv.x : mv.x, ady = mv.y < 0 ? -mv.y : mv.y;
+            int large = adx >= 8 || ady >= 8;
+            int dx = mv.x & 3, dy = mv.y & 3;
+            int dqtx = large || !(dx & 1) || (A.tmc & 1);
+            int dqty = large || !(dy & 1) || (A.tmc & 1);
+            PAR_FOR(k, (bh + 3) * (bw + 3)) {
+                int r = k / (bw + 3), q = k - r * (bw + 3);
+                win[r * WS + q] = P.ref[(py + r) * P.ref_stride + px + q];
+            }
+            DSVCU_SYNC();
+            PAR_FOR(k, (bh + 3) * bw) {
+                int r = k / bw, q = k - r * bw;
+                const uint8_t *s = win + r * WS + q;
+                int a = s[0], b = s[1], cc = s[2], d = s[3];
+                int f = dqtx ? HPF_A(a, b, cc, d) : HPF_B(a, b, cc, d);
+                tmp[r * BMC_MAXB + q] = (int16_t) bmc_blend(f, b, cc, dx);
+            }
+            DSVCU_SYNC();
+            PAR_FOR(k, bh * bw) {
+                int r = k / bw, q = k - r * bw;
+                const int16_t *s = tmp + r * BMC_MAXB + q;
+                int a = s[0], b = s[BMC_MAXB], cc = s[2 * BMC_MAXB], d = s[3 * BMC_MAXB];
+                int f = dqty ? HPF_A(a, b, cc, d) : HPF_B(a, b, cc, d);
+                prd[r * BMC_MAXB + q] = (uint8_t) bmc_u8(bmc_blend(f, b, cc, dy));
+            }
+        }
+    } else {
+        /* chroma bilinear at 1/(4<<shift) pel (bmc.c:772-812) */
+        px = bmc_clampi(px, -BMC_BORDER, limx);
+        py = bmc_clampi(py, -BMC_BORDER, limy);
+        int hbits = 2 + P.sh, vbits = 2 + P.sv;
+        int hf = 1 << hbits, vf = 1 << vbits;
+        int dx = mv.x & (hf - 1), dy = mv.y & (vf - 1);
+        if (dx | dy) {
+            int f0 = (hf - dx) * (vf - dy), f1 = dx * (vf - dy);
+            int f2 = (hf - dx) * dy, f3 = dx * dy;
+            int sf = hbits + vbits, af = 1 << (sf - 1);
+            PAR_FOR(k, (bh + 1) * (bw + 1)) {
+                int r = k / (bw + 1), q = k - r * (bw + 1);
+                win[r * WS + q] = P.ref[(py + r) * P.ref_stride + px + q];
+            }
+            DSVCU_SYNC();
+            PAR_FOR(k, bh * bw) {
+                int r = k / bw, q = k - r * bw;
+                const uint8_t *s = win + r * WS + q;
+                prd[r * BMC_MAXB + q] =
+                    (uint8_t) ((f0 * s[0] + f1 * s[1] + f2 * s[WS] + f3 * s[WS + 1] + af) >> sf);
+            }
+        } else {
+            PAR_FOR(k, bw * bh) {
+                int r = k / bw, q = k - r * bw;
+                prd[r * BMC_MAXB + q] = P.ref[(py + r) * P.ref_stride + px + q];
+            }
+        }
+    }
+    DSVCU_SYNC();
+
+    const int skip = mv.flags & MVF_SKIP, eprm = mv.flags & MVF_EPRM;
+    if (A.mode == 0) {
+        /* encoder: store prediction, residual = source - prediction (bmc.c:989-1055) */
+        const int noxmit = !intra && (skip || (c == 0 && (mv.flags & MVF_NOXMITY)) ||
+                                      (c != 0 && (mv.flags & MVF_NOXMITC)));
+        PAR_FOR(k, bw * bh) {
+            int r = k / bw, q = k - r * bw;
+            int p = prd[r * BMC_MAXB + q];
+            uint8_t *rp = P.res + (y + r) * P.res_stride + x + q;
+            int s = *rp, o;
+            P.pred[(y + r) * P.pred_stride + x + q] = (uint8_t) p;
+            if (A.lossless) {
+                o = (s - p + 128) & 0xff;
+            } else if (noxmit) {
+                o = 128;
+            } else if (eprm) {
+                o = bmc_u8((s - p + 256) >> 1);
+            } else {
+                o = bmc_u8(s - p + 128);
+            }
+            *rp = (uint8_t) o;
+        }
+    } else {
+        /* decoder: out = prediction + residual (bmc.c:925-987) */
+        const int plain = !eprm || (!intra && skip);
+        PAR_FOR(k, bw * bh) {
+            int r = k / bw, q = k - r * bw;
+            int p = prd[r * BMC_MAXB + q];
+            int s = P.res[(y + r) * P.res_stride + x + q], o;
+            if (A.lossless) {
+                o = (p + s - 128) & 0xff;
+            } else if (plain) {
+                o = bmc_u8(p + s - 128);
+            } else {
+                o = bmc_u8(p + (s - 128) * 2);
+            }
+            P.out[(y + r) * P.out_stride + x + q] = (uint8_t) o;
+        }
+    }
+}
+
+/* encoder-side reconstruct: res = pred (+) res, in place (dsv_add_res, bmc.c:1072-1090) */
+DSVCU_KERNEL void __launch_bounds__(BMC_THREADS)
+k_reconstruct(BmcArgs A)
+{
+    const int c = (int) blockIdx.y;
+    const BmcPlane P = A.pl[c];
+    const int bi = (int) blockIdx.x % A.nbh, bj = (int) blockIdx.x / A.nbh;
+    const dsvcu_mv mv = A.mvs[bi + bj * A.nbh];
+    const int bw = A.blk_w >> P.sh, bh = A.blk_h >> P.sv;
+    const int x = bi * bw, y = bj * bh;
+    const int intra = mv.flags & MVF_INTRA, skip = mv.flags & MVF_SKIP, eprm = mv.flags & MVF_EPRM;
+    const int plain = !eprm || (!intra && skip);
+    PAR_FOR(k, bw * bh) {
+        int r = k / bw, q = k - r * bw;
+        int p = P.pred[(y + r) * P.pred_stride + x + q];
+        uint8_t *rp = P.res + (y + r) * P.res_stride + x + q;
+        int s = *rp, o;
+        if (A.lossless) {
+            o = (p + s - 128) & 0xff;
+        } else if (plain) {
+            o = bmc_u8(p + s - 128);
+        } else {
+            o = bmc_u8(p + (s - 128) * 2);
+        }
+        *rp = (uint8_t) o;
+    }
+}
+
+#endif /* K_BMC_CUH */

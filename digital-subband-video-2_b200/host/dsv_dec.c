@@ -1,0 +1,447 @@
+/*
+ * dsv_dec.c -- decoder control: packet / picture header parsing, block side
+ * information (stability, intra meta, motion) and the per-picture GPU
+ * schedule.
+ *
+ * Bitstream syntax follows the reference decoder (src/dsv_decoder.c:21-238,
+ * :393-590; spec B.1-B.2.3).  What differs is where pixels live: coefficient
+ * planes, the residual, the output picture and the reference picture are
+ * device-resident (dsv_cuda.h).  Per picture the host parses bits into small
+ * arrays (blockdata, motion vectors, ordered coefficient symbols), uploads
+ * them, queues dequant -> inverse SBT -> (intra filter | predict + reconstruct
+ * + loop filters) -> border extension on one stream, and copies the finished
+ * picture back once.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "dsv_host.h"
+#include "../../include/dsv_decoder.h"
+
+typedef struct {
+    DSV_IMAGE img; /* first member: DSV_DECODER.ref points at this object */
+    dsvcu_ctx *ctx;
+    dsvcu_coefs *coefs;
+    dsvcu_frame *resd;
+    dsvcu_frame *pic[2]; /* output / reference, swapped after every reference picture */
+    int cur;
+    int have_ref;
+    int w, h, subsamp;
+    uint8_t *blockdata;
+    DSV_MV *mvs;
+    int nblk_cap;
+} DEC_STATE;
+
+static int
+env_device(void)
+{
+    const char *e = getenv("DSV_CUDA_DEVICE");
+    return e ? atoi(e) : 0;
+}
+
+static void
+state_free(DEC_STATE *s)
+{
+    if (!s) {
+        return;
+    }
+    if (s->ctx) {
+        dsvcu_sync(s->ctx);
+        if (s->coefs) dsvcu_coefs_destroy(s->ctx, s->coefs);
+        if (s->resd) dsvcu_frame_destroy(s->ctx, s->resd);
+        if (s->pic[0]) dsvcu_frame_destroy(s->ctx, s->pic[0]);
+        if (s->pic[1]) dsvcu_frame_destroy(s->ctx, s->pic[1]);
+        dsvcu_ctx_destroy(s->ctx);
+    }
+    free(s->blockdata);
+    free(s->mvs);
+    free(s);
+}
+
+static DEC_STATE *
+state_get(DSV_DECODER *d)
+{
+    DEC_STATE *s = (DEC_STATE *) d->ref;
+    DSV_META *m = &d->vidmeta;
+    if (s && (s->w != m->width || s->h != m->height || s->subsamp != m->subsamp)) {
+        state_free(s);
+        s = NULL;
+        d->ref = NULL;
+    }
+    if (s) {
+        return s;
+    }
+    s = calloc(1, sizeof(*s));
+    if (!s) {
+        return NULL;
+    }
+    s->img.refcount = 1;
+    s->w = m->width;
+    s->h = m->height;
+    s->subsamp = m->subsamp;
+    if (dsvcu_ctx_create(&s->ctx, env_device(), m->width, m->height, m->subsamp) ||
+        dsvcu_coefs_create(s->ctx, &s->coefs) || dsvcu_frame_create(s->ctx, &s->resd) ||
+        dsvcu_frame_create(s->ctx, &s->pic[0]) || dsvcu_frame_create(s->ctx, &s->pic[1])) {
+        DSV_ERROR(("GPU decoder state: %s", dsvcu_last_error()));
+        state_free(s);
+        return NULL;
+    }
+    d->ref = &s->img;
+    return s;
+}
+
+/* B.1 packet header; returns the packet type or -1 */
+static int
+read_packet_hdr(DSV_BITRD *br)
+{
+    int c0 = (int) dsv_br_bits(br, 8), c1 = (int) dsv_br_bits(br, 8);
+    int c2 = (int) dsv_br_bits(br, 8), c3 = (int) dsv_br_bits(br, 8);
+    int type;
+    if (c0 != DSV_FOURCC_0 || c1 != DSV_FOURCC_1 || c2 != DSV_FOURCC_2 || c3 != DSV_FOURCC_3) {
+        DSV_ERROR(("bad 4cc (%c %c %c %c)\n", c0, c1, c2, c3));
+        return -1;
+    }
+    (void) dsv_br_bits(br, 8); /* minor version */
+    type = (int) dsv_br_bits(br, 8);
+    (void) dsv_br_bits(br, 32); /* prev link */
+    (void) dsv_br_bits(br, 32); /* next link */
+    return type;
+}
+
+/* B.2.1 metadata packet */
+static void
+read_meta(DSV_DECODER *d, DSV_BITRD *br)
+{
+    DSV_META *m = &d->vidmeta;
+    m->width = (int) dsv_br_ueg(br);
+    m->height = (int) dsv_br_ueg(br);
+    m->subsamp = (int) dsv_br_ueg(br);
+    m->fps_num = (int) dsv_br_ueg(br);
+    m->fps_den = (int) dsv_br_ueg(br);
+    m->aspect_num = (int) dsv_br_ueg(br);
+    m->aspect_den = (int) dsv_br_ueg(br);
+    m->inter_sharpen = (int) dsv_br_ueg(br);
+    m->reserved = dsv_br_bit(br) ? (int) dsv_br_bits(br, 15) : 0;
+}
+
+/* a length-prefixed, byte-aligned sub-stream inside the picture payload */
+static void
+open_substream(DSV_BITRD *in, const uint8_t **start, size_t *len)
+{
+    size_t n = dsv_br_ueg(in);
+    dsv_br_align(in);
+    *start = in->buf + dsv_br_byte(in);
+    *len = (dsv_br_byte(in) + n <= in->len) ? n : (in->len > dsv_br_byte(in) ? in->len - dsv_br_byte(in) : 0);
+    in->pos += n * 8;
+}
+
+/* B.2.3.1 stability (I) / skip (P) bits */
+static void
+read_stability(DSV_BITRD *in, uint8_t *blockdata, int nblk, int isP, const int *stats)
+{
+    DSV_RLERD rle;
+    const uint8_t *p;
+    size_t len;
+    int i, shift = isP ? DSV_SKIP_BIT : DSV_STABLE_BIT;
+
+    dsv_br_align(in);
+    open_substream(in, &p, &len);
+    dsv_rle_rd_init(&rle, p, len + 8);
+    for (i = 0; i < nblk; i++) {
+        int bit = dsv_rle_rd_get(&rle);
+        if (stats[DSV_STABLE_STAT] == DSV_ZERO_MARKER) {
+            bit = !bit;
+        }
+        blockdata[i] = (uint8_t) (bit << shift);
+    }
+    dsv_rle_rd_end(&rle);
+}
+
+/* B.2.3.2 ringing + B.2.3.3 maintain bits of an intra picture */
+static void
+read_intra_meta(DSV_BITRD *in, uint8_t *blockdata, int nblk, const int *stats)
+{
+    DSV_RLERD rr, rm;
+    const uint8_t *p;
+    size_t len;
+    int i;
+
+    dsv_br_align(in);
+    open_substream(in, &p, &len);
+    dsv_rle_rd_init(&rr, p, len + 8);
+    dsv_br_align(in);
+    open_substream(in, &p, &len);
+    dsv_rle_rd_init(&rm, p, len + 8);
+    for (i = 0; i < nblk; i++) {
+        int br = dsv_rle_rd_get(&rr), bm = dsv_rle_rd_get(&rm);
+        if (stats[DSV_RINGING_STAT] == DSV_ZERO_MARKER) {
+            br = !br;
+        }
+        if (stats[DSV_MAINTAIN_STAT] == DSV_ZERO_MARKER) {
+            bm = !bm;
+        }
+        blockdata[i] |= (uint8_t) ((bm << DSV_MAINTAIN_BIT) | (br << DSV_RINGING_BIT));
+    }
+    dsv_rle_rd_end(&rr);
+    dsv_rle_rd_end(&rm);
+}
+
+/* B.2.3.4 motion data: five sub-streams, vectors coded against the
+ * left/top/top-left predictor */
+static void
+read_motion(DSV_BITRD *in, DSV_PARAMS *prm, uint8_t *blockdata, DSV_MV *mvs, const int *stats)
+{
+    DSV_BITRD sub[DSV_SUB_NSUB];
+    DSV_RLERD mode_rle, eprm_rle;
+    int i, j;
+
+    dsv_br_align(in);
+    for (i = 0; i < DSV_SUB_NSUB; i++) {
+        const uint8_t *p;
+        size_t len;
+        open_substream(in, &p, &len);
+        if (i == DSV_SUB_MODE) {
+            dsv_rle_rd_init(&mode_rle, p, len + 8);
+        } else if (i == DSV_SUB_EPRM) {
+            dsv_rle_rd_init(&eprm_rle, p, len + 8);
+        } else {
+            dsv_br_init(&sub[i], p, len + 8);
+        }
+    }
+    for (j = 0; j < prm->nblocks_v; j++) {
+        for (i = 0; i < prm->nblocks_h; i++) {
+            int idx = i + j * prm->nblocks_h;
+            DSV_MV *mv = &mvs[idx];
+            int mode, eprm, px, py;
+
+            if (blockdata[idx] & DSV_IS_SKIP) {
+                DSV_MV_SET_SKIP(mv, 1);
+                mv->u.all = 0;
+                blockdata[idx] |= DSV_IS_STABLE;
+                continue;
+            }
+            DSV_MV_SET_SKIP(mv, 0);
+            mode = dsv_rle_rd_get(&mode_rle);
+            eprm = dsv_rle_rd_get(&eprm_rle);
+            if (stats[DSV_MODE_STAT] == DSV_ZERO_MARKER) {
+                mode = !mode;
+            }
+            if (stats[DSV_EPRM_STAT] == DSV_ZERO_MARKER) {
+                eprm = !eprm;
+            }
+            DSV_MV_SET_INTRA(mv, mode);
+            DSV_MV_SET_EPRM(mv, eprm);
+            blockdata[idx] &= (uint8_t) ~DSV_IS_STABLE;
+            blockdata[idx] |= (uint8_t) (eprm << DSV_EPRM_BIT);
+
+            dsv_movec_pred(mvs, prm, i, j, &px, &py);
+            if (mode) {
+                px = DSV_SAR_R(px, 2);
+                py = DSV_SAR_R(py, 2);
+            }
+            mv->u.mv.x = (int16_t) (dsv_br_seg(&sub[DSV_SUB_MV_X]) + px);
+            mv->u.mv.y = (int16_t) (dsv_br_seg(&sub[DSV_SUB_MV_Y]) + py);
+            if (mode) {
+                DSV_BITRD *sb = &sub[DSV_SUB_SBIM];
+                mv->u.mv.x *= 4; /* intra vectors are full-pel */
+                mv->u.mv.y *= 4;
+                mv->submask = dsv_br_bit(sb) ? DSV_MASK_ALL_INTRA : (uint8_t) dsv_br_bits(sb, 4);
+                mv->dc = dsv_br_bit(sb) ? (uint16_t) (dsv_br_bits(sb, 8) | DSV_SRC_DC_PRED) : 0;
+                blockdata[idx] |= DSV_IS_INTRA;
+            }
+            if (dsv_neighbordif(mvs, prm, i, j) > DSV_NDIF_THRESH) {
+                blockdata[idx] |= DSV_IS_STABLE;
+            }
+        }
+    }
+    dsv_rle_rd_end(&mode_rle);
+    dsv_rle_rd_end(&eprm_rle);
+}
+
+void
+dsv_dec_free(DSV_DECODER *d)
+{
+    if (d->ref) {
+        state_free((DEC_STATE *) d->ref);
+        d->ref = NULL;
+    }
+}
+
+DSV_META *
+dsv_get_metadata(DSV_DECODER *d)
+{
+    DSV_META *m = dsv_alloc(sizeof(DSV_META));
+    memcpy(m, &d->vidmeta, sizeof(DSV_META));
+    return m;
+}
+
+#define GPU(call)                                              \
+    do {                                                       \
+        if (call) {                                            \
+            DSV_ERROR(("%s: %s", #call, dsvcu_last_error())); \
+            return DSV_DEC_ERROR;                              \
+        }                                                      \
+    } while (0)
+
+static int
+decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FRAME **out, DSV_FNUM *fn)
+{
+    DSV_META *meta = &d->vidmeta;
+    DSV_PARAMS *p = &s->img.params;
+    dsvcu_fmeta fm;
+    dsvcu_frame *dst, *ref;
+    DSV_FRAME *host;
+    DSV_FNUM fno;
+    int stats[DSV_MAX_STAT];
+    int i, nblk, quant, is_ref, do_filter, isP;
+
+    memset(p, 0, sizeof(*p));
+    p->vidmeta = meta;
+    p->has_ref = DSV_PT_HAS_REF(pkt_type);
+    isP = p->has_ref;
+    is_ref = DSV_PT_IS_REF(pkt_type);
+
+    dsv_br_align(br);
+    fno = dsv_br_bits(br, 32);
+    dsv_br_align(br);
+    p->blk_w = 16 << dsv_br_ueg(br);
+    p->blk_h = 16 << dsv_br_ueg(br);
+    if (p->blk_w < DSV_MIN_BLOCK_SIZE || p->blk_h < DSV_MIN_BLOCK_SIZE || p->blk_w > DSV_MAX_BLOCK_SIZE ||
+        p->blk_h > DSV_MAX_BLOCK_SIZE) {
+        return DSV_DEC_ERROR;
+    }
+    p->nblocks_h = DSV_UDIV_ROUND_UP(meta->width, p->blk_w);
+    p->nblocks_v = DSV_UDIV_ROUND_UP(meta->height, p->blk_h);
+    nblk = p->nblocks_h * p->nblocks_v;
+
+    dsv_br_align(br);
+    for (i = 0; i < DSV_MAX_STAT; i++) {
+        stats[i] = DSV_ONE_MARKER;
+    }
+    stats[DSV_STABLE_STAT] = (int) dsv_br_bit(br);
+    if (!isP) {
+        stats[DSV_MAINTAIN_STAT] = (int) dsv_br_bit(br);
+        stats[DSV_RINGING_STAT] = (int) dsv_br_bit(br);
+    } else {
+        stats[DSV_MODE_STAT] = (int) dsv_br_bit(br);
+        stats[DSV_EPRM_STAT] = (int) dsv_br_bit(br);
+    }
+    do_filter = (int) dsv_br_bit(br);
+    quant = (int) dsv_br_bits(br, DSV_MAX_QP_BITS);
+    p->lossless = (quant == 1);
+    p->reserved = dsv_br_bit(br) ? (int) dsv_br_bits(br, 15) : 0;
+    dsv_br_align(br);
+
+    if (nblk > s->nblk_cap) {
+        free(s->blockdata);
+        free(s->mvs);
+        s->blockdata = malloc((size_t) nblk);
+        s->mvs = malloc((size_t) nblk * sizeof(DSV_MV));
+        s->nblk_cap = nblk;
+    }
+    memset(s->blockdata, 0, (size_t) nblk);
+    memset(s->mvs, 0, (size_t) nblk * sizeof(DSV_MV));
+    read_stability(br, s->blockdata, nblk, isP, stats);
+    if (isP) {
+        read_motion(br, p, s->blockdata, s->mvs, stats);
+    } else {
+        read_intra_meta(br, s->blockdata, nblk, stats);
+    }
+    dsv_br_align(br);
+
+    p->temporal_mc = isP ? (int) DSV_TEMPORAL_MC(fno) : 0;
+    dsv_fmeta_from_params(&fm, p, isP, fno);
+    GPU(dsvcu_set_blockdata(s->ctx, s->blockdata, nblk));
+    if (isP) {
+        GPU(dsvcu_set_mvs(s->ctx, s->mvs, nblk));
+    }
+
+    /* intra pictures are reconstructed straight into the output picture;
+     * inter pictures into the residual frame, then predicted + added */
+    dst = s->pic[s->cur];
+    ref = s->pic[s->cur ^ 1];
+    for (i = 0; i < 3; i++) {
+        int cap, nsym, lstart[5], dc, cw, ch;
+        dsvcu_symbol *st = dsvcu_symbol_staging(s->ctx, i, &cap);
+        dsvcu_coefs_plane_dims(s->coefs, i, &cw, &ch);
+        nsym = dsv_hzcc_read_plane(br, st, cap - 1, cw, ch, lstart, &dc);
+        if (nsym < 0) {
+            DSV_ERROR(("decoding error in plane %d", i));
+            /* the reference leaves a fresh (zeroed) residual plane here */
+            GPU(dsvcu_frame_clear_plane(s->ctx, isP ? s->resd : dst, i, 0));
+            continue;
+        }
+        GPU(dsvcu_dequant_plane(s->ctx, s->coefs, i, quant, &fm, nsym, lstart, dc));
+        GPU(dsvcu_inv_sbt(s->ctx, isP ? s->resd : dst, i, s->coefs, quant, &fm));
+        if (!isP) {
+            GPU(dsvcu_intra_filter(s->ctx, quant, &fm, i, dst, do_filter));
+        }
+    }
+    *fn = fno;
+    if (isP) {
+        if (!s->have_ref) {
+            DSV_WARNING(("reference frame not found"));
+            return DSV_DEC_ERROR;
+        }
+        GPU(dsvcu_add_pred(s->ctx, &fm, quant, s->resd, dst, ref, do_filter));
+    }
+    if (is_ref) {
+        GPU(dsvcu_extend_frame(s->ctx, dst, 0));
+    }
+
+    host = dsv_mk_frame(meta->subsamp, meta->width, meta->height, 0);
+    for (i = 0; i < 3; i++) {
+        GPU(dsvcu_frame_download(s->ctx, dst, i, host->planes[i].data, host->planes[i].stride));
+    }
+    GPU(dsvcu_sync(s->ctx));
+    if (is_ref) {
+        s->cur ^= 1;
+        s->have_ref = 1;
+    }
+    if (d->draw_info) {
+        DSV_WARNING(("draw_info overlays are not implemented in the B200 build"));
+    }
+    *out = host;
+    return DSV_DEC_OK;
+}
+
+int
+dsv_dec(DSV_DECODER *d, DSV_BUF *buffer, DSV_FRAME **out, DSV_FNUM *fn)
+{
+    DSV_BITRD br;
+    uint8_t *pkt;
+    int pkt_type, ret = DSV_DEC_ERROR;
+
+    *fn = (DSV_FNUM) -1;
+    *out = NULL;
+    /* the bit reader looks ahead 8 bytes: parse from a zero-padded copy */
+    pkt = malloc((size_t) buffer->len + 32);
+    if (!pkt) {
+        dsv_buf_free(buffer);
+        return DSV_DEC_ERROR;
+    }
+    memcpy(pkt, buffer->data, buffer->len);
+    memset(pkt + buffer->len, 0, 32);
+    dsv_br_init(&br, pkt, buffer->len);
+    pkt_type = read_packet_hdr(&br);
+
+    if (pkt_type == -1) {
+        ret = DSV_DEC_ERROR;
+    } else if (!DSV_PT_IS_PIC(pkt_type)) {
+        if (pkt_type == DSV_PT_META) {
+            read_meta(d, &br);
+            d->got_metadata = 1;
+            ret = DSV_DEC_GOT_META;
+        } else if (pkt_type == DSV_PT_EOS) {
+            ret = DSV_DEC_EOS;
+        }
+    } else if (!d->got_metadata) {
+        DSV_WARNING(("no metadata, skipping frame"));
+        ret = DSV_DEC_OK;
+    } else {
+        DEC_STATE *s = state_get(d);
+        ret = s ? decode_picture(d, s, &br, pkt_type, out, fn) : DSV_DEC_ERROR;
+    }
+    free(pkt);
+    dsv_buf_free(buffer);
+    return ret;
+}

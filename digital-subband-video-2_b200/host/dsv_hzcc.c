@@ -1,0 +1,128 @@
+/*
+ * dsv_hzcc.c -- serialisation half of the Hierarchical Zero Coefficient Coder.
+ *
+ * The reference fuses quantisation and entropy coding in one raster walk over
+ * every coefficient (src/hzcc.c:234-448 / :450-583).  Here the arithmetic runs
+ * on the GPU (csrc/k_quant.cuh) and the host only sees the ordered list of
+ * non-zero symbols: (scan position, value).  Writing a plane is a walk over
+ * that list (run = gap between positions); reading a plane rebuilds the list
+ * in O(non-zeros) instead of O(coefficients).
+ *
+ * Plane layout (reference hzcc.c:585-649): [32-bit byte length][SEG dc]
+ * [align][24-bit pair count][align][(UEG run, value)...][align][0x55][align],
+ * value = NEG in the LL part, adaptive Rice with damping 3+level elsewhere.
+ */
+#include <string.h>
+#include "dsv_host.h"
+
+void
+dsv_hzcc_write_plane(DSV_BITWR *bw, const dsvcu_symbol *syms, int nsyms, int dc, int w, int h)
+{
+    int part[5], i, l = -1, vk = 0;
+    size_t start, cnt_at;
+    unsigned prev = 0;
+
+    dsvcu_scan_layout(w, h, part);
+    dsv_bw_align(bw);
+    start = dsv_bw_byte(bw);
+    dsv_bw_bits(bw, 32, 0);
+    dsv_bw_seg(bw, dc);
+
+    dsv_bw_align(bw);
+    cnt_at = dsv_bw_byte(bw);
+    dsv_bw_bits(bw, 24, 0);
+    dsv_bw_align(bw);
+    for (i = 0; i < nsyms; i++) {
+        unsigned pos = syms[i].pos;
+        while (l < 2 && pos >= (unsigned) part[l + 2]) {
+            l++;
+        }
+        dsv_bw_ueg(bw, pos - prev);
+        if (l < 0) {
+            dsv_bw_neg(bw, syms[i].v);
+        } else {
+            dsv_bw_nrice(bw, syms[i].v, &vk, 3 + l);
+        }
+        prev = pos + 1;
+    }
+    dsv_bw_align(bw);
+    dsv_bw_patch24(bw, cnt_at, (unsigned) nsyms);
+
+    dsv_bw_bits(bw, 8, DSV_EOP_SYMBOL);
+    dsv_bw_align(bw);
+    dsv_bw_patch32(bw, start, (unsigned) (dsv_bw_byte(bw) - start - 4));
+}
+
+int
+dsv_hzcc_read_plane(DSV_BITRD *br, dsvcu_symbol *syms, int cap, int w, int h, int level_start[5], int *dc)
+{
+    int part[5], total, n = 0, l = -1, vk = 0, i;
+    unsigned plen;
+    size_t start, limit;
+    int runs, truncated = 0;
+    unsigned cur = 0, run;
+
+    total = dsvcu_scan_layout(w, h, part);
+    for (i = 0; i < 5; i++) {
+        level_start[i] = 0;
+    }
+    *dc = 0;
+    dsv_br_align(br);
+    plen = dsv_br_bits(br, 32);
+    dsv_br_align(br);
+    if (!(plen > 0 && plen < (unsigned) w * (unsigned) h * sizeof(DSV_SBC) * 2)) {
+        DSV_ERROR(("plane length was strange: %d", (int) plen));
+        return -1;
+    }
+    start = dsv_br_byte(br);
+    limit = start + plen;
+    *dc = dsv_br_seg(br);
+
+    dsv_br_align(br);
+    runs = (int) dsv_br_bits(br, 24);
+    dsv_br_align(br);
+    /* (run, value) pairs.  As in the reference (hzcc.c:476-486) the next run
+     * is fetched before the bounds test, and a pair whose bits end at or past
+     * the declared plane length is dropped together with everything after it */
+    run = (runs-- > 0) ? dsv_br_ueg(br) : UINT_MAX;
+    while (run != UINT_MAX) {
+        unsigned pos = cur + run;
+        int v;
+        if (pos >= (unsigned) total || pos < cur) {
+            break;
+        }
+        while (l < 2 && pos >= (unsigned) part[l + 2]) {
+            l++;
+            level_start[l + 1] = n;
+        }
+        v = (l < 0) ? dsv_br_neg(br) : dsv_br_nrice(br, &vk, 3 + l);
+        run = (runs-- > 0) ? dsv_br_ueg(br) : UINT_MAX;
+        if (dsv_br_byte(br) >= limit) {
+            truncated = 1;
+            break;
+        }
+        if (n < cap && pos != 0) {
+            syms[n].pos = pos;
+            syms[n].v = v;
+            n++;
+        }
+        cur = pos + 1;
+    }
+    while (l < 2) {
+        l++;
+        level_start[l + 1] = n;
+    }
+    level_start[4] = n;
+
+    /* end-of-plane marker: checked where sequential parsing stopped */
+    if (!truncated) {
+        dsv_br_align(br);
+    }
+    if (dsv_br_bits(br, 8) != DSV_EOP_SYMBOL) {
+        DSV_ERROR(("bad eop, frame data incomplete and/or corrupt"));
+        br->pos = limit * 8;
+        return -1;
+    }
+    br->pos = limit * 8;
+    return n;
+}

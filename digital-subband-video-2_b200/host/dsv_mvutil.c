@@ -1,0 +1,128 @@
+/*
+ * dsv_mvutil.c -- motion-vector field helpers used by the host-side motion
+ * (de)coder: neighbour predictor, neighbour difference, rate estimate.
+ * Same arithmetic as reference src/dsv.c:324-459 (spec B.2.3.4); the device
+ * twins of these live in csrc/ for the kernels that need them.
+ */
+#include <stdlib.h>
+#include "dsv_host.h"
+
+int
+dsv_lb2(unsigned n)
+{
+    int l = 0;
+    unsigned i = 1;
+    while (i < n) {
+        i <<= 1;
+        l++;
+    }
+    return l;
+}
+
+/* pick whichever of left/top is closer to the gradient left + top - topleft */
+static int
+grad_pick(int left, int top, int topleft)
+{
+    int g = left + top - topleft;
+    return (abs(g - left) < abs(g - top)) ? left : top;
+}
+
+void
+dsv_movec_pred(DSV_MV *vecs, DSV_PARAMS *p, int x, int y, int *px, int *py)
+{
+    int lx = 0, ly = 0, tx = 0, ty = 0, dx = 0, dy = 0;
+    DSV_MV *row = vecs + y * p->nblocks_h;
+    if (x > 0) {
+        lx = row[x - 1].u.mv.x;
+        ly = row[x - 1].u.mv.y;
+    }
+    if (y > 0) {
+        tx = row[x - p->nblocks_h].u.mv.x;
+        ty = row[x - p->nblocks_h].u.mv.y;
+        if (x > 0) {
+            dx = row[x - 1 - p->nblocks_h].u.mv.x;
+            dy = row[x - 1 - p->nblocks_h].u.mv.y;
+        }
+    }
+    *px = grad_pick(lx, tx, dx);
+    *py = grad_pick(ly, ty, dy);
+}
+
+void
+dsv_neighbordif2(DSV_MV *vecs, DSV_PARAMS *p, int x, int y, int *dx, int *dy)
+{
+    DSV_MV *c = vecs + x + y * p->nblocks_h, *n;
+    int cx = c->u.mv.x, cy = c->u.mv.y;
+    int lx = cx, ly = cy, tx = cx, ty = cy;
+
+    if (abs(cx) < 2 && abs(cy) < 2) {
+        *dx = *dy = 0;
+        return;
+    }
+    if (x > 0) {
+        n = c - 1;
+        if (n->u.all && !DSV_MV_IS_SKIP(n)) {
+            lx = n->u.mv.x;
+            ly = n->u.mv.y;
+        }
+    }
+    if (y > 0) {
+        n = c - p->nblocks_h;
+        if (n->u.all && !DSV_MV_IS_SKIP(n)) {
+            tx = n->u.mv.x;
+            ty = n->u.mv.y;
+        }
+    }
+    *dx = abs(lx - cx) + abs(ly - cy);
+    *dy = abs(tx - cx) + abs(ty - cy);
+}
+
+int
+dsv_neighbordif(DSV_MV *vecs, DSV_PARAMS *p, int x, int y)
+{
+    int a, b;
+    dsv_neighbordif2(vecs, p, x, y, &a, &b);
+    return (a + b) / 3;
+}
+
+static int
+seg_len(int v) /* bit length of the SEG code of v */
+{
+    unsigned x;
+    int nb = -1;
+    if (v < 0) {
+        v = -v;
+    }
+    v++;
+    for (x = (unsigned) v; x; x >>= 1) {
+        nb++;
+    }
+    return nb * 2 + 1 + (v ? 1 : 0);
+}
+
+int
+dsv_mv_cost(DSV_MV *vecs, DSV_PARAMS *p, int i, int j, int mx, int my, int q, int sqr)
+{
+    int px, py, bits, b2sr;
+    dsv_movec_pred(vecs, p, i, j, &px, &py);
+    bits = seg_len(mx - px) + seg_len(my - py);
+    b2sr = (256 * (q * q >> DSV_MAX_QP_BITS) * p->blk_w * p->blk_h) / (p->vidmeta->width * p->vidmeta->height);
+    bits += bits * b2sr >> 7;
+    return sqr ? bits * bits : bits;
+}
+
+void
+dsv_fmeta_from_params(dsvcu_fmeta *fm, const DSV_PARAMS *p, int isP, unsigned fnum)
+{
+    fm->isP = isP;
+    fm->lossless = p->lossless;
+    fm->do_psy = p->do_psy;
+    fm->blk_w = p->blk_w;
+    fm->blk_h = p->blk_h;
+    fm->nblocks_h = p->nblocks_h;
+    fm->nblocks_v = p->nblocks_v;
+    fm->temporal_mc = p->temporal_mc;
+    fm->inter_sharpen = p->vidmeta ? p->vidmeta->inter_sharpen : 0;
+    fm->effort = p->effort;
+    fm->fnum = fnum;
+}

@@ -1,0 +1,136 @@
+/*
+ * dsv_cuda.h -- C ABI of the B200 (sm_100a) pixel path of DSV2.
+ *
+ * This is the one new boundary the B200 build adds to the codec: host C
+ * (bitstream, rate control, I/O) on one side, device-resident frames and
+ * hand-written kernels on the other.  Every entry point is plain C: opaque
+ * handles, raw pointers and sizes, `int` status (0 = ok, negative = failure;
+ * dsvcu_last_error() gives the text).  Nothing here ever falls back to a CPU
+ * implementation: without a usable CUDA device dsvcu_ctx_create() fails.
+ *
+ * Each stage call replaces one operator of the reference's internal boundary
+ * (reference src/dsv_internal.h:112-147, src/dsv_encoder.h:215, src/dsv.h:
+ * 232-237); the reference file:line is given next to each prototype.  All stage
+ * calls are asynchronous on the context's stream; dsvcu_sync() waits.
+ */
+#ifndef DSV2_B200_DSV_CUDA_H
+#define DSV2_B200_DSV_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dsvcu_ctx dsvcu_ctx;
+typedef struct dsvcu_frame dsvcu_frame; /* u8 planar frame, 32-px border, on device */
+typedef struct dsvcu_coefs dsvcu_coefs; /* int32 subband planes, on device */
+
+/* per-frame parameters the operators read (subset of DSV_PARAMS/DSV_FMETA,
+ * reference dsv.h:242-268, dsv_internal.h:40-47) */
+typedef struct {
+    int isP;
+    int lossless;
+    int do_psy;
+    int blk_w, blk_h;
+    int nblocks_h, nblocks_v;
+    int temporal_mc;
+    int inter_sharpen;
+    int effort;
+    unsigned fnum;
+} dsvcu_fmeta;
+
+/* one coded coefficient: position in HZCC scan order + quantised value */
+typedef struct {
+    uint32_t pos;
+    int32_t v;
+} dsvcu_symbol;
+
+/* ---- context ---- */
+int dsvcu_device_count(void);
+const char *dsvcu_last_error(void);
+int dsvcu_ctx_create(dsvcu_ctx **out, int device, int width, int height, int subsamp);
+void dsvcu_ctx_destroy(dsvcu_ctx *ctx);
+/* the CUDA stream (cudaStream_t) all work of this context is issued on */
+void *dsvcu_ctx_stream(dsvcu_ctx *ctx);
+int dsvcu_sync(dsvcu_ctx *ctx);
+
+/* ---- device objects ---- */
+/* frame with the stream geometry (3 planes) or a luma-only frame of w x h */
+int dsvcu_frame_create(dsvcu_ctx *ctx, dsvcu_frame **out);
+int dsvcu_frame_create_luma(dsvcu_ctx *ctx, dsvcu_frame **out, int w, int h);
+void dsvcu_frame_destroy(dsvcu_ctx *ctx, dsvcu_frame *f);
+int dsvcu_frame_plane_dims(dsvcu_frame *f, int plane, int *w, int *h, int *stride);
+/* host <-> device, visible w x h area of one plane (host rows `hstride` apart) */
+int dsvcu_frame_upload(dsvcu_ctx *ctx, dsvcu_frame *f, int plane, const uint8_t *src, int hstride);
+int dsvcu_frame_download(dsvcu_ctx *ctx, dsvcu_frame *f, int plane, uint8_t *dst, int hstride);
+/* memset of the visible area of one plane */
+int dsvcu_frame_clear_plane(dsvcu_ctx *ctx, dsvcu_frame *f, int plane, int value);
+/* whole bordered plane, (h+64) rows of `stride` bytes; used by tests of the border */
+int dsvcu_frame_upload_bordered(dsvcu_ctx *ctx, dsvcu_frame *f, int plane, const uint8_t *src);
+int dsvcu_frame_download_bordered(dsvcu_ctx *ctx, dsvcu_frame *f, int plane, uint8_t *dst);
+
+int dsvcu_coefs_create(dsvcu_ctx *ctx, dsvcu_coefs **out);
+void dsvcu_coefs_destroy(dsvcu_ctx *ctx, dsvcu_coefs *c);
+int dsvcu_coefs_plane_dims(dsvcu_coefs *c, int plane, int *w, int *h);
+int dsvcu_coefs_upload(dsvcu_ctx *ctx, dsvcu_coefs *c, int plane, const int32_t *src);
+int dsvcu_coefs_download(dsvcu_ctx *ctx, dsvcu_coefs *c, int plane, int32_t *dst);
+
+/* per-frame block side information (reference DSV_FMETA.blockdata / .mvs) */
+int dsvcu_set_blockdata(dsvcu_ctx *ctx, const uint8_t *blockdata, int nblocks);
+int dsvcu_set_mvs(dsvcu_ctx *ctx, const void *dsv_mv_array, int nblocks);
+
+/* ---- subband transforms ---- */
+/* dsv_fwd_sbt, reference sbt.c:847-886 (dsv_internal.h:112) */
+int dsvcu_fwd_sbt(dsvcu_ctx *ctx, dsvcu_frame *src, int plane, dsvcu_coefs *dst, const dsvcu_fmeta *fm);
+/* dsv_inv_sbt, reference sbt.c:889-934 (dsv_internal.h:113) */
+int dsvcu_inv_sbt(dsvcu_ctx *ctx, dsvcu_frame *dst, int plane, dsvcu_coefs *src, int q, const dsvcu_fmeta *fm);
+
+/* ---- quantisation: arithmetic half of dsv_encode_plane / dsv_decode_plane ---- */
+/* reference hzcc.c:254-448 (quantise in place, leave the de-quantised value,
+ * produce the ordered symbol list on the device) */
+int dsvcu_quant_plane(dsvcu_ctx *ctx, dsvcu_coefs *c, int plane, int q, const dsvcu_fmeta *fm);
+/* wait for the symbols of `plane`; pointers stay valid until the next quant of
+ * that plane.  *dc receives coefficient 0 (sent raw, hzcc.c:599-602) */
+int dsvcu_fetch_symbols(dsvcu_ctx *ctx, int plane, const dsvcu_symbol **syms, int *nsyms, int *dc);
+/* reference hzcc.c:450-583.  `syms` must come from dsvcu_symbol_staging(); the
+ * list is in scan order; level_start[0..4] = index of the first symbol of the
+ * LL part, level 0, 1, 2 and the end.  Zero-fills the plane first. */
+dsvcu_symbol *dsvcu_symbol_staging(dsvcu_ctx *ctx, int plane, int *capacity);
+int dsvcu_dequant_plane(dsvcu_ctx *ctx, dsvcu_coefs *c, int plane, int q, const dsvcu_fmeta *fm,
+                        int nsyms, const int level_start[5], int dc);
+/* number of scan positions of a plane and the first scan position of each
+ * HZCC part (LL, level 0, 1, 2, end) -- the host coder needs them */
+int dsvcu_scan_layout(int w, int h, int part_start[5]);
+
+/* ---- motion compensation, reconstruction, filters ---- */
+/* dsv_sub_pred, reference bmc.c:1057-1070 */
+int dsvcu_sub_pred(dsvcu_ctx *ctx, const dsvcu_fmeta *fm, dsvcu_frame *pred, dsvcu_frame *resd, dsvcu_frame *ref);
+/* dsv_add_pred, reference bmc.c:1093-1111 */
+int dsvcu_add_pred(dsvcu_ctx *ctx, const dsvcu_fmeta *fm, int q, dsvcu_frame *resd, dsvcu_frame *out,
+                   dsvcu_frame *ref, int do_filter);
+/* dsv_add_res, reference bmc.c:1072-1090 */
+int dsvcu_add_res(dsvcu_ctx *ctx, const dsvcu_fmeta *fm, int q, dsvcu_frame *resd, dsvcu_frame *pred, int do_filter);
+/* dsv_intra_filter, reference bmc.c:390-457 */
+int dsvcu_intra_filter(dsvcu_ctx *ctx, int q, const dsvcu_fmeta *fm, int plane, dsvcu_frame *f, int do_filter);
+/* dsv_post_process, reference bmc.c:340-361 (luma) */
+int dsvcu_post_process(dsvcu_ctx *ctx, dsvcu_frame *f);
+
+/* ---- frame helpers ---- */
+/* dsv_extend_frame / dsv_extend_frame_luma, reference frame.c:413-434 */
+int dsvcu_extend_frame(dsvcu_ctx *ctx, dsvcu_frame *f, int luma_only);
+/* dsv_ds2x_frame_luma, reference frame.c:210-234 */
+int dsvcu_ds2x_luma(dsvcu_ctx *ctx, dsvcu_frame *dst, dsvcu_frame *src);
+/* dsv_frame_copy, reference frame.c:185-207 (copies, then extends dst) */
+int dsvcu_frame_copy(dsvcu_ctx *ctx, dsvcu_frame *dst, dsvcu_frame *src);
+
+/* ---- timing on the context's stream (CUDA events) ---- */
+int dsvcu_timer_start(dsvcu_ctx *ctx);
+int dsvcu_timer_stop_ms(dsvcu_ctx *ctx, float *ms); /* synchronises */
+/* number of kernels this context has launched so far */
+long long dsvcu_launch_count(dsvcu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

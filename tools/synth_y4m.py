@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""Deterministic synthetic y4m generator (SURVEY.md section 8d recipe).
+
+Luma canvas = smooth sinusoid field + 2x2-box-filtered noise; the view pans by
+(2t + t%3, t) per frame; a 64x64 inverted-luma square moves by (17t, 9t); sensor
+noise [-3,3]; hard scene cut (canvas inverted) every `cut` frames.  Output is the
+exact y4m subset the reference parser accepts (util.c:184-307):
+"YUV4MPEG2 W.. H.. F..:1 A1:1 Ip C420|C444" + "FRAME\n" per frame.
+
+Used by tests/ and bench.py; no dependency on the reference.
+"""
+import argparse
+import sys
+
+import numpy as np
+
+
+def _canvas(w, h, rng, noise_amp):
+    cw, ch = w * 2 + 256, h * 2 + 256
+    x = np.arange(cw, dtype=np.float64)[None, :]
+    y = np.arange(ch, dtype=np.float64)[:, None]
+    luma = 128 + 60 * np.sin(x / 37.0) * np.cos(y / 23.0) + 30 * np.sin((x + y) / 11.0)
+    if noise_amp > 0:
+        n = rng.uniform(-noise_amp, noise_amp, size=(ch + 1, cw + 1))
+        n = (n[:-1, :-1] + n[1:, :-1] + n[:-1, 1:] + n[1:, 1:]) / 4.0
+        luma = luma + n
+    cb = 128 + 50 * np.sin(x / 53.0) + 0 * y
+    cr = 128 + 50 * np.cos(y / 41.0) + 0 * x
+    return luma, cb, cr
+
+
+def frames(w, h, nfr, fmt="420", seed=1234, noise=24.0, sensor=3, cut=40):
+    """Yield (Y, U, V) uint8 arrays for nfr frames."""
+    rng = np.random.default_rng(seed)
+    luma, cb, cr = _canvas(w, h, rng, noise)
+    ch_h, ch_w = luma.shape
+    sub = 2 if fmt == "420" else 1
+    for t in range(nfr):
+        ox = (2 * t + t % 3) % (ch_w - w)
+        oy = t % (ch_h - h)
+        Y = luma[oy:oy + h, ox:ox + w].copy()
+        U = cb[oy:oy + h, ox:ox + w]
+        V = cr[oy:oy + h, ox:ox + w]
+        if cut > 0 and (t // cut) % 2 == 1:
+            Y = 255.0 - Y
+        sx = (17 * t) % max(1, w - 64)
+        sy = (9 * t) % max(1, h - 64)
+        Y[sy:sy + 64, sx:sx + 64] = 255.0 - Y[sy:sy + 64, sx:sx + 64]
+        U = U.copy()
+        V = V.copy()
+        U[sy:sy + 64, sx:sx + 64] = 90.0
+        V[sy:sy + 64, sx:sx + 64] = 170.0
+        if sensor > 0:
+            Y = Y + rng.integers(-sensor, sensor + 1, size=Y.shape)
+        Y8 = np.clip(np.rint(Y), 0, 255).astype(np.uint8)
+        if sub == 2:
+            U = (U[0::2, 0::2] + U[1::2, 0::2] + U[0::2, 1::2] + U[1::2, 1::2]) / 4.0
+            V = (V[0::2, 0::2] + V[1::2, 0::2] + V[0::2, 1::2] + V[1::2, 1::2]) / 4.0
+        U8 = np.clip(np.rint(U), 0, 255).astype(np.uint8)
+        V8 = np.clip(np.rint(V), 0, 255).astype(np.uint8)
+        yield Y8, U8, V8
+
+
+def write_y4m(path, w, h, nfr, fmt="420", fps=30, **kw):
+    with open(path, "wb") as f:
+        f.write(("YUV4MPEG2 W%d H%d F%d:1 A1:1 Ip C%s\n" % (w, h, fps, fmt)).encode())
+        for Y, U, V in frames(w, h, nfr, fmt, **kw):
+            f.write(b"FRAME\n")
+            f.write(Y.tobytes())
+            f.write(U.tobytes())
+            f.write(V.tobytes())
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("out")
+    ap.add_argument("-W", type=int, default=352)
+    ap.add_argument("-H", type=int, default=288)
+    ap.add_argument("-n", type=int, default=60)
+    ap.add_argument("--fmt", default="420", choices=["420", "444"])
+    ap.add_argument("--fps", type=int, default=30)
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--noise", type=float, default=24.0)
+    ap.add_argument("--sensor", type=int, default=3)
+    ap.add_argument("--cut", type=int, default=40)
+    a = ap.parse_args(argv)
+    write_y4m(a.out, a.W, a.H, a.n, a.fmt, a.fps, seed=a.seed, noise=a.noise,
+              sensor=a.sensor, cut=a.cut)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
