@@ -24,7 +24,8 @@ EMUOBJ  := $(HOSTSRC:.c=.emu.o)
 KHDRS   := $(wildcard $(CSRC)/*.cuh) $(CSRC)/dsvcu_rt.h include/dsv_cuda.h
 REFSRC  := /root/reference/src
 
-all: $(PKG)/libdsv2cuda.so $(PKG)/dsv2cu
+CLI := $(if $(wildcard $(HOST)/dsv_cli.c),$(PKG)/dsv2cu,)
+all: $(PKG)/libdsv2cuda.so $(CLI)
 
 $(CSRC)/dsvcu_api.o: $(CSRC)/dsvcu_api.cu $(KHDRS)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
@@ -33,7 +34,7 @@ $(HOST)/%.o: $(HOST)/%.c $(HOST)/dsv_host.h include/dsv.h include/dsv_cuda.h
 	$(CC) $(CFLAGS) -c $< -o $@
 
 $(PKG)/libdsv2cuda.so: $(CSRC)/dsvcu_api.o $(HOSTOBJ)
-	$(NVCC) $(ARCH) -shared -o $@ $^ -Xlinker -Bsymbolic -lcudart -lpthread
+	$(NVCC) $(ARCH) -shared -o $@ $^ -Xlinker -Bsymbolic -lpthread
 
 $(PKG)/dsv2cu: $(HOST)/dsv_cli.c $(PKG)/libdsv2cuda.so
 	$(CC) $(CFLAGS) -o $@ $(HOST)/dsv_cli.c -L$(PKG) -ldsv2cuda -Wl,-rpath,'$$ORIGIN' -lpthread

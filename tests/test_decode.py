@@ -1,0 +1,41 @@
+"""Whole-stream decode parity: dsv_dec() of the B200 library vs the reference
+decoder (oracle/_ref/dsv2 d) on streams produced by the reference encoder."""
+import pytest
+
+import util
+
+CASES = [
+    # name, w, h, frames, fmt, encoder args  (BASELINE.json configs, shortened)
+    ("cif", 352, 288, 20, "420", ["-qp=60", "-gop=48"]),
+    ("cif_lowq", 352, 288, 8, "420", ["-qp=20", "-gop=4"]),
+    ("odd", 200, 136, 6, "420", ["-qp=70", "-gop=3"]),
+    ("hd", 1280, 720, 4, "420", ["-gop=250", "-effort=10"]),
+    ("fhd", 1920, 1080, 4, "420", ["-qp=60", "-gop=48"]),
+    ("fhd444ll", 1920, 1080, 2, "444", ["-qp=100"]),
+    ("cif444", 352, 288, 6, "444", ["-qp=50", "-gop=5"]),
+]
+SMALL = [c for c in CASES if c[1] <= 352]
+
+
+def _run(case, emu):
+    name, w, h, n, fmt, args = case
+    y4m = util.clip(name, w, h, n, fmt)
+    dsv = util.ref_encode(y4m, args, "ref")
+    _, _, ref = util.read_y4m(util.ref_decode(dsv))
+    meta, got = util.pkg().decode_stream(open(dsv, "rb").read(), emu=emu)
+    assert meta["width"] == w and meta["height"] == h
+    util.assert_same_frames(got, ref, w, h)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", SMALL, ids=[c[0] for c in SMALL])
+def test_decode_emulated_kernels(case):
+    """CPU-only: host logic + kernel arithmetic (test-only host emulation)."""
+    util.ensure_emu()
+    _run(case, emu=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_decode_gpu(case):
+    _run(case, emu=False)
