@@ -12,6 +12,7 @@
 #include "k_bmc.cuh"
 #include "k_filter.cuh"
 #include "k_frame.cuh"
+#include "k_hme.cuh"
 #include "../../include/dsv_cuda.h"
 
 #ifdef DSVCU_EMU
@@ -97,6 +98,13 @@ struct dsvcu_ctx {
     int sym_cap[3];
     int *d_progress;
     int progress_cap;
+    /* motion estimation */
+    dsvcu_mv *d_mvf[ME_MAXLVL + 1]; /* [0] aliases d_mvs */
+    dsvcu_mv *d_prev_mvf;
+    int mvf_cap;
+    int *d_me;  /* [0..1] global motion, [2..5] accumulators, [6] luma avg */
+    int *h_me;  /* pinned mirror */
+    int me_nblk;
 #ifndef DSVCU_EMU
     cudaEvent_t ev0, ev1;
 #endif
@@ -210,6 +218,8 @@ dsvcu_ctx_create(dsvcu_ctx **out, int device, int width, int height, int subsamp
     }
     c->progress_cap = height / 4 + 64;
     CK(dsvcu_malloc(&c->d_progress, (size_t) c->progress_cap * sizeof(int)));
+    CK(dsvcu_malloc(&c->d_me, 16 * sizeof(int)));
+    CK(dsvcu_malloc_host(&c->h_me, 16 * sizeof(int)));
     *out = c;
     return 0;
 }
@@ -236,6 +246,12 @@ dsvcu_ctx_destroy(dsvcu_ctx *c)
     dsvcu_free_dev(c->d_progress);
     if (c->d_blockdata) dsvcu_free_dev(c->d_blockdata);
     if (c->d_mvs) dsvcu_free_dev(c->d_mvs);
+    for (i = 1; i <= ME_MAXLVL; i++) {
+        if (c->d_mvf[i]) dsvcu_free_dev(c->d_mvf[i]);
+    }
+    if (c->d_prev_mvf) dsvcu_free_dev(c->d_prev_mvf);
+    dsvcu_free_dev(c->d_me);
+    dsvcu_free_host(c->h_me);
 #ifndef DSVCU_EMU
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -1078,4 +1094,231 @@ dsvcu_frame_copy(dsvcu_ctx *c, dsvcu_frame *dst, dsvcu_frame *src)
                               dst->p[i].h, c->stream));
     }
     return dsvcu_extend_frame(c, dst, 0);
+}
+
+/* ------------------------------------------------- motion estimation (encoder) */
+
+struct dsvcu_pyramid {
+    int levels;
+    dsvcu_frame *f[ME_MAXLVL + 1]; /* [1..levels] */
+};
+
+extern "C" int
+dsvcu_pyramid_create(dsvcu_ctx *c, dsvcu_pyramid **out, int levels)
+{
+    dsvcu_pyramid *p = (dsvcu_pyramid *) calloc(1, sizeof(*p));
+    int i;
+    if (!p || levels > ME_MAXLVL) return -1;
+    p->levels = levels;
+    for (i = 1; i <= levels; i++) {
+        if (dsvcu_frame_create_luma(c, &p->f[i], RSHIFT_UP(c->width, i), RSHIFT_UP(c->height, i))) return -1;
+    }
+    *out = p;
+    return 0;
+}
+
+extern "C" void
+dsvcu_pyramid_destroy(dsvcu_ctx *c, dsvcu_pyramid *p)
+{
+    int i;
+    if (!p) return;
+    for (i = 1; i <= p->levels; i++) dsvcu_frame_destroy(c, p->f[i]);
+    free(p);
+}
+
+extern "C" dsvcu_frame *
+dsvcu_pyramid_level(dsvcu_pyramid *p, int level)
+{
+    return (level >= 1 && level <= p->levels) ? p->f[level] : NULL;
+}
+
+extern "C" int
+dsvcu_pyramid_build(dsvcu_ctx *c, dsvcu_pyramid *p, dsvcu_frame *base)
+{
+    dsvcu_frame *prev = base;
+    int i;
+    for (i = 1; i <= p->levels; i++) {
+        if (dsvcu_ds2x_luma(c, p->f[i], prev)) return -1;
+        if (dsvcu_extend_frame(c, p->f[i], 1)) return -1;
+        prev = p->f[i];
+    }
+    return 0;
+}
+
+static int
+ensure_mvf(dsvcu_ctx *c, int nblk)
+{
+    int i;
+    if (ensure_blocks(c, nblk)) return -1;
+    if (nblk <= c->mvf_cap) return 0;
+    for (i = 1; i <= ME_MAXLVL; i++) {
+        if (c->d_mvf[i]) dsvcu_free_dev(c->d_mvf[i]);
+        CK(dsvcu_malloc(&c->d_mvf[i], ((size_t) nblk + 4) * sizeof(dsvcu_mv)));
+    }
+    if (c->d_prev_mvf) dsvcu_free_dev(c->d_prev_mvf);
+    CK(dsvcu_malloc(&c->d_prev_mvf, ((size_t) nblk + 4) * sizeof(dsvcu_mv)));
+    CK(dsvcu_memset_async(c->d_prev_mvf, 0, ((size_t) nblk + 4) * sizeof(dsvcu_mv), c->stream));
+    c->mvf_cap = nblk;
+    return 0;
+}
+
+extern "C" int
+dsvcu_set_prev_mvs(dsvcu_ctx *c, const void *mvs, int n)
+{
+    if (ensure_mvf(c, n)) return -1;
+    CK(dsvcu_h2d_async(c->d_prev_mvf, mvs, (size_t) n * sizeof(dsvcu_mv), c->stream));
+    return 0;
+}
+
+static void
+me_plane(MePlane *m, dsvcu_frame *f, int plane)
+{
+    m->data = f->p[plane].data;
+    m->stride = f->p[plane].stride;
+    m->w = f->p[plane].w;
+    m->h = f->p[plane].h;
+}
+
+extern "C" int
+dsvcu_hme(dsvcu_ctx *c, const dsvcu_fmeta *fm, const dsvcu_hme_params *hp, dsvcu_frame *src, dsvcu_pyramid *src_pyr,
+          dsvcu_frame *ref, dsvcu_pyramid *ref_pyr, dsvcu_frame *ogr, dsvcu_pyramid *ogr_pyr)
+{
+    const int nblk = fm->nblocks_h * fm->nblocks_v;
+    int lvl;
+    if (ensure_mvf(c, nblk)) return -1;
+    c->me_nblk = nblk;
+    c->d_mvf[0] = c->d_mvs;
+    CK(dsvcu_memset_async(c->d_me, 0, 16 * sizeof(int), c->stream));
+    for (lvl = hp->pyramid_levels; lvl >= 0; lvl--) {
+        MeArgs A;
+        int step = 1 << lvl, rows, ctas;
+        dsvcu_frame *fs = lvl ? src_pyr->f[lvl] : src;
+        dsvcu_frame *fr = lvl ? ref_pyr->f[lvl] : ref;
+        dsvcu_frame *fo = lvl ? ogr_pyr->f[lvl] : ogr;
+        memset(&A, 0, sizeof(A));
+        me_plane(&A.src[0], fs, 0);
+        me_plane(&A.ref[0], fr, 0);
+        me_plane(&A.ogr, fo, 0);
+        if (lvl == 0) {
+            me_plane(&A.src[1], fs, 1);
+            me_plane(&A.src[2], fs, 2);
+            me_plane(&A.ref[1], fr, 1);
+            me_plane(&A.ref[2], fr, 2);
+        }
+        A.mvf = c->d_mvf[lvl];
+        A.parent = (lvl < hp->pyramid_levels) ? c->d_mvf[lvl + 1] : NULL;
+        A.ref_mvf = hp->use_prev_mvs ? c->d_prev_mvf : NULL;
+        A.nxb = fm->nblocks_h;
+        A.nyb = fm->nblocks_v;
+        A.y_w = fm->blk_w;
+        A.y_h = fm->blk_h;
+        A.level = lvl;
+        A.quant = hp->quant;
+        A.effort = fm->effort;
+        A.lossless = fm->lossless;
+        A.skip_thresh = hp->skip_block_thresh;
+        A.hs = FMT_HSHIFT(c->subsamp);
+        A.vs = FMT_VSHIFT(c->subsamp);
+        A.vid_w = c->width;
+        A.vid_h = c->height;
+        A.psyscale = psy_factor(fm, -1);
+        A.gxy = c->d_me;
+        A.acc = c->d_me + 2;
+        rows = (fm->nblocks_v + step - 1) / step;
+        A.nrows = rows;
+        if (rows > c->progress_cap) {
+            dsvcu_free_dev(c->d_progress);
+            c->progress_cap = rows + 64;
+            CK(dsvcu_malloc(&c->d_progress, (size_t) c->progress_cap * sizeof(int)));
+        }
+        A.progress = c->d_progress;
+        CK(dsvcu_memset_async(c->d_progress, 0, (size_t) rows * sizeof(int), c->stream));
+        CK(dsvcu_memset_async(c->d_mvf[lvl], 0, (size_t) nblk * sizeof(dsvcu_mv), c->stream));
+#ifdef DSVCU_EMU
+        ctas = 1;
+#else
+        ctas = (rows + ME_WARPS_PER_CTA - 1) / ME_WARPS_PER_CTA;
+        if (ctas > 148 * 4) ctas = 148 * 4;
+#endif
+        DSVCU_LAUNCH(k_me_level, ctas, ME_WARPS_PER_CTA * 32, 0, c->stream, A);
+        CK_LAUNCH(c);
+        if (lvl != 0) {
+            DSVCU_LAUNCH(k_me_global, 1, 256, 0, c->stream, c->d_mvf[lvl], fm->nblocks_h, fm->nblocks_v, lvl, c->d_me);
+            CK_LAUNCH(c);
+        }
+    }
+    /* this picture's field is the next picture's temporal predictor */
+    CK(dsvcu_d2d_async(c->d_prev_mvf, c->d_mvs, (size_t) nblk * sizeof(dsvcu_mv), c->stream));
+    return 0;
+}
+
+extern "C" int
+dsvcu_hme_fetch(dsvcu_ctx *c, void *mvs_out, int nblocks, int *intra_pct, int *scene_change_blocks, int *avg_err)
+{
+    int elig;
+    CK(dsvcu_d2h_async(c->h_me, c->d_me, 16 * sizeof(int), c->stream));
+    CK(dsvcu_d2h_async(mvs_out, c->d_mvs, (size_t) nblocks * sizeof(dsvcu_mv), c->stream));
+    CK(dsvcu_stream_sync(c->stream));
+    elig = c->h_me[4] ? c->h_me[4] : 1;
+    *intra_pct = (c->h_me[2] * 100) / nblocks;
+    *scene_change_blocks = c->h_me[3] * 100 / elig;
+    *avg_err = (int) ((unsigned) c->h_me[5] / (unsigned) nblocks);
+    return 0;
+}
+
+extern "C" int
+dsvcu_intra_analysis(dsvcu_ctx *c, const dsvcu_fmeta *fm, dsvcu_frame *src, void *mvs_out, int nblocks)
+{
+    IaArgs A;
+    int ctas;
+    if (ensure_mvf(c, nblocks)) return -1;
+    memset(&A, 0, sizeof(A));
+    me_plane(&A.src[0], src, 0);
+    me_plane(&A.src[1], src, 1);
+    me_plane(&A.src[2], src, 2);
+    A.out = c->d_mvf[1]; /* scratch field; intra pictures run no motion search */
+    A.nxb = fm->nblocks_h;
+    A.nyb = fm->nblocks_v;
+    A.y_w = fm->blk_w;
+    A.y_h = fm->blk_h;
+    A.hs = FMT_HSHIFT(c->subsamp);
+    A.vs = FMT_VSHIFT(c->subsamp);
+    A.do_psy = fm->do_psy;
+    A.scale = 2 * psy_factor(fm, -1);
+    ctas = (nblocks + ME_WARPS_PER_CTA - 1) / ME_WARPS_PER_CTA;
+    if (ctas > 148 * 8) ctas = 148 * 8;
+    DSVCU_LAUNCH(k_intra_analysis, ctas, ME_WARPS_PER_CTA * 32, 0, c->stream, A);
+    CK_LAUNCH(c);
+    CK(dsvcu_d2h_async(mvs_out, A.out, (size_t) nblocks * sizeof(dsvcu_mv), c->stream));
+    CK(dsvcu_stream_sync(c->stream));
+    return 0;
+}
+
+/* frame_luma_avg (dsv_encoder.c:108-127): sum over rows of (row sum / w), / h */
+DSVCU_KERNEL void __launch_bounds__(256)
+k_luma_avg(const uint8_t *data, int stride, int w, int h, int *out)
+{
+    DSVCU_SHARED unsigned tot;
+    unsigned acc = 0;
+    if (DSVCU_TID == 0) tot = 0;
+    DSVCU_SYNC();
+    PAR_FOR(j, h) {
+        unsigned rav = 0;
+        for (int i = 0; i < w; i++) rav += data[(size_t) j * stride + i];
+        acc += rav / (unsigned) w;
+    }
+    atomicAdd(&tot, acc);
+    DSVCU_SYNC();
+    if (DSVCU_TID == 0) *out = (int) (tot / (unsigned) h);
+}
+
+extern "C" int
+dsvcu_frame_luma_avg(dsvcu_ctx *c, dsvcu_frame *f, unsigned *avg)
+{
+    DSVCU_LAUNCH(k_luma_avg, 1, 256, 0, c->stream, f->p[0].data, f->p[0].stride, f->p[0].w, f->p[0].h, c->d_me + 6);
+    CK_LAUNCH(c);
+    CK(dsvcu_d2h_async(c->h_me + 6, c->d_me + 6, sizeof(int), c->stream));
+    CK(dsvcu_stream_sync(c->stream));
+    *avg = (unsigned) c->h_me[6];
+    return 0;
 }

@@ -124,6 +124,39 @@ int dsvcu_ds2x_luma(dsvcu_ctx *ctx, dsvcu_frame *dst, dsvcu_frame *src);
 /* dsv_frame_copy, reference frame.c:185-207 (copies, then extends dst) */
 int dsvcu_frame_copy(dsvcu_ctx *ctx, dsvcu_frame *dst, dsvcu_frame *src);
 
+/* ---- motion estimation / block analysis (encoder) ---- */
+typedef struct dsvcu_pyramid dsvcu_pyramid; /* luma-only 2x pyramid, levels 1..n */
+int dsvcu_pyramid_create(dsvcu_ctx *ctx, dsvcu_pyramid **out, int levels);
+void dsvcu_pyramid_destroy(dsvcu_ctx *ctx, dsvcu_pyramid *p);
+/* mk_pyramid, reference dsv_encoder.c:493-516 (ds2x + luma border per level) */
+int dsvcu_pyramid_build(dsvcu_ctx *ctx, dsvcu_pyramid *p, dsvcu_frame *base);
+dsvcu_frame *dsvcu_pyramid_level(dsvcu_pyramid *p, int level); /* 1..n */
+
+typedef struct {
+    int quant;             /* DSV_HME.quant = previous picture's quantiser */
+    int skip_block_thresh; /* DSV_ENCODER.skip_block_thresh */
+    int pyramid_levels;
+    int use_prev_mvs;      /* DSV_HME.ref_mvf != NULL */
+} dsvcu_hme_params;
+
+/* the previous picture's final vector field (DSV_HME.ref_mvf).  dsvcu_hme keeps
+ * its own result for the next call; this overrides it (tests / resync) */
+int dsvcu_set_prev_mvs(dsvcu_ctx *ctx, const void *dsv_mv_array, int nblocks);
+/* dsv_hme, reference hme.c:2001-2016 (struct DSV_HME, dsv_encoder.h:202-213).
+ * Leaves the final field on the device as the current MV array (as if
+ * dsvcu_set_mvs had been called with it). */
+int dsvcu_hme(dsvcu_ctx *ctx, const dsvcu_fmeta *fm, const dsvcu_hme_params *hp, dsvcu_frame *src,
+              dsvcu_pyramid *src_pyr, dsvcu_frame *ref, dsvcu_pyramid *ref_pyr, dsvcu_frame *ogr,
+              dsvcu_pyramid *ogr_pyr);
+/* waits; copies the field to `mvs_out` (nblocks DSV_MV) and the three scalars
+ * dsv_hme returns (intra %, scene-change blocks %, average error) */
+int dsvcu_hme_fetch(dsvcu_ctx *ctx, void *mvs_out, int nblocks, int *intra_pct, int *scene_change_blocks,
+                    int *avg_err);
+/* dsv_intra_analysis, reference hme.c:1835-1971; result via dsvcu_hme_fetch-like copy */
+int dsvcu_intra_analysis(dsvcu_ctx *ctx, const dsvcu_fmeta *fm, dsvcu_frame *src, void *mvs_out, int nblocks);
+/* frame_luma_avg, reference dsv_encoder.c:108-127 (sum of per-row averages / h); waits */
+int dsvcu_frame_luma_avg(dsvcu_ctx *ctx, dsvcu_frame *f, unsigned *avg);
+
 /* ---- timing on the context's stream (CUDA events) ---- */
 int dsvcu_timer_start(dsvcu_ctx *ctx);
 int dsvcu_timer_stop_ms(dsvcu_ctx *ctx, float *ms); /* synchronises */
