@@ -88,6 +88,11 @@ class DSVCU_FMETA(C.Structure):
                 ("effort", C.c_int), ("fnum", C.c_uint)]
 
 
+class DSVCU_HME_PARAMS(C.Structure):
+    _fields_ = [("quant", C.c_int), ("skip_block_thresh", C.c_int),
+                ("pyramid_levels", C.c_int), ("use_prev_mvs", C.c_int)]
+
+
 class DSVCU_SYMBOL(C.Structure):
     _fields_ = [("pos", C.c_uint32), ("v", C.c_int32)]
 
@@ -122,6 +127,7 @@ def load(emu=False):
         "dsv_set_log_level": (None, [ip]),
         "dsv_dec": (ip, [P(DSV_DECODER), P(DSV_BUF), P(P(DSV_FRAME)), P(C.c_uint32)]),
         "dsv_dec_free": (None, [P(DSV_DECODER)]),
+        "dsv_hzcc_pack_plane": (ip, [vp, ip, ip, ip, ip, vp, ip]),
         "dsvcu_device_count": (ip, []),
         "dsvcu_last_error": (C.c_char_p, []),
         "dsvcu_ctx_create": (ip, [P(vp), ip, ip, ip, ip]),
@@ -159,6 +165,15 @@ def load(emu=False):
         "dsvcu_extend_frame": (ip, [vp, vp, ip]),
         "dsvcu_ds2x_luma": (ip, [vp, vp, vp]),
         "dsvcu_frame_copy": (ip, [vp, vp, vp]),
+        "dsvcu_pyramid_create": (ip, [vp, P(vp), ip]),
+        "dsvcu_pyramid_destroy": (None, [vp, vp]),
+        "dsvcu_pyramid_build": (ip, [vp, vp, vp]),
+        "dsvcu_pyramid_level": (vp, [vp, ip]),
+        "dsvcu_set_prev_mvs": (ip, [vp, vp, ip]),
+        "dsvcu_hme": (ip, [vp, P(DSVCU_FMETA), P(DSVCU_HME_PARAMS), vp, vp, vp, vp, vp, vp]),
+        "dsvcu_hme_fetch": (ip, [vp, vp, ip, P(ip), P(ip), P(ip)]),
+        "dsvcu_intra_analysis": (ip, [vp, P(DSVCU_FMETA), vp, vp, ip]),
+        "dsvcu_frame_luma_avg": (ip, [vp, vp, P(C.c_uint)]),
         "dsvcu_timer_start": (ip, [vp]),
         "dsvcu_timer_stop_ms": (ip, [vp, P(C.c_float)]),
         "dsvcu_launch_count": (C.c_longlong, [vp]),

@@ -126,3 +126,22 @@ dsv_hzcc_read_plane(DSV_BITRD *br, dsvcu_symbol *syms, int cap, int w, int h, in
     br->pos = limit * 8;
     return n;
 }
+
+/* convenience for callers that want one plane as a byte string (tests, tools):
+ * returns the byte length, or -1 when `cap` is too small */
+int
+dsv_hzcc_pack_plane(const dsvcu_symbol *syms, int nsyms, int dc, int w, int h, uint8_t *out, int cap)
+{
+    DSV_BITWR bw;
+    int n;
+    dsv_bw_init(&bw, (size_t) nsyms * 4 + 64);
+    dsv_hzcc_write_plane(&bw, syms, nsyms, dc, w, h);
+    n = (int) dsv_bw_byte(&bw);
+    if (n > cap) {
+        n = -1;
+    } else {
+        memcpy(out, bw.buf, (size_t) n);
+    }
+    dsv_bw_free(&bw);
+    return n;
+}
