@@ -88,6 +88,15 @@ class DSVCU_FMETA(C.Structure):
                 ("effort", C.c_int), ("fnum", C.c_uint)]
 
 
+class DSV_ENC_OPTS(C.Structure):
+    """dsv_enc_opts (include/dsv_session.h): the reference CLI's parameter table"""
+    _fields_ = [(n, C.c_int) for n in
+                ("w", "h", "fmt", "fps_num", "fps_den", "aspect_num", "aspect_den", "qp", "effort", "gop",
+                 "rc_mode", "rc_pergop", "kbps", "minqstep", "maxqstep", "minqp", "maxqp", "iminqp",
+                 "stabref", "scd", "tempaq", "bszx", "bszy", "scpct", "skipthresh", "varint", "psy", "dib",
+                 "ifilter", "pfilter", "psharp", "ipct", "pyrlevels", "noeos")]
+
+
 class DSVCU_HME_PARAMS(C.Structure):
     _fields_ = [("quant", C.c_int), ("skip_block_thresh", C.c_int),
                 ("pyramid_levels", C.c_int), ("use_prev_mvs", C.c_int)]
@@ -128,6 +137,16 @@ def load(emu=False):
         "dsv_dec": (ip, [P(DSV_DECODER), P(DSV_BUF), P(P(DSV_FRAME)), P(C.c_uint32)]),
         "dsv_dec_free": (None, [P(DSV_DECODER)]),
         "dsv_hzcc_pack_plane": (ip, [vp, ip, ip, ip, ip, vp, ip]),
+        "dsv_enc_opts_default": (None, [P(DSV_ENC_OPTS), ip, ip, ip, ip, ip]),
+        "dsv_set_thread_device": (None, [ip]),
+        "dsv_pinned_alloc": (vp, [C.c_size_t]),
+        "dsv_pinned_free": (None, [vp]),
+        "dsv_encode_buffer": (ip, [P(DSV_ENC_OPTS), vp, ip, ip, P(vp), P(C.c_size_t)]),
+        "dsv_encode_sharded": (ip, [P(DSV_ENC_OPTS), vp, ip, ip, ip, P(ip), ip, P(vp), P(C.c_size_t)]),
+        "dsv_decode_buffer": (ip, [vp, C.c_size_t, ip, P(vp), P(C.c_size_t), P(ip), P(DSV_META)]),
+        "dsv_decode_sharded": (ip, [vp, C.c_size_t, ip, P(ip), ip, ip, P(vp), P(C.c_size_t), P(ip), P(DSV_META)]),
+        "dsvcu_host_alloc": (vp, [C.c_size_t]),
+        "dsvcu_host_free": (None, [vp]),
         "dsvcu_device_count": (ip, []),
         "dsvcu_last_error": (C.c_char_p, []),
         "dsvcu_ctx_create": (ip, [P(vp), ip, ip, ip, ip]),
@@ -170,6 +189,7 @@ def load(emu=False):
         "dsvcu_pyramid_build": (ip, [vp, vp, vp]),
         "dsvcu_pyramid_level": (vp, [vp, ip]),
         "dsvcu_set_prev_mvs": (ip, [vp, vp, ip]),
+        "dsvcu_mvs_to_prev": (ip, [vp, ip]),
         "dsvcu_hme": (ip, [vp, P(DSVCU_FMETA), P(DSVCU_HME_PARAMS), vp, vp, vp, vp, vp, vp]),
         "dsvcu_hme_fetch": (ip, [vp, vp, ip, P(ip), P(ip), P(ip)]),
         "dsvcu_intra_analysis": (ip, [vp, P(DSVCU_FMETA), vp, vp, ip]),
@@ -236,3 +256,58 @@ def decode_stream(data, emu=False, loglevel=1):
     meta = {k: getattr(dec.vidmeta, k) for k, _ in DSV_META._fields_}
     lib.dsv_dec_free(C.byref(dec))
     return meta, frames
+
+
+def enc_opts(w, h, fmt=SUBSAMP_420, fps=(30, 1), **kw):
+    """dsv_enc_opts with the reference CLI defaults; keyword names are the
+    reference's option names (qp, gop, effort, rc_mode, ...)."""
+    lib_ = load(kw.pop("emu", False))
+    o = DSV_ENC_OPTS()
+    lib_.dsv_enc_opts_default(C.byref(o), w, h, fmt, fps[0], fps[1])
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise KeyError(k)
+        setattr(o, k, v)
+    return o
+
+
+def _take(lib, ptr, n, pinned=False):
+    data = C.string_at(ptr, n.value)
+    if pinned:
+        lib.dsv_pinned_free(ptr)
+    else:
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        libc.free(ptr)
+    return data
+
+
+def encode_frames(opts, yuv, nframes, emu=False, exhausted=True, chunk=0, threads=1, devices=None):
+    """Encode packed planar frames (bytes) -> .dsv bytes.  chunk > 0 selects the
+    closed-GOP sharded driver (parallel_encode_yuv.sh semantics)."""
+    lib = load(emu)
+    out, n = C.c_void_p(), C.c_size_t()
+    buf = (C.c_uint8 * len(yuv)).from_buffer_copy(yuv) if not isinstance(yuv, C.Array) else yuv
+    if chunk > 0:
+        devs = devices or [0]
+        arr = (C.c_int * len(devs))(*devs)
+        r = lib.dsv_encode_sharded(C.byref(opts), buf, nframes, chunk, threads, arr, len(devs), C.byref(out), C.byref(n))
+    else:
+        r = lib.dsv_encode_buffer(C.byref(opts), buf, nframes, 1 if exhausted else 0, C.byref(out), C.byref(n))
+    if r:
+        raise RuntimeError("encode failed: %s" % lib.dsvcu_last_error().decode())
+    return _take(lib, out, n)
+
+
+def decode_frames(data, emu=False, threads=1, devices=None):
+    """Decode .dsv bytes -> (DSV_META, nframes, packed planar frames bytes)."""
+    lib = load(emu)
+    out, n, nfr, meta = C.c_void_p(), C.c_size_t(), C.c_int(), DSV_META()
+    devs = devices or [0]
+    arr = (C.c_int * len(devs))(*devs)
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    r = lib.dsv_decode_sharded(buf, len(data), threads, arr, len(devs), 0, C.byref(out), C.byref(n), C.byref(nfr),
+                               C.byref(meta))
+    if r:
+        raise RuntimeError("decode failed: %s" % lib.dsvcu_last_error().decode())
+    return meta, nfr.value, _take(lib, out, n)

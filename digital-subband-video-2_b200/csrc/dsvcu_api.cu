@@ -105,8 +105,12 @@ struct dsvcu_ctx {
     int *d_me;  /* [0..1] global motion, [2..5] accumulators, [6] luma avg */
     int *h_me;  /* pinned mirror */
     int me_nblk;
+    dsvcu_mv *h_mvs; /* pinned mirror of a block array */
+    int h_mvs_cap;
+    int *d_lavg, *h_lavg; /* top-of-pyramid luma average */
 #ifndef DSVCU_EMU
     cudaEvent_t ev0, ev1;
+    cudaEvent_t ev_sym[3]; /* symbols of plane i are in pinned memory */
 #endif
 };
 
@@ -202,6 +206,9 @@ dsvcu_ctx_create(dsvcu_ctx **out, int device, int width, int height, int subsamp
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
+    for (i = 0; i < 3; i++) {
+        CK(cudaEventCreateWithFlags(&c->ev_sym[i], cudaEventDisableTiming));
+    }
 #endif
     maxplane = (size_t) c->cw[0] * c->ch[0];
     if ((size_t) c->cw[1] * c->ch[1] > maxplane) maxplane = (size_t) c->cw[1] * c->ch[1];
@@ -220,6 +227,9 @@ dsvcu_ctx_create(dsvcu_ctx **out, int device, int width, int height, int subsamp
     CK(dsvcu_malloc(&c->d_progress, (size_t) c->progress_cap * sizeof(int)));
     CK(dsvcu_malloc(&c->d_me, 16 * sizeof(int)));
     CK(dsvcu_malloc_host(&c->h_me, 16 * sizeof(int)));
+    CK(dsvcu_malloc(&c->d_lavg, 4 * sizeof(int)));
+    CK(dsvcu_malloc_host(&c->h_lavg, 4 * sizeof(int)));
+    *c->h_lavg = 255;
     *out = c;
     return 0;
 }
@@ -252,12 +262,35 @@ dsvcu_ctx_destroy(dsvcu_ctx *c)
     if (c->d_prev_mvf) dsvcu_free_dev(c->d_prev_mvf);
     dsvcu_free_dev(c->d_me);
     dsvcu_free_host(c->h_me);
+    dsvcu_free_dev(c->d_lavg);
+    dsvcu_free_host(c->h_lavg);
+    if (c->h_mvs) dsvcu_free_host(c->h_mvs);
 #ifndef DSVCU_EMU
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    for (i = 0; i < 3; i++) cudaEventDestroy(c->ev_sym[i]);
     cudaStreamDestroy(c->stream);
 #endif
     free(c);
+}
+
+extern "C" void *
+dsvcu_host_alloc(size_t bytes)
+{
+    void *p = NULL;
+    if (dsvcu_malloc_host(&p, bytes ? bytes : 1)) {
+#ifndef DSVCU_EMU
+        cudaGetLastError();
+#endif
+        return NULL;
+    }
+    return p;
+}
+
+extern "C" void
+dsvcu_host_free(void *p)
+{
+    if (p) dsvcu_free_host(p);
 }
 
 extern "C" void *
@@ -779,7 +812,7 @@ dsvcu_quant_plane(dsvcu_ctx *c, dsvcu_coefs *k, int plane, int q, const dsvcu_fm
 
     total = dsvcu_scan_layout(w, h, part);
     /* the DC coefficient is sent raw */
-    CK(dsvcu_d2d_async(c->d_meta + 3 + plane, k->data[plane], sizeof(int), c->stream));
+    CK(dsvcu_d2h_async(c->h_meta + 3 + plane, k->data[plane], sizeof(int), c->stream));
     quant_level_geom(&Q, c, k, plane, qf, fm, -1, part);
     Q.qv = c->d_qv;
     DSVCU_LAUNCH(k_quant_ll, grid_for(Q.w * Q.h, 256), 256, 0, c->stream, Q, fm->lossless ? 1 : lfquant(qf, plane, fm));
@@ -797,10 +830,17 @@ dsvcu_quant_plane(dsvcu_ctx *c, dsvcu_coefs *k, int plane, int q, const dsvcu_fm
     nchunks = (total + CMP_CHUNK - 1) / CMP_CHUNK;
     DSVCU_LAUNCH(k_compact_count, nchunks, CMP_THREADS, 0, c->stream, c->d_qv, total, c->d_chunk);
     CK_LAUNCH(c);
-    DSVCU_LAUNCH(k_compact_scan, 1, 1024, 0, c->stream, c->d_chunk, nchunks, c->d_meta + plane);
+    /* the symbol count and the ordered (position, value) list are written by
+     * the kernels straight into pinned host memory (unified addressing): the
+     * host entropy coder needs nothing else from this plane, so one event is
+     * all it waits for while the GPU carries on with the inverse transform */
+    DSVCU_LAUNCH(k_compact_scan, 1, 1024, 0, c->stream, c->d_chunk, nchunks, c->h_meta + plane);
     CK_LAUNCH(c);
-    DSVCU_LAUNCH(k_compact_scatter, nchunks, CMP_THREADS, 0, c->stream, c->d_qv, total, c->d_chunk, c->d_syms[plane]);
+    DSVCU_LAUNCH(k_compact_scatter, nchunks, CMP_THREADS, 0, c->stream, c->d_qv, total, c->d_chunk, c->h_syms[plane]);
     CK_LAUNCH(c);
+#ifndef DSVCU_EMU
+    CK(cudaEventRecord(c->ev_sym[plane], c->stream));
+#endif
     return 0;
 }
 
@@ -808,13 +848,10 @@ extern "C" int
 dsvcu_fetch_symbols(dsvcu_ctx *c, int plane, const dsvcu_symbol **syms, int *nsyms, int *dc)
 {
     int n;
-    CK(dsvcu_d2h_async(c->h_meta, c->d_meta, 6 * sizeof(int), c->stream));
-    CK(dsvcu_stream_sync(c->stream));
+#ifndef DSVCU_EMU
+    CK(cudaEventSynchronize(c->ev_sym[plane]));
+#endif
     n = c->h_meta[plane];
-    if (n > 0) {
-        CK(dsvcu_d2h_async(c->h_syms[plane], c->d_syms[plane], (size_t) n * sizeof(dsvcu_sym), c->stream));
-        CK(dsvcu_stream_sync(c->stream));
-    }
     *syms = (const dsvcu_symbol *) c->h_syms[plane];
     *nsyms = n;
     *dc = c->h_meta[3 + plane];
@@ -1247,8 +1284,26 @@ dsvcu_hme(dsvcu_ctx *c, const dsvcu_fmeta *fm, const dsvcu_hme_params *hp, dsvcu
             CK_LAUNCH(c);
         }
     }
-    /* this picture's field is the next picture's temporal predictor */
-    CK(dsvcu_d2d_async(c->d_prev_mvf, c->d_mvs, (size_t) nblk * sizeof(dsvcu_mv), c->stream));
+    return 0;
+}
+
+extern "C" int
+dsvcu_mvs_to_prev(dsvcu_ctx *c, int nblocks)
+{
+    if (ensure_mvf(c, nblocks)) return -1;
+    CK(dsvcu_d2d_async(c->d_prev_mvf, c->d_mvs, (size_t) nblocks * sizeof(dsvcu_mv), c->stream));
+    return 0;
+}
+
+/* pinned mirror for block arrays read back by the host */
+static int
+ensure_hmvs(dsvcu_ctx *c, int nblk)
+{
+    if (nblk <= c->h_mvs_cap) return 0;
+    if (c->h_mvs) dsvcu_free_host(c->h_mvs);
+    c->h_mvs = NULL;
+    CK(dsvcu_malloc_host(&c->h_mvs, ((size_t) nblk + 4) * sizeof(dsvcu_mv)));
+    c->h_mvs_cap = nblk;
     return 0;
 }
 
@@ -1256,9 +1311,11 @@ extern "C" int
 dsvcu_hme_fetch(dsvcu_ctx *c, void *mvs_out, int nblocks, int *intra_pct, int *scene_change_blocks, int *avg_err)
 {
     int elig;
+    if (ensure_hmvs(c, nblocks)) return -1;
     CK(dsvcu_d2h_async(c->h_me, c->d_me, 16 * sizeof(int), c->stream));
-    CK(dsvcu_d2h_async(mvs_out, c->d_mvs, (size_t) nblocks * sizeof(dsvcu_mv), c->stream));
+    CK(dsvcu_d2h_async(c->h_mvs, c->d_mvs, (size_t) nblocks * sizeof(dsvcu_mv), c->stream));
     CK(dsvcu_stream_sync(c->stream));
+    memcpy(mvs_out, c->h_mvs, (size_t) nblocks * sizeof(dsvcu_mv));
     elig = c->h_me[4] ? c->h_me[4] : 1;
     *intra_pct = (c->h_me[2] * 100) / nblocks;
     *scene_change_blocks = c->h_me[3] * 100 / elig;
@@ -1267,11 +1324,11 @@ dsvcu_hme_fetch(dsvcu_ctx *c, void *mvs_out, int nblocks, int *intra_pct, int *s
 }
 
 extern "C" int
-dsvcu_intra_analysis(dsvcu_ctx *c, const dsvcu_fmeta *fm, dsvcu_frame *src, void *mvs_out, int nblocks)
+dsvcu_intra_analysis_async(dsvcu_ctx *c, const dsvcu_fmeta *fm, dsvcu_frame *src, int nblocks)
 {
     IaArgs A;
     int ctas;
-    if (ensure_mvf(c, nblocks)) return -1;
+    if (ensure_mvf(c, nblocks) || ensure_hmvs(c, nblocks)) return -1;
     memset(&A, 0, sizeof(A));
     me_plane(&A.src[0], src, 0);
     me_plane(&A.src[1], src, 1);
@@ -1289,9 +1346,23 @@ dsvcu_intra_analysis(dsvcu_ctx *c, const dsvcu_fmeta *fm, dsvcu_frame *src, void
     if (ctas > 148 * 8) ctas = 148 * 8;
     DSVCU_LAUNCH(k_intra_analysis, ctas, ME_WARPS_PER_CTA * 32, 0, c->stream, A);
     CK_LAUNCH(c);
-    CK(dsvcu_d2h_async(mvs_out, A.out, (size_t) nblocks * sizeof(dsvcu_mv), c->stream));
-    CK(dsvcu_stream_sync(c->stream));
+    CK(dsvcu_d2h_async(c->h_mvs, A.out, (size_t) nblocks * sizeof(dsvcu_mv), c->stream));
     return 0;
+}
+
+extern "C" int
+dsvcu_intra_analysis_fetch(dsvcu_ctx *c, void *mvs_out, int nblocks)
+{
+    CK(dsvcu_stream_sync(c->stream));
+    memcpy(mvs_out, c->h_mvs, (size_t) nblocks * sizeof(dsvcu_mv));
+    return 0;
+}
+
+extern "C" int
+dsvcu_intra_analysis(dsvcu_ctx *c, const dsvcu_fmeta *fm, dsvcu_frame *src, void *mvs_out, int nblocks)
+{
+    if (dsvcu_intra_analysis_async(c, fm, src, nblocks)) return -1;
+    return dsvcu_intra_analysis_fetch(c, mvs_out, nblocks);
 }
 
 /* frame_luma_avg (dsv_encoder.c:108-127): sum over rows of (row sum / w), / h */
@@ -1313,12 +1384,25 @@ k_luma_avg(const uint8_t *data, int stride, int w, int h, int *out)
 }
 
 extern "C" int
+dsvcu_frame_luma_avg_async(dsvcu_ctx *c, dsvcu_frame *f)
+{
+    DSVCU_LAUNCH(k_luma_avg, 1, 256, 0, c->stream, f->p[0].data, f->p[0].stride, f->p[0].w, f->p[0].h, c->d_lavg);
+    CK_LAUNCH(c);
+    CK(dsvcu_d2h_async(c->h_lavg, c->d_lavg, sizeof(int), c->stream));
+    return 0;
+}
+
+extern "C" unsigned
+dsvcu_frame_luma_avg_result(dsvcu_ctx *c)
+{
+    return (unsigned) *c->h_lavg;
+}
+
+extern "C" int
 dsvcu_frame_luma_avg(dsvcu_ctx *c, dsvcu_frame *f, unsigned *avg)
 {
-    DSVCU_LAUNCH(k_luma_avg, 1, 256, 0, c->stream, f->p[0].data, f->p[0].stride, f->p[0].w, f->p[0].h, c->d_me + 6);
-    CK_LAUNCH(c);
-    CK(dsvcu_d2h_async(c->h_me + 6, c->d_me + 6, sizeof(int), c->stream));
+    if (dsvcu_frame_luma_avg_async(c, f)) return -1;
     CK(dsvcu_stream_sync(c->stream));
-    *avg = (unsigned) c->h_me[6];
+    *avg = dsvcu_frame_luma_avg_result(c);
     return 0;
 }

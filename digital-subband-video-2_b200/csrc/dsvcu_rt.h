@@ -50,8 +50,9 @@ typedef cudaEvent_t dsvcu_event_t;
 #define dsvcu_h2d_async(d, h, n, s) cudaMemcpyAsync((d), (h), (n), cudaMemcpyHostToDevice, (s))
 #define dsvcu_d2h_async(h, d, n, s) cudaMemcpyAsync((h), (d), (n), cudaMemcpyDeviceToHost, (s))
 #define dsvcu_d2d_async(d, s0, n, s) cudaMemcpyAsync((d), (s0), (n), cudaMemcpyDeviceToDevice, (s))
-#define dsvcu_h2d_2d_async(d, dp, h, hp, w, ht, s) cudaMemcpy2DAsync((d), (dp), (h), (hp), (w), (ht), cudaMemcpyHostToDevice, (s))
-#define dsvcu_d2h_2d_async(h, hp, d, dp, w, ht, s) cudaMemcpy2DAsync((h), (hp), (d), (dp), (w), (ht), cudaMemcpyDeviceToHost, (s))
+/* frame upload / download: the far side may be host OR device memory (unified addressing) */
+#define dsvcu_h2d_2d_async(d, dp, h, hp, w, ht, s) cudaMemcpy2DAsync((d), (dp), (h), (hp), (w), (ht), cudaMemcpyDefault, (s))
+#define dsvcu_d2h_2d_async(h, hp, d, dp, w, ht, s) cudaMemcpy2DAsync((h), (hp), (d), (dp), (w), (ht), cudaMemcpyDefault, (s))
 #define dsvcu_d2d_2d_async(d, dp, s0, sp, w, ht, s) cudaMemcpy2DAsync((d), (dp), (s0), (sp), (w), (ht), cudaMemcpyDeviceToDevice, (s))
 #define dsvcu_stream_sync(s) cudaStreamSynchronize(s)
 #define dsvcu_memset_2d_async(p, pitch, v, w, h, s) cudaMemset2DAsync((p), (pitch), (v), (w), (h), (s))

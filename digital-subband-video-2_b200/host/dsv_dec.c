@@ -31,11 +31,17 @@ typedef struct {
     int nblk_cap;
 } DEC_STATE;
 
-static int
-env_device(void)
+int dsv_get_thread_device(void);
+
+/* set by the whole-stream drivers (dsv_pipe.c): the next decoded picture of
+ * this thread is copied device -> dst directly (tightly packed planes) instead
+ * of into a freshly allocated host frame */
+static __thread uint8_t *tls_direct_out = NULL;
+
+void
+dsv_dec_direct_output(uint8_t *dst)
 {
-    const char *e = getenv("DSV_CUDA_DEVICE");
-    return e ? atoi(e) : 0;
+    tls_direct_out = dst;
 }
 
 static void
@@ -78,7 +84,7 @@ state_get(DSV_DECODER *d)
     s->w = m->width;
     s->h = m->height;
     s->subsamp = m->subsamp;
-    if (dsvcu_ctx_create(&s->ctx, env_device(), m->width, m->height, m->subsamp) ||
+    if (dsvcu_ctx_create(&s->ctx, dsv_get_thread_device(), m->width, m->height, m->subsamp) ||
         dsvcu_coefs_create(s->ctx, &s->coefs) || dsvcu_frame_create(s->ctx, &s->resd) ||
         dsvcu_frame_create(s->ctx, &s->pic[0]) || dsvcu_frame_create(s->ctx, &s->pic[1])) {
         DSV_ERROR(("GPU decoder state: %s", dsvcu_last_error()));
@@ -388,7 +394,11 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
         GPU(dsvcu_extend_frame(s->ctx, dst, 0));
     }
 
-    host = dsv_mk_frame(meta->subsamp, meta->width, meta->height, 0);
+    if (tls_direct_out) {
+        host = dsv_load_planar_frame(meta->subsamp, tls_direct_out, meta->width, meta->height);
+    } else {
+        host = dsv_mk_frame(meta->subsamp, meta->width, meta->height, 0);
+    }
     for (i = 0; i < 3; i++) {
         GPU(dsvcu_frame_download(s->ctx, dst, i, host->planes[i].data, host->planes[i].stride));
     }

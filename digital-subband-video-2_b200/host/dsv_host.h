@@ -113,6 +113,7 @@ void dsv_neighbordif2(DSV_MV *vecs, DSV_PARAMS *p, int x, int y, int *dx, int *d
 int dsv_neighbordif(DSV_MV *vecs, DSV_PARAMS *p, int x, int y);
 int dsv_mv_cost(DSV_MV *vecs, DSV_PARAMS *p, int i, int j, int mx, int my, int q, int sqr);
 int dsv_lb2(unsigned n);
+int dsv_spatial_psy_factor(DSV_PARAMS *p, int subband);
 
 /* ---- misc host helpers ---- */
 void dsv_host_copy_planes(DSV_FRAME *dst, DSV_FRAME *src);

@@ -111,6 +111,31 @@ dsv_mv_cost(DSV_MV *vecs, DSV_PARAMS *p, int i, int j, int mx, int my, int q, in
     return sqr ? bits * bits : bits;
 }
 
+/* resolution-dependent perceptual scale, 0 at CIF .. 128 at 1080p
+ * (reference dsv_spatial_psy_factor, hzcc.c:66-86) */
+int
+dsv_spatial_psy_factor(DSV_PARAMS *p, int subband)
+{
+    int lo, hi, cur;
+    int cif_h = DSV_UDIV_ROUND_UP(352, p->blk_w), cif_v = DSV_UDIV_ROUND_UP(288, p->blk_h);
+    int fhd_h = DSV_UDIV_ROUND_UP(1920, p->blk_w), fhd_v = DSV_UDIV_ROUND_UP(1080, p->blk_h);
+    if (subband == 1) {
+        lo = cif_h;
+        hi = fhd_h;
+        cur = p->nblocks_h;
+    } else if (subband == 2) {
+        lo = cif_v;
+        hi = fhd_v;
+        cur = p->nblocks_v;
+    } else {
+        lo = cif_h * cif_v;
+        hi = fhd_h * fhd_v;
+        cur = p->nblocks_h * p->nblocks_v;
+    }
+    cur = MAX(0, cur - lo);
+    return (cur << 7) / (hi - lo);
+}
+
 void
 dsv_fmeta_from_params(dsvcu_fmeta *fm, const DSV_PARAMS *p, int isP, unsigned fnum)
 {

@@ -1,0 +1,647 @@
+/*
+ * dsv_pipe.c -- whole-stream drivers (include/dsv_session.h).
+ *
+ * dsv_encode_buffer / dsv_decode_buffer do what one run of the reference CLI
+ * does (src/dsv_main.c:547-905, :959-1120) on memory buffers.  The sharded
+ * forms reproduce parallel_encode_yuv.sh (:31-52): independent closed-GOP
+ * chunks, each coded by a fresh encoder instance, concatenated in order.  The
+ * shell script forks processes; here a chunk is a job taken by one of a set of
+ * host threads, and each thread owns one CUDA context (stream, device frames)
+ * on one of the GPUs, so several chunks are in flight per GPU and their kernels
+ * overlap.  There is no exchange between chunks, hence no collective.
+ */
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include "dsv_host.h"
+#include "../../include/dsv_encoder.h"
+#include "../../include/dsv_decoder.h"
+#include "../../include/dsv_session.h"
+
+/* internal hooks of dsv_enc.c / dsv_dec.c */
+void dsv_enc_recycle(DSV_ENCODER *from, DSV_ENCODER *to);
+void dsv_dec_direct_output(uint8_t *dst);
+
+static __thread int tls_device = -1;
+
+void
+dsv_set_thread_device(int device)
+{
+    tls_device = device;
+}
+
+int
+dsv_get_thread_device(void)
+{
+    if (tls_device < 0) {
+        const char *e = getenv("DSV_CUDA_DEVICE");
+        return e ? atoi(e) : 0;
+    }
+    return tls_device;
+}
+
+void *
+dsv_pinned_alloc(size_t bytes)
+{
+    return dsvcu_host_alloc(bytes);
+}
+
+void
+dsv_pinned_free(void *p)
+{
+    dsvcu_host_free(p);
+}
+
+void
+dsv_enc_opts_default(dsv_enc_opts *o, int w, int h, int fmt, int fps_num, int fps_den)
+{
+    memset(o, 0, sizeof(*o));
+    o->w = w;
+    o->h = h;
+    o->fmt = fmt;
+    o->fps_num = fps_num;
+    o->fps_den = fps_den;
+    o->aspect_num = o->aspect_den = 1;
+    o->qp = -1;
+    o->effort = DSV_MAX_EFFORT;
+    o->gop = -1;
+    o->rc_mode = DSV_RATE_CONTROL_CRF;
+    o->minqstep = DSV_USER_QUAL_TO_RC_QUAL(1) / 2;
+    o->maxqstep = DSV_USER_QUAL_TO_RC_QUAL(1) / 4;
+    o->minqp = o->maxqp = o->iminqp = -1;
+    o->scd = 1;
+    o->tempaq = 1;
+    o->bszx = o->bszy = -1;
+    o->scpct = 85;
+    o->varint = 1;
+    o->psy = DSV_PSY_ALL;
+    o->dib = 1;
+    o->ifilter = 1;
+    o->pfilter = -1;
+    o->psharp = 1;
+    o->ipct = 90;
+}
+
+/* heuristic bytes/s for a quality percent (reference util.c:21-57) */
+static unsigned
+guess_bitrate(int quality, int gop, const DSV_META *md)
+{
+    int fps = (md->fps_num + md->fps_den / 2) / md->fps_den;
+    int bpf, scale;
+    switch (md->subsamp) {
+        case DSV_SUBSAMP_422:
+        case DSV_SUBSAMP_UYVY: bpf = 352 * 288 * 2; break;
+        case DSV_SUBSAMP_420:
+        case DSV_SUBSAMP_411: bpf = 352 * 288 * 3 / 2; break;
+        case DSV_SUBSAMP_410: bpf = 352 * 288 * 9 / 8; break;
+        default: bpf = 352 * 288 * 3; break;
+    }
+    if (gop == DSV_GOP_INTRA) {
+        bpf *= 4;
+    }
+    if (md->width < 320 && md->height < 240) {
+        bpf /= 4;
+    }
+    scale = (((md->width + md->height) / 2) << 8) / 352;
+    bpf = bpf * scale >> 8;
+    return (unsigned) ((bpf * fps) / (26 - quality / 4)) * 3 / 2;
+}
+
+static int
+guess_quality(int bps, int gop, const DSV_META *md) /* util.c:59-76 */
+{
+    int q, bestq = 50, best = INT_MAX;
+    for (q = 0; q < 100; q++) {
+        int dif = abs((int) guess_bitrate(q, gop, md) - bps);
+        if (dif < best) {
+            bestq = q;
+            best = dif;
+        }
+    }
+    return CLAMP(bestq, 0, 99);
+}
+
+static int
+pct_or_auto(int pct)
+{
+    return pct < 0 ? -1 : DSV_USER_QUAL_TO_RC_QUAL(pct);
+}
+
+/* option table -> encoder configuration, as the CLI does it
+ * (reference dsv_main.c:573-723) */
+static void
+configure_encoder(DSV_ENCODER *enc, const dsv_enc_opts *o)
+{
+    DSV_META md;
+    int fps, bps;
+
+    dsv_enc_init(enc);
+    memset(&md, 0, sizeof(md));
+    md.width = o->w;
+    md.height = o->h;
+    md.subsamp = o->fmt;
+    md.fps_num = o->fps_num;
+    md.fps_den = o->fps_den > 0 ? o->fps_den : 1;
+    md.aspect_num = o->aspect_num;
+    md.aspect_den = o->aspect_den;
+    md.inter_sharpen = o->psharp;
+    fps = (md.fps_num + md.fps_den / 2) / md.fps_den;
+    if (fps <= 0) {
+        md.fps_num = md.fps_den = 1;
+        fps = 1;
+    }
+    dsv_enc_set_metadata(enc, &md);
+
+    enc->gop = o->gop < 0 ? fps : o->gop;
+    enc->scene_change_pct = o->scpct;
+    enc->do_scd = o->scd;
+    enc->intra_pct_thresh = o->ipct;
+    enc->skip_block_thresh = o->skipthresh;
+    enc->rc_mode = o->rc_mode;
+    enc->rc_pergop = o->rc_pergop;
+    bps = o->kbps * 1024;
+    if (o->qp < 0) {
+        int pct = (enc->rc_mode != DSV_RATE_CONTROL_ABR || bps == 0) ? 85 : guess_quality(bps, enc->gop, &md);
+        enc->quality = DSV_USER_QUAL_TO_RC_QUAL(pct);
+    } else {
+        enc->quality = DSV_USER_QUAL_TO_RC_QUAL(o->qp);
+    }
+    enc->bitrate = bps ? (unsigned) bps : guess_bitrate(enc->quality * 100 / DSV_RC_QUAL_MAX, enc->gop, &md);
+    enc->min_q_step = o->minqstep;
+    enc->max_q_step = o->maxqstep;
+    enc->min_quality = pct_or_auto(o->minqp);
+    enc->max_quality = pct_or_auto(o->maxqp);
+    enc->min_I_frame_quality = pct_or_auto(o->iminqp);
+    if (enc->rc_mode == DSV_RATE_CONTROL_CRF) {
+        if (enc->min_quality < 0) enc->min_quality = enc->quality - DSV_USER_QUAL_TO_RC_QUAL(5);
+        if (enc->min_I_frame_quality < 0) enc->min_I_frame_quality = enc->quality - DSV_USER_QUAL_TO_RC_QUAL(2);
+    } else {
+        if (enc->min_quality < 0) enc->min_quality = 0;
+        if (enc->min_I_frame_quality < 0) enc->min_I_frame_quality = DSV_USER_QUAL_TO_RC_QUAL(5);
+    }
+    if (enc->max_quality < 0) {
+        enc->max_quality = DSV_RC_QUAL_MAX;
+    }
+    enc->min_quality = CLAMP(enc->min_quality, 0, DSV_RC_QUAL_MAX);
+    enc->min_I_frame_quality = CLAMP(enc->min_I_frame_quality, 0, DSV_RC_QUAL_MAX);
+    enc->max_quality = CLAMP(enc->max_quality, 0, DSV_RC_QUAL_MAX);
+    enc->pyramid_levels = o->pyrlevels;
+    enc->stable_refresh = o->stabref ? (unsigned) o->stabref : (unsigned) CLAMP(fps, 1, 60);
+    enc->do_temporal_aq = o->tempaq;
+    enc->variable_i_interval = o->varint;
+    enc->block_size_override_x = o->bszx;
+    enc->block_size_override_y = o->bszy;
+    enc->effort = o->effort;
+    enc->do_psy = o->psy;
+    enc->do_dark_intra_boost = o->dib;
+    enc->do_intra_filter = o->ifilter;
+    enc->do_inter_filter = o->pfilter;
+}
+
+static size_t
+frame_bytes(int w, int h, int fmt)
+{
+    size_t cw = (size_t) DSV_ROUND_SHIFT(w, DSV_FORMAT_H_SHIFT(fmt));
+    size_t ch = (size_t) DSV_ROUND_SHIFT(h, DSV_FORMAT_V_SHIFT(fmt));
+    return (size_t) w * h + 2 * cw * ch;
+}
+
+typedef struct {
+    uint8_t *data;
+    size_t len, cap;
+} BYTES;
+
+static int
+bytes_append(BYTES *b, const uint8_t *p, size_t n)
+{
+    if (b->len + n > b->cap) {
+        size_t ncap = b->cap ? b->cap * 2 : (1 << 16);
+        uint8_t *nd;
+        while (ncap < b->len + n) {
+            ncap *= 2;
+        }
+        nd = realloc(b->data, ncap);
+        if (!nd) {
+            return -1;
+        }
+        b->data = nd;
+        b->cap = ncap;
+    }
+    memcpy(b->data + b->len, p, n);
+    b->len += n;
+    return 0;
+}
+
+/* one encoder instance over `nframes` pictures -> `out` (appended) */
+static int
+run_encoder(DSV_ENCODER *enc, const dsv_enc_opts *o, const uint8_t *yuv, int nframes, int write_eos, BYTES *out)
+{
+    size_t fsz = frame_bytes(o->w, o->h, o->fmt);
+    DSV_BUF bufs[4];
+    int f, i, n;
+
+    dsv_enc_start(enc);
+    for (f = 0; f < nframes; f++) {
+        DSV_FRAME *fr = dsv_load_planar_frame(o->fmt, (void *) (yuv + (size_t) f * fsz), o->w, o->h);
+        n = dsv_enc(enc, fr, bufs) & DSV_ENC_NUM_BUFS;
+        if (n == 0) {
+            return -1;
+        }
+        for (i = 0; i < n; i++) {
+            int r = bytes_append(out, bufs[i].data, bufs[i].len);
+            dsv_buf_free(&bufs[i]);
+            if (r) {
+                return -1;
+            }
+        }
+    }
+    if (write_eos) {
+        dsv_enc_end_of_stream(enc, bufs);
+        bytes_append(out, bufs[0].data, bufs[0].len);
+        dsv_buf_free(&bufs[0]);
+    }
+    return 0;
+}
+
+int
+dsv_encode_buffer(const dsv_enc_opts *o, const uint8_t *yuv, int nframes, int exhausted, uint8_t **out, size_t *out_len)
+{
+    DSV_ENCODER enc;
+    BYTES b;
+    int r;
+    memset(&b, 0, sizeof(b));
+    configure_encoder(&enc, o);
+    r = run_encoder(&enc, o, yuv, nframes, !o->noeos || (exhausted && nframes > 0), &b);
+    dsv_enc_free(&enc);
+    if (r) {
+        free(b.data);
+        return -1;
+    }
+    *out = b.data;
+    *out_len = b.len;
+    return 0;
+}
+
+/* ----------------------------------------------------------- sharded encode */
+
+typedef struct {
+    const dsv_enc_opts *o;
+    const uint8_t *yuv;
+    int nframes, chunk, nchunks;
+    int next; /* next chunk to take */
+    pthread_mutex_t lock;
+    BYTES *parts;
+    int failed;
+} ENC_JOB;
+
+typedef struct {
+    ENC_JOB *job;
+    int device;
+} WORKER;
+
+static int
+take(int *next, int limit, pthread_mutex_t *lock)
+{
+    int k;
+    pthread_mutex_lock(lock);
+    k = (*next < limit) ? (*next)++ : -1;
+    pthread_mutex_unlock(lock);
+    return k;
+}
+
+static void *
+encode_worker(void *arg)
+{
+    WORKER *w = arg;
+    ENC_JOB *j = w->job;
+    DSV_ENCODER enc, prev;
+    size_t fsz = frame_bytes(j->o->w, j->o->h, j->o->fmt);
+    int k, have_prev = 0;
+
+    dsv_set_thread_device(w->device);
+    while ((k = take(&j->next, j->nchunks, &j->lock)) >= 0) {
+        int first = k * j->chunk;
+        int n = MIN(j->chunk, j->nframes - first);
+        /* a fresh encoder per chunk (frame numbers, rate control and block
+         * statistics restart), but the device buffers are handed over */
+        configure_encoder(&enc, j->o);
+        if (have_prev) {
+            dsv_enc_recycle(&prev, &enc);
+            dsv_enc_free(&prev);
+        }
+        if (run_encoder(&enc, j->o, j->yuv + (size_t) first * fsz, n, 0, &j->parts[k])) {
+            j->failed = 1;
+        }
+        prev = enc;
+        have_prev = 1;
+    }
+    if (have_prev) {
+        dsv_enc_free(&prev);
+    }
+    return NULL;
+}
+
+int
+dsv_encode_sharded(const dsv_enc_opts *o, const uint8_t *yuv, int nframes, int chunk, int nthreads, const int *devices,
+                   int ndevices, uint8_t **out, size_t *out_len)
+{
+    ENC_JOB job;
+    pthread_t *th;
+    WORKER *wk;
+    size_t total = 0, off = 0;
+    int i, started = 0;
+
+    if (chunk <= 0 || nframes <= 0 || nthreads <= 0 || ndevices <= 0) {
+        return -1;
+    }
+    memset(&job, 0, sizeof(job));
+    job.o = o;
+    job.yuv = yuv;
+    job.nframes = nframes;
+    job.chunk = chunk;
+    job.nchunks = (nframes + chunk - 1) / chunk;
+    job.parts = calloc((size_t) job.nchunks, sizeof(BYTES));
+    pthread_mutex_init(&job.lock, NULL);
+    nthreads = MIN(nthreads, job.nchunks);
+    th = calloc((size_t) nthreads, sizeof(*th));
+    wk = calloc((size_t) nthreads, sizeof(*wk));
+    for (i = 0; i < nthreads; i++) {
+        wk[i].job = &job;
+        wk[i].device = devices ? devices[i % ndevices] : i % ndevices;
+        if (pthread_create(&th[i], NULL, encode_worker, &wk[i])) {
+            job.failed = 1;
+            break;
+        }
+        started++;
+    }
+    for (i = 0; i < started; i++) {
+        pthread_join(th[i], NULL);
+    }
+    for (i = 0; i < job.nchunks; i++) {
+        total += job.parts[i].len;
+    }
+    *out = NULL;
+    *out_len = 0;
+    if (!job.failed) {
+        *out = malloc(total ? total : 1);
+        for (i = 0; i < job.nchunks; i++) {
+            memcpy(*out + off, job.parts[i].data, job.parts[i].len);
+            off += job.parts[i].len;
+        }
+        *out_len = total;
+    }
+    for (i = 0; i < job.nchunks; i++) {
+        free(job.parts[i].data);
+    }
+    free(job.parts);
+    free(th);
+    free(wk);
+    pthread_mutex_destroy(&job.lock);
+    return job.failed ? -1 : 0;
+}
+
+/* ------------------------------------------------------------------ decode */
+
+typedef struct {
+    size_t off, len; /* packet position in the stream */
+    int type;
+} PKT;
+
+/* walk the packet chain by the next-link field (reference dsv_main.c:912-957) */
+static int
+index_packets(const uint8_t *d, size_t len, PKT **out)
+{
+    PKT *v = NULL;
+    int n = 0, cap = 0;
+    size_t off = 0;
+    while (off + DSV_PACKET_HDR_SIZE <= len) {
+        const uint8_t *p = d + off;
+        size_t size;
+        if (p[0] != DSV_FOURCC_0 || p[1] != DSV_FOURCC_1 || p[2] != DSV_FOURCC_2 || p[3] != DSV_FOURCC_3) {
+            break;
+        }
+        size = ((size_t) p[10] << 24) | ((size_t) p[11] << 16) | ((size_t) p[12] << 8) | p[13];
+        if (size == 0) {
+            size = DSV_PACKET_HDR_SIZE; /* EOS */
+        }
+        if (size < DSV_PACKET_HDR_SIZE || off + size > len) {
+            break;
+        }
+        if (n == cap) {
+            cap = cap ? cap * 2 : 256;
+            v = realloc(v, (size_t) cap * sizeof(PKT));
+        }
+        v[n].off = off;
+        v[n].len = size;
+        v[n].type = p[DSV_PACKET_TYPE_OFFSET];
+        n++;
+        off += size;
+    }
+    *out = v;
+    return n;
+}
+
+/* metadata of a stream = its first metadata packet, parsed by the decoder */
+static int
+probe_meta(const uint8_t *d, const PKT *pk, int npk, DSV_META *meta)
+{
+    DSV_DECODER dec;
+    int i;
+    memset(&dec, 0, sizeof(dec));
+    for (i = 0; i < npk; i++) {
+        if (pk[i].type == DSV_PT_META) {
+            DSV_BUF b;
+            DSV_FRAME *fr;
+            DSV_FNUM fn;
+            dsv_mk_buf(&b, (int) pk[i].len);
+            memcpy(b.data, d + pk[i].off, pk[i].len);
+            if (dsv_dec(&dec, &b, &fr, &fn) == DSV_DEC_GOT_META) {
+                *meta = dec.vidmeta;
+                return 0;
+            }
+        }
+    }
+    return -1;
+}
+
+/* decode packets [first, last) with `dec`; frames are written to dst one after
+ * the other.  returns the number of frames written */
+static int
+decode_range(DSV_DECODER *dec, const uint8_t *d, const PKT *pk, int first, int last, uint8_t *dst, size_t fsz)
+{
+    int i, nfr = 0;
+    for (i = first; i < last; i++) {
+        DSV_BUF b;
+        DSV_FRAME *fr = NULL;
+        DSV_FNUM fn;
+        int code;
+        dsv_mk_buf(&b, (int) pk[i].len);
+        memcpy(b.data, d + pk[i].off, pk[i].len);
+        if (DSV_PT_IS_PIC(pk[i].type)) {
+            dsv_dec_direct_output(dst + (size_t) nfr * fsz);
+        }
+        code = dsv_dec(dec, &b, &fr, &fn);
+        dsv_dec_direct_output(NULL);
+        if (code == DSV_DEC_EOS) {
+            break;
+        }
+        if (code == DSV_DEC_OK && fr) {
+            nfr++;
+            dsv_frame_ref_dec(fr);
+        }
+    }
+    return nfr;
+}
+
+static int
+count_pictures(const PKT *pk, int first, int last)
+{
+    int i, n = 0;
+    for (i = first; i < last; i++) {
+        n += !!DSV_PT_IS_PIC(pk[i].type);
+    }
+    return n;
+}
+
+int
+dsv_decode_buffer(const uint8_t *dsv, size_t len, int pinned, uint8_t **yuv, size_t *yuv_len, int *nframes, DSV_META *meta)
+{
+    return dsv_decode_sharded(dsv, len, 1, NULL, 1, pinned, yuv, yuv_len, nframes, meta);
+}
+
+typedef struct {
+    const uint8_t *d;
+    const PKT *pk;
+    int *seg_first, *seg_last, *seg_frame0; /* per segment */
+    int nseg, next;
+    pthread_mutex_t lock;
+    uint8_t *dst;
+    size_t fsz;
+    int *seg_done; /* frames actually decoded per segment */
+} DEC_JOB;
+
+typedef struct {
+    DEC_JOB *job;
+    int device;
+} DWORKER;
+
+static void *
+decode_worker(void *arg)
+{
+    DWORKER *w = arg;
+    DEC_JOB *j = w->job;
+    DSV_DECODER dec;
+    int k;
+    memset(&dec, 0, sizeof(dec));
+    dsv_set_thread_device(w->device);
+    while ((k = take(&j->next, j->nseg, &j->lock)) >= 0) {
+        j->seg_done[k] = decode_range(&dec, j->d, j->pk, j->seg_first[k], j->seg_last[k],
+                                      j->dst + (size_t) j->seg_frame0[k] * j->fsz, j->fsz);
+    }
+    dsv_dec_free(&dec);
+    return NULL;
+}
+
+int
+dsv_decode_sharded(const uint8_t *dsv, size_t len, int nthreads, const int *devices, int ndevices, int pinned,
+                   uint8_t **yuv, size_t *yuv_len, int *nframes, DSV_META *meta)
+{
+    PKT *pk = NULL;
+    DEC_JOB job;
+    DSV_META md;
+    pthread_t *th;
+    DWORKER *wk;
+    int npk, i, nseg = 0, total, started = 0, ok = 1;
+
+    *yuv = NULL;
+    *yuv_len = 0;
+    *nframes = 0;
+    npk = index_packets(dsv, len, &pk);
+    if (npk <= 0 || probe_meta(dsv, pk, npk, &md)) {
+        free(pk);
+        return -1;
+    }
+    if (meta) {
+        *meta = md;
+    }
+    memset(&job, 0, sizeof(job));
+    job.seg_first = calloc((size_t) npk + 1, sizeof(int));
+    job.seg_last = calloc((size_t) npk + 1, sizeof(int));
+    job.seg_frame0 = calloc((size_t) npk + 1, sizeof(int));
+    job.seg_done = calloc((size_t) npk + 1, sizeof(int));
+    /* a segment starts at every metadata packet: the picture that follows has
+     * no reference (closed GOP), so segments decode independently */
+    for (i = 0; i < npk; i++) {
+        if (pk[i].type == DSV_PT_META || nseg == 0) {
+            job.seg_first[nseg] = i;
+            if (nseg) {
+                job.seg_last[nseg - 1] = i;
+            }
+            nseg++;
+        }
+    }
+    job.seg_last[nseg - 1] = npk;
+    total = 0;
+    for (i = 0; i < nseg; i++) {
+        job.seg_frame0[i] = total;
+        total += count_pictures(pk, job.seg_first[i], job.seg_last[i]);
+    }
+    job.d = dsv;
+    job.pk = pk;
+    job.nseg = nseg;
+    job.fsz = frame_bytes(md.width, md.height, md.subsamp);
+    job.dst = pinned ? dsv_pinned_alloc(job.fsz * (size_t) MAX(total, 1)) : malloc(job.fsz * (size_t) MAX(total, 1));
+    pthread_mutex_init(&job.lock, NULL);
+    if (!job.dst) {
+        ok = 0;
+    }
+    nthreads = CLAMP(nthreads, 1, nseg);
+    if (ndevices <= 0) {
+        ndevices = 1;
+    }
+    th = calloc((size_t) nthreads, sizeof(*th));
+    wk = calloc((size_t) nthreads, sizeof(*wk));
+    if (ok && nthreads == 1) {
+        wk[0].job = &job;
+        wk[0].device = devices ? devices[0] : dsv_get_thread_device();
+        decode_worker(&wk[0]);
+    } else if (ok) {
+        for (i = 0; i < nthreads; i++) {
+            wk[i].job = &job;
+            wk[i].device = devices ? devices[i % ndevices] : i % ndevices;
+            if (pthread_create(&th[i], NULL, decode_worker, &wk[i])) {
+                ok = 0;
+                break;
+            }
+            started++;
+        }
+        for (i = 0; i < started; i++) {
+            pthread_join(th[i], NULL);
+        }
+    }
+    if (ok) {
+        /* frames of a damaged segment may be missing: close the gaps */
+        int outn = 0;
+        for (i = 0; i < nseg; i++) {
+            if (job.seg_done[i] > 0 && outn != job.seg_frame0[i]) {
+                memmove(job.dst + (size_t) outn * job.fsz, job.dst + (size_t) job.seg_frame0[i] * job.fsz,
+                        (size_t) job.seg_done[i] * job.fsz);
+            }
+            outn += job.seg_done[i];
+        }
+        *yuv = job.dst;
+        *yuv_len = (size_t) outn * job.fsz;
+        *nframes = outn;
+    } else if (job.dst) {
+        if (pinned) dsv_pinned_free(job.dst); else free(job.dst);
+    }
+    pthread_mutex_destroy(&job.lock);
+    free(job.seg_first);
+    free(job.seg_last);
+    free(job.seg_frame0);
+    free(job.seg_done);
+    free(th);
+    free(wk);
+    free(pk);
+    return ok ? 0 : -1;
+}

@@ -16,6 +16,7 @@
 #ifndef DSV2_B200_DSV_CUDA_H
 #define DSV2_B200_DSV_CUDA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -54,6 +55,10 @@ void dsvcu_ctx_destroy(dsvcu_ctx *ctx);
 /* the CUDA stream (cudaStream_t) all work of this context is issued on */
 void *dsvcu_ctx_stream(dsvcu_ctx *ctx);
 int dsvcu_sync(dsvcu_ctx *ctx);
+
+/* page-locked host memory (frame / stream staging); NULL on failure */
+void *dsvcu_host_alloc(size_t bytes);
+void dsvcu_host_free(void *p);
 
 /* ---- device objects ---- */
 /* frame with the stream geometry (3 planes) or a luma-only frame of w x h */
@@ -139,9 +144,10 @@ typedef struct {
     int use_prev_mvs;      /* DSV_HME.ref_mvf != NULL */
 } dsvcu_hme_params;
 
-/* the previous picture's final vector field (DSV_HME.ref_mvf).  dsvcu_hme keeps
- * its own result for the next call; this overrides it (tests / resync) */
+/* the previous picture's final vector field (DSV_HME.ref_mvf), from the host ... */
 int dsvcu_set_prev_mvs(dsvcu_ctx *ctx, const void *dsv_mv_array, int nblocks);
+/* ... or from the device's current MV array (after dsvcu_hme / dsvcu_set_mvs) */
+int dsvcu_mvs_to_prev(dsvcu_ctx *ctx, int nblocks);
 /* dsv_hme, reference hme.c:2001-2016 (struct DSV_HME, dsv_encoder.h:202-213).
  * Leaves the final field on the device as the current MV array (as if
  * dsvcu_set_mvs had been called with it). */
@@ -154,8 +160,14 @@ int dsvcu_hme_fetch(dsvcu_ctx *ctx, void *mvs_out, int nblocks, int *intra_pct, 
                     int *avg_err);
 /* dsv_intra_analysis, reference hme.c:1835-1971; result via dsvcu_hme_fetch-like copy */
 int dsvcu_intra_analysis(dsvcu_ctx *ctx, const dsvcu_fmeta *fm, dsvcu_frame *src, void *mvs_out, int nblocks);
+/* the same in two halves: queue the kernel + copy, then wait and read */
+int dsvcu_intra_analysis_async(dsvcu_ctx *ctx, const dsvcu_fmeta *fm, dsvcu_frame *src, int nblocks);
+int dsvcu_intra_analysis_fetch(dsvcu_ctx *ctx, void *mvs_out, int nblocks);
 /* frame_luma_avg, reference dsv_encoder.c:108-127 (sum of per-row averages / h); waits */
 int dsvcu_frame_luma_avg(dsvcu_ctx *ctx, dsvcu_frame *f, unsigned *avg);
+/* queued form; the result is valid after the next wait on the context's stream */
+int dsvcu_frame_luma_avg_async(dsvcu_ctx *ctx, dsvcu_frame *f);
+unsigned dsvcu_frame_luma_avg_result(dsvcu_ctx *ctx);
 
 /* ---- timing on the context's stream (CUDA events) ---- */
 int dsvcu_timer_start(dsvcu_ctx *ctx);

@@ -1,0 +1,81 @@
+/*
+ * dsv_session.h -- whole-stream entry points of the B200 build (plain C ABI).
+ *
+ * One call = what one `dsv2 e ...` / `dsv2 d ...` process of the reference does
+ * (reference src/dsv_main.c:547-905 encode(), :959-1120 decode()), on buffers
+ * instead of files, plus the closed-GOP sharded form of the reference's
+ * parallel_encode_yuv.sh (:31-52): N fresh encoder instances on consecutive
+ * chunks, outputs concatenated in order -- here as host threads that each own a
+ * CUDA context on one of the visible GPUs instead of N processes.
+ *
+ * Frames cross this boundary as tightly packed planar YUV (Y, U, V; the raw
+ * .yuv layout the reference CLI reads and writes).
+ */
+#ifndef DSV2_B200_DSV_SESSION_H
+#define DSV2_B200_DSV_SESSION_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "dsv.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* encoder options: the reference CLI's parameter table (dsv_main.c:111-233),
+ * same names, same defaults, same units */
+typedef struct {
+    int w, h, fmt; /* fmt = DSV_SUBSAMP_* */
+    int fps_num, fps_den, aspect_num, aspect_den;
+    int qp;        /* 0..100 percent, 100 = lossless, -1 = default (85) */
+    int effort;    /* 0..10 */
+    int gop;       /* -1 = frame rate, 0 = intra only */
+    int rc_mode;   /* 0 CRF, 1 ABR, 2 CQP */
+    int rc_pergop;
+    int kbps;      /* ABR only; 0 = estimate from qp */
+    int minqstep, maxqstep;
+    int minqp, maxqp, iminqp; /* percent, -1 = auto */
+    int stabref, scd, tempaq, bszx, bszy, scpct, skipthresh, varint, psy, dib;
+    int ifilter, pfilter, psharp, ipct, pyrlevels;
+    int noeos;
+} dsv_enc_opts;
+
+void dsv_enc_opts_default(dsv_enc_opts *o, int w, int h, int fmt, int fps_num, int fps_den);
+
+/* the CUDA device used by encoder / decoder instances created by the calling
+ * thread from now on (default: $DSV_CUDA_DEVICE or 0) */
+void dsv_set_thread_device(int device);
+int dsv_get_thread_device(void);
+
+/* pinned host memory for frame / stream buffers (optional; any memory works) */
+void *dsv_pinned_alloc(size_t bytes);
+void dsv_pinned_free(void *p);
+
+/* `dsv2 e`: encodes nframes pictures.  `exhausted` != 0 says the input ended
+ * with these frames (the reference then appends an EOS packet even with
+ * -noeos=1, dsv_main.c:797).  *out is malloc'ed; the caller frees it. */
+int dsv_encode_buffer(const dsv_enc_opts *o, const uint8_t *yuv, int nframes, int exhausted, uint8_t **out,
+                      size_t *out_len);
+
+/* parallel_encode_yuv.sh: chunks of `chunk` frames, each coded by a fresh
+ * encoder with -noeos=1 semantics, by `nthreads` workers spread round-robin
+ * over `ndevices` GPUs (devices[] lists them; NULL = 0..ndevices-1); chunk k's
+ * bytes land at their place in the concatenation. */
+int dsv_encode_sharded(const dsv_enc_opts *o, const uint8_t *yuv, int nframes, int chunk, int nthreads,
+                       const int *devices, int ndevices, uint8_t **out, size_t *out_len);
+
+/* `dsv2 d`: decodes a stream into packed frames.  *yuv is malloc'ed (or pinned
+ * when `pinned` != 0: free with dsv_pinned_free). */
+int dsv_decode_buffer(const uint8_t *dsv, size_t len, int pinned, uint8_t **yuv, size_t *yuv_len, int *nframes,
+                      DSV_META *meta);
+
+/* closed-GOP sharded decode: the stream is cut at metadata packets (every
+ * chunk of a sharded encode starts with one), segments decoded by `nthreads`
+ * workers over `ndevices` GPUs, frames written in stream order. */
+int dsv_decode_sharded(const uint8_t *dsv, size_t len, int nthreads, const int *devices, int ndevices, int pinned,
+                       uint8_t **yuv, size_t *yuv_len, int *nframes, DSV_META *meta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
