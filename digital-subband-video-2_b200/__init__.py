@@ -145,6 +145,11 @@ def load(emu=False):
         "dsv_encode_sharded": (ip, [P(DSV_ENC_OPTS), vp, ip, ip, ip, P(ip), ip, P(vp), P(C.c_size_t)]),
         "dsv_decode_buffer": (ip, [vp, C.c_size_t, ip, P(vp), P(C.c_size_t), P(ip), P(DSV_META)]),
         "dsv_decode_sharded": (ip, [vp, C.c_size_t, ip, P(ip), ip, ip, P(vp), P(C.c_size_t), P(ip), P(DSV_META)]),
+        "dsv_pool_create": (vp, [ip, P(ip), ip]),
+        "dsv_pool_destroy": (None, [vp]),
+        "dsv_pool_threads": (ip, [vp]),
+        "dsv_pool_encode": (ip, [vp, P(DSV_ENC_OPTS), vp, ip, ip, P(vp), P(C.c_size_t)]),
+        "dsv_pool_decode": (ip, [vp, vp, C.c_size_t, vp, C.c_size_t, P(ip), P(DSV_META)]),
         "dsvcu_host_alloc": (vp, [C.c_size_t]),
         "dsvcu_host_free": (None, [vp]),
         "dsvcu_device_count": (ip, []),
@@ -197,6 +202,7 @@ def load(emu=False):
         "dsvcu_timer_start": (ip, [vp]),
         "dsvcu_timer_stop_ms": (ip, [vp, P(C.c_float)]),
         "dsvcu_launch_count": (C.c_longlong, [vp]),
+        "dsvcu_total_launches": (C.c_longlong, []),
     }
     for name, (res, args) in sig.items():
         try:

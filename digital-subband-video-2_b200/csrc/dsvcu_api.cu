@@ -28,6 +28,7 @@ size_t dsvcu_emu_smem_size = 0;
 #define PSY_P_VISUAL_MASKING 8
 
 static char g_err[256] = "";
+static long long g_launches = 0; /* kernels launched by every context of this process */
 
 static int
 fail(const char *what, int code)
@@ -50,6 +51,7 @@ fail(const char *what, int code)
 #define CK_LAUNCH(ctx)                                             \
     do {                                                           \
         (ctx)->launches++;                                         \
+        __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);      \
         cudaError_t e_ = cudaGetLastError();                       \
         if (e_ != cudaSuccess) return fail("kernel launch", e_);   \
     } while (0)
@@ -316,6 +318,12 @@ extern "C" long long
 dsvcu_launch_count(dsvcu_ctx *c)
 {
     return c->launches;
+}
+
+extern "C" long long
+dsvcu_total_launches(void)
+{
+    return __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
 }
 
 extern "C" int

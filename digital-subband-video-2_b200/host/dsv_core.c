@@ -46,10 +46,13 @@ dsv_alloc(int size)
         return NULL;
     }
     *(int *) p = size;
-    g_allocated++;
-    g_bytes += (unsigned) size;
-    if (g_bytes > g_peak) {
-        g_peak = g_bytes;
+    /* encoder / decoder instances run on several host threads */
+    __atomic_add_fetch(&g_allocated, 1, __ATOMIC_RELAXED);
+    {
+        unsigned now = __atomic_add_fetch(&g_bytes, (unsigned) size, __ATOMIC_RELAXED);
+        if (now > g_peak) {
+            g_peak = now;
+        }
     }
     return p + 16;
 }
@@ -62,8 +65,8 @@ dsv_free(void *ptr)
         return;
     }
     p -= 16;
-    g_bytes -= (unsigned) *(int *) p;
-    g_freed++;
+    __atomic_sub_fetch(&g_bytes, (unsigned) *(int *) p, __ATOMIC_RELAXED);
+    __atomic_add_fetch(&g_freed, 1, __ATOMIC_RELAXED);
     free(p);
 }
 

@@ -282,122 +282,238 @@ dsv_encode_buffer(const dsv_enc_opts *o, const uint8_t *yuv, int nframes, int ex
     return 0;
 }
 
+/* ------------------------------------------------------------ worker pool */
+
+/* A pool is a set of persistent host threads, each bound to one GPU and each
+ * keeping its CUDA context objects (stream, device frames, pinned staging)
+ * alive between jobs.  A job is "run fn(k) for k in [0, n)"; workers take
+ * indices from a shared counter, so chunks/segments balance themselves. */
+typedef struct WORKER WORKER;
+typedef void (*job_fn)(WORKER *w, void *arg, int k);
+
+struct dsv_pool {
+    int nthreads;
+    WORKER *wk;
+    pthread_mutex_t lock;
+    pthread_cond_t wake, done;
+    job_fn fn;
+    void *arg;
+    int n, next, running, generation, quit;
+};
+
+struct WORKER {
+    struct dsv_pool *pool;
+    pthread_t th;
+    int device;
+    int seen; /* last generation served */
+    DSV_ENCODER enc_keep; /* finished encoder whose device buffers get recycled */
+    int have_enc;
+    DSV_DECODER dec;
+};
+
+static void *
+pool_worker(void *p)
+{
+    WORKER *w = p;
+    struct dsv_pool *pl = w->pool;
+    dsv_set_thread_device(w->device);
+    pthread_mutex_lock(&pl->lock);
+    for (;;) {
+        while (!pl->quit && (pl->generation == w->seen || pl->next >= pl->n)) {
+            if (pl->generation != w->seen) {
+                w->seen = pl->generation; /* nothing left for me in this job */
+            }
+            pthread_cond_wait(&pl->wake, &pl->lock);
+        }
+        if (pl->quit) {
+            break;
+        }
+        while (pl->next < pl->n) {
+            int k = pl->next++;
+            pl->running++;
+            pthread_mutex_unlock(&pl->lock);
+            pl->fn(w, pl->arg, k);
+            pthread_mutex_lock(&pl->lock);
+            pl->running--;
+        }
+        w->seen = pl->generation;
+        if (pl->running == 0) {
+            pthread_cond_broadcast(&pl->done);
+        }
+    }
+    pthread_mutex_unlock(&pl->lock);
+    if (w->have_enc) {
+        dsv_enc_free(&w->enc_keep);
+    }
+    dsv_dec_free(&w->dec);
+    return NULL;
+}
+
+dsv_pool *
+dsv_pool_create(int nthreads, const int *devices, int ndevices)
+{
+    struct dsv_pool *pl;
+    int i;
+    if (nthreads <= 0) {
+        return NULL;
+    }
+    if (ndevices <= 0) {
+        ndevices = 1;
+    }
+    pl = calloc(1, sizeof(*pl));
+    pl->wk = calloc((size_t) nthreads, sizeof(WORKER));
+    pthread_mutex_init(&pl->lock, NULL);
+    pthread_cond_init(&pl->wake, NULL);
+    pthread_cond_init(&pl->done, NULL);
+    for (i = 0; i < nthreads; i++) {
+        pl->wk[i].pool = pl;
+        pl->wk[i].device = devices ? devices[i % ndevices] : (ndevices > 1 ? i % ndevices : dsv_get_thread_device());
+        if (pthread_create(&pl->wk[i].th, NULL, pool_worker, &pl->wk[i])) {
+            break;
+        }
+        pl->nthreads++;
+    }
+    if (pl->nthreads == 0) {
+        free(pl->wk);
+        free(pl);
+        return NULL;
+    }
+    return pl;
+}
+
+void
+dsv_pool_destroy(dsv_pool *pl)
+{
+    int i;
+    if (!pl) {
+        return;
+    }
+    pthread_mutex_lock(&pl->lock);
+    pl->quit = 1;
+    pthread_cond_broadcast(&pl->wake);
+    pthread_mutex_unlock(&pl->lock);
+    for (i = 0; i < pl->nthreads; i++) {
+        pthread_join(pl->wk[i].th, NULL);
+    }
+    pthread_mutex_destroy(&pl->lock);
+    pthread_cond_destroy(&pl->wake);
+    pthread_cond_destroy(&pl->done);
+    free(pl->wk);
+    free(pl);
+}
+
+int
+dsv_pool_threads(dsv_pool *pl)
+{
+    return pl ? pl->nthreads : 0;
+}
+
+static void
+pool_run(struct dsv_pool *pl, job_fn fn, void *arg, int n)
+{
+    pthread_mutex_lock(&pl->lock);
+    pl->fn = fn;
+    pl->arg = arg;
+    pl->n = n;
+    pl->next = 0;
+    pl->generation++;
+    pthread_cond_broadcast(&pl->wake);
+    while (pl->next < pl->n || pl->running > 0) {
+        pthread_cond_wait(&pl->done, &pl->lock);
+    }
+    pthread_mutex_unlock(&pl->lock);
+}
+
 /* ----------------------------------------------------------- sharded encode */
 
 typedef struct {
     const dsv_enc_opts *o;
     const uint8_t *yuv;
-    int nframes, chunk, nchunks;
-    int next; /* next chunk to take */
-    pthread_mutex_t lock;
+    int nframes, chunk;
     BYTES *parts;
     int failed;
 } ENC_JOB;
 
-typedef struct {
-    ENC_JOB *job;
-    int device;
-} WORKER;
-
-static int
-take(int *next, int limit, pthread_mutex_t *lock)
+static void
+encode_chunk(WORKER *w, void *arg, int k)
 {
-    int k;
-    pthread_mutex_lock(lock);
-    k = (*next < limit) ? (*next)++ : -1;
-    pthread_mutex_unlock(lock);
-    return k;
+    ENC_JOB *j = arg;
+    DSV_ENCODER enc;
+    size_t fsz = frame_bytes(j->o->w, j->o->h, j->o->fmt);
+    int first = k * j->chunk;
+    int n = MIN(j->chunk, j->nframes - first);
+    /* a fresh encoder per chunk (frame numbers, rate control and block
+     * statistics restart, parallel_encode_yuv.sh:34-41), but the device
+     * buffers of the worker's previous encoder are handed over */
+    configure_encoder(&enc, j->o);
+    if (w->have_enc) {
+        dsv_enc_recycle(&w->enc_keep, &enc);
+        dsv_enc_free(&w->enc_keep);
+        w->have_enc = 0;
+    }
+    if (run_encoder(&enc, j->o, j->yuv + (size_t) first * fsz, n, 0, &j->parts[k])) {
+        j->failed = 1;
+    }
+    w->enc_keep = enc;
+    w->have_enc = 1;
 }
 
-static void *
-encode_worker(void *arg)
+int
+dsv_pool_encode(dsv_pool *pl, const dsv_enc_opts *o, const uint8_t *yuv, int nframes, int chunk, uint8_t **out,
+                size_t *out_len)
 {
-    WORKER *w = arg;
-    ENC_JOB *j = w->job;
-    DSV_ENCODER enc, prev;
-    size_t fsz = frame_bytes(j->o->w, j->o->h, j->o->fmt);
-    int k, have_prev = 0;
+    ENC_JOB job;
+    size_t total = 0, off = 0;
+    int i, nchunks;
 
-    dsv_set_thread_device(w->device);
-    while ((k = take(&j->next, j->nchunks, &j->lock)) >= 0) {
-        int first = k * j->chunk;
-        int n = MIN(j->chunk, j->nframes - first);
-        /* a fresh encoder per chunk (frame numbers, rate control and block
-         * statistics restart), but the device buffers are handed over */
-        configure_encoder(&enc, j->o);
-        if (have_prev) {
-            dsv_enc_recycle(&prev, &enc);
-            dsv_enc_free(&prev);
-        }
-        if (run_encoder(&enc, j->o, j->yuv + (size_t) first * fsz, n, 0, &j->parts[k])) {
-            j->failed = 1;
-        }
-        prev = enc;
-        have_prev = 1;
+    *out = NULL;
+    *out_len = 0;
+    if (!pl || chunk <= 0 || nframes <= 0) {
+        return -1;
     }
-    if (have_prev) {
-        dsv_enc_free(&prev);
+    memset(&job, 0, sizeof(job));
+    nchunks = (nframes + chunk - 1) / chunk;
+    job.o = o;
+    job.yuv = yuv;
+    job.nframes = nframes;
+    job.chunk = chunk;
+    job.parts = calloc((size_t) nchunks, sizeof(BYTES));
+    pool_run(pl, encode_chunk, &job, nchunks);
+    for (i = 0; i < nchunks; i++) {
+        total += job.parts[i].len;
     }
-    return NULL;
+    if (!job.failed) {
+        *out = malloc(total ? total : 1);
+        for (i = 0; i < nchunks; i++) {
+            memcpy(*out + off, job.parts[i].data, job.parts[i].len);
+            off += job.parts[i].len;
+        }
+        *out_len = total;
+    }
+    for (i = 0; i < nchunks; i++) {
+        free(job.parts[i].data);
+    }
+    free(job.parts);
+    return job.failed ? -1 : 0;
 }
 
 int
 dsv_encode_sharded(const dsv_enc_opts *o, const uint8_t *yuv, int nframes, int chunk, int nthreads, const int *devices,
                    int ndevices, uint8_t **out, size_t *out_len)
 {
-    ENC_JOB job;
-    pthread_t *th;
-    WORKER *wk;
-    size_t total = 0, off = 0;
-    int i, started = 0;
-
-    if (chunk <= 0 || nframes <= 0 || nthreads <= 0 || ndevices <= 0) {
+    dsv_pool *pl;
+    int r, nchunks;
+    if (chunk <= 0 || nframes <= 0 || nthreads <= 0) {
         return -1;
     }
-    memset(&job, 0, sizeof(job));
-    job.o = o;
-    job.yuv = yuv;
-    job.nframes = nframes;
-    job.chunk = chunk;
-    job.nchunks = (nframes + chunk - 1) / chunk;
-    job.parts = calloc((size_t) job.nchunks, sizeof(BYTES));
-    pthread_mutex_init(&job.lock, NULL);
-    nthreads = MIN(nthreads, job.nchunks);
-    th = calloc((size_t) nthreads, sizeof(*th));
-    wk = calloc((size_t) nthreads, sizeof(*wk));
-    for (i = 0; i < nthreads; i++) {
-        wk[i].job = &job;
-        wk[i].device = devices ? devices[i % ndevices] : i % ndevices;
-        if (pthread_create(&th[i], NULL, encode_worker, &wk[i])) {
-            job.failed = 1;
-            break;
-        }
-        started++;
+    nchunks = (nframes + chunk - 1) / chunk;
+    pl = dsv_pool_create(MIN(nthreads, nchunks), devices, ndevices);
+    if (!pl) {
+        return -1;
     }
-    for (i = 0; i < started; i++) {
-        pthread_join(th[i], NULL);
-    }
-    for (i = 0; i < job.nchunks; i++) {
-        total += job.parts[i].len;
-    }
-    *out = NULL;
-    *out_len = 0;
-    if (!job.failed) {
-        *out = malloc(total ? total : 1);
-        for (i = 0; i < job.nchunks; i++) {
-            memcpy(*out + off, job.parts[i].data, job.parts[i].len);
-            off += job.parts[i].len;
-        }
-        *out_len = total;
-    }
-    for (i = 0; i < job.nchunks; i++) {
-        free(job.parts[i].data);
-    }
-    free(job.parts);
-    free(th);
-    free(wk);
-    pthread_mutex_destroy(&job.lock);
-    return job.failed ? -1 : 0;
+    r = dsv_pool_encode(pl, o, yuv, nframes, chunk, out, out_len);
+    dsv_pool_destroy(pl);
+    return r;
 }
 
 /* ------------------------------------------------------------------ decode */
@@ -503,57 +619,37 @@ count_pictures(const PKT *pk, int first, int last)
     return n;
 }
 
-int
-dsv_decode_buffer(const uint8_t *dsv, size_t len, int pinned, uint8_t **yuv, size_t *yuv_len, int *nframes, DSV_META *meta)
-{
-    return dsv_decode_sharded(dsv, len, 1, NULL, 1, pinned, yuv, yuv_len, nframes, meta);
-}
-
 typedef struct {
     const uint8_t *d;
     const PKT *pk;
     int *seg_first, *seg_last, *seg_frame0; /* per segment */
-    int nseg, next;
-    pthread_mutex_t lock;
     uint8_t *dst;
     size_t fsz;
     int *seg_done; /* frames actually decoded per segment */
 } DEC_JOB;
 
-typedef struct {
-    DEC_JOB *job;
-    int device;
-} DWORKER;
-
-static void *
-decode_worker(void *arg)
+static void
+decode_segment(WORKER *w, void *arg, int k)
 {
-    DWORKER *w = arg;
-    DEC_JOB *j = w->job;
-    DSV_DECODER dec;
-    int k;
-    memset(&dec, 0, sizeof(dec));
-    dsv_set_thread_device(w->device);
-    while ((k = take(&j->next, j->nseg, &j->lock)) >= 0) {
-        j->seg_done[k] = decode_range(&dec, j->d, j->pk, j->seg_first[k], j->seg_last[k],
-                                      j->dst + (size_t) j->seg_frame0[k] * j->fsz, j->fsz);
-    }
-    dsv_dec_free(&dec);
-    return NULL;
+    DEC_JOB *j = arg;
+    j->seg_done[k] = decode_range(&w->dec, j->d, j->pk, j->seg_first[k], j->seg_last[k],
+                                  j->dst + (size_t) j->seg_frame0[k] * j->fsz, j->fsz);
 }
 
-int
-dsv_decode_sharded(const uint8_t *dsv, size_t len, int nthreads, const int *devices, int ndevices, int pinned,
-                   uint8_t **yuv, size_t *yuv_len, int *nframes, DSV_META *meta)
+/* frames are written to `dst` (host, pinned or DEVICE memory) when it is given
+ * and large enough for dst_cap bytes; with dst == NULL *yuv is allocated */
+static int
+pool_decode(dsv_pool *pl, const uint8_t *dsv, size_t len, uint8_t *dst, size_t dst_cap, int pinned, uint8_t **yuv,
+            size_t *yuv_len, int *nframes, DSV_META *meta)
 {
     PKT *pk = NULL;
     DEC_JOB job;
     DSV_META md;
-    pthread_t *th;
-    DWORKER *wk;
-    int npk, i, nseg = 0, total, started = 0, ok = 1;
+    int npk, i, nseg = 0, total, ok = 1, outn = 0;
 
-    *yuv = NULL;
+    if (yuv) {
+        *yuv = NULL;
+    }
     *yuv_len = 0;
     *nframes = 0;
     npk = index_packets(dsv, len, &pk);
@@ -588,60 +684,69 @@ dsv_decode_sharded(const uint8_t *dsv, size_t len, int nthreads, const int *devi
     }
     job.d = dsv;
     job.pk = pk;
-    job.nseg = nseg;
     job.fsz = frame_bytes(md.width, md.height, md.subsamp);
-    job.dst = pinned ? dsv_pinned_alloc(job.fsz * (size_t) MAX(total, 1)) : malloc(job.fsz * (size_t) MAX(total, 1));
-    pthread_mutex_init(&job.lock, NULL);
-    if (!job.dst) {
-        ok = 0;
-    }
-    nthreads = CLAMP(nthreads, 1, nseg);
-    if (ndevices <= 0) {
-        ndevices = 1;
-    }
-    th = calloc((size_t) nthreads, sizeof(*th));
-    wk = calloc((size_t) nthreads, sizeof(*wk));
-    if (ok && nthreads == 1) {
-        wk[0].job = &job;
-        wk[0].device = devices ? devices[0] : dsv_get_thread_device();
-        decode_worker(&wk[0]);
-    } else if (ok) {
-        for (i = 0; i < nthreads; i++) {
-            wk[i].job = &job;
-            wk[i].device = devices ? devices[i % ndevices] : i % ndevices;
-            if (pthread_create(&th[i], NULL, decode_worker, &wk[i])) {
-                ok = 0;
-                break;
-            }
-            started++;
+    if (dst) {
+        if (dst_cap < job.fsz * (size_t) total) {
+            ok = 0;
         }
-        for (i = 0; i < started; i++) {
-            pthread_join(th[i], NULL);
+        job.dst = dst;
+    } else {
+        job.dst = pinned ? dsv_pinned_alloc(job.fsz * (size_t) MAX(total, 1)) : malloc(job.fsz * (size_t) MAX(total, 1));
+        if (!job.dst) {
+            ok = 0;
         }
     }
     if (ok) {
-        /* frames of a damaged segment may be missing: close the gaps */
-        int outn = 0;
+        pool_run(pl, decode_segment, &job, nseg);
+        /* frames of a damaged segment may be missing: close the gaps (host
+         * destinations only; a device destination keeps segment positions) */
         for (i = 0; i < nseg; i++) {
-            if (job.seg_done[i] > 0 && outn != job.seg_frame0[i]) {
+            if (!dst && job.seg_done[i] > 0 && outn != job.seg_frame0[i]) {
                 memmove(job.dst + (size_t) outn * job.fsz, job.dst + (size_t) job.seg_frame0[i] * job.fsz,
                         (size_t) job.seg_done[i] * job.fsz);
             }
             outn += job.seg_done[i];
         }
-        *yuv = job.dst;
+        if (yuv) {
+            *yuv = job.dst;
+        }
         *yuv_len = (size_t) outn * job.fsz;
         *nframes = outn;
-    } else if (job.dst) {
-        if (pinned) dsv_pinned_free(job.dst); else free(job.dst);
     }
-    pthread_mutex_destroy(&job.lock);
     free(job.seg_first);
     free(job.seg_last);
     free(job.seg_frame0);
     free(job.seg_done);
-    free(th);
-    free(wk);
     free(pk);
     return ok ? 0 : -1;
+}
+
+int
+dsv_pool_decode(dsv_pool *pl, const uint8_t *dsv, size_t len, uint8_t *dst, size_t dst_cap, int *nframes, DSV_META *meta)
+{
+    size_t n;
+    if (!pl || !dst) {
+        return -1;
+    }
+    return pool_decode(pl, dsv, len, dst, dst_cap, 0, NULL, &n, nframes, meta);
+}
+
+int
+dsv_decode_sharded(const uint8_t *dsv, size_t len, int nthreads, const int *devices, int ndevices, int pinned,
+                   uint8_t **yuv, size_t *yuv_len, int *nframes, DSV_META *meta)
+{
+    dsv_pool *pl = dsv_pool_create(MAX(nthreads, 1), devices, ndevices);
+    int r;
+    if (!pl) {
+        return -1;
+    }
+    r = pool_decode(pl, dsv, len, NULL, 0, pinned, yuv, yuv_len, nframes, meta);
+    dsv_pool_destroy(pl);
+    return r;
+}
+
+int
+dsv_decode_buffer(const uint8_t *dsv, size_t len, int pinned, uint8_t **yuv, size_t *yuv_len, int *nframes, DSV_META *meta)
+{
+    return dsv_decode_sharded(dsv, len, 1, NULL, 1, pinned, yuv, yuv_len, nframes, meta);
 }

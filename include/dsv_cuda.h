@@ -174,6 +174,8 @@ int dsvcu_timer_start(dsvcu_ctx *ctx);
 int dsvcu_timer_stop_ms(dsvcu_ctx *ctx, float *ms); /* synchronises */
 /* number of kernels this context has launched so far */
 long long dsvcu_launch_count(dsvcu_ctx *ctx);
+/* ... and every context of this process together */
+long long dsvcu_total_launches(void);
 
 #ifdef __cplusplus
 }

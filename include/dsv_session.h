@@ -64,6 +64,20 @@ int dsv_encode_buffer(const dsv_enc_opts *o, const uint8_t *yuv, int nframes, in
 int dsv_encode_sharded(const dsv_enc_opts *o, const uint8_t *yuv, int nframes, int chunk, int nthreads,
                        const int *devices, int ndevices, uint8_t **out, size_t *out_len);
 
+/* persistent worker pool: `nthreads` host threads spread round-robin over the
+ * listed GPUs, each keeping its CUDA context objects between calls.  The
+ * one-shot dsv_encode_sharded / dsv_decode_sharded build a pool per call. */
+typedef struct dsv_pool dsv_pool;
+dsv_pool *dsv_pool_create(int nthreads, const int *devices, int ndevices);
+void dsv_pool_destroy(dsv_pool *pool);
+int dsv_pool_threads(dsv_pool *pool);
+/* `yuv` may be host, pinned or DEVICE memory (unified addressing) */
+int dsv_pool_encode(dsv_pool *pool, const dsv_enc_opts *o, const uint8_t *yuv, int nframes, int chunk, uint8_t **out,
+                    size_t *out_len);
+/* frames are written to caller memory `dst` (host, pinned or DEVICE) */
+int dsv_pool_decode(dsv_pool *pool, const uint8_t *dsv, size_t len, uint8_t *dst, size_t dst_cap, int *nframes,
+                    DSV_META *meta);
+
 /* `dsv2 d`: decodes a stream into packed frames.  *yuv is malloc'ed (or pinned
  * when `pinned` != 0: free with dsv_pinned_free). */
 int dsv_decode_buffer(const uint8_t *dsv, size_t len, int pinned, uint8_t **yuv, size_t *yuv_len, int *nframes,
