@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
+#include <math.h>
 
 #ifndef DSVCU_EMU
 /* ------------------------------------------------------------------ CUDA */

@@ -440,46 +440,115 @@ f_chroma_cell(const FiltArgs &A, int i, int j)
     return (tx > 0) || (ty > 0);
 }
 
-/* slope-2 wavefront over rows of cells; see file header */
+/* Can cell (i, row) touch pixels at all?  Decided from block data only (vectors,
+ * flags), never from pixels, so it can be evaluated ahead of the wavefront.
+ * Cells that cannot are skipped without waiting for their neighbours. */
+DSVCU_DEV int
+f_cell_active(const FiltArgs &A, int i, int j)
+{
+    if (A.mode == FILT_MODE_CHROMA) {
+        const dsvcu_mv mv = A.mvs[i + j * A.nbh];
+        if (mv.flags & MVF_SKIP) return 0;
+        if (mv.flags & MVF_INTRA) return 1;
+        int ndx, ndy;
+        f_neighbordif2(A.mvs, A.nbh, i, j, &ndx, &ndy);
+        if (ndx < f_abs(mv.y) && ndy < f_abs(mv.x)) return 0;
+        return ((min(ndy, 64) * A.q) >> 12) > 0 || ((min(ndx, 64) * A.q) >> 12) > 0;
+    }
+    const int nsbx = A.w / 4, nsby = A.h / 4;
+    const int x = i * 4, y = j * 4;
+    if (y + 4 >= A.h || x + 4 >= A.w) return 0;
+    const int fy = j * A.nbv / nsby, fx = i * A.nbh / nsbx;
+    if (A.mode == FILT_MODE_INTRA) {
+        return !(A.blockdata[fx + fy * A.nbh] & BD_RING);
+    }
+    const dsvcu_mv mv = A.mvs[fx + fy * A.nbh];
+    if (mv.flags & MVF_SKIP) return 0;
+    if (mv.flags & MVF_INTRA) return 1;
+    if (A.do_filter) {
+        int ndx, ndy;
+        f_neighbordif2(A.mvs, A.nbh, fx, fy, &ndx, &ndy);
+        if (ndx || ndy) return 1;
+    }
+    return A.sharpen && (mv.x & 3) && (mv.y & 3) && ((mv.x | mv.y) & 1) && f_abs(mv.x) < 8 && f_abs(mv.y) < 8;
+}
+
+/* Slope-2 wavefront over rows of cells (see file header).  Protocol: row r
+ * publishes progress P = "cells < P of this row are complete, and row r-1 has
+ * completed cells < P+1" (the second half covers the footprint overlap between
+ * rows r-1 and r+1 in the same column).  An active cell i waits for row r-1 to
+ * reach min(i+2, ncols).  Inactive cells are not visited one by one: the warp
+ * finds the next active cell with a ballot and, while it waits for that cell's
+ * dependency, keeps relaying the progress of the row above (minus one cell), so
+ * a region without filtering costs one flag round trip per row instead of one
+ * per cell. */
 DSVCU_KERNEL void __launch_bounds__(FILT_WARPS_PER_CTA * 32)
 k_filter_wavefront(FiltArgs A)
 {
     const int lane = FILT_LANE;
+    const int ncols = A.ncols;
     for (int row = FILT_WARP; row < A.nrows; row += FILT_NWARPS) {
-        int seen = (row == 0) ? A.ncols + 2 : 0; /* progress of the row above, cached */
-        for (int i = 0; i < A.ncols; i++) {
-            int need = min(i + 2, A.ncols);
-            if (seen < need) {
+        int seen = (row == 0) ? 0x7fffffff : 0; /* progress of the row above, cached */
+        int published = 0;
+        (void) published;
+        for (int base = 0; base < ncols; base += FILT_NLANES) {
 #ifndef DSVCU_EMU
-                do {
+            int cell = base + lane;
+            unsigned mask = __ballot_sync(0xffffffffu, cell < ncols && f_cell_active(A, cell, row));
+#else
+            unsigned mask = (base < ncols && f_cell_active(A, base, row)) ? 1u : 0u;
+#endif
+            while (mask) {
+#ifndef DSVCU_EMU
+                int i = base + __ffs(mask) - 1;
+                int need = min(i + 2, ncols);
+                mask &= mask - 1;
+                while (seen < need) {
                     seen = PROG_LD(A.progress + row - 1);
-                } while (seen < need);
+                    int relay = min(i, seen >= ncols ? i : seen - 1);
+                    if (relay > published) {
+                        published = relay;
+                        if (lane == 0) *(volatile int *) (A.progress + row) = relay;
+                    }
+                    if (seen < need) __nanosleep(32);
+                }
                 __threadfence();
+                if (i > published) {
+                    published = i;
+                    if (lane == 0) *(volatile int *) (A.progress + row) = i;
+                }
 #else
-                seen = A.ncols;
+                int i = base;
+                mask = 0;
 #endif
-            }
-            int touched;
-            if (A.mode == FILT_MODE_LUMA) {
-                touched = f_luma_cell(A, i, row);
-            } else if (A.mode == FILT_MODE_INTRA) {
-                touched = f_intra_cell(A, i, row);
-            } else {
-                touched = f_chroma_cell(A, i, row);
-            }
-            (void) touched;
+                if (A.mode == FILT_MODE_LUMA) {
+                    f_luma_cell(A, i, row);
+                } else if (A.mode == FILT_MODE_INTRA) {
+                    f_intra_cell(A, i, row);
+                } else {
+                    f_chroma_cell(A, i, row);
+                }
 #ifndef DSVCU_EMU
-            if (touched) {
                 __threadfence();
-            }
-            __syncwarp();
-            if (lane == 0) {
-                *(volatile int *) (A.progress + row) = i + 1;
-            }
-#else
-            (void) lane;
+                __syncwarp();
+                published = i + 1;
+                if (lane == 0) *(volatile int *) (A.progress + row) = i + 1;
 #endif
+            }
         }
+#ifndef DSVCU_EMU
+        /* tail without active cells: relay until the row above is done */
+        while (seen < ncols) {
+            seen = PROG_LD(A.progress + row - 1);
+            int relay = seen >= ncols ? ncols : seen - 1;
+            if (relay > published) {
+                published = relay;
+                if (lane == 0) *(volatile int *) (A.progress + row) = relay;
+            }
+            if (seen < ncols) __nanosleep(32);
+        }
+        if (lane == 0) *(volatile int *) (A.progress + row) = ncols;
+#endif
     }
 }
 

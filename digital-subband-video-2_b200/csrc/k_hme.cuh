@@ -84,23 +84,69 @@ DSVCU_HD unsigned me_uavg4(int a, int b, int c, int d) { return (unsigned) (a + 
 DSVCU_HD int me_u8(int v) { return v > 255 ? 255 : (v < 0 ? 0 : v); }
 DSVCU_HD int me_sar_r2(int v) { return (v + 2) >> 2; } /* DSV_SAR_R(v, 2) */
 
-DSVCU_HD unsigned
-me_isqrt(unsigned n) /* hme.c:99-124 */
+/* ---- packed-byte helpers: four horizontally adjacent pixels per 32-bit word.
+ * On the device these map to one instruction each (byte-SIMD absolute
+ * difference, 4-way dot product, byte permute); the host emulation spells them
+ * out.  Blocks whose width is 4, 8, 16 or 32 take the packed paths below, any
+ * other width the generic per-pixel loops. ---- */
+#ifndef DSVCU_EMU
+DSVCU_DEV uint32_t me_ld4(const uint8_t *p)
 {
-    unsigned pos, res = 0, rem = n;
-    if (n == 0) return 0;
-    pos = 1u << 30;
-    while (pos > rem) pos >>= 2;
-    while (pos) {
-        unsigned dif = res + pos;
-        res >>= 1;
-        if (rem >= dif) {
-            rem -= dif;
-            res += pos;
-        }
-        pos >>= 2;
+    /* unaligned 4-byte read from two aligned words; may touch up to 3 bytes
+     * past p+3, which always lie inside the frame allocation */
+    uintptr_t a = (uintptr_t) p;
+    const uint32_t *q = (const uint32_t *) (a & ~(uintptr_t) 3);
+    return __funnelshift_r(q[0], q[1], (unsigned) (a & 3) * 8);
+}
+DSVCU_DEV uint32_t me_absdiff4(uint32_t a, uint32_t b) { return __vabsdiffu4(a, b); }
+DSVCU_DEV unsigned me_dot4(uint32_t a, uint32_t b, unsigned acc) { return __dp4a(a, b, acc); }
+DSVCU_DEV uint32_t me_perm(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+#else
+DSVCU_DEV uint32_t me_ld4(const uint8_t *p)
+{
+    return (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24);
+}
+DSVCU_DEV uint32_t me_absdiff4(uint32_t a, uint32_t b)
+{
+    uint32_t r = 0;
+    for (int k = 0; k < 4; k++) {
+        int x = (int) ((a >> (8 * k)) & 255) - (int) ((b >> (8 * k)) & 255);
+        r |= (uint32_t) (x < 0 ? -x : x) << (8 * k);
     }
-    return res;
+    return r;
+}
+DSVCU_DEV unsigned me_dot4(uint32_t a, uint32_t b, unsigned acc)
+{
+    for (int k = 0; k < 4; k++) acc += ((a >> (8 * k)) & 255) * ((b >> (8 * k)) & 255);
+    return acc;
+}
+DSVCU_DEV uint32_t me_perm(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint64_t v = ((uint64_t) b << 32) | a;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; k++) r |= (uint32_t) ((v >> (8 * ((sel >> (4 * k)) & 7))) & 255) << (8 * k);
+    return r;
+}
+#endif
+#define ME_ONES 0x01010101u
+
+/* log2(w / 4) for w in {4, 8, 16, 32}, else -1 (generic path) */
+DSVCU_DEV int me_gshift(int w)
+{
+    return w == 16 ? 2 : (w == 8 ? 1 : (w == 32 ? 3 : (w == 4 ? 0 : -1)));
+}
+
+/* floor(sqrt(n)): what the reference's digit-by-digit iisqrt (hme.c:99-124)
+ * returns; here from the hardware square root plus an exact integer fix-up
+ * (checked against the digit-by-digit form over the full 32-bit range at
+ * every perfect square +-2 and a dense sample, see tests) */
+DSVCU_HD unsigned
+me_isqrt(unsigned n)
+{
+    unsigned r = (unsigned) sqrtf((float) n);
+    while ((unsigned long long) r * r > n) r--;
+    while ((unsigned long long) (r + 1) * (r + 1) <= n) r++;
+    return r;
 }
 
 struct MePsy {
@@ -122,12 +168,39 @@ me_cell(int a1, int a2, int a3, int a4, int b1, int b2, int b3, int b4, const Me
     return acc;
 }
 
+/* the same on packed cells A = (a1,a2,a3,a4), B = (b1,b2,b3,b4) */
+DSVCU_DEV unsigned
+me_cell4(uint32_t A, uint32_t B, const MePsy &p)
+{
+    int s0 = (int) ((me_dot4(A, ME_ONES, 2)) >> 2), s1 = (int) ((me_dot4(B, ME_ONES, 2)) >> 2);
+    int se = (int) ((me_dot4(me_absdiff4(A, B), ME_ONES, 2)) >> 2);
+    int ta = (int) ((me_dot4(me_absdiff4(A, me_perm(A, A, 0x0321)), ME_ONES, 2)) >> 2);
+    int tb = (int) ((me_dot4(me_absdiff4(B, me_perm(B, B, 0x0321)), ME_ONES, 2)) >> 2);
+    unsigned acc = (unsigned) (me_sqr(se) << p.err_w);
+    acc += (unsigned) (me_sqr(ta - tb) << p.tex_w);
+    acc += (unsigned) (me_sqr(s0 - s1) << p.avg_w);
+    return acc;
+}
+
 /* raw accumulator of the psy metric over w x h (umetr_wxh, hme.c:191-196) */
 DSVCU_DEV unsigned
 me_umetr(const uint8_t *a, int as, const uint8_t *b, int bs, int w, int h, const MePsy &p)
 {
     int cw = w / 2, ch = h / 2, n = cw * ch;
     unsigned acc = 0;
+    const int gs = me_gshift(w);
+    if (gs >= 0) {
+        /* one work item = 4 pixels x 2 rows = two 2x2 cells */
+        const int ng = ch << gs, gm = (1 << gs) - 1;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            int y = (g >> gs) * 2, x = (g & gm) * 4;
+            uint32_t a0 = me_ld4(a + y * as + x), a1 = me_ld4(a + (y + 1) * as + x);
+            uint32_t b0 = me_ld4(b + y * bs + x), b1 = me_ld4(b + (y + 1) * bs + x);
+            acc += me_cell4(me_perm(a0, a1, 0x5410), me_perm(b0, b1, 0x5410), p);
+            acc += me_cell4(me_perm(a0, a1, 0x7632), me_perm(b0, b1, 0x7632), p);
+        }
+        return me_wsumu(acc);
+    }
     for (int k = ME_LANE; k < n; k += ME_NL) {
         int j = k / cw, i = k - j * cw;
         const uint8_t *pa = a + (2 * j) * as + 2 * i, *pb = b + (2 * j) * bs + 2 * i;
@@ -152,6 +225,16 @@ me_sse(const uint8_t *a, int as, const uint8_t *b, int bs, int w, int h)
     if (w == 0 || h == 0) return 0x7fffffffu;
     unsigned acc = 0;
     int n = w * h;
+    const int gs = me_gshift(w);
+    if (gs >= 0) {
+        const int ng = h << gs, gm = (1 << gs) - 1;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            int y = g >> gs, x = (g & gm) * 4;
+            uint32_t d = me_absdiff4(me_ld4(a + y * as + x), me_ld4(b + y * bs + x));
+            acc = me_dot4(d, d, acc);
+        }
+        return me_wsumu(acc);
+    }
     for (int k = ME_LANE; k < n; k += ME_NL) {
         int j = k / w, i = k - j * w;
         int d = (int) a[j * as + i] - (int) b[j * bs + i];
@@ -213,21 +296,29 @@ me_movec_pred(const dsvcu_mv *vecs, int nbh, int x, int y, int *px, int *py)
 DSVCU_DEV int
 me_seg_len(int v)
 {
-    unsigned x;
-    int nb = -1;
+    /* 2 * floor(log2(|v| + 1)) + 2 */
     if (v < 0) v = -v;
     v++;
-    for (x = (unsigned) v; x; x >>= 1) nb++;
-    return nb * 2 + 1 + (v ? 1 : 0);
+#ifndef DSVCU_EMU
+    return (31 - __clz(v)) * 2 + 2;
+#else
+    return (31 - __builtin_clz((unsigned) v)) * 2 + 2;
+#endif
 }
 
 /* mv_cost (hme.c:354-366) on top of dsv_mv_cost (dsv.c:357-374) */
+/* the predictor of a block depends only on its left / top / top-left
+ * neighbours, which are final before the block starts: computed once per block
+ * (MePred) instead of inside every rate term */
+struct MePred {
+    int x, y;
+};
+
 DSVCU_DEV int
-me_mv_cost(const MeArgs &A, int i, int j, int mx, int my, int level)
+me_mv_cost(const MeArgs &A, const MePred &pr, int mx, int my, int level)
 {
-    int px, py, bits, b2sr, q = A.quant;
+    int px = pr.x, py = pr.y, bits, b2sr, q = A.quant;
     int sqr = level > 1;
-    me_movec_pred(A.mvf, A.nxb, i, j, &px, &py);
     bits = me_seg_len(mx - px) + me_seg_len(my - py);
     b2sr = (256 * (q * q >> 12) * A.y_w * A.y_h) / (A.vid_w * A.vid_h);
     bits += bits * b2sr >> 7;
@@ -269,6 +360,15 @@ DSVCU_DEV int
 me_block_avg(const uint8_t *a, int as, int w, int h)
 {
     int s = 0, n = w * h;
+    const int gs = me_gshift(w);
+    if (gs >= 0) {
+        const int ng = h << gs, gm = (1 << gs) - 1;
+        unsigned u = 0;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            u = me_dot4(me_ld4(a + (g >> gs) * as + (g & gm) * 4), ME_ONES, u);
+        }
+        return me_wsum((int) u) / (w * h);
+    }
     for (int k = ME_LANE; k < n; k += ME_NL) {
         int j = k / w, i = k - j * w;
         s += a[j * as + i];
@@ -282,6 +382,25 @@ me_grad_sums(const uint8_t *a, int as, int w, int h, unsigned *psh, unsigned *ps
 {
     unsigned sh = 0, sv = 0;
     int s = 0, n = w * h;
+    const int gs = me_gshift(w);
+    if (gs >= 0) {
+        const int ng = h << gs, gm = (1 << gs) - 1;
+        unsigned us = 0;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            int y = g >> gs, x = (g & gm) * 4;
+            const uint8_t *p = a + y * as + x;
+            uint32_t c = me_ld4(p);
+            uint32_t dl = me_absdiff4(c, me_ld4(p - 1));
+            us = me_dot4(c, ME_ONES, us);
+            if (x == 0) dl &= 0xffffff00u; /* column 0 has no left neighbour */
+            sh = me_dot4(dl, ME_ONES, sh);
+            if (y > 0) sv = me_dot4(me_absdiff4(c, me_ld4(p - as)), ME_ONES, sv);
+        }
+        *psh = me_wsumu(sh);
+        *psv = me_wsumu(sv);
+        *psum = me_wsum((int) us);
+        return;
+    }
     for (int k = ME_LANE; k < n; k += ME_NL) {
         int j = k / w, i = k - j * w;
         int px = a[j * as + i];
@@ -307,6 +426,16 @@ DSVCU_DEV int
 me_abs_dev(const uint8_t *a, int as, int w, int h, int mean)
 {
     int var = 0, n = w * h;
+    const int gs = me_gshift(w);
+    if (gs >= 0 && mean >= 0 && mean <= 255) {
+        const int ng = h << gs, gm = (1 << gs) - 1;
+        const uint32_t m4 = (uint32_t) mean * ME_ONES;
+        unsigned u = 0;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            u = me_dot4(me_absdiff4(me_ld4(a + (g >> gs) * as + (g & gm) * 4), m4), ME_ONES, u);
+        }
+        return me_wsum((int) u);
+    }
     for (int k = ME_LANE; k < n; k += ME_NL) {
         int j = k / w, i = k - j * w;
         var += me_abs((int) a[j * as + i] - mean);
@@ -317,12 +446,7 @@ me_abs_dev(const uint8_t *a, int as, int w, int h, int mean)
 DSVCU_DEV int
 me_block_var(const uint8_t *a, int as, int w, int h, unsigned *avg)
 {
-    int s = 0, n = w * h;
-    for (int k = ME_LANE; k < n; k += ME_NL) {
-        int j = k / w, i = k - j * w;
-        s += a[j * as + i];
-    }
-    s = me_wsum(s) / (w * h);
+    int s = me_block_avg(a, as, w, h);
     *avg = (unsigned) s;
     return me_abs_dev(a, as, w, h, s);
 }
@@ -345,6 +469,25 @@ me_quant_tex(const uint8_t *a, int as, int w, int h)
 {
     unsigned sh = 0, sv = 0;
     int n = w * h;
+    const int gs = me_gshift(w);
+    if (gs >= 0) {
+        const int ng = h << gs, gm = (1 << gs) - 1;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            int y = g >> gs, x = (g & gm) * 4;
+            const uint8_t *p = a + y * as + x;
+            uint32_t c = (me_ld4(p) >> 4) & 0x0f0f0f0fu;
+            uint32_t dr = me_absdiff4(c, (me_ld4(p + 1) >> 4) & 0x0f0f0f0fu);
+            if (x == w - 4) dr &= 0x00ffffffu; /* last column has no right neighbour */
+            sh = me_dot4(dr, dr, sh);
+            if (y > 0) {
+                uint32_t du = me_absdiff4(c, (me_ld4(p - as) >> 4) & 0x0f0f0f0fu);
+                sv = me_dot4(du, du, sv);
+            }
+        }
+        sh = me_wsumu(sh);
+        sv = me_wsumu(sv);
+        return (int) (me_isqrt(max(sh, sv)) / (unsigned) me_avg2(w, h));
+    }
     for (int k = ME_LANE; k < n; k += ME_NL) {
         int j = k / w, i = k - j * w;
         int px = a[j * as + i] >> 4;
@@ -374,19 +517,27 @@ DSVCU_DEV unsigned
 me_block_hist_var(const uint8_t *a, int as, int w, int h, int *hist)
 {
     unsigned avg, quant16, var = 0;
-    int s = 0, n = w * h;
+    int n = w * h;
+    const int gs = me_gshift(w);
     me_hist_clear(hist);
-    for (int k = ME_LANE; k < n; k += ME_NL) {
-        int j = k / w, i = k - j * w;
-        s += a[j * as + i];
-    }
-    avg = (unsigned) me_wsum(s) / (unsigned) (w * h);
+    avg = (unsigned) me_block_avg(a, as, w, h);
     if (avg == 0) avg = 1;
     quant16 = ((1u << 3) << 16) / avg;
-    for (int k = ME_LANE; k < n; k += ME_NL) {
-        int j = k / w, i = k - j * w;
-        int hi = (int) (a[j * as + i] * quant16 >> 16);
-        atomicAdd(&hist[hi < 0 ? 0 : (hi > 15 ? 15 : hi)], 1);
+    if (gs >= 0) {
+        const int ng = h << gs, gm = (1 << gs) - 1;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            uint32_t c = me_ld4(a + (g >> gs) * as + (g & gm) * 4);
+            for (int k = 0; k < 4; k++) {
+                unsigned hi = ((c >> (8 * k)) & 255u) * quant16 >> 16;
+                atomicAdd(&hist[hi > 15 ? 15 : hi], 1);
+            }
+        }
+    } else {
+        for (int k = ME_LANE; k < n; k += ME_NL) {
+            int j = k / w, i = k - j * w;
+            int hi = (int) (a[j * as + i] * quant16 >> 16);
+            atomicAdd(&hist[hi < 0 ? 0 : (hi > 15 ? 15 : hi)], 1);
+        }
     }
     DSVCU_SYNCWARP();
     avg = 0;
@@ -407,12 +558,27 @@ me_block_peaks(const uint8_t *a, int as, int w, int h, int *hist, int bavg)
     cw = w / 2;
     ch = h / 2;
     n = cw * ch;
-    for (int k = ME_LANE; k < n; k += ME_NL) {
-        int j = k / cw, i = k - j * cw;
-        const uint8_t *p = a + (2 * j) * as + 2 * i;
-        int ds = (int) me_uavg4(p[0], p[1], p[as], p[as + 1]);
-        int hi = ds * quant16 >> 16;
-        atomicAdd(&hist[min(hi, 15)], 1);
+    {
+        const int gs = me_gshift(w);
+        if (gs >= 0) {
+            const int ng = ch << gs, gm = (1 << gs) - 1;
+            for (int g = ME_LANE; g < ng; g += ME_NL) {
+                int y = (g >> gs) * 2, x = (g & gm) * 4;
+                uint32_t r0 = me_ld4(a + y * as + x), r1 = me_ld4(a + (y + 1) * as + x);
+                int d0 = (int) (me_dot4(me_perm(r0, r1, 0x5410), ME_ONES, 2) >> 2);
+                int d1 = (int) (me_dot4(me_perm(r0, r1, 0x7632), ME_ONES, 2) >> 2);
+                atomicAdd(&hist[min(d0 * quant16 >> 16, 15)], 1);
+                atomicAdd(&hist[min(d1 * quant16 >> 16, 15)], 1);
+            }
+        } else {
+            for (int k = ME_LANE; k < n; k += ME_NL) {
+                int j = k / cw, i = k - j * cw;
+                const uint8_t *p = a + (2 * j) * as + 2 * i;
+                int ds = (int) me_uavg4(p[0], p[1], p[as], p[as + 1]);
+                int hi = ds * quant16 >> 16;
+                atomicAdd(&hist[min(hi, 15)], 1);
+            }
+        }
     }
     DSVCU_SYNCWARP();
     avg = 0;
@@ -437,10 +603,23 @@ DSVCU_DEV void
 me_c_average(const MePlane *pl, int x, int y, int w, int h, int *uavg, int *vavg)
 {
     int su = 0, sv = 0, n = w * h;
-    for (int k = ME_LANE; k < n; k += ME_NL) {
-        int j = k / w, i = k - j * w;
-        su += pl[1].data[(y + j) * pl[1].stride + x + i];
-        sv += pl[2].data[(y + j) * pl[2].stride + x + i];
+    const int gs = me_gshift(w);
+    if (gs >= 0) {
+        const int ng = h << gs, gm = (1 << gs) - 1;
+        unsigned uu = 0, uv = 0;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            int j = g >> gs, i = (g & gm) * 4;
+            uu = me_dot4(me_ld4(pl[1].data + (y + j) * pl[1].stride + x + i), ME_ONES, uu);
+            uv = me_dot4(me_ld4(pl[2].data + (y + j) * pl[2].stride + x + i), ME_ONES, uv);
+        }
+        su = (int) uu;
+        sv = (int) uv;
+    } else {
+        for (int k = ME_LANE; k < n; k += ME_NL) {
+            int j = k / w, i = k - j * w;
+            su += pl[1].data[(y + j) * pl[1].stride + x + i];
+            sv += pl[2].data[(y + j) * pl[2].stride + x + i];
+        }
     }
     su = me_wsum(su);
     sv = me_wsum(sv);
@@ -509,12 +688,29 @@ me_calc_eprm(const uint8_t *src, int ss, const uint8_t *mvr, int rs, int avg_src
     int ci = 0, cd = 0, cr = 0, n = w * h;
     avg_src -= 128;
     avg_ref -= 128;
-    for (int k = ME_LANE; k < n; k += ME_NL) {
-        int j = k / w, i = k - j * w;
-        int s = src[j * ss + i];
-        cr |= ((s - (int) mvr[j * rs + i]) + 128) & ~0xff;
-        ci |= (s - avg_ref) & ~0xff;
-        cd |= (s - avg_src) & ~0xff;
+    {
+        const int gs = me_gshift(w);
+        if (gs >= 0) {
+            const int ng = h << gs, gm = (1 << gs) - 1;
+            for (int g = ME_LANE; g < ng; g += ME_NL) {
+                int j = g >> gs, i = (g & gm) * 4;
+                uint32_t sw = me_ld4(src + j * ss + i), rw = me_ld4(mvr + j * rs + i);
+                for (int k = 0; k < 4; k++) {
+                    int s = (int) ((sw >> (8 * k)) & 255u);
+                    cr |= ((s - (int) ((rw >> (8 * k)) & 255u)) + 128) & ~0xff;
+                    ci |= (s - avg_ref) & ~0xff;
+                    cd |= (s - avg_src) & ~0xff;
+                }
+            }
+        } else {
+            for (int k = ME_LANE; k < n; k += ME_NL) {
+                int j = k / w, i = k - j * w;
+                int s = src[j * ss + i];
+                cr |= ((s - (int) mvr[j * rs + i]) + 128) & ~0xff;
+                ci |= (s - avg_ref) & ~0xff;
+                cd |= (s - avg_src) & ~0xff;
+            }
+        }
     }
     *eprmi = me_wor(ci != 0);
     *eprmd = me_wor(cd != 0);
@@ -525,52 +721,72 @@ me_calc_eprm(const uint8_t *src, int ss, const uint8_t *mvr, int rs, int avg_src
 
 #define ME_HPF(a, b, c, d) ((5 * ((b) + (c))) - ((a) + (d)))
 
-/* build the 34x34 half-pel and 68x68 quarter-pel images of the 17x17 window at r */
+/* Half-pel image (34 x 34, HP_STRIDE) of the 17 x 17 window at r, as the
+ * reference's hpel() builds it (hme.c:787-813).  The reference then expands it
+ * to a 68 x 68 quarter-pel image by bilinear averaging (qpel(), :815-837) of
+ * which the search samples 7 x 256 points; here those points are averaged from
+ * the half-pel image on the fly (me_qsample), same arithmetic. */
+#define ME_WIN (SP_DIM + 3) /* full-pel window rows/cols -1 .. SP_DIM+1 */
 DSVCU_DEV void
-me_interp(uint8_t *tmph, uint8_t *tmpq, int16_t *hbuf, const uint8_t *r, int rs)
+me_interp(uint8_t *tmph, uint8_t *win, int16_t *hbuf, const uint8_t *r, int rs)
 {
+    /* stage the full-pel window once */
+    for (int k = ME_LANE; k < ME_WIN * ME_WIN; k += ME_NL) {
+        int j = k / ME_WIN, i = k - j * ME_WIN;
+        win[k] = r[(j - 1) * rs + i - 1];
+    }
+    DSVCU_SYNCWARP();
     /* horizontal half-pel sums for rows -1 .. SP_DIM+1 */
-    for (int k = ME_LANE; k < (SP_DIM + 3) * SP_DIM; k += ME_NL) {
+    for (int k = ME_LANE; k < ME_WIN * SP_DIM; k += ME_NL) {
         int j = k / SP_DIM, i = k - j * SP_DIM;
-        const uint8_t *p = r + (j - 1) * rs + i;
+        const uint8_t *p = win + j * ME_WIN + i + 1;
         hbuf[k] = (int16_t) ME_HPF(p[-1], p[0], p[1], p[2]);
     }
     DSVCU_SYNCWARP();
     for (int k = ME_LANE; k < SP_DIM * SP_DIM; k += ME_NL) {
         int j = k / SP_DIM, i = k - j * SP_DIM;
-        const uint8_t *p = r + j * rs + i;
+        const uint8_t *p = win + (j + 1) * ME_WIN + i + 1;
         uint8_t *d = tmph + (2 * j) * HP_STRIDE + 2 * i;
         int c = ME_HPF(hbuf[k], hbuf[k + SP_DIM], hbuf[k + 2 * SP_DIM], hbuf[k + 3 * SP_DIM]);
         d[0] = p[0];
         d[1] = (uint8_t) me_u8((ME_HPF(p[-1], p[0], p[1], p[2]) + 4) >> 3);
-        d[HP_STRIDE] = (uint8_t) me_u8((ME_HPF(p[-rs], p[0], p[rs], p[2 * rs]) + 4) >> 3);
+        d[HP_STRIDE] = (uint8_t) me_u8((ME_HPF(p[-ME_WIN], p[0], p[ME_WIN], p[2 * ME_WIN]) + 4) >> 3);
         d[HP_STRIDE + 1] = (uint8_t) me_u8((c + 32) >> 6);
-    }
-    DSVCU_SYNCWARP();
-    /* quarter-pel by averaging; the last row/column read past the 34x34 image
-     * exactly like the reference (never sampled by the search) */
-    for (int k = ME_LANE; k < HP_STRIDE * HP_STRIDE; k += ME_NL) {
-        int j = k / HP_STRIDE, i = k - j * HP_STRIDE;
-        const uint8_t *h0 = tmph + j * HP_STRIDE + i;
-        uint8_t *d = tmpq + (2 * j) * QP_STRIDE + 2 * i;
-        int a = h0[0], b = h0[1], c = h0[HP_STRIDE], e = h0[HP_STRIDE + 1];
-        d[0] = (uint8_t) a;
-        d[1] = (uint8_t) me_avg2(a, b);
-        d[QP_STRIDE] = (uint8_t) me_avg2(a, c);
-        d[QP_STRIDE + 1] = (uint8_t) ((a + b + c + e + 2) >> 2);
     }
     DSVCU_SYNCWARP();
 }
 
+/* quarter-pel sample (qx, qy) of the image the reference's qpel() would build */
+DSVCU_DEV int
+me_qsample(const uint8_t *tmph, int qx, int qy)
+{
+    const uint8_t *h0 = tmph + (qy >> 1) * HP_STRIDE + (qx >> 1);
+    int a = h0[0];
+    if (qx & 1) {
+        if (qy & 1) return (a + h0[1] + h0[HP_STRIDE] + h0[HP_STRIDE + 1] + 2) >> 2;
+        return me_avg2(a, h0[1]);
+    }
+    if (qy & 1) return me_avg2(a, h0[HP_STRIDE]);
+    return a;
+}
+
+/* psy metric of the 16 x 16 source window against the quarter-pel image at
+ * offset (tx, ty) quarter pels (qpsad, hme.c:244-269) */
 DSVCU_DEV unsigned
-me_qpsad(const uint8_t *a, int as, const uint8_t *b, const MePsy &psy)
+me_qpsad(const uint8_t *a, int as, const uint8_t *tmph, int tx, int ty, const MePsy &psy)
 {
     unsigned acc = 0;
-    for (int k = ME_LANE; k < (SP_SZ / 2) * (SP_SZ / 2); k += ME_NL) {
-        int j = k / (SP_SZ / 2), i = k - j * (SP_SZ / 2);
-        const uint8_t *pa = a + (2 * j) * as + 2 * i;
-        acc += me_cell(pa[0], pa[1], pa[as], pa[as + 1], b[MEQ_OFF(i * 2, j * 2)], b[MEQ_OFF(i * 2 + 1, j * 2)],
-                       b[MEQ_OFF(i * 2, j * 2 + 1)], b[MEQ_OFF(i * 2 + 1, j * 2 + 1)], psy);
+    for (int g = ME_LANE; g < (SP_SZ / 2) * (SP_SZ / 4); g += ME_NL) {
+        /* one work item = 4 source pixels x 2 rows = two cells */
+        int y = (g >> 2) * 2, x = (g & 3) * 4;
+        uint32_t a0 = me_ld4(a + y * as + x), a1 = me_ld4(a + (y + 1) * as + x);
+        int qx = 4 + tx + 4 * x, qy = 4 + ty + 4 * y;
+        uint32_t B0 = (uint32_t) me_qsample(tmph, qx, qy) | ((uint32_t) me_qsample(tmph, qx + 4, qy) << 8) |
+                      ((uint32_t) me_qsample(tmph, qx, qy + 4) << 16) | ((uint32_t) me_qsample(tmph, qx + 4, qy + 4) << 24);
+        uint32_t B1 = (uint32_t) me_qsample(tmph, qx + 8, qy) | ((uint32_t) me_qsample(tmph, qx + 12, qy) << 8) |
+                      ((uint32_t) me_qsample(tmph, qx + 8, qy + 4) << 16) | ((uint32_t) me_qsample(tmph, qx + 12, qy + 4) << 24);
+        acc += me_cell4(me_perm(a0, a1, 0x5410), B0, psy);
+        acc += me_cell4(me_perm(a0, a1, 0x7632), B1, psy);
     }
     acc = me_wsumu(acc);
     return me_isqrt(acc) * (unsigned) SP_SZ * (unsigned) SP_SZ / (unsigned) SP_SZ;
@@ -578,13 +794,13 @@ me_qpsad(const uint8_t *a, int as, const uint8_t *b, const MePsy &psy)
 
 struct MeScratch {
     uint8_t tmph[(2 + HP_STRIDE) * (2 + HP_STRIDE)];
-    uint8_t tmpq[(4 + QP_STRIDE) * (4 + QP_STRIDE)];
+    uint8_t win[ME_WIN * ME_WIN + 16];
     int16_t hbuf[(SP_DIM + 3) * SP_DIM + 4];
     int hist[16];
 };
 
 DSVCU_DEV unsigned
-me_subpixel(const MeArgs &A, MeScratch *S, int *outx, int *outy, int fpelx, int fpely, int i, int j, unsigned best, int bx,
+me_subpixel(const MeArgs &A, MeScratch *S, int *outx, int *outy, int fpelx, int fpely, const MePred &pr, unsigned best, int bx,
             int by, int bw, int bh, const MePsy &psy)
 {
     const MePlane &sp = A.src[0], &rp = A.ref[0];
@@ -607,7 +823,7 @@ me_subpixel(const MeArgs &A, MeScratch *S, int *outx, int *outy, int fpelx, int 
     best = best * (unsigned) area_ratio >> 3;
     xx = bx + ((bw >> 1) - ((SP_SZ + 1) / 2));
     yy = by + ((bh >> 1) - ((SP_SZ + 1) / 2));
-    me_interp(S->tmph, S->tmpq, S->hbuf, rp.data + (yy + fpely - 1) * rp.stride + xx + fpelx - 1, rp.stride);
+    me_interp(S->tmph, S->win, S->hbuf, rp.data + (yy + fpely - 1) * rp.stride + xx + fpelx - 1, rp.stride);
 
     pri[0] = 0; pri[1] = -1;
     sec[0] = -1; sec[1] = 0;
@@ -629,7 +845,6 @@ me_subpixel(const MeArgs &A, MeScratch *S, int *outx, int *outy, int fpelx, int 
     diag[0] = pri[0] + sec[0];
     diag[1] = pri[1] + sec[1];
     {
-        const uint8_t *imq = S->tmpq + MEQ_OFF(1, 1);
         const uint8_t *ssp = sp.data + yy * sp.stride + xx;
         for (int n = 0; n <= 6; n++) {
             int t[2], evx, evy;
@@ -643,10 +858,10 @@ me_subpixel(const MeArgs &A, MeScratch *S, int *outx, int *outy, int fpelx, int 
                 t[1] = tv[1] * (1 << hp);
             }
             if (((t[0] | t[1]) & 1) && A.effort < 8) continue;
-            score = me_qpsad(ssp, sp.stride, imq + t[0] + t[1] * QP_STRIDE, psy);
+            score = me_qpsad(ssp, sp.stride, S->tmph, t[0], t[1], psy);
             evx = fpelx * 4 + t[0];
             evy = fpely * 4 + t[1];
-            score += (unsigned) me_mv_cost(A, i, j, evx, evy, 0);
+            score += (unsigned) me_mv_cost(A, pr, evx, evy, 0);
             if (best > score) {
                 best = score;
                 bestv[0] = t[0];
@@ -667,6 +882,38 @@ me_err_intra(const uint8_t *a, int as, const uint8_t *b, int bs, int avg_sb, int
 {
     unsigned isb = 0, isrc = 0, inter = 0;
     int cw = w / 2, ch = h / 2, n = cw * ch;
+    const int gs = me_gshift(w);
+    if (gs >= 0 && avg_sb >= 0 && avg_sb <= 255 && avg_src >= 0 && avg_src <= 255) {
+        const int ng = ch << gs, gm = (1 << gs) - 1;
+        const uint32_t sb4 = (uint32_t) avg_sb * ME_ONES, sr4 = (uint32_t) avg_src * ME_ONES;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            int y = (g >> gs) * 2, x = (g & gm) * 4;
+            uint32_t a0 = me_ld4(a + y * as + x), a1 = me_ld4(a + (y + 1) * as + x);
+            uint32_t b0 = me_ld4(b + y * bs + x), b1 = me_ld4(b + (y + 1) * bs + x);
+            for (int c = 0; c < 2; c++) {
+                uint32_t A = me_perm(a0, a1, c ? 0x7632 : 0x5410), B = me_perm(b0, b1, c ? 0x7632 : 0x5410);
+                int s0 = (int) (me_dot4(A, ME_ONES, 2) >> 2), s1 = (int) (me_dot4(B, ME_ONES, 2) >> 2);
+                int ae = (int) (me_dot4(me_absdiff4(A, B), ME_ONES, 2) >> 2);
+                int ta = (int) (me_dot4(me_absdiff4(A, me_perm(A, A, 0x0321)), ME_ONES, 2) >> 2);
+                int tb = (int) (me_dot4(me_absdiff4(B, me_perm(B, B, 0x0321)), ME_ONES, 2) >> 2);
+                inter += (unsigned) (me_sqr(ae) * ratio >> (5 - psy.err_w));
+                inter += (unsigned) (me_sqr(ta - tb) << psy.tex_w);
+                inter += (unsigned) (me_sqr(s0 - s1) << psy.avg_w);
+                ae = (int) (me_dot4(me_absdiff4(A, sb4), ME_ONES, 2) >> 2);
+                isb += (unsigned) (me_sqr(ae) << psy.err_w);
+                isb += (unsigned) (me_sqr(ta) << psy.tex_w);
+                isb += (unsigned) (me_sqr(s0 - avg_sb) << (psy.avg_w + 1));
+                ae = (int) (me_dot4(me_absdiff4(A, sr4), ME_ONES, 2) >> 2);
+                isrc += (unsigned) (me_sqr(ae) << psy.err_w);
+                isrc += (unsigned) (me_sqr(ta) << psy.tex_w);
+                isrc += (unsigned) (me_sqr(s0 - avg_src) << (psy.avg_w + 1));
+            }
+        }
+        *intra_err = me_wsumu(isb);
+        *intrasrc_err = me_wsumu(isrc);
+        *inter_err = me_wsumu(inter) * (unsigned) ratio >> 5;
+        return;
+    }
     for (int k = ME_LANE; k < n; k += ME_NL) {
         int j = k / cw, i = k - j * cw;
         const uint8_t *pa = a + (2 * j) * as + 2 * i, *pb = b + (2 * j) * bs + 2 * i;
@@ -806,6 +1053,8 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
     srcd = sp.data + by * sp.stride + bx;
     bw = min(sp.w - bx, A.y_w);
     bh = min(sp.h - by, A.y_h);
+    MePred pred;
+    me_movec_pred(A.mvf, nxb, i, j, &pred.x, &pred.y);
     cx[n] = 0;
     cy[n] = 0;
     n++;
@@ -881,10 +1130,8 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
             /* spatial predictions (hme.c:1202-1227); vectors pass through the
              * qpel->fpel rounding whatever unit they are stored in */
             if (level == 0) {
-                int px, py;
-                me_movec_pred(A.mvf, nxb, i, j, &px, &py);
-                cx[n] = me_sar_r2(px);
-                cy[n] = me_sar_r2(py);
+                cx[n] = me_sar_r2(pred.x);
+                cy[n] = me_sar_r2(pred.y);
                 n++;
             }
             if (i > 0) {
@@ -959,7 +1206,7 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
             if (me_invalid_block(rp.w, rp.h, bx + dx, by + dy, bw, bh, 0)) continue;
             score = me_hier_metr(level, srcd, sp.stride, rp.data + (by + dy) * rp.stride + bx + dx, rp.stride, bw, bh, psy);
             if (dx == 0 && dy == 0) score_zero = score;
-            score += (unsigned) me_mv_cost(A, i, j, dx * step * 4, dy * step * 4, level);
+            score += (unsigned) me_mv_cost(A, pred, dx * step * 4, dy * step * 4, level);
             if (dx == lax && dy == lay) score = (unsigned) max((int) score - (motion_bias >> level), 0);
             if (best_score > score) {
                 best_score = score;
@@ -1004,7 +1251,7 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
                     good_enough = 1;
                     break;
                 }
-                score += (unsigned) me_mv_cost(A, i, j, tvx * step * 4, tvy * step * 4, level);
+                score += (unsigned) me_mv_cost(A, pred, tvx * step * 4, tvy * step * 4, level);
                 if (best > score) {
                     best = score;
                     dx = tvx;
@@ -1018,7 +1265,7 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
             tvy = dy + recty[(metr[2] <= metr[3]) ? 3 : 4];
             if (me_invalid_block(rp.w, rp.h, bx + tvx, by + tvy, bw, bh, 0)) break;
             score = me_hier_metr(level, srcd, sp.stride, rp.data + (by + tvy) * rp.stride + bx + tvx, rp.stride, bw, bh, psy);
-            score += (unsigned) me_mv_cost(A, i, j, tvx * step * 4, tvy * step * 4, level);
+            score += (unsigned) me_mv_cost(A, pred, tvx * step * 4, tvy * step * 4, level);
             if (best > score) {
                 best = score;
                 dx = tvx;
@@ -1043,14 +1290,14 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
         best_fp = best;
         if (A.effort >= 4) {
             if (!me_invalid_block(rp.w, rp.h, bx + lax, by + lay, bw, bh, 4)) {
-                best = me_subpixel(A, S, &subx, &suby, lax, lay, i, j, best_fp, bx, by, bw, bh, psy);
+                best = me_subpixel(A, S, &subx, &suby, lax, lay, pred, best_fp, bx, by, bw, bh, psy);
                 if (subx | suby) {
                     fpelx = lax;
                     fpely = lay;
                 }
             }
             if (!(subx | suby) && !good_enough && !me_invalid_block(rp.w, rp.h, bx + fpelx, by + fpely, bw, bh, 4)) {
-                best = me_subpixel(A, S, &subx, &suby, fpelx, fpely, i, j, best_fp, bx, by, bw, bh, psy);
+                best = me_subpixel(A, S, &subx, &suby, fpelx, fpely, pred, best_fp, bx, by, bw, bh, psy);
             }
         }
         mv.x = fpelx * 4 + subx;
@@ -1202,9 +1449,9 @@ k_me_level(MeArgs A)
             int need = col + 1;
             if (seen < need) {
 #ifndef DSVCU_EMU
-                do {
-                    seen = *(volatile const int *) (A.progress + row - 1);
-                } while (seen < need);
+                while ((seen = *(volatile const int *) (A.progress + row - 1)) < need) {
+                    __nanosleep(64); /* leave the issue slots to warps that have work */
+                }
                 __threadfence();
 #else
                 seen = 0x7fffffff;
