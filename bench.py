@@ -32,6 +32,10 @@ import sys
 import threading
 import time
 
+# one CUDA stream per encoder/decoder instance: give them separate hardware queues
+# (must be set before the CUDA context is created; the library does the same)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -55,7 +59,7 @@ def synth_chunks(ndistinct):
         try:
             a = np.load(cache, mmap_mode="r")
             if a.size == ndistinct * GOP * FRAME_BYTES:
-                return np.ascontiguousarray(a)
+                return np.ascontiguousarray(a).reshape(-1)
         except Exception:
             pass
     out = np.empty((ndistinct * GOP, FRAME_BYTES), np.uint8)

@@ -27,6 +27,19 @@ size_t dsvcu_emu_smem_size = 0;
 #define PSY_I_VISUAL_MASKING 4
 #define PSY_P_VISUAL_MASKING 8
 
+#ifndef DSVCU_EMU
+/* Every encoder / decoder instance owns a stream and they are meant to overlap.
+ * Streams are multiplexed onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues
+ * (default 8): with more instances than queues, one instance's short kernels
+ * line up behind another's long wavefront kernel.  Ask for the maximum unless
+ * the user chose a value; only effective if no CUDA context exists yet. */
+__attribute__((constructor)) static void
+dsvcu_more_connections(void)
+{
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+}
+#endif
+
 static char g_err[256] = "";
 static long long g_launches = 0; /* kernels launched by every context of this process */
 
@@ -113,8 +126,26 @@ struct dsvcu_ctx {
 #ifndef DSVCU_EMU
     cudaEvent_t ev0, ev1;
     cudaEvent_t ev_sym[3]; /* symbols of plane i are in pinned memory */
+    cudaEvent_t ev_wait;
 #endif
 };
+
+/* Host wait for everything queued on the context's stream.  Encoder / decoder
+ * instances run on many host threads per GPU: the wait blocks in the OS
+ * (cudaEventBlockingSync) instead of spinning, so waiting threads do not take
+ * cores away from the ones that are packing bits or queueing kernels. */
+static int
+ctx_wait(dsvcu_ctx *c)
+{
+#ifndef DSVCU_EMU
+    cudaError_t e = cudaEventRecord(c->ev_wait, c->stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(c->ev_wait);
+    return (int) e;
+#else
+    (void) c;
+    return 0;
+#endif
+}
 
 static int
 ilb2(unsigned n) /* dsv_lb2, dsv.c:449-459: ceil(log2(n)) */
@@ -209,8 +240,9 @@ dsvcu_ctx_create(dsvcu_ctx **out, int device, int width, int height, int subsamp
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     for (i = 0; i < 3; i++) {
-        CK(cudaEventCreateWithFlags(&c->ev_sym[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_sym[i], cudaEventDisableTiming | cudaEventBlockingSync));
     }
+    CK(cudaEventCreateWithFlags(&c->ev_wait, cudaEventDisableTiming | cudaEventBlockingSync));
 #endif
     maxplane = (size_t) c->cw[0] * c->ch[0];
     if ((size_t) c->cw[1] * c->ch[1] > maxplane) maxplane = (size_t) c->cw[1] * c->ch[1];
@@ -271,6 +303,7 @@ dsvcu_ctx_destroy(dsvcu_ctx *c)
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     for (i = 0; i < 3; i++) cudaEventDestroy(c->ev_sym[i]);
+    cudaEventDestroy(c->ev_wait);
     cudaStreamDestroy(c->stream);
 #endif
     free(c);
@@ -310,7 +343,7 @@ extern "C" int
 dsvcu_sync(dsvcu_ctx *c)
 {
     (void) c;
-    CK(dsvcu_stream_sync(c->stream));
+    CK(ctx_wait(c));
     return 0;
 }
 
@@ -1322,7 +1355,7 @@ dsvcu_hme_fetch(dsvcu_ctx *c, void *mvs_out, int nblocks, int *intra_pct, int *s
     if (ensure_hmvs(c, nblocks)) return -1;
     CK(dsvcu_d2h_async(c->h_me, c->d_me, 16 * sizeof(int), c->stream));
     CK(dsvcu_d2h_async(c->h_mvs, c->d_mvs, (size_t) nblocks * sizeof(dsvcu_mv), c->stream));
-    CK(dsvcu_stream_sync(c->stream));
+    CK(ctx_wait(c));
     memcpy(mvs_out, c->h_mvs, (size_t) nblocks * sizeof(dsvcu_mv));
     elig = c->h_me[4] ? c->h_me[4] : 1;
     *intra_pct = (c->h_me[2] * 100) / nblocks;
@@ -1361,7 +1394,7 @@ dsvcu_intra_analysis_async(dsvcu_ctx *c, const dsvcu_fmeta *fm, dsvcu_frame *src
 extern "C" int
 dsvcu_intra_analysis_fetch(dsvcu_ctx *c, void *mvs_out, int nblocks)
 {
-    CK(dsvcu_stream_sync(c->stream));
+    CK(ctx_wait(c));
     memcpy(mvs_out, c->h_mvs, (size_t) nblocks * sizeof(dsvcu_mv));
     return 0;
 }
@@ -1410,7 +1443,7 @@ extern "C" int
 dsvcu_frame_luma_avg(dsvcu_ctx *c, dsvcu_frame *f, unsigned *avg)
 {
     if (dsvcu_frame_luma_avg_async(c, f)) return -1;
-    CK(dsvcu_stream_sync(c->stream));
+    CK(ctx_wait(c));
     *avg = dsvcu_frame_luma_avg_result(c);
     return 0;
 }

@@ -792,6 +792,57 @@ me_qpsad(const uint8_t *a, int as, const uint8_t *tmph, int tx, int ty, const Me
     return me_isqrt(acc) * (unsigned) SP_SZ * (unsigned) SP_SZ / (unsigned) SP_SZ;
 }
 
+/* cell metric with the source-side terms (mean s0, texture ta) precomputed */
+DSVCU_DEV unsigned
+me_cell4_pre(uint32_t A, int s0, int ta, uint32_t B, const MePsy &p)
+{
+    int s1 = (int) ((me_dot4(B, ME_ONES, 2)) >> 2);
+    int se = (int) ((me_dot4(me_absdiff4(A, B), ME_ONES, 2)) >> 2);
+    int tb = (int) ((me_dot4(me_absdiff4(B, me_perm(B, B, 0x0321)), ME_ONES, 2)) >> 2);
+    unsigned acc = (unsigned) (me_sqr(se) << p.err_w);
+    acc += (unsigned) (me_sqr(ta - tb) << p.tex_w);
+    acc += (unsigned) (me_sqr(s0 - s1) << p.avg_w);
+    return acc;
+}
+
+/* me_qpsad for up to 7 offsets in one pass over the source window: the source
+ * cells are loaded (and their own terms computed) once, and the offsets give
+ * independent accumulation chains */
+#define ME_MAXSP 7
+DSVCU_DEV void
+me_qpsad_multi(const uint8_t *a, int as, const uint8_t *tmph, int nv, const int *tx, const int *ty, const MePsy &psy,
+               unsigned *out)
+{
+    unsigned acc[ME_MAXSP];
+    for (int v = 0; v < ME_MAXSP; v++) acc[v] = 0;
+    for (int g = ME_LANE; g < (SP_SZ / 2) * (SP_SZ / 4); g += ME_NL) {
+        int y = (g >> 2) * 2, x = (g & 3) * 4;
+        uint32_t a0 = me_ld4(a + y * as + x), a1 = me_ld4(a + (y + 1) * as + x);
+        uint32_t A0 = me_perm(a0, a1, 0x5410), A1 = me_perm(a0, a1, 0x7632);
+        int s00 = (int) (me_dot4(A0, ME_ONES, 2) >> 2), s01 = (int) (me_dot4(A1, ME_ONES, 2) >> 2);
+        int ta0 = (int) (me_dot4(me_absdiff4(A0, me_perm(A0, A0, 0x0321)), ME_ONES, 2) >> 2);
+        int ta1 = (int) (me_dot4(me_absdiff4(A1, me_perm(A1, A1, 0x0321)), ME_ONES, 2) >> 2);
+#ifndef DSVCU_EMU
+#pragma unroll
+#endif
+        for (int v = 0; v < ME_MAXSP; v++) {
+            if (v < nv) {
+                int qx = 4 + tx[v] + 4 * x, qy = 4 + ty[v] + 4 * y;
+                uint32_t B0 = (uint32_t) me_qsample(tmph, qx, qy) | ((uint32_t) me_qsample(tmph, qx + 4, qy) << 8) |
+                              ((uint32_t) me_qsample(tmph, qx, qy + 4) << 16) |
+                              ((uint32_t) me_qsample(tmph, qx + 4, qy + 4) << 24);
+                uint32_t B1 = (uint32_t) me_qsample(tmph, qx + 8, qy) | ((uint32_t) me_qsample(tmph, qx + 12, qy) << 8) |
+                              ((uint32_t) me_qsample(tmph, qx + 8, qy + 4) << 16) |
+                              ((uint32_t) me_qsample(tmph, qx + 12, qy + 4) << 24);
+                acc[v] += me_cell4_pre(A0, s00, ta0, B0, psy) + me_cell4_pre(A1, s01, ta1, B1, psy);
+            }
+        }
+    }
+    for (int v = 0; v < ME_MAXSP; v++) {
+        if (v < nv) out[v] = me_isqrt(me_wsumu(acc[v])) * (unsigned) SP_SZ * (unsigned) SP_SZ / (unsigned) SP_SZ;
+    }
+}
+
 struct MeScratch {
     uint8_t tmph[(2 + HP_STRIDE) * (2 + HP_STRIDE)];
     uint8_t win[ME_WIN * ME_WIN + 16];
@@ -846,8 +897,12 @@ me_subpixel(const MeArgs &A, MeScratch *S, int *outx, int *outy, int fpelx, int 
     diag[1] = pri[1] + sec[1];
     {
         const uint8_t *ssp = sp.data + yy * sp.stride + xx;
+        int tvx[ME_MAXSP], tvy[ME_MAXSP], nv = 0;
+        unsigned sc[ME_MAXSP];
+        /* test order of the reference (hme.c:1137-1160): half then quarter
+         * steps along pri, sec, diag, then pri + diag */
         for (int n = 0; n <= 6; n++) {
-            int t[2], evx, evy;
+            int t[2];
             if (n == 6) {
                 t[0] = pri[0] + diag[0];
                 t[1] = pri[1] + diag[1];
@@ -858,14 +913,17 @@ me_subpixel(const MeArgs &A, MeScratch *S, int *outx, int *outy, int fpelx, int 
                 t[1] = tv[1] * (1 << hp);
             }
             if (((t[0] | t[1]) & 1) && A.effort < 8) continue;
-            score = me_qpsad(ssp, sp.stride, S->tmph, t[0], t[1], psy);
-            evx = fpelx * 4 + t[0];
-            evy = fpely * 4 + t[1];
-            score += (unsigned) me_mv_cost(A, pr, evx, evy, 0);
+            tvx[nv] = t[0];
+            tvy[nv] = t[1];
+            nv++;
+        }
+        me_qpsad_multi(ssp, sp.stride, S->tmph, nv, tvx, tvy, psy, sc);
+        for (int n = 0; n < nv; n++) {
+            score = sc[n] + (unsigned) me_mv_cost(A, pr, fpelx * 4 + tvx[n], fpely * 4 + tvy[n], 0);
             if (best > score) {
                 best = score;
-                bestv[0] = t[0];
-                bestv[1] = t[1];
+                bestv[0] = tvx[n];
+                bestv[1] = tvy[n];
             }
         }
     }
@@ -1025,6 +1083,33 @@ me_test_intra_c(const MeArgs &A, MeMv *mv, unsigned mad, unsigned detail_src, un
     if (mv->submask) mv->flags |= MVF_INTRA;
 }
 
+/* full-pel metric with a per-block memo: the candidate scan and the descent
+ * probe overlapping positions (the reference recomputes them; the value is a
+ * pure function of the position) */
+#define ME_MEMO 24
+struct MeMemo {
+    int n;
+    int x[ME_MEMO], y[ME_MEMO];
+    unsigned v[ME_MEMO];
+};
+
+DSVCU_DEV unsigned
+me_eval(MeMemo &mm, int level, const uint8_t *srcd, int ss, const MePlane &rp, int bx, int by, int dx, int dy, int bw, int bh,
+        const MePsy &psy)
+{
+    for (int k = 0; k < mm.n; k++) {
+        if (mm.x[k] == dx && mm.y[k] == dy) return mm.v[k];
+    }
+    unsigned sc = me_hier_metr(level, srcd, ss, rp.data + (by + dy) * rp.stride + bx + dx, rp.stride, bw, bh, psy);
+    if (mm.n < ME_MEMO) {
+        mm.x[mm.n] = dx;
+        mm.y[mm.n] = dy;
+        mm.v[mm.n] = sc;
+        mm.n++;
+    }
+    return sc;
+}
+
 /* ---- one block of refine_level (hme.c:1413-1823) ---- */
 
 #define ME_MAXCAND 40
@@ -1054,6 +1139,8 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
     bw = min(sp.w - bx, A.y_w);
     bh = min(sp.h - by, A.y_h);
     MePred pred;
+    MeMemo memo;
+    memo.n = 0;
     me_movec_pred(A.mvf, nxb, i, j, &pred.x, &pred.y);
     cx[n] = 0;
     cy[n] = 0;
@@ -1204,7 +1291,7 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
             dx = cx[k];
             dy = cy[k];
             if (me_invalid_block(rp.w, rp.h, bx + dx, by + dy, bw, bh, 0)) continue;
-            score = me_hier_metr(level, srcd, sp.stride, rp.data + (by + dy) * rp.stride + bx + dx, rp.stride, bw, bh, psy);
+            score = me_eval(memo, level, srcd, sp.stride, rp, bx, by, dx, dy, bw, bh, psy);
             if (dx == 0 && dy == 0) score_zero = score;
             score += (unsigned) me_mv_cost(A, pred, dx * step * 4, dy * step * 4, level);
             if (dx == lax && dy == lay) score = (unsigned) max((int) score - (motion_bias >> level), 0);
@@ -1241,8 +1328,7 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
                 tvx = dx + rectx[k];
                 tvy = dy + recty[k];
                 if (me_invalid_block(rp.w, rp.h, bx + tvx, by + tvy, bw, bh, 0)) continue;
-                score = me_hier_metr(level, srcd, sp.stride, rp.data + (by + tvy) * rp.stride + bx + tvx, rp.stride, bw, bh,
-                                     psy);
+                score = me_eval(memo, level, srcd, sp.stride, rp, bx, by, tvx, tvy, bw, bh, psy);
                 if (k >= 1) metr[k - 1] = score;
                 if (level == 0 && !tvx && !tvy && score <= qthresh) {
                     dx = tvx;
@@ -1264,7 +1350,7 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
             tvx = dx + rectx[(metr[0] <= metr[1]) ? 1 : 2];
             tvy = dy + recty[(metr[2] <= metr[3]) ? 3 : 4];
             if (me_invalid_block(rp.w, rp.h, bx + tvx, by + tvy, bw, bh, 0)) break;
-            score = me_hier_metr(level, srcd, sp.stride, rp.data + (by + tvy) * rp.stride + bx + tvx, rp.stride, bw, bh, psy);
+            score = me_eval(memo, level, srcd, sp.stride, rp, bx, by, tvx, tvy, bw, bh, psy);
             score += (unsigned) me_mv_cost(A, pred, tvx * step * 4, tvy * step * 4, level);
             if (best > score) {
                 best = score;
@@ -1289,14 +1375,20 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
         if (fpelx == lax && fpely == lay) best += (unsigned) motion_bias;
         best_fp = best;
         if (A.effort >= 4) {
+            int tried_la = 0;
             if (!me_invalid_block(rp.w, rp.h, bx + lax, by + lay, bw, bh, 4)) {
                 best = me_subpixel(A, S, &subx, &suby, lax, lay, pred, best_fp, bx, by, bw, bh, psy);
+                tried_la = 1;
                 if (subx | suby) {
                     fpelx = lax;
                     fpely = lay;
                 }
             }
-            if (!(subx | suby) && !good_enough && !me_invalid_block(rp.w, rp.h, bx + fpelx, by + fpely, bw, bh, 4)) {
+            /* the reference repeats the refinement around the full-pel winner;
+             * when that is the position just tried (and nothing was found) the
+             * second pass would recompute the very same numbers */
+            if (!(subx | suby) && !good_enough && !(tried_la && fpelx == lax && fpely == lay) &&
+                !me_invalid_block(rp.w, rp.h, bx + fpelx, by + fpely, bw, bh, 4)) {
                 best = me_subpixel(A, S, &subx, &suby, fpelx, fpely, pred, best_fp, bx, by, bw, bh, psy);
             }
         }

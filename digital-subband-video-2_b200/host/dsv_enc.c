@@ -27,6 +27,30 @@
 #include "dsv_host.h"
 #include "../../include/dsv_encoder.h"
 
+#include <time.h>
+
+/* optional wall-clock phase accounting (DSV_PROFILE=1): where one encoder
+ * instance spends its time, summed over pictures and printed by dsv_enc_free */
+static int g_prof = -1;
+enum { PH_UPLOAD, PH_ANALYSIS_WAIT, PH_DECIDE, PH_SIDEINFO, PH_QUEUE, PH_SYM_WAIT, PH_PACK, PH_N };
+static const char *ph_name[PH_N] = { "upload+queue analysis", "wait analysis", "decisions", "side info bits",
+                                     "queue pixel pipeline", "wait symbols", "pack planes" };
+static double
+now_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+#define PROF_MARK(g, ph)                         \
+    do {                                         \
+        if (g_prof > 0) {                        \
+            double t_ = now_ms();                \
+            (g)->ph_ms[ph] += t_ - (g)->ph_t0;   \
+            (g)->ph_t0 = t_;                     \
+        }                                        \
+    } while (0)
+
 #define QPCT(pct) ((pct) * DSV_RC_QUAL_SCALE)
 #define ISQ(x) ((x) * (x))
 
@@ -46,6 +70,8 @@ struct _DSV_ENCDATA {
     DSV_MV *mvs;              /* this picture's field (host copy) */
     DSV_MV *imv;              /* intra analysis flags (host copy) */
     int nblk;
+    double ph_ms[8], ph_t0;
+    int ph_frames;
 };
 
 int dsv_get_thread_device(void);
@@ -56,6 +82,13 @@ gpu_state_free(DSV_ENCDATA *g)
     int i;
     if (!g) {
         return;
+    }
+    if (g_prof > 0 && g->ph_frames) {
+        double tot = 0;
+        for (i = 0; i < PH_N; i++) tot += g->ph_ms[i];
+        printf("[dsv_enc profile] %d pictures, %.2f ms/picture:", g->ph_frames, tot / g->ph_frames);
+        for (i = 0; i < PH_N; i++) printf(" %s %.2f;", ph_name[i], g->ph_ms[i] / g->ph_frames);
+        printf("\n");
     }
     if (g->ctx) {
         dsvcu_sync(g->ctx);
@@ -854,6 +887,11 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
         return -1;
     }
     *pg = g;
+    if (g_prof < 0) {
+        g_prof = getenv("DSV_PROFILE") ? 1 : 0;
+    }
+    g->ph_t0 = g_prof > 0 ? now_ms() : 0;
+    g->ph_frames++;
     src = g->src[g->cur];
     rec = g->rec[g->cur];
     ref_src = g->src[g->cur ^ 1];
@@ -901,6 +939,7 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
     if (enc->do_dark_intra_boost && enc->rc_mode != DSV_RATE_CONTROL_CQP) {
         GPU(dsvcu_frame_luma_avg_async(g->ctx, dsvcu_pyramid_level(g->src_pyr[g->cur], enc->pyramid_levels)));
     }
+    PROF_MARK(g, PH_UPLOAD);
     /* first (and for most pictures only) wait on analysis results */
     if (tried_motion) {
         GPU(dsvcu_hme_fetch(g->ctx, g->mvs, nblk, &enc->curr_intra_pct, &enc->curr_scblocks, &enc->avg_err));
@@ -913,6 +952,7 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
     if (!p->has_ref) {
         GPU(dsvcu_intra_analysis_fetch(g->ctx, g->imv, nblk));
     }
+    PROF_MARK(g, PH_ANALYSIS_WAIT);
     top_avg = dsvcu_frame_luma_avg_result(g->ctx);
     if (enc->variable_i_interval && forced_intra) {
         enc->prev_gop = fnum;
@@ -924,6 +964,7 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
     pick_loop_filter(enc, p, quant);
     dsv_fmeta_from_params(&fm, p, p->has_ref, fnum);
 
+    PROF_MARK(g, PH_DECIDE);
     /* ---- picture packet: header and block side information (host) ---- */
     dsv_bw_init(&bw, (size_t) nblk * 8 + 4096);
     put_packet_header(&bw, DSV_MAKE_PT(p->is_ref, p->has_ref));
@@ -957,6 +998,7 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
     }
     dsv_bw_align(&bw);
 
+    PROF_MARK(g, PH_SIDEINFO);
     /* ---- pixel pipeline (device), queued in one go ---- */
     GPU(dsvcu_set_blockdata(g->ctx, enc->blockdata, nblk));
     if (p->has_ref) {
@@ -991,13 +1033,16 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
         GPU(dsvcu_pyramid_build(g->ctx, g->ref_pyr, rec));
     }
 
+    PROF_MARK(g, PH_QUEUE);
     /* ---- coefficient planes: pack symbols as they arrive ---- */
     for (i = 0; i < 3; i++) {
         const dsvcu_symbol *syms;
         int nsym, dc, cw, ch;
         GPU(dsvcu_fetch_symbols(g->ctx, i, &syms, &nsym, &dc));
+        PROF_MARK(g, PH_SYM_WAIT);
         dsvcu_coefs_plane_dims(g->coefs, i, &cw, &ch);
         dsv_hzcc_write_plane(&bw, syms, nsym, dc, cw, ch);
+        PROF_MARK(g, PH_PACK);
     }
     finish_packet(&bw, out);
 

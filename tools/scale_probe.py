@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""encode throughput vs host threads, with the per-phase profile of dsv_enc"""
+import ctypes as C, os, sys, time
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench, util
+import torch
+P = util.pkg(); lib = P.load()
+data = bench.synth_chunks(2)
+GOPN = int(os.environ.get("GOPN", "24"))
+for threads in [int(t) for t in sys.argv[1].split(",")]:
+    nfr = threads * GOPN
+    host = torch.empty(nfr * bench.FRAME_BYTES, dtype=torch.uint8, pin_memory=True)
+    hv = host.numpy()
+    for c in range(threads):
+        k = c % 2
+        hv[c*GOPN*bench.FRAME_BYTES:(c+1)*GOPN*bench.FRAME_BYTES] = data[k*48*bench.FRAME_BYTES:(k*48+GOPN)*bench.FRAME_BYTES]
+    dev = host.cuda(); torch.cuda.synchronize()
+    devs = (C.c_int * 1)(0)
+    pool = lib.dsv_pool_create(threads, devs, 1)
+    o = P.enc_opts(bench.W, bench.H, P.SUBSAMP_420, (30, 1), qp=60, gop=48, noeos=1)
+    out, outn = C.c_void_p(), C.c_size_t()
+    libc = C.CDLL(None); libc.free.argtypes = [C.c_void_p]
+    for rep in range(3):
+        t0 = time.perf_counter()
+        lib.dsv_pool_encode(pool, C.byref(o), C.c_void_p(dev.data_ptr()), nfr, GOPN, C.byref(out), C.byref(outn))
+        dt = time.perf_counter() - t0
+        libc.free(out)
+    print("threads %2d: %6.1f fps  (%.1f ms/frame/stream)" % (threads, nfr / dt, 1000 * dt / GOPN), flush=True)
+    lib.dsv_pool_destroy(pool)
