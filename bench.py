@@ -318,7 +318,8 @@ def run_own(args):
     P = util.pkg()
     lib = P.load()
     cores = cpu_count()
-    threads = args.threads or max(2, min(16, cores // max(1, world)))
+    # instances block in event waits most of the time: two per core, at most one per hardware queue (32)
+    threads = args.threads or max(2, min(32, 2 * cores // max(1, world)))
     chunks = args.chunks or threads
     nframes = chunks * GOP
 

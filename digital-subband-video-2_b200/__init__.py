@@ -317,3 +317,24 @@ def decode_frames(data, emu=False, threads=1, devices=None):
     if r:
         raise RuntimeError("decode failed: %s" % lib.dsvcu_last_error().decode())
     return meta, nfr.value, _take(lib, out, n)
+
+
+def rank_range(nchunks, rank, world):
+    """Closed-GOP chunks [first, last) owned by `rank` of `world` ranks (one rank
+    per GPU): contiguous ranges, sizes differing by at most one.  Chunks are
+    independent (parallel_encode_yuv.sh semantics), so ranks never exchange
+    data; the host concatenates the per-rank byte strings in rank order."""
+    base, extra = divmod(nchunks, world)
+    first = rank * base + min(rank, extra)
+    return first, first + base + (1 if rank < extra else 0)
+
+
+def encode_rank_shard(opts, yuv, nframes, chunk, rank, world, emu=False, threads=1, device=0):
+    """This rank's part of a sharded encode: bytes of its chunk range."""
+    nchunks = (nframes + chunk - 1) // chunk
+    first, last = rank_range(nchunks, rank, world)
+    if first >= last:
+        return b""
+    fsz = len(yuv) // nframes
+    f0, f1 = first * chunk, min(nframes, last * chunk)
+    return encode_frames(opts, yuv[f0 * fsz:f1 * fsz], f1 - f0, emu=emu, chunk=chunk, threads=threads, devices=[device])

@@ -224,6 +224,24 @@ dsv_host_copy_planes(DSV_FRAME *dst, DSV_FRAME *src)
     }
 }
 
+/* Host-side frame copies (reference frame.c:185-207, :436-446 semantics for
+ * the visible area).  Bordered HOST frames are not part of this build -- the
+ * padded pictures the operators read live on the device and are extended there
+ * (dsvcu_extend_frame) -- so a host copy never synthesises border pixels. */
+void
+dsv_frame_copy(DSV_FRAME *dst, DSV_FRAME *src)
+{
+    dsv_host_copy_planes(dst, src);
+}
+
+DSV_FRAME *
+dsv_clone_frame(DSV_FRAME *f, int border)
+{
+    DSV_FRAME *d = dsv_mk_frame(f->format, f->width, f->height, border);
+    dsv_host_copy_planes(d, f);
+    return d;
+}
+
 /* ------------------------------------------------------------ raw YUV I/O */
 
 static size_t
