@@ -203,6 +203,7 @@ def load(emu=False):
         "dsvcu_timer_stop_ms": (ip, [vp, P(C.c_float)]),
         "dsvcu_launch_count": (C.c_longlong, [vp]),
         "dsvcu_total_launches": (C.c_longlong, []),
+        "dsvcu_isqrt": (C.c_uint, [C.c_uint]),
     }
     for name, (res, args) in sig.items():
         try:

@@ -353,6 +353,15 @@ dsvcu_launch_count(dsvcu_ctx *c)
     return c->launches;
 }
 
+/* host evaluation of the integer square root the motion search uses (same
+ * source as the device function); lets the test-suite check it against the
+ * reference's digit-by-digit form without a GPU */
+extern "C" unsigned
+dsvcu_isqrt(unsigned n)
+{
+    return me_isqrt(n);
+}
+
 extern "C" long long
 dsvcu_total_launches(void)
 {

@@ -86,6 +86,7 @@ extern size_t dsvcu_emu_smem_size;
 #define DSVCU_SYNCWARP() ((void) 0)
 #define DSVCU_FENCE() ((void) 0)
 #define __restrict__
+#define __align__(n) alignas(n)
 #define __launch_bounds__(...)
 
 static inline void

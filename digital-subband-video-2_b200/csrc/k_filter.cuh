@@ -264,10 +264,76 @@ f_neighbordif2(const dsvcu_mv *vecs, int nbh, int x, int y, int *dx, int *dy)
     *dy = f_abs(vx1 - cmx) + f_abs(vy1 - cmy);
 }
 
+/* ---- per-cell staging.  A cell reads and writes inside the 11 x 11 pixel
+ * neighbourhood rows y-3..y+7, cols x-3..x+7.  Instead of three dependent
+ * round trips to L2 (texture probe, horizontal pass, vertical pass) the warp
+ * copies the neighbourhood (11 rows x 3 aligned words) into shared memory in
+ * one batch, filters there, and writes back only the words its filters own
+ * (rows y..y+3 for the horizontal pass, column word x..x+3 rows y-2..y+6 for the
+ * vertical pass, the cell itself for the sharpener) -- the same pixels the
+ * wavefront protocol already reserves for this cell. ---- */
+#define FT_S 16                      /* tile pitch */
+#define FT_ROWS 11
+#define FT_BYTES (FT_ROWS * FT_S)
+#define FT_ORG (3 * FT_S + 4)        /* tile offset of pixel (x, y) */
+
+DSVCU_DEV void
+f_tile_load(uint8_t *T, const FiltArgs &A, int x, int y)
+{
+    for (int k = FILT_LANE; k < FT_ROWS * 3; k += FILT_NLANES) {
+        int r = k / 3, q = k - r * 3;
+        const uint8_t *g = A.data + (ptrdiff_t) (y - 3 + r) * A.stride + x - 4 + 4 * q;
+#ifndef DSVCU_EMU
+        *(uint32_t *) (T + r * FT_S + 4 * q) = *(volatile const uint32_t *) g;
+#else
+        memcpy(T + r * FT_S + 4 * q, g, 4);
+#endif
+    }
+    DSVCU_SYNCWARP();
+}
+
+/* what: 1 = horizontal pass region, 2 = vertical pass region, 4 = the cell */
+DSVCU_DEV void
+f_tile_store(const uint8_t *T, const FiltArgs &A, int x, int y, int what)
+{
+    DSVCU_SYNCWARP();
+    for (int k = FILT_LANE; k < 12 + 9; k += FILT_NLANES) {
+        int r, q;
+        if (k < 12) {
+            if (!(what & 5)) continue;
+            r = 3 + k / 3;
+            q = k % 3;
+            if (!(what & 1) && q != 1) continue; /* sharpener only: the cell's own word */
+        } else {
+            if (!(what & 2)) continue;
+            r = 1 + (k - 12);
+            q = 1;
+            if ((what & 5) && r >= 3 && r < 7) continue; /* already written above */
+        }
+        uint8_t *g = A.data + (ptrdiff_t) (y - 3 + r) * A.stride + x - 4 + 4 * q;
+#ifndef DSVCU_EMU
+        *(uint32_t *) g = *(const uint32_t *) (T + r * FT_S + 4 * q);
+#else
+        memcpy(g, T + r * FT_S + 4 * q, 4);
+#endif
+    }
+}
+
+/* view of the tile with the plane's coordinates (pixel (x,y) at T + FT_ORG) */
+DSVCU_DEV FiltArgs
+f_tile_view(const FiltArgs &A, uint8_t *T, int x, int y)
+{
+    FiltArgs L = A;
+    L.data = T + FT_ORG - ((ptrdiff_t) y * FT_S + x);
+    L.stride = FT_S;
+    return L;
+}
+
 /* one 4x4 cell of luma_filter (bmc.c:492-600) */
 DSVCU_DEV int
-f_luma_cell(const FiltArgs &A, int i, int j)
+f_luma_cell(const FiltArgs &G, uint8_t *T, int i, int j)
 {
+    const FiltArgs &A = G;
     const int nsbx = A.w / 4, nsby = A.h / 4;
     const int x = i * 4, y = j * 4;
     int touched = 0;
@@ -279,7 +345,9 @@ f_luma_cell(const FiltArgs &A, int i, int j)
     const int edgeh = (x % A.blk_w) == 0, edgehs = (x % (A.blk_w / 2)) == 0;
     const int amx = f_abs(mv.x), amy = f_abs(mv.y);
     const int q = A.q;
-    uint8_t *dxy = A.data + (size_t) y * A.stride + x;
+    uint8_t *dxy = T + FT_ORG;
+    const FiltArgs L = f_tile_view(A, T, x, y);
+    int what = 0;
 
     if (mv.flags & MVF_INTRA) {
         int tH = f_clamp((64 * q) >> 12, 2, 32), tL = f_clamp((32 * q) >> 12, 2, 32);
@@ -288,10 +356,11 @@ f_luma_cell(const FiltArgs &A, int i, int j)
             teh |= edgehs;
             tev |= edgevs;
         }
-        f_hfilter(A, x, y, teh, tH, tL);
+        f_tile_load(T, A, x, y);
+        f_hfilter(L, x, y, teh, tH, tL);
         DSVCU_SYNCWARP();
-        f_vfilter(A, x, y, tev, tH, tL);
-        DSVCU_SYNCWARP();
+        f_vfilter(L, x, y, tev, tH, tL);
+        f_tile_store(T, A, x, y, 3);
         return 1;
     }
     int ndx = 0, ndy = 0;
@@ -304,7 +373,9 @@ f_luma_cell(const FiltArgs &A, int i, int j)
         int teh = edgeh || eprm, tev = edgev || eprm;
         int tndc = (ndx + ndy + 1) >> 1;
         F4x4 b;
-        f_load4x4(b, dxy, A.stride);
+        f_tile_load(T, A, x, y);
+        what |= 8; /* tile is loaded */
+        f_load4x4(b, dxy, FT_S);
         f_artf(b, &sh, &sv, &shl, &svl);
         if (sh < 2 * sv && sv < 2 * sh) {
             if (ndx < amx) ndx >>= 1;
@@ -325,29 +396,35 @@ f_luma_cell(const FiltArgs &A, int i, int j)
         addy = (min(ndx, A.fthresh) * q) >> 12;
         DSVCU_SYNCWARP();
         if (sh > 2 * sv || amy > 2 * amx) {
-            f_vfilter(A, x, y, tev, tt + addy, tt);
+            f_vfilter(L, x, y, tev, tt + addy, tt);
+            what |= 2;
         } else if (sv > 2 * sh || amx > 2 * amy) {
-            f_hfilter(A, x, y, teh, tt + addx, tt);
+            f_hfilter(L, x, y, teh, tt + addx, tt);
+            what |= 1;
         } else {
-            f_hfilter(A, x, y, teh, tt + addx, tt);
+            f_hfilter(L, x, y, teh, tt + addx, tt);
             DSVCU_SYNCWARP();
-            f_vfilter(A, x, y, tev, tt + addy, tt);
+            f_vfilter(L, x, y, tev, tt + addy, tt);
+            what |= 3;
         }
         DSVCU_SYNCWARP();
         touched = 1;
     }
     if (A.sharpen && (mv.x & 3) && (mv.y & 3) && ((mv.x | mv.y) & 1) && amx < 8 && amy < 8) {
-        if (FILT_LANE == 0) f_degrad(dxy, A.stride);
-        DSVCU_SYNCWARP();
+        if (!(what & 8)) f_tile_load(T, A, x, y);
+        if (FILT_LANE == 0) f_degrad(dxy, FT_S);
+        what |= 4;
         touched = 1;
     }
+    if (what & 7) f_tile_store(T, A, x, y, what & 7);
     return touched;
 }
 
 /* one 4x4 cell of dsv_intra_filter (bmc.c:411-455) */
 DSVCU_DEV int
-f_intra_cell(const FiltArgs &A, int i, int j)
+f_intra_cell(const FiltArgs &G, uint8_t *T, int i, int j)
 {
+    const FiltArgs &A = G;
     const int nsbx = A.w / 4, nsby = A.h / 4;
     const int x = i * 4, y = j * 4;
     if (y + 4 >= A.h || x + 4 >= A.w) return 0;
@@ -355,10 +432,12 @@ f_intra_cell(const FiltArgs &A, int i, int j)
     const int flags = A.blockdata[fx + fy * A.nbh];
     if (flags & BD_RING) return 0;
     const int q = A.q;
-    uint8_t *dxy = A.data + (size_t) y * A.stride + x;
+    uint8_t *dxy = T + FT_ORG;
+    const FiltArgs L = f_tile_view(A, T, x, y);
     int sh, sv, shl, svl, tt = 32;
     F4x4 b;
-    f_load4x4(b, dxy, A.stride);
+    f_tile_load(T, A, x, y);
+    f_load4x4(b, dxy, FT_S);
     f_artf(b, &sh, &sv, &shl, &svl);
     int mxs = max(sh, sv);
     if (!(mxs < 256 && mxs > 8)) return 0;
@@ -372,19 +451,19 @@ f_intra_cell(const FiltArgs &A, int i, int j)
     tt = (tt * q) >> 12;
     tt = f_clamp(tt, 0, A.fthresh);
     DSVCU_SYNCWARP();
-    f_hfilter(A, x, y, 0, tt, tt);
+    f_hfilter(L, x, y, 0, tt, tt);
     DSVCU_SYNCWARP();
-    f_vfilter(A, x, y, 0, tt, tt);
+    f_vfilter(L, x, y, 0, tt, tt);
     DSVCU_SYNCWARP();
     tt = (sh > sv) ? (3 * sh + sv) : (3 * sv + sh);
     tt = f_curve_tex(tt);
     tt = 16 + ((tt + 2) >> 2);
     tt = (tt * q) >> 12;
     tt = f_clamp(tt, 0, A.fthresh);
-    f_hfilter(A, x, y, 0, tt, tt);
+    f_hfilter(L, x, y, 0, tt, tt);
     DSVCU_SYNCWARP();
-    f_vfilter(A, x, y, 0, tt, tt);
-    DSVCU_SYNCWARP();
+    f_vfilter(L, x, y, 0, tt, tt);
+    f_tile_store(T, A, x, y, 3);
     return 1;
 }
 
@@ -485,8 +564,14 @@ f_cell_active(const FiltArgs &A, int i, int j)
 DSVCU_KERNEL void __launch_bounds__(FILT_WARPS_PER_CTA * 32)
 k_filter_wavefront(FiltArgs A)
 {
+    __align__(16) DSVCU_SHARED uint8_t tiles[FILT_WARPS_PER_CTA][FT_BYTES];
     const int lane = FILT_LANE;
     const int ncols = A.ncols;
+#ifndef DSVCU_EMU
+    uint8_t *T = tiles[threadIdx.x >> 5];
+#else
+    uint8_t *T = tiles[0];
+#endif
     for (int row = FILT_WARP; row < A.nrows; row += FILT_NWARPS) {
         int seen = (row == 0) ? 0x7fffffff : 0; /* progress of the row above, cached */
         int published = 0;
@@ -522,9 +607,9 @@ k_filter_wavefront(FiltArgs A)
                 mask = 0;
 #endif
                 if (A.mode == FILT_MODE_LUMA) {
-                    f_luma_cell(A, i, row);
+                    f_luma_cell(A, T, i, row);
                 } else if (A.mode == FILT_MODE_INTRA) {
-                    f_intra_cell(A, i, row);
+                    f_intra_cell(A, T, i, row);
                 } else {
                     f_chroma_cell(A, i, row);
                 }

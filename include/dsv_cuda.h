@@ -169,6 +169,9 @@ int dsvcu_frame_luma_avg(dsvcu_ctx *ctx, dsvcu_frame *f, unsigned *avg);
 int dsvcu_frame_luma_avg_async(dsvcu_ctx *ctx, dsvcu_frame *f);
 unsigned dsvcu_frame_luma_avg_result(dsvcu_ctx *ctx);
 
+/* floor(sqrt(n)) exactly as the motion search computes it (reference iisqrt, hme.c:99-124) */
+unsigned dsvcu_isqrt(unsigned n);
+
 /* ---- timing on the context's stream (CUDA events) ---- */
 int dsvcu_timer_start(dsvcu_ctx *ctx);
 int dsvcu_timer_stop_ms(dsvcu_ctx *ctx, float *ms); /* synchronises */

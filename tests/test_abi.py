@@ -48,3 +48,36 @@ def test_no_cpu_fallback_without_device():
     ctx = C.c_void_p()
     assert lib.dsvcu_ctx_create(C.byref(ctx), 0, 352, 288, 5) != 0
     assert b"no CUDA device" in lib.dsvcu_last_error()
+
+
+def test_isqrt_matches_reference_form():
+    """me_isqrt (hardware sqrt + exact fix-up) == the reference's digit-by-digit
+    iisqrt (hme.c:99-124) == floor(sqrt(n)): every perfect square +-2 up to 2^32
+    (sampled) and the extremes"""
+    import math
+    lib = util.pkg().load()
+
+    def ref(n):  # restatement of the reference loop
+        if n == 0:
+            return 0
+        pos, res, rem = 1 << 30, 0, n
+        while pos > rem:
+            pos >>= 2
+        while pos:
+            dif = res + pos
+            res >>= 1
+            if rem >= dif:
+                rem -= dif
+                res += pos
+            pos >>= 2
+        return res
+
+    vals = {0, 1, 2, 3, 0xffffffff, 0xfffffffe, 0x7fffffff, 0x80000000}
+    for r in list(range(0, 3000)) + list(range(3000, 65536, 37)) + [65535]:
+        for d in (-2, -1, 0, 1, 2):
+            n = r * r + d
+            if 0 <= n <= 0xffffffff:
+                vals.add(n)
+    for n in sorted(vals):
+        got = lib.dsvcu_isqrt(n)
+        assert got == math.isqrt(n) == ref(n), n
