@@ -324,7 +324,13 @@ def run_own(args):
     nframes = chunks * GOP
 
     distinct = 2
-    data = synth_chunks(distinct)
+    # rank 0 generates (and caches on tmpfs) the synthetic chunks, the others read the cache
+    if rank == 0:
+        data = synth_chunks(distinct)
+    if dist is not None:
+        dist.barrier()
+    if rank != 0:
+        data = synth_chunks(distinct)
     host = torch.empty(nframes * FRAME_BYTES, dtype=torch.uint8, pin_memory=True)
     hv = host.numpy()
     for c in range(chunks):

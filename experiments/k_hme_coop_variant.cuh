@@ -1,0 +1,1936 @@
+/*
+ * k_hme.cuh -- hierarchical motion estimation, sub-pel refinement, per-block
+ * mode decision (skip / no-transmit / intra sub-blocks / EPRM) and the I-frame
+ * block analysis.
+ *
+ * Replaces reference src/hme.c: dsv_hme (:2001-2016), refine_level (:1372-1833)
+ * and everything it calls (metrics :97-352, block statistics :492-775, half /
+ * quarter-pel interpolation :777-837, intra tests :839-1049, subpixel_ME
+ * :1051-1164, candidate lists :1166-1298, refine_best_fpel_cand :1300-1370),
+ * global_motion (:1973-1999) and dsv_intra_analysis (:1835-1971); plus the MV
+ * helpers of src/dsv.c:324-447 it needs.
+ *
+ * Parallel structure: pyramid levels are sequential (one launch each).  Inside a
+ * level, block (i,j) needs the FINAL vectors of its left, top and top-left
+ * neighbours (spatial candidates, the MV predictor inside every rate term, the
+ * neighbour difference used by the mode decision), so blocks are scheduled as a
+ * wavefront: one warp owns one block row and walks it left to right once the
+ * row above has published progress > i.  Inside a block
+ * the 32 lanes split every pixel loop (SSE, the 2x2-cell psy metric, block
+ * statistics, histograms, interpolation) and combine with warp reductions, so
+ * all lanes take the same decisions and the reference's first-wins tie-break
+ * order is kept by evaluating candidates in list order.
+ */
+#ifndef K_HME_CUH
+#define K_HME_CUH
+
+#include "dsvcu_rt.h"
+#include "k_quant.cuh"
+
+#define ME_WARPS_PER_CTA 4
+#define ME_BORDER 32
+#define ME_MAXLVL 5
+#define SP_SZ 16
+#define SP_DIM (SP_SZ + 1)
+#define HP_STRIDE (SP_DIM * 2)
+#define QP_STRIDE (SP_DIM * 4)
+#define MEQ_OFF(fx, fy) (4 * (fx) + (4 * (fy)) * QP_STRIDE)
+
+struct MePlane {
+    const uint8_t *data;
+    int stride, w, h;
+};
+
+struct MeArgs {
+    MePlane src[3], ref[3], ogr; /* this level; chroma only used at level 0 */
+    dsvcu_mv *mvf;               /* this level's field (zero-initialised) */
+    const dsvcu_mv *parent;      /* level + 1 field or NULL */
+    const dsvcu_mv *ref_mvf;     /* previous picture's final field or NULL */
+    int nxb, nyb, y_w, y_h;
+    int level, quant, effort, lossless, skip_thresh;
+    int hs, vs, vid_w, vid_h, psyscale;
+    const int *gxy; /* global motion from the level above */
+    int *acc;       /* [0] nintra [1] ndiff [2] eligible [3] total_err */
+    int *progress;
+    int nrows;
+};
+
+#ifdef DSVCU_EMU
+#define ME_LANE 0
+#define ME_NL 1
+#define ME_WARP ((int) blockIdx.x)
+#define ME_NWARPS ((int) gridDim.x)
+#define ME_WIC 0
+DSVCU_DEV int me_wsum(int v) { return v; }
+DSVCU_DEV unsigned me_wsumu(unsigned v) { return v; }
+DSVCU_DEV int me_wor(int v) { return v; }
+DSVCU_DEV unsigned me_wmaxu(unsigned v) { return v; }
+#else
+#define ME_LANE ((int) (threadIdx.x & 31))
+#define ME_NL 32
+#define ME_WARP ((int) ((blockIdx.x * blockDim.x + threadIdx.x) >> 5))
+#define ME_NWARPS ((int) ((gridDim.x * blockDim.x) >> 5))
+#define ME_WIC ((int) (threadIdx.x >> 5))
+DSVCU_DEV int me_wsum(int v) { return __reduce_add_sync(0xffffffffu, v); }
+DSVCU_DEV unsigned me_wsumu(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
+DSVCU_DEV int me_wor(int v) { return (int) __reduce_or_sync(0xffffffffu, (unsigned) v); }
+DSVCU_DEV unsigned me_wmaxu(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
+#endif
+
+DSVCU_HD int me_abs(int v) { return v < 0 ? -v : v; }
+DSVCU_HD int me_sqr(int v) { return v * v; }
+DSVCU_HD int me_avg2(int a, int b) { return (a + b + 1) >> 1; }
+DSVCU_HD unsigned me_uavg4(int a, int b, int c, int d) { return (unsigned) (a + b + c + d + 2) >> 2; }
+DSVCU_HD int me_u8(int v) { return v > 255 ? 255 : (v < 0 ? 0 : v); }
+DSVCU_HD int me_sar_r2(int v) { return (v + 2) >> 2; } /* DSV_SAR_R(v, 2) */
+
+/* ---- packed-byte helpers: four horizontally adjacent pixels per 32-bit word.
+ * On the device these map to one instruction each (byte-SIMD absolute
+ * difference, 4-way dot product, byte permute); the host emulation spells them
+ * out.  Blocks whose width is 4, 8, 16 or 32 take the packed paths below, any
+ * other width the generic per-pixel loops. ---- */
+#ifndef DSVCU_EMU
+DSVCU_DEV uint32_t me_ld4(const uint8_t *p)
+{
+    /* unaligned 4-byte read from two aligned words; may touch up to 3 bytes
+     * past p+3, which always lie inside the frame allocation */
+    uintptr_t a = (uintptr_t) p;
+    const uint32_t *q = (const uint32_t *) (a & ~(uintptr_t) 3);
+    return __funnelshift_r(q[0], q[1], (unsigned) (a & 3) * 8);
+}
+DSVCU_DEV uint32_t me_absdiff4(uint32_t a, uint32_t b) { return __vabsdiffu4(a, b); }
+DSVCU_DEV unsigned me_dot4(uint32_t a, uint32_t b, unsigned acc) { return __dp4a(a, b, acc); }
+DSVCU_DEV uint32_t me_perm(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+#else
+DSVCU_DEV uint32_t me_ld4(const uint8_t *p)
+{
+    return (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24);
+}
+DSVCU_DEV uint32_t me_absdiff4(uint32_t a, uint32_t b)
+{
+    uint32_t r = 0;
+    for (int k = 0; k < 4; k++) {
+        int x = (int) ((a >> (8 * k)) & 255) - (int) ((b >> (8 * k)) & 255);
+        r |= (uint32_t) (x < 0 ? -x : x) << (8 * k);
+    }
+    return r;
+}
+DSVCU_DEV unsigned me_dot4(uint32_t a, uint32_t b, unsigned acc)
+{
+    for (int k = 0; k < 4; k++) acc += ((a >> (8 * k)) & 255) * ((b >> (8 * k)) & 255);
+    return acc;
+}
+DSVCU_DEV uint32_t me_perm(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint64_t v = ((uint64_t) b << 32) | a;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; k++) r |= (uint32_t) ((v >> (8 * ((sel >> (4 * k)) & 7))) & 255) << (8 * k);
+    return r;
+}
+#endif
+#define ME_ONES 0x01010101u
+
+/* log2(w / 4) for w in {4, 8, 16, 32}, else -1 (generic path) */
+DSVCU_DEV int me_gshift(int w)
+{
+    return w == 16 ? 2 : (w == 8 ? 1 : (w == 32 ? 3 : (w == 4 ? 0 : -1)));
+}
+
+/* floor(sqrt(n)): what the reference's digit-by-digit iisqrt (hme.c:99-124)
+ * returns; here from the hardware square root plus an exact integer fix-up
+ * (checked against the digit-by-digit form over the full 32-bit range at
+ * every perfect square +-2 and a dense sample, see tests) */
+DSVCU_HD unsigned
+me_isqrt(unsigned n)
+{
+    unsigned r = (unsigned) sqrtf((float) n);
+    while ((unsigned long long) r * r > n) r--;
+    while ((unsigned long long) (r + 1) * (r + 1) <= n) r++;
+    return r;
+}
+
+struct MePsy {
+    int err_w, tex_w, avg_w;
+};
+
+/* one 2x2 cell of the psycho-visual metric (METR_CALC, hme.c:126-134) */
+DSVCU_DEV unsigned
+me_cell(int a1, int a2, int a3, int a4, int b1, int b2, int b3, int b4, const MePsy &p)
+{
+    int s0 = (int) me_uavg4(a1, a2, a3, a4), s1 = (int) me_uavg4(b1, b2, b3, b4);
+    int se = (int) me_uavg4(me_abs(a1 - b1), me_abs(a2 - b2), me_abs(a3 - b3), me_abs(a4 - b4));
+    int ta = (int) me_uavg4(me_abs(a1 - a2), me_abs(a2 - a3), me_abs(a3 - a4), me_abs(a4 - a1));
+    int tb = (int) me_uavg4(me_abs(b1 - b2), me_abs(b2 - b3), me_abs(b3 - b4), me_abs(b4 - b1));
+    unsigned acc = 0;
+    acc += (unsigned) (me_sqr(se) << p.err_w);
+    acc += (unsigned) (me_sqr(ta - tb) << p.tex_w);
+    acc += (unsigned) (me_sqr(s0 - s1) << p.avg_w);
+    return acc;
+}
+
+/* the same on packed cells A = (a1,a2,a3,a4), B = (b1,b2,b3,b4) */
+DSVCU_DEV unsigned
+me_cell4(uint32_t A, uint32_t B, const MePsy &p)
+{
+    int s0 = (int) ((me_dot4(A, ME_ONES, 2)) >> 2), s1 = (int) ((me_dot4(B, ME_ONES, 2)) >> 2);
+    int se = (int) ((me_dot4(me_absdiff4(A, B), ME_ONES, 2)) >> 2);
+    int ta = (int) ((me_dot4(me_absdiff4(A, me_perm(A, A, 0x0321)), ME_ONES, 2)) >> 2);
+    int tb = (int) ((me_dot4(me_absdiff4(B, me_perm(B, B, 0x0321)), ME_ONES, 2)) >> 2);
+    unsigned acc = (unsigned) (me_sqr(se) << p.err_w);
+    acc += (unsigned) (me_sqr(ta - tb) << p.tex_w);
+    acc += (unsigned) (me_sqr(s0 - s1) << p.avg_w);
+    return acc;
+}
+
+/* raw accumulator of the psy metric over w x h (umetr_wxh, hme.c:191-196) */
+DSVCU_DEV unsigned
+me_umetr(const uint8_t *a, int as, const uint8_t *b, int bs, int w, int h, const MePsy &p)
+{
+    int cw = w / 2, ch = h / 2, n = cw * ch;
+    unsigned acc = 0;
+    const int gs = me_gshift(w);
+    if (gs >= 0) {
+        /* one work item = 4 pixels x 2 rows = two 2x2 cells */
+        const int ng = ch << gs, gm = (1 << gs) - 1;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            int y = (g >> gs) * 2, x = (g & gm) * 4;
+            uint32_t a0 = me_ld4(a + y * as + x), a1 = me_ld4(a + (y + 1) * as + x);
+            uint32_t b0 = me_ld4(b + y * bs + x), b1 = me_ld4(b + (y + 1) * bs + x);
+            acc += me_cell4(me_perm(a0, a1, 0x5410), me_perm(b0, b1, 0x5410), p);
+            acc += me_cell4(me_perm(a0, a1, 0x7632), me_perm(b0, b1, 0x7632), p);
+        }
+        return me_wsumu(acc);
+    }
+    for (int k = ME_LANE; k < n; k += ME_NL) {
+        int j = k / cw, i = k - j * cw;
+        const uint8_t *pa = a + (2 * j) * as + 2 * i, *pb = b + (2 * j) * bs + 2 * i;
+        acc += me_cell(pa[0], pa[1], pa[as], pa[as + 1], pb[0], pb[1], pb[bs], pb[bs + 1], p);
+    }
+    return me_wsumu(acc);
+}
+
+/* fastmetr (hme.c:271-306): sqrt-normalised */
+DSVCU_DEV unsigned
+me_metr(const uint8_t *a, int as, const uint8_t *b, int bs, int w, int h, const MePsy &p)
+{
+    if (w == 0 || h == 0) return 0x7fffffffu;
+    unsigned acc = me_umetr(a, as, b, bs, w, h, p);
+    return me_isqrt(acc) * (unsigned) w * (unsigned) h / (unsigned) me_avg2(w, h);
+}
+
+/* SSE over w x h (hme.c:198-242) */
+DSVCU_DEV unsigned
+me_sse(const uint8_t *a, int as, const uint8_t *b, int bs, int w, int h)
+{
+    if (w == 0 || h == 0) return 0x7fffffffu;
+    unsigned acc = 0;
+    int n = w * h;
+    const int gs = me_gshift(w);
+    if (gs >= 0) {
+        const int ng = h << gs, gm = (1 << gs) - 1;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            int y = g >> gs, x = (g & gm) * 4;
+            uint32_t d = me_absdiff4(me_ld4(a + y * as + x), me_ld4(b + y * bs + x));
+            acc = me_dot4(d, d, acc);
+        }
+        return me_wsumu(acc);
+    }
+    for (int k = ME_LANE; k < n; k += ME_NL) {
+        int j = k / w, i = k - j * w;
+        int d = (int) a[j * as + i] - (int) b[j * bs + i];
+        acc += (unsigned) (d * d);
+    }
+    return me_wsumu(acc);
+}
+
+DSVCU_DEV unsigned
+me_hier_metr(int level, const uint8_t *a, int as, const uint8_t *b, int bs, int w, int h, const MePsy &p)
+{
+    if (level > 1) return me_sse(a, as, b, bs, w, h);
+    return me_metr(a, as, b, bs, w, h, p);
+}
+
+/* ---- MV field helpers (dsv.c:324-447) ---- */
+
+/* entries of the level being built are written by other warps: bypass L1 */
+DSVCU_DEV void
+me_ldmv(const dsvcu_mv *p, int *x, int *y, unsigned *fl)
+{
+#ifndef DSVCU_EMU
+    int w = *(volatile const int *) p;
+    *x = (int16_t) (w & 0xffff);
+    *y = (int16_t) (w >> 16);
+    if (fl) *fl = *((volatile const unsigned *) p + 1);
+#else
+    *x = p->x;
+    *y = p->y;
+    if (fl) *fl = p->flags;
+#endif
+}
+
+DSVCU_DEV int
+me_grad_pick(int left, int top, int topleft)
+{
+    int g = left + top - topleft;
+    return (me_abs(g - left) < me_abs(g - top)) ? left : top;
+}
+
+DSVCU_DEV void
+me_movec_pred(const dsvcu_mv *vecs, int nbh, int x, int y, int *px, int *py)
+{
+    int lx = 0, ly = 0, tx = 0, ty = 0, dx = 0, dy = 0;
+    const dsvcu_mv *c = vecs + x + y * nbh;
+    if (x > 0) {
+        me_ldmv(c - 1, &lx, &ly, NULL);
+    }
+    if (y > 0) {
+        me_ldmv(c - nbh, &tx, &ty, NULL);
+        if (x > 0) {
+            me_ldmv(c - nbh - 1, &dx, &dy, NULL);
+        }
+    }
+    *px = me_grad_pick(lx, tx, dx);
+    *py = me_grad_pick(ly, ty, dy);
+}
+
+DSVCU_DEV int
+me_seg_len(int v)
+{
+    /* 2 * floor(log2(|v| + 1)) + 2 */
+    if (v < 0) v = -v;
+    v++;
+#ifndef DSVCU_EMU
+    return (31 - __clz(v)) * 2 + 2;
+#else
+    return (31 - __builtin_clz((unsigned) v)) * 2 + 2;
+#endif
+}
+
+/* mv_cost (hme.c:354-366) on top of dsv_mv_cost (dsv.c:357-374) */
+/* the predictor of a block depends only on its left / top / top-left
+ * neighbours, which are final before the block starts: computed once per block
+ * (MePred) instead of inside every rate term */
+struct MePred {
+    int x, y;
+};
+
+DSVCU_DEV int
+me_mv_cost(const MeArgs &A, const MePred &pr, int mx, int my, int level)
+{
+    int px = pr.x, py = pr.y, bits, b2sr, q = A.quant;
+    int sqr = level > 1;
+    bits = me_seg_len(mx - px) + me_seg_len(my - py);
+    b2sr = (256 * (q * q >> 12) * A.y_w * A.y_h) / (A.vid_w * A.vid_h);
+    bits += bits * b2sr >> 7;
+    if (sqr) bits *= bits;
+    bits = min(bits, 1 << 19);
+    if (sqr) return bits * (q * q >> 12) >> (12 - 2);
+    return 3 * bits * q >> 12;
+}
+
+DSVCU_DEV int
+me_neighbordif(const dsvcu_mv *vecs, int nbh, int x, int y)
+{
+    const dsvcu_mv *c = vecs + x + y * nbh;
+    int cx, cy, nx, ny;
+    unsigned nf;
+    me_ldmv(c, &cx, &cy, NULL);
+    int lx = cx, ly = cy, tx = cx, ty = cy;
+    if (me_abs(cx) < 2 && me_abs(cy) < 2) return 0;
+    if (x > 0) {
+        me_ldmv(c - 1, &nx, &ny, &nf);
+        if ((nx | ny) != 0 && !(nf & MVF_SKIP)) {
+            lx = nx;
+            ly = ny;
+        }
+    }
+    if (y > 0) {
+        me_ldmv(c - nbh, &nx, &ny, &nf);
+        if ((nx | ny) != 0 && !(nf & MVF_SKIP)) {
+            tx = nx;
+            ty = ny;
+        }
+    }
+    return (me_abs(lx - cx) + me_abs(ly - cy) + me_abs(tx - cx) + me_abs(ty - cy)) / 3;
+}
+
+/* ---- block statistics (hme.c:492-775); every lane returns the same value ---- */
+
+DSVCU_DEV int
+me_block_avg(const uint8_t *a, int as, int w, int h)
+{
+    int s = 0, n = w * h;
+    const int gs = me_gshift(w);
+    if (gs >= 0) {
+        const int ng = h << gs, gm = (1 << gs) - 1;
+        unsigned u = 0;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            u = me_dot4(me_ld4(a + (g >> gs) * as + (g & gm) * 4), ME_ONES, u);
+        }
+        return me_wsum((int) u) / (w * h);
+    }
+    for (int k = ME_LANE; k < n; k += ME_NL) {
+        int j = k / w, i = k - j * w;
+        s += a[j * as + i];
+    }
+    return me_wsum(s) / (w * h);
+}
+
+/* sums of horizontal / vertical absolute gradients (block_tex core) */
+DSVCU_DEV void
+me_grad_sums(const uint8_t *a, int as, int w, int h, unsigned *psh, unsigned *psv, int *psum)
+{
+    unsigned sh = 0, sv = 0;
+    int s = 0, n = w * h;
+    const int gs = me_gshift(w);
+    if (gs >= 0) {
+        const int ng = h << gs, gm = (1 << gs) - 1;
+        unsigned us = 0;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            int y = g >> gs, x = (g & gm) * 4;
+            const uint8_t *p = a + y * as + x;
+            uint32_t c = me_ld4(p);
+            uint32_t dl = me_absdiff4(c, me_ld4(p - 1));
+            us = me_dot4(c, ME_ONES, us);
+            if (x == 0) dl &= 0xffffff00u; /* column 0 has no left neighbour */
+            sh = me_dot4(dl, ME_ONES, sh);
+            if (y > 0) sv = me_dot4(me_absdiff4(c, me_ld4(p - as)), ME_ONES, sv);
+        }
+        *psh = me_wsumu(sh);
+        *psv = me_wsumu(sv);
+        *psum = me_wsum((int) us);
+        return;
+    }
+    for (int k = ME_LANE; k < n; k += ME_NL) {
+        int j = k / w, i = k - j * w;
+        int px = a[j * as + i];
+        s += px;
+        if (i > 0) sh += (unsigned) me_abs(px - a[j * as + i - 1]);
+        if (j > 0) sv += (unsigned) me_abs(px - a[(j - 1) * as + i]);
+    }
+    *psh = me_wsumu(sh);
+    *psv = me_wsumu(sv);
+    *psum = me_wsum(s);
+}
+
+DSVCU_DEV unsigned
+me_block_tex(const uint8_t *a, int as, int w, int h)
+{
+    unsigned sh, sv;
+    int s;
+    me_grad_sums(a, as, w, h, &sh, &sv, &s);
+    return max(sh, sv);
+}
+
+DSVCU_DEV int
+me_abs_dev(const uint8_t *a, int as, int w, int h, int mean)
+{
+    int var = 0, n = w * h;
+    const int gs = me_gshift(w);
+    if (gs >= 0 && mean >= 0 && mean <= 255) {
+        const int ng = h << gs, gm = (1 << gs) - 1;
+        const uint32_t m4 = (uint32_t) mean * ME_ONES;
+        unsigned u = 0;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            u = me_dot4(me_absdiff4(me_ld4(a + (g >> gs) * as + (g & gm) * 4), m4), ME_ONES, u);
+        }
+        return me_wsum((int) u);
+    }
+    for (int k = ME_LANE; k < n; k += ME_NL) {
+        int j = k / w, i = k - j * w;
+        var += me_abs((int) a[j * as + i] - mean);
+    }
+    return me_wsum(var);
+}
+
+DSVCU_DEV int
+me_block_var(const uint8_t *a, int as, int w, int h, unsigned *avg)
+{
+    int s = me_block_avg(a, as, w, h);
+    *avg = (unsigned) s;
+    return me_abs_dev(a, as, w, h, s);
+}
+
+DSVCU_DEV int
+me_block_detail(const uint8_t *a, int as, int w, int h, unsigned *avg)
+{
+    unsigned sh, sv;
+    int s, var, tex;
+    me_grad_sums(a, as, w, h, &sh, &sv, &s);
+    s /= (w * h);
+    *avg = (unsigned) s;
+    var = me_abs_dev(a, as, w, h, s) >> 1;
+    tex = (int) max(sh, sv) - var;
+    return var + max(tex, 0);
+}
+
+DSVCU_DEV int
+me_quant_tex(const uint8_t *a, int as, int w, int h)
+{
+    unsigned sh = 0, sv = 0;
+    int n = w * h;
+    const int gs = me_gshift(w);
+    if (gs >= 0) {
+        const int ng = h << gs, gm = (1 << gs) - 1;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            int y = g >> gs, x = (g & gm) * 4;
+            const uint8_t *p = a + y * as + x;
+            uint32_t c = (me_ld4(p) >> 4) & 0x0f0f0f0fu;
+            uint32_t dr = me_absdiff4(c, (me_ld4(p + 1) >> 4) & 0x0f0f0f0fu);
+            if (x == w - 4) dr &= 0x00ffffffu; /* last column has no right neighbour */
+            sh = me_dot4(dr, dr, sh);
+            if (y > 0) {
+                uint32_t du = me_absdiff4(c, (me_ld4(p - as) >> 4) & 0x0f0f0f0fu);
+                sv = me_dot4(du, du, sv);
+            }
+        }
+        sh = me_wsumu(sh);
+        sv = me_wsumu(sv);
+        return (int) (me_isqrt(max(sh, sv)) / (unsigned) me_avg2(w, h));
+    }
+    for (int k = ME_LANE; k < n; k += ME_NL) {
+        int j = k / w, i = k - j * w;
+        int px = a[j * as + i] >> 4;
+        if (i < w - 1) {
+            int d = px - (a[j * as + i + 1] >> 4);
+            sh += (unsigned) (d * d);
+        }
+        if (j > 0) {
+            int d = px - (a[(j - 1) * as + i] >> 4);
+            sv += (unsigned) (d * d);
+        }
+    }
+    sh = me_wsumu(sh);
+    sv = me_wsumu(sv);
+    return (int) (me_isqrt(max(sh, sv)) / (unsigned) me_avg2(w, h));
+}
+
+/* 16-bin histograms are built in per-warp shared memory */
+DSVCU_DEV void
+me_hist_clear(int *hist)
+{
+    for (int k = ME_LANE; k < 16; k += ME_NL) hist[k] = 0;
+    DSVCU_SYNCWARP();
+}
+
+DSVCU_DEV unsigned
+me_block_hist_var(const uint8_t *a, int as, int w, int h, int *hist)
+{
+    unsigned avg, quant16, var = 0;
+    int n = w * h;
+    const int gs = me_gshift(w);
+    me_hist_clear(hist);
+    avg = (unsigned) me_block_avg(a, as, w, h);
+    if (avg == 0) avg = 1;
+    quant16 = ((1u << 3) << 16) / avg;
+    if (gs >= 0) {
+        const int ng = h << gs, gm = (1 << gs) - 1;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            uint32_t c = me_ld4(a + (g >> gs) * as + (g & gm) * 4);
+            for (int k = 0; k < 4; k++) {
+                unsigned hi = ((c >> (8 * k)) & 255u) * quant16 >> 16;
+                atomicAdd(&hist[hi > 15 ? 15 : hi], 1);
+            }
+        }
+    } else {
+        for (int k = ME_LANE; k < n; k += ME_NL) {
+            int j = k / w, i = k - j * w;
+            int hi = (int) (a[j * as + i] * quant16 >> 16);
+            atomicAdd(&hist[hi < 0 ? 0 : (hi > 15 ? 15 : hi)], 1);
+        }
+    }
+    DSVCU_SYNCWARP();
+    avg = 0;
+    for (int x = 0; x < 16; x++) avg += (unsigned) hist[x];
+    avg /= 16;
+    for (int x = 0; x < 16; x++) var += ((unsigned) hist[x] - avg) * ((unsigned) hist[x] - avg);
+    DSVCU_SYNCWARP();
+    return (var * 16 * 16) / (unsigned) (16 * w * h * w * h);
+}
+
+DSVCU_DEV int
+me_block_peaks(const uint8_t *a, int as, int w, int h, int *hist, int bavg)
+{
+    int avg = bavg, maxv = 0, npeaks = 0, quant16, cw, ch, n;
+    me_hist_clear(hist);
+    if (avg == 0) avg = 1;
+    quant16 = ((1 << 3) << 16) / avg;
+    cw = w / 2;
+    ch = h / 2;
+    n = cw * ch;
+    {
+        const int gs = me_gshift(w);
+        if (gs >= 0) {
+            const int ng = ch << gs, gm = (1 << gs) - 1;
+            for (int g = ME_LANE; g < ng; g += ME_NL) {
+                int y = (g >> gs) * 2, x = (g & gm) * 4;
+                uint32_t r0 = me_ld4(a + y * as + x), r1 = me_ld4(a + (y + 1) * as + x);
+                int d0 = (int) (me_dot4(me_perm(r0, r1, 0x5410), ME_ONES, 2) >> 2);
+                int d1 = (int) (me_dot4(me_perm(r0, r1, 0x7632), ME_ONES, 2) >> 2);
+                atomicAdd(&hist[min(d0 * quant16 >> 16, 15)], 1);
+                atomicAdd(&hist[min(d1 * quant16 >> 16, 15)], 1);
+            }
+        } else {
+            for (int k = ME_LANE; k < n; k += ME_NL) {
+                int j = k / cw, i = k - j * cw;
+                const uint8_t *p = a + (2 * j) * as + 2 * i;
+                int ds = (int) me_uavg4(p[0], p[1], p[as], p[as + 1]);
+                int hi = ds * quant16 >> 16;
+                atomicAdd(&hist[min(hi, 15)], 1);
+            }
+        }
+    }
+    DSVCU_SYNCWARP();
+    avg = 0;
+    for (int x = 0; x < 16; x++) {
+        maxv = max(maxv, hist[x]);
+        avg += hist[x];
+    }
+    avg /= 16;
+    maxv >>= 2;
+    for (int x = 0; x < 16; x++) {
+        int c = hist[x], is_peak = 1;
+        if (x > 0) is_peak &= (c > hist[x - 1]);
+        if (x < 15) is_peak &= (c > hist[x + 1]);
+        is_peak &= (c > maxv) || (c > avg);
+        npeaks += is_peak;
+    }
+    DSVCU_SYNCWARP();
+    return npeaks;
+}
+
+DSVCU_DEV void
+me_c_average(const MePlane *pl, int x, int y, int w, int h, int *uavg, int *vavg)
+{
+    int su = 0, sv = 0, n = w * h;
+    const int gs = me_gshift(w);
+    if (gs >= 0) {
+        const int ng = h << gs, gm = (1 << gs) - 1;
+        unsigned uu = 0, uv = 0;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            int j = g >> gs, i = (g & gm) * 4;
+            uu = me_dot4(me_ld4(pl[1].data + (y + j) * pl[1].stride + x + i), ME_ONES, uu);
+            uv = me_dot4(me_ld4(pl[2].data + (y + j) * pl[2].stride + x + i), ME_ONES, uv);
+        }
+        su = (int) uu;
+        sv = (int) uv;
+    } else {
+        for (int k = ME_LANE; k < n; k += ME_NL) {
+            int j = k / w, i = k - j * w;
+            su += pl[1].data[(y + j) * pl[1].stride + x + i];
+            sv += pl[2].data[(y + j) * pl[2].stride + x + i];
+        }
+    }
+    su = me_wsum(su);
+    sv = me_wsum(sv);
+    /* w*h == 0 divides by zero in the reference too; callers never pass it */
+    *uavg = su / (w * h);
+    *vavg = sv / (w * h);
+}
+
+struct MeChroma {
+    int nature, hifreq, greyish, skinnish;
+};
+
+DSVCU_DEV void
+me_chroma_analysis(MeChroma *c, int y, int u, int v)
+{
+    c->nature = u < 128 && v < 160;
+    c->greyish = me_abs(u - 128) < 8 && me_abs(v - 128) < 8;
+    c->skinnish = (y > 80) && (y < 230) && me_abs(u - 108) < 24 && me_abs(v - 148) < 24;
+    c->hifreq = (u > 160) && !c->greyish && !c->skinnish;
+}
+
+DSVCU_DEV int
+me_invalid_block(int fw, int fh, int bx, int by, int bw, int bh, int pad)
+{
+    return (bx - pad) < -ME_BORDER || (by - pad) < -ME_BORDER || (bx + bw + pad) >= (fw + ME_BORDER) ||
+           (by + bh + pad) >= (fh + ME_BORDER);
+}
+
+/* max over the four quadrants of the raw psy metric, luma + both chroma planes
+ * (yuv_max_subblock_err, hme.c:368-411) */
+DSVCU_DEV void
+me_yuv_max_sub(unsigned out[3], const MePlane *sp, const MePlane *rp, int bx, int by, int brx, int bry, int bw, int bh,
+               int cbx, int cby, int cbrx, int cbry, int cbw, int cbh, const MePsy &psy)
+{
+    bw /= 2;
+    bh /= 2;
+    cbw /= 2;
+    cbh /= 2;
+    for (int z = 0; z < 3; z++) {
+        unsigned sub[4] = { 0, 0, 0, 0 };
+        int pos = 0;
+        for (int g = 0; g <= bh; g += (bh + !bh)) {
+            for (int f = 0; f <= bw; f += (bw + !bw)) {
+                const uint8_t *s = sp[z].data + (by + g) * sp[z].stride + bx + f;
+                const uint8_t *r = rp[z].data + (bry + g) * rp[z].stride + brx + f;
+                if (pos < 4) sub[pos] = me_umetr(s, sp[z].stride, r, rp[z].stride, bw, bh, psy);
+                pos++;
+            }
+        }
+        bx = cbx;
+        by = cby;
+        brx = cbrx;
+        bry = cbry;
+        bw = cbw;
+        bh = cbh;
+        out[z] = max(max(sub[0], sub[1]), max(sub[2], sub[3]));
+    }
+}
+
+/* calc_EPRM (hme.c:452-490): does MV / intra(ref avg) / intra(src avg)
+ * prediction clip anywhere in the block?  OR over pixels == the early-out scan */
+DSVCU_DEV void
+me_calc_eprm(const uint8_t *src, int ss, const uint8_t *mvr, int rs, int avg_src, int avg_ref, int w, int h, int *eprmi,
+             int *eprmd, int *eprmr)
+{
+    int ci = 0, cd = 0, cr = 0, n = w * h;
+    avg_src -= 128;
+    avg_ref -= 128;
+    {
+        const int gs = me_gshift(w);
+        if (gs >= 0) {
+            const int ng = h << gs, gm = (1 << gs) - 1;
+            for (int g = ME_LANE; g < ng; g += ME_NL) {
+                int j = g >> gs, i = (g & gm) * 4;
+                uint32_t sw = me_ld4(src + j * ss + i), rw = me_ld4(mvr + j * rs + i);
+                for (int k = 0; k < 4; k++) {
+                    int s = (int) ((sw >> (8 * k)) & 255u);
+                    cr |= ((s - (int) ((rw >> (8 * k)) & 255u)) + 128) & ~0xff;
+                    ci |= (s - avg_ref) & ~0xff;
+                    cd |= (s - avg_src) & ~0xff;
+                }
+            }
+        } else {
+            for (int k = ME_LANE; k < n; k += ME_NL) {
+                int j = k / w, i = k - j * w;
+                int s = src[j * ss + i];
+                cr |= ((s - (int) mvr[j * rs + i]) + 128) & ~0xff;
+                ci |= (s - avg_ref) & ~0xff;
+                cd |= (s - avg_src) & ~0xff;
+            }
+        }
+    }
+    *eprmi = me_wor(ci != 0);
+    *eprmd = me_wor(cd != 0);
+    *eprmr = me_wor(cr != 0);
+}
+
+/* ---- cooperative execution -------------------------------------------------
+ * One CTA of ME_NW warps works on one block at a time.  The search logic of a
+ * block is strictly sequential, but nearly every step is "evaluate a handful of
+ * independent block metrics, then decide": the metrics of a step are dealt to
+ * the warps (ME_TASKS), written to a small result board in shared memory
+ * (ME_PUT) and read by every thread after one CTA barrier (ME_JOIN), so all
+ * threads take the same decisions.  Two boards alternate; one barrier per step
+ * suffices because a warp can only write board k+2 after every warp has passed
+ * the barrier of step k+1, i.e. has finished reading board k.
+ * The host emulation runs with a single "warp" of one lane. */
+#ifdef DSVCU_EMU
+#define ME_NW 1
+#define ME_TID 0
+#define ME_NT 1
+#define ME_CTASYNC() ((void) 0)
+#else
+#define ME_NW ME_WARPS_PER_CTA
+#define ME_TID ((int) threadIdx.x)
+#define ME_NT ((int) blockDim.x)
+#define ME_CTASYNC() __syncthreads()
+#endif
+#define ME_BOARD 48
+#define ME_TASKS(t, n) for (int t = ME_WIC; t < (n); t += ME_NW)
+/* `val` is usually a warp-collective reduction: every lane evaluates it, lane 0 posts it */
+#define ME_PUT(idx, val)                                  \
+    do {                                                  \
+        unsigned v_ = (unsigned) (val);                   \
+        if (ME_LANE == 0) S->res[ph & 1][idx] = v_;       \
+    } while (0)
+#define ME_JOIN()                \
+    do {                         \
+        ME_CTASYNC();            \
+        R = S->res[ph & 1];      \
+        ph++;                    \
+    } while (0)
+
+/* ---- sub-pel refinement (hme.c:777-837, :1051-1164) ---- */
+
+#define ME_HPF(a, b, c, d) ((5 * ((b) + (c))) - ((a) + (d)))
+
+/* Half-pel image (34 x 34, HP_STRIDE) of the 17 x 17 window at r, as the
+ * reference's hpel() builds it (hme.c:787-813).  The reference then expands it
+ * to a 68 x 68 quarter-pel image by bilinear averaging (qpel(), :815-837) of
+ * which the search samples 7 x 256 points; here those points are averaged from
+ * the half-pel image on the fly (me_qsample), same arithmetic. */
+#define ME_WIN (SP_DIM + 3) /* full-pel window rows/cols -1 .. SP_DIM+1 */
+DSVCU_DEV void
+me_interp(uint8_t *tmph, uint8_t *win, int16_t *hbuf, const uint8_t *r, int rs)
+{
+    /* stage the full-pel window once */
+    for (int k = ME_TID; k < ME_WIN * ME_WIN; k += ME_NT) {
+        int j = k / ME_WIN, i = k - j * ME_WIN;
+        win[k] = r[(j - 1) * rs + i - 1];
+    }
+    ME_CTASYNC();
+    /* horizontal half-pel sums for rows -1 .. SP_DIM+1 */
+    for (int k = ME_TID; k < ME_WIN * SP_DIM; k += ME_NT) {
+        int j = k / SP_DIM, i = k - j * SP_DIM;
+        const uint8_t *p = win + j * ME_WIN + i + 1;
+        hbuf[k] = (int16_t) ME_HPF(p[-1], p[0], p[1], p[2]);
+    }
+    ME_CTASYNC();
+    for (int k = ME_TID; k < SP_DIM * SP_DIM; k += ME_NT) {
+        int j = k / SP_DIM, i = k - j * SP_DIM;
+        const uint8_t *p = win + (j + 1) * ME_WIN + i + 1;
+        uint8_t *d = tmph + (2 * j) * HP_STRIDE + 2 * i;
+        int c = ME_HPF(hbuf[k], hbuf[k + SP_DIM], hbuf[k + 2 * SP_DIM], hbuf[k + 3 * SP_DIM]);
+        d[0] = p[0];
+        d[1] = (uint8_t) me_u8((ME_HPF(p[-1], p[0], p[1], p[2]) + 4) >> 3);
+        d[HP_STRIDE] = (uint8_t) me_u8((ME_HPF(p[-ME_WIN], p[0], p[ME_WIN], p[2 * ME_WIN]) + 4) >> 3);
+        d[HP_STRIDE + 1] = (uint8_t) me_u8((c + 32) >> 6);
+    }
+    ME_CTASYNC();
+}
+
+/* quarter-pel sample (qx, qy) of the image the reference's qpel() would build */
+DSVCU_DEV int
+me_qsample(const uint8_t *tmph, int qx, int qy)
+{
+    const uint8_t *h0 = tmph + (qy >> 1) * HP_STRIDE + (qx >> 1);
+    int a = h0[0];
+    if (qx & 1) {
+        if (qy & 1) return (a + h0[1] + h0[HP_STRIDE] + h0[HP_STRIDE + 1] + 2) >> 2;
+        return me_avg2(a, h0[1]);
+    }
+    if (qy & 1) return me_avg2(a, h0[HP_STRIDE]);
+    return a;
+}
+
+/* cell metric with the source-side terms (mean s0, texture ta) precomputed */
+DSVCU_DEV unsigned
+me_cell4_pre(uint32_t A, int s0, int ta, uint32_t B, const MePsy &p)
+{
+    int s1 = (int) ((me_dot4(B, ME_ONES, 2)) >> 2);
+    int se = (int) ((me_dot4(me_absdiff4(A, B), ME_ONES, 2)) >> 2);
+    int tb = (int) ((me_dot4(me_absdiff4(B, me_perm(B, B, 0x0321)), ME_ONES, 2)) >> 2);
+    unsigned acc = (unsigned) (me_sqr(se) << p.err_w);
+    acc += (unsigned) (me_sqr(ta - tb) << p.tex_w);
+    acc += (unsigned) (me_sqr(s0 - s1) << p.avg_w);
+    return acc;
+}
+
+/* me_qpsad for up to 7 offsets in one pass over the source window: the source
+ * cells are loaded (and their own terms computed) once, and the offsets give
+ * independent accumulation chains */
+#define ME_MAXSP 7
+DSVCU_DEV void
+me_qpsad_multi(const uint8_t *a, int as, const uint8_t *tmph, int nv, const int *tx, const int *ty, const MePsy &psy,
+               unsigned *out)
+{
+    unsigned acc[ME_MAXSP];
+    for (int v = 0; v < ME_MAXSP; v++) acc[v] = 0;
+    for (int g = ME_LANE; g < (SP_SZ / 2) * (SP_SZ / 4); g += ME_NL) {
+        int y = (g >> 2) * 2, x = (g & 3) * 4;
+        uint32_t a0 = me_ld4(a + y * as + x), a1 = me_ld4(a + (y + 1) * as + x);
+        uint32_t A0 = me_perm(a0, a1, 0x5410), A1 = me_perm(a0, a1, 0x7632);
+        int s00 = (int) (me_dot4(A0, ME_ONES, 2) >> 2), s01 = (int) (me_dot4(A1, ME_ONES, 2) >> 2);
+        int ta0 = (int) (me_dot4(me_absdiff4(A0, me_perm(A0, A0, 0x0321)), ME_ONES, 2) >> 2);
+        int ta1 = (int) (me_dot4(me_absdiff4(A1, me_perm(A1, A1, 0x0321)), ME_ONES, 2) >> 2);
+#ifndef DSVCU_EMU
+#pragma unroll
+#endif
+        for (int v = 0; v < ME_MAXSP; v++) {
+            if (v < nv) {
+                int qx = 4 + tx[v] + 4 * x, qy = 4 + ty[v] + 4 * y;
+                uint32_t B0 = (uint32_t) me_qsample(tmph, qx, qy) | ((uint32_t) me_qsample(tmph, qx + 4, qy) << 8) |
+                              ((uint32_t) me_qsample(tmph, qx, qy + 4) << 16) |
+                              ((uint32_t) me_qsample(tmph, qx + 4, qy + 4) << 24);
+                uint32_t B1 = (uint32_t) me_qsample(tmph, qx + 8, qy) | ((uint32_t) me_qsample(tmph, qx + 12, qy) << 8) |
+                              ((uint32_t) me_qsample(tmph, qx + 8, qy + 4) << 16) |
+                              ((uint32_t) me_qsample(tmph, qx + 12, qy + 4) << 24);
+                acc[v] += me_cell4_pre(A0, s00, ta0, B0, psy) + me_cell4_pre(A1, s01, ta1, B1, psy);
+            }
+        }
+    }
+    for (int v = 0; v < ME_MAXSP; v++) {
+        if (v < nv) out[v] = me_isqrt(me_wsumu(acc[v])) * (unsigned) SP_SZ * (unsigned) SP_SZ / (unsigned) SP_SZ;
+    }
+}
+
+struct MeScratch {
+    uint8_t tmph[(2 + HP_STRIDE) * (2 + HP_STRIDE)];
+    uint8_t win[ME_WIN * ME_WIN + 16];
+    int16_t hbuf[(SP_DIM + 3) * SP_DIM + 4];
+    int hist[2 * ME_WARPS_PER_CTA][16];
+    unsigned res[2][ME_BOARD];
+};
+
+DSVCU_DEV unsigned
+me_subpixel(const MeArgs &A, MeScratch *S, int &ph, int *outx, int *outy, int fpelx, int fpely, const MePred &pr,
+            unsigned best, int bx, int by, int bw, int bh, const MePsy &psy)
+{
+    const MePlane &sp = A.src[0], &rp = A.ref[0];
+    const unsigned *R;
+    unsigned quad[4], score, ms1, ms2;
+    int pri[2], sec[2], diag[2], bestv[2] = { 0, 0 };
+    int yarea = bw * bh, area_ratio, iarea_ratio, xx, yy;
+    const int ddx[4] = { 1, -1, 0, 0 }, ddy[4] = { 0, 0, 1, -1 };
+    *outx = 0;
+    *outy = 0;
+    if (best == 0) return best;
+    {
+        const uint8_t *s = sp.data + by * sp.stride + bx;
+        ME_TASKS(n, 4) {
+            const uint8_t *r = rp.data + (by + fpely + ddy[n]) * rp.stride + bx + fpelx + ddx[n];
+            ME_PUT(n, me_sse(s, sp.stride, r, rp.stride, bw, bh));
+        }
+    }
+    area_ratio = 8 * (SP_SZ * SP_SZ) / yarea;
+    iarea_ratio = 8 * yarea / (SP_SZ * SP_SZ);
+    best = best * (unsigned) area_ratio >> 3;
+    xx = bx + ((bw >> 1) - ((SP_SZ + 1) / 2));
+    yy = by + ((bh >> 1) - ((SP_SZ + 1) / 2));
+    /* all threads build the half-pel image together (its barriers also order
+     * the board writes above) */
+    me_interp(S->tmph, S->win, S->hbuf, rp.data + (yy + fpely - 1) * rp.stride + xx + fpelx - 1, rp.stride);
+    ME_JOIN();
+    for (int n = 0; n < 4; n++) quad[n] = R[n];
+
+    pri[0] = 0; pri[1] = -1;
+    sec[0] = -1; sec[1] = 0;
+    ms1 = quad[1];
+    ms2 = quad[3];
+    if (quad[3] >= quad[2]) {
+        pri[0] = 0; pri[1] = 1;
+        ms2 = quad[2];
+    }
+    if (quad[1] >= quad[0]) {
+        sec[0] = 1; sec[1] = 0;
+        ms1 = quad[0];
+    }
+    if (ms2 > ms1) {
+        int t0 = sec[0], t1 = sec[1];
+        sec[0] = pri[0]; sec[1] = pri[1];
+        pri[0] = t0; pri[1] = t1;
+    }
+    diag[0] = pri[0] + sec[0];
+    diag[1] = pri[1] + sec[1];
+    {
+        const uint8_t *ssp = sp.data + yy * sp.stride + xx;
+        int tvx[ME_MAXSP], tvy[ME_MAXSP], nv = 0;
+        /* test order of the reference (hme.c:1137-1160): half then quarter
+         * steps along pri, sec, diag, then pri + diag */
+        for (int n = 0; n <= 6; n++) {
+            int t[2];
+            if (n == 6) {
+                t[0] = pri[0] + diag[0];
+                t[1] = pri[1] + diag[1];
+            } else {
+                int hp = !(n & 1);
+                const int *tv = (n >> 1) == 0 ? pri : ((n >> 1) == 1 ? sec : diag);
+                t[0] = tv[0] * (1 << hp);
+                t[1] = tv[1] * (1 << hp);
+            }
+            if (((t[0] | t[1]) & 1) && A.effort < 8) continue;
+            tvx[nv] = t[0];
+            tvy[nv] = t[1];
+            nv++;
+        }
+        /* warp w takes offsets w, w + ME_NW, ... in one fused pass */
+        {
+            int mx[ME_MAXSP], my[ME_MAXSP], slot[ME_MAXSP], mine = 0;
+            unsigned sc[ME_MAXSP];
+            for (int n = ME_WIC; n < nv; n += ME_NW) {
+                mx[mine] = tvx[n];
+                my[mine] = tvy[n];
+                slot[mine] = n;
+                mine++;
+            }
+            if (mine) {
+                me_qpsad_multi(ssp, sp.stride, S->tmph, mine, mx, my, psy, sc);
+                for (int n = 0; n < mine; n++) ME_PUT(slot[n], sc[n]);
+            }
+        }
+        ME_JOIN();
+        for (int n = 0; n < nv; n++) {
+            score = R[n] + (unsigned) me_mv_cost(A, pr, fpelx * 4 + tvx[n], fpely * 4 + tvy[n], 0);
+            if (best > score) {
+                best = score;
+                bestv[0] = tvx[n];
+                bestv[1] = tvy[n];
+            }
+        }
+    }
+    *outx = bestv[0];
+    *outy = bestv[1];
+    return best * (unsigned) iarea_ratio >> 3;
+}
+
+/* ---- intra sub-block tests (hme.c:839-1049) ---- */
+
+DSVCU_DEV void
+me_err_intra(const uint8_t *a, int as, const uint8_t *b, int bs, int avg_sb, int avg_src, int w, int h, unsigned *intra_err,
+             unsigned *intrasrc_err, unsigned *inter_err, const MePsy &psy, int ratio)
+{
+    unsigned isb = 0, isrc = 0, inter = 0;
+    int cw = w / 2, ch = h / 2, n = cw * ch;
+    const int gs = me_gshift(w);
+    if (gs >= 0 && avg_sb >= 0 && avg_sb <= 255 && avg_src >= 0 && avg_src <= 255) {
+        const int ng = ch << gs, gm = (1 << gs) - 1;
+        const uint32_t sb4 = (uint32_t) avg_sb * ME_ONES, sr4 = (uint32_t) avg_src * ME_ONES;
+        for (int g = ME_LANE; g < ng; g += ME_NL) {
+            int y = (g >> gs) * 2, x = (g & gm) * 4;
+            uint32_t a0 = me_ld4(a + y * as + x), a1 = me_ld4(a + (y + 1) * as + x);
+            uint32_t b0 = me_ld4(b + y * bs + x), b1 = me_ld4(b + (y + 1) * bs + x);
+            for (int c = 0; c < 2; c++) {
+                uint32_t A = me_perm(a0, a1, c ? 0x7632 : 0x5410), B = me_perm(b0, b1, c ? 0x7632 : 0x5410);
+                int s0 = (int) (me_dot4(A, ME_ONES, 2) >> 2), s1 = (int) (me_dot4(B, ME_ONES, 2) >> 2);
+                int ae = (int) (me_dot4(me_absdiff4(A, B), ME_ONES, 2) >> 2);
+                int ta = (int) (me_dot4(me_absdiff4(A, me_perm(A, A, 0x0321)), ME_ONES, 2) >> 2);
+                int tb = (int) (me_dot4(me_absdiff4(B, me_perm(B, B, 0x0321)), ME_ONES, 2) >> 2);
+                inter += (unsigned) (me_sqr(ae) * ratio >> (5 - psy.err_w));
+                inter += (unsigned) (me_sqr(ta - tb) << psy.tex_w);
+                inter += (unsigned) (me_sqr(s0 - s1) << psy.avg_w);
+                ae = (int) (me_dot4(me_absdiff4(A, sb4), ME_ONES, 2) >> 2);
+                isb += (unsigned) (me_sqr(ae) << psy.err_w);
+                isb += (unsigned) (me_sqr(ta) << psy.tex_w);
+                isb += (unsigned) (me_sqr(s0 - avg_sb) << (psy.avg_w + 1));
+                ae = (int) (me_dot4(me_absdiff4(A, sr4), ME_ONES, 2) >> 2);
+                isrc += (unsigned) (me_sqr(ae) << psy.err_w);
+                isrc += (unsigned) (me_sqr(ta) << psy.tex_w);
+                isrc += (unsigned) (me_sqr(s0 - avg_src) << (psy.avg_w + 1));
+            }
+        }
+        *intra_err = me_wsumu(isb);
+        *intrasrc_err = me_wsumu(isrc);
+        *inter_err = me_wsumu(inter) * (unsigned) ratio >> 5;
+        return;
+    }
+    for (int k = ME_LANE; k < n; k += ME_NL) {
+        int j = k / cw, i = k - j * cw;
+        const uint8_t *pa = a + (2 * j) * as + 2 * i, *pb = b + (2 * j) * bs + 2 * i;
+        int a1 = pa[0], a2 = pa[1], a3 = pa[as], a4 = pa[as + 1];
+        int b1 = pb[0], b2 = pb[1], b3 = pb[bs], b4 = pb[bs + 1];
+        int s0 = (int) me_uavg4(a1, a2, a3, a4), s1 = (int) me_uavg4(b1, b2, b3, b4);
+        int ae, ta, tb;
+        ae = (int) me_uavg4(me_abs(a1 - b1), me_abs(a2 - b2), me_abs(a3 - b3), me_abs(a4 - b4));
+        ta = (int) me_uavg4(me_abs(a1 - a2), me_abs(a2 - a3), me_abs(a3 - a4), me_abs(a4 - a1));
+        tb = (int) me_uavg4(me_abs(b1 - b2), me_abs(b2 - b3), me_abs(b3 - b4), me_abs(b4 - b1));
+        inter += (unsigned) (me_sqr(ae) * ratio >> (5 - psy.err_w));
+        inter += (unsigned) (me_sqr(ta - tb) << psy.tex_w);
+        inter += (unsigned) (me_sqr(s0 - s1) << psy.avg_w);
+        ae = (int) me_uavg4(me_abs(a1 - avg_sb), me_abs(a2 - avg_sb), me_abs(a3 - avg_sb), me_abs(a4 - avg_sb));
+        isb += (unsigned) (me_sqr(ae) << psy.err_w);
+        isb += (unsigned) (me_sqr(ta) << psy.tex_w);
+        isb += (unsigned) (me_sqr(s0 - avg_sb) << (psy.avg_w + 1));
+        ae = (int) me_uavg4(me_abs(a1 - avg_src), me_abs(a2 - avg_src), me_abs(a3 - avg_src), me_abs(a4 - avg_src));
+        isrc += (unsigned) (me_sqr(ae) << psy.err_w);
+        isrc += (unsigned) (me_sqr(ta) << psy.tex_w);
+        isrc += (unsigned) (me_sqr(s0 - avg_src) << (psy.avg_w + 1));
+    }
+    *intra_err = me_wsumu(isb);
+    *intrasrc_err = me_wsumu(isrc);
+    *inter_err = me_wsumu(inter) * (unsigned) ratio >> 5;
+}
+
+struct MeMv { /* working copy of the block's DSV_MV */
+    int x, y;
+    unsigned flags;
+    unsigned err, dc, submask;
+};
+
+/* the four quadrant origins of a w x h block, in the reference's loop order
+ * (for g = 0; g <= sbh; g += sbh + !sbh) for f ...): returns how many there are */
+DSVCU_DEV int
+me_quadrants(int sbw, int sbh, int *qf, int *qg)
+{
+    int n = 0;
+    for (int g = 0; g <= sbh; g += (sbh + !sbh)) {
+        for (int f = 0; f <= sbw; f += (sbw + !sbw)) {
+            if (n < 4) {
+                qf[n] = f;
+                qg[n] = g;
+            }
+            n++;
+        }
+    }
+    return n < 4 ? n : 4;
+}
+
+DSVCU_DEV void
+me_test_intra_y(const MeArgs &A, MeScratch *S, int &ph, const dsvcu_mv *refmv, MeMv *mv, const uint8_t *srcd, int ss,
+                const uint8_t *refd, int rs, int detail_src, int avg_src, int neidif, unsigned ratio, int bw, int bh)
+{
+    const unsigned *R;
+    int sbw = bw / 2, sbh = bh / 2, nsub = 0, nq, qf[4], qg[4];
+    unsigned avg_tot = 0, err_sub = 0, err_src = 0;
+    unsigned avg_sub[4], avg_local[4], local_detail[4], sub_err[4], src_err[4], intererr[4];
+    int dc[4], tested[4];
+    MePsy psy;
+    int rx = refmv ? refmv->x : mv->x, ry = refmv ? refmv->y : mv->y;
+    if ((mv->x | mv->y) != 0 && neidif < 3 && me_abs(rx - mv->x) < 3 && me_abs(ry - mv->y) < 3) return;
+    if (sbw == 0 || sbh == 0) return;
+    psy.err_w = 0;
+    psy.tex_w = 1;
+    psy.avg_w = 2;
+    detail_src += detail_src / max(neidif, 1);
+    nq = me_quadrants(sbw, sbh, qf, qg);
+    /* step 1: per quadrant, mean of the prediction and detail + mean of the source */
+    ME_TASKS(t, 2 * nq) {
+        int k = t >> 1;
+        if (t & 1) {
+            unsigned al;
+            unsigned ld = (unsigned) me_block_detail(srcd + qf[k] + qg[k] * ss, ss, sbw, sbh, &al);
+            ME_PUT(4 + 2 * k, ld);
+            ME_PUT(5 + 2 * k, al);
+        } else {
+            ME_PUT(k, me_block_avg(refd + qf[k] + qg[k] * rs, rs, sbw, sbh));
+        }
+    }
+    ME_JOIN();
+    for (int k = 0; k < nq; k++) {
+        unsigned dcd;
+        avg_sub[k] = R[k];
+        local_detail[k] = R[4 + 2 * k];
+        avg_local[k] = R[5 + 2 * k];
+        dcd = (unsigned) me_abs((int) avg_local[k] - (int) avg_sub[k]) + 2;
+        tested[k] = !(mv->submask & (1u << k)) &&
+                    !(local_detail[k] > ((dcd * dcd * (unsigned) bw * (unsigned) bh * ratio) >> 5));
+        dc[k] = (int) (avg_local[k] + (unsigned) avg_src * 3 + 2) >> 2;
+    }
+    /* step 2: the three competing errors of every quadrant still in the race */
+    ME_TASKS(k, nq) {
+        if (tested[k]) {
+            unsigned e0, e1, e2;
+            me_err_intra(srcd + qf[k] + qg[k] * ss, ss, refd + qf[k] + qg[k] * rs, rs, (int) avg_sub[k], dc[k], sbw, sbh, &e0,
+                         &e1, &e2, psy, (int) ratio);
+            ME_PUT(3 * k, e0);
+            ME_PUT(3 * k + 1, e1);
+            ME_PUT(3 * k + 2, e2);
+        }
+    }
+    ME_JOIN();
+    /* step 3: the reference's sequential decision (detail_src decays as
+     * quadrants turn intra) */
+    for (int k = 0; k < nq; k++) {
+        if (!tested[k]) continue;
+        int lo, hi, lerp;
+        unsigned ld;
+        sub_err[k] = R[3 * k];
+        src_err[k] = R[3 * k + 1];
+        intererr[k] = R[3 * k + 2];
+        lo = me_avg2(detail_src, (int) local_detail[k]);
+        hi = detail_src;
+        lerp = (lo * (32 - A.psyscale) + hi * A.psyscale) >> 5;
+        ld = (unsigned) max(lerp, lo);
+        if ((sub_err[k] + ld) < intererr[k] || (src_err[k] + ld) < intererr[k]) {
+            mv->submask |= (1u << k);
+            err_src += src_err[k];
+            err_sub += sub_err[k];
+            avg_tot += (sub_err[k] < src_err[k]) ? avg_sub[k] : (unsigned) dc[k];
+            nsub++;
+            detail_src = detail_src * 4 / 5;
+        }
+    }
+    if (mv->submask) {
+        mv->flags |= MVF_INTRA;
+        mv->dc = (err_src < err_sub) ? ((avg_tot / (unsigned) nsub) | 0x100u) : 0;
+    }
+}
+
+DSVCU_DEV void
+me_test_intra_c(const MeArgs &A, MeScratch *S, int &ph, MeMv *mv, unsigned mad, unsigned detail_src, unsigned avg_src, int cbx,
+                int cby, int cbmx, int cbmy, int cbw, int cbh)
+{
+    const unsigned *R;
+    int sbw = cbw / 2, sbh = cbh / 2, nq, qf[4], qg[4];
+    unsigned thr, avg_ramp;
+    if (A.effort < 6) return;
+    thr = (mv->flags & MVF_INTRA) ? detail_src : detail_src * detail_src;
+    if (sbw == 0 || sbh == 0 || mad <= thr || thr > 64 || (me_abs(mv->x) < 4 && me_abs(mv->y) < 4)) return;
+    avg_ramp = avg_src * avg_src >> 8;
+    nq = me_quadrants(sbw, sbh, qf, qg);
+    ME_TASKS(t, 2 * nq) {
+        int k = t >> 1, u, v;
+        if (!(mv->submask & (1u << k))) {
+            if (t & 1) {
+                me_c_average(A.ref, cbmx + qf[k], cbmy + qg[k], sbw, sbh, &u, &v);
+            } else {
+                me_c_average(A.src, cbx + qf[k], cby + qg[k], sbw, sbh, &u, &v);
+            }
+            ME_PUT(2 * t, u);
+            ME_PUT(2 * t + 1, v);
+        }
+    }
+    ME_JOIN();
+    for (int k = 0; k < nq; k++) {
+        if (!(mv->submask & (1u << k))) {
+            int us = (int) R[4 * k], vs = (int) R[4 * k + 1], um = (int) R[4 * k + 2], vm = (int) R[4 * k + 3];
+            unsigned dif = (unsigned) (me_sqr(us - um) + me_sqr(vs - vm)) * avg_ramp >> 8;
+            if (dif > thr) mv->submask |= (1u << k);
+        }
+    }
+    if (mv->submask) mv->flags |= MVF_INTRA;
+}
+
+/* max over the four quadrants of the raw psy metric, luma + both chroma planes
+ * (yuv_max_subblock_err, hme.c:368-411): 12 independent metrics */
+DSVCU_DEV void
+me_yuv_max_sub(MeScratch *S, int &ph, unsigned out[3], const MePlane *sp, const MePlane *rp, int bx, int by, int brx, int bry,
+               int bw, int bh, int cbx, int cby, int cbrx, int cbry, int cbw, int cbh, const MePsy &psy, int extra_tasks,
+               const MePlane *texsrc, int tcbx, int tcby, int tcbw, int tcbh, unsigned *tex_out)
+{
+    const unsigned *R;
+    int qf[2][4], qg[2][4], nq[2];
+    nq[0] = me_quadrants(bw / 2, bh / 2, qf[0], qg[0]);
+    nq[1] = me_quadrants(cbw / 2, cbh / 2, qf[1], qg[1]);
+    ME_TASKS(t, 12 + extra_tasks) {
+        if (t >= 12) { /* chroma texture of the source block, rides along (caller's choice) */
+            int z = 1 + (t - 12);
+            ME_PUT(t, me_block_tex(texsrc[z].data + tcby * texsrc[z].stride + tcbx, texsrc[z].stride, tcbw, tcbh));
+            continue;
+        }
+        int z = t >> 2, k = t & 3, c = z ? 1 : 0;
+        unsigned v = 0;
+        if (k < nq[c]) {
+            int ox = c ? cbx : bx, oy = c ? cby : by, rx = c ? cbrx : brx, ry = c ? cbry : bry;
+            int w = (c ? cbw : bw) / 2, h = (c ? cbh : bh) / 2;
+            const uint8_t *s = sp[z].data + (oy + qg[c][k]) * sp[z].stride + ox + qf[c][k];
+            const uint8_t *r = rp[z].data + (ry + qg[c][k]) * rp[z].stride + rx + qf[c][k];
+            v = me_umetr(s, sp[z].stride, r, rp[z].stride, w, h, psy);
+        }
+        ME_PUT(t, v);
+    }
+    ME_JOIN();
+    for (int z = 0; z < 3; z++) {
+        out[z] = max(max(R[4 * z], R[4 * z + 1]), max(R[4 * z + 2], R[4 * z + 3]));
+    }
+    for (int e = 0; e < extra_tasks; e++) tex_out[e] = R[12 + e];
+}
+
+/* full-pel metric memo: the candidate scan and the descent probe overlapping
+ * positions (the reference recomputes them; the value is a pure function of the
+ * position) */
+#define ME_MEMO 24
+struct MeMemo {
+    int n;
+    int x[ME_MEMO], y[ME_MEMO];
+    unsigned v[ME_MEMO];
+};
+
+DSVCU_DEV int
+me_memo_find(const MeMemo &mm, int dx, int dy)
+{
+    for (int k = 0; k < mm.n; k++) {
+        if (mm.x[k] == dx && mm.y[k] == dy) return k;
+    }
+    return -1;
+}
+
+DSVCU_DEV void
+me_memo_add(MeMemo &mm, int dx, int dy, unsigned v)
+{
+    if (mm.n < ME_MEMO) {
+        mm.x[mm.n] = dx;
+        mm.y[mm.n] = dy;
+        mm.v[mm.n] = v;
+        mm.n++;
+    }
+}
+
+/* metrics of up to `np` positions, dealt to the warps; positions already in the
+ * memo cost nothing.  out[k] is the raw metric at (px[k], py[k]). */
+DSVCU_DEV void
+me_eval_many(MeScratch *S, int &ph, MeMemo &mm, int level, const uint8_t *srcd, int ss, const MePlane &rp, int bx, int by,
+             int np, const int *px, const int *py, int bw, int bh, const MePsy &psy, unsigned *out)
+{
+    const unsigned *R;
+    int todo[16], nt = 0;
+    for (int k = 0; k < np; k++) {
+        int m = me_memo_find(mm, px[k], py[k]);
+        if (m >= 0) {
+            out[k] = mm.v[m];
+        } else {
+            int dup = 0;
+            for (int q = 0; q < nt; q++) dup |= (px[todo[q]] == px[k] && py[todo[q]] == py[k]);
+            if (!dup) todo[nt++] = k;
+        }
+    }
+    if (nt == 0) return;
+    ME_TASKS(t, nt) {
+        int k = todo[t];
+        ME_PUT(t, me_hier_metr(level, srcd, ss, rp.data + (by + py[k]) * rp.stride + bx + px[k], rp.stride, bw, bh, psy));
+    }
+    ME_JOIN();
+    for (int t = 0; t < nt; t++) me_memo_add(mm, px[todo[t]], py[todo[t]], R[t]);
+    for (int k = 0; k < np; k++) {
+        int m = me_memo_find(mm, px[k], py[k]);
+        if (m >= 0) {
+            out[k] = mm.v[m];
+        } else { /* memo full: value is on the board */
+            for (int t = 0; t < nt; t++) {
+                if (px[todo[t]] == px[k] && py[todo[t]] == py[k]) out[k] = R[t];
+            }
+        }
+    }
+}
+
+/* ---- one block of refine_level (hme.c:1413-1823) ---- */
+
+#define ME_MAXCAND 40
+
+DSVCU_DEV void
+me_block(const MeArgs &A, MeScratch *S, int &ph, int i, int j, int *acc_local)
+{
+    const int level = A.level, step = 1 << level;
+    const MePlane &sp = A.src[0], &rp = A.ref[0];
+    const int nxb = A.nxb, nyb = A.nyb;
+    const int gx = A.gxy[0], gy = A.gxy[1];
+    const unsigned *R;
+    int bx = (i * A.y_w) >> level, by = (j * A.y_h) >> level;
+    dsvcu_mv *out = A.mvf + i + j * nxb;
+    int cx[ME_MAXCAND], cy[ME_MAXCAND], n = 0;
+    int bw, bh, dx, dy, lax = 0, lay = 0, motion_bias, good_enough = 0;
+    unsigned best, score_zero, score, best_score, qthresh, var_src = 0, avg_src = 0, zoscore;
+    MePsy psy;
+    const uint8_t *srcd;
+
+    psy.err_w = 2;
+    psy.tex_w = 1;
+    psy.avg_w = 0;
+    if (bx >= sp.w || by >= sp.h) {
+        return; /* field is zero-initialised: inter, zero vector */
+    }
+    srcd = sp.data + by * sp.stride + bx;
+    bw = min(sp.w - bx, A.y_w);
+    bh = min(sp.h - by, A.y_h);
+    MePred pred;
+    MeMemo memo;
+    memo.n = 0;
+    me_movec_pred(A.mvf, nxb, i, j, &pred.x, &pred.y);
+    cx[n] = 0;
+    cy[n] = 0;
+    n++;
+    motion_bias = A.y_w * A.y_h;
+    if (level <= 1) {
+        int tvar;
+        /* source statistics: four independent reductions */
+        ME_TASKS(t, 4) {
+            if (t == 0) {
+                unsigned av;
+                unsigned vs = (unsigned) me_block_detail(srcd, sp.stride, bw, bh, &av);
+                ME_PUT(0, vs);
+                ME_PUT(1, av);
+            } else if (t == 1) {
+                ME_PUT(2, me_block_hist_var(srcd, sp.stride, bw, bh, S->hist[2 * ME_WIC]));
+            } else if (t == 2) {
+                ME_PUT(3, me_quant_tex(srcd, sp.stride, bw, bh));
+            } else {
+                ME_PUT(4, me_block_peaks(srcd, sp.stride, bw, bh, S->hist[2 * ME_WIC + 1],
+                                         me_block_avg(srcd, sp.stride, bw, bh)));
+            }
+        }
+        ME_JOIN();
+        var_src = R[0];
+        avg_src = R[1];
+        tvar = (int) (var_src + (var_src >> 10) * (var_src >> 10));
+        tvar = ((int) (8u * (unsigned) tvar * (unsigned) A.quant) >> 9) / (bw * bh);
+        if (tvar) {
+            int hvar = (int) R[2], qtex = (int) R[3], npeaks = (int) R[4];
+            motion_bias += tvar * (hvar - qtex) * npeaks;
+        }
+        motion_bias = max(motion_bias, 0) / (2 + (me_abs(gx) + me_abs(gy)));
+        if (var_src <= (unsigned) (8 * bw * bh * A.quant >> 9)) {
+            psy.err_w = 2;
+            psy.tex_w = 1;
+            psy.avg_w = 2;
+            motion_bias = 0;
+        } else {
+            psy.err_w = 1;
+            psy.tex_w = 2;
+            psy.avg_w = 1;
+        }
+        if (var_src > (unsigned) (24 * bw * bh)) psy.avg_w = 0;
+    }
+    if (A.parent) {
+        const int pt[18] = { 0, 0, -2, 0, 2, 0, 0, -2, 0, 2, -2, -2, 2, 2, 2, -2, -2, 2 };
+        int pmask = ~((step << 1) - 1);
+        int pi = i & pmask, pj = j & pmask;
+        int lx[9], ly[9], npar = 0, sumx = 0, sumy = 0;
+        for (int m = 0; m < 9; m++) {
+            int x = pi + pt[2 * m] * step, y = pj + pt[2 * m + 1] * step;
+            if (x >= 0 && x < nxb && y >= 0 && y < nyb) {
+                const dsvcu_mv *pmv = A.parent + x + y * nxb;
+                lx[npar] = pmv->x;
+                ly[npar] = pmv->y;
+                sumx += pmv->x;
+                sumy += pmv->y;
+                npar++;
+            }
+        }
+        if (npar) {
+            /* find_inliers (hme.c:1258-1298) */
+            int dist[9], keep[9], nl = 0, avgd = 0, ssd = 0, thresh, ax, ay;
+            lax = sumx / npar;
+            lay = sumy / npar;
+            for (int m = 0; m < npar; m++) {
+                dist[m] = me_sqr(lx[m] - lax) + me_sqr(ly[m] - lay);
+                avgd += dist[m];
+            }
+            avgd /= npar;
+            for (int m = 0; m < npar; m++) ssd += me_sqr(dist[m] - avgd);
+            thresh = avgd + (int) me_isqrt((unsigned) (ssd / npar));
+            ax = 0;
+            ay = 0;
+            for (int m = 0; m < npar; m++) {
+                if (dist[m] <= thresh) {
+                    ax += lx[m];
+                    ay += ly[m];
+                    keep[nl++] = m;
+                }
+            }
+            if (nl) {
+                lax = ax / nl;
+                lay = ay / nl;
+            }
+            cx[n] = lax;
+            cy[n] = lay;
+            n++;
+            /* spatial predictions (hme.c:1202-1227); vectors pass through the
+             * qpel->fpel rounding whatever unit they are stored in */
+            if (level == 0) {
+                cx[n] = me_sar_r2(pred.x);
+                cy[n] = me_sar_r2(pred.y);
+                n++;
+            }
+            if (i > 0) {
+                int mx_, my_;
+                me_ldmv(A.mvf + (i - step) + j * nxb, &mx_, &my_, NULL);
+                cx[n] = me_sar_r2(mx_);
+                cy[n] = me_sar_r2(my_);
+                n++;
+            }
+            if (j > 0) {
+                int mx_, my_;
+                me_ldmv(A.mvf + i + (j - step) * nxb, &mx_, &my_, NULL);
+                cx[n] = me_sar_r2(mx_);
+                cy[n] = me_sar_r2(my_);
+                n++;
+            }
+            if (i > 0 && j > 0) {
+                int mx_, my_;
+                me_ldmv(A.mvf + (i - step) + (j - step) * nxb, &mx_, &my_, NULL);
+                cx[n] = me_sar_r2(mx_);
+                cy[n] = me_sar_r2(my_);
+                n++;
+            }
+            /* temporal predictions (hme.c:1229-1256) */
+            if (A.ref_mvf) {
+                const int rectx[9] = { 0, 1, -1, 0, 0, -1, 1, -1, 1 };
+                const int recty[9] = { 0, 0, 0, 1, -1, -1, -1, 1, 1 };
+                for (int k = 0; k < 9; k++) {
+                    int rx = i + rectx[k] * step, ry = j + recty[k] * step;
+                    if (rx < 0 || ry < 0 || rx >= nxb || ry >= nyb) continue;
+                    cx[n] = me_sar_r2(A.ref_mvf[rx + ry * nxb].x);
+                    cy[n] = me_sar_r2(A.ref_mvf[rx + ry * nxb].y);
+                    n++;
+                }
+            }
+            cx[n] = gx;
+            cy[n] = gy;
+            n++;
+            for (int m = 0; m < nl; m++) {
+                cx[n] = lx[keep[m]];
+                cy[n] = ly[keep[m]];
+                n++;
+            }
+        }
+    }
+    /* candidates live in int16 fields in the reference */
+    for (int k = 0; k < n; k++) {
+        cx[k] = (int16_t) cx[k] >> level;
+        cy[k] = (int16_t) cy[k] >> level;
+    }
+    {   /* remove_dupes (hme.c:1166-1183) */
+        int newn = 1;
+        for (int a = 1; a < n; a++) {
+            int b;
+            for (b = 0; b < newn; b++) {
+                if (cx[a] == cx[b] && cy[a] == cy[b]) break;
+            }
+            if (b == newn) {
+                cx[newn] = cx[a];
+                cy[newn] = cy[a];
+                newn++;
+            }
+        }
+        n = newn;
+    }
+    {
+        /* metrics of all valid candidates + the zero-vector score against the
+         * ORIGINAL reference picture, in one step */
+        int vx[ME_MAXCAND], vy[ME_MAXCAND], vk[ME_MAXCAND], nvld = 0, bestk = 0;
+        unsigned vs[ME_MAXCAND];
+        for (int k = 0; k < n; k++) {
+            if (me_invalid_block(rp.w, rp.h, bx + cx[k], by + cy[k], bw, bh, 0)) continue;
+            vx[nvld] = cx[k];
+            vy[nvld] = cy[k];
+            vk[nvld] = k;
+            nvld++;
+        }
+        ME_TASKS(t, nvld + 1) {
+            if (t == nvld) {
+                ME_PUT(t, me_metr(srcd, sp.stride, A.ogr.data + by * A.ogr.stride + bx, A.ogr.stride, bw, bh, psy));
+            } else {
+                ME_PUT(t, me_hier_metr(level, srcd, sp.stride, rp.data + (by + vy[t]) * rp.stride + bx + vx[t], rp.stride, bw,
+                                       bh, psy));
+            }
+        }
+        ME_JOIN();
+        zoscore = R[nvld];
+        for (int t = 0; t < nvld; t++) {
+            vs[t] = R[t];
+            me_memo_add(memo, vx[t], vy[t], vs[t]);
+        }
+        best_score = score_zero = 0xffffffffu;
+        for (int t = 0; t < nvld; t++) {
+            dx = vx[t];
+            dy = vy[t];
+            score = vs[t];
+            if (dx == 0 && dy == 0) score_zero = score;
+            score += (unsigned) me_mv_cost(A, pred, dx * step * 4, dy * step * 4, level);
+            if (dx == lax && dy == lay) score = (unsigned) max((int) score - (motion_bias >> level), 0);
+            if (best_score > score) {
+                best_score = score;
+                bestk = vk[t];
+            }
+        }
+        dx = cx[bestk];
+        dy = cy[bestk];
+    }
+    best = best_score;
+    qthresh = (unsigned) (A.quant * bw * bh >> 11);
+    if (me_abs(dx) <= 1 && me_abs(dy) <= 1) qthresh *= 2;
+    if (zoscore < qthresh) {
+        best = (level == 0) ? score_zero : 0;
+        dx = 0;
+        dy = 0;
+        good_enough = 1;
+    }
+    if (!good_enough) {
+        /* refine_best_fpel_cand (hme.c:1300-1370): the five cross positions are
+         * measured together, then scanned in the reference's order (which stops
+         * at the first improvement and only then has assigned metr[]) */
+        const int rectx[9] = { 0, 1, -1, 0, 0, -1, 1, -1, 1 };
+        const int recty[9] = { 0, 0, 0, 1, -1, -1, -1, 1, 1 };
+        unsigned metr[4] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu };
+        int again = 1;
+        while (again) {
+            int tvx, tvy, px[5], py[5], pk[5], np = 0;
+            unsigned ps[5];
+            again = 0;
+            for (int k = 0; k < 5; k++) {
+                tvx = dx + rectx[k];
+                tvy = dy + recty[k];
+                if (me_invalid_block(rp.w, rp.h, bx + tvx, by + tvy, bw, bh, 0)) continue;
+                px[np] = tvx;
+                py[np] = tvy;
+                pk[np] = k;
+                np++;
+            }
+            me_eval_many(S, ph, memo, level, srcd, sp.stride, rp, bx, by, np, px, py, bw, bh, psy, ps);
+            for (int t = 0; t < np; t++) {
+                int k = pk[t];
+                tvx = px[t];
+                tvy = py[t];
+                score = ps[t];
+                if (k >= 1) metr[k - 1] = score;
+                if (level == 0 && !tvx && !tvy && score <= qthresh) {
+                    dx = tvx;
+                    dy = tvy;
+                    best = score;
+                    good_enough = 1;
+                    break;
+                }
+                score += (unsigned) me_mv_cost(A, pred, tvx * step * 4, tvy * step * 4, level);
+                if (best > score) {
+                    best = score;
+                    dx = tvx;
+                    dy = tvy;
+                    again = 1;
+                    break;
+                }
+            }
+            if (again || good_enough) continue;
+            tvx = dx + rectx[(metr[0] <= metr[1]) ? 1 : 2];
+            tvy = dy + recty[(metr[2] <= metr[3]) ? 3 : 4];
+            if (me_invalid_block(rp.w, rp.h, bx + tvx, by + tvy, bw, bh, 0)) break;
+            me_eval_many(S, ph, memo, level, srcd, sp.stride, rp, bx, by, 1, &tvx, &tvy, bw, bh, psy, &score);
+            score += (unsigned) me_mv_cost(A, pred, tvx * step * 4, tvy * step * 4, level);
+            if (best > score) {
+                best = score;
+                dx = tvx;
+                dy = tvy;
+                again = 1;
+            }
+        }
+    }
+
+    MeMv mv;
+    mv.x = dx * step;
+    mv.y = dy * step;
+    mv.flags = 0;
+    mv.err = 0;
+    mv.dc = 0;
+    mv.submask = 0;
+
+    if (level == 0) {
+        int fpelx = mv.x, fpely = mv.y, subx = 0, suby = 0;
+        unsigned yarea = (unsigned) (bw * bh), best_fp;
+        if (fpelx == lax && fpely == lay) best += (unsigned) motion_bias;
+        best_fp = best;
+        if (A.effort >= 4) {
+            int tried_la = 0;
+            if (!me_invalid_block(rp.w, rp.h, bx + lax, by + lay, bw, bh, 4)) {
+                best = me_subpixel(A, S, ph, &subx, &suby, lax, lay, pred, best_fp, bx, by, bw, bh, psy);
+                tried_la = 1;
+                if (subx | suby) {
+                    fpelx = lax;
+                    fpely = lay;
+                }
+            }
+            /* the reference repeats the refinement around the full-pel winner;
+             * when that is the position just tried (and nothing was found) the
+             * second pass would recompute the very same numbers */
+            if (!(subx | suby) && !good_enough && !(tried_la && fpelx == lax && fpely == lay) &&
+                !me_invalid_block(rp.w, rp.h, bx + fpelx, by + fpely, bw, bh, 4)) {
+                best = me_subpixel(A, S, ph, &subx, &suby, fpelx, fpely, pred, best_fp, bx, by, bw, bh, psy);
+            }
+        }
+        mv.x = fpelx * 4 + subx;
+        mv.y = fpely * 4 + suby;
+        /* publish the vector now: the neighbour difference below reads it */
+        if (ME_TID == 0) {
+            out->x = (int16_t) mv.x;
+            out->y = (int16_t) mv.y;
+            out->flags = 0;
+        }
+        {
+            const uint8_t *refd = rp.data + (by + fpely) * rp.stride + bx + fpelx;
+            const uint8_t *ogrd = A.ogr.data + (by + fpely) * A.ogr.stride + bx + fpelx;
+            unsigned var_ref, avg_ref, mad, ogrerr, ogrmad, avg_y_dif, avg_c_dif;
+            int uavg_src, vavg_src, uavg_ref, vavg_ref, cbx, cby, cbw, cbh, cbmx, cbmy;
+            int eprmi, eprmd, eprmr, neidif, oob, ipolvar, dv, skipped = 0;
+            unsigned skipt = ((unsigned) A.quant * (unsigned) A.quant) >> 19;
+            unsigned ratio = 1 << 5, chroma_ratio;
+            MeChroma cpsy;
+            const dsvcu_mv *refmv = A.ref_mvf ? A.ref_mvf + i + j * nxb : NULL;
+
+            if ((mv.x | mv.y) & 3) ratio = (best << 5) / (best_fp + !best_fp);
+            cbx = i * (A.y_w >> A.hs);
+            cby = j * (A.y_h >> A.vs);
+            cbmx = cbx + (fpelx >> A.hs);
+            cbmy = cby + (fpely >> A.vs);
+            cbw = bw >> A.hs;
+            cbh = bh >> A.vs;
+            /* block statistics against the chosen reference position: five
+             * independent reductions (the barrier also publishes `out`) */
+            ME_TASKS(t, 5) {
+                if (t == 0) {
+                    ME_PUT(0, me_metr(srcd, sp.stride, ogrd, A.ogr.stride, bw, bh, psy));
+                } else if (t == 1) {
+                    unsigned av;
+                    unsigned vr = (unsigned) me_block_detail(refd, rp.stride, bw, bh, &av);
+                    ME_PUT(1, vr);
+                    ME_PUT(2, av);
+                } else if (t == 2) {
+                    int u, v;
+                    me_c_average(A.src, cbx, cby, cbw, cbh, &u, &v);
+                    ME_PUT(3, u);
+                    ME_PUT(4, v);
+                } else if (t == 3) {
+                    int u, v;
+                    me_c_average(A.ref, cbmx, cbmy, cbw, cbh, &u, &v);
+                    ME_PUT(5, u);
+                    ME_PUT(6, v);
+                } else {
+                    int e0, e1, e2;
+                    me_calc_eprm(srcd, sp.stride, refd, rp.stride, (int) avg_src, me_block_avg(refd, rp.stride, bw, bh), bw, bh,
+                                 &e0, &e1, &e2);
+                    ME_PUT(7, e0);
+                    ME_PUT(8, e1);
+                    ME_PUT(9, e2);
+                }
+            }
+            ME_JOIN();
+            ogrerr = R[0];
+            var_ref = R[1];
+            avg_ref = R[2];
+            uavg_src = (int) R[3];
+            vavg_src = (int) R[4];
+            uavg_ref = (int) R[5];
+            vavg_ref = (int) R[6];
+            eprmi = (int) R[7];
+            eprmd = (int) R[8];
+            eprmr = (int) R[9];
+            ogrmad = (ogrerr + yarea / 2) / yarea;
+            ogrmad = ogrmad * ratio >> 5;
+            mad = (best + yarea / 2) / yarea;
+            dv = (int) min(ratio, 32u);
+            ipolvar = (int) ((var_src * (unsigned) dv + var_ref * (unsigned) (32 - dv)) >> 5);
+            dv = me_abs((int) var_src - ipolvar);
+            if ((var_src > 16 * yarea) && (var_src < 32 * yarea)) mv.flags |= MVF_MAINTAIN;
+            chroma_ratio = ((unsigned) (cbw * cbh) << 4) / yarea;
+            me_chroma_analysis(&cpsy, (int) avg_src, uavg_src, vavg_src);
+            avg_y_dif = (unsigned) me_abs((int) avg_src - (int) avg_ref);
+            avg_c_dif = (unsigned) me_avg2(me_abs(uavg_src - uavg_ref), me_abs(vavg_src - vavg_ref));
+            {   /* outofbounds (hme.c:413-424) */
+                int limx = ((nxb - 1) * A.y_w) - 1, limy = ((nyb - 1) * A.y_h) - 1;
+                int px = i * A.y_w + (mv.x >> 2), py = j * A.y_h + (mv.y >> 2);
+                oob = (px < 0 || py < 0 || px >= limx || py >= limy);
+            }
+            neidif = me_neighbordif(A.mvf, nxb, i, j);
+
+            if ((good_enough || (mv.x | mv.y) == 0) && A.skip_thresh >= 0 && !A.lossless) {
+                unsigned cth, sth = skipt * yarea, zsub[3];
+                sth += 4 * var_src;
+                sth += yarea * (unsigned) A.skip_thresh;
+                if (A.quant < (1 << 10)) sth = sth * (unsigned) A.quant >> 10;
+                if (avg_y_dif <= 2) sth = max(sth, 3 * (yarea + var_src));
+                sth = max(sth, yarea);
+                if (good_enough) sth *= 2;
+                me_yuv_max_sub(S, ph, zsub, A.src, A.ref, bx, by, bx, by, bw, bh, cbx, cby, cbx, cby, cbw, cbh, psy, 0, NULL, 0,
+                               0, 0, 0, NULL);
+                cth = (chroma_ratio * sth * max(skipt, 1u) >> (4 + 1));
+                zsub[0] = zsub[0] * ratio >> 5;
+                zsub[1] = zsub[1] * ratio >> 5;
+                zsub[2] = zsub[2] * ratio >> 5;
+                zsub[0] += (unsigned) me_sqr((int) avg_src - (int) avg_ref) * yarea;
+                if (zsub[0] <= sth && zsub[1] <= cth && zsub[2] <= cth) {
+                    mv.flags |= MVF_SKIP;
+                    mv.x = 0;
+                    mv.y = 0;
+                    mv.err = 0;
+                    skipped = 1;
+                }
+            }
+            if (!skipped) {
+                if (!oob && !A.lossless) {
+                    int y_pre = (avg_y_dif <= 2), c_pre = !cpsy.greyish && (avg_c_dif <= 2);
+                    if (y_pre || c_pre) {
+                        unsigned bsub[3], xth = skipt * yarea, tex[2];
+                        int utex, vtex, carea = 4 * cbw * cbh;
+                        me_yuv_max_sub(S, ph, bsub, A.src, A.ref, bx, by, bx + fpelx, by + fpely, bw, bh, cbx, cby, cbmx, cbmy,
+                                       cbw, cbh, psy, 2, A.src, cbx, cby, cbw, cbh, tex);
+                        utex = (int) tex[0];
+                        vtex = (int) tex[1];
+                        xth += (unsigned) ipolvar;
+                        xth = (unsigned) max((int) xth - ((int) yarea * neidif * 2), 0);
+                        xth = xth * (unsigned) A.quant >> 12;
+                        xth = xth < 32 ? 32 : (xth > yarea * 4 ? yarea * 4 : xth);
+                        bsub[0] = bsub[0] * ratio >> 5;
+                        bsub[1] = bsub[1] * ratio >> 5;
+                        bsub[2] = bsub[2] * ratio >> 5;
+                        if (y_pre && bsub[0] < 4 * xth) mv.flags |= MVF_NOXMITY;
+                        c_pre &= (utex > carea || vtex > carea);
+                        xth = chroma_ratio * xth >> 4;
+                        if (c_pre && bsub[1] < xth && bsub[2] < xth) mv.flags |= MVF_NOXMITC;
+                    }
+                    if ((unsigned) dv < (var_src / 4)) mv.flags |= MVF_SIMCMPLX;
+                }
+                me_test_intra_y(A, S, ph, refmv, &mv, srcd, sp.stride, refd, rp.stride, ipolvar, (int) avg_src, neidif, ratio, bw,
+                                bh);
+                me_test_intra_c(A, S, ph, &mv, mad, (unsigned) (ipolvar / (bw * bh)), avg_src, cbx, cby, cbmx, cbmy, cbw, cbh);
+                if (!(mv.flags & MVF_NOXMITY)) {
+                    mv.err = mad & 0xffff;
+                    acc_local[3] += (int) mad;
+                }
+                acc_local[1] += (ogrmad > 11) + (avg_c_dif >= 32);
+            }
+            if (best > 0) acc_local[2]++;
+            if (mv.flags & MVF_INTRA) {
+                int merged = (mv.dc & 0x100) ? eprmd : eprmi;
+                if (mv.submask != 15) merged |= eprmr;
+                if (merged) mv.flags |= MVF_EPRM;
+                acc_local[0]++;
+                mv.x = fpelx * 4;
+                mv.y = fpely * 4;
+            } else {
+                int merged = eprmr;
+                if (mv.submask) merged |= eprmi;
+                if (merged) mv.flags |= MVF_EPRM;
+            }
+            if (mv.flags & (MVF_INTRA | MVF_EPRM)) mv.flags &= ~(unsigned) MVF_SIMCMPLX;
+        }
+    }
+    if (ME_TID == 0) {
+        out->x = (int16_t) mv.x;
+        out->y = (int16_t) mv.y;
+        out->flags = mv.flags;
+        out->err = (uint16_t) mv.err;
+        out->dc = (uint16_t) mv.dc;
+        out->submask = (uint8_t) mv.submask;
+    }
+}
+
+/* wavefront over block rows of one pyramid level: one CTA per row at a time */
+DSVCU_KERNEL void __launch_bounds__(ME_WARPS_PER_CTA * 32)
+k_me_level(MeArgs A)
+{
+    DSVCU_SHARED MeScratch scratch;
+    MeScratch *S = &scratch;
+    const int step = 1 << A.level;
+    int acc_local[4] = { 0, 0, 0, 0 };
+    int ph = 0;
+    for (int row = (int) blockIdx.x; row < A.nrows; row += (int) gridDim.x) {
+        int j = row * step;
+        int seen = (row == 0) ? 0x7fffffff : 0;
+        int col = 0;
+        for (int i = 0; i < A.nxb; i += step, col++) {
+#ifndef DSVCU_EMU
+            int need = col + 1;
+            if (seen < need) {
+                while ((seen = *(volatile const int *) (A.progress + row - 1)) < need) {
+                    __nanosleep(64); /* leave the issue slots to warps that have work */
+                }
+                __threadfence();
+            }
+#else
+            (void) seen;
+#endif
+            me_block(A, S, ph, i, j, acc_local);
+#ifndef DSVCU_EMU
+            __threadfence();
+            __syncthreads();
+            if (ME_TID == 0) *(volatile int *) (A.progress + row) = col + 1;
+#endif
+        }
+    }
+    if (ME_TID == 0 && A.level == 0) {
+        for (int k = 0; k < 4; k++) {
+            if (acc_local[k]) atomicAdd(&A.acc[k], acc_local[k]);
+        }
+    }
+}
+
+/* global_motion (hme.c:1973-1999): average vector of a level, x2 */
+DSVCU_KERNEL void __launch_bounds__(256)
+k_me_global(const dsvcu_mv *vecs, int nxb, int nyb, int level, int *gxy)
+{
+    DSVCU_SHARED int sx, sy;
+    int step = 1 << level;
+    int cols = (nxb + step - 1) / step, rows = (nyb + step - 1) / step, n = cols * rows;
+    int ax = 0, ay = 0;
+    if (DSVCU_TID == 0) {
+        sx = 0;
+        sy = 0;
+    }
+    DSVCU_SYNC();
+    PAR_FOR(k, n) {
+        int r = k / cols, c = k - r * cols;
+        const dsvcu_mv *m = vecs + c * step + r * step * nxb;
+        ax += m->x;
+        ay += m->y;
+    }
+    atomicAdd(&sx, ax);
+    atomicAdd(&sy, ay);
+    DSVCU_SYNC();
+    if (DSVCU_TID == 0) {
+        gxy[0] = n ? sx * 2 / n : 0;
+        gxy[1] = n ? sy * 2 / n : 0;
+    }
+}
+
+/* ---- dsv_intra_analysis (hme.c:1835-1971): one warp per block ---- */
+
+struct IaArgs {
+    MePlane src[3];
+    dsvcu_mv *out;
+    int nxb, nyb, y_w, y_h, hs, vs, do_psy, scale;
+};
+
+DSVCU_KERNEL void __launch_bounds__(ME_WARPS_PER_CTA * 32)
+k_intra_analysis(IaArgs A)
+{
+    DSVCU_SHARED int hists[ME_WARPS_PER_CTA][16];
+    int *hist = hists[ME_WIC];
+    const int total = A.nxb * A.nyb;
+    for (int b = ME_WARP; b < total; b += ME_NWARPS) {
+        int j = b / A.nxb, i = b - j * A.nxb;
+        int bx = i * A.y_w, by = j * A.y_h;
+        const MePlane &sp = A.src[0];
+        unsigned flags = 0;
+        if (!(bx >= sp.w || by >= sp.h)) {
+            const uint8_t *srcd = sp.data + by * sp.stride + bx;
+            int bw = min(sp.w - bx, A.y_w), bh = min(sp.h - by, A.y_h);
+            int cbx = i * (A.y_w >> A.hs), cby = j * (A.y_h >> A.vs), cbw = bw >> A.hs, cbh = bh >> A.vs;
+            unsigned luma_detail, luma_avg, var_t;
+            int maintain = 1, keep_hf = 1, npeaks = 0, foliage = 0, is_text = 0, ringing = 0;
+            MeChroma cpsy;
+            luma_detail = (unsigned) me_block_detail(srcd, sp.stride, bw, bh, &luma_avg);
+            if (A.do_psy & (16 | 2)) {
+                int skip_tones, uavg, vavg, tf = 0, tf2 = 0, qtex, hvar, luma_var, luma_tex;
+                hvar = (int) me_block_hist_var(srcd, sp.stride, bw, bh, hist);
+                qtex = me_quant_tex(srcd, sp.stride, bw, bh);
+                luma_var = me_block_var(srcd, sp.stride, bw, bh, &luma_avg);
+                luma_var /= (bw * bh);
+                luma_tex = (int) me_block_tex(srcd, sp.stride, bw, bh);
+                luma_tex /= (bw * bh);
+                npeaks = me_block_peaks(srcd, sp.stride, bw, bh, hist, (int) luma_avg);
+                is_text = (me_abs(npeaks - 2) <= 1);
+                if (qtex == 1 || qtex == 2) tf2 = hvar <= 3 && (luma_tex >= 10 && luma_var >= luma_tex);
+                if (qtex == 2 || qtex == 3) {
+                    tf = luma_tex >= 8 && luma_var >= (2 * luma_tex);
+                    tf &= (me_abs(hvar - 5) <= 3);
+                }
+                is_text &= (tf || tf2);
+                me_c_average(A.src, cbx, cby, cbw, cbh, &uavg, &vavg);
+                me_chroma_analysis(&cpsy, (int) luma_avg, uavg, vavg);
+                foliage = (cpsy.nature && luma_avg < 160);
+                foliage &= luma_detail > (unsigned) ((36 * bw * bh) / max(A.scale, 1));
+                if (foliage) is_text = 0;
+                skip_tones = cpsy.hifreq;
+                if ((A.do_psy & 16) && !skip_tones && (foliage || (hvar <= (min(qtex - 3, 2) * 16) && qtex > 1))) {
+                    ringing = 1;
+                }
+                var_t = 8;
+                if (cpsy.nature || cpsy.greyish || cpsy.skinnish) {
+                    var_t += 12;
+                } else if (!cpsy.hifreq) {
+                    var_t += 8;
+                }
+            } else {
+                var_t = 16;
+            }
+            if (A.do_psy & (2 | 1)) {
+                luma_detail /= (unsigned) (bw * bh);
+                keep_hf &= luma_detail < 48;
+                maintain = (luma_detail < var_t * 4);
+            }
+            if (A.do_psy & 2) {
+                if (foliage) {
+                    keep_hf = 0;
+                    maintain = 1;
+                } else if (is_text) {
+                    keep_hf = 1;
+                    maintain = 0;
+                }
+            }
+            if ((A.do_psy & 16) && luma_avg < 24) ringing = 1;
+            if (ringing) flags |= MVF_RINGING;
+            if (maintain) flags |= MVF_MAINTAIN;
+            if (keep_hf) flags |= MVF_SKIP;
+        }
+        if (ME_LANE == 0) {
+            dsvcu_mv *o = A.out + b;
+            o->x = 0;
+            o->y = 0;
+            o->flags = flags;
+            o->err = 0;
+            o->dc = 0;
+            o->submask = 0;
+        }
+    }
+}
+
+#endif /* K_HME_CUH */
