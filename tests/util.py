@@ -89,7 +89,12 @@ def read_y4m(path):
     w = int([t for t in toks if t[0] == "W"][0][1:])
     h = int([t for t in toks if t[0] == "H"][0][1:])
     c = [t for t in toks if t[0] == "C"][0][1:]
-    cw, ch = (w, h) if c.startswith("444") else ((w + 1) // 2, (h + 1) // 2)
+    if c.startswith("444"):
+        cw, ch = w, h
+    elif c.startswith("422"):
+        cw, ch = (w + 1) // 2, h
+    else:
+        cw, ch = (w + 1) // 2, (h + 1) // 2
     fsz = w * h + 2 * cw * ch
     off, frames = e + 1, []
     while off < len(d):

@@ -56,6 +56,9 @@ def frames(w, h, nfr, fmt="420", seed=1234, noise=24.0, sensor=3, cut=40):
         if sub == 2:
             U = (U[0::2, 0::2] + U[1::2, 0::2] + U[0::2, 1::2] + U[1::2, 1::2]) / 4.0
             V = (V[0::2, 0::2] + V[1::2, 0::2] + V[0::2, 1::2] + V[1::2, 1::2]) / 4.0
+        elif fmt == "422":
+            U = (U[:, 0::2] + U[:, 1::2]) / 2.0
+            V = (V[:, 0::2] + V[:, 1::2]) / 2.0
         U8 = np.clip(np.rint(U), 0, 255).astype(np.uint8)
         V8 = np.clip(np.rint(V), 0, 255).astype(np.uint8)
         yield Y8, U8, V8
@@ -77,7 +80,7 @@ def main(argv=None):
     ap.add_argument("-W", type=int, default=352)
     ap.add_argument("-H", type=int, default=288)
     ap.add_argument("-n", type=int, default=60)
-    ap.add_argument("--fmt", default="420", choices=["420", "444"])
+    ap.add_argument("--fmt", default="420", choices=["420", "422", "444"])
     ap.add_argument("--fps", type=int, default=30)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--noise", type=float, default=24.0)
