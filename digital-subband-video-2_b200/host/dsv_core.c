@@ -383,6 +383,8 @@ dsv_y4m_write_hdr(FILE *out, int w, int h, int subsamp, int fpsn, int fpsd, int 
         c = "422";
     } else if (subsamp == DSV_SUBSAMP_411) {
         c = "411";
+    } else if (subsamp == DSV_SUBSAMP_410) {
+        c = "410";
     }
     fprintf(out, "YUV4MPEG2 W%d H%d F%d:%d A%d:%d Ip C%s\n", w, h, fpsn, fpsd, aspn, aspd, c);
 }

@@ -46,7 +46,11 @@ CASES = [
 BIG = [
     ("fhd_b32", 1920, 1080, 3, "420", 30, ["-qp=50", "-bszx=1", "-bszy=1"], dict(qp=50, bszx=1, bszy=1), {}),
     ("hd_static", 1280, 720, 4, "420", 50, ["-qp=70"], dict(qp=70), dict(noise=0.0, sensor=0)),
-    ("uhd_strip", 2048, 256, 3, "420", 30, ["-qp=60"], dict(qp=60), {}),
+    # wider than 1280 and not "mostly square": 32 x 16 blocks (dsv_encoder.c:1203-1209).  Aspect ratios of 8:1
+    # and beyond are NOT covered: there a lifting level meets a 1-sample dimension and the reference's
+    # DO_SIMPLE_LO / DO_5_TAP_LO read v[s] outside the line (sbt.c:199, :221), i.e. stale scratch memory from
+    # earlier calls -- its own encoder and decoder disagree on such input.
+    ("wide_32x16", 1536, 384, 3, "420", 30, ["-qp=60"], dict(qp=60), {}),
 ]
 FMT = {"420": 0x5, "444": 0x0, "422": 0x4}
 
