@@ -1022,12 +1022,9 @@ run_wavefront(dsvcu_ctx *c, FiltArgs *F)
     }
     CK(dsvcu_memset_async(c->d_progress, 0, (size_t) F->nrows * sizeof(int), c->stream));
     F->progress = c->d_progress;
-#ifdef DSVCU_EMU
-    ctas = 1;
-#else
+    /* one CTA per FILT_WARPS_PER_CTA rows; CTA k only ever waits for CTA k-1,
+     * which the hardware dispatches first */
     ctas = (F->nrows + FILT_WARPS_PER_CTA - 1) / FILT_WARPS_PER_CTA;
-    if (ctas > 148 * 4) ctas = 148 * 4; /* all CTAs must be co-resident */
-#endif
     DSVCU_LAUNCH(k_filter_wavefront, ctas, FILT_WARPS_PER_CTA * 32, 0, c->stream, *F);
     CK_LAUNCH(c);
     return 0;

@@ -25,7 +25,7 @@
 #define FILT_MODE_LUMA 0
 #define FILT_MODE_INTRA 1
 #define FILT_MODE_CHROMA 2
-#define FILT_WARPS_PER_CTA 8
+#define FILT_WARPS_PER_CTA 16
 
 struct FiltArgs {
     uint8_t *data;
@@ -560,81 +560,118 @@ f_cell_active(const FiltArgs &A, int i, int j)
  * finds the next active cell with a ballot and, while it waits for that cell's
  * dependency, keeps relaying the progress of the row above (minus one cell), so
  * a region without filtering costs one flag round trip per row instead of one
- * per cell. */
+ * per cell.
+ *
+ * A CTA owns FILT_WARPS_PER_CTA consecutive rows, one warp each.  Hand-offs
+ * between rows of the same CTA go through shared-memory progress words and
+ * block-scope fences (tens of cycles); only the last row of a CTA also
+ * publishes to global memory with a device-scope fence, for the first row of
+ * the next CTA.  Pixels always travel through L2 (volatile accesses). */
+#ifndef DSVCU_EMU
+#define FILT_FENCE(dev)                  \
+    do {                                 \
+        if (dev) {                       \
+            __threadfence();             \
+        } else {                         \
+            __threadfence_block();       \
+        }                                \
+    } while (0)
+#endif
+
+DSVCU_DEV void
+f_row(const FiltArgs &A, uint8_t *T, int row, volatile int *sprog, int lr)
+{
+    const int ncols = A.ncols;
+#ifndef DSVCU_EMU
+    const int lane = FILT_LANE;
+    /* where the progress of the row above lives, and who needs ours */
+    const bool above_global = (lr == 0);
+    const bool pub_global = (lr == FILT_WARPS_PER_CTA - 1);
+    const bool dev_fence = (lr >= FILT_WARPS_PER_CTA - 2); /* rows whose pixels the next CTA reads */
+    volatile const int *above = above_global ? (volatile const int *) (A.progress + row - 1) : (sprog + lr - 1);
+    int seen = (row == 0) ? 0x7fffffff : 0; /* progress of the row above, cached */
+    int published = 0;
+#define F_PUBLISH(v)                                                      \
+    do {                                                                  \
+        published = (v);                                                  \
+        if (lane == 0) {                                                  \
+            sprog[lr] = published;                                        \
+            if (pub_global) *(volatile int *) (A.progress + row) = published; \
+        }                                                                 \
+    } while (0)
+#else
+    (void) sprog;
+    (void) lr;
+#endif
+    for (int base = 0; base < ncols; base += FILT_NLANES) {
+#ifndef DSVCU_EMU
+        int cell = base + lane;
+        unsigned mask = __ballot_sync(0xffffffffu, cell < ncols && f_cell_active(A, cell, row));
+#else
+        unsigned mask = (base < ncols && f_cell_active(A, base, row)) ? 1u : 0u;
+#endif
+        while (mask) {
+#ifndef DSVCU_EMU
+            int i = base + __ffs(mask) - 1;
+            int need = min(i + 2, ncols);
+            mask &= mask - 1;
+            while (seen < need) {
+                seen = *above;
+                int relay = min(i, seen >= ncols ? i : seen - 1);
+                if (relay > published) F_PUBLISH(relay);
+                if (seen < need && above_global) __nanosleep(32);
+            }
+            FILT_FENCE(above_global);
+            if (i > published) F_PUBLISH(i);
+#else
+            int i = base;
+            mask = 0;
+#endif
+            if (A.mode == FILT_MODE_LUMA) {
+                f_luma_cell(A, T, i, row);
+            } else if (A.mode == FILT_MODE_INTRA) {
+                f_intra_cell(A, T, i, row);
+            } else {
+                f_chroma_cell(A, i, row);
+            }
+#ifndef DSVCU_EMU
+            FILT_FENCE(dev_fence);
+            __syncwarp();
+            F_PUBLISH(i + 1);
+#endif
+        }
+    }
+#ifndef DSVCU_EMU
+    /* tail without active cells: relay until the row above is done */
+    while (seen < ncols) {
+        seen = *above;
+        int relay = seen >= ncols ? ncols : seen - 1;
+        if (relay > published) F_PUBLISH(relay);
+        if (seen < ncols && above_global) __nanosleep(32);
+    }
+    FILT_FENCE(dev_fence);
+    F_PUBLISH(ncols);
+#undef F_PUBLISH
+#endif
+}
+
 DSVCU_KERNEL void __launch_bounds__(FILT_WARPS_PER_CTA * 32)
 k_filter_wavefront(FiltArgs A)
 {
     __align__(16) DSVCU_SHARED uint8_t tiles[FILT_WARPS_PER_CTA][FT_BYTES];
-    const int lane = FILT_LANE;
-    const int ncols = A.ncols;
+    DSVCU_SHARED int sprog[FILT_WARPS_PER_CTA];
 #ifndef DSVCU_EMU
-    uint8_t *T = tiles[threadIdx.x >> 5];
+    const int lr = (int) (threadIdx.x >> 5);
+    const int row = (int) blockIdx.x * FILT_WARPS_PER_CTA + lr;
+    if (threadIdx.x < FILT_WARPS_PER_CTA) sprog[threadIdx.x] = 0;
+    __syncthreads();
+    if (row < A.nrows) f_row(A, tiles[lr], row, sprog, lr);
 #else
-    uint8_t *T = tiles[0];
-#endif
-    for (int row = FILT_WARP; row < A.nrows; row += FILT_NWARPS) {
-        int seen = (row == 0) ? 0x7fffffff : 0; /* progress of the row above, cached */
-        int published = 0;
-        (void) published;
-        for (int base = 0; base < ncols; base += FILT_NLANES) {
-#ifndef DSVCU_EMU
-            int cell = base + lane;
-            unsigned mask = __ballot_sync(0xffffffffu, cell < ncols && f_cell_active(A, cell, row));
-#else
-            unsigned mask = (base < ncols && f_cell_active(A, base, row)) ? 1u : 0u;
-#endif
-            while (mask) {
-#ifndef DSVCU_EMU
-                int i = base + __ffs(mask) - 1;
-                int need = min(i + 2, ncols);
-                mask &= mask - 1;
-                while (seen < need) {
-                    seen = PROG_LD(A.progress + row - 1);
-                    int relay = min(i, seen >= ncols ? i : seen - 1);
-                    if (relay > published) {
-                        published = relay;
-                        if (lane == 0) *(volatile int *) (A.progress + row) = relay;
-                    }
-                    if (seen < need) __nanosleep(32);
-                }
-                __threadfence();
-                if (i > published) {
-                    published = i;
-                    if (lane == 0) *(volatile int *) (A.progress + row) = i;
-                }
-#else
-                int i = base;
-                mask = 0;
-#endif
-                if (A.mode == FILT_MODE_LUMA) {
-                    f_luma_cell(A, T, i, row);
-                } else if (A.mode == FILT_MODE_INTRA) {
-                    f_intra_cell(A, T, i, row);
-                } else {
-                    f_chroma_cell(A, i, row);
-                }
-#ifndef DSVCU_EMU
-                __threadfence();
-                __syncwarp();
-                published = i + 1;
-                if (lane == 0) *(volatile int *) (A.progress + row) = i + 1;
-#endif
-            }
-        }
-#ifndef DSVCU_EMU
-        /* tail without active cells: relay until the row above is done */
-        while (seen < ncols) {
-            seen = PROG_LD(A.progress + row - 1);
-            int relay = seen >= ncols ? ncols : seen - 1;
-            if (relay > published) {
-                published = relay;
-                if (lane == 0) *(volatile int *) (A.progress + row) = relay;
-            }
-            if (seen < ncols) __nanosleep(32);
-        }
-        if (lane == 0) *(volatile int *) (A.progress + row) = ncols;
-#endif
+    for (int lr = 0; lr < FILT_WARPS_PER_CTA; lr++) {
+        int row = (int) blockIdx.x * FILT_WARPS_PER_CTA + lr;
+        if (row < A.nrows) f_row(A, tiles[0], row, sprog, lr);
     }
+#endif
 }
 
 /* dsv_post_process (bmc.c:340-361): cells are disjoint -> fully parallel */

@@ -98,6 +98,8 @@ DSVCU_DEV uint32_t me_ld4(const uint8_t *p)
     const uint32_t *q = (const uint32_t *) (a & ~(uintptr_t) 3);
     return __funnelshift_r(q[0], q[1], (unsigned) (a & 3) * 8);
 }
+/* the same when p is known to be 4-byte aligned */
+DSVCU_DEV uint32_t me_ld4a(const uint8_t *p) { return *(const uint32_t *) p; }
 DSVCU_DEV uint32_t me_absdiff4(uint32_t a, uint32_t b) { return __vabsdiffu4(a, b); }
 DSVCU_DEV unsigned me_dot4(uint32_t a, uint32_t b, unsigned acc) { return __dp4a(a, b, acc); }
 DSVCU_DEV uint32_t me_perm(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
@@ -106,6 +108,7 @@ DSVCU_DEV uint32_t me_ld4(const uint8_t *p)
 {
     return (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24);
 }
+DSVCU_DEV uint32_t me_ld4a(const uint8_t *p) { return me_ld4(p); }
 DSVCU_DEV uint32_t me_absdiff4(uint32_t a, uint32_t b)
 {
     uint32_t r = 0;
@@ -192,9 +195,13 @@ me_umetr(const uint8_t *a, int as, const uint8_t *b, int bs, int w, int h, const
     if (gs >= 0) {
         /* one work item = 4 pixels x 2 rows = two 2x2 cells */
         const int ng = ch << gs, gm = (1 << gs) - 1;
+        /* the source block is word-aligned at every level whose block origin is
+         * a multiple of 4 (always at level 0): one load instead of two per word */
+        const bool al = ((((uintptr_t) a) | (unsigned) as) & 3) == 0;
         for (int g = ME_LANE; g < ng; g += ME_NL) {
             int y = (g >> gs) * 2, x = (g & gm) * 4;
-            uint32_t a0 = me_ld4(a + y * as + x), a1 = me_ld4(a + (y + 1) * as + x);
+            uint32_t a0 = al ? me_ld4a(a + y * as + x) : me_ld4(a + y * as + x);
+            uint32_t a1 = al ? me_ld4a(a + (y + 1) * as + x) : me_ld4(a + (y + 1) * as + x);
             uint32_t b0 = me_ld4(b + y * bs + x), b1 = me_ld4(b + (y + 1) * bs + x);
             acc += me_cell4(me_perm(a0, a1, 0x5410), me_perm(b0, b1, 0x5410), p);
             acc += me_cell4(me_perm(a0, a1, 0x7632), me_perm(b0, b1, 0x7632), p);
@@ -228,9 +235,11 @@ me_sse(const uint8_t *a, int as, const uint8_t *b, int bs, int w, int h)
     const int gs = me_gshift(w);
     if (gs >= 0) {
         const int ng = h << gs, gm = (1 << gs) - 1;
+        const bool al = ((((uintptr_t) a) | (unsigned) as) & 3) == 0;
         for (int g = ME_LANE; g < ng; g += ME_NL) {
             int y = g >> gs, x = (g & gm) * 4;
-            uint32_t d = me_absdiff4(me_ld4(a + y * as + x), me_ld4(b + y * bs + x));
+            uint32_t sa = al ? me_ld4a(a + y * as + x) : me_ld4(a + y * as + x);
+            uint32_t d = me_absdiff4(sa, me_ld4(b + y * bs + x));
             acc = me_dot4(d, d, acc);
         }
         return me_wsumu(acc);
@@ -756,18 +765,16 @@ me_interp(uint8_t *tmph, uint8_t *win, int16_t *hbuf, const uint8_t *r, int rs)
     DSVCU_SYNCWARP();
 }
 
-/* quarter-pel sample (qx, qy) of the image the reference's qpel() would build */
+/* quarter-pel sample (qx, qy) of the image the reference's qpel() would build:
+ * a, avg2(a,b), avg2(a,c) or avg4(a,b,c,e) by the parity of (qx, qy).  All four
+ * cases are (a + h[ox] + h[oy*S] + h[ox + oy*S] + 2) >> 2 with ox, oy the parity
+ * bits ((2a+2b+2)>>2 == (a+b+1)>>1), so the sample is branch-free. */
 DSVCU_DEV int
 me_qsample(const uint8_t *tmph, int qx, int qy)
 {
     const uint8_t *h0 = tmph + (qy >> 1) * HP_STRIDE + (qx >> 1);
-    int a = h0[0];
-    if (qx & 1) {
-        if (qy & 1) return (a + h0[1] + h0[HP_STRIDE] + h0[HP_STRIDE + 1] + 2) >> 2;
-        return me_avg2(a, h0[1]);
-    }
-    if (qy & 1) return me_avg2(a, h0[HP_STRIDE]);
-    return a;
+    int ox = qx & 1, oy = (qy & 1) * HP_STRIDE;
+    return (h0[0] + h0[ox] + h0[oy] + h0[ox + oy] + 2) >> 2;
 }
 
 /* psy metric of the 16 x 16 source window against the quarter-pel image at
@@ -1291,7 +1298,14 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
             dx = cx[k];
             dy = cy[k];
             if (me_invalid_block(rp.w, rp.h, bx + dx, by + dy, bw, bh, 0)) continue;
-            score = me_eval(memo, level, srcd, sp.stride, rp, bx, by, dx, dy, bw, bh, psy);
+            /* candidates are unique after remove_dupes: no memo search, just record */
+            score = me_hier_metr(level, srcd, sp.stride, rp.data + (by + dy) * rp.stride + bx + dx, rp.stride, bw, bh, psy);
+            if (memo.n < ME_MEMO) {
+                memo.x[memo.n] = dx;
+                memo.y[memo.n] = dy;
+                memo.v[memo.n] = score;
+                memo.n++;
+            }
             if (dx == 0 && dy == 0) score_zero = score;
             score += (unsigned) me_mv_cost(A, pred, dx * step * 4, dy * step * 4, level);
             if (dx == lax && dy == lay) score = (unsigned) max((int) score - (motion_bias >> level), 0);
