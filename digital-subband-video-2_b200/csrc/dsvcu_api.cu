@@ -117,6 +117,7 @@ struct dsvcu_ctx {
     dsvcu_mv *d_mvf[ME_MAXLVL + 1]; /* [0] aliases d_mvs */
     dsvcu_mv *d_prev_mvf;
     int mvf_cap;
+    MePre *d_pre; /* per-block prepass records of the level being searched */
     int *d_me;  /* [0..1] global motion, [2..5] accumulators, [6] luma avg */
     int *h_me;  /* pinned mirror */
     int me_nblk;
@@ -294,6 +295,7 @@ dsvcu_ctx_destroy(dsvcu_ctx *c)
         if (c->d_mvf[i]) dsvcu_free_dev(c->d_mvf[i]);
     }
     if (c->d_prev_mvf) dsvcu_free_dev(c->d_prev_mvf);
+    if (c->d_pre) dsvcu_free_dev(c->d_pre);
     dsvcu_free_dev(c->d_me);
     dsvcu_free_host(c->h_me);
     dsvcu_free_dev(c->d_lavg);
@@ -1240,6 +1242,9 @@ ensure_mvf(dsvcu_ctx *c, int nblk)
         CK(dsvcu_malloc(&c->d_mvf[i], ((size_t) nblk + 4) * sizeof(dsvcu_mv)));
     }
     if (c->d_prev_mvf) dsvcu_free_dev(c->d_prev_mvf);
+    if (c->d_pre) dsvcu_free_dev(c->d_pre);
+    c->d_pre = NULL;
+    CK(dsvcu_malloc(&c->d_pre, ((size_t) nblk + 4) * sizeof(MePre)));
     CK(dsvcu_malloc(&c->d_prev_mvf, ((size_t) nblk + 4) * sizeof(dsvcu_mv)));
     CK(dsvcu_memset_async(c->d_prev_mvf, 0, ((size_t) nblk + 4) * sizeof(dsvcu_mv), c->stream));
     c->mvf_cap = nblk;
@@ -1318,6 +1323,19 @@ dsvcu_hme(dsvcu_ctx *c, const dsvcu_fmeta *fm, const dsvcu_hme_params *hp, dsvcu
         A.progress = c->d_progress;
         CK(dsvcu_memset_async(c->d_progress, 0, (size_t) rows * sizeof(int), c->stream));
         CK(dsvcu_memset_async(c->d_mvf[lvl], 0, (size_t) nblk * sizeof(dsvcu_mv), c->stream));
+        A.pre = c->d_pre;
+        {
+            /* everything a block needs that does not depend on its same-level
+             * neighbours, for all blocks at once */
+            int cols = (fm->nblocks_h + step - 1) / step;
+            int pctas = (cols * rows + ME_WARPS_PER_CTA - 1) / ME_WARPS_PER_CTA;
+#ifdef DSVCU_EMU
+            pctas = 1;
+#endif
+            if (pctas > 148 * 8) pctas = 148 * 8;
+            DSVCU_LAUNCH(k_me_prepass, pctas, ME_WARPS_PER_CTA * 32, 0, c->stream, A);
+            CK_LAUNCH(c);
+        }
 #ifdef DSVCU_EMU
         ctas = 1;
 #else

@@ -53,6 +53,7 @@ struct MeArgs {
     int *acc;       /* [0] nintra [1] ndiff [2] eligible [3] total_err */
     int *progress;
     int nrows;
+    struct MePre *pre; /* per-block results of k_me_prepass for this level */
 };
 
 #ifdef DSVCU_EMU
@@ -850,11 +851,15 @@ me_qpsad_multi(const uint8_t *a, int as, const uint8_t *tmph, int nv, const int 
     }
 }
 
+#define ME_MEMO 32
 struct MeScratch {
     uint8_t tmph[(2 + HP_STRIDE) * (2 + HP_STRIDE)];
     uint8_t win[ME_WIN * ME_WIN + 16];
     int16_t hbuf[(SP_DIM + 3) * SP_DIM + 4];
     int hist[16];
+    /* full-pel metric memo of the current block: position -> raw metric */
+    short memo_x[ME_MEMO], memo_y[ME_MEMO];
+    unsigned memo_v[ME_MEMO];
 };
 
 DSVCU_DEV unsigned
@@ -1090,31 +1095,247 @@ me_test_intra_c(const MeArgs &A, MeMv *mv, unsigned mad, unsigned detail_src, un
     if (mv->submask) mv->flags |= MVF_INTRA;
 }
 
-/* full-pel metric with a per-block memo: the candidate scan and the descent
- * probe overlapping positions (the reference recomputes them; the value is a
- * pure function of the position) */
-#define ME_MEMO 24
-struct MeMemo {
-    int n;
-    int x[ME_MEMO], y[ME_MEMO];
-    unsigned v[ME_MEMO];
+/* ---- neighbour-independent part of a block, computed for every block of a
+ * level in parallel by k_me_prepass and consumed by the wavefront ---- */
+#define ME_PRE_NB 20 /* temporal (<= 9) + global + parent inliers (<= 9) */
+#define ME_PRE_NM 24
+struct MePre {
+    unsigned var_src, avg_src;
+    int motion_bias, psy_pack; /* err_w | tex_w << 8 | avg_w << 16 */
+    int lax, lay, has_list, nb;
+    unsigned zoscore;
+    int uavg, vavg, nm;
+    short bx[ME_PRE_NB], by[ME_PRE_NB]; /* non-spatial candidates after (lax, lay), raw units */
+    short mx[ME_PRE_NM], my[ME_PRE_NM]; /* positions already measured ... */
+    unsigned mv[ME_PRE_NM];             /* ... and their raw metric */
 };
 
-DSVCU_DEV unsigned
-me_eval(MeMemo &mm, int level, const uint8_t *srcd, int ss, const MePlane &rp, int bx, int by, int dx, int dy, int bw, int bh,
-        const MePsy &psy)
+/* Full-pel metric memo.  The candidate scan and the descent probe overlapping
+ * positions, and k_me_prepass has already measured the neighbour-independent
+ * candidates; the value is a pure function of the position (the reference
+ * recomputes it).  Entries live in per-warp shared memory, one per lane, so a
+ * lookup is one compare + ballot. */
+DSVCU_DEV int
+me_memo_find(const MeScratch *S, int n, int dx, int dy)
 {
-    for (int k = 0; k < mm.n; k++) {
-        if (mm.x[k] == dx && mm.y[k] == dy) return mm.v[k];
+#ifndef DSVCU_EMU
+    int l = ME_LANE;
+    unsigned hit = __ballot_sync(0xffffffffu, l < n && S->memo_x[l] == dx && S->memo_y[l] == dy);
+    return hit ? __ffs(hit) - 1 : -1;
+#else
+    for (int k = 0; k < n; k++) {
+        if (S->memo_x[k] == dx && S->memo_y[k] == dy) return k;
     }
+    return -1;
+#endif
+}
+
+DSVCU_DEV void
+me_memo_add(MeScratch *S, int &n, int dx, int dy, unsigned v)
+{
+    if (n < ME_MEMO) {
+        if (ME_LANE == 0) {
+            S->memo_x[n] = (short) dx;
+            S->memo_y[n] = (short) dy;
+            S->memo_v[n] = v;
+        }
+        n++;
+        DSVCU_SYNCWARP();
+    }
+}
+
+DSVCU_DEV unsigned
+me_eval(MeScratch *S, int &mn, int level, const uint8_t *srcd, int ss, const MePlane &rp, int bx, int by, int dx, int dy, int bw,
+        int bh, const MePsy &psy)
+{
+    int k = me_memo_find(S, mn, dx, dy);
+    if (k >= 0) return S->memo_v[k];
     unsigned sc = me_hier_metr(level, srcd, ss, rp.data + (by + dy) * rp.stride + bx + dx, rp.stride, bw, bh, psy);
-    if (mm.n < ME_MEMO) {
-        mm.x[mm.n] = dx;
-        mm.y[mm.n] = dy;
-        mm.v[mm.n] = sc;
-        mm.n++;
-    }
+    me_memo_add(S, mn, dx, dy, sc);
     return sc;
+}
+
+/* source-block statistics -> metric weights and motion bias (hme.c:1445-1481) */
+DSVCU_DEV void
+me_src_stats(const MeArgs &A, MeScratch *S, const uint8_t *srcd, int ss, int bw, int bh, int gx, int gy, unsigned *pvar,
+             unsigned *pavg, int *pbias, MePsy *ppsy)
+{
+    MePsy psy;
+    unsigned var_src = 0, avg_src = 0;
+    int motion_bias = A.y_w * A.y_h;
+    psy.err_w = 2;
+    psy.tex_w = 1;
+    psy.avg_w = 0;
+    if (A.level <= 1) {
+        int tvar;
+        var_src = (unsigned) me_block_detail(srcd, ss, bw, bh, &avg_src);
+        tvar = (int) (var_src + (var_src >> 10) * (var_src >> 10));
+        tvar = ((int) (8u * (unsigned) tvar * (unsigned) A.quant) >> 9) / (bw * bh);
+        if (tvar) {
+            int hvar = (int) me_block_hist_var(srcd, ss, bw, bh, S->hist);
+            int qtex = me_quant_tex(srcd, ss, bw, bh);
+            int npeaks = me_block_peaks(srcd, ss, bw, bh, S->hist, (int) avg_src);
+            motion_bias += tvar * (hvar - qtex) * npeaks;
+        }
+        motion_bias = max(motion_bias, 0) / (2 + (me_abs(gx) + me_abs(gy)));
+        if (var_src <= (unsigned) (8 * bw * bh * A.quant >> 9)) {
+            psy.err_w = 2;
+            psy.tex_w = 1;
+            psy.avg_w = 2;
+            motion_bias = 0;
+        } else {
+            psy.err_w = 1;
+            psy.tex_w = 2;
+            psy.avg_w = 1;
+        }
+        if (var_src > (unsigned) (24 * bw * bh)) psy.avg_w = 0;
+    }
+    *pvar = var_src;
+    *pavg = avg_src;
+    *pbias = motion_bias;
+    *ppsy = psy;
+}
+
+/* candidates that do not depend on same-level neighbours: parent average with
+ * outlier rejection (find_inliers, hme.c:1258-1298), temporal neighbours of the
+ * previous picture's field (:1229-1256), global motion, parent inliers.
+ * Returns has_list (the reference only builds the list when the parent level
+ * gave at least one vector); values are raw (before the >> level) */
+DSVCU_DEV int
+me_nonspatial(const MeArgs &A, int i, int j, int gx, int gy, int *plax, int *play, int *bx, int *by, int *pnb)
+{
+    const int step = 1 << A.level, nxb = A.nxb, nyb = A.nyb;
+    int nb = 0;
+    *plax = 0;
+    *play = 0;
+    *pnb = 0;
+    if (!A.parent) return 0;
+    const int pt[18] = { 0, 0, -2, 0, 2, 0, 0, -2, 0, 2, -2, -2, 2, 2, 2, -2, -2, 2 };
+    int pmask = ~((step << 1) - 1);
+    int pi = i & pmask, pj = j & pmask;
+    int lx[9], ly[9], npar = 0, sumx = 0, sumy = 0;
+    for (int m = 0; m < 9; m++) {
+        int x = pi + pt[2 * m] * step, y = pj + pt[2 * m + 1] * step;
+        if (x >= 0 && x < nxb && y >= 0 && y < nyb) {
+            const dsvcu_mv *pmv = A.parent + x + y * nxb;
+            lx[npar] = pmv->x;
+            ly[npar] = pmv->y;
+            sumx += pmv->x;
+            sumy += pmv->y;
+            npar++;
+        }
+    }
+    if (!npar) return 0;
+    int dist[9], keep[9], nl = 0, avgd = 0, ssd = 0, thresh, ax = 0, ay = 0;
+    int lax = sumx / npar, lay = sumy / npar;
+    for (int m = 0; m < npar; m++) {
+        dist[m] = me_sqr(lx[m] - lax) + me_sqr(ly[m] - lay);
+        avgd += dist[m];
+    }
+    avgd /= npar;
+    for (int m = 0; m < npar; m++) ssd += me_sqr(dist[m] - avgd);
+    thresh = avgd + (int) me_isqrt((unsigned) (ssd / npar));
+    for (int m = 0; m < npar; m++) {
+        if (dist[m] <= thresh) {
+            ax += lx[m];
+            ay += ly[m];
+            keep[nl++] = m;
+        }
+    }
+    if (nl) {
+        lax = ax / nl;
+        lay = ay / nl;
+    }
+    *plax = lax;
+    *play = lay;
+    if (A.ref_mvf) {
+        const int rectx[9] = { 0, 1, -1, 0, 0, -1, 1, -1, 1 };
+        const int recty[9] = { 0, 0, 0, 1, -1, -1, -1, 1, 1 };
+        for (int k = 0; k < 9; k++) {
+            int rx = i + rectx[k] * step, ry = j + recty[k] * step;
+            if (rx < 0 || ry < 0 || rx >= nxb || ry >= nyb) continue;
+            bx[nb] = me_sar_r2(A.ref_mvf[rx + ry * nxb].x);
+            by[nb] = me_sar_r2(A.ref_mvf[rx + ry * nxb].y);
+            nb++;
+        }
+    }
+    bx[nb] = gx;
+    by[nb] = gy;
+    nb++;
+    for (int m = 0; m < nl; m++) {
+        bx[nb] = lx[keep[m]];
+        by[nb] = ly[keep[m]];
+        nb++;
+    }
+    *pnb = nb;
+    return 1;
+}
+
+/* neighbour-independent half of refine_level's block loop, all blocks of the
+ * level in parallel (one warp per block) */
+DSVCU_DEV void
+me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j)
+{
+    const int level = A.level;
+    const MePlane &sp = A.src[0], &rp = A.ref[0];
+    const int gx = A.gxy[0], gy = A.gxy[1];
+    int bx = (i * A.y_w) >> level, by = (j * A.y_h) >> level;
+    MePre *P = A.pre + i + j * A.nxb;
+    if (bx >= sp.w || by >= sp.h) return;
+    const uint8_t *srcd = sp.data + by * sp.stride + bx;
+    int bw = min(sp.w - bx, A.y_w), bh = min(sp.h - by, A.y_h);
+    unsigned var_src, avg_src, zoscore;
+    int motion_bias, lax, lay, nb, cbx[ME_PRE_NB], cby[ME_PRE_NB], has, mn = 0, uavg = 0, vavg = 0;
+    MePsy psy;
+    me_src_stats(A, S, srcd, sp.stride, bw, bh, gx, gy, &var_src, &avg_src, &motion_bias, &psy);
+    has = me_nonspatial(A, i, j, gx, gy, &lax, &lay, cbx, cby, &nb);
+    /* measure zero, the parent average and the list (valid, distinct positions) */
+    for (int k = -2; k < (has ? nb : 0); k++) {
+        int dx, dy;
+        if (k == -2) {
+            dx = 0;
+            dy = 0;
+        } else if (k == -1) {
+            if (!has) continue;
+            dx = (int16_t) lax >> level;
+            dy = (int16_t) lay >> level;
+        } else {
+            dx = (int16_t) cbx[k] >> level;
+            dy = (int16_t) cby[k] >> level;
+        }
+        if (me_invalid_block(rp.w, rp.h, bx + dx, by + dy, bw, bh, 0)) continue;
+        if (mn >= ME_PRE_NM) break;
+        (void) me_eval(S, mn, level, srcd, sp.stride, rp, bx, by, dx, dy, bw, bh, psy);
+    }
+    zoscore = me_metr(srcd, sp.stride, A.ogr.data + by * A.ogr.stride + bx, A.ogr.stride, bw, bh, psy);
+    if (level == 0) {
+        me_c_average(A.src, i * (A.y_w >> A.hs), j * (A.y_h >> A.vs), bw >> A.hs, bh >> A.vs, &uavg, &vavg);
+    }
+    DSVCU_SYNCWARP();
+    if (ME_LANE == 0) {
+        P->var_src = var_src;
+        P->avg_src = avg_src;
+        P->motion_bias = motion_bias;
+        P->psy_pack = psy.err_w | (psy.tex_w << 8) | (psy.avg_w << 16);
+        P->lax = lax;
+        P->lay = lay;
+        P->has_list = has;
+        P->nb = nb;
+        P->zoscore = zoscore;
+        P->uavg = uavg;
+        P->vavg = vavg;
+        P->nm = mn;
+        for (int k = 0; k < nb; k++) {
+            P->bx[k] = (short) cbx[k];
+            P->by[k] = (short) cby[k];
+        }
+    }
+    for (int k = ME_LANE; k < mn; k += ME_NL) {
+        P->mx[k] = S->memo_x[k];
+        P->my[k] = S->memo_y[k];
+        P->mv[k] = S->memo_v[k];
+    }
+    DSVCU_SYNCWARP();
 }
 
 /* ---- one block of refine_level (hme.c:1413-1823) ---- */
@@ -1146,129 +1367,67 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
     bw = min(sp.w - bx, A.y_w);
     bh = min(sp.h - by, A.y_h);
     MePred pred;
-    MeMemo memo;
-    memo.n = 0;
+    int mn = 0; /* entries in the block's metric memo */
+    const MePre *P = A.pre + i + j * nxb;
     me_movec_pred(A.mvf, nxb, i, j, &pred.x, &pred.y);
+    /* neighbour-independent results of k_me_prepass: statistics, metric weights,
+     * the non-spatial candidates and their metrics (memo seed) */
+    var_src = P->var_src;
+    avg_src = P->avg_src;
+    motion_bias = P->motion_bias;
+    psy.err_w = P->psy_pack & 255;
+    psy.tex_w = (P->psy_pack >> 8) & 255;
+    psy.avg_w = (P->psy_pack >> 16) & 255;
+    mn = P->nm;
+    for (int k = ME_LANE; k < mn; k += ME_NL) {
+        S->memo_x[k] = P->mx[k];
+        S->memo_y[k] = P->my[k];
+        S->memo_v[k] = P->mv[k];
+    }
+    DSVCU_SYNCWARP();
     cx[n] = 0;
     cy[n] = 0;
     n++;
-    motion_bias = A.y_w * A.y_h;
-    if (level <= 1) {
-        int tvar;
-        var_src = (unsigned) me_block_detail(srcd, sp.stride, bw, bh, &avg_src);
-        tvar = (int) (var_src + (var_src >> 10) * (var_src >> 10));
-        tvar = ((int) (8u * (unsigned) tvar * (unsigned) A.quant) >> 9) / (bw * bh);
-        if (tvar) {
-            int hvar = (int) me_block_hist_var(srcd, sp.stride, bw, bh, S->hist);
-            int qtex = me_quant_tex(srcd, sp.stride, bw, bh);
-            int npeaks = me_block_peaks(srcd, sp.stride, bw, bh, S->hist, (int) avg_src);
-            motion_bias += tvar * (hvar - qtex) * npeaks;
-        }
-        motion_bias = max(motion_bias, 0) / (2 + (me_abs(gx) + me_abs(gy)));
-        if (var_src <= (unsigned) (8 * bw * bh * A.quant >> 9)) {
-            psy.err_w = 2;
-            psy.tex_w = 1;
-            psy.avg_w = 2;
-            motion_bias = 0;
-        } else {
-            psy.err_w = 1;
-            psy.tex_w = 2;
-            psy.avg_w = 1;
-        }
-        if (var_src > (unsigned) (24 * bw * bh)) psy.avg_w = 0;
-    }
-    if (A.parent) {
-        const int pt[18] = { 0, 0, -2, 0, 2, 0, 0, -2, 0, 2, -2, -2, 2, 2, 2, -2, -2, 2 };
-        int pmask = ~((step << 1) - 1);
-        int pi = i & pmask, pj = j & pmask;
-        int lx[9], ly[9], npar = 0, sumx = 0, sumy = 0;
-        for (int m = 0; m < 9; m++) {
-            int x = pi + pt[2 * m] * step, y = pj + pt[2 * m + 1] * step;
-            if (x >= 0 && x < nxb && y >= 0 && y < nyb) {
-                const dsvcu_mv *pmv = A.parent + x + y * nxb;
-                lx[npar] = pmv->x;
-                ly[npar] = pmv->y;
-                sumx += pmv->x;
-                sumy += pmv->y;
-                npar++;
-            }
-        }
-        if (npar) {
-            /* find_inliers (hme.c:1258-1298) */
-            int dist[9], keep[9], nl = 0, avgd = 0, ssd = 0, thresh, ax, ay;
-            lax = sumx / npar;
-            lay = sumy / npar;
-            for (int m = 0; m < npar; m++) {
-                dist[m] = me_sqr(lx[m] - lax) + me_sqr(ly[m] - lay);
-                avgd += dist[m];
-            }
-            avgd /= npar;
-            for (int m = 0; m < npar; m++) ssd += me_sqr(dist[m] - avgd);
-            thresh = avgd + (int) me_isqrt((unsigned) (ssd / npar));
-            ax = 0;
-            ay = 0;
-            for (int m = 0; m < npar; m++) {
-                if (dist[m] <= thresh) {
-                    ax += lx[m];
-                    ay += ly[m];
-                    keep[nl++] = m;
-                }
-            }
-            if (nl) {
-                lax = ax / nl;
-                lay = ay / nl;
-            }
-            cx[n] = lax;
-            cy[n] = lay;
+    if (P->has_list) {
+        const int nb = P->nb;
+        lax = P->lax;
+        lay = P->lay;
+        cx[n] = lax;
+        cy[n] = lay;
+        n++;
+        /* spatial predictions (hme.c:1202-1227); vectors pass through the
+         * qpel->fpel rounding whatever unit they are stored in */
+        if (level == 0) {
+            cx[n] = me_sar_r2(pred.x);
+            cy[n] = me_sar_r2(pred.y);
             n++;
-            /* spatial predictions (hme.c:1202-1227); vectors pass through the
-             * qpel->fpel rounding whatever unit they are stored in */
-            if (level == 0) {
-                cx[n] = me_sar_r2(pred.x);
-                cy[n] = me_sar_r2(pred.y);
-                n++;
-            }
-            if (i > 0) {
-                int mx_, my_;
-                me_ldmv(A.mvf + (i - step) + j * nxb, &mx_, &my_, NULL);
-                cx[n] = me_sar_r2(mx_);
-                cy[n] = me_sar_r2(my_);
-                n++;
-            }
-            if (j > 0) {
-                int mx_, my_;
-                me_ldmv(A.mvf + i + (j - step) * nxb, &mx_, &my_, NULL);
-                cx[n] = me_sar_r2(mx_);
-                cy[n] = me_sar_r2(my_);
-                n++;
-            }
-            if (i > 0 && j > 0) {
-                int mx_, my_;
-                me_ldmv(A.mvf + (i - step) + (j - step) * nxb, &mx_, &my_, NULL);
-                cx[n] = me_sar_r2(mx_);
-                cy[n] = me_sar_r2(my_);
-                n++;
-            }
-            /* temporal predictions (hme.c:1229-1256) */
-            if (A.ref_mvf) {
-                const int rectx[9] = { 0, 1, -1, 0, 0, -1, 1, -1, 1 };
-                const int recty[9] = { 0, 0, 0, 1, -1, -1, -1, 1, 1 };
-                for (int k = 0; k < 9; k++) {
-                    int rx = i + rectx[k] * step, ry = j + recty[k] * step;
-                    if (rx < 0 || ry < 0 || rx >= nxb || ry >= nyb) continue;
-                    cx[n] = me_sar_r2(A.ref_mvf[rx + ry * nxb].x);
-                    cy[n] = me_sar_r2(A.ref_mvf[rx + ry * nxb].y);
-                    n++;
-                }
-            }
-            cx[n] = gx;
-            cy[n] = gy;
+        }
+        if (i > 0) {
+            int mx_, my_;
+            me_ldmv(A.mvf + (i - step) + j * nxb, &mx_, &my_, NULL);
+            cx[n] = me_sar_r2(mx_);
+            cy[n] = me_sar_r2(my_);
             n++;
-            for (int m = 0; m < nl; m++) {
-                cx[n] = lx[keep[m]];
-                cy[n] = ly[keep[m]];
-                n++;
-            }
+        }
+        if (j > 0) {
+            int mx_, my_;
+            me_ldmv(A.mvf + i + (j - step) * nxb, &mx_, &my_, NULL);
+            cx[n] = me_sar_r2(mx_);
+            cy[n] = me_sar_r2(my_);
+            n++;
+        }
+        if (i > 0 && j > 0) {
+            int mx_, my_;
+            me_ldmv(A.mvf + (i - step) + (j - step) * nxb, &mx_, &my_, NULL);
+            cx[n] = me_sar_r2(mx_);
+            cy[n] = me_sar_r2(my_);
+            n++;
+        }
+        /* temporal neighbours, global motion, parent inliers (from the prepass) */
+        for (int k = 0; k < nb; k++) {
+            cx[n] = P->bx[k];
+            cy[n] = P->by[k];
+            n++;
         }
     }
     /* candidates live in int16 fields in the reference */
@@ -1298,14 +1457,7 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
             dx = cx[k];
             dy = cy[k];
             if (me_invalid_block(rp.w, rp.h, bx + dx, by + dy, bw, bh, 0)) continue;
-            /* candidates are unique after remove_dupes: no memo search, just record */
-            score = me_hier_metr(level, srcd, sp.stride, rp.data + (by + dy) * rp.stride + bx + dx, rp.stride, bw, bh, psy);
-            if (memo.n < ME_MEMO) {
-                memo.x[memo.n] = dx;
-                memo.y[memo.n] = dy;
-                memo.v[memo.n] = score;
-                memo.n++;
-            }
+            score = me_eval(S, mn, level, srcd, sp.stride, rp, bx, by, dx, dy, bw, bh, psy);
             if (dx == 0 && dy == 0) score_zero = score;
             score += (unsigned) me_mv_cost(A, pred, dx * step * 4, dy * step * 4, level);
             if (dx == lax && dy == lay) score = (unsigned) max((int) score - (motion_bias >> level), 0);
@@ -1320,7 +1472,7 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
     best = best_score;
     qthresh = (unsigned) (A.quant * bw * bh >> 11);
     {
-        unsigned zoscore = me_metr(srcd, sp.stride, A.ogr.data + by * A.ogr.stride + bx, A.ogr.stride, bw, bh, psy);
+        unsigned zoscore = P->zoscore;
         if (me_abs(dx) <= 1 && me_abs(dy) <= 1) qthresh *= 2;
         if (zoscore < qthresh) {
             best = (level == 0) ? score_zero : 0;
@@ -1342,7 +1494,7 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
                 tvx = dx + rectx[k];
                 tvy = dy + recty[k];
                 if (me_invalid_block(rp.w, rp.h, bx + tvx, by + tvy, bw, bh, 0)) continue;
-                score = me_eval(memo, level, srcd, sp.stride, rp, bx, by, tvx, tvy, bw, bh, psy);
+                score = me_eval(S, mn, level, srcd, sp.stride, rp, bx, by, tvx, tvy, bw, bh, psy);
                 if (k >= 1) metr[k - 1] = score;
                 if (level == 0 && !tvx && !tvy && score <= qthresh) {
                     dx = tvx;
@@ -1364,7 +1516,7 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
             tvx = dx + rectx[(metr[0] <= metr[1]) ? 1 : 2];
             tvy = dy + recty[(metr[2] <= metr[3]) ? 3 : 4];
             if (me_invalid_block(rp.w, rp.h, bx + tvx, by + tvy, bw, bh, 0)) break;
-            score = me_eval(memo, level, srcd, sp.stride, rp, bx, by, tvx, tvy, bw, bh, psy);
+            score = me_eval(S, mn, level, srcd, sp.stride, rp, bx, by, tvx, tvy, bw, bh, psy);
             score += (unsigned) me_mv_cost(A, pred, tvx * step * 4, tvy * step * 4, level);
             if (best > score) {
                 best = score;
@@ -1444,7 +1596,8 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
             cbw = bw >> A.hs;
             cbh = bh >> A.vs;
             chroma_ratio = ((unsigned) (cbw * cbh) << 4) / yarea;
-            me_c_average(A.src, cbx, cby, cbw, cbh, &uavg_src, &vavg_src);
+            uavg_src = P->uavg;
+            vavg_src = P->vavg;
             me_c_average(A.ref, cbmx, cbmy, cbw, cbh, &uavg_ref, &vavg_ref);
             me_chroma_analysis(&cpsy, (int) avg_src, uavg_src, vavg_src);
             avg_y_dif = (unsigned) me_abs((int) avg_src - (int) avg_ref);
@@ -1537,6 +1690,20 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
         out->submask = (uint8_t) mv.submask;
     }
     DSVCU_SYNCWARP();
+}
+
+/* neighbour-independent half of every block of a level: one warp per block */
+DSVCU_KERNEL void __launch_bounds__(ME_WARPS_PER_CTA * 32)
+k_me_prepass(MeArgs A)
+{
+    DSVCU_SHARED MeScratch scratch[ME_WARPS_PER_CTA];
+    MeScratch *S = &scratch[ME_WIC];
+    const int step = 1 << A.level;
+    const int cols = (A.nxb + step - 1) / step, rows = (A.nyb + step - 1) / step;
+    for (int b = ME_WARP; b < cols * rows; b += ME_NWARPS) {
+        int r = b / cols, c = b - r * cols;
+        me_prepass_block(A, S, c * step, r * step);
+    }
 }
 
 /* wavefront over block rows of one pyramid level */
