@@ -862,18 +862,25 @@ struct MeScratch {
     unsigned memo_v[ME_MEMO];
 };
 
-DSVCU_DEV unsigned
-me_subpixel(const MeArgs &A, MeScratch *S, int *outx, int *outy, int fpelx, int fpely, const MePred &pr, unsigned best, int bx,
-            int by, int bw, int bh, const MePsy &psy)
+/* Sub-pel refinement, split in two.  me_subpel_measure: everything that depends
+ * only on the full-pel position -- the four neighbour SSEs that order the
+ * search (hme.c:1084-1136), the half-pel image and the metric at the <= 7 test
+ * offsets in the reference's order (:1137-1160).  me_subpel_decide: the scalar
+ * part that needs the block's running best score and rate predictor. */
+struct MeSubpel {
+    int nv;
+    int tx[ME_MAXSP], ty[ME_MAXSP];
+    unsigned sc[ME_MAXSP];
+};
+
+DSVCU_DEV void
+me_subpel_measure(const MeArgs &A, MeScratch *S, MeSubpel *M, int fpelx, int fpely, int bx, int by, int bw, int bh,
+                  const MePsy &psy)
 {
     const MePlane &sp = A.src[0], &rp = A.ref[0];
-    unsigned quad[4], score, ms1, ms2;
-    int pri[2], sec[2], diag[2], bestv[2] = { 0, 0 };
-    int yarea = bw * bh, area_ratio, iarea_ratio, xx, yy;
+    unsigned quad[4], ms1, ms2;
+    int pri[2], sec[2], diag[2], xx, yy, nv = 0;
     const int ddx[4] = { 1, -1, 0, 0 }, ddy[4] = { 0, 0, 1, -1 };
-    *outx = 0;
-    *outy = 0;
-    if (best == 0) return best;
     {
         const uint8_t *s = sp.data + by * sp.stride + bx;
         for (int n = 0; n < 4; n++) {
@@ -881,9 +888,6 @@ me_subpixel(const MeArgs &A, MeScratch *S, int *outx, int *outy, int fpelx, int 
             quad[n] = me_sse(s, sp.stride, r, rp.stride, bw, bh);
         }
     }
-    area_ratio = 8 * (SP_SZ * SP_SZ) / yarea;
-    iarea_ratio = 8 * yarea / (SP_SZ * SP_SZ);
-    best = best * (unsigned) area_ratio >> 3;
     xx = bx + ((bw >> 1) - ((SP_SZ + 1) / 2));
     yy = by + ((bh >> 1) - ((SP_SZ + 1) / 2));
     me_interp(S->tmph, S->win, S->hbuf, rp.data + (yy + fpely - 1) * rp.stride + xx + fpelx - 1, rp.stride);
@@ -907,36 +911,41 @@ me_subpixel(const MeArgs &A, MeScratch *S, int *outx, int *outy, int fpelx, int 
     }
     diag[0] = pri[0] + sec[0];
     diag[1] = pri[1] + sec[1];
-    {
-        const uint8_t *ssp = sp.data + yy * sp.stride + xx;
-        int tvx[ME_MAXSP], tvy[ME_MAXSP], nv = 0;
-        unsigned sc[ME_MAXSP];
-        /* test order of the reference (hme.c:1137-1160): half then quarter
-         * steps along pri, sec, diag, then pri + diag */
-        for (int n = 0; n <= 6; n++) {
-            int t[2];
-            if (n == 6) {
-                t[0] = pri[0] + diag[0];
-                t[1] = pri[1] + diag[1];
-            } else {
-                int hp = !(n & 1);
-                const int *tv = (n >> 1) == 0 ? pri : ((n >> 1) == 1 ? sec : diag);
-                t[0] = tv[0] * (1 << hp);
-                t[1] = tv[1] * (1 << hp);
-            }
-            if (((t[0] | t[1]) & 1) && A.effort < 8) continue;
-            tvx[nv] = t[0];
-            tvy[nv] = t[1];
-            nv++;
+    /* test order of the reference: half then quarter steps along pri, sec,
+     * diag, then pri + diag */
+    for (int n = 0; n <= 6; n++) {
+        int t[2];
+        if (n == 6) {
+            t[0] = pri[0] + diag[0];
+            t[1] = pri[1] + diag[1];
+        } else {
+            int hp = !(n & 1);
+            const int *tv = (n >> 1) == 0 ? pri : ((n >> 1) == 1 ? sec : diag);
+            t[0] = tv[0] * (1 << hp);
+            t[1] = tv[1] * (1 << hp);
         }
-        me_qpsad_multi(ssp, sp.stride, S->tmph, nv, tvx, tvy, psy, sc);
-        for (int n = 0; n < nv; n++) {
-            score = sc[n] + (unsigned) me_mv_cost(A, pr, fpelx * 4 + tvx[n], fpely * 4 + tvy[n], 0);
-            if (best > score) {
-                best = score;
-                bestv[0] = tvx[n];
-                bestv[1] = tvy[n];
-            }
+        if (((t[0] | t[1]) & 1) && A.effort < 8) continue;
+        M->tx[nv] = t[0];
+        M->ty[nv] = t[1];
+        nv++;
+    }
+    M->nv = nv;
+    me_qpsad_multi(sp.data + yy * sp.stride + xx, sp.stride, S->tmph, nv, M->tx, M->ty, psy, M->sc);
+}
+
+DSVCU_DEV unsigned
+me_subpel_decide(const MeArgs &A, const MeSubpel *M, int *outx, int *outy, int fpelx, int fpely, const MePred &pr,
+                 unsigned best, int bw, int bh)
+{
+    int yarea = bw * bh, bestv[2] = { 0, 0 };
+    int area_ratio = 8 * (SP_SZ * SP_SZ) / yarea, iarea_ratio = 8 * yarea / (SP_SZ * SP_SZ);
+    best = best * (unsigned) area_ratio >> 3;
+    for (int n = 0; n < M->nv; n++) {
+        unsigned score = M->sc[n] + (unsigned) me_mv_cost(A, pr, fpelx * 4 + M->tx[n], fpely * 4 + M->ty[n], 0);
+        if (best > score) {
+            best = score;
+            bestv[0] = M->tx[n];
+            bestv[1] = M->ty[n];
         }
     }
     *outx = bestv[0];
@@ -1108,6 +1117,10 @@ struct MePre {
     short bx[ME_PRE_NB], by[ME_PRE_NB]; /* non-spatial candidates after (lax, lay), raw units */
     short mx[ME_PRE_NM], my[ME_PRE_NM]; /* positions already measured ... */
     unsigned mv[ME_PRE_NM];             /* ... and their raw metric */
+    /* level 0: sub-pel measurements around the parent-average position (lax, lay) */
+    int sp_valid, sp_nv;
+    signed char sp_tx[ME_MAXSP + 1], sp_ty[ME_MAXSP + 1];
+    unsigned sp_sc[ME_MAXSP];
 };
 
 /* Full-pel metric memo.  The candidate scan and the descent probe overlapping
@@ -1308,11 +1321,26 @@ me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j)
         (void) me_eval(S, mn, level, srcd, sp.stride, rp, bx, by, dx, dy, bw, bh, psy);
     }
     zoscore = me_metr(srcd, sp.stride, A.ogr.data + by * A.ogr.stride + bx, A.ogr.stride, bw, bh, psy);
+    MeSubpel M;
+    int sp_valid = 0;
+    M.nv = 0;
     if (level == 0) {
         me_c_average(A.src, i * (A.y_w >> A.hs), j * (A.y_h >> A.vs), bw >> A.hs, bh >> A.vs, &uavg, &vavg);
+        /* the first sub-pel pass of the reference is always around (lax, lay) */
+        if (A.effort >= 4 && !me_invalid_block(rp.w, rp.h, bx + lax, by + lay, bw, bh, 4)) {
+            me_subpel_measure(A, S, &M, lax, lay, bx, by, bw, bh, psy);
+            sp_valid = 1;
+        }
     }
     DSVCU_SYNCWARP();
     if (ME_LANE == 0) {
+        P->sp_valid = sp_valid;
+        P->sp_nv = M.nv;
+        for (int k = 0; k < M.nv; k++) {
+            P->sp_tx[k] = (signed char) M.tx[k];
+            P->sp_ty[k] = (signed char) M.ty[k];
+            P->sp_sc[k] = M.sc[k];
+        }
         P->var_src = var_src;
         P->avg_src = avg_src;
         P->motion_bias = motion_bias;
@@ -1348,7 +1376,6 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
     const int level = A.level, step = 1 << level;
     const MePlane &sp = A.src[0], &rp = A.ref[0];
     const int nxb = A.nxb, nyb = A.nyb;
-    const int gx = A.gxy[0], gy = A.gxy[1];
     int bx = (i * A.y_w) >> level, by = (j * A.y_h) >> level;
     dsvcu_mv *out = A.mvf + i + j * nxb;
     int cx[ME_MAXCAND], cy[ME_MAXCAND], n = 0;
@@ -1542,8 +1569,20 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
         best_fp = best;
         if (A.effort >= 4) {
             int tried_la = 0;
+            MeSubpel M;
             if (!me_invalid_block(rp.w, rp.h, bx + lax, by + lay, bw, bh, 4)) {
-                best = me_subpixel(A, S, &subx, &suby, lax, lay, pred, best_fp, bx, by, bw, bh, psy);
+                /* measured by the prepass; only the decision is left */
+                if (best_fp != 0) {
+                    M.nv = P->sp_nv;
+                    for (int k = 0; k < M.nv; k++) {
+                        M.tx[k] = P->sp_tx[k];
+                        M.ty[k] = P->sp_ty[k];
+                        M.sc[k] = P->sp_sc[k];
+                    }
+                    best = me_subpel_decide(A, &M, &subx, &suby, lax, lay, pred, best_fp, bw, bh);
+                } else {
+                    best = best_fp;
+                }
                 tried_la = 1;
                 if (subx | suby) {
                     fpelx = lax;
@@ -1555,7 +1594,12 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
              * second pass would recompute the very same numbers */
             if (!(subx | suby) && !good_enough && !(tried_la && fpelx == lax && fpely == lay) &&
                 !me_invalid_block(rp.w, rp.h, bx + fpelx, by + fpely, bw, bh, 4)) {
-                best = me_subpixel(A, S, &subx, &suby, fpelx, fpely, pred, best_fp, bx, by, bw, bh, psy);
+                if (best_fp != 0) {
+                    me_subpel_measure(A, S, &M, fpelx, fpely, bx, by, bw, bh, psy);
+                    best = me_subpel_decide(A, &M, &subx, &suby, fpelx, fpely, pred, best_fp, bw, bh);
+                } else {
+                    best = best_fp;
+                }
             }
         }
         mv.x = fpelx * 4 + subx;
