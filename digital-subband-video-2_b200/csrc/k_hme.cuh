@@ -953,6 +953,34 @@ me_subpel_decide(const MeArgs &A, const MeSubpel *M, int *outx, int *outy, int f
     return best * (unsigned) iarea_ratio >> 3;
 }
 
+/* ---- neighbour-independent part of a block, computed for every block of a
+ * level in parallel by k_me_prepass and consumed by the wavefront ---- */
+#define ME_PRE_NB 20 /* temporal (<= 9) + global + parent inliers (<= 9) */
+#define ME_PRE_NM 32
+struct MePre {
+    unsigned var_src, avg_src;
+    int motion_bias, psy_pack; /* err_w | tex_w << 8 | avg_w << 16 */
+    int lax, lay, has_list, nb;
+    unsigned zoscore;
+    int uavg, vavg, nm;
+    short bx[ME_PRE_NB], by[ME_PRE_NB]; /* non-spatial candidates after (lax, lay), raw units */
+    short mx[ME_PRE_NM], my[ME_PRE_NM]; /* positions already measured ... */
+    unsigned mv[ME_PRE_NM];             /* ... and their raw metric */
+    /* level 0: statistics of the block against the reference at (lax, lay) [0]
+     * and at the zero vector [1] (what the mode decision needs once the final
+     * vector is known), source-side quadrant statistics for the intra test,
+     * chroma texture of the source block */
+    int rs_valid[2];
+    unsigned rs_ogrerr[2], rs_var[2], rs_avg[2];
+    int rs_u[2], rs_v[2], rs_eprm[2]; /* eprm: bit0 i, bit1 d, bit2 r */
+    unsigned q_detail[4], q_avg[4];
+    int utex, vtex;
+    /* level 0: sub-pel measurements around the parent-average position (lax, lay) */
+    int sp_valid, sp_nv;
+    signed char sp_tx[ME_MAXSP + 1], sp_ty[ME_MAXSP + 1];
+    unsigned sp_sc[ME_MAXSP];
+};
+
 /* ---- intra sub-block tests (hme.c:839-1049) ---- */
 
 DSVCU_DEV void
@@ -1027,7 +1055,7 @@ struct MeMv { /* working copy of the block's DSV_MV */
 };
 
 DSVCU_DEV void
-me_test_intra_y(const MeArgs &A, const dsvcu_mv *refmv, MeMv *mv, const uint8_t *srcd, int ss, const uint8_t *refd, int rs,
+me_test_intra_y(const MeArgs &A, const MePre *P, const dsvcu_mv *refmv, MeMv *mv, const uint8_t *srcd, int ss, const uint8_t *refd, int rs,
                 int detail_src, int avg_src, int neidif, unsigned ratio, int bw, int bh)
 {
     int sbw = bw / 2, sbh = bh / 2, bit_index = 0, nsub = 0;
@@ -1047,7 +1075,8 @@ me_test_intra_y(const MeArgs &A, const dsvcu_mv *refmv, MeMv *mv, const uint8_t 
             int dc, lo, hi, lerp, sub_better, src_better;
             if (bit_index < 4 && !(mv->submask & (1u << bit_index))) {
                 avg_sub = (unsigned) me_block_avg(mvr_d, rs, sbw, sbh);
-                local_detail = (unsigned) me_block_detail(src_d, ss, sbw, sbh, &avg_local);
+                local_detail = P->q_detail[bit_index]; /* source-side, from the prepass */
+                avg_local = P->q_avg[bit_index];
                 dcd = (unsigned) me_abs((int) avg_local - (int) avg_sub) + 2;
                 if (!(local_detail > ((dcd * dcd * (unsigned) bw * (unsigned) bh * ratio) >> 5))) {
                     dc = (int) (avg_local + (unsigned) avg_src * 3 + 2) >> 2;
@@ -1103,25 +1132,6 @@ me_test_intra_c(const MeArgs &A, MeMv *mv, unsigned mad, unsigned detail_src, un
     }
     if (mv->submask) mv->flags |= MVF_INTRA;
 }
-
-/* ---- neighbour-independent part of a block, computed for every block of a
- * level in parallel by k_me_prepass and consumed by the wavefront ---- */
-#define ME_PRE_NB 20 /* temporal (<= 9) + global + parent inliers (<= 9) */
-#define ME_PRE_NM 24
-struct MePre {
-    unsigned var_src, avg_src;
-    int motion_bias, psy_pack; /* err_w | tex_w << 8 | avg_w << 16 */
-    int lax, lay, has_list, nb;
-    unsigned zoscore;
-    int uavg, vavg, nm;
-    short bx[ME_PRE_NB], by[ME_PRE_NB]; /* non-spatial candidates after (lax, lay), raw units */
-    short mx[ME_PRE_NM], my[ME_PRE_NM]; /* positions already measured ... */
-    unsigned mv[ME_PRE_NM];             /* ... and their raw metric */
-    /* level 0: sub-pel measurements around the parent-average position (lax, lay) */
-    int sp_valid, sp_nv;
-    signed char sp_tx[ME_MAXSP + 1], sp_ty[ME_MAXSP + 1];
-    unsigned sp_sc[ME_MAXSP];
-};
 
 /* Full-pel metric memo.  The candidate scan and the descent probe overlapping
  * positions, and k_me_prepass has already measured the neighbour-independent
@@ -1284,6 +1294,30 @@ me_nonspatial(const MeArgs &A, int i, int j, int gx, int gy, int *plax, int *pla
     return 1;
 }
 
+/* statistics of a block against the reference at full-pel offset (fx, fy):
+ * metric against the ORIGINAL reference picture, detail + mean of the
+ * prediction, chroma means, EPRM clipping tests (hme.c:1640-1690) */
+struct MeRefStats {
+    unsigned ogrerr, var_ref, avg_ref;
+    int u, v, eprm;
+};
+
+DSVCU_DEV void
+me_ref_stats(const MeArgs &A, MeRefStats *R, const uint8_t *srcd, int i, int j, int bx, int by, int bw, int bh, int fx, int fy,
+             int avg_src, const MePsy &psy)
+{
+    const MePlane &sp = A.src[0], &rp = A.ref[0];
+    const uint8_t *refd = rp.data + (by + fy) * rp.stride + bx + fx;
+    const uint8_t *ogrd = A.ogr.data + (by + fy) * A.ogr.stride + bx + fx;
+    int e0, e1, e2;
+    R->ogrerr = me_metr(srcd, sp.stride, ogrd, A.ogr.stride, bw, bh, psy);
+    R->var_ref = (unsigned) me_block_detail(refd, rp.stride, bw, bh, &R->avg_ref);
+    me_c_average(A.ref, i * (A.y_w >> A.hs) + (fx >> A.hs), j * (A.y_h >> A.vs) + (fy >> A.vs), bw >> A.hs, bh >> A.vs, &R->u,
+                 &R->v);
+    me_calc_eprm(srcd, sp.stride, refd, rp.stride, avg_src, (int) R->avg_ref, bw, bh, &e0, &e1, &e2);
+    R->eprm = (e0 ? 1 : 0) | (e1 ? 2 : 0) | (e2 ? 4 : 0);
+}
+
 /* neighbour-independent half of refine_level's block loop, all blocks of the
  * level in parallel (one warp per block) */
 DSVCU_DEV void
@@ -1320,7 +1354,44 @@ me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j)
         if (mn >= ME_PRE_NM) break;
         (void) me_eval(S, mn, level, srcd, sp.stride, rp, bx, by, dx, dy, bw, bh, psy);
     }
+    if (has) {
+        /* the descent starts at the best candidate, most often the parent
+         * average: measure its eight neighbours too */
+        const int nx[8] = { 1, -1, 0, 0, -1, 1, -1, 1 }, ny[8] = { 0, 0, 1, -1, -1, -1, 1, 1 };
+        int cxl = (int16_t) lax >> level, cyl = (int16_t) lay >> level;
+        for (int k = 0; k < 8 && mn < ME_PRE_NM; k++) {
+            if (me_invalid_block(rp.w, rp.h, bx + cxl + nx[k], by + cyl + ny[k], bw, bh, 0)) continue;
+            (void) me_eval(S, mn, level, srcd, sp.stride, rp, bx, by, cxl + nx[k], cyl + ny[k], bw, bh, psy);
+        }
+    }
     zoscore = me_metr(srcd, sp.stride, A.ogr.data + by * A.ogr.stride + bx, A.ogr.stride, bw, bh, psy);
+    MeRefStats rs[2];
+    int rs_valid[2] = { 0, 0 }, utex = 0, vtex = 0;
+    unsigned q_detail[4] = { 0, 0, 0, 0 }, q_avg[4] = { 0, 0, 0, 0 };
+    if (level == 0) {
+        int qn = 0, sbw = bw / 2, sbh = bh / 2;
+        int cbw = bw >> A.hs, cbh = bh >> A.vs, cbx = i * (A.y_w >> A.hs), cby = j * (A.y_h >> A.vs);
+        if (!me_invalid_block(rp.w, rp.h, bx + lax, by + lay, bw, bh, 0)) {
+            me_ref_stats(A, &rs[0], srcd, i, j, bx, by, bw, bh, lax, lay, (int) avg_src, psy);
+            rs_valid[0] = 1;
+        }
+        if (lax | lay) {
+            me_ref_stats(A, &rs[1], srcd, i, j, bx, by, bw, bh, 0, 0, (int) avg_src, psy);
+            rs_valid[1] = 1;
+        }
+        if (sbw && sbh) {
+            for (int g = 0; g <= sbh; g += (sbh + !sbh)) {
+                for (int f = 0; f <= sbw; f += (sbw + !sbw)) {
+                    if (qn < 4) q_detail[qn] = (unsigned) me_block_detail(srcd + f + g * sp.stride, sp.stride, sbw, sbh, &q_avg[qn]);
+                    qn++;
+                }
+            }
+        }
+        if (cbw > 0 && cbh > 0) {
+            utex = (int) me_block_tex(A.src[1].data + cby * A.src[1].stride + cbx, A.src[1].stride, cbw, cbh);
+            vtex = (int) me_block_tex(A.src[2].data + cby * A.src[2].stride + cbx, A.src[2].stride, cbw, cbh);
+        }
+    }
     MeSubpel M;
     int sp_valid = 0;
     M.nv = 0;
@@ -1334,6 +1405,23 @@ me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j)
     }
     DSVCU_SYNCWARP();
     if (ME_LANE == 0) {
+        for (int k = 0; k < 2; k++) {
+            P->rs_valid[k] = rs_valid[k];
+            if (rs_valid[k]) {
+                P->rs_ogrerr[k] = rs[k].ogrerr;
+                P->rs_var[k] = rs[k].var_ref;
+                P->rs_avg[k] = rs[k].avg_ref;
+                P->rs_u[k] = rs[k].u;
+                P->rs_v[k] = rs[k].v;
+                P->rs_eprm[k] = rs[k].eprm;
+            }
+        }
+        for (int k = 0; k < 4; k++) {
+            P->q_detail[k] = q_detail[k];
+            P->q_avg[k] = q_avg[k];
+        }
+        P->utex = utex;
+        P->vtex = vtex;
         P->sp_valid = sp_valid;
         P->sp_nv = M.nv;
         for (int k = 0; k < M.nv; k++) {
@@ -1623,11 +1711,35 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
             const dsvcu_mv *refmv = A.ref_mvf ? A.ref_mvf + i + j * nxb : NULL;
 
             if ((mv.x | mv.y) & 3) ratio = (best << 5) / (best_fp + !best_fp);
-            ogrerr = me_metr(srcd, sp.stride, ogrd, A.ogr.stride, bw, bh, psy);
+            {
+                /* reference-side statistics at the chosen position: from the
+                 * prepass when that position is the parent average or zero */
+                int slot = (fpelx == lax && fpely == lay && P->rs_valid[0]) ? 0
+                         : ((fpelx | fpely) == 0 && P->rs_valid[1]) ? 1 : -1;
+                MeRefStats rs;
+                if (slot >= 0) {
+                    rs.ogrerr = P->rs_ogrerr[slot];
+                    rs.var_ref = P->rs_var[slot];
+                    rs.avg_ref = P->rs_avg[slot];
+                    rs.u = P->rs_u[slot];
+                    rs.v = P->rs_v[slot];
+                    rs.eprm = P->rs_eprm[slot];
+                } else {
+                    me_ref_stats(A, &rs, srcd, i, j, bx, by, bw, bh, fpelx, fpely, (int) avg_src, psy);
+                }
+                ogrerr = rs.ogrerr;
+                var_ref = rs.var_ref;
+                avg_ref = rs.avg_ref;
+                uavg_ref = rs.u;
+                vavg_ref = rs.v;
+                eprmi = rs.eprm & 1;
+                eprmd = (rs.eprm >> 1) & 1;
+                eprmr = (rs.eprm >> 2) & 1;
+            }
+            (void) ogrd;
             ogrmad = (ogrerr + yarea / 2) / yarea;
             ogrmad = ogrmad * ratio >> 5;
             mad = (best + yarea / 2) / yarea;
-            var_ref = (unsigned) me_block_detail(refd, rp.stride, bw, bh, &avg_ref);
             dv = (int) min(ratio, 32u);
             ipolvar = (int) ((var_src * (unsigned) dv + var_ref * (unsigned) (32 - dv)) >> 5);
             dv = me_abs((int) var_src - ipolvar);
@@ -1642,11 +1754,9 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
             chroma_ratio = ((unsigned) (cbw * cbh) << 4) / yarea;
             uavg_src = P->uavg;
             vavg_src = P->vavg;
-            me_c_average(A.ref, cbmx, cbmy, cbw, cbh, &uavg_ref, &vavg_ref);
             me_chroma_analysis(&cpsy, (int) avg_src, uavg_src, vavg_src);
             avg_y_dif = (unsigned) me_abs((int) avg_src - (int) avg_ref);
             avg_c_dif = (unsigned) me_avg2(me_abs(uavg_src - uavg_ref), me_abs(vavg_src - vavg_ref));
-            me_calc_eprm(srcd, sp.stride, refd, rp.stride, (int) avg_src, (int) avg_ref, bw, bh, &eprmi, &eprmd, &eprmr);
             {   /* outofbounds (hme.c:413-424) */
                 int limx = ((nxb - 1) * A.y_w) - 1, limy = ((nyb - 1) * A.y_h) - 1;
                 int px = i * A.y_w + (mv.x >> 2), py = j * A.y_h + (mv.y >> 2);
@@ -1692,15 +1802,15 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
                         bsub[1] = bsub[1] * ratio >> 5;
                         bsub[2] = bsub[2] * ratio >> 5;
                         if (y_pre && bsub[0] < 4 * xth) mv.flags |= MVF_NOXMITY;
-                        utex = (int) me_block_tex(A.src[1].data + cby * A.src[1].stride + cbx, A.src[1].stride, cbw, cbh);
-                        vtex = (int) me_block_tex(A.src[2].data + cby * A.src[2].stride + cbx, A.src[2].stride, cbw, cbh);
+                        utex = P->utex;
+                        vtex = P->vtex;
                         c_pre &= (utex > carea || vtex > carea);
                         xth = chroma_ratio * xth >> 4;
                         if (c_pre && bsub[1] < xth && bsub[2] < xth) mv.flags |= MVF_NOXMITC;
                     }
                     if ((unsigned) dv < (var_src / 4)) mv.flags |= MVF_SIMCMPLX;
                 }
-                me_test_intra_y(A, refmv, &mv, srcd, sp.stride, refd, rp.stride, ipolvar, (int) avg_src, neidif, ratio, bw,
+                me_test_intra_y(A, P, refmv, &mv, srcd, sp.stride, refd, rp.stride, ipolvar, (int) avg_src, neidif, ratio, bw,
                                 bh);
                 me_test_intra_c(A, &mv, mad, (unsigned) (ipolvar / (bw * bh)), avg_src, cbx, cby, cbmx, cbmy, cbw, cbh);
                 if (!(mv.flags & MVF_NOXMITY)) {
