@@ -1550,27 +1550,43 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
         cx[k] = (int16_t) cx[k] >> level;
         cy[k] = (int16_t) cy[k] >> level;
     }
-    {   /* remove_dupes (hme.c:1166-1183) */
-        int newn = 1;
-        for (int a = 1; a < n; a++) {
-            int b;
-            for (b = 0; b < newn; b++) {
-                if (cx[a] == cx[b] && cy[a] == cy[b]) break;
-            }
-            if (b == newn) {
-                cx[newn] = cx[a];
-                cy[newn] = cy[a];
-                newn++;
-            }
-        }
-        n = newn;
-    }
     {
-        int bestk = 0;
+        /* remove_dupes (hme.c:1166-1183) keeps the FIRST occurrence of every
+         * position, then the candidates are scored in list order.  On the device
+         * each lane holds one candidate (n <= 32): duplicates are found with one
+         * match instruction and the survivors are visited in lane order. */
+        int bestx = cx[0], besty = cy[0];
         best_score = score_zero = 0xffffffffu;
+#ifndef DSVCU_EMU
+        const int lane = ME_LANE;
+        const int myx = lane < n ? cx[lane] : 0, myy = lane < n ? cy[lane] : 0;
+        const unsigned key = lane < n ? (((unsigned) myx << 16) | ((unsigned) myy & 0xffffu)) : (0x7fff0000u | (unsigned) lane);
+        const unsigned same = __match_any_sync(0xffffffffu, key);
+        unsigned keep = __ballot_sync(0xffffffffu, lane < n && (__ffs(same) - 1) == lane);
+        for (; keep; keep &= keep - 1) {
+            const int srcl = __ffs(keep) - 1;
+            dx = __shfl_sync(0xffffffffu, myx, srcl);
+            dy = __shfl_sync(0xffffffffu, myy, srcl);
+#else
+        {
+            int newn = 1;
+            for (int a = 1; a < n; a++) {
+                int b;
+                for (b = 0; b < newn; b++) {
+                    if (cx[a] == cx[b] && cy[a] == cy[b]) break;
+                }
+                if (b == newn) {
+                    cx[newn] = cx[a];
+                    cy[newn] = cy[a];
+                    newn++;
+                }
+            }
+            n = newn;
+        }
         for (int k = 0; k < n; k++) {
             dx = cx[k];
             dy = cy[k];
+#endif
             if (me_invalid_block(rp.w, rp.h, bx + dx, by + dy, bw, bh, 0)) continue;
             score = me_eval(S, mn, level, srcd, sp.stride, rp, bx, by, dx, dy, bw, bh, psy);
             if (dx == 0 && dy == 0) score_zero = score;
@@ -1578,11 +1594,12 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
             if (dx == lax && dy == lay) score = (unsigned) max((int) score - (motion_bias >> level), 0);
             if (best_score > score) {
                 best_score = score;
-                bestk = k;
+                bestx = dx;
+                besty = dy;
             }
         }
-        dx = cx[bestk];
-        dy = cy[bestk];
+        dx = bestx;
+        dy = besty;
     }
     best = best_score;
     qthresh = (unsigned) (A.quant * bw * bh >> 11);
