@@ -41,6 +41,7 @@ struct FiltArgs {
     int ncols, nrows;
     int *progress;
     int mode;
+    int cached; /* set per row by the kernel: tile loads may use L1 */
 };
 
 #ifdef DSVCU_EMU
@@ -264,6 +265,53 @@ f_neighbordif2(const dsvcu_mv *vecs, int nbh, int x, int y, int *dx, int *dy)
     *dy = f_abs(vx1 - cmx) + f_abs(vy1 - cmy);
 }
 
+/* Everything a cell needs that depends only on block data (vectors, flags):
+ * evaluated by one lane per cell while the warp looks for active cells, then
+ * broadcast to the warp when the cell is processed -- the scalar set-up
+ * (divisions, vector loads, neighbour differences) leaves the serial chain. */
+struct FPrep {
+    int mvxy;  /* x | y << 16 */
+    int bits;  /* flags (8) | submask << 8 | edgeh << 16 | edgehs << 17 | edgev << 18 | edgevs << 19 | blockdata << 24 */
+    int nd;    /* ndx | ndy << 16 */
+    int active;
+};
+
+DSVCU_DEV FPrep
+f_prep(const FiltArgs &A, int i, int j)
+{
+    FPrep P;
+    P.mvxy = 0;
+    P.bits = 0;
+    P.nd = 0;
+    P.active = 0;
+    if (A.mode == FILT_MODE_CHROMA) {
+        return P; /* chroma blocks keep the direct path */
+    }
+    const int nsbx = A.w / 4, nsby = A.h / 4;
+    const int x = i * 4, y = j * 4;
+    if (y + 4 >= A.h || x + 4 >= A.w) return P;
+    const int fy = j * A.nbv / nsby, fx = i * A.nbh / nsbx;
+    if (A.mode == FILT_MODE_INTRA) {
+        int bd = A.blockdata[fx + fy * A.nbh];
+        P.bits = bd << 24;
+        P.active = !(bd & BD_RING);
+        return P;
+    }
+    const dsvcu_mv mv = A.mvs[fx + fy * A.nbh];
+    int ndx = 0, ndy = 0;
+    P.mvxy = (mv.x & 0xffff) | ((int) mv.y << 16);
+    P.bits = (int) (mv.flags & 255u) | ((int) mv.submask << 8) | (((x % A.blk_w) == 0) << 16) |
+             (((x % (A.blk_w / 2)) == 0) << 17) | (((y % A.blk_h) == 0) << 18) | (((y % (A.blk_h / 2)) == 0) << 19);
+    if (mv.flags & MVF_SKIP) return P;
+    if (A.do_filter && !(mv.flags & MVF_INTRA)) {
+        f_neighbordif2(A.mvs, A.nbh, fx, fy, &ndx, &ndy);
+    }
+    P.nd = (ndx & 0xffff) | (ndy << 16);
+    P.active = (mv.flags & MVF_INTRA) || (A.do_filter && (ndx || ndy)) ||
+               (A.sharpen && (mv.x & 3) && (mv.y & 3) && ((mv.x | mv.y) & 1) && f_abs(mv.x) < 8 && f_abs(mv.y) < 8);
+    return P;
+}
+
 /* ---- per-cell staging.  A cell reads and writes inside the 11 x 11 pixel
  * neighbourhood rows y-3..y+7, cols x-3..x+7.  Instead of three dependent
  * round trips to L2 (texture probe, horizontal pass, vertical pass) the warp
@@ -284,7 +332,12 @@ f_tile_load(uint8_t *T, const FiltArgs &A, int x, int y)
         int r = k / 3, q = k - r * 3;
         const uint8_t *g = A.data + (ptrdiff_t) (y - 3 + r) * A.stride + x - 4 + 4 * q;
 #ifndef DSVCU_EMU
-        *(uint32_t *) (T + r * FT_S + 4 * q) = *(volatile const uint32_t *) g;
+        /* pixels a cell reads were last written by rows r-2 .. r of the same
+         * picture.  For rows >= 2 inside a CTA all of them ran on this SM, so an
+         * L1-cached load is coherent (after the block-scope fence of the
+         * hand-off); the first two rows of a CTA read what another SM wrote and
+         * go to L2. */
+        *(uint32_t *) (T + r * FT_S + 4 * q) = A.cached ? *(const uint32_t *) g : *(volatile const uint32_t *) g;
 #else
         memcpy(T + r * FT_S + 4 * q, g, 4);
 #endif
@@ -329,20 +382,23 @@ f_tile_view(const FiltArgs &A, uint8_t *T, int x, int y)
     return L;
 }
 
-/* one 4x4 cell of luma_filter (bmc.c:492-600) */
+/* one 4x4 cell of luma_filter (bmc.c:492-600); P = f_prep() of this cell */
 DSVCU_DEV int
-f_luma_cell(const FiltArgs &G, uint8_t *T, int i, int j)
+f_luma_cell(const FiltArgs &G, uint8_t *T, int i, int j, const FPrep &P)
 {
     const FiltArgs &A = G;
-    const int nsbx = A.w / 4, nsby = A.h / 4;
     const int x = i * 4, y = j * 4;
     int touched = 0;
-    if (y + 4 >= A.h || x + 4 >= A.w) return 0;
-    const int fy = j * A.nbv / nsby, fx = i * A.nbh / nsbx;
-    const dsvcu_mv mv = A.mvs[fx + fy * A.nbh];
-    if (mv.flags & MVF_SKIP) return 0;
-    const int edgev = (y % A.blk_h) == 0, edgevs = (y % (A.blk_h / 2)) == 0;
-    const int edgeh = (x % A.blk_w) == 0, edgehs = (x % (A.blk_w / 2)) == 0;
+    struct {
+        int x, y;
+        unsigned flags, submask;
+    } mv;
+    mv.x = (int16_t) (P.mvxy & 0xffff);
+    mv.y = (int16_t) (P.mvxy >> 16);
+    mv.flags = (unsigned) P.bits & 255u;
+    mv.submask = ((unsigned) P.bits >> 8) & 255u;
+    const int edgeh = (P.bits >> 16) & 1, edgehs = (P.bits >> 17) & 1;
+    const int edgev = (P.bits >> 18) & 1, edgevs = (P.bits >> 19) & 1;
     const int amx = f_abs(mv.x), amy = f_abs(mv.y);
     const int q = A.q;
     uint8_t *dxy = T + FT_ORG;
@@ -363,10 +419,7 @@ f_luma_cell(const FiltArgs &G, uint8_t *T, int i, int j)
         f_tile_store(T, A, x, y, 3);
         return 1;
     }
-    int ndx = 0, ndy = 0;
-    if (A.do_filter) {
-        f_neighbordif2(A.mvs, A.nbh, fx, fy, &ndx, &ndy);
-    }
+    int ndx = P.nd & 0xffff, ndy = (P.nd >> 16) & 0xffff;
     if (A.do_filter && (ndx || ndy)) {
         int tt, addx, addy, sh, sv, shl, svl;
         int eprm = (mv.flags & MVF_EPRM) != 0;
@@ -422,15 +475,11 @@ f_luma_cell(const FiltArgs &G, uint8_t *T, int i, int j)
 
 /* one 4x4 cell of dsv_intra_filter (bmc.c:411-455) */
 DSVCU_DEV int
-f_intra_cell(const FiltArgs &G, uint8_t *T, int i, int j)
+f_intra_cell(const FiltArgs &G, uint8_t *T, int i, int j, const FPrep &P)
 {
     const FiltArgs &A = G;
-    const int nsbx = A.w / 4, nsby = A.h / 4;
     const int x = i * 4, y = j * 4;
-    if (y + 4 >= A.h || x + 4 >= A.w) return 0;
-    const int fy = j * A.nbv / nsby, fx = i * A.nbh / nsbx;
-    const int flags = A.blockdata[fx + fy * A.nbh];
-    if (flags & BD_RING) return 0;
+    const int flags = (P.bits >> 24) & 255;
     const int q = A.q;
     uint8_t *dxy = T + FT_ORG;
     const FiltArgs L = f_tile_view(A, T, x, y);
@@ -579,9 +628,11 @@ f_cell_active(const FiltArgs &A, int i, int j)
 #endif
 
 DSVCU_DEV void
-f_row(const FiltArgs &A, uint8_t *T, int row, volatile int *sprog, int lr)
+f_row(const FiltArgs &A0, uint8_t *T, int row, volatile int *sprog, int lr)
 {
+    FiltArgs A = A0;
     const int ncols = A.ncols;
+    A.cached = (lr >= 2);
 #ifndef DSVCU_EMU
     const int lane = FILT_LANE;
     /* where the progress of the row above lives, and who needs ours */
@@ -606,14 +657,30 @@ f_row(const FiltArgs &A, uint8_t *T, int row, volatile int *sprog, int lr)
     for (int base = 0; base < ncols; base += FILT_NLANES) {
 #ifndef DSVCU_EMU
         int cell = base + lane;
-        unsigned mask = __ballot_sync(0xffffffffu, cell < ncols && f_cell_active(A, cell, row));
+        FPrep mine;
+        bool act;
+        if (A.mode == FILT_MODE_CHROMA) {
+            mine = f_prep(A, 0, 0);
+            act = cell < ncols && f_cell_active(A, cell, row);
+        } else {
+            mine = f_prep(A, min(cell, ncols - 1), row);
+            act = cell < ncols && mine.active;
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, act);
 #else
-        unsigned mask = (base < ncols && f_cell_active(A, base, row)) ? 1u : 0u;
+        FPrep P = f_prep(A, min(base, ncols - 1), row);
+        unsigned mask = (base < ncols && (A.mode == FILT_MODE_CHROMA ? f_cell_active(A, base, row) : P.active)) ? 1u : 0u;
 #endif
         while (mask) {
 #ifndef DSVCU_EMU
-            int i = base + __ffs(mask) - 1;
+            const int src = __ffs(mask) - 1;
+            int i = base + src;
             int need = min(i + 2, ncols);
+            FPrep P;
+            P.mvxy = __shfl_sync(0xffffffffu, mine.mvxy, src);
+            P.bits = __shfl_sync(0xffffffffu, mine.bits, src);
+            P.nd = __shfl_sync(0xffffffffu, mine.nd, src);
+            P.active = 1;
             mask &= mask - 1;
             while (seen < need) {
                 seen = *above;
@@ -628,9 +695,9 @@ f_row(const FiltArgs &A, uint8_t *T, int row, volatile int *sprog, int lr)
             mask = 0;
 #endif
             if (A.mode == FILT_MODE_LUMA) {
-                f_luma_cell(A, T, i, row);
+                f_luma_cell(A, T, i, row, P);
             } else if (A.mode == FILT_MODE_INTRA) {
-                f_intra_cell(A, T, i, row);
+                f_intra_cell(A, T, i, row, P);
             } else {
                 f_chroma_cell(A, i, row);
             }
