@@ -35,6 +35,8 @@ import time
 # one CUDA stream per encoder/decoder instance: give them separate hardware queues
 # (must be set before the CUDA context is created; the library does the same)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# stdout carries exactly one JSON line: keep NCCL's version banner off it
+os.environ["NCCL_DEBUG"] = os.environ.get("NCCL_DEBUG_BENCH", "WARN")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -76,23 +78,58 @@ def synth_chunks(ndistinct):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clocks / throttle reasons of the GPUs in use while the timed region
+    runs, read through NVML (no nvidia-smi processes competing with the job)."""
 
-    def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], False
+    def __init__(self, indices, period=0.5):
+        self.indices, self.period = list(indices), period
+        self.sm, self.mx, self.reasons, self.stop = [], [], set(), False
         self.th = threading.Thread(target=self.run, daemon=True)
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+        except Exception:
+            self.nv = None
+
+    def sample(self):
+        nv = self.nv
+        if nv is None:
+            return self.sample_smi()
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        for h in self.handles:
+            self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            self.mx.append(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            for name, bit in bits.items():
+                if r & bit:
+                    self.reasons.add(name)
+
+    def sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        o = subprocess.run(["nvidia-smi", "-i", ",".join(map(str, self.indices)), "--query-gpu=" + q,
+                            "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in o.strip().splitlines():
+            t = [x.strip() for x in line.split(",")]
+            if len(t) >= 6 and t[0].isdigit():
+                self.sm.append(int(t[0]))
+                self.mx.append(int(t[1]))
+                for k, n in enumerate(names):
+                    if t[2 + k] == "Active":
+                        self.reasons.add(n)
 
     def run(self):
         while not self.stop:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([t.strip() for t in o.strip().split(",")])
+                self.sample()
             except Exception:
                 pass
-            time.sleep(0.25)
+            time.sleep(self.period)
 
     def __enter__(self):
         self.th.start()
@@ -103,12 +140,21 @@ class ClockSampler:
         self.th.join(timeout=6)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k] == "Active" for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(sm), "gpus_sampled": self.indices,
+                "source": "nvml" if self.nv is not None else "nvidia-smi"}
+
+
+class NoSampler:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        pass
+
+    def summary(self):
+        return None
 
 
 def cpu_count():
@@ -386,7 +432,8 @@ def run_own(args):
     for _ in range(args.warmup):
         enc_dev()
     l0 = lib.dsvcu_total_launches()
-    with ClockSampler(local) as clk:
+    # rank 0 samples the clocks of every GPU of the job (NVML, 2 Hz)
+    with (ClockSampler(range(world)) if rank == 0 else NoSampler()) as clk:
         dt = timed(enc_dev, args.steps)
     launches = lib.dsvcu_total_launches() - l0
     enc_host()

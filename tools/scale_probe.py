@@ -22,10 +22,16 @@ for threads in [int(t) for t in sys.argv[1].split(",")]:
     o = P.enc_opts(bench.W, bench.H, P.SUBSAMP_420, (30, 1), qp=60, gop=48, noeos=1)
     out, outn = C.c_void_p(), C.c_size_t()
     libc = C.CDLL(None); libc.free.argtypes = [C.c_void_p]
+    import resource
     for rep in range(3):
+        ru0 = resource.getrusage(resource.RUSAGE_SELF)
         t0 = time.perf_counter()
         lib.dsv_pool_encode(pool, C.byref(o), C.c_void_p(dev.data_ptr()), nfr, GOPN, C.byref(out), C.byref(outn))
         dt = time.perf_counter() - t0
         libc.free(out)
-    print("threads %2d: %6.1f fps  (%.1f ms/frame/stream)" % (threads, nfr / dt, 1000 * dt / GOPN), flush=True)
+    ru1 = resource.getrusage(resource.RUSAGE_SELF)
+    cpu = (ru1.ru_utime - ru0.ru_utime) + (ru1.ru_stime - ru0.ru_stime)
+    print("threads %2d: %6.1f fps  (%.1f ms/frame/stream)  host CPU %.2f ms/frame (user %.2f sys %.2f), %.1f cores busy" % (
+        threads, nfr / dt, 1000 * dt / GOPN, 1000 * cpu / nfr, 1000 * (ru1.ru_utime - ru0.ru_utime) / nfr,
+        1000 * (ru1.ru_stime - ru0.ru_stime) / nfr, cpu / dt), flush=True)
     lib.dsv_pool_destroy(pool)
