@@ -35,8 +35,16 @@ import time
 # one CUDA stream per encoder/decoder instance: give them separate hardware queues
 # (must be set before the CUDA context is created; the library does the same)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-# stdout carries exactly one JSON line: keep NCCL's version banner off it
-os.environ["NCCL_DEBUG"] = os.environ.get("NCCL_DEBUG_BENCH", "WARN")
+# stdout carries exactly one JSON line: everything any library prints on fd 1
+# (NCCL's version banner, for one) is sent to stderr; emit() writes the line to
+# the real stdout
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -193,7 +201,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     if not os.path.exists(REF_BIN):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/dsv2 not built (needs /root/reference)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/dsv2 not built (needs /root/reference)"})
         return 0
     cores = cpu_count()
     per = 6  # frames per process and step: a bounded sample of a 48-frame chunk
@@ -221,7 +229,7 @@ def run_reference(args):
         "e2e": {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -516,7 +524,7 @@ def run_own(args):
         line["kernels"] = kern
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
