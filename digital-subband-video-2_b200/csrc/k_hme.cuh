@@ -28,6 +28,9 @@
 #include "k_quant.cuh"
 
 #define ME_WARPS_PER_CTA 4
+#ifndef ME_POLL_NS
+#define ME_POLL_NS 256 /* back-off between polls of the row above (a block takes ~30 us) */
+#endif
 #define ME_BORDER 32
 #define ME_MAXLVL 5
 #define SP_SZ 16
@@ -1894,7 +1897,7 @@ k_me_level(MeArgs A)
             if (seen < need) {
 #ifndef DSVCU_EMU
                 while ((seen = *(volatile const int *) (A.progress + row - 1)) < need) {
-                    __nanosleep(64); /* leave the issue slots to warps that have work */
+                    __nanosleep(ME_POLL_NS); /* leave the issue slots to warps that have work */
                 }
                 __threadfence();
 #else

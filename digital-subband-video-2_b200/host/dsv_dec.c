@@ -455,3 +455,37 @@ dsv_dec(DSV_DECODER *d, DSV_BUF *buffer, DSV_FRAME **out, DSV_FNUM *fn)
     dsv_buf_free(buffer);
     return ret;
 }
+
+/* dsv_post_process (reference bmc.c:340-361, called by the CLI for -postsharp):
+ * decoder-side sharpening of a HOST luma plane.  The plane makes a round trip
+ * through the device; the context is kept per thread and per plane size. */
+void
+dsv_post_process(DSV_PLANE *dp)
+{
+    static __thread dsvcu_ctx *ctx = NULL;
+    static __thread dsvcu_frame *fr = NULL;
+    static __thread int cw = 0, ch = 0;
+    if (!dp || !dp->data) {
+        return;
+    }
+    if (ctx && (cw != dp->w || ch != dp->h)) {
+        dsvcu_frame_destroy(ctx, fr);
+        dsvcu_ctx_destroy(ctx);
+        ctx = NULL;
+        fr = NULL;
+    }
+    if (!ctx) {
+        if (dsvcu_ctx_create(&ctx, dsv_get_thread_device(), dp->w, dp->h, DSV_SUBSAMP_420) ||
+            dsvcu_frame_create_luma(ctx, &fr, dp->w, dp->h)) {
+            DSV_ERROR(("dsv_post_process: %s", dsvcu_last_error()));
+            ctx = NULL;
+            return;
+        }
+        cw = dp->w;
+        ch = dp->h;
+    }
+    if (dsvcu_frame_upload(ctx, fr, 0, dp->data, dp->stride) || dsvcu_post_process(ctx, fr) ||
+        dsvcu_frame_download(ctx, fr, 0, dp->data, dp->stride) || dsvcu_sync(ctx)) {
+        DSV_ERROR(("dsv_post_process: %s", dsvcu_last_error()));
+    }
+}

@@ -48,6 +48,9 @@ typedef struct {
 extern int dsv_dec(DSV_DECODER *d, DSV_BUF *buf, DSV_FRAME **out, DSV_FNUM *fn);
 extern DSV_META *dsv_get_metadata(DSV_DECODER *d);
 extern void dsv_dec_free(DSV_DECODER *d);
+/* decoder-side luma sharpening of a host plane (reference dsv_internal.h:147,
+ * bmc.c:340-361; what the CLI's -postsharp calls) */
+extern void dsv_post_process(DSV_PLANE *dp);
 
 #ifdef __cplusplus
 }

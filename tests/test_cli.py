@@ -47,3 +47,28 @@ def test_cli_chunk_semantics_match_parallel_encode_script():
                     "-threads=3"], check=False)
     got = open(one, "rb").read()
     assert got == cat[:len(got)] and len(cat) - len(got) in (0, 14)
+
+
+@pytest.mark.gpu
+def test_reference_cli_sources_link_against_the_library(tmp_path):
+    """INTEGRATION.md route 1: the reference's own dsv_main.c + util.c, compiled
+    against include/ and linked with libdsv2cuda.so (oracle/Makefile target
+    _ref/dsv2_dropin, built where /root/reference exists), is a working `dsv2`
+    whose output equals the reference build's."""
+    exe = os.path.join(util.REF_DIR, "dsv2_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/dsv2_dropin not built")
+    y4m = util.clip("cli3", 352, 288, 6, "420")
+    ref_dsv = util.ref_encode(y4m, ["-qp=70", "-gop=3"], "cli3")
+    out = str(tmp_path / "o.dsv")
+    r = subprocess.run([exe, "e", "-y", "-inp=" + y4m, "-out=" + out, "-y4m=1", "-qp=70", "-gop=3"],
+                       stdout=subprocess.DEVNULL)
+    assert r.returncode in (0, 254)
+    assert open(out, "rb").read() == open(ref_dsv, "rb").read()
+    dec = str(tmp_path / "o.y4m")
+    subprocess.run([exe, "d", "-y", "-inp=" + out, "-out=" + dec, "-y4m=1", "-postsharp=1"], check=True,
+                   stdout=subprocess.DEVNULL)
+    refdec = str(tmp_path / "r.y4m")
+    subprocess.run([util.REF_BIN, "d", "-y", "-inp=" + ref_dsv, "-out=" + refdec, "-y4m=1", "-postsharp=1"], check=True,
+                   stdout=subprocess.DEVNULL)
+    assert open(dec, "rb").read() == open(refdec, "rb").read()
