@@ -1336,12 +1336,8 @@ dsvcu_hme(dsvcu_ctx *c, const dsvcu_fmeta *fm, const dsvcu_hme_params *hp, dsvcu
             DSVCU_LAUNCH(k_me_prepass, pctas, ME_WARPS_PER_CTA * 32, 0, c->stream, A);
             CK_LAUNCH(c);
         }
-#ifdef DSVCU_EMU
-        ctas = 1;
-#else
+        /* one warp per block row; CTA k only waits for CTA k-1, dispatched first */
         ctas = (rows + ME_WARPS_PER_CTA - 1) / ME_WARPS_PER_CTA;
-        if (ctas > 148 * 4) ctas = 148 * 4;
-#endif
         DSVCU_LAUNCH(k_me_level, ctas, ME_WARPS_PER_CTA * 32, 0, c->stream, A);
         CK_LAUNCH(c);
         if (lvl != 0) {

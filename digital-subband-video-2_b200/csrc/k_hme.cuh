@@ -27,7 +27,7 @@
 #include "dsvcu_rt.h"
 #include "k_quant.cuh"
 
-#define ME_WARPS_PER_CTA 4
+#define ME_WARPS_PER_CTA 8
 #ifndef ME_POLL_NS
 #define ME_POLL_NS 256 /* back-off between polls of the row above (a block takes ~30 us) */
 #endif
@@ -1880,38 +1880,69 @@ k_me_prepass(MeArgs A)
     }
 }
 
-/* wavefront over block rows of one pyramid level */
+/* Wavefront over the block rows of one pyramid level: one warp per row, a CTA
+ * owns ME_WARPS_PER_CTA consecutive rows.  Row r may start block c once row r-1
+ * has finished block c (left / top / top-left dependencies).
+ * Hand-offs inside a CTA go through shared-memory progress words and
+ * block-scope fences; the last row of a CTA also publishes through global memory
+ * (device-scope fence) for the first row of the next CTA.  The vector field
+ * itself is read with volatile loads (me_ldmv), i.e. from L2. */
 DSVCU_KERNEL void __launch_bounds__(ME_WARPS_PER_CTA * 32)
 k_me_level(MeArgs A)
 {
     DSVCU_SHARED MeScratch scratch[ME_WARPS_PER_CTA];
-    MeScratch *S = &scratch[ME_WIC];
+    DSVCU_SHARED int sprog[ME_WARPS_PER_CTA];
     const int step = 1 << A.level;
     int acc_local[4] = { 0, 0, 0, 0 };
-    for (int row = ME_WARP; row < A.nrows; row += ME_NWARPS) {
-        int j = row * step;
+#ifndef DSVCU_EMU
+    const int lr = ME_WIC;
+    const int row = (int) blockIdx.x * ME_WARPS_PER_CTA + lr;
+    MeScratch *S = &scratch[lr];
+    if (threadIdx.x < ME_WARPS_PER_CTA) sprog[threadIdx.x] = 0;
+    __syncthreads();
+    if (row < A.nrows) {
+        const bool above_global = (lr == 0), pub_global = (lr == ME_WARPS_PER_CTA - 1);
+        volatile const int *above = above_global ? (volatile const int *) (A.progress + row - 1)
+                                                 : (volatile const int *) (sprog + lr - 1);
+        const int j = row * step;
         int seen = (row == 0) ? 0x7fffffff : 0;
         int col = 0;
         for (int i = 0; i < A.nxb; i += step, col++) {
-            int need = col + 1;
+            const int need = col + 1;
             if (seen < need) {
-#ifndef DSVCU_EMU
-                while ((seen = *(volatile const int *) (A.progress + row - 1)) < need) {
-                    __nanosleep(ME_POLL_NS); /* leave the issue slots to warps that have work */
+                while ((seen = *above) < need) {
+                    if (above_global) __nanosleep(ME_POLL_NS); /* leave the issue slots to warps that have work */
                 }
-                __threadfence();
-#else
-                seen = 0x7fffffff;
-#endif
+                if (above_global) {
+                    __threadfence();
+                } else {
+                    __threadfence_block();
+                }
             }
             me_block(A, S, i, j, acc_local);
-#ifndef DSVCU_EMU
-            __threadfence();
+            if (pub_global) {
+                __threadfence();
+            } else {
+                __threadfence_block();
+            }
             __syncwarp();
-            if (ME_LANE == 0) *(volatile int *) (A.progress + row) = col + 1;
-#endif
+            if (ME_LANE == 0) {
+                *(volatile int *) (sprog + lr) = col + 1;
+                if (pub_global) *(volatile int *) (A.progress + row) = col + 1;
+            }
         }
     }
+#else
+    MeScratch *S = &scratch[0];
+    (void) sprog;
+    for (int lr = 0; lr < ME_WARPS_PER_CTA; lr++) {
+        int row = (int) blockIdx.x * ME_WARPS_PER_CTA + lr;
+        if (row >= A.nrows) continue;
+        for (int i = 0; i < A.nxb; i += step) {
+            me_block(A, S, i, row * step, acc_local);
+        }
+    }
+#endif
     if (ME_LANE == 0 && A.level == 0) {
         for (int k = 0; k < 4; k++) {
             if (acc_local[k]) atomicAdd(&A.acc[k], acc_local[k]);
