@@ -1324,6 +1324,7 @@ dsvcu_hme(dsvcu_ctx *c, const dsvcu_fmeta *fm, const dsvcu_hme_params *hp, dsvcu
         CK(dsvcu_memset_async(c->d_progress, 0, (size_t) rows * sizeof(int), c->stream));
         CK(dsvcu_memset_async(c->d_mvf[lvl], 0, (size_t) nblk * sizeof(dsvcu_mv), c->stream));
         A.pre = c->d_pre;
+        A.b2sr = (256 * (hp->quant * hp->quant >> 12) * fm->blk_w * fm->blk_h) / (c->width * c->height);
         {
             /* everything a block needs that does not depend on its same-level
              * neighbours, for all blocks at once */

@@ -56,6 +56,7 @@ struct MeArgs {
     int *acc;       /* [0] nintra [1] ndiff [2] eligible [3] total_err */
     int *progress;
     int nrows;
+    int b2sr;          /* (256 * (q*q >> 12) * blk_w * blk_h) / (width * height), dsv.c:370 */
     struct MePre *pre; /* per-block results of k_me_prepass for this level */
 };
 
@@ -333,7 +334,7 @@ me_mv_cost(const MeArgs &A, const MePred &pr, int mx, int my, int level)
     int px = pr.x, py = pr.y, bits, b2sr, q = A.quant;
     int sqr = level > 1;
     bits = me_seg_len(mx - px) + me_seg_len(my - py);
-    b2sr = (256 * (q * q >> 12) * A.y_w * A.y_h) / (A.vid_w * A.vid_h);
+    b2sr = A.b2sr;
     bits += bits * b2sr >> 7;
     if (sqr) bits *= bits;
     bits = min(bits, 1 << 19);
@@ -863,6 +864,8 @@ struct MeScratch {
     /* full-pel metric memo of the current block: position -> raw metric */
     short memo_x[ME_MEMO], memo_y[ME_MEMO];
     unsigned memo_v[ME_MEMO];
+    /* the block's prepass record, fetched from global memory in one batch */
+    uint32_t pre_words[160];
 };
 
 /* Sub-pel refinement, split in two.  me_subpel_measure: everything that depends
@@ -1135,6 +1138,8 @@ me_test_intra_c(const MeArgs &A, MeMv *mv, unsigned mad, unsigned detail_src, un
     }
     if (mv->submask) mv->flags |= MVF_INTRA;
 }
+
+static_assert(sizeof(MePre) % 4 == 0 && sizeof(MePre) <= 160 * 4, "MePre must fit MeScratch::pre_words");
 
 /* Full-pel metric memo.  The candidate scan and the descent probe overlapping
  * positions, and k_me_prepass has already measured the neighbour-independent
@@ -1486,7 +1491,14 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
     bh = min(sp.h - by, A.y_h);
     MePred pred;
     int mn = 0; /* entries in the block's metric memo */
-    const MePre *P = A.pre + i + j * nxb;
+    /* one coalesced batch of loads (a single L2 round trip) instead of a miss
+     * per touched line of the record */
+    {
+        const uint32_t *g = (const uint32_t *) (A.pre + i + j * nxb);
+        for (int k = ME_LANE; k < (int) (sizeof(MePre) / 4); k += ME_NL) S->pre_words[k] = g[k];
+        DSVCU_SYNCWARP();
+    }
+    const MePre *P = (const MePre *) S->pre_words;
     me_movec_pred(A.mvf, nxb, i, j, &pred.x, &pred.y);
     /* neighbour-independent results of k_me_prepass: statistics, metric weights,
      * the non-spatial candidates and their metrics (memo seed) */
