@@ -42,6 +42,8 @@ CASES = [
     ("ll420", 352, 288, 3, "420", 30, ["-qp=100"], dict(qp=100), {}),
     ("c422", 352, 288, 6, "422", 30, ["-qp=60"], dict(qp=60), {}),
     ("c422q", 176, 144, 5, "422", 30, ["-qp=30", "-gop=2"], dict(qp=30, gop=2), {}),
+    ("c411", 352, 288, 5, "411", 30, ["-qp=60"], dict(qp=60), {}),
+    ("c410", 352, 288, 5, "410", 30, ["-qp=60"], dict(qp=60), {}),
 ]
 BIG = [
     ("fhd_b32", 1920, 1080, 3, "420", 30, ["-qp=50", "-bszx=1", "-bszy=1"], dict(qp=50, bszx=1, bszy=1), {}),
@@ -52,7 +54,7 @@ BIG = [
     # earlier calls -- its own encoder and decoder disagree on such input.
     ("wide_32x16", 1536, 384, 3, "420", 30, ["-qp=60"], dict(qp=60), {}),
 ]
-FMT = {"420": 0x5, "444": 0x0, "422": 0x4}
+FMT = {"420": 0x5, "444": 0x0, "422": 0x4, "411": 0x8, "410": 0xA}
 
 
 def _run(case, emu):

@@ -93,6 +93,10 @@ def read_y4m(path):
         cw, ch = w, h
     elif c.startswith("422"):
         cw, ch = (w + 1) // 2, h
+    elif c.startswith("411"):
+        cw, ch = (w + 3) // 4, h
+    elif c.startswith("410"):
+        cw, ch = (w + 3) // 4, (h + 3) // 4
     else:
         cw, ch = (w + 1) // 2, (h + 1) // 2
     fsz = w * h + 2 * cw * ch

@@ -59,6 +59,10 @@ def frames(w, h, nfr, fmt="420", seed=1234, noise=24.0, sensor=3, cut=40):
         elif fmt == "422":
             U = (U[:, 0::2] + U[:, 1::2]) / 2.0
             V = (V[:, 0::2] + V[:, 1::2]) / 2.0
+        elif fmt in ("411", "410"):
+            cw_, ch_ = (w + 3) // 4, (h if fmt == "411" else (h + 3) // 4)
+            U = U[::(1 if fmt == "411" else 4), ::4][:ch_, :cw_]
+            V = V[::(1 if fmt == "411" else 4), ::4][:ch_, :cw_]
         U8 = np.clip(np.rint(U), 0, 255).astype(np.uint8)
         V8 = np.clip(np.rint(V), 0, 255).astype(np.uint8)
         yield Y8, U8, V8
@@ -80,7 +84,7 @@ def main(argv=None):
     ap.add_argument("-W", type=int, default=352)
     ap.add_argument("-H", type=int, default=288)
     ap.add_argument("-n", type=int, default=60)
-    ap.add_argument("--fmt", default="420", choices=["420", "422", "444"])
+    ap.add_argument("--fmt", default="420", choices=["420", "422", "444", "411", "410"])
     ap.add_argument("--fps", type=int, default=30)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--noise", type=float, default=24.0)
