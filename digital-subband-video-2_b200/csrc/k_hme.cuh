@@ -1733,7 +1733,6 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
         DSVCU_SYNCWARP();
         {
             const uint8_t *refd = rp.data + (by + fpely) * rp.stride + bx + fpelx;
-            const uint8_t *ogrd = A.ogr.data + (by + fpely) * A.ogr.stride + bx + fpelx;
             unsigned var_ref, avg_ref, mad, ogrerr, ogrmad, avg_y_dif, avg_c_dif;
             int uavg_src, vavg_src, uavg_ref, vavg_ref, cbx, cby, cbw, cbh, cbmx, cbmy;
             int eprmi, eprmd, eprmr, neidif, oob, ipolvar, dv, skipped = 0;
@@ -1768,7 +1767,6 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
                 eprmd = (rs.eprm >> 1) & 1;
                 eprmr = (rs.eprm >> 2) & 1;
             }
-            (void) ogrd;
             ogrmad = (ogrerr + yarea / 2) / yarea;
             ogrmad = ogrmad * ratio >> 5;
             mad = (best + yarea / 2) / yarea;

@@ -294,11 +294,17 @@ k_compact_scan(int *chunk_count, int nchunks, int *out_n)
     }
 }
 
-/* pass 3: ordered scatter; each thread owns a contiguous run of its chunk */
+/* pass 3: ordered scatter.  Each thread owns a contiguous run of its chunk and
+ * writes its non-zeros into a shared-memory image of the chunk's output, which
+ * the CTA then copies out with consecutive threads writing consecutive
+ * symbols: the destination is pinned HOST memory, where scattered 8-byte
+ * stores would each become their own PCIe write. */
 DSVCU_KERNEL void __launch_bounds__(CMP_THREADS)
 k_compact_scatter(const int32_t *qv, int n, const int *chunk_off, dsvcu_sym *out)
 {
     DSVCU_SHARED int part[CMP_THREADS];
+    DSVCU_SHARED dsvcu_sym stage[CMP_CHUNK];
+    DSVCU_SHARED int total;
     int base = (int) blockIdx.x * CMP_CHUNK;
     int per = CMP_CHUNK / DSVCU_NTH;
     int b = base + DSVCU_TID * per, e = min(n, b + per);
@@ -307,22 +313,29 @@ k_compact_scatter(const int32_t *qv, int n, const int *chunk_off, dsvcu_sym *out
     part[DSVCU_TID] = c;
     DSVCU_SYNC();
     if (DSVCU_TID == 0) {
-        int acc = chunk_off[blockIdx.x];
+        int acc = 0;
         for (int i = 0; i < DSVCU_NTH; i++) {
             int v = part[i];
             part[i] = acc;
             acc += v;
         }
+        total = acc;
     }
     DSVCU_SYNC();
     int o = part[DSVCU_TID];
     for (int i = b; i < e; i++) {
         int v = qv[i];
         if (v) {
-            out[o].pos = (uint32_t) i;
-            out[o].v = v;
+            stage[o].pos = (uint32_t) i;
+            stage[o].v = v;
             o++;
         }
+    }
+    DSVCU_SYNC();
+    {
+        dsvcu_sym *dst = out + chunk_off[blockIdx.x];
+        const int cnt = total;
+        for (int k = DSVCU_TID; k < cnt; k += DSVCU_NTH) dst[k] = stage[k];
     }
 }
 
