@@ -14,7 +14,8 @@ NVCC    ?= nvcc
 CC      ?= gcc
 CXX     ?= g++
 ARCH    := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=default
+EXTRA   ?=
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=default $(EXTRA)
 CFLAGS  := -O2 -fPIC -Wall -Wextra -Wno-unused-parameter -Iinclude
 HOSTSRC := $(HOST)/dsv_core.c $(HOST)/dsv_bits.c $(HOST)/dsv_hzcc.c $(HOST)/dsv_mvutil.c \
            $(HOST)/dsv_dec.c $(wildcard $(HOST)/dsv_enc.c) $(wildcard $(HOST)/dsv_ops.c) \

@@ -41,6 +41,8 @@ dsvcu_more_connections(void)
 #endif
 
 static char g_err[256] = "";
+static int g_pre_cap = getenv("DSVCU_PRE_GRID") ? atoi(getenv("DSVCU_PRE_GRID")) : 0; /* experiments: cap the prepass grid */
+static int g_me_smem = getenv("DSVCU_ME_SMEM") ? atoi(getenv("DSVCU_ME_SMEM")) : 0; /* experiments: pad the search kernel's shared memory to limit co-residency */
 static long long g_launches = 0; /* kernels launched by every context of this process */
 
 static int
@@ -113,6 +115,11 @@ struct dsvcu_ctx {
     int sym_cap[3];
     int *d_progress;
     int progress_cap;
+    int me_smem_set;
+    int filt_big_smem; /* opted in to > 48 KB dynamic shared memory on this device */
+#ifndef DSVCU_EMU
+    cudaEvent_t marks[DSVCU_MARKS];
+#endif
     /* motion estimation */
     dsvcu_mv *d_mvf[ME_MAXLVL + 1]; /* [0] aliases d_mvs */
     dsvcu_mv *d_prev_mvf;
@@ -391,6 +398,50 @@ dsvcu_timer_stop_ms(dsvcu_ctx *c, float *ms)
 #else
     (void) c;
     *ms = 0.f;
+#endif
+    return 0;
+}
+
+#if defined(ME_TIMING) && !defined(DSVCU_EMU)
+extern "C" int
+dsvcu_debug_me_counters(unsigned long long out[4], int reset)
+{
+    static const unsigned long long z[4] = { 0, 0, 0, 0 };
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_me_dbg, sizeof(z));
+    if (reset) cudaMemcpyToSymbol(g_me_dbg, z, sizeof(z));
+    return 0;
+}
+#endif
+
+/* Device-side phase stamps for the encoder's profiler (DSV_PROFILE=2): record
+ * mark k on the stream; read the time between two marks once both completed. */
+extern "C" int
+dsvcu_mark(dsvcu_ctx *c, int k)
+{
+#ifndef DSVCU_EMU
+    if (k < 0 || k >= DSVCU_MARKS) return -1;
+    if (!c->marks[k]) CK(cudaEventCreate(&c->marks[k]));
+    CK(cudaEventRecord(c->marks[k], c->stream));
+#else
+    (void) c;
+    (void) k;
+#endif
+    return 0;
+}
+
+extern "C" int
+dsvcu_mark_elapsed_ms(dsvcu_ctx *c, int a, int b, float *ms)
+{
+    *ms = 0.f;
+#ifndef DSVCU_EMU
+    if (a < 0 || b < 0 || a >= DSVCU_MARKS || b >= DSVCU_MARKS || !c->marks[a] || !c->marks[b]) return -1;
+    CK(cudaEventSynchronize(c->marks[b]));
+    CK(cudaEventElapsedTime(ms, c->marks[a], c->marks[b]));
+#else
+    (void) c;
+    (void) a;
+    (void) b;
 #endif
     return 0;
 }
@@ -1012,66 +1063,94 @@ filter_q(const dsvcu_fmeta *fm, int q) /* compute_filter_q, bmc.c:376-388 */
     return q;
 }
 
+/* k_filter.cuh, skewed lockstep: FILT_CELLS cell rows per CTA, the planes of the
+ * job back to back in one grid */
 static int
-run_wavefront(dsvcu_ctx *c, FiltArgs *F)
+run_filter_job(dsvcu_ctx *c, FiltJob *J, int nplanes)
 {
-    int ctas;
-    if (F->nrows <= 0 || F->ncols <= 0) return 0;
-    if (F->nrows > c->progress_cap) {
+    int i, ctas = 0, bands = 0, smem = 0;
+    for (i = 0; i < nplanes; i++) {
+        FiltArgs *F = &J->p[i];
+        int b = filt_smem_bytes(*F);
+        if (F->nrows <= 0 || F->ncols <= 0) F->nrows = 0;
+        if (b > smem) smem = b;
+        F->first_cta = ctas;
+        ctas += filt_ctas(*F);
+        bands += (F->nrows + FILT_G - 1) / FILT_G;
+    }
+    J->nplanes = nplanes;
+    if (!ctas) return 0;
+    if (smem > 200 * 1024) {
+        snprintf(g_err, sizeof(g_err), "picture too wide for the filter schedule");
+        return -1;
+    }
+    if (bands > c->progress_cap) {
         dsvcu_free_dev(c->d_progress);
-        c->progress_cap = F->nrows + 64;
+        c->progress_cap = bands + 64;
         CK(dsvcu_malloc(&c->d_progress, (size_t) c->progress_cap * sizeof(int)));
     }
-    CK(dsvcu_memset_async(c->d_progress, 0, (size_t) F->nrows * sizeof(int), c->stream));
-    F->progress = c->d_progress;
-    /* one CTA per FILT_WARPS_PER_CTA rows; CTA k only ever waits for CTA k-1,
-     * which the hardware dispatches first */
-    ctas = (F->nrows + FILT_WARPS_PER_CTA - 1) / FILT_WARPS_PER_CTA;
-    DSVCU_LAUNCH(k_filter_wavefront, ctas, FILT_WARPS_PER_CTA * 32, 0, c->stream, *F);
+    CK(dsvcu_memset_async(c->d_progress, 0, (size_t) bands * sizeof(int), c->stream));
+    bands = 0;
+    for (i = 0; i < nplanes; i++) {
+        J->p[i].progress = c->d_progress + bands;
+        bands += (J->p[i].nrows + FILT_G - 1) / FILT_G;
+    }
+#ifndef DSVCU_EMU
+    if (smem > 48 * 1024 && !c->filt_big_smem) {
+        CK(cudaFuncSetAttribute(k_filter_skew, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        c->filt_big_smem = 1;
+    }
+#endif
+    DSVCU_LAUNCH(k_filter_skew, ctas, FILT_THREADS, smem, c->stream, *J);
     CK_LAUNCH(c);
     return 0;
+}
+
+static void
+filt_common(FiltArgs *F, dsvcu_ctx *c, const dsvcu_fmeta *fm)
+{
+    memset(F, 0, sizeof(*F));
+    F->mvs = c->d_mvs;
+    F->blockdata = c->d_blockdata;
+    F->nbh = fm->nblocks_h;
+    F->nbv = fm->nblocks_v;
+    F->blk_w = fm->blk_w;
+    F->blk_h = fm->blk_h;
 }
 
 static int
 loop_filters(dsvcu_ctx *c, const dsvcu_fmeta *fm, int q, dsvcu_frame *f, int do_filter)
 {
-    /* luma_filter + chroma_filter, bmc.c:459-659 */
-    FiltArgs F;
+    /* luma_filter + chroma_filter, bmc.c:459-659: the three planes are
+     * independent and run as three CTAs of one launch */
+    FiltJob J;
     int i;
     if (fm->lossless) return 0;
-    memset(&F, 0, sizeof(F));
-    F.mvs = c->d_mvs;
-    F.blockdata = c->d_blockdata;
-    F.nbh = fm->nblocks_h;
-    F.nbv = fm->nblocks_v;
-    F.blk_w = fm->blk_w;
-    F.blk_h = fm->blk_h;
-    F.data = f->p[0].data;
-    F.stride = f->p[0].stride;
-    F.w = f->p[0].w;
-    F.h = f->p[0].h;
-    F.q = filter_q(fm, q);
-    F.fthresh = 32 * (14 - ilb2((unsigned) F.q));
-    F.do_filter = do_filter;
-    F.sharpen = fm->inter_sharpen ? fm->temporal_mc : 0;
-    F.ncols = F.w / 4;
-    F.nrows = F.h / 4;
-    F.mode = FILT_MODE_LUMA;
-    if (run_wavefront(c, &F)) return -1;
-    for (i = 1; i < 3; i++) {
-        F.data = f->p[i].data;
-        F.stride = f->p[i].stride;
-        F.w = f->p[i].w;
-        F.h = f->p[i].h;
-        F.q = q;
-        F.bw = fm->blk_w >> FMT_HSHIFT(c->subsamp);
-        F.bh = fm->blk_h >> FMT_VSHIFT(c->subsamp);
-        F.ncols = fm->nblocks_h;
-        F.nrows = fm->nblocks_v;
-        F.mode = FILT_MODE_CHROMA;
-        if (run_wavefront(c, &F)) return -1;
+    for (i = 0; i < 3; i++) {
+        FiltArgs *F = &J.p[i];
+        filt_common(F, c, fm);
+        F->data = f->p[i].data;
+        F->stride = f->p[i].stride;
+        F->w = f->p[i].w;
+        F->h = f->p[i].h;
+        F->do_filter = do_filter;
+        if (i == 0) {
+            F->q = filter_q(fm, q);
+            F->fthresh = 32 * (14 - ilb2((unsigned) F->q));
+            F->sharpen = fm->inter_sharpen ? fm->temporal_mc : 0;
+            F->ncols = F->w / 4;
+            F->nrows = F->h / 4;
+            F->mode = FILT_MODE_LUMA;
+        } else {
+            F->q = q;
+            F->bw = fm->blk_w >> FMT_HSHIFT(c->subsamp);
+            F->bh = fm->blk_h >> FMT_VSHIFT(c->subsamp);
+            F->ncols = fm->nblocks_h;
+            F->nrows = fm->nblocks_v;
+            F->mode = FILT_MODE_CHROMA;
+        }
     }
-    return 0;
+    return run_filter_job(c, &J, 3);
 }
 
 extern "C" int
@@ -1108,26 +1187,22 @@ dsvcu_add_res(dsvcu_ctx *c, const dsvcu_fmeta *fm, int q, dsvcu_frame *resd, dsv
 extern "C" int
 dsvcu_intra_filter(dsvcu_ctx *c, int q, const dsvcu_fmeta *fm, int plane, dsvcu_frame *f, int do_filter)
 {
-    FiltArgs F;
+    FiltJob J;
+    FiltArgs *F = &J.p[0];
     if (fm->lossless || plane != 0 || !do_filter) return 0;
-    memset(&F, 0, sizeof(F));
-    F.mvs = c->d_mvs;
-    F.blockdata = c->d_blockdata;
-    F.nbh = fm->nblocks_h;
-    F.nbv = fm->nblocks_v;
-    F.blk_w = fm->blk_w;
-    F.blk_h = fm->blk_h;
-    F.data = f->p[0].data;
-    F.stride = f->p[0].stride;
-    F.w = f->p[0].w;
-    F.h = f->p[0].h;
-    F.q = filter_q(fm, q);
-    F.fthresh = 32 * (14 - ilb2((unsigned) F.q));
-    F.do_filter = 1;
-    F.ncols = F.w / 4;
-    F.nrows = F.h / 4;
-    F.mode = FILT_MODE_INTRA;
-    return run_wavefront(c, &F);
+    memset(&J, 0, sizeof(J));
+    filt_common(F, c, fm);
+    F->data = f->p[0].data;
+    F->stride = f->p[0].stride;
+    F->w = f->p[0].w;
+    F->h = f->p[0].h;
+    F->q = filter_q(fm, q);
+    F->fthresh = 32 * (14 - ilb2((unsigned) F->q));
+    F->do_filter = 1;
+    F->ncols = F->w / 4;
+    F->nrows = F->h / 4;
+    F->mode = FILT_MODE_INTRA;
+    return run_filter_job(c, &J, 1);
 }
 
 extern "C" int
@@ -1334,12 +1409,19 @@ dsvcu_hme(dsvcu_ctx *c, const dsvcu_fmeta *fm, const dsvcu_hme_params *hp, dsvcu
             pctas = 1;
 #endif
             if (pctas > 148 * 8) pctas = 148 * 8;
+            if (g_pre_cap > 0 && pctas > g_pre_cap) pctas = g_pre_cap;
             DSVCU_LAUNCH(k_me_prepass, pctas, ME_WARPS_PER_CTA * 32, 0, c->stream, A);
             CK_LAUNCH(c);
         }
         /* one warp per block row; CTA k only waits for CTA k-1, dispatched first */
         ctas = (rows + ME_WARPS_PER_CTA - 1) / ME_WARPS_PER_CTA;
-        DSVCU_LAUNCH(k_me_level, ctas, ME_WARPS_PER_CTA * 32, 0, c->stream, A);
+#ifndef DSVCU_EMU
+        if (g_me_smem > 0 && !c->me_smem_set) {
+            CK(cudaFuncSetAttribute(k_me_level, cudaFuncAttributeMaxDynamicSharedMemorySize, g_me_smem));
+            c->me_smem_set = 1;
+        }
+#endif
+        DSVCU_LAUNCH(k_me_level, ctas, ME_WARPS_PER_CTA * 32, g_me_smem, c->stream, A);
         CK_LAUNCH(c);
         if (lvl != 0) {
             DSVCU_LAUNCH(k_me_global, 1, 256, 0, c->stream, c->d_mvf[lvl], fm->nblocks_h, fm->nblocks_v, lvl, c->d_me);

@@ -8,13 +8,21 @@
  * (:390-457), luma_filter (:459-602), chroma_filter (:604-659).
  *
  * The reference filters 4x4 cells in place in raster order; cell (p,q) reads
- * pixels already modified by (p-1,q) and (p+1,q-1).  The
- * GPU schedule is a wavefront with slope 2: one warp owns one row of cells and
- * walks it left to right; before touching cell p of row q it waits until row
- * q-1 has published progress >= p+2.  Lanes split the four pixel lines of a
- * cell.  Progress counters live in global memory and are published with a
- * release fence; pixels are read with volatile loads so every read observes
- * what other SMs have published.
+ * pixels already modified by (p-1,q) and (p+1,q-1), so the
+ * legal parallel schedule is a wavefront with slope 2: cell p of row q may run
+ * once row q-1 has completed cell p+1.
+ *
+ * Schedule ("skewed lockstep"): a group of FILT_LPC lanes owns one row of
+ * cells; a warp therefore owns a band of FILT_G = 32 / FILT_LPC consecutive
+ * rows, and at warp-step t group g works on column t - 2g.  Inside a band the
+ * slope-2 dependency is satisfied by construction -- the warp executes in
+ * lockstep, one __syncwarp per step, no flags, no polling.  Band b trails band
+ * b-1 by 2*FILT_G steps; that single hand-off per step goes through a step
+ * counter: in shared memory between the FILT_WPC bands of one CTA, in global
+ * memory (with device-scope fences, and L2 loads for the two cell rows that
+ * read what the neighbouring SM wrote) between CTAs.  CTAs are small (128
+ * threads) so they fit beside whatever else is resident; the three planes of a
+ * picture are filtered by one launch.
  */
 #ifndef K_FILTER_CUH
 #define K_FILTER_CUH
@@ -25,7 +33,16 @@
 #define FILT_MODE_LUMA 0
 #define FILT_MODE_INTRA 1
 #define FILT_MODE_CHROMA 2
-#define FILT_WARPS_PER_CTA 16
+
+#ifndef FILT_LPC
+#define FILT_LPC 4                        /* lanes per cell row */
+#endif
+#define FILT_G (32 / FILT_LPC)            /* cell rows per warp (band height) */
+#ifndef FILT_WPC
+#define FILT_WPC 4                        /* bands (warps) per CTA */
+#endif
+#define FILT_CELLS (FILT_WPC * FILT_G)    /* cell rows per CTA */
+#define FILT_THREADS (FILT_WPC * 32)
 
 struct FiltArgs {
     uint8_t *data;
@@ -39,26 +56,27 @@ struct FiltArgs {
     int sharpen;
     int bw, bh;   /* chroma: block size in this plane */
     int ncols, nrows;
-    int *progress;
     int mode;
-    int cached; /* set per row by the kernel: tile loads may use L1 */
+    int *progress; /* completed steps per band (global; zeroed before the launch) */
+    int first_cta; /* this plane's first CTA in the grid */
+};
+
+struct FiltJob {
+    FiltArgs p[3];
+    int nplanes;
 };
 
 #ifdef DSVCU_EMU
-#define PXLD(p) (*(p))
-#define PROG_LD(p) (*(p))
-#define FILT_LANE 0
-#define FILT_NLANES 1
-#define FILT_WARP ((int) blockIdx.x)
-#define FILT_NWARPS ((int) gridDim.x)
+#define FILT_SUB 0
+#define FILT_NSUB 1
+#define F_GSYNC() ((void) 0)
 #else
-#define PXLD(p) (*(volatile const uint8_t *) (p))
-#define PROG_LD(p) (*(volatile const int *) (p))
-#define FILT_LANE ((int) (threadIdx.x & 31))
-#define FILT_NLANES 32
-#define FILT_WARP ((int) ((blockIdx.x * blockDim.x + threadIdx.x) >> 5))
-#define FILT_NWARPS ((int) ((gridDim.x * blockDim.x) >> 5))
+#define FILT_SUB ((int) (threadIdx.x & (FILT_LPC - 1)))
+#define FILT_NSUB FILT_LPC
+/* barrier + memory ordering among the lanes that share a cell */
+#define F_GSYNC() __syncwarp((((1u << FILT_LPC) - 1u)) << ((threadIdx.x & 31u) & ~(unsigned) (FILT_LPC - 1)))
 #endif
+#define PXLD(p) (*(p))
 
 DSVCU_HD int f_abs(int v) { return v < 0 ? -v : v; }
 DSVCU_HD int f_clamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -69,9 +87,22 @@ DSVCU_HD int f_clamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi 
      f_abs((i1) - (avg)) < (t) && f_abs((e2) - (avg)) < (t) && f_abs((i2) - (avg)) < (t))
 
 /* one line of the edge filter: 11 samples p[-3..7] with pitch d (bmc.c:86-127) */
-DSVCU_DEV void
-f_edge_line(uint8_t *p, int d, int tE, int tM, int in_edge)
+template <bool VOL>
+DSVCU_DEV int
+f_px(const uint8_t *p)
 {
+#ifndef DSVCU_EMU
+    if (VOL) return *(volatile const uint8_t *) p; /* written by another SM: read it from L2 */
+#endif
+    return *p;
+}
+
+template <bool VOL>
+DSVCU_DEV void
+f_edge_line_t(uint8_t *p, int d, int tE, int tM, int in_edge)
+{
+#undef PXLD
+#define PXLD(q) f_px<VOL>(q)
     int e2 = PXLD(p - 3 * d), e1 = PXLD(p - 2 * d), e0 = PXLD(p - d);
     int i0 = PXLD(p), i1 = PXLD(p + d), i2 = PXLD(p + 2 * d);
     int n1 = 0, n0 = 0, m0 = 0, m1 = 0, m2 = 0;
@@ -105,6 +136,15 @@ f_edge_line(uint8_t *p, int d, int tE, int tM, int in_edge)
     }
 }
 
+#undef PXLD
+#define PXLD(p) (*(p))
+
+DSVCU_DEV void
+f_edge_line(uint8_t *p, int d, int tE, int tM, int in_edge)
+{
+    f_edge_line_t<false>(p, d, tE, tM, in_edge);
+}
+
 /* ihfilter4x4 (bmc.c:70-128): lanes split the rows */
 DSVCU_DEV void
 f_hfilter(const FiltArgs &A, int x, int y, int edge, int tE, int tM)
@@ -113,7 +153,7 @@ f_hfilter(const FiltArgs &A, int x, int y, int edge, int tE, int tM)
     int top = f_clamp(y, 0, A.h - 1), bot = f_clamp(y + 4, 0, A.h - 1);
     int in_edge = x < (A.w - 8);
     if (!edge) tE = tM;
-    for (int r = top + FILT_LANE; r < bot; r += FILT_NLANES) {
+    for (int r = top + FILT_SUB; r < bot; r += FILT_NSUB) {
         f_edge_line(A.data + (size_t) r * A.stride + x, 1, tE, tM, in_edge);
     }
 }
@@ -126,7 +166,7 @@ f_vfilter(const FiltArgs &A, int x, int y, int edge, int tE, int tM)
     int beg = f_clamp(x, 0, A.w - 1), end = f_clamp(x + 4, 0, A.w - 1);
     int in_edge = y < (A.h - 8);
     if (!edge) tE = tM;
-    for (int c = beg + FILT_LANE; c < end; c += FILT_NLANES) {
+    for (int c = beg + FILT_SUB; c < end; c += FILT_NSUB) {
         f_edge_line(A.data + (size_t) y * A.stride + c, A.stride, tE, tM, in_edge);
     }
 }
@@ -228,6 +268,71 @@ f_degrad(uint8_t *a, int as)
     }
 }
 
+/* reductions over the lanes that share a cell */
+#ifdef DSVCU_EMU
+#define F_GRED(v, op) ((void) 0)
+#else
+#define F_GMASK ((((1u << FILT_LPC) - 1u)) << ((threadIdx.x & 31u) & ~(unsigned) (FILT_LPC - 1)))
+#define F_GRED(v, op)                                         \
+    do {                                                      \
+        for (int o_ = 1; o_ < FILT_LPC; o_ <<= 1) {           \
+            int w_ = __shfl_xor_sync(F_GMASK, (v), o_);       \
+            (v) = op((v), w_);                                \
+        }                                                     \
+    } while (0)
+#endif
+DSVCU_DEV int f_add(int a, int b) { return a + b; }
+
+/* degrad4x4 on a staged cell, the cell's lanes taking its rows.  Only the lowest
+ * and the highest occupied histogram bin matter (bmc.c:296-312), so the 16-bin
+ * histogram reduces to a min/max and two (count, sum) pairs. */
+DSVCU_DEV void
+f_degrad_grp(uint8_t *a, int as)
+{
+    int lo = 16, hi = -1;
+    for (int r = FILT_SUB; r < 4; r += FILT_NSUB) {
+        for (int c = 0; c < 4; c++) {
+            int t = a[r * as + c] >> 4;
+            lo = min(lo, t);
+            hi = max(hi, t);
+        }
+    }
+    F_GRED(lo, min);
+    F_GRED(hi, max);
+    if (lo >= hi) return;
+    int cnt = 0, sums = 0; /* lo in the low half, hi in the high half */
+    for (int r = FILT_SUB; r < 4; r += FILT_NSUB) {
+        for (int c = 0; c < 4; c++) {
+            int p = a[r * as + c], t = p >> 4;
+            if (t == lo) {
+                cnt += 1;
+                sums += p;
+            }
+            if (t == hi) {
+                cnt += 1 << 16;
+                sums += p << 16;
+            }
+        }
+    }
+    F_GRED(cnt, f_add);
+    F_GRED(sums, f_add);
+    const int flo = cnt & 0xffff, fhi = cnt >> 16;
+    int alo = (sums & 0xffff) / flo, ahi = (sums >> 16) / fhi;
+    if (alo == 0) alo = 1;
+    if (ahi == 0) ahi = 1;
+    const int t = (alo + ahi + 1) >> 1;
+    for (int r = FILT_SUB; r < 4; r += FILT_NSUB) {
+        for (int c = 0; c < 4; c++) {
+            int os = a[r * as + c];
+            if (os < t) {
+                a[r * as + c] = (uint8_t) (os + ((flo * (alo - os)) / 16));
+            } else if (os > t) {
+                a[r * as + c] = (uint8_t) (os + ((fhi * (ahi - os)) / 16));
+            }
+        }
+    }
+}
+
 DSVCU_DEV int
 f_curve_tex(int tt)
 {
@@ -276,40 +381,100 @@ struct FPrep {
     int active;
 };
 
-DSVCU_DEV FPrep
-f_prep(const FiltArgs &A, int i, int j)
+DSVCU_DEV int
+f_mod(int v, int m)
 {
-    FPrep P;
-    P.mvxy = 0;
-    P.bits = 0;
-    P.nd = 0;
-    P.active = 0;
-    if (A.mode == FILT_MODE_CHROMA) {
-        return P; /* chroma blocks keep the direct path */
-    }
-    const int nsbx = A.w / 4, nsby = A.h / 4;
-    const int x = i * 4, y = j * 4;
-    if (y + 4 >= A.h || x + 4 >= A.w) return P;
-    const int fy = j * A.nbv / nsby, fx = i * A.nbh / nsbx;
+    return (m & (m - 1)) ? v % m : (v & (m - 1));
+}
+
+/* Block-level half of the preparation: what every cell of motion block
+ * (fx, fy) shares.  Built for all blocks a CTA can touch before its first step
+ * (table in shared memory), so the serial chain only adds the edge flags. */
+struct FBlk {
+    int mvxy; /* x | y << 16 */
+    int nd;   /* ndx | ndy << 16 */
+    int bits; /* flags (8) | submask << 8 | blockdata << 16 | active << 24 */
+};
+
+DSVCU_DEV FBlk
+f_blk(const FiltArgs &A, int fx, int fy)
+{
+    FBlk B;
+    B.mvxy = 0;
+    B.nd = 0;
+    B.bits = 0;
     if (A.mode == FILT_MODE_INTRA) {
         int bd = A.blockdata[fx + fy * A.nbh];
-        P.bits = bd << 24;
-        P.active = !(bd & BD_RING);
-        return P;
+        B.bits = (bd << 16) | ((!(bd & BD_RING)) << 24);
+        return B;
     }
     const dsvcu_mv mv = A.mvs[fx + fy * A.nbh];
-    int ndx = 0, ndy = 0;
-    P.mvxy = (mv.x & 0xffff) | ((int) mv.y << 16);
-    P.bits = (int) (mv.flags & 255u) | ((int) mv.submask << 8) | (((x % A.blk_w) == 0) << 16) |
-             (((x % (A.blk_w / 2)) == 0) << 17) | (((y % A.blk_h) == 0) << 18) | (((y % (A.blk_h / 2)) == 0) << 19);
-    if (mv.flags & MVF_SKIP) return P;
+    int ndx = 0, ndy = 0, active;
+    B.mvxy = (mv.x & 0xffff) | ((int) mv.y << 16);
+    B.bits = (int) (mv.flags & 255u) | ((int) mv.submask << 8);
+    if (mv.flags & MVF_SKIP) return B;
     if (A.do_filter && !(mv.flags & MVF_INTRA)) {
         f_neighbordif2(A.mvs, A.nbh, fx, fy, &ndx, &ndy);
     }
-    P.nd = (ndx & 0xffff) | (ndy << 16);
-    P.active = (mv.flags & MVF_INTRA) || (A.do_filter && (ndx || ndy)) ||
-               (A.sharpen && (mv.x & 3) && (mv.y & 3) && ((mv.x | mv.y) & 1) && f_abs(mv.x) < 8 && f_abs(mv.y) < 8);
+    B.nd = (ndx & 0xffff) | (ndy << 16);
+    active = (mv.flags & MVF_INTRA) || (A.do_filter && (ndx || ndy)) ||
+             (A.sharpen && (mv.x & 3) && (mv.y & 3) && ((mv.x | mv.y) & 1) && f_abs(mv.x) < 8 && f_abs(mv.y) < 8);
+    B.bits |= active << 24;
+    return B;
+}
+
+/* cell (i, j) of a block whose shared part is B */
+DSVCU_DEV FPrep
+f_prep_cell(const FiltArgs &A, int i, int j, const FBlk &B)
+{
+    FPrep P;
+    const int x = i * 4, y = j * 4;
+    P.mvxy = B.mvxy;
+    P.nd = B.nd;
+    P.bits = 0;
+    P.active = 0;
+    if (y + 4 >= A.h || x + 4 >= A.w) return P;
+    P.active = (B.bits >> 24) & 1;
+    if (A.mode == FILT_MODE_INTRA) {
+        P.bits = ((B.bits >> 16) & 255) << 24;
+        return P;
+    }
+    P.bits = (B.bits & 0xffff) | ((f_mod(x, A.blk_w) == 0) << 16) | ((f_mod(x, A.blk_w / 2) == 0) << 17) |
+             ((f_mod(y, A.blk_h) == 0) << 18) | ((f_mod(y, A.blk_h / 2) == 0) << 19);
     return P;
+}
+
+/* (fx, fy) = motion block of cell (i, j) as the reference maps it */
+DSVCU_DEV FPrep
+f_prep(const FiltArgs &A, int i, int j)
+{
+    const int nsbx = A.w / 4, nsby = A.h / 4;
+    return f_prep_cell(A, i, j, f_blk(A, i * A.nbh / max(nsbx, 1), j * A.nbv / max(nsby, 1)));
+}
+
+/* chroma_filter thresholds of motion block (i, j) (bmc.c:620-640):
+ * tx | ty << 15 | active << 30 */
+DSVCU_DEV int
+f_chroma_blk(const FiltArgs &A, int i, int j)
+{
+    const dsvcu_mv mv = A.mvs[i + j * A.nbh];
+    if (mv.flags & MVF_SKIP) return 0;
+    int it = f_clamp((64 * A.q) >> 12, 2, 32);
+    int tx = it, ty = it;
+    if (!(mv.flags & MVF_INTRA)) {
+        int ndx, ndy;
+        f_neighbordif2(A.mvs, A.nbh, i, j, &ndx, &ndy);
+        int amx = f_abs(mv.x), amy = f_abs(mv.y);
+        if (ndx < amy && ndy < amx) {
+            tx = ty = 0;
+        } else {
+            tx = (min(ndy, 64) * A.q) >> 12;
+            ty = (min(ndx, 64) * A.q) >> 12;
+        }
+    }
+    tx = f_clamp(tx, 0, 32767);
+    ty = f_clamp(ty, 0, 32767);
+    return tx | (ty << 15) | ((tx > 0 || ty > 0) << 30);
 }
 
 /* ---- per-cell staging.  A cell reads and writes inside the 11 x 11 pixel
@@ -322,53 +487,72 @@ f_prep(const FiltArgs &A, int i, int j)
  * wavefront protocol already reserves for this cell. ---- */
 #define FT_S 16                      /* tile pitch */
 #define FT_ROWS 11
-#define FT_BYTES (FT_ROWS * FT_S)
+#define FT_BYTES (FT_ROWS * FT_S + 4)  /* 45 words: odd pitch between tiles, no bank conflicts */
 #define FT_ORG (3 * FT_S + 4)        /* tile offset of pixel (x, y) */
 
-DSVCU_DEV void
-f_tile_load(uint8_t *T, const FiltArgs &A, int x, int y)
-{
-    for (int k = FILT_LANE; k < FT_ROWS * 3; k += FILT_NLANES) {
-        int r = k / 3, q = k - r * 3;
-        const uint8_t *g = A.data + (ptrdiff_t) (y - 3 + r) * A.stride + x - 4 + 4 * q;
-#ifndef DSVCU_EMU
-        /* pixels a cell reads were last written by rows r-2 .. r of the same
-         * picture.  For rows >= 2 inside a CTA all of them ran on this SM, so an
-         * L1-cached load is coherent (after the block-scope fence of the
-         * hand-off); the first two rows of a CTA read what another SM wrote and
-         * go to L2. */
-        *(uint32_t *) (T + r * FT_S + 4 * q) = A.cached ? *(const uint32_t *) g : *(volatile const uint32_t *) g;
+/* 4-byte copy between word-aligned pixel addresses */
+#ifdef DSVCU_EMU
+#define F_CP4(dst, src) memcpy((dst), (src), 4)
 #else
-        memcpy(T + r * FT_S + 4 * q, g, 4);
+#define F_CP4(dst, src) (*(uint32_t *) (dst) = *(const uint32_t *) (src))
 #endif
+
+DSVCU_DEV void
+f_tile_load(uint8_t *T, const FiltArgs &A, int x, int y, bool vol)
+{
+    /* Pixels a cell reads were last written by cell rows r-2 .. r.  When all of
+     * them belong to this CTA, a plain (L1-cached) load observes their stores
+     * once the step barrier has been passed; the first two rows of a CTA read
+     * what another SM wrote and go to L2.  The cell's lanes take the tile rows
+     * round-robin; all loads are issued before the first store so the batch
+     * costs one memory round trip. */
+    const int NIT = (FT_ROWS + FILT_NSUB - 1) / FILT_NSUB;
+    uint32_t v[NIT][3];
+    const uint8_t *g = A.data + (ptrdiff_t) (y - 3 + FILT_SUB) * A.stride + x - 4;
+#pragma unroll
+    for (int n = 0; n < NIT; n++) {
+        if (FILT_SUB + n * FILT_NSUB < FT_ROWS) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+#ifndef DSVCU_EMU
+                v[n][q] = vol ? *(volatile const uint32_t *) (g + 4 * q) : *(const uint32_t *) (g + 4 * q);
+#else
+                (void) vol;
+                memcpy(&v[n][q], g + 4 * q, 4);
+#endif
+            }
+        }
+        g += (ptrdiff_t) FILT_NSUB * A.stride;
     }
-    DSVCU_SYNCWARP();
+    uint8_t *t = T + FILT_SUB * FT_S;
+#pragma unroll
+    for (int n = 0; n < NIT; n++) {
+        if (FILT_SUB + n * FILT_NSUB < FT_ROWS) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) F_CP4(t + 4 * q, &v[n][q]);
+        }
+        t += FILT_NSUB * FT_S;
+    }
+    F_GSYNC();
 }
 
-/* what: 1 = horizontal pass region, 2 = vertical pass region, 4 = the cell */
+/* what: 1 = horizontal pass region (rows y..y+3, all three words), 2 = vertical
+ * pass region (the cell's column word, rows y-2..y+6), 4 = the cell */
 DSVCU_DEV void
 f_tile_store(const uint8_t *T, const FiltArgs &A, int x, int y, int what)
 {
-    DSVCU_SYNCWARP();
-    for (int k = FILT_LANE; k < 12 + 9; k += FILT_NLANES) {
-        int r, q;
-        if (k < 12) {
-            if (!(what & 5)) continue;
-            r = 3 + k / 3;
-            q = k % 3;
-            if (!(what & 1) && q != 1) continue; /* sharpener only: the cell's own word */
-        } else {
-            if (!(what & 2)) continue;
-            r = 1 + (k - 12);
-            q = 1;
-            if ((what & 5) && r >= 3 && r < 7) continue; /* already written above */
+    F_GSYNC();
+    for (int r = 1 + FILT_SUB; r < 10; r += FILT_NSUB) {
+        const bool own = r >= 3 && r < 7; /* the cell's rows */
+        uint8_t *g = A.data + (ptrdiff_t) (y - 3 + r) * A.stride + x - 4;
+        const uint8_t *t = T + r * FT_S;
+        if (own && (what & 1)) {
+            F_CP4(g, t);
+            F_CP4(g + 4, t + 4);
+            F_CP4(g + 8, t + 8);
+        } else if ((what & 2) || (own && (what & 4))) {
+            F_CP4(g + 4, t + 4);
         }
-        uint8_t *g = A.data + (ptrdiff_t) (y - 3 + r) * A.stride + x - 4 + 4 * q;
-#ifndef DSVCU_EMU
-        *(uint32_t *) g = *(const uint32_t *) (T + r * FT_S + 4 * q);
-#else
-        memcpy(g, T + r * FT_S + 4 * q, 4);
-#endif
     }
 }
 
@@ -384,7 +568,7 @@ f_tile_view(const FiltArgs &A, uint8_t *T, int x, int y)
 
 /* one 4x4 cell of luma_filter (bmc.c:492-600); P = f_prep() of this cell */
 DSVCU_DEV int
-f_luma_cell(const FiltArgs &G, uint8_t *T, int i, int j, const FPrep &P)
+f_luma_cell(const FiltArgs &G, uint8_t *T, int i, int j, const FPrep &P, bool vol)
 {
     const FiltArgs &A = G;
     const int x = i * 4, y = j * 4;
@@ -412,9 +596,9 @@ f_luma_cell(const FiltArgs &G, uint8_t *T, int i, int j, const FPrep &P)
             teh |= edgehs;
             tev |= edgevs;
         }
-        f_tile_load(T, A, x, y);
+        f_tile_load(T, A, x, y, vol);
         f_hfilter(L, x, y, teh, tH, tL);
-        DSVCU_SYNCWARP();
+        F_GSYNC();
         f_vfilter(L, x, y, tev, tH, tL);
         f_tile_store(T, A, x, y, 3);
         return 1;
@@ -426,7 +610,7 @@ f_luma_cell(const FiltArgs &G, uint8_t *T, int i, int j, const FPrep &P)
         int teh = edgeh || eprm, tev = edgev || eprm;
         int tndc = (ndx + ndy + 1) >> 1;
         F4x4 b;
-        f_tile_load(T, A, x, y);
+        f_tile_load(T, A, x, y, vol);
         what |= 8; /* tile is loaded */
         f_load4x4(b, dxy, FT_S);
         f_artf(b, &sh, &sv, &shl, &svl);
@@ -447,7 +631,7 @@ f_luma_cell(const FiltArgs &G, uint8_t *T, int i, int j, const FPrep &P)
         tt = (min(tt, A.fthresh) * q) >> 12;
         addx = (min(ndy, A.fthresh) * q) >> 12;
         addy = (min(ndx, A.fthresh) * q) >> 12;
-        DSVCU_SYNCWARP();
+        F_GSYNC();
         if (sh > 2 * sv || amy > 2 * amx) {
             f_vfilter(L, x, y, tev, tt + addy, tt);
             what |= 2;
@@ -456,16 +640,16 @@ f_luma_cell(const FiltArgs &G, uint8_t *T, int i, int j, const FPrep &P)
             what |= 1;
         } else {
             f_hfilter(L, x, y, teh, tt + addx, tt);
-            DSVCU_SYNCWARP();
+            F_GSYNC();
             f_vfilter(L, x, y, tev, tt + addy, tt);
             what |= 3;
         }
-        DSVCU_SYNCWARP();
+        F_GSYNC();
         touched = 1;
     }
     if (A.sharpen && (mv.x & 3) && (mv.y & 3) && ((mv.x | mv.y) & 1) && amx < 8 && amy < 8) {
-        if (!(what & 8)) f_tile_load(T, A, x, y);
-        if (FILT_LANE == 0) f_degrad(dxy, FT_S);
+        if (!(what & 8)) f_tile_load(T, A, x, y, vol);
+        f_degrad_grp(dxy, FT_S);
         what |= 4;
         touched = 1;
     }
@@ -475,7 +659,7 @@ f_luma_cell(const FiltArgs &G, uint8_t *T, int i, int j, const FPrep &P)
 
 /* one 4x4 cell of dsv_intra_filter (bmc.c:411-455) */
 DSVCU_DEV int
-f_intra_cell(const FiltArgs &G, uint8_t *T, int i, int j, const FPrep &P)
+f_intra_cell(const FiltArgs &G, uint8_t *T, int i, int j, const FPrep &P, bool vol)
 {
     const FiltArgs &A = G;
     const int x = i * 4, y = j * 4;
@@ -485,7 +669,7 @@ f_intra_cell(const FiltArgs &G, uint8_t *T, int i, int j, const FPrep &P)
     const FiltArgs L = f_tile_view(A, T, x, y);
     int sh, sv, shl, svl, tt = 32;
     F4x4 b;
-    f_tile_load(T, A, x, y);
+    f_tile_load(T, A, x, y, vol);
     f_load4x4(b, dxy, FT_S);
     f_artf(b, &sh, &sv, &shl, &svl);
     int mxs = max(sh, sv);
@@ -499,244 +683,218 @@ f_intra_cell(const FiltArgs &G, uint8_t *T, int i, int j, const FPrep &P)
     tt = tt * 2 / 3;
     tt = (tt * q) >> 12;
     tt = f_clamp(tt, 0, A.fthresh);
-    DSVCU_SYNCWARP();
+    F_GSYNC();
     f_hfilter(L, x, y, 0, tt, tt);
-    DSVCU_SYNCWARP();
+    F_GSYNC();
     f_vfilter(L, x, y, 0, tt, tt);
-    DSVCU_SYNCWARP();
+    F_GSYNC();
     tt = (sh > sv) ? (3 * sh + sv) : (3 * sv + sh);
     tt = f_curve_tex(tt);
     tt = 16 + ((tt + 2) >> 2);
     tt = (tt * q) >> 12;
     tt = f_clamp(tt, 0, A.fthresh);
     f_hfilter(L, x, y, 0, tt, tt);
-    DSVCU_SYNCWARP();
+    F_GSYNC();
     f_vfilter(L, x, y, 0, tt, tt);
     f_tile_store(T, A, x, y, 3);
     return 1;
 }
 
 /* one motion block of chroma_filter (bmc.c:620-657) */
+template <bool VOL>
 DSVCU_DEV int
-f_chroma_cell(const FiltArgs &A, int i, int j)
+f_chroma_cell(const FiltArgs &A, int i, int j, int blk)
 {
-    const dsvcu_mv mv = A.mvs[i + j * A.nbh];
-    if (mv.flags & MVF_SKIP) return 0;
     const int x = i * A.bw, y = j * A.bh;
-    int it = f_clamp((64 * A.q) >> 12, 2, 32);
-    int tx = it, ty = it;
-    if (!(mv.flags & MVF_INTRA)) {
-        int ndx, ndy;
-        f_neighbordif2(A.mvs, A.nbh, i, j, &ndx, &ndy);
-        int amx = f_abs(mv.x), amy = f_abs(mv.y);
-        if (ndx < amy && ndy < amx) {
-            tx = ty = 0;
-        } else {
-            tx = (min(ndy, 64) * A.q) >> 12;
-            ty = (min(ndx, 64) * A.q) >> 12;
-        }
-    }
+    const int tx = blk & 32767, ty = (blk >> 15) & 32767;
     /* left side: the bh/4 row groups are independent, lanes take lines */
     if (!(x < 4 || x > A.w - 4 || tx <= 0)) {
         int in_edge = x < (A.w - 8);
-        for (int k = FILT_LANE; k < A.bh; k += FILT_NLANES) {
+        for (int k = FILT_SUB; k < A.bh; k += FILT_NSUB) {
             int z = k & ~3;
             if (y + z + 4 < A.h) {
                 int top = f_clamp(y + z, 0, A.h - 1), bot = f_clamp(y + z + 4, 0, A.h - 1);
                 int r = y + k;
                 if (r >= top && r < bot) {
-                    f_edge_line(A.data + (size_t) r * A.stride + x, 1, tx, tx, in_edge);
+                    f_edge_line_t<VOL>(A.data + (size_t) r * A.stride + x, 1, tx, tx, in_edge);
                 }
             }
         }
     }
-    DSVCU_SYNCWARP();
+    F_GSYNC();
     if (!(y < 4 || y > A.h - 4 || ty <= 0)) {
         int in_edge = y < (A.h - 8);
-        for (int k = FILT_LANE; k < A.bw; k += FILT_NLANES) {
+        for (int k = FILT_SUB; k < A.bw; k += FILT_NSUB) {
             int z = k & ~3;
             if (x + z + 4 < A.w) {
                 int beg = f_clamp(x + z, 0, A.w - 1), end = f_clamp(x + z + 4, 0, A.w - 1);
                 int c = x + k;
                 if (c >= beg && c < end) {
-                    f_edge_line(A.data + (size_t) y * A.stride + c, A.stride, ty, ty, in_edge);
+                    f_edge_line_t<VOL>(A.data + (size_t) y * A.stride + c, A.stride, ty, ty, in_edge);
                 }
             }
         }
     }
-    DSVCU_SYNCWARP();
+    F_GSYNC();
     return (tx > 0) || (ty > 0);
 }
 
-/* Can cell (i, row) touch pixels at all?  Decided from block data only (vectors,
- * flags), never from pixels, so it can be evaluated ahead of the wavefront.
- * Cells that cannot are skipped without waiting for their neighbours. */
-DSVCU_DEV int
-f_cell_active(const FiltArgs &A, int i, int j)
-{
-    if (A.mode == FILT_MODE_CHROMA) {
-        const dsvcu_mv mv = A.mvs[i + j * A.nbh];
-        if (mv.flags & MVF_SKIP) return 0;
-        if (mv.flags & MVF_INTRA) return 1;
-        int ndx, ndy;
-        f_neighbordif2(A.mvs, A.nbh, i, j, &ndx, &ndy);
-        if (ndx < f_abs(mv.y) && ndy < f_abs(mv.x)) return 0;
-        return ((min(ndy, 64) * A.q) >> 12) > 0 || ((min(ndx, 64) * A.q) >> 12) > 0;
-    }
-    const int nsbx = A.w / 4, nsby = A.h / 4;
-    const int x = i * 4, y = j * 4;
-    if (y + 4 >= A.h || x + 4 >= A.w) return 0;
-    const int fy = j * A.nbv / nsby, fx = i * A.nbh / nsbx;
-    if (A.mode == FILT_MODE_INTRA) {
-        return !(A.blockdata[fx + fy * A.nbh] & BD_RING);
-    }
-    const dsvcu_mv mv = A.mvs[fx + fy * A.nbh];
-    if (mv.flags & MVF_SKIP) return 0;
-    if (mv.flags & MVF_INTRA) return 1;
-    if (A.do_filter) {
-        int ndx, ndy;
-        f_neighbordif2(A.mvs, A.nbh, fx, fy, &ndx, &ndy);
-        if (ndx || ndy) return 1;
-    }
-    return A.sharpen && (mv.x & 3) && (mv.y & 3) && ((mv.x | mv.y) & 1) && f_abs(mv.x) < 8 && f_abs(mv.y) < 8;
-}
-
-/* Slope-2 wavefront over rows of cells (see file header).  Protocol: row r
- * publishes progress P = "cells < P of this row are complete, and row r-1 has
- * completed cells < P+1" (the second half covers the footprint overlap between
- * rows r-1 and r+1 in the same column).  An active cell i waits for row r-1 to
- * reach min(i+2, ncols).  Inactive cells are not visited one by one: the warp
- * finds the next active cell with a ballot and, while it waits for that cell's
- * dependency, keeps relaying the progress of the row above (minus one cell), so
- * a region without filtering costs one flag round trip per row instead of one
- * per cell.
+/* The skewed-lockstep schedule described in the file header.
  *
- * A CTA owns FILT_WARPS_PER_CTA consecutive rows, one warp each.  Hand-offs
- * between rows of the same CTA go through shared-memory progress words and
- * block-scope fences (tens of cycles); only the last row of a CTA also
- * publishes to global memory with a device-scope fence, for the first row of
- * the next CTA.  Pixels always travel through L2 (volatile accesses). */
-#ifndef DSVCU_EMU
-#define FILT_FENCE(dev)                  \
-    do {                                 \
-        if (dev) {                       \
-            __threadfence();             \
-        } else {                         \
-            __threadfence_block();       \
-        }                                \
-    } while (0)
-#endif
-
-DSVCU_DEV void
-f_row(const FiltArgs &A0, uint8_t *T, int row, volatile int *sprog, int lr)
+ * Step t of a band: group g handles cell t - 2g of row band*FILT_G + g.  The
+ * first row of band b needs the last row of band b-1 to have COMPLETED cell
+ * t+1, i.e. band b-1 to have completed step t + 2*FILT_G - 1: band b waits for
+ * done[b-1] >= min(t + 2*FILT_G, nsteps).  A step in which no cell of the band
+ * can touch pixels costs one look-up in the activity bitmap and a ballot.
+ *
+ * CTA c of a plane owns bands c*FILT_WPC .. +FILT_WPC-1 (one warp each); CTA c
+ * only ever waits for CTA c-1, which the hardware dispatches first.
+ * Dynamic shared memory: FILT_CELLS tiles | done[FILT_WPC] | activity bitmap of
+ * the block rows this CTA's cells map to. */
+DSVCU_HD int
+filt_block_rows(const FiltArgs &A)
 {
-    FiltArgs A = A0;
-    const int ncols = A.ncols;
-    A.cached = (lr >= 2);
-#ifndef DSVCU_EMU
-    const int lane = FILT_LANE;
-    /* where the progress of the row above lives, and who needs ours */
-    const bool above_global = (lr == 0);
-    const bool pub_global = (lr == FILT_WARPS_PER_CTA - 1);
-    const bool dev_fence = (lr >= FILT_WARPS_PER_CTA - 2); /* rows whose pixels the next CTA reads */
-    volatile const int *above = above_global ? (volatile const int *) (A.progress + row - 1) : (sprog + lr - 1);
-    int seen = (row == 0) ? 0x7fffffff : 0; /* progress of the row above, cached */
-    int published = 0;
-#define F_PUBLISH(v)                                                      \
-    do {                                                                  \
-        published = (v);                                                  \
-        if (lane == 0) {                                                  \
-            sprog[lr] = published;                                        \
-            if (pub_global) *(volatile int *) (A.progress + row) = published; \
-        }                                                                 \
-    } while (0)
-#else
-    (void) sprog;
-    (void) lr;
-#endif
-    for (int base = 0; base < ncols; base += FILT_NLANES) {
-#ifndef DSVCU_EMU
-        int cell = base + lane;
-        FPrep mine;
-        bool act;
-        if (A.mode == FILT_MODE_CHROMA) {
-            mine = f_prep(A, 0, 0);
-            act = cell < ncols && f_cell_active(A, cell, row);
-        } else {
-            mine = f_prep(A, min(cell, ncols - 1), row);
-            act = cell < ncols && mine.active;
-        }
-        unsigned mask = __ballot_sync(0xffffffffu, act);
-#else
-        FPrep P = f_prep(A, min(base, ncols - 1), row);
-        unsigned mask = (base < ncols && (A.mode == FILT_MODE_CHROMA ? f_cell_active(A, base, row) : P.active)) ? 1u : 0u;
-#endif
-        while (mask) {
-#ifndef DSVCU_EMU
-            const int src = __ffs(mask) - 1;
-            int i = base + src;
-            int need = min(i + 2, ncols);
-            FPrep P;
-            P.mvxy = __shfl_sync(0xffffffffu, mine.mvxy, src);
-            P.bits = __shfl_sync(0xffffffffu, mine.bits, src);
-            P.nd = __shfl_sync(0xffffffffu, mine.nd, src);
-            P.active = 1;
-            mask &= mask - 1;
-            while (seen < need) {
-                seen = *above;
-                int relay = min(i, seen >= ncols ? i : seen - 1);
-                if (relay > published) F_PUBLISH(relay);
-                if (seen < need && above_global) __nanosleep(32);
-            }
-            FILT_FENCE(above_global);
-            if (i > published) F_PUBLISH(i);
-#else
-            int i = base;
-            mask = 0;
-#endif
-            if (A.mode == FILT_MODE_LUMA) {
-                f_luma_cell(A, T, i, row, P);
-            } else if (A.mode == FILT_MODE_INTRA) {
-                f_intra_cell(A, T, i, row, P);
-            } else {
-                f_chroma_cell(A, i, row);
-            }
-#ifndef DSVCU_EMU
-            FILT_FENCE(dev_fence);
-            __syncwarp();
-            F_PUBLISH(i + 1);
-#endif
-        }
-    }
-#ifndef DSVCU_EMU
-    /* tail without active cells: relay until the row above is done */
-    while (seen < ncols) {
-        seen = *above;
-        int relay = seen >= ncols ? ncols : seen - 1;
-        if (relay > published) F_PUBLISH(relay);
-        if (seen < ncols && above_global) __nanosleep(32);
-    }
-    FILT_FENCE(dev_fence);
-    F_PUBLISH(ncols);
-#undef F_PUBLISH
-#endif
+    /* upper bound on the motion-block rows one CTA's cell rows can map to */
+    if (A.mode == FILT_MODE_CHROMA) return FILT_CELLS;
+    return FILT_CELLS * 4 / max(A.blk_h, 4) + 2;
 }
 
-DSVCU_KERNEL void __launch_bounds__(FILT_WARPS_PER_CTA * 32)
-k_filter_wavefront(FiltArgs A)
+DSVCU_HD int
+filt_smem_bytes(const FiltArgs &A)
 {
-    __align__(16) DSVCU_SHARED uint8_t tiles[FILT_WARPS_PER_CTA][FT_BYTES];
-    DSVCU_SHARED int sprog[FILT_WARPS_PER_CTA];
+    const int per_block = A.mode == FILT_MODE_CHROMA ? 4 : (int) sizeof(FBlk);
+    return FILT_CELLS * FT_BYTES + 4 * FILT_WPC + per_block * filt_block_rows(A) * A.nbh + 16;
+}
+
+DSVCU_HD int
+filt_ctas(const FiltArgs &A)
+{
+    return (A.nrows + FILT_CELLS - 1) / FILT_CELLS;
+}
+
+DSVCU_KERNEL void __launch_bounds__(FILT_THREADS)
+k_filter_skew(FiltJob J)
+{
+    DSVCU_DYN_SMEM(uint8_t, smem);
+    int pl = 0;
+    while (pl + 1 < J.nplanes && (int) blockIdx.x >= J.p[pl + 1].first_cta) pl++;
+    const FiltArgs &A = J.p[pl];
+    const int ncols = A.ncols, nrows = A.nrows;
+    int *done = (int *) (smem + FILT_CELLS * FT_BYTES);
+    int *btab = done + FILT_WPC; /* chroma: one word per block; luma/intra: FBlk */
 #ifndef DSVCU_EMU
-    const int lr = (int) (threadIdx.x >> 5);
-    const int row = (int) blockIdx.x * FILT_WARPS_PER_CTA + lr;
-    if (threadIdx.x < FILT_WARPS_PER_CTA) sprog[threadIdx.x] = 0;
+    const int cta = (int) blockIdx.x - A.first_cta;
+    const int lane = (int) (threadIdx.x & 31), warp = (int) (threadIdx.x >> 5);
+    const int grp = lane / FILT_LPC;
+    const int nbands = (nrows + FILT_G - 1) / FILT_G;
+    const int nsteps = ncols + 2 * (FILT_G - 1);
+    const int nsbx = max(A.w / 4, 1), nsby = max(A.h / 4, 1);
+    const bool chroma = A.mode == FILT_MODE_CHROMA;
+    const int band = cta * FILT_WPC + warp;
+    const int row = band * FILT_G + grp;
+    uint8_t *T = smem + (warp * FILT_G + grp) * FT_BYTES;
+    /* block rows this CTA can touch -> block table */
+    const int r0 = cta * FILT_CELLS, r1 = min(nrows, r0 + FILT_CELLS) - 1;
+    const int fy0 = chroma ? r0 : min(r0 * A.nbv / nsby, A.nbv - 1);
+    const int fy1 = chroma ? r1 : min(r1 * A.nbv / nsby, A.nbv - 1);
+    const int nmap = (fy1 - fy0 + 1) * A.nbh;
+    if (threadIdx.x < FILT_WPC) done[threadIdx.x] = 0;
+    for (int b = (int) threadIdx.x; b < nmap; b += (int) blockDim.x) {
+        const int fx = b % A.nbh, fy = fy0 + b / A.nbh;
+        if (chroma) {
+            btab[b] = f_chroma_blk(A, fx, fy);
+        } else {
+            ((FBlk *) btab)[b] = f_blk(A, fx, fy);
+        }
+    }
     __syncthreads();
-    if (row < A.nrows) f_row(A, tiles[lr], row, sprog, lr);
+    if (band >= nbands) return;
+    const bool row_ok = row < nrows && (chroma || row * 4 + 4 < A.h);
+    const int fy = chroma ? min(row, A.nbv - 1) : (row_ok ? min(row * A.nbv / nsby, A.nbv - 1) : fy0);
+    const int abase = (fy - fy0) * A.nbh;
+    /* hand-off words: from the band above / to the band below */
+    const bool above_global = warp == 0, pub_global = warp == FILT_WPC - 1 && band + 1 < nbands;
+    volatile const int *above = above_global ? (volatile const int *) (A.progress + band - 1) : (volatile const int *) (done + warp - 1);
+    /* cell rows whose footprint holds pixels written by the CTA above (luma: its
+     * first two rows; chroma blocks: the first) read them from L2 */
+    const bool vol = cta > 0 && warp == 0 && grp < (chroma ? 1 : 2);
+    int seen = band ? 0 : 0x7fffffff;
+    int fx = 0, rem = 0; /* luma: i * nbh = fx * nsbx + rem */
+    for (int t = 0; t < nsteps; t++) {
+        const int i = t - 2 * grp;
+        bool act = false;
+        int cblk = 0;
+        FBlk B;
+        if (i >= 0 && i < ncols && row_ok) {
+            if (chroma) {
+                cblk = btab[abase + i];
+                act = (cblk >> 30) & 1;
+            } else {
+                B = ((const FBlk *) btab)[abase + min(fx, A.nbh - 1)];
+                act = i * 4 + 4 < A.w && ((B.bits >> 24) & 1);
+                rem += A.nbh;
+                if (rem >= nsbx) {
+                    rem -= nsbx;
+                    fx++;
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, act)) {
+            const int need = min(t + 2 * FILT_G, nsteps);
+            if (seen < need) {
+                unsigned ns = 32;
+                while ((seen = *above) < need) {
+                    __nanosleep(ns);
+                    if (ns < 512) ns <<= 1;
+                }
+                if (above_global) {
+                    __threadfence();
+                } else {
+                    __threadfence_block();
+                }
+            }
+            if (act) {
+                if (A.mode == FILT_MODE_LUMA) {
+                    f_luma_cell(A, T, i, row, f_prep_cell(A, i, row, B), vol);
+                } else if (A.mode == FILT_MODE_INTRA) {
+                    f_intra_cell(A, T, i, row, f_prep_cell(A, i, row, B), vol);
+                } else if (vol) {
+                    f_chroma_cell<true>(A, i, row, cblk);
+                } else {
+                    f_chroma_cell<false>(A, i, row, cblk);
+                }
+            }
+            if (pub_global) {
+                __threadfence();
+            } else {
+                __threadfence_block();
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            done[warp] = t + 1;
+            if (pub_global) *(volatile int *) (A.progress + band) = t + 1;
+        }
+    }
 #else
-    for (int lr = 0; lr < FILT_WARPS_PER_CTA; lr++) {
-        int row = (int) blockIdx.x * FILT_WARPS_PER_CTA + lr;
-        if (row < A.nrows) f_row(A, tiles[0], row, sprog, lr);
+    (void) done;
+    (void) btab;
+    if ((int) blockIdx.x != A.first_cta) return; /* emulation: the plane's first CTA walks it in raster order */
+    for (int row = 0; row < nrows; row++) {
+        for (int i = 0; i < ncols; i++) {
+            if (A.mode == FILT_MODE_CHROMA) {
+                int blk = f_chroma_blk(A, i, row);
+                if ((blk >> 30) & 1) f_chroma_cell<false>(A, i, row, blk);
+            } else {
+                FPrep P = f_prep(A, i, row);
+                if (!P.active) continue;
+                if (A.mode == FILT_MODE_LUMA) {
+                    f_luma_cell(A, smem, i, row, P, false);
+                } else {
+                    f_intra_cell(A, smem, i, row, P, false);
+                }
+            }
+        }
     }
 #endif
 }

@@ -28,6 +28,14 @@
 #include "k_quant.cuh"
 
 #define ME_WARPS_PER_CTA 8
+/* residency targets (CTAs per SM) the register allocation is held to: with many
+ * encoder instances on one GPU the register file is what runs out first */
+#ifndef ME_MIN_CTAS
+#define ME_MIN_CTAS 2
+#endif
+#ifndef ME_PRE_MIN_CTAS
+#define ME_PRE_MIN_CTAS 4
+#endif
 #ifndef ME_POLL_NS
 #define ME_POLL_NS 256 /* back-off between polls of the row above (a block takes ~30 us) */
 #endif
@@ -1877,7 +1885,7 @@ me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
 }
 
 /* neighbour-independent half of every block of a level: one warp per block */
-DSVCU_KERNEL void __launch_bounds__(ME_WARPS_PER_CTA * 32)
+DSVCU_KERNEL void __launch_bounds__(ME_WARPS_PER_CTA * 32, ME_PRE_MIN_CTAS)
 k_me_prepass(MeArgs A)
 {
     DSVCU_SHARED MeScratch scratch[ME_WARPS_PER_CTA];
@@ -1897,7 +1905,12 @@ k_me_prepass(MeArgs A)
  * block-scope fences; the last row of a CTA also publishes through global memory
  * (device-scope fence) for the first row of the next CTA.  The vector field
  * itself is read with volatile loads (me_ldmv), i.e. from L2. */
-DSVCU_KERNEL void __launch_bounds__(ME_WARPS_PER_CTA * 32)
+#if defined(ME_TIMING) && !defined(DSVCU_EMU)
+/* diagnostics build only: [0] cycles in me_block, [1] cycles waiting for the row above, [2] blocks (level 0) */
+__device__ unsigned long long g_me_dbg[4];
+#endif
+
+DSVCU_KERNEL void __launch_bounds__(ME_WARPS_PER_CTA * 32, ME_MIN_CTAS)
 k_me_level(MeArgs A)
 {
     DSVCU_SHARED MeScratch scratch[ME_WARPS_PER_CTA];
@@ -1917,8 +1930,14 @@ k_me_level(MeArgs A)
         const int j = row * step;
         int seen = (row == 0) ? 0x7fffffff : 0;
         int col = 0;
+#if defined(ME_TIMING)
+        long long tw = 0, tb = 0;
+#endif
         for (int i = 0; i < A.nxb; i += step, col++) {
             const int need = col + 1;
+#if defined(ME_TIMING)
+            long long c0 = clock64();
+#endif
             if (seen < need) {
                 while ((seen = *above) < need) {
                     if (above_global) __nanosleep(ME_POLL_NS); /* leave the issue slots to warps that have work */
@@ -1929,7 +1948,14 @@ k_me_level(MeArgs A)
                     __threadfence_block();
                 }
             }
+#if defined(ME_TIMING)
+            long long c1 = clock64();
+#endif
             me_block(A, S, i, j, acc_local);
+#if defined(ME_TIMING)
+            tw += c1 - c0;
+            tb += clock64() - c1;
+#endif
             if (pub_global) {
                 __threadfence();
             } else {
@@ -1941,6 +1967,13 @@ k_me_level(MeArgs A)
                 if (pub_global) *(volatile int *) (A.progress + row) = col + 1;
             }
         }
+#if defined(ME_TIMING)
+        if (ME_LANE == 0 && A.level == 0) {
+            atomicAdd(&g_me_dbg[0], (unsigned long long) tb);
+            atomicAdd(&g_me_dbg[1], (unsigned long long) tw);
+            atomicAdd(&g_me_dbg[2], (unsigned long long) col);
+        }
+#endif
     }
 #else
     MeScratch *S = &scratch[0];

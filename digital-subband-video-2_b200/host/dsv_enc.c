@@ -72,6 +72,8 @@ struct _DSV_ENCDATA {
     int nblk;
     double ph_ms[8], ph_t0;
     int ph_frames;
+    double gpu_ms[8];         /* DSV_PROFILE=2: device time between phase stamps */
+    int gpu_frames, marks_live;
 };
 
 int dsv_get_thread_device(void);
@@ -89,6 +91,13 @@ gpu_state_free(DSV_ENCDATA *g)
         printf("[dsv_enc profile] %d pictures, %.2f ms/picture:", g->ph_frames, tot / g->ph_frames);
         for (i = 0; i < PH_N; i++) printf(" %s %.2f;", ph_name[i], g->ph_ms[i] / g->ph_frames);
         printf("\n");
+        if (g->gpu_frames) {
+            static const char *gn[6] = { "upload+extend+pyramid", "motion search", "(host decisions)", "sub+fwd+quant+inv",
+                                         "reconstruct+filters", "extend+ref pyramid" };
+            printf("[dsv_enc device] %d P pictures:", g->gpu_frames);
+            for (i = 0; i < 6; i++) printf(" %s %.2f;", gn[i], g->gpu_ms[i] / g->gpu_frames);
+            printf("\n");
+        }
     }
     if (g->ctx) {
         dsvcu_sync(g->ctx);
@@ -888,10 +897,22 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
     }
     *pg = g;
     if (g_prof < 0) {
-        g_prof = getenv("DSV_PROFILE") ? 1 : 0;
+        g_prof = getenv("DSV_PROFILE") ? atoi(getenv("DSV_PROFILE")) : 0;
     }
     g->ph_t0 = g_prof > 0 ? now_ms() : 0;
     g->ph_frames++;
+    if (g_prof > 1) {
+        if (g->marks_live) {
+            for (i = 0; i < 6; i++) {
+                float ms = 0.f;
+                dsvcu_mark_elapsed_ms(g->ctx, i, i + 1, &ms);
+                g->gpu_ms[i] += ms;
+            }
+            g->gpu_frames++;
+            g->marks_live = 0;
+        }
+        dsvcu_mark(g->ctx, 0);
+    }
     src = g->src[g->cur];
     rec = g->rec[g->cur];
     ref_src = g->src[g->cur ^ 1];
@@ -931,8 +952,10 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
         hp.skip_block_thresh = enc->skip_block_thresh;
         hp.pyramid_levels = enc->pyramid_levels;
         hp.use_prev_mvs = g->ref_has_mvs;
+        if (g_prof > 1) dsvcu_mark(g->ctx, 1);
         GPU(dsvcu_hme(g->ctx, &fm, &hp, src, g->src_pyr[g->cur], ref_rec, g->ref_pyr, ref_src, g->src_pyr[g->cur ^ 1]));
         tried_motion = 1;
+        if (g_prof > 1) dsvcu_mark(g->ctx, 2);
     } else {
         GPU(dsvcu_intra_analysis_async(g->ctx, &fm, src, nblk));
     }
@@ -1013,6 +1036,7 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
             GPU(dsvcu_mvs_to_prev(g->ctx, nblk));
         }
     }
+    if (g_prof > 1 && p->has_ref) dsvcu_mark(g->ctx, 3);
     GPU(dsvcu_frame_copy(g->ctx, rec, src));
     if (p->has_ref) {
         GPU(dsvcu_sub_pred(g->ctx, &fm, g->pred, rec, ref_rec));
@@ -1026,11 +1050,17 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
         }
     }
     if (p->has_ref) {
+        if (g_prof > 1) dsvcu_mark(g->ctx, 4);
         GPU(dsvcu_add_res(g->ctx, &fm, quant, rec, g->pred, inter_filter));
+        if (g_prof > 1) dsvcu_mark(g->ctx, 5);
     }
     if (p->is_ref) {
         GPU(dsvcu_extend_frame(g->ctx, rec, 0));
         GPU(dsvcu_pyramid_build(g->ctx, g->ref_pyr, rec));
+    }
+    if (g_prof > 1 && p->has_ref) {
+        dsvcu_mark(g->ctx, 6);
+        g->marks_live = 1;
     }
 
     PROF_MARK(g, PH_QUEUE);

@@ -175,6 +175,9 @@ unsigned dsvcu_isqrt(unsigned n);
 /* ---- timing on the context's stream (CUDA events) ---- */
 int dsvcu_timer_start(dsvcu_ctx *ctx);
 int dsvcu_timer_stop_ms(dsvcu_ctx *ctx, float *ms); /* synchronises */
+#define DSVCU_MARKS 8
+int dsvcu_mark(dsvcu_ctx *ctx, int k);                                 /* stamp k on the context's stream */
+int dsvcu_mark_elapsed_ms(dsvcu_ctx *ctx, int a, int b, float *ms);   /* waits for stamp b */
 /* number of kernels this context has launched so far */
 long long dsvcu_launch_count(dsvcu_ctx *ctx);
 /* ... and every context of this process together */

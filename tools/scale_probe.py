@@ -34,4 +34,9 @@ for threads in [int(t) for t in sys.argv[1].split(",")]:
     print("threads %2d: %6.1f fps  (%.1f ms/frame/stream)  host CPU %.2f ms/frame (user %.2f sys %.2f), %.1f cores busy" % (
         threads, nfr / dt, 1000 * dt / GOPN, 1000 * cpu / nfr, 1000 * (ru1.ru_utime - ru0.ru_utime) / nfr,
         1000 * (ru1.ru_stime - ru0.ru_stime) / nfr, cpu / dt), flush=True)
+    if hasattr(lib, "dsvcu_debug_me_counters"):
+        d = (C.c_ulonglong * 4)()
+        lib.dsvcu_debug_me_counters(d, 1)
+        if d[2]:
+            print("   level-0 search: %.1f us in me_block, %.1f us waiting, per block (all reps)" % (d[0] / d[2] / 1965.0, d[1] / d[2] / 1965.0), flush=True)
     lib.dsv_pool_destroy(pool)
