@@ -289,26 +289,26 @@ def kernel_rooflines(P, lib, peak_gbs):
         return g
 
     l0 = lib.dsvcu_launch_count(ctx)
-    t = timed(all_planes(lambda i, p: lib.dsvcu_fwd_sbt(ctx, src[i], p, coefs[i], C.byref(fmP))))
+    t = timed(lambda i: lib.dsvcu_fwd_sbt_frame(ctx, src[i], coefs[i], C.byref(fmP), 7))
     nl = (lib.dsvcu_launch_count(ctx) - l0) // (RING * 4)
-    add("fwd_sbt (P picture, 3 planes: k_fwd_haar/k_fwd_lift)", t, 5 * Pb, nl)
+    add("fwd_sbt (P picture, 3 planes per launch: k_sbt_fwd)", t, 5 * Pb, nl)
     l0 = lib.dsvcu_launch_count(ctx)
     t = timed(all_planes(lambda i, p: lib.dsvcu_quant_plane(ctx, coefs[i], p, q, C.byref(fmP))))
     nl = (lib.dsvcu_launch_count(ctx) - l0) // (RING * 4)
     add("quantise + symbol compaction (k_quant_*, k_compact_*)", t, 8 * Pb, nl)
     l0 = lib.dsvcu_launch_count(ctx)
-    t = timed(all_planes(lambda i, p: lib.dsvcu_inv_sbt(ctx, dst[i], p, coefs[i], q, C.byref(fmP))))
+    t = timed(lambda i: lib.dsvcu_inv_sbt_frame(ctx, dst[i], coefs[i], q, C.byref(fmP), 7))
     nl = (lib.dsvcu_launch_count(ctx) - l0) // (RING * 4)
-    add("inv_sbt (P picture, 3 planes: k_inv_haar/k_inv_lift)", t, 5 * Pb, nl)
-    t = timed(all_planes(lambda i, p: lib.dsvcu_inv_sbt(ctx, dst[i], p, coefs[i], q, C.byref(fmI))))
-    add("inv_sbt (I picture, 3 planes)", t, 5 * Pb, nl)
+    add("inv_sbt (P picture, 3 planes per launch: k_sbt_inv)", t, 5 * Pb, nl)
+    t = timed(lambda i: lib.dsvcu_inv_sbt_frame(ctx, dst[i], coefs[i], q, C.byref(fmI), 7))
+    add("inv_sbt (I picture, 3 planes per launch)", t, 5 * Pb, nl)
     t = timed(lambda i: lib.dsvcu_sub_pred(ctx, C.byref(fmP), dst[i], dst[(i + 1) % RING], src[i]))
     add("predict + subtract (k_predict)", t, 4 * Pb, 1)
     t = timed(lambda i: lib.dsvcu_add_res(ctx, C.byref(fmP), q, dst[i], src[i], 0))
-    add("reconstruct + filter traversal, do_filter=0 (random vectors: sharpening cells active)", t, 3 * Pb, 4)
+    add("reconstruct + filter traversal, do_filter=0 (k_reconstruct + k_filter_skew; random vectors: sharpening cells active)", t, 3 * Pb, 2)
     t_rec = t
     t = timed(lambda i: lib.dsvcu_add_res(ctx, C.byref(fmP), q, dst[i], src[i], 1))
-    add("loop filters, extra cost of do_filter=1 (random vectors: every cell active, worst case)", max(t - t_rec, 1e-4), 2 * Pb, 3)
+    add("loop filters, extra cost of do_filter=1 (k_filter_skew; random vectors: every cell active, worst case)", max(t - t_rec, 1e-4), 2 * Pb, 1)
     t = timed(lambda i: lib.dsvcu_extend_frame(ctx, dst[i], 0))
     add("border extension (k_extend)", t, 2 * 64 * (W + H) * 3 // 2, 1)
 

@@ -176,6 +176,8 @@ def load(emu=False):
         "dsvcu_set_mvs": (ip, [vp, vp, ip]),
         "dsvcu_fwd_sbt": (ip, [vp, vp, ip, vp, P(DSVCU_FMETA)]),
         "dsvcu_inv_sbt": (ip, [vp, vp, ip, vp, ip, P(DSVCU_FMETA)]),
+        "dsvcu_fwd_sbt_frame": (ip, [vp, vp, vp, P(DSVCU_FMETA), ip]),
+        "dsvcu_inv_sbt_frame": (ip, [vp, vp, vp, ip, P(DSVCU_FMETA), ip]),
         "dsvcu_quant_plane": (ip, [vp, vp, ip, ip, P(DSVCU_FMETA)]),
         "dsvcu_fetch_symbols": (ip, [vp, ip, P(P(DSVCU_SYMBOL)), P(ip), P(ip)]),
         "dsvcu_symbol_staging": (P(DSVCU_SYMBOL), [vp, ip, P(ip)]),

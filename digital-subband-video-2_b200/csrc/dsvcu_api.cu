@@ -103,8 +103,9 @@ struct dsvcu_ctx {
     uint8_t *d_blockdata;
     dsvcu_mv *d_mvs;
     int nblk_cap;
-    /* transform scratch: two planes of the largest coefficient plane */
-    int32_t *scratch[2];
+    /* transform scratch: two LL ping-pong planes per coefficient plane (the
+     * three planes of a picture are transformed by the same launches) */
+    int32_t *scratch[3][2];
     /* quantiser outputs */
     int32_t *d_qv;
     int *d_chunk;
@@ -116,6 +117,7 @@ struct dsvcu_ctx {
     int *d_progress;
     int progress_cap;
     int me_smem_set;
+    SbtJob sbt_job; /* launch descriptor under construction (3.7 KB: kept off the stack) */
     int filt_big_smem; /* opted in to > 48 KB dynamic shared memory on this device */
 #ifndef DSVCU_EMU
     cudaEvent_t marks[DSVCU_MARKS];
@@ -254,8 +256,10 @@ dsvcu_ctx_create(dsvcu_ctx **out, int device, int width, int height, int subsamp
 #endif
     maxplane = (size_t) c->cw[0] * c->ch[0];
     if ((size_t) c->cw[1] * c->ch[1] > maxplane) maxplane = (size_t) c->cw[1] * c->ch[1];
-    CK(dsvcu_malloc(&c->scratch[0], maxplane * sizeof(int32_t)));
-    CK(dsvcu_malloc(&c->scratch[1], maxplane * sizeof(int32_t)));
+    for (i = 0; i < 3; i++) {
+        CK(dsvcu_malloc(&c->scratch[i][0], (size_t) c->cw[i] * c->ch[i] * sizeof(int32_t)));
+        CK(dsvcu_malloc(&c->scratch[i][1], (size_t) c->cw[i] * c->ch[i] * sizeof(int32_t)));
+    }
     CK(dsvcu_malloc(&c->d_qv, (maxplane + CMP_CHUNK) * sizeof(int32_t)));
     CK(dsvcu_malloc(&c->d_chunk, (maxplane / CMP_CHUNK + 2) * sizeof(int)));
     CK(dsvcu_malloc(&c->d_meta, 8 * sizeof(int)));
@@ -285,8 +289,10 @@ dsvcu_ctx_destroy(dsvcu_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
 #endif
-    dsvcu_free_dev(c->scratch[0]);
-    dsvcu_free_dev(c->scratch[1]);
+    for (i = 0; i < 3; i++) {
+        dsvcu_free_dev(c->scratch[i][0]);
+        dsvcu_free_dev(c->scratch[i][1]);
+    }
     dsvcu_free_dev(c->d_qv);
     dsvcu_free_dev(c->d_chunk);
     dsvcu_free_dev(c->d_meta);
@@ -688,44 +694,130 @@ sbt_level_geom(SbtLevel *L, int w, int h, int l, const dsvcu_fmeta *fm, const ui
     L->dby = (fm->nblocks_v << BLOCK_INTERP_P) / L->sh;
 }
 
-extern "C" int
-dsvcu_inv_sbt(dsvcu_ctx *c, dsvcu_frame *dst, int plane, dsvcu_coefs *src, int q, const dsvcu_fmeta *fm)
+/* level l of a plane, inverse direction */
+static void
+sbt_inv_level(dsvcu_ctx *c, SbtLevel *L, dsvcu_frame *dst, int plane, dsvcu_coefs *src, int q, const dsvcu_fmeta *fm, int l,
+              int lvls)
 {
-    const int w = src->w[plane], h = src->h[plane];
-    const int lvls = sbt_nlevels(w, h);
     const int luma = (plane == 0);
+    sbt_level_geom(L, src->w[plane], src->h[plane], l, fm, c->d_blockdata);
+    L->hqp = luma ? (q / (fm->isP ? 14 : (l > 4 ? 2 : 8))) : (q / 2);
+    L->ovf = (l >= 6 && l >= lvls - 3 && !fm->lossless);
+    L->ll = (l == lvls) ? src->data[plane] : c->scratch[plane][(l + 1) & 1];
+    L->bands = src->data[plane];
+    if (l == 1) {
+        L->px = dst->p[plane].data;
+        L->px_stride = dst->p[plane].stride;
+        L->px_w = dst->p[plane].w;
+        L->px_h = dst->p[plane].h;
+    } else {
+        L->dst = c->scratch[plane][l & 1];
+    }
+}
+
+static void
+sbt_fwd_level(dsvcu_ctx *c, SbtLevel *L, dsvcu_frame *src, int plane, dsvcu_coefs *dst, const dsvcu_fmeta *fm, int l, int lvls)
+{
+    sbt_level_geom(L, dst->w[plane], dst->h[plane], l, fm, c->d_blockdata);
+    L->ovf = (l >= 6 && l >= lvls - 3 && !fm->lossless);
+    if (l == 1) {
+        L->px = src->p[plane].data;
+        L->px_stride = src->p[plane].stride;
+        L->px_w = src->p[plane].w;
+        L->px_h = src->p[plane].h;
+    } else {
+        L->src = c->scratch[plane][(l - 1) & 1];
+    }
+    L->out_ll = (l == lvls) ? dst->data[plane] : c->scratch[plane][l & 1];
+    L->out_bands = dst->data[plane];
+}
+
+static int
+sbt_is_lift(int f)
+{
+    return f != SBT_F_HAAR && f != SBT_F_HAAR_SIMPLE;
+}
+
+/* first level from which a plane's sub-images are at most two tiles: that
+ * level and everything above it is transformed by one CTA in one launch */
+static int
+sbt_tail_start(int w, int h, int lvls)
+{
     int l;
-    for (l = lvls; l > 0; l--) {
-        SbtLevel L;
-        int f = sbt_pick(l, lvls, luma, fm->isP, fm->lossless);
-        dim3 tg;
-        sbt_level_geom(&L, w, h, l, fm, c->d_blockdata);
-        L.hqp = luma ? (q / (fm->isP ? 14 : (l > 4 ? 2 : 8))) : (q / 2);
-        L.ovf = (l >= 6 && l >= lvls - 3 && !fm->lossless);
-        L.ll = (l == lvls) ? src->data[plane] : c->scratch[(l + 1) & 1];
-        L.bands = src->data[plane];
-        if (l == 1) {
-            L.px = dst->p[plane].data;
-            L.px_stride = dst->p[plane].stride;
-            L.px_w = dst->p[plane].w;
-            L.px_h = dst->p[plane].h;
-        } else {
-            L.dst = c->scratch[l & 1];
+    for (l = 1; l <= lvls; l++) {
+        int sw = RSHIFT_UP(w, l - 1), sh = RSHIFT_UP(h, l - 1);
+        if (((sw + SBT_TW - 1) / SBT_TW) * ((sh + SBT_TH - 1) / SBT_TH) <= 2) break;
+    }
+    if (l > lvls) l = lvls;
+    if (lvls - l + 1 > SBT_MAX_FUSED) l = lvls - SBT_MAX_FUSED + 1;
+    return l;
+}
+
+static int
+sbt_level_ctas(const SbtLevel *L, int f)
+{
+    if (sbt_is_lift(f)) return sbt_level_tiles(*L);
+    return grid_for(L->cw * L->ch, SBT_THREADS);
+}
+
+/* Transform the planes selected by `mask` (bit p = plane p): one launch per
+ * pyramid level covering every selected plane that still has a large level
+ * there, and one launch for the fused small levels of all of them. */
+static int
+sbt_run(dsvcu_ctx *c, dsvcu_frame *fr, dsvcu_coefs *k, int q, const dsvcu_fmeta *fm, int mask, int fwd)
+{
+    int lvls[3], tail[3], p, l, maxbig = 0, stage;
+    SbtJob *J = &c->sbt_job;
+    for (p = 0; p < 3; p++) {
+        if (!(mask & (1 << p))) continue;
+        lvls[p] = sbt_nlevels(k->w[p], k->h[p]);
+        tail[p] = sbt_tail_start(k->w[p], k->h[p], lvls[p]);
+        if (tail[p] - 1 > maxbig) maxbig = tail[p] - 1;
+    }
+    /* stages: forward = levels 1..maxbig then the tails; inverse = the tails then maxbig..1 */
+    if (!mask) return 0;
+    for (stage = 0; stage <= maxbig; stage++) {
+        const int is_tail = fwd ? (stage == maxbig) : (stage == 0);
+        int ctas = 0;
+        l = fwd ? stage + 1 : maxbig - stage + 1;
+        J->nplanes = 0;
+        for (p = 0; p < 3; p++) {
+            SbtPlaneJob *P;
+            int n = 0, ll;
+            if (!(mask & (1 << p))) continue;
+            if (!is_tail && l >= tail[p]) continue;
+            P = &J->p[J->nplanes];
+            if (is_tail) {
+                for (ll = fwd ? tail[p] : lvls[p]; fwd ? ll <= lvls[p] : ll >= tail[p]; ll += fwd ? 1 : -1) {
+                    P->f[n] = sbt_pick(ll, lvls[p], p == 0, fm->isP, fm->lossless);
+                    if (fwd) {
+                        sbt_fwd_level(c, &P->L[n], fr, p, k, fm, ll, lvls[p]);
+                    } else {
+                        sbt_inv_level(c, &P->L[n], fr, p, k, q, fm, ll, lvls[p]);
+                    }
+                    n++;
+                }
+                P->ncta = 1;
+            } else {
+                P->f[0] = sbt_pick(l, lvls[p], p == 0, fm->isP, fm->lossless);
+                if (fwd) {
+                    sbt_fwd_level(c, &P->L[0], fr, p, k, fm, l, lvls[p]);
+                } else {
+                    sbt_inv_level(c, &P->L[0], fr, p, k, q, fm, l, lvls[p]);
+                }
+                n = 1;
+                P->ncta = sbt_level_ctas(&P->L[0], P->f[0]);
+            }
+            P->nlev = n;
+            P->first_cta = ctas;
+            ctas += P->ncta;
+            J->nplanes++;
         }
-        tg = dim3((L.sw + SBT_TW - 1) / SBT_TW, (L.sh + SBT_TH - 1) / SBT_TH, 1);
-        switch (f) {
-            case SBT_F_LLI: DSVCU_LAUNCH(k_inv_lift<SBT_F_LLI>, tg, SBT_THREADS, 0, c->stream, L); break;
-            case SBT_F_LLP: DSVCU_LAUNCH(k_inv_lift<SBT_F_LLP>, tg, SBT_THREADS, 0, c->stream, L); break;
-            case SBT_F_CC: DSVCU_LAUNCH(k_inv_lift<SBT_F_CC>, tg, SBT_THREADS, 0, c->stream, L); break;
-            case SBT_F_L2A: DSVCU_LAUNCH(k_inv_lift<SBT_F_L2A>, tg, SBT_THREADS, 0, c->stream, L); break;
-            case SBT_F_L1: DSVCU_LAUNCH(k_inv_lift<SBT_F_L1>, tg, SBT_THREADS, 0, c->stream, L); break;
-            case SBT_F_LOSSLESS: DSVCU_LAUNCH(k_inv_lift<SBT_F_LOSSLESS>, tg, SBT_THREADS, 0, c->stream, L); break;
-            case SBT_F_HAAR:
-                DSVCU_LAUNCH(k_inv_haar<true>, grid_for(L.cw * L.ch, 256), 256, 0, c->stream, L);
-                break;
-            default:
-                DSVCU_LAUNCH(k_inv_haar<false>, grid_for(L.cw * L.ch, 256), 256, 0, c->stream, L);
-                break;
+        if (!J->nplanes) continue;
+        if (fwd) {
+            DSVCU_LAUNCH(k_sbt_fwd, ctas, SBT_THREADS, 0, c->stream, *J);
+        } else {
+            DSVCU_LAUNCH(k_sbt_inv, ctas, SBT_THREADS, 0, c->stream, *J);
         }
         CK_LAUNCH(c);
     }
@@ -733,43 +825,28 @@ dsvcu_inv_sbt(dsvcu_ctx *c, dsvcu_frame *dst, int plane, dsvcu_coefs *src, int q
 }
 
 extern "C" int
+dsvcu_inv_sbt(dsvcu_ctx *c, dsvcu_frame *dst, int plane, dsvcu_coefs *src, int q, const dsvcu_fmeta *fm)
+{
+    return sbt_run(c, dst, src, q, fm, 1 << plane, 0);
+}
+
+extern "C" int
 dsvcu_fwd_sbt(dsvcu_ctx *c, dsvcu_frame *src, int plane, dsvcu_coefs *dst, const dsvcu_fmeta *fm)
 {
-    const int w = dst->w[plane], h = dst->h[plane];
-    const int lvls = sbt_nlevels(w, h);
-    const int luma = (plane == 0);
-    int l;
-    for (l = 1; l <= lvls; l++) {
-        SbtLevel L;
-        int f = sbt_pick(l, lvls, luma, fm->isP, fm->lossless);
-        dim3 tg;
-        sbt_level_geom(&L, w, h, l, fm, c->d_blockdata);
-        L.ovf = (l >= 6 && l >= lvls - 3 && !fm->lossless);
-        if (l == 1) {
-            L.px = src->p[plane].data;
-            L.px_stride = src->p[plane].stride;
-            L.px_w = src->p[plane].w;
-            L.px_h = src->p[plane].h;
-        } else {
-            L.src = c->scratch[(l - 1) & 1];
-        }
-        L.out_ll = (l == lvls) ? dst->data[plane] : c->scratch[l & 1];
-        L.out_bands = dst->data[plane];
-        tg = dim3((L.sw + SBT_TW - 1) / SBT_TW, (L.sh + SBT_TH - 1) / SBT_TH, 1);
-        switch (f) {
-            case SBT_F_LLI: DSVCU_LAUNCH(k_fwd_lift<SBT_F_LLI>, tg, SBT_THREADS, 0, c->stream, L); break;
-            case SBT_F_LLP: DSVCU_LAUNCH(k_fwd_lift<SBT_F_LLP>, tg, SBT_THREADS, 0, c->stream, L); break;
-            case SBT_F_CC: DSVCU_LAUNCH(k_fwd_lift<SBT_F_CC>, tg, SBT_THREADS, 0, c->stream, L); break;
-            case SBT_F_L2A: DSVCU_LAUNCH(k_fwd_lift<SBT_F_L2A>, tg, SBT_THREADS, 0, c->stream, L); break;
-            case SBT_F_L1: DSVCU_LAUNCH(k_fwd_l1, tg, SBT_THREADS, 0, c->stream, L); break;
-            case SBT_F_LOSSLESS: DSVCU_LAUNCH(k_fwd_lift<SBT_F_LOSSLESS>, tg, SBT_THREADS, 0, c->stream, L); break;
-            default:
-                DSVCU_LAUNCH(k_fwd_haar, grid_for(L.cw * L.ch, 256), 256, 0, c->stream, L);
-                break;
-        }
-        CK_LAUNCH(c);
-    }
-    return 0;
+    return sbt_run(c, src, dst, 0, fm, 1 << plane, 1);
+}
+
+/* all three planes of a picture through the same launches */
+extern "C" int
+dsvcu_inv_sbt_frame(dsvcu_ctx *c, dsvcu_frame *dst, dsvcu_coefs *src, int q, const dsvcu_fmeta *fm, int plane_mask)
+{
+    return sbt_run(c, dst, src, q, fm, plane_mask & 7, 0);
+}
+
+extern "C" int
+dsvcu_fwd_sbt_frame(dsvcu_ctx *c, dsvcu_frame *src, dsvcu_coefs *dst, const dsvcu_fmeta *fm, int plane_mask)
+{
+    return sbt_run(c, src, dst, 0, fm, plane_mask & 7, 1);
 }
 
 /* ------------------------------------------------------------- quantisation */

@@ -147,12 +147,11 @@ sbt_hi_term(const int32_t *v, int s, int base, int i, int n)
 /* --------------------------------------------------- inverse lifting level */
 
 template <int F>
-DSVCU_KERNEL void __launch_bounds__(SBT_THREADS)
-k_inv_lift(SbtLevel L)
+DSVCU_DEV void
+sbt_inv_lift_tile(const SbtLevel &L, int32_t *t, int tile_x, int tile_y)
 {
-    DSVCU_SHARED int32_t t[SBT_SH * SBT_SW];
-    const int X0 = (int) blockIdx.x * SBT_TW - SBT_HALO;
-    const int Y0 = (int) blockIdx.y * SBT_TH - SBT_HALO;
+    const int X0 = tile_x * SBT_TW - SBT_HALO;
+    const int Y0 = tile_y * SBT_TH - SBT_HALO;
     const int sw = L.sw, sh = L.sh, cw = L.cw, ch = L.ch, fw = L.fw;
     const int even_w = sw & ~1, even_h = sh & ~1;
 
@@ -275,12 +274,11 @@ sbt_fwd_fetch(const SbtLevel &L, int X, int Y)
 }
 
 template <int F>
-DSVCU_KERNEL void __launch_bounds__(SBT_THREADS)
-k_fwd_lift(SbtLevel L)
+DSVCU_DEV void
+sbt_fwd_lift_tile(const SbtLevel &L, int32_t *t, int tile_x, int tile_y)
 {
-    DSVCU_SHARED int32_t t[SBT_SH * SBT_SW];
-    const int X0 = (int) blockIdx.x * SBT_TW - SBT_HALO;
-    const int Y0 = (int) blockIdx.y * SBT_TH - SBT_HALO;
+    const int X0 = tile_x * SBT_TW - SBT_HALO;
+    const int Y0 = tile_y * SBT_TH - SBT_HALO;
     const int sw = L.sw, sh = L.sh, cw = L.cw, ch = L.ch, fw = L.fw;
     const int even_w = sw & ~1, even_h = sh & ~1;
 
@@ -401,13 +399,12 @@ sbt_asf_sample(const int32_t *v, int s, int base, int i, int n, int ring)
 #undef V
 }
 
-DSVCU_KERNEL void __launch_bounds__(SBT_THREADS)
-k_fwd_l1(SbtLevel L)
+DSVCU_DEV void
+sbt_fwd_l1_tile(const SbtLevel &L, int32_t *t, int tile_x, int tile_y)
 {
-    DSVCU_SHARED int32_t t[SBT_SH * SBT_SW];
-    DSVCU_SHARED int32_t u[SBT_SH * SBT_SW];
-    const int X0 = (int) blockIdx.x * SBT_TW - SBT_HALO;
-    const int Y0 = (int) blockIdx.y * SBT_TH - SBT_HALO;
+    int32_t *u = t + SBT_SH * SBT_SW;
+    const int X0 = tile_x * SBT_TW - SBT_HALO;
+    const int Y0 = tile_y * SBT_TH - SBT_HALO;
     const int sw = L.sw, sh = L.sh, cw = L.cw, ch = L.ch, fw = L.fw;
 
     /* the horizontal FIR needs +-4 columns around every column of the tile
@@ -463,15 +460,15 @@ k_fwd_l1(SbtLevel L)
 /* Inverse Haar, one thread per 2x2 output cell (sbt.c:615-795).  FILTERED
  * selects the LL-gradient-guided nudge of LH/HL (C.3.1.2). */
 template <bool FILTERED>
-DSVCU_KERNEL void __launch_bounds__(256)
-k_inv_haar(SbtLevel L)
+DSVCU_DEV void
+sbt_inv_haar_cells(const SbtLevel &L, int cta, int ncta)
 {
     const int sw = L.sw, sh = L.sh, cw = L.cw, ch = L.ch, fw = L.fw;
     const int oddw = sw & 1, oddh = sh & 1;
     const int ncx = cw, ncy = ch; /* cells incl. the odd remainder column/row */
     const int total = ncx * ncy;
     const int ovf = L.ovf;
-    for (int k = (int) blockIdx.x * DSVCU_NTH + DSVCU_TID; k < total; k += (int) gridDim.x * DSVCU_NTH) {
+    for (int k = cta * DSVCU_NTH + DSVCU_TID; k < total; k += ncta * DSVCU_NTH) {
         int cy = k / ncx, cx = k - cy * ncx;
         int x = cx * 2, y = cy * 2;
         int fullx = (x < sw - oddw), fully = (y < sh - oddh);
@@ -556,14 +553,14 @@ k_inv_haar(SbtLevel L)
 }
 
 /* Forward Haar (sbt.c:546-612) */
-DSVCU_KERNEL void __launch_bounds__(256)
-k_fwd_haar(SbtLevel L)
+DSVCU_DEV void
+sbt_fwd_haar_cells(const SbtLevel &L, int cta, int ncta)
 {
     const int sw = L.sw, sh = L.sh, cw = L.cw, ch = L.ch, fw = L.fw;
     const int oddw = sw & 1, oddh = sh & 1;
     const int total = cw * ch;
     const int dv = L.ovf ? 2 : 1;
-    for (int k = (int) blockIdx.x * DSVCU_NTH + DSVCU_TID; k < total; k += (int) gridDim.x * DSVCU_NTH) {
+    for (int k = cta * DSVCU_NTH + DSVCU_TID; k < total; k += ncta * DSVCU_NTH) {
         int cy = k / cw, cx = k - cy * cw;
         int x = cx * 2, y = cy * 2;
         int fullx = (x < sw - oddw), fully = (y < sh - oddh);
@@ -584,6 +581,101 @@ k_fwd_haar(SbtLevel L)
             L.out_bands[cy * fw + cw + cx] = 2 * (x0 - x1);
         } else {
             L.out_ll[cy * fw + cx] = (x0 * 4) / dv;
+        }
+    }
+}
+
+/* ------------------------------------------------------------ fused launches
+ *
+ * One launch transforms one level of up to three planes (their CTAs back to
+ * back in the grid), or -- for the small top of the pyramid, where a level is
+ * one or two tiles -- ALL remaining levels of each plane with one CTA per
+ * plane, the LL image ping-ponging between the plane's two scratch buffers
+ * behind a CTA barrier.  1080p: 6 launches per picture and direction instead
+ * of 31. */
+#define SBT_MAX_FUSED 10
+
+struct SbtPlaneJob {
+    SbtLevel L[SBT_MAX_FUSED]; /* in execution order */
+    int f[SBT_MAX_FUSED];
+    int nlev;                  /* > 1 only with ncta == 1 */
+    int first_cta, ncta;
+};
+
+struct SbtJob {
+    SbtPlaneJob p[3];
+    int nplanes;
+};
+
+DSVCU_HD int
+sbt_level_tiles(const SbtLevel &L)
+{
+    return ((L.sw + SBT_TW - 1) / SBT_TW) * ((L.sh + SBT_TH - 1) / SBT_TH);
+}
+
+#define SBT_TILE_LOOP(call)                                              \
+    do {                                                                 \
+        const int ntx_ = (L.sw + SBT_TW - 1) / SBT_TW;                   \
+        const int nt_ = sbt_level_tiles(L);                              \
+        for (int tile_ = cta; tile_ < nt_; tile_ += P.ncta) {            \
+            call(L, t, tile_ % ntx_, tile_ / ntx_);                      \
+            DSVCU_SYNC(); /* the tile buffer is reused */                \
+        }                                                                \
+    } while (0)
+
+DSVCU_KERNEL void __launch_bounds__(SBT_THREADS)
+k_sbt_inv(SbtJob J)
+{
+    DSVCU_SHARED int32_t t[SBT_SH * SBT_SW];
+    int pl = 0;
+    while (pl + 1 < J.nplanes && (int) blockIdx.x >= J.p[pl + 1].first_cta) pl++;
+    const SbtPlaneJob &P = J.p[pl];
+    const int cta = (int) blockIdx.x - P.first_cta;
+    for (int lv = 0; lv < P.nlev; lv++) {
+        const SbtLevel &L = P.L[lv];
+        switch (P.f[lv]) {
+            case SBT_F_LLI: SBT_TILE_LOOP(sbt_inv_lift_tile<SBT_F_LLI>); break;
+            case SBT_F_LLP: SBT_TILE_LOOP(sbt_inv_lift_tile<SBT_F_LLP>); break;
+            case SBT_F_CC: SBT_TILE_LOOP(sbt_inv_lift_tile<SBT_F_CC>); break;
+            case SBT_F_L2A: SBT_TILE_LOOP(sbt_inv_lift_tile<SBT_F_L2A>); break;
+            case SBT_F_L1: SBT_TILE_LOOP(sbt_inv_lift_tile<SBT_F_L1>); break;
+            case SBT_F_LOSSLESS: SBT_TILE_LOOP(sbt_inv_lift_tile<SBT_F_LOSSLESS>); break;
+            case SBT_F_HAAR: sbt_inv_haar_cells<true>(L, cta, P.ncta); break;
+            default: sbt_inv_haar_cells<false>(L, cta, P.ncta); break;
+        }
+        if (lv + 1 < P.nlev) {
+#ifndef DSVCU_EMU
+            __threadfence_block();
+#endif
+            DSVCU_SYNC();
+        }
+    }
+}
+
+DSVCU_KERNEL void __launch_bounds__(SBT_THREADS)
+k_sbt_fwd(SbtJob J)
+{
+    DSVCU_SHARED int32_t t[2 * SBT_SH * SBT_SW];
+    int pl = 0;
+    while (pl + 1 < J.nplanes && (int) blockIdx.x >= J.p[pl + 1].first_cta) pl++;
+    const SbtPlaneJob &P = J.p[pl];
+    const int cta = (int) blockIdx.x - P.first_cta;
+    for (int lv = 0; lv < P.nlev; lv++) {
+        const SbtLevel &L = P.L[lv];
+        switch (P.f[lv]) {
+            case SBT_F_LLI: SBT_TILE_LOOP(sbt_fwd_lift_tile<SBT_F_LLI>); break;
+            case SBT_F_LLP: SBT_TILE_LOOP(sbt_fwd_lift_tile<SBT_F_LLP>); break;
+            case SBT_F_CC: SBT_TILE_LOOP(sbt_fwd_lift_tile<SBT_F_CC>); break;
+            case SBT_F_L2A: SBT_TILE_LOOP(sbt_fwd_lift_tile<SBT_F_L2A>); break;
+            case SBT_F_L1: SBT_TILE_LOOP(sbt_fwd_l1_tile); break;
+            case SBT_F_LOSSLESS: SBT_TILE_LOOP(sbt_fwd_lift_tile<SBT_F_LOSSLESS>); break;
+            default: sbt_fwd_haar_cells(L, cta, P.ncta); break;
+        }
+        if (lv + 1 < P.nlev) {
+#ifndef DSVCU_EMU
+            __threadfence_block();
+#endif
+            DSVCU_SYNC();
         }
     }
 }

@@ -298,7 +298,7 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
     DSV_FRAME *host;
     DSV_FNUM fno;
     int stats[DSV_MAX_STAT];
-    int i, nblk, quant, is_ref, do_filter, isP;
+    int i, nblk, quant, is_ref, do_filter, isP, good_planes = 0;
 
     memset(p, 0, sizeof(*p));
     p->vidmeta = meta;
@@ -377,10 +377,12 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
             continue;
         }
         GPU(dsvcu_dequant_plane(s->ctx, s->coefs, i, quant, &fm, nsym, lstart, dc));
-        GPU(dsvcu_inv_sbt(s->ctx, isP ? s->resd : dst, i, s->coefs, quant, &fm));
-        if (!isP) {
-            GPU(dsvcu_intra_filter(s->ctx, quant, &fm, i, dst, do_filter));
-        }
+        good_planes |= 1 << i;
+    }
+    /* the planes that decoded go through the inverse transform together */
+    GPU(dsvcu_inv_sbt_frame(s->ctx, isP ? s->resd : dst, s->coefs, quant, &fm, good_planes));
+    if (!isP && (good_planes & 1)) {
+        GPU(dsvcu_intra_filter(s->ctx, quant, &fm, 0, dst, do_filter));
     }
     *fn = fno;
     if (isP) {

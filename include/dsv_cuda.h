@@ -90,6 +90,10 @@ int dsvcu_set_mvs(dsvcu_ctx *ctx, const void *dsv_mv_array, int nblocks);
 int dsvcu_fwd_sbt(dsvcu_ctx *ctx, dsvcu_frame *src, int plane, dsvcu_coefs *dst, const dsvcu_fmeta *fm);
 /* dsv_inv_sbt, reference sbt.c:889-934 (dsv_internal.h:113) */
 int dsvcu_inv_sbt(dsvcu_ctx *ctx, dsvcu_frame *dst, int plane, dsvcu_coefs *src, int q, const dsvcu_fmeta *fm);
+/* the planes selected by plane_mask (bit p = plane p) through shared launches: same results as
+ * the per-plane calls, one launch per pyramid level for all of them */
+int dsvcu_fwd_sbt_frame(dsvcu_ctx *ctx, dsvcu_frame *src, dsvcu_coefs *dst, const dsvcu_fmeta *fm, int plane_mask);
+int dsvcu_inv_sbt_frame(dsvcu_ctx *ctx, dsvcu_frame *dst, dsvcu_coefs *src, int q, const dsvcu_fmeta *fm, int plane_mask);
 
 /* ---- quantisation: arithmetic half of dsv_encode_plane / dsv_decode_plane ---- */
 /* reference hzcc.c:254-448 (quantise in place, leave the de-quantised value,
