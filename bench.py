@@ -293,7 +293,7 @@ def kernel_rooflines(P, lib, peak_gbs):
     nl = (lib.dsvcu_launch_count(ctx) - l0) // (RING * 4)
     add("fwd_sbt (P picture, 3 planes per launch: k_sbt_fwd)", t, 5 * Pb, nl)
     l0 = lib.dsvcu_launch_count(ctx)
-    t = timed(all_planes(lambda i, p: lib.dsvcu_quant_plane(ctx, coefs[i], p, q, C.byref(fmP))))
+    t = timed(lambda i: lib.dsvcu_quant_frame(ctx, coefs[i], q, C.byref(fmP), 7))
     nl = (lib.dsvcu_launch_count(ctx) - l0) // (RING * 4)
     add("quantise + symbol compaction (k_quant_*, k_compact_*)", t, 8 * Pb, nl)
     l0 = lib.dsvcu_launch_count(ctx)

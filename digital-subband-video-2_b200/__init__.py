@@ -179,6 +179,7 @@ def load(emu=False):
         "dsvcu_fwd_sbt_frame": (ip, [vp, vp, vp, P(DSVCU_FMETA), ip]),
         "dsvcu_inv_sbt_frame": (ip, [vp, vp, vp, ip, P(DSVCU_FMETA), ip]),
         "dsvcu_quant_plane": (ip, [vp, vp, ip, ip, P(DSVCU_FMETA)]),
+        "dsvcu_quant_frame": (ip, [vp, vp, ip, P(DSVCU_FMETA), ip]),
         "dsvcu_fetch_symbols": (ip, [vp, ip, P(P(DSVCU_SYMBOL)), P(ip), P(ip)]),
         "dsvcu_symbol_staging": (P(DSVCU_SYMBOL), [vp, ip, P(ip)]),
         "dsvcu_dequant_plane": (ip, [vp, vp, ip, ip, P(DSVCU_FMETA), ip, P(ip), ip]),

@@ -41,6 +41,7 @@ dsvcu_more_connections(void)
 #endif
 
 static char g_err[256] = "";
+static int uniform_carveout(int device);
 static int g_pre_cap = getenv("DSVCU_PRE_GRID") ? atoi(getenv("DSVCU_PRE_GRID")) : 0; /* experiments: cap the prepass grid */
 static int g_me_smem = getenv("DSVCU_ME_SMEM") ? atoi(getenv("DSVCU_ME_SMEM")) : 0; /* experiments: pad the search kernel's shared memory to limit co-residency */
 static long long g_launches = 0; /* kernels launched by every context of this process */
@@ -107,8 +108,8 @@ struct dsvcu_ctx {
      * three planes of a picture are transformed by the same launches) */
     int32_t *scratch[3][2];
     /* quantiser outputs */
-    int32_t *d_qv;
-    int *d_chunk;
+    int32_t *d_qv[3];     /* dense scan-order quantiser output, per plane */
+    int *d_chunk[3];
     int *d_meta;          /* [0..2] nsyms, [3..5] dc */
     int *h_meta;          /* pinned mirror */
     dsvcu_sym *d_syms[3];
@@ -246,6 +247,7 @@ dsvcu_ctx_create(dsvcu_ctx **out, int device, int width, int height, int subsamp
     c->subsamp = subsamp;
     coef_dims(subsamp, width, height, c->cw, c->ch);
 #ifndef DSVCU_EMU
+    if (uniform_carveout(device)) return -1;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
@@ -260,8 +262,11 @@ dsvcu_ctx_create(dsvcu_ctx **out, int device, int width, int height, int subsamp
         CK(dsvcu_malloc(&c->scratch[i][0], (size_t) c->cw[i] * c->ch[i] * sizeof(int32_t)));
         CK(dsvcu_malloc(&c->scratch[i][1], (size_t) c->cw[i] * c->ch[i] * sizeof(int32_t)));
     }
-    CK(dsvcu_malloc(&c->d_qv, (maxplane + CMP_CHUNK) * sizeof(int32_t)));
-    CK(dsvcu_malloc(&c->d_chunk, (maxplane / CMP_CHUNK + 2) * sizeof(int)));
+    for (i = 0; i < 3; i++) {
+        size_t pn = (size_t) c->cw[i] * c->ch[i];
+        CK(dsvcu_malloc(&c->d_qv[i], (pn + CMP_CHUNK) * sizeof(int32_t)));
+        CK(dsvcu_malloc(&c->d_chunk[i], (pn / CMP_CHUNK + 2) * sizeof(int)));
+    }
     CK(dsvcu_malloc(&c->d_meta, 8 * sizeof(int)));
     CK(dsvcu_malloc_host(&c->h_meta, 8 * sizeof(int)));
     for (i = 0; i < 3; i++) {
@@ -293,8 +298,10 @@ dsvcu_ctx_destroy(dsvcu_ctx *c)
         dsvcu_free_dev(c->scratch[i][0]);
         dsvcu_free_dev(c->scratch[i][1]);
     }
-    dsvcu_free_dev(c->d_qv);
-    dsvcu_free_dev(c->d_chunk);
+    for (i = 0; i < 3; i++) {
+        dsvcu_free_dev(c->d_qv[i]);
+        dsvcu_free_dev(c->d_chunk[i]);
+    }
     dsvcu_free_dev(c->d_meta);
     dsvcu_free_host(c->h_meta);
     for (i = 0; i < 3; i++) {
@@ -982,46 +989,89 @@ quant_level_geom(QuantLevel *Q, dsvcu_ctx *c, dsvcu_coefs *k, int plane, int q, 
     }
 }
 
-extern "C" int
-dsvcu_quant_plane(dsvcu_ctx *c, dsvcu_coefs *k, int plane, int q, const dsvcu_fmeta *fm)
+/* Quantise the planes in `mask` with shared launches (bit p = plane p): the LL
+ * part, three levels (+ their aliased edges), then the ordered compaction of the
+ * non-zero symbols into pinned host memory -- 10 launches whatever the number of
+ * planes.  Level order inside a plane is a data dependency (a child reads its
+ * quantised parent); planes are independent. */
+static int
+quant_run(dsvcu_ctx *c, dsvcu_coefs *k, int q, const dsvcu_fmeta *fm, int mask)
 {
-    const int w = k->w[plane], h = k->h[plane];
-    int part[5], total, l, nchunks;
-    QuantLevel Q;
+    QuantJob J;
+    CompactJob CJ;
+    int part[3][5], total[3], pl[3], n = 0, l, i, gmax, emax, cmax = 0;
     int qf = q * 3 / 2; /* fix_quant, hzcc.c:59-63 */
 
-    total = dsvcu_scan_layout(w, h, part);
-    /* the DC coefficient is sent raw */
-    CK(dsvcu_d2h_async(c->h_meta + 3 + plane, k->data[plane], sizeof(int), c->stream));
-    quant_level_geom(&Q, c, k, plane, qf, fm, -1, part);
-    Q.qv = c->d_qv;
-    DSVCU_LAUNCH(k_quant_ll, grid_for(Q.w * Q.h, 256), 256, 0, c->stream, Q, fm->lossless ? 1 : lfquant(qf, plane, fm));
+    for (i = 0; i < 3; i++) {
+        if (mask & (1 << i)) pl[n++] = i;
+    }
+    if (!n) return 0;
+    memset(&CJ, 0, sizeof(CJ));
+    gmax = 1;
+    for (i = 0; i < n; i++) {
+        const int p = pl[i];
+        total[i] = dsvcu_scan_layout(k->w[p], k->h[p], part[i]);
+        quant_level_geom(&J.Q[i], c, k, p, qf, fm, -1, part[i]);
+        J.Q[i].qv = c->d_qv[p];
+        J.lfq[i] = fm->lossless ? 1 : lfquant(qf, p, fm);
+        gmax = max(gmax, grid_for(J.Q[i].w * J.Q[i].h, 256));
+    }
+    DSVCU_LAUNCH(k_quant_ll, dim3(gmax, 1, n), 256, 0, c->stream, J);
     CK_LAUNCH(c);
     for (l = 0; l < 3; l++) {
-        quant_level_geom(&Q, c, k, plane, qf, fm, l, part);
-        Q.qv = c->d_qv;
-        DSVCU_LAUNCH(k_quant_hf, dim3(grid_for(Q.w * Q.h, 256), 3, 1), 256, 0, c->stream, Q);
+        gmax = emax = 1;
+        for (i = 0; i < n; i++) {
+            quant_level_geom(&J.Q[i], c, k, pl[i], qf, fm, l, part[i]);
+            J.Q[i].qv = c->d_qv[pl[i]];
+            gmax = max(gmax, grid_for(J.Q[i].w * J.Q[i].h, 256));
+            emax = max(emax, grid_for(J.Q[i].w + J.Q[i].h, 256));
+        }
+        DSVCU_LAUNCH(k_quant_hf, dim3(gmax, 3, n), 256, 0, c->stream, J);
         CK_LAUNCH(c);
         if (!fm->lossless) {
-            DSVCU_LAUNCH(k_quant_hf_edge, dim3(grid_for(Q.w + Q.h, 256), 3, 1), 256, 0, c->stream, Q);
+            DSVCU_LAUNCH(k_quant_hf_edge, dim3(emax, 3, n), 256, 0, c->stream, J);
             CK_LAUNCH(c);
         }
     }
-    nchunks = (total + CMP_CHUNK - 1) / CMP_CHUNK;
-    DSVCU_LAUNCH(k_compact_count, nchunks, CMP_THREADS, 0, c->stream, c->d_qv, total, c->d_chunk);
+    /* the symbol count, the DC coefficient and the ordered (position, value)
+     * list are written by the kernels straight into pinned host memory
+     * (unified addressing): the host entropy coder needs nothing else, so one
+     * event is all it waits for while the GPU carries on with the inverse
+     * transform */
+    for (i = 0; i < n; i++) {
+        const int p = pl[i];
+        CJ.qv[i] = c->d_qv[p];
+        CJ.n[i] = total[i];
+        CJ.chunk[i] = c->d_chunk[p];
+        CJ.nchunks[i] = (total[i] + CMP_CHUNK - 1) / CMP_CHUNK;
+        CJ.out[i] = c->h_syms[p];
+        CJ.out_n[i] = c->h_meta + p;
+        CJ.dc_src[i] = k->data[p];
+        CJ.dc_dst[i] = c->h_meta + 3 + p;
+        cmax = max(cmax, CJ.nchunks[i]);
+    }
+    DSVCU_LAUNCH(k_compact_count, dim3(cmax, n, 1), CMP_THREADS, 0, c->stream, CJ);
     CK_LAUNCH(c);
-    /* the symbol count and the ordered (position, value) list are written by
-     * the kernels straight into pinned host memory (unified addressing): the
-     * host entropy coder needs nothing else from this plane, so one event is
-     * all it waits for while the GPU carries on with the inverse transform */
-    DSVCU_LAUNCH(k_compact_scan, 1, 1024, 0, c->stream, c->d_chunk, nchunks, c->h_meta + plane);
+    DSVCU_LAUNCH(k_compact_scan, n, 1024, 0, c->stream, CJ);
     CK_LAUNCH(c);
-    DSVCU_LAUNCH(k_compact_scatter, nchunks, CMP_THREADS, 0, c->stream, c->d_qv, total, c->d_chunk, c->h_syms[plane]);
+    DSVCU_LAUNCH(k_compact_scatter, dim3(cmax, n, 1), CMP_THREADS, 0, c->stream, CJ);
     CK_LAUNCH(c);
 #ifndef DSVCU_EMU
-    CK(cudaEventRecord(c->ev_sym[plane], c->stream));
+    for (i = 0; i < n; i++) CK(cudaEventRecord(c->ev_sym[pl[i]], c->stream));
 #endif
     return 0;
+}
+
+extern "C" int
+dsvcu_quant_plane(dsvcu_ctx *c, dsvcu_coefs *k, int plane, int q, const dsvcu_fmeta *fm)
+{
+    return quant_run(c, k, q, fm, 1 << plane);
+}
+
+extern "C" int
+dsvcu_quant_frame(dsvcu_ctx *c, dsvcu_coefs *k, int q, const dsvcu_fmeta *fm, int plane_mask)
+{
+    return quant_run(c, k, q, fm, plane_mask & 7);
 }
 
 extern "C" int
@@ -1625,5 +1675,49 @@ dsvcu_frame_luma_avg(dsvcu_ctx *c, dsvcu_frame *f, unsigned *avg)
     if (dsvcu_frame_luma_avg_async(c, f)) return -1;
     CK(ctx_wait(c));
     *avg = dsvcu_frame_luma_avg_result(c);
+    return 0;
+}
+
+/* ------------------------------------------------------ shared-memory carve-out
+ *
+ * An SM switches its L1 / shared-memory split only when it is empty.  With tens
+ * of encoder instances the CTAs of twenty different kernels want to share SMs;
+ * if every kernel asked for its own split they could only follow each other.
+ * All kernels of the library therefore ask for the same carve-out (enough for
+ * four search CTAs or the filter's largest job), once per device. */
+static int
+uniform_carveout(int device)
+{
+#ifndef DSVCU_EMU
+    static int done[64];
+    static const int pct = getenv("DSVCU_CARVEOUT") ? atoi(getenv("DSVCU_CARVEOUT")) : 58;
+    if (device < 0 || device >= 64 || done[device] || pct < 0) return 0;
+#define CARVE(k) CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct))
+    CARVE(k_compact_count);
+    CARVE(k_compact_scan);
+    CARVE(k_compact_scatter);
+    CARVE(k_dequant_hf);
+    CARVE(k_dequant_ll);
+    CARVE(k_ds2x);
+    CARVE(k_extend);
+    CARVE(k_filter_skew);
+    CARVE(k_intra_analysis);
+    CARVE(k_me_global);
+    CARVE(k_me_level);
+    CARVE(k_me_prepass);
+    CARVE(k_post_sharpen);
+    CARVE(k_predict);
+    CARVE(k_quant_hf);
+    CARVE(k_quant_hf_edge);
+    CARVE(k_quant_ll);
+    CARVE(k_reconstruct);
+    CARVE(k_sbt_fwd);
+    CARVE(k_sbt_inv);
+    CARVE(k_luma_avg);
+#undef CARVE
+    done[device] = 1;
+#else
+    (void) device;
+#endif
     return 0;
 }

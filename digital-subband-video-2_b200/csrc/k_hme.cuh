@@ -36,6 +36,9 @@
 #ifndef ME_PRE_MIN_CTAS
 #define ME_PRE_MIN_CTAS 4
 #endif
+#ifndef ME_POLL_NS_CTA
+#define ME_POLL_NS_CTA 128 /* same, for rows whose predecessor is in the same CTA */
+#endif
 #ifndef ME_POLL_NS
 #define ME_POLL_NS 256 /* back-off between polls of the row above (a block takes ~30 us) */
 #endif
@@ -1940,7 +1943,10 @@ k_me_level(MeArgs A)
 #endif
             if (seen < need) {
                 while ((seen = *above) < need) {
-                    if (above_global) __nanosleep(ME_POLL_NS); /* leave the issue slots to warps that have work */
+                    /* leave the issue slots to warps that have work: a row that polls
+                     * shared memory without pausing takes a third of its scheduler
+                     * from the row it is waiting for */
+                    __nanosleep(above_global ? ME_POLL_NS : ME_POLL_NS_CTA);
                 }
                 if (above_global) {
                     __threadfence();

@@ -83,6 +83,23 @@ struct QuantLevel {
     QuantBand band[3];
 };
 
+/* up to three planes per launch: blockIdx.z selects the plane */
+struct QuantJob {
+    QuantLevel Q[3];
+    int lfq[3]; /* LL step size per plane */
+};
+
+struct CompactJob {
+    const int32_t *qv[3];
+    int n[3];
+    int *chunk[3];
+    int nchunks[3];
+    dsvcu_sym *out[3];
+    int *out_n[3];            /* pinned host: symbol count */
+    const int32_t *dc_src[3]; /* the plane's DC coefficient ... */
+    int *dc_dst[3];           /* ... and where the host wants it */
+};
+
 DSVCU_HD int q_sub(int v, int q, int sub) { return ((v >= 0) ? v - sub : v + sub) / q; }
 DSVCU_HD int q_deq_s(int v, int q) { return v * q + ((v < 0) ? -(q * 2 / 3) : (q * 2 / 3)); }
 DSVCU_HD int q_deq_d(int v, int q) { return v * q + ((v < 0) ? -(q / 2) : (q / 2)); }
@@ -124,8 +141,10 @@ q_parent_aliased(const QuantLevel &Q, const QuantBand &B, int x, int y)
 
 /* LL part: one step size, no parents (hzcc.c:308-328; lossless :269-283) */
 DSVCU_KERNEL void __launch_bounds__(256)
-k_quant_ll(QuantLevel Q, int qp)
+k_quant_ll(QuantJob J)
 {
+    const QuantLevel &Q = J.Q[blockIdx.z];
+    const int qp = J.lfq[blockIdx.z];
     const int total = Q.w * Q.h;
     for (int k = (int) blockIdx.x * DSVCU_NTH + DSVCU_TID; k < total; k += (int) gridDim.x * DSVCU_NTH) {
         int y = k / Q.w, x = k - y * Q.w;
@@ -208,8 +227,9 @@ quant_hf_one(const QuantLevel &Q, const QuantBand &B, int x, int y)
 
 /* wave A: every element of the three rectangles whose parent is final */
 DSVCU_KERNEL void __launch_bounds__(256)
-k_quant_hf(QuantLevel Q)
+k_quant_hf(QuantJob J)
 {
+    const QuantLevel &Q = J.Q[blockIdx.z];
     const QuantBand B = Q.band[blockIdx.y];
     const int total = Q.w * Q.h;
     for (int k = (int) blockIdx.x * DSVCU_NTH + DSVCU_TID; k < total; k += (int) gridDim.x * DSVCU_NTH) {
@@ -223,8 +243,9 @@ k_quant_hf(QuantLevel Q)
 
 /* wave B: last column + last row of each rectangle, only if aliased */
 DSVCU_KERNEL void __launch_bounds__(256)
-k_quant_hf_edge(QuantLevel Q)
+k_quant_hf_edge(QuantJob J)
 {
+    const QuantLevel &Q = J.Q[blockIdx.z];
     const QuantBand B = Q.band[blockIdx.y];
     const int total = Q.w + Q.h - 1;
     for (int k = (int) blockIdx.x * DSVCU_NTH + DSVCU_TID; k < total; k += (int) gridDim.x * DSVCU_NTH) {
@@ -249,9 +270,13 @@ k_quant_hf_edge(QuantLevel Q)
 
 /* pass 1: non-zero count per chunk of the dense scan-order array */
 DSVCU_KERNEL void __launch_bounds__(CMP_THREADS)
-k_compact_count(const int32_t *qv, int n, int *chunk_count)
+k_compact_count(CompactJob J)
 {
     DSVCU_SHARED int cnt;
+    const int32_t *qv = J.qv[blockIdx.y];
+    const int n = J.n[blockIdx.y];
+    int *chunk_count = J.chunk[blockIdx.y];
+    if ((int) blockIdx.x >= J.nchunks[blockIdx.y]) return;
     int base = (int) blockIdx.x * CMP_CHUNK;
     int lim = min(n, base + CMP_CHUNK);
     int local = 0;
@@ -267,9 +292,12 @@ k_compact_count(const int32_t *qv, int n, int *chunk_count)
 
 /* pass 2: exclusive scan of the chunk counts (single block), total -> *out_n */
 DSVCU_KERNEL void __launch_bounds__(1024)
-k_compact_scan(int *chunk_count, int nchunks, int *out_n)
+k_compact_scan(CompactJob J)
 {
     DSVCU_SHARED int part[1024];
+    int *chunk_count = J.chunk[blockIdx.x];
+    const int nchunks = J.nchunks[blockIdx.x];
+    int *out_n = J.out_n[blockIdx.x];
     int per = (nchunks + DSVCU_NTH - 1) / DSVCU_NTH;
     int b = DSVCU_TID * per, e = min(nchunks, b + per);
     int s = 0;
@@ -284,6 +312,7 @@ k_compact_scan(int *chunk_count, int nchunks, int *out_n)
             acc += v;
         }
         *out_n = acc;
+        *J.dc_dst[blockIdx.x] = *J.dc_src[blockIdx.x]; /* the DC coefficient is sent raw */
     }
     DSVCU_SYNC();
     s = part[DSVCU_TID];
@@ -300,11 +329,16 @@ k_compact_scan(int *chunk_count, int nchunks, int *out_n)
  * symbols: the destination is pinned HOST memory, where scattered 8-byte
  * stores would each become their own PCIe write. */
 DSVCU_KERNEL void __launch_bounds__(CMP_THREADS)
-k_compact_scatter(const int32_t *qv, int n, const int *chunk_off, dsvcu_sym *out)
+k_compact_scatter(CompactJob J)
 {
     DSVCU_SHARED int part[CMP_THREADS];
     DSVCU_SHARED dsvcu_sym stage[CMP_CHUNK];
     DSVCU_SHARED int total;
+    const int32_t *qv = J.qv[blockIdx.y];
+    const int n = J.n[blockIdx.y];
+    const int *chunk_off = J.chunk[blockIdx.y];
+    dsvcu_sym *out = J.out[blockIdx.y];
+    if ((int) blockIdx.x >= J.nchunks[blockIdx.y]) return;
     int base = (int) blockIdx.x * CMP_CHUNK;
     int per = CMP_CHUNK / DSVCU_NTH;
     int b = base + DSVCU_TID * per, e = min(n, b + per);

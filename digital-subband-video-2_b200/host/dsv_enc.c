@@ -1042,9 +1042,7 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
         GPU(dsvcu_sub_pred(g->ctx, &fm, g->pred, rec, ref_rec));
     }
     GPU(dsvcu_fwd_sbt_frame(g->ctx, rec, g->coefs, &fm, 7));
-    for (i = 0; i < 3; i++) {
-        GPU(dsvcu_quant_plane(g->ctx, g->coefs, i, quant, &fm));
-    }
+    GPU(dsvcu_quant_frame(g->ctx, g->coefs, quant, &fm, 7));
     GPU(dsvcu_inv_sbt_frame(g->ctx, rec, g->coefs, quant, &fm, 7));
     if (!p->has_ref) {
         GPU(dsvcu_intra_filter(g->ctx, quant, &fm, 0, rec, enc->do_intra_filter));

@@ -99,6 +99,8 @@ int dsvcu_inv_sbt_frame(dsvcu_ctx *ctx, dsvcu_frame *dst, dsvcu_coefs *src, int 
 /* reference hzcc.c:254-448 (quantise in place, leave the de-quantised value,
  * produce the ordered symbol list on the device) */
 int dsvcu_quant_plane(dsvcu_ctx *ctx, dsvcu_coefs *c, int plane, int q, const dsvcu_fmeta *fm);
+/* the planes selected by plane_mask through shared launches (same results as the per-plane calls) */
+int dsvcu_quant_frame(dsvcu_ctx *ctx, dsvcu_coefs *c, int q, const dsvcu_fmeta *fm, int plane_mask);
 /* wait for the symbols of `plane`; pointers stay valid until the next quant of
  * that plane.  *dc receives coefficient 0 (sent raw, hzcc.c:599-602) */
 int dsvcu_fetch_symbols(dsvcu_ctx *ctx, int plane, const dsvcu_symbol **syms, int *nsyms, int *dc);
