@@ -27,7 +27,9 @@
 #include "dsvcu_rt.h"
 #include "k_quant.cuh"
 
+#ifndef ME_WARPS_PER_CTA
 #define ME_WARPS_PER_CTA 8
+#endif
 /* residency targets (CTAs per SM) the register allocation is held to: with many
  * encoder instances on one GPU the register file is what runs out first */
 #ifndef ME_MIN_CTAS
@@ -1339,9 +1341,22 @@ me_ref_stats(const MeArgs &A, MeRefStats *R, const uint8_t *srcd, int i, int j, 
 
 /* neighbour-independent half of refine_level's block loop, all blocks of the
  * level in parallel (one warp per block) */
+/* ME_PHASE: optional CTA barrier between the phases of the prepass, so that the
+ * eight warps of a CTA walk the same stretch of this very long kernel at the
+ * same time and share its instruction fetches (`ps` is CTA-uniform) */
+#if defined(ME_PRE_PHASE_SYNC) && !defined(DSVCU_EMU)
+#define ME_PHASE()            \
+    do {                      \
+        if (ps) __syncthreads(); \
+    } while (0)
+#else
+#define ME_PHASE() ((void) 0)
+#endif
+
 DSVCU_DEV void
-me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j)
+me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j, bool ps)
 {
+    (void) ps;
     const int level = A.level;
     const MePlane &sp = A.src[0], &rp = A.ref[0];
     const int gx = A.gxy[0], gy = A.gxy[1];
@@ -1355,6 +1370,7 @@ me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j)
     MePsy psy;
     me_src_stats(A, S, srcd, sp.stride, bw, bh, gx, gy, &var_src, &avg_src, &motion_bias, &psy);
     has = me_nonspatial(A, i, j, gx, gy, &lax, &lay, cbx, cby, &nb);
+    ME_PHASE();
     /* measure zero, the parent average and the list (valid, distinct positions) */
     for (int k = -2; k < (has ? nb : 0); k++) {
         int dx, dy;
@@ -1383,6 +1399,7 @@ me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j)
             (void) me_eval(S, mn, level, srcd, sp.stride, rp, bx, by, cxl + nx[k], cyl + ny[k], bw, bh, psy);
         }
     }
+    ME_PHASE();
     zoscore = me_metr(srcd, sp.stride, A.ogr.data + by * A.ogr.stride + bx, A.ogr.stride, bw, bh, psy);
     MeRefStats rs[2];
     int rs_valid[2] = { 0, 0 }, utex = 0, vtex = 0;
@@ -1394,10 +1411,12 @@ me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j)
             me_ref_stats(A, &rs[0], srcd, i, j, bx, by, bw, bh, lax, lay, (int) avg_src, psy);
             rs_valid[0] = 1;
         }
+        ME_PHASE();
         if (lax | lay) {
             me_ref_stats(A, &rs[1], srcd, i, j, bx, by, bw, bh, 0, 0, (int) avg_src, psy);
             rs_valid[1] = 1;
         }
+        ME_PHASE();
         if (sbw && sbh) {
             for (int g = 0; g <= sbh; g += (sbh + !sbh)) {
                 for (int f = 0; f <= sbw; f += (sbw + !sbw)) {
@@ -1411,6 +1430,7 @@ me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j)
             vtex = (int) me_block_tex(A.src[2].data + cby * A.src[2].stride + cbx, A.src[2].stride, cbw, cbh);
         }
     }
+    ME_PHASE();
     MeSubpel M;
     int sp_valid = 0;
     M.nv = 0;
@@ -1895,10 +1915,21 @@ k_me_prepass(MeArgs A)
     MeScratch *S = &scratch[ME_WIC];
     const int step = 1 << A.level;
     const int cols = (A.nxb + step - 1) / step, rows = (A.nyb + step - 1) / step;
+#if defined(ME_PRE_PHASE_SYNC) && !defined(DSVCU_EMU)
+    for (int base = (int) blockIdx.x * ME_WARPS_PER_CTA; base < cols * rows; base += (int) gridDim.x * ME_WARPS_PER_CTA) {
+        const int b = base + ME_WIC;
+        const int r = b / cols, c = b - r * cols;
+        const bool live = b < cols * rows && ((c * step * A.y_w) >> A.level) < A.src[0].w &&
+                          ((r * step * A.y_h) >> A.level) < A.src[0].h;
+        const bool ps = __syncthreads_and(live);
+        if (live) me_prepass_block(A, S, c * step, r * step, ps);
+    }
+#else
     for (int b = ME_WARP; b < cols * rows; b += ME_NWARPS) {
         int r = b / cols, c = b - r * cols;
-        me_prepass_block(A, S, c * step, r * step);
+        me_prepass_block(A, S, c * step, r * step, false);
     }
+#endif
 }
 
 /* Wavefront over the block rows of one pyramid level: one warp per row, a CTA
