@@ -191,3 +191,76 @@ def test_quant_lossless_gpu():
 def test_mc_gpu(geom):
     _mc(geom, False)
     _mc(geom, False, q=1500, do_filter=0)
+
+
+def _frame_calls_equal_plane_calls(geom, emu, isP, q=252):
+    """dsvcu_fwd_sbt_frame / dsvcu_quant_frame / dsvcu_inv_sbt_frame (all planes
+    through shared launches) against the per-plane entry points, which the tests
+    above pin to the reference."""
+    name, w, h, fmt = geom
+    fr = _frames(name, w, h, fmt, 1)
+    cfg = _cfg(w, h, fmt, isP=1 if isP else 0, fnum=1)
+    bd = np.zeros(cfg.nblk, np.uint8)
+    rng = np.random.default_rng(7)
+    bd[:] = rng.integers(0, 128, cfg.nblk)
+    mvs = np.zeros(cfg.nblk, ops.MV_DTYPE)
+    mvs["x"] = rng.integers(-40, 41, cfg.nblk)
+    mvs["y"] = rng.integers(-40, 41, cfg.nblk)
+    D = ops.Dev(cfg, emu)
+    try:
+        lib, ctx, fm = D.lib, D.ctx, cfg.fmeta()
+        D.set_blockdata(bd)
+        D.set_mvs(mvs)
+        src = D.frame(fr[0])
+        ka, kb = D.coefs(), D.coefs()
+        oa, ob = D.frame(), D.frame()
+        for p in range(3):
+            D.ck(lib.dsvcu_fwd_sbt(ctx, src, p, ka, C.byref(fm)))
+        D.ck(lib.dsvcu_fwd_sbt_frame(ctx, src, kb, C.byref(fm), 7))
+        for p in range(3):
+            assert np.array_equal(D.coefs_download(ka, p), D.coefs_download(kb, p)), "forward transform, plane %d" % p
+        want = []
+        for p in range(3):
+            D.ck(lib.dsvcu_quant_plane(ctx, ka, p, q, C.byref(fm)))
+            want.append(_fetch(D, p))
+        D.ck(lib.dsvcu_quant_frame(ctx, kb, q, C.byref(fm), 7))
+        for p in range(3):
+            got = _fetch(D, p)
+            assert got[1] == want[p][1] and np.array_equal(got[0], want[p][0]), "symbols, plane %d" % p
+            assert np.array_equal(D.coefs_download(ka, p), D.coefs_download(kb, p)), "dequantised coefficients, plane %d" % p
+        for p in range(3):
+            D.ck(lib.dsvcu_inv_sbt(ctx, oa, p, ka, q, C.byref(fm)))
+        D.ck(lib.dsvcu_inv_sbt_frame(ctx, ob, kb, q, C.byref(fm), 7))
+        assert D.download(oa) == D.download(ob), "inverse transform"
+        # a partial mask only touches the selected planes
+        D.ck(lib.dsvcu_frame_clear_plane(ctx, ob, 1, 0))
+        D.ck(lib.dsvcu_inv_sbt_frame(ctx, ob, kb, q, C.byref(fm), 5))
+        a, b = D.download(oa), D.download(ob)
+        ysz = w * h
+        csz = cfg.cw * cfg.ch
+        assert a[:ysz] == b[:ysz] and a[ysz + csz:] == b[ysz + csz:]
+        assert b[ysz:ysz + csz] == bytes(csz)
+    finally:
+        D.close()
+
+
+def _fetch(D, plane):
+    syms = C.POINTER(D.P.DSVCU_SYMBOL)()
+    n, dc = C.c_int(), C.c_int()
+    D.ck(D.lib.dsvcu_fetch_symbols(D.ctx, plane, C.byref(syms), C.byref(n), C.byref(dc)))
+    arr = np.ctypeslib.as_array(C.cast(syms, C.POINTER(C.c_int32)), shape=(max(n.value, 1), 2))[:n.value].copy()
+    return arr, dc.value
+
+
+@pytest.mark.parametrize("geom", GEOM, ids=[g[0] for g in GEOM])
+@pytest.mark.parametrize("mode", ["I", "P"])
+def test_frame_level_calls_emulated(geom, mode):
+    util.ensure_emu()
+    _frame_calls_equal_plane_calls(geom, True, mode == "P")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", GEOM + BIG, ids=[g[0] for g in GEOM + BIG])
+@pytest.mark.parametrize("mode", ["I", "P"])
+def test_frame_level_calls_gpu(geom, mode):
+    _frame_calls_equal_plane_calls(geom, False, mode == "P")
