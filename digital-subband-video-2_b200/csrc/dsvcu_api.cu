@@ -416,6 +416,61 @@ dsvcu_timer_stop_ms(dsvcu_ctx *c, float *ms)
 }
 
 #if defined(ME_TIMING) && !defined(DSVCU_EMU)
+/* Diagnostics build only: what does ONE extra warp per SM see while the encoder
+ * instances run?  mode 0: a dependent integer chain in a hot loop (issue
+ * arbitration only); mode 1: a dependent chain of L2 loads (ld.cg pointer chase
+ * over 4 MB); mode 2: a dependent chain of shared-memory loads.  Returns the
+ * average cycles per step over all probe warps. */
+__global__ static void
+k_probe(int mode, int iters, const unsigned *chase, unsigned long long *out)
+{
+    __shared__ unsigned sm[1024];
+    unsigned v = threadIdx.x + blockIdx.x;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = (i * 197 + 31) & 1023;
+    __syncthreads();
+    long long t0 = clock64();
+    if (mode == 0) {
+        for (int i = 0; i < iters; i++) v = v * 1664525u + 1013904223u;
+    } else if (mode == 1) {
+        v = (blockIdx.x * 7919u) & ((1u << 20) - 1);
+        for (int i = 0; i < iters; i++) v = __ldcg(chase + v);
+    } else {
+        v &= 1023;
+        for (int i = 0; i < iters; i++) v = sm[v];
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) {
+        atomicAdd(&out[0], (unsigned long long) (t1 - t0));
+        atomicAdd(&out[1], 1ull);
+        if (v == 0xffffffffu) out[2] = v;
+    }
+}
+
+extern "C" int
+dsvcu_debug_probe(int mode, int iters, double *cycles_per_step)
+{
+    static unsigned *chase = NULL;
+    static unsigned long long *out = NULL;
+    static cudaStream_t st;
+    unsigned long long h[3];
+    if (!chase) {
+        unsigned *hc = (unsigned *) malloc(4u << 20);
+        unsigned n = 1u << 20, i;
+        for (i = 0; i < n; i++) hc[i] = (unsigned) (((unsigned long long) i * 1000003ull + 12345ull) & (n - 1));
+        cudaMalloc((void **) &chase, 4u << 20);
+        cudaMemcpy(chase, hc, 4u << 20, cudaMemcpyHostToDevice);
+        free(hc);
+        cudaMalloc((void **) &out, 32);
+        cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    }
+    cudaMemsetAsync(out, 0, 32, st);
+    k_probe<<<148, 32, 0, st>>>(mode, iters, chase, out);
+    cudaMemcpyAsync(h, out, 24, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    *cycles_per_step = h[1] ? (double) h[0] / (double) h[1] / iters : 0.0;
+    return 0;
+}
+
 extern "C" int
 dsvcu_debug_me_counters(unsigned long long out[4], int reset)
 {
