@@ -77,7 +77,12 @@ struct FiltJob {
 #define FILT_SUB ((int) (threadIdx.x & (FILT_LPC - 1)))
 #define FILT_NSUB FILT_LPC
 /* barrier + memory ordering among the lanes that share a cell */
-#define F_GSYNC() __syncwarp((((1u << FILT_LPC) - 1u)) << ((threadIdx.x & 31u) & ~(unsigned) (FILT_LPC - 1)))
+#if FILT_LPC >= 32
+#define F_GROUP_MASK 0xffffffffu
+#else
+#define F_GROUP_MASK ((((1u << FILT_LPC) - 1u)) << ((threadIdx.x & 31u) & ~(unsigned) (FILT_LPC - 1)))
+#endif
+#define F_GSYNC() __syncwarp(F_GROUP_MASK)
 #endif
 #define PXLD(p) (*(p))
 
@@ -324,7 +329,7 @@ f_degrad(uint8_t *a, int as)
 #ifdef DSVCU_EMU
 #define F_GRED(v, op) ((void) 0)
 #else
-#define F_GMASK ((((1u << FILT_LPC) - 1u)) << ((threadIdx.x & 31u) & ~(unsigned) (FILT_LPC - 1)))
+#define F_GMASK F_GROUP_MASK
 #define F_GRED(v, op)                                         \
     do {                                                      \
         for (int o_ = 1; o_ < FILT_LPC; o_ <<= 1) {           \
@@ -866,10 +871,12 @@ k_filter_skew(FiltJob J)
     const int abase = (fy - fy0) * A.nbh;
     /* hand-off words: from the band above / to the band below */
     const bool above_global = warp == 0, pub_global = warp == FILT_WPC - 1 && band + 1 < nbands;
+    /* the CTA below reads pixels written by this CTA's last two cell rows */
+    const bool dev_fence = band + 1 < nbands && warp * FILT_G + FILT_G - 1 >= FILT_CELLS - 2;
     volatile const int *above = above_global ? (volatile const int *) (A.progress + band - 1) : (volatile const int *) (done + warp - 1);
     /* cell rows whose footprint holds pixels written by the CTA above (luma: its
      * first two rows; chroma blocks: the first) read them from L2 */
-    const bool vol = cta > 0 && warp == 0 && grp < (chroma ? 1 : 2);
+    const bool vol = cta > 0 && warp * FILT_G + grp < (chroma ? 1 : 2);
     int seen = band ? 0 : 0x7fffffff;
     int fx = 0, rem = 0; /* luma: i * nbh = fx * nsbx + rem */
     for (int t = 0; t < nsteps; t++) {
@@ -916,7 +923,7 @@ k_filter_skew(FiltJob J)
                     f_chroma_cell<false>(A, i, row, cblk);
                 }
             }
-            if (pub_global) {
+            if (dev_fence) {
                 __threadfence();
             } else {
                 __threadfence_block();
