@@ -207,6 +207,13 @@ bw_reserve(DSV_BITWR *bw, size_t bits_more)
     }
 }
 
+/* for the register-resident writer of dsv_bits_inl.h */
+void
+dsv_bw_reserve(DSV_BITWR *bw, size_t bits_more)
+{
+    bw_reserve(bw, bits_more);
+}
+
 void
 dsv_bw_init(DSV_BITWR *bw, size_t initial_bytes)
 {

@@ -14,6 +14,7 @@
  */
 #include <string.h>
 #include "dsv_host.h"
+#include "dsv_bits_inl.h"
 
 void
 dsv_hzcc_write_plane(DSV_BITWR *bw, const dsvcu_symbol *syms, int nsyms, int dc, int w, int h)
@@ -32,18 +33,57 @@ dsv_hzcc_write_plane(DSV_BITWR *bw, const dsvcu_symbol *syms, int nsyms, int dc,
     cnt_at = dsv_bw_byte(bw);
     dsv_bw_bits(bw, 24, 0);
     dsv_bw_align(bw);
-    for (i = 0; i < nsyms; i++) {
-        unsigned pos = syms[i].pos;
-        while (l < 2 && pos >= (unsigned) part[l + 2]) {
-            l++;
+    {
+        /* the hot loop of the host side: ~45 k pairs per 1080p picture.  The bit
+         * accumulator lives in registers; whole code words leave 32 bits at a time. */
+        DSV_FW f;
+        dsv_bw_reserve(bw, (size_t) nsyms * 24 + 1024);
+        dsv_fw_begin(&f, bw);
+        for (i = 0; i < nsyms; i++) {
+            unsigned pos = syms[i].pos;
+            int v = syms[i].v;
+            if ((size_t) (f.p - bw->buf) + 96 > bw->cap) {
+                dsv_fw_end(&f, bw);
+                dsv_bw_reserve(bw, (size_t) (nsyms - i) * 24 + 8192);
+                dsv_fw_begin(&f, bw);
+            }
+            while (l < 2 && pos >= (unsigned) part[l + 2]) {
+                l++;
+            }
+            dsv_fw_ueg(&f, pos - prev);
+            if (l < 0) {
+                /* NEG: |v| - 1 as UEG, then the sign */
+                unsigned a = v < 0 ? (unsigned) -v : (unsigned) v;
+                dsv_fw_ueg(&f, a - 1);
+                if (a) dsv_fw_put(&f, v < 0, 1);
+            } else {
+                const int damp = 3 + l;
+                unsigned uv = ((unsigned) (2 * v) ^ (v < 0 ? ~0u : 0u)) - 1;
+                unsigned k = (unsigned) (vk >> damp);
+                unsigned q = k < 32 ? uv >> k : 0;
+                if (k > 24 || q > 256) {
+                    /* out of the ordinary: let the general writer deal with it */
+                    dsv_fw_end(&f, bw);
+                    dsv_bw_nrice(bw, v, &vk, damp);
+                    dsv_fw_begin(&f, bw);
+                } else {
+                    if (q) {
+                        vk++;
+                    } else if (vk > 0) {
+                        vk--;
+                    }
+                    if (q + 1 + k <= 32) {
+                        dsv_fw_put(&f, (1u << k) | (uv & ((1u << k) - 1)), (int) (q + 1 + k));
+                    } else {
+                        dsv_fw_zeros(&f, q);
+                        dsv_fw_put(&f, 1, 1);
+                        if (k) dsv_fw_put(&f, uv & ((1u << k) - 1), (int) k);
+                    }
+                }
+            }
+            prev = pos + 1;
         }
-        dsv_bw_ueg(bw, pos - prev);
-        if (l < 0) {
-            dsv_bw_neg(bw, syms[i].v);
-        } else {
-            dsv_bw_nrice(bw, syms[i].v, &vk, 3 + l);
-        }
-        prev = pos + 1;
+        dsv_fw_end(&f, bw);
     }
     dsv_bw_align(bw);
     dsv_bw_patch24(bw, cnt_at, (unsigned) nsyms);
@@ -84,29 +124,36 @@ dsv_hzcc_read_plane(DSV_BITRD *br, dsvcu_symbol *syms, int cap, int w, int h, in
     /* (run, value) pairs.  As in the reference (hzcc.c:476-486) the next run
      * is fetched before the bounds test, and a pair whose bits end at or past
      * the declared plane length is dropped together with everything after it */
-    run = (runs-- > 0) ? dsv_br_ueg(br) : UINT_MAX;
-    while (run != UINT_MAX) {
-        unsigned pos = cur + run;
-        int v;
-        if (pos >= (unsigned) total || pos < cur) {
-            break;
+    {
+        DSV_FR r;
+        r.buf = br->buf;
+        r.len = br->len;
+        r.pos = br->pos;
+        run = (runs-- > 0) ? dsv_fr_ueg(&r) : UINT_MAX;
+        while (run != UINT_MAX) {
+            unsigned pos = cur + run;
+            int v;
+            if (pos >= (unsigned) total || pos < cur) {
+                break;
+            }
+            while (l < 2 && pos >= (unsigned) part[l + 2]) {
+                l++;
+                level_start[l + 1] = n;
+            }
+            v = (l < 0) ? dsv_fr_neg(&r) : dsv_fr_nrice(&r, &vk, 3 + l);
+            run = (runs-- > 0) ? dsv_fr_ueg(&r) : UINT_MAX;
+            if ((r.pos >> 3) >= limit) {
+                truncated = 1;
+                break;
+            }
+            if (n < cap && pos != 0) {
+                syms[n].pos = pos;
+                syms[n].v = v;
+                n++;
+            }
+            cur = pos + 1;
         }
-        while (l < 2 && pos >= (unsigned) part[l + 2]) {
-            l++;
-            level_start[l + 1] = n;
-        }
-        v = (l < 0) ? dsv_br_neg(br) : dsv_br_nrice(br, &vk, 3 + l);
-        run = (runs-- > 0) ? dsv_br_ueg(br) : UINT_MAX;
-        if (dsv_br_byte(br) >= limit) {
-            truncated = 1;
-            break;
-        }
-        if (n < cap && pos != 0) {
-            syms[n].pos = pos;
-            syms[n].v = v;
-            n++;
-        }
-        cur = pos + 1;
+        br->pos = r.pos;
     }
     while (l < 2) {
         l++;
