@@ -324,6 +324,9 @@ dsvcu_ctx_destroy(dsvcu_ctx *c)
 #ifndef DSVCU_EMU
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    for (i = 0; i < DSVCU_MARKS; i++) {
+        if (c->marks[i]) cudaEventDestroy(c->marks[i]);
+    }
     for (i = 0; i < 3; i++) cudaEventDestroy(c->ev_sym[i]);
     cudaEventDestroy(c->ev_wait);
     cudaStreamDestroy(c->stream);

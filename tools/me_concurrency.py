@@ -43,7 +43,8 @@ def main():
             d.ck(d.lib.dsvcu_hme(d.ctx, C.byref(d.fm), C.byref(d.hp), fs, ps, frf, pr, fo, po))
             d.ck(d.lib.dsvcu_hme_fetch(d.ctx, d.out.ctypes.data_as(C.c_void_p), cfg.nblk, C.byref(a), C.byref(b), C.byref(c)))
 
-    work(devs[0], 2)
+    for d in devs:  # first use of a context allocates its search scratch (cudaMalloc synchronises the device)
+        work(d, 1)
     for n in counts:
         th = [threading.Thread(target=work, args=(devs[k], reps)) for k in range(n)]
         t0 = time.perf_counter()
