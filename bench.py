@@ -54,6 +54,7 @@ W, H, GOP, QP, FPS = 1920, 1080, 48, 60, 30
 FRAME_BYTES = W * H * 3 // 2
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "dsv2")
 METRIC = "1080p 4:2:0 encode fps (48-frame closed GOPs, bit-exact .dsv)"
+WORKLOAD = "1920x1080 4:2:0, -qp=60 -gop=48 -noeos=1 closed-GOP chunks of 48 frames (BASELINE configs[4])"
 
 
 def log(*a):
@@ -182,21 +183,40 @@ def write_y4m(path, frames_u8, nframes):
             f.write(frames_u8[i * FRAME_BYTES:(i + 1) * FRAME_BYTES].tobytes())
 
 
-def ref_encode_procs(y4m, nproc, per, tag):
-    """nproc reference encoders, process k codes frames [k*per, k*per+per)"""
-    ps = []
-    for k in range(nproc):
+def ref_encode_procs(y4m, jobs, tag):
+    """one reference encoder process per job; job = (first frame, frames):
+    `dsv2 e -sfr=first -nfr=frames -noeos=1`, parallel_encode_yuv.sh:34-41"""
+    ps, outs = [], []
+    for k, (first, n) in enumerate(jobs):
         out = "/dev/shm/dsv2_bench_ref_%s_%d.dsv" % (tag, k)
+        outs.append(out)
         ps.append(subprocess.Popen([REF_BIN, "e", "-y", "-inp=" + y4m, "-out=" + out, "-y4m=1", "-qp=%d" % QP,
-                                    "-gop=%d" % GOP, "-sfr=%d" % (k * per), "-nfr=%d" % per, "-noeos=1"],
+                                    "-gop=%d" % GOP, "-sfr=%d" % first, "-nfr=%d" % n, "-noeos=1"],
                                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
     for p in ps:
         p.wait()
         if p.returncode not in (0, 254):
             raise RuntimeError("reference encoder exit %d" % p.returncode)
+    return outs
+
+
+DISTINCT = 2  # different 48-frame chunks in the workload (chunk c of rank r is chunk (c + r) % DISTINCT)
+
+
+def ref_input():
+    """the bench workload's distinct chunks as one y4m on tmpfs"""
+    y4m = "/dev/shm/dsv2_bench_ref_in.y4m"
+    want = len("YUV4MPEG2 W%d H%d F%d:1 A1:1 Ip C420\n" % (W, H, FPS)) + DISTINCT * GOP * (FRAME_BYTES + 6)
+    if not (os.path.exists(y4m) and os.path.getsize(y4m) == want):
+        write_y4m(y4m + ".tmp", synth_chunks(DISTINCT), DISTINCT * GOP)
+        os.replace(y4m + ".tmp", y4m)
+    return y4m
 
 
 def run_reference(args):
+    """the UNMODIFIED reference on the host cores: one `dsv2 e` process per core, each
+    coding one WHOLE 48-frame chunk of the workload per step (same chunks, same I:P
+    mix as the repo arm; parallel_encode_yuv.sh semantics)"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -204,33 +224,51 @@ def run_reference(args):
         emit({"impl": "reference", "unavailable": "oracle/_ref/dsv2 not built (needs /root/reference)"})
         return 0
     cores = cpu_count()
-    per = 6  # frames per process and step: a bounded sample of a 48-frame chunk
-    data = synth_chunks(2)
-    nfr = min(cores * per, 2 * GOP)
-    nproc = nfr // per
-    y4m = "/dev/shm/dsv2_bench_ref_in.y4m"
-    write_y4m(y4m, data, nfr)
+    y4m = ref_input()
+    jobs = [((k % DISTINCT) * GOP, GOP) for k in range(cores)]
     for _ in range(args.warmup):
-        ref_encode_procs(y4m, nproc, per, "w")
+        ref_encode_procs(y4m, jobs[:max(1, cores)], "w")
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ref_encode_procs(y4m, nproc, per, "t")
+        ref_encode_procs(y4m, jobs, "t")
     dt = time.perf_counter() - t0
-    fps = nproc * per * args.steps / dt
-    sample = "%d processes x %d frames of a %d-frame closed-GOP chunk per step (first frame intra)" % (nproc, per, GOP)
+    fps = len(jobs) * GOP * args.steps / dt
+    sample = "%d processes x one whole %d-frame closed-GOP chunk per step (1 I + 47 P, cut at 40 -> scene-change I)" % (
+        len(jobs), GOP)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(fps, 3), "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000 * dt / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
-        "config": {"workload": "1920x1080 4:2:0, -qp=60 -gop=48 -noeos=1 closed-GOP chunks (BASELINE configs[4])",
-                   "reference": "oracle/_ref/dsv2 (unmodified reference, cc -O3), one process per host core"},
-        "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": nproc, "kind": "reference",
+        "config": {"workload": WORKLOAD,
+                   "reference": "oracle/_ref/dsv2 (unmodified reference, cc -O3), one process per host core, "
+                                "whole chunks", "frames_per_step": len(jobs) * GOP, "host_cores": cores},
+        "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": len(jobs), "kind": "reference",
                          "sample": sample},
         "e2e": {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
     return 0
+
+
+def md5(b):
+    import hashlib
+    return hashlib.md5(b).hexdigest()
+
+
+def reference_chunks(compute):
+    """.dsv bytes and decoded frames of every distinct chunk of the workload from the
+    unmodified reference (`dsv2 e -qp=60 -gop=48 -sfr=48k -nfr=48 -noeos=1`, `dsv2 d`).
+    Checker only: runs outside every timed region.  compute=False reads what another
+    rank left on tmpfs."""
+    names = [("/dev/shm/dsv2_bench_ref_par_%d.dsv" % k, "/dev/shm/dsv2_bench_ref_par_%d.yuv" % k) for k in range(DISTINCT)]
+    if compute:
+        ref_encode_procs(ref_input(), [(k * GOP, GOP) for k in range(DISTINCT)], "par")
+        ps = [subprocess.Popen([REF_BIN, "d", "-y", "-inp=" + o, "-out=" + d], stdout=subprocess.DEVNULL,
+                               stderr=subprocess.DEVNULL) for o, d in names]
+        for p in ps:
+            p.wait()
+    return [open(o, "rb").read() for o, _ in names], [open(d, "rb").read() for _, d in names]
 
 
 # --------------------------------------------------------------------- own arm
@@ -335,24 +373,26 @@ def kernel_rooflines(P, lib, peak_gbs):
 
 
 def cpu_baseline_sample():
-    """single-core reference encoder on a bounded sample (rank 0, N=1)"""
+    """single-core reference encoder + decoder on ONE WHOLE chunk of the workload
+    (rank 0, N=1): about 10 s of CPU work"""
     if not os.path.exists(REF_BIN):
         return None
-    nfr = 24
-    data = synth_chunks(2)
-    y4m = "/dev/shm/dsv2_bench_cpu_in.y4m"
-    write_y4m(y4m, data, nfr)
+    y4m = ref_input()
     t0 = time.perf_counter()
-    ref_encode_procs(y4m, 1, nfr, "cpu")
+    out = ref_encode_procs(y4m, [(0, GOP)], "cpu")[0]
     dt = time.perf_counter() - t0
     t0 = time.perf_counter()
-    subprocess.run([REF_BIN, "d", "-y", "-inp=/dev/shm/dsv2_bench_ref_cpu_0.dsv", "-out=/dev/shm/dsv2_bench_cpu_dec.yuv"],
+    subprocess.run([REF_BIN, "d", "-y", "-inp=" + out, "-out=/dev/shm/dsv2_bench_cpu_dec.yuv"],
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     dd = time.perf_counter() - t0
-    return {"value": round(nfr / dt, 3), "unit": "frames/s", "cores": 1, "kind": "reference",
-            "sample": "first %d frames of one 48-frame chunk, oracle/_ref/dsv2 e -qp=60 -gop=48 (1 process); "
-                      "decode of the same: %.2f frames/s" % (nfr, nfr / dd),
-            "decode_value": round(nfr / dd, 3)}
+    try:
+        os.unlink("/dev/shm/dsv2_bench_cpu_dec.yuv")
+    except OSError:
+        pass
+    return {"value": round(GOP / dt, 3), "unit": "frames/s", "cores": 1, "kind": "reference",
+            "sample": "one whole %d-frame chunk of the workload (chunk 0), oracle/_ref/dsv2 e -qp=60 -gop=48 -nfr=48 "
+                      "-noeos=1, 1 process; decode of the same stream with dsv2 d: %.2f frames/s" % (GOP, GOP / dd),
+            "decode_value": round(GOP / dd, 3)}
 
 
 def run_own(args):
@@ -378,7 +418,7 @@ def run_own(args):
     chunks = args.chunks or threads
     nframes = chunks * GOP
 
-    distinct = 2
+    distinct = DISTINCT
     # rank 0 generates (and caches on tmpfs) the synthetic chunks, the others read the cache
     if rank == 0:
         data = synth_chunks(distinct)
@@ -466,10 +506,44 @@ def run_own(args):
     ddt = timed(lambda: dec(ddev.data_ptr()), args.steps)
     dec(dhost.data_ptr())
     ddt_e2e = timed(lambda: dec(dhost.data_ptr()), args.steps)
-    # the decoder's output must be what the encoder reconstructed: spot check
-    # against the reference happens in tests/; here only a sanity checksum
     chk = int(dhost[:FRAME_BYTES].to(torch.int64).sum().item())
     lib.dsv_pool_destroy(pool)
+
+    # ---- parity of exactly what was timed (outside every timed region): the stream of
+    # the last encode step and the frames of the last decode step against the unmodified
+    # reference on the same chunks.  Every rank checks its own output.
+    parity = None
+    if os.path.exists(REF_BIN) and not args.no_parity:
+        ref_dsv, ref_yuv = (None, None)
+        if rank == 0:
+            ref_dsv, ref_yuv = reference_chunks(True)
+        if dist is not None:
+            dist.barrier()  # rank 0 has left the reference outputs on tmpfs
+            if rank != 0:
+                ref_dsv, ref_yuv = reference_chunks(False)
+        order = [(c + rank) % DISTINCT for c in range(chunks)]
+        want_dsv = b"".join(ref_dsv[k] for k in order)
+        ok_e = bytes(dsv) == want_dsv
+        got = dhost.numpy()
+        ok_d = True
+        for c, k in enumerate(order):
+            a = got[c * GOP * FRAME_BYTES:(c + 1) * GOP * FRAME_BYTES]
+            if a.tobytes() != ref_yuv[k]:
+                ok_d = False
+                break
+        dd = ddev.cpu().numpy()
+        ok_d = ok_d and bool((dd == got).all())
+        parity = {"encode": ok_e, "decode": ok_d, "chunks": DISTINCT, "chunks_checked": chunks,
+                  "reference": "oracle/_ref/dsv2 e -qp=60 -gop=48 -sfr=48k -nfr=48 -noeos=1 per distinct chunk, "
+                               "dsv2 d of each; compared: every byte of the last timed step's .dsv and every decoded frame",
+                  "dsv_md5": md5(bytes(dsv)), "dsv_bytes": len(dsv)}
+        if dist is not None:
+            t = torch.tensor([int(ok_e), int(ok_d)], device="cuda", dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            parity["encode"], parity["decode"] = bool(t[0].item()), bool(t[1].item())
+            parity["ranks"] = world
+        if not (parity["encode"] and parity["decode"]):
+            log("PARITY FAILURE: encode %s decode %s" % (parity["encode"], parity["decode"]))
 
     total_frames = nframes * world * args.steps
     value = total_frames / dt
@@ -502,9 +576,7 @@ def run_own(args):
         "metric": METRIC, "value": round(value, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(1000 * dt / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
-        "config": {"workload": "1920x1080 4:2:0, -qp=60 -gop=48 -noeos=1 closed-GOP chunks (BASELINE configs[4]); "
-                               "%d chunks x %d frames per GPU and step, %d host threads / CUDA streams per GPU"
-                               % (chunks, GOP, threads),
+        "config": {"workload": WORKLOAD, "chunks_per_gpu_per_step": chunks,
                    "frames_per_step": nframes * world, "host_threads_per_gpu": threads, "host_cores": cores,
                    "l2": "inputs larger than L2: %.0f MB of source frames per step" % (nframes * FRAME_BYTES / 1e6),
                    "timer": "host clock around a device-synchronised, barrier-bracketed region (work spans %d CUDA "
@@ -516,6 +588,7 @@ def run_own(args):
                    "d2h_bytes_per_step_e2e": nframes * FRAME_BYTES, "first_frame_checksum": chk},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
+        "parity": parity,
     }
     if me is not None:
         traffic, ncu = None, {}
@@ -539,6 +612,8 @@ def run_own(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not (parity["encode"] and parity["decode"]):
+        return 3  # a fast encoder whose bytes differ from the reference's is not a result
     return 0
 
 
@@ -551,6 +626,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="host threads (CUDA streams) per GPU")
     ap.add_argument("--chunks", type=int, default=0, help="48-frame chunks per GPU and step")
     ap.add_argument("--no-micro", action="store_true", help="skip the per-kernel microbench / CPU sample")
+    ap.add_argument("--no-parity", action="store_true", help="skip the reference comparison of the timed output")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -113,35 +113,68 @@ read_packet_hdr(DSV_BITRD *br)
     return type;
 }
 
-/* B.2.1 metadata packet */
-static void
+/* B.2.1 metadata packet.  Returns 0 when the fields describe a picture this
+ * build can hold (the reference accepts anything and fails later in its
+ * allocator; a device allocation sized by a corrupt field must not happen) */
+#define DSV_DEC_MAX_DIM 16384
+static int
 read_meta(DSV_DECODER *d, DSV_BITRD *br)
 {
-    DSV_META *m = &d->vidmeta;
-    m->width = (int) dsv_br_ueg(br);
-    m->height = (int) dsv_br_ueg(br);
-    m->subsamp = (int) dsv_br_ueg(br);
-    m->fps_num = (int) dsv_br_ueg(br);
-    m->fps_den = (int) dsv_br_ueg(br);
-    m->aspect_num = (int) dsv_br_ueg(br);
-    m->aspect_den = (int) dsv_br_ueg(br);
-    m->inter_sharpen = (int) dsv_br_ueg(br);
-    m->reserved = dsv_br_bit(br) ? (int) dsv_br_bits(br, 15) : 0;
+    DSV_META m;
+    memset(&m, 0, sizeof(m));
+    m.width = (int) dsv_br_ueg(br);
+    m.height = (int) dsv_br_ueg(br);
+    m.subsamp = (int) dsv_br_ueg(br);
+    m.fps_num = (int) dsv_br_ueg(br);
+    m.fps_den = (int) dsv_br_ueg(br);
+    m.aspect_num = (int) dsv_br_ueg(br);
+    m.aspect_den = (int) dsv_br_ueg(br);
+    m.inter_sharpen = (int) dsv_br_ueg(br);
+    m.reserved = dsv_br_bit(br) ? (int) dsv_br_bits(br, 15) : 0;
+    if (m.width <= 0 || m.height <= 0 || m.width > DSV_DEC_MAX_DIM || m.height > DSV_DEC_MAX_DIM) {
+        DSV_ERROR(("metadata: unusable picture size %d x %d", m.width, m.height));
+        return -1;
+    }
+    switch (m.subsamp) {
+        case DSV_SUBSAMP_444:
+        case DSV_SUBSAMP_422:
+        case DSV_SUBSAMP_UYVY:
+        case DSV_SUBSAMP_420:
+        case DSV_SUBSAMP_411:
+        case DSV_SUBSAMP_410:
+            break;
+        default:
+            DSV_ERROR(("metadata: unknown subsampling code %d", m.subsamp));
+            return -1;
+    }
+    d->vidmeta = m;
+    return 0;
 }
 
-/* a length-prefixed, byte-aligned sub-stream inside the picture payload */
-static void
+/* a length-prefixed, byte-aligned sub-stream inside the picture payload.  The
+ * coded length is not trusted: a sub-stream that would start or end outside the
+ * packet yields an empty one and puts the reader at the end of the packet (every
+ * later read then sees the zero padding); returns -1 in that case */
+static int
 open_substream(DSV_BITRD *in, const uint8_t **start, size_t *len)
 {
-    size_t n = dsv_br_ueg(in);
+    size_t n = dsv_br_ueg(in), at;
     dsv_br_align(in);
-    *start = in->buf + dsv_br_byte(in);
-    *len = (dsv_br_byte(in) + n <= in->len) ? n : (in->len > dsv_br_byte(in) ? in->len - dsv_br_byte(in) : 0);
+    at = dsv_br_byte(in);
+    if (at > in->len || n > in->len - at) {
+        *start = in->buf + in->len;
+        *len = 0;
+        in->pos = in->len * 8;
+        return -1;
+    }
+    *start = in->buf + at;
+    *len = n;
     in->pos += n * 8;
+    return 0;
 }
 
 /* B.2.3.1 stability (I) / skip (P) bits */
-static void
+static int
 read_stability(DSV_BITRD *in, uint8_t *blockdata, int nblk, int isP, const int *stats)
 {
     DSV_RLERD rle;
@@ -150,7 +183,9 @@ read_stability(DSV_BITRD *in, uint8_t *blockdata, int nblk, int isP, const int *
     int i, shift = isP ? DSV_SKIP_BIT : DSV_STABLE_BIT;
 
     dsv_br_align(in);
-    open_substream(in, &p, &len);
+    if (open_substream(in, &p, &len)) {
+        return -1;
+    }
     dsv_rle_rd_init(&rle, p, len + 8);
     for (i = 0; i < nblk; i++) {
         int bit = dsv_rle_rd_get(&rle);
@@ -160,10 +195,11 @@ read_stability(DSV_BITRD *in, uint8_t *blockdata, int nblk, int isP, const int *
         blockdata[i] = (uint8_t) (bit << shift);
     }
     dsv_rle_rd_end(&rle);
+    return 0;
 }
 
 /* B.2.3.2 ringing + B.2.3.3 maintain bits of an intra picture */
-static void
+static int
 read_intra_meta(DSV_BITRD *in, uint8_t *blockdata, int nblk, const int *stats)
 {
     DSV_RLERD rr, rm;
@@ -172,10 +208,14 @@ read_intra_meta(DSV_BITRD *in, uint8_t *blockdata, int nblk, const int *stats)
     int i;
 
     dsv_br_align(in);
-    open_substream(in, &p, &len);
+    if (open_substream(in, &p, &len)) {
+        return -1;
+    }
     dsv_rle_rd_init(&rr, p, len + 8);
     dsv_br_align(in);
-    open_substream(in, &p, &len);
+    if (open_substream(in, &p, &len)) {
+        return -1;
+    }
     dsv_rle_rd_init(&rm, p, len + 8);
     for (i = 0; i < nblk; i++) {
         int br = dsv_rle_rd_get(&rr), bm = dsv_rle_rd_get(&rm);
@@ -189,11 +229,12 @@ read_intra_meta(DSV_BITRD *in, uint8_t *blockdata, int nblk, const int *stats)
     }
     dsv_rle_rd_end(&rr);
     dsv_rle_rd_end(&rm);
+    return 0;
 }
 
 /* B.2.3.4 motion data: five sub-streams, vectors coded against the
  * left/top/top-left predictor */
-static void
+static int
 read_motion(DSV_BITRD *in, DSV_PARAMS *prm, uint8_t *blockdata, DSV_MV *mvs, const int *stats)
 {
     DSV_BITRD sub[DSV_SUB_NSUB];
@@ -204,7 +245,9 @@ read_motion(DSV_BITRD *in, DSV_PARAMS *prm, uint8_t *blockdata, DSV_MV *mvs, con
     for (i = 0; i < DSV_SUB_NSUB; i++) {
         const uint8_t *p;
         size_t len;
-        open_substream(in, &p, &len);
+        if (open_substream(in, &p, &len)) {
+            return -1;
+        }
         if (i == DSV_SUB_MODE) {
             dsv_rle_rd_init(&mode_rle, p, len + 8);
         } else if (i == DSV_SUB_EPRM) {
@@ -261,6 +304,7 @@ read_motion(DSV_BITRD *in, DSV_PARAMS *prm, uint8_t *blockdata, DSV_MV *mvs, con
     }
     dsv_rle_rd_end(&mode_rle);
     dsv_rle_rd_end(&eprm_rle);
+    return 0;
 }
 
 void
@@ -309,8 +353,16 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
     dsv_br_align(br);
     fno = dsv_br_bits(br, 32);
     dsv_br_align(br);
-    p->blk_w = 16 << dsv_br_ueg(br);
-    p->blk_h = 16 << dsv_br_ueg(br);
+    {
+        /* exponents above 1 are outside the format (and an unchecked shift is undefined) */
+        unsigned ex = dsv_br_ueg(br), ey = dsv_br_ueg(br);
+        if (ex > 2 || ey > 2) {
+            DSV_ERROR(("bad block size exponents %u, %u", ex, ey));
+            return DSV_DEC_ERROR;
+        }
+        p->blk_w = 16 << ex;
+        p->blk_h = 16 << ey;
+    }
     if (p->blk_w < DSV_MIN_BLOCK_SIZE || p->blk_h < DSV_MIN_BLOCK_SIZE || p->blk_w > DSV_MAX_BLOCK_SIZE ||
         p->blk_h > DSV_MAX_BLOCK_SIZE) {
         return DSV_DEC_ERROR;
@@ -343,14 +395,21 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
         s->blockdata = malloc((size_t) nblk);
         s->mvs = malloc((size_t) nblk * sizeof(DSV_MV));
         s->nblk_cap = nblk;
+        if (!s->blockdata || !s->mvs) {
+            free(s->blockdata);
+            free(s->mvs);
+            s->blockdata = NULL;
+            s->mvs = NULL;
+            s->nblk_cap = 0;
+            return DSV_DEC_ERROR;
+        }
     }
     memset(s->blockdata, 0, (size_t) nblk);
     memset(s->mvs, 0, (size_t) nblk * sizeof(DSV_MV));
-    read_stability(br, s->blockdata, nblk, isP, stats);
-    if (isP) {
-        read_motion(br, p, s->blockdata, s->mvs, stats);
-    } else {
-        read_intra_meta(br, s->blockdata, nblk, stats);
+    if (read_stability(br, s->blockdata, nblk, isP, stats) ||
+        (isP ? read_motion(br, p, s->blockdata, s->mvs, stats) : read_intra_meta(br, s->blockdata, nblk, stats))) {
+        DSV_ERROR(("side information runs past the end of the packet"));
+        return DSV_DEC_ERROR;
     }
     dsv_br_align(br);
 
@@ -440,9 +499,10 @@ dsv_dec(DSV_DECODER *d, DSV_BUF *buffer, DSV_FRAME **out, DSV_FNUM *fn)
         ret = DSV_DEC_ERROR;
     } else if (!DSV_PT_IS_PIC(pkt_type)) {
         if (pkt_type == DSV_PT_META) {
-            read_meta(d, &br);
-            d->got_metadata = 1;
-            ret = DSV_DEC_GOT_META;
+            if (read_meta(d, &br) == 0) {
+                d->got_metadata = 1;
+                ret = DSV_DEC_GOT_META;
+            }
         } else if (pkt_type == DSV_PT_EOS) {
             ret = DSV_DEC_EOS;
         }

@@ -70,6 +70,7 @@ struct _DSV_ENCDATA {
     DSV_MV *mvs;              /* this picture's field (host copy) */
     DSV_MV *imv;              /* intra analysis flags (host copy) */
     int nblk;
+    int pyr_levels;           /* depth the three pyramids were created with */
     double ph_ms[8], ph_t0;
     int ph_frames;
     double gpu_ms[8];         /* DSV_PROFILE=2: device time between phase stamps */
@@ -133,6 +134,7 @@ gpu_state_get(DSV_ENCODER *enc, int nblk)
     g->h = m->height;
     g->subsamp = m->subsamp;
     g->nblk = nblk;
+    g->pyr_levels = enc->pyramid_levels;
     g->mvs = calloc((size_t) nblk, sizeof(DSV_MV));
     g->imv = calloc((size_t) nblk, sizeof(DSV_MV));
     ok = g->mvs && g->imv && !dsvcu_ctx_create(&g->ctx, dsv_get_thread_device(), m->width, m->height, m->subsamp);
@@ -151,15 +153,24 @@ gpu_state_get(DSV_ENCODER *enc, int nblk)
     return g;
 }
 
-/* hands the device buffers of a finished encoder to a fresh one of the same
- * geometry (used by the chunked drivers: a new encoder per closed-GOP chunk
- * without re-allocating device memory) */
+static void picture_geometry(DSV_ENCODER *enc, DSV_PARAMS *p);
+
+/* hands the device buffers of a finished encoder to a fresh one (used by the
+ * chunked drivers: a new encoder per closed-GOP chunk without re-allocating
+ * device memory).  Only when everything the buffers were sized by agrees:
+ * picture geometry, the number of blocks (block-size overrides change it) and
+ * the resolved pyramid depth; otherwise the fresh encoder builds its own state */
 void
 dsv_enc_recycle(DSV_ENCODER *from, DSV_ENCODER *to)
 {
     DSV_ENCDATA *g = from->ref;
-    if (!g || to->ref || g->w != to->vidmeta.width || g->h != to->vidmeta.height || g->subsamp != to->vidmeta.subsamp ||
-        (to->pyramid_levels && to->pyramid_levels != from->pyramid_levels)) {
+    DSV_PARAMS p;
+    if (!g || to->ref || g->w != to->vidmeta.width || g->h != to->vidmeta.height || g->subsamp != to->vidmeta.subsamp) {
+        return;
+    }
+    memset(&p, 0, sizeof(p));
+    picture_geometry(to, &p); /* resolves to->pyramid_levels exactly as the first picture would */
+    if (p.nblocks_h * p.nblocks_v != g->nblk || to->pyramid_levels != g->pyr_levels) {
         return;
     }
     from->ref = NULL;

@@ -557,12 +557,17 @@ index_packets(const uint8_t *d, size_t len, PKT **out)
     return n;
 }
 
-/* metadata of a stream = its first metadata packet, parsed by the decoder */
+/* metadata of a stream = its first metadata packet, parsed by the decoder.
+ * The whole-stream drivers write every picture into one array of equally sized
+ * frames, so EVERY metadata packet is parsed here and a stream whose geometry
+ * changes on the way is refused (the reference CLI sizes each frame from the
+ * metadata current at that point, dsv_main.c:1008-1060; a fixed-size output
+ * cannot represent that, and silently keeping the first size would overrun it) */
 static int
 probe_meta(const uint8_t *d, const PKT *pk, int npk, DSV_META *meta)
 {
     DSV_DECODER dec;
-    int i;
+    int i, have = 0;
     memset(&dec, 0, sizeof(dec));
     for (i = 0; i < npk; i++) {
         if (pk[i].type == DSV_PT_META) {
@@ -571,13 +576,22 @@ probe_meta(const uint8_t *d, const PKT *pk, int npk, DSV_META *meta)
             DSV_FNUM fn;
             dsv_mk_buf(&b, (int) pk[i].len);
             memcpy(b.data, d + pk[i].off, pk[i].len);
-            if (dsv_dec(&dec, &b, &fr, &fn) == DSV_DEC_GOT_META) {
+            if (dsv_dec(&dec, &b, &fr, &fn) != DSV_DEC_GOT_META) {
+                return -1;
+            }
+            if (!have) {
                 *meta = dec.vidmeta;
-                return 0;
+                have = 1;
+            } else if (dec.vidmeta.width != meta->width || dec.vidmeta.height != meta->height ||
+                       dec.vidmeta.subsamp != meta->subsamp) {
+                DSV_ERROR(("picture geometry changes inside the stream (%dx%d fmt %d -> %dx%d fmt %d): not supported "
+                           "by the whole-stream drivers", meta->width, meta->height, meta->subsamp, dec.vidmeta.width,
+                           dec.vidmeta.height, dec.vidmeta.subsamp));
+                return -1;
             }
         }
     }
-    return -1;
+    return have ? 0 : -1;
 }
 
 /* decode packets [first, last) with `dec`; frames are written to dst one after
@@ -594,6 +608,12 @@ decode_range(DSV_DECODER *dec, const uint8_t *d, const PKT *pk, int first, int l
         dsv_mk_buf(&b, (int) pk[i].len);
         memcpy(b.data, d + pk[i].off, pk[i].len);
         if (DSV_PT_IS_PIC(pk[i].type)) {
+            /* never arm a direct copy for a geometry other than the one dst was sized for */
+            if (dec->got_metadata &&
+                frame_bytes(dec->vidmeta.width, dec->vidmeta.height, dec->vidmeta.subsamp) != fsz) {
+                DSV_ERROR(("picture packet with unexpected geometry: segment abandoned"));
+                break;
+            }
             dsv_dec_direct_output(dst + (size_t) nfr * fsz);
         }
         code = dsv_dec(dec, &b, &fr, &fn);

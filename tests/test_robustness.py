@@ -87,3 +87,99 @@ def test_bad_start_code_is_an_error():
     assert lib.dsv_dec(C.byref(dec), C.byref(buf), C.byref(fr), C.byref(fno)) == P.DEC_OK
     assert not fr
     lib.dsv_set_log_level(1)
+
+
+# ---- regressions for the round-1 advisor findings (host logic, run in emulation)
+
+def _tiny_stream(P, w, h, n, **kw):
+    import numpy as np
+    rng = np.random.default_rng(w * 131 + h)
+    fsz = w * h * 3 // 2
+    yuv = rng.integers(0, 256, n * fsz, dtype=np.uint8).tobytes()
+    o = P.enc_opts(w, h, P.SUBSAMP_420, (30, 1), emu=True, qp=60, gop=4, **kw)
+    return P.encode_frames(o, yuv, n, emu=True), yuv
+
+
+def test_geometry_change_inside_a_stream_is_refused():
+    """dsv_pipe.c sizes its output from the stream's metadata: a stream whose later
+    metadata packet announces a bigger picture must be refused, not decoded into the
+    first size (heap overflow in round 1)."""
+    util.ensure_emu()
+    P = util.pkg()
+    lib = P.load(True)
+    a, _ = _tiny_stream(P, 128, 96, 3, noeos=1)
+    b, _ = _tiny_stream(P, 256, 192, 3)
+    lib.dsv_set_log_level(0)
+    try:
+        with pytest.raises(RuntimeError):
+            P.decode_frames(a + b, emu=True)
+        with pytest.raises(RuntimeError):
+            P.decode_frames(a + b, emu=True, threads=2)
+        # the two halves on their own are fine, and so is the same geometry twice
+        assert P.decode_frames(a, emu=True)[1] == 3
+        assert P.decode_frames(a + a, emu=True, threads=2)[1] == 6
+    finally:
+        lib.dsv_set_log_level(1)
+
+
+def test_pool_recycles_device_state_only_for_the_same_block_geometry():
+    """one persistent pool, same resolution, block-size override changed between
+    calls: the second encoder must not inherit buffers sized for fewer blocks"""
+    util.ensure_emu()
+    P = util.pkg()
+    lib = P.load(True)
+    import numpy as np
+    w, h, n = 256, 192, 4
+    fsz = w * h * 3 // 2
+    yuv = np.random.default_rng(5).integers(0, 256, n * fsz, dtype=np.uint8).tobytes()
+    buf = (C.c_uint8 * len(yuv)).from_buffer_copy(yuv)
+    devs = (C.c_int * 1)(0)
+    pool = lib.dsv_pool_create(1, devs, 1)
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    try:
+        got = {}
+        for bs in (1, 0, 1, -1):
+            o = P.enc_opts(w, h, P.SUBSAMP_420, (30, 1), emu=True, qp=60, gop=2, noeos=1, bszx=bs, bszy=bs)
+            out, outn = C.c_void_p(), C.c_size_t()
+            assert lib.dsv_pool_encode(pool, C.byref(o), buf, n, 2, C.byref(out), C.byref(outn)) == 0
+            got[bs] = C.string_at(out, outn.value)
+            libc.free(out)
+            # same bytes as a fresh one-shot sharded encode with these options
+            assert got[bs] == P.encode_frames(o, yuv, n, emu=True, chunk=2)
+    finally:
+        lib.dsv_pool_destroy(pool)
+
+
+def test_corrupt_side_information_lengths_are_contained():
+    """every byte of the picture header / first sub-stream lengths forced to 0x00, 0x01
+    and 0xff: the decoder must come back (error or damaged picture) without touching
+    memory outside the packet.  Run under the emulation library: a wild read shows
+    up as a crash of the test process."""
+    util.ensure_emu()
+    P = util.pkg()
+    lib = P.load(True)
+    data, _ = _tiny_stream(P, 128, 96, 3)
+    pk = P.split_packets(data)
+    pics = [i for i, p in enumerate(pk) if p[5] & 0x04]
+    assert len(pics) == 3
+    lib.dsv_set_log_level(0)
+    try:
+        for pi in (pics[0], pics[1]):  # an intra and a predicted picture
+            base = sum(len(p) for p in pk[:pi])
+            for at in range(14, 14 + 48):
+                for val in (0x00, 0x01, 0xff):
+                    d = bytearray(data)
+                    d[base + at] = val
+                    try:
+                        P.decode_frames(bytes(d), emu=True)
+                    except RuntimeError:
+                        pass
+        # metadata with absurd dimensions is refused as well
+        d = bytearray(data)
+        for at in range(14, 20):
+            d[at] = 0x00
+        with pytest.raises(RuntimeError):
+            P.decode_frames(bytes(d), emu=True)
+    finally:
+        lib.dsv_set_log_level(1)
