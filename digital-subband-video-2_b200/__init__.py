@@ -137,6 +137,7 @@ def load(emu=False):
         "dsv_dec": (ip, [P(DSV_DECODER), P(DSV_BUF), P(P(DSV_FRAME)), P(C.c_uint32)]),
         "dsv_dec_free": (None, [P(DSV_DECODER)]),
         "dsv_hzcc_pack_plane": (ip, [vp, ip, ip, ip, ip, vp, ip]),
+        "dsv_hzcc_unpack_plane": (ip, [vp, ip, vp, ip, ip, ip, P(ip), P(ip)]),
         "dsv_enc_opts_default": (None, [P(DSV_ENC_OPTS), ip, ip, ip, ip, ip]),
         "dsv_set_thread_device": (None, [ip]),
         "dsv_pinned_alloc": (vp, [C.c_size_t]),

@@ -42,8 +42,13 @@ dsvcu_more_connections(void)
 
 static char g_err[256] = "";
 static int uniform_carveout(int device);
-static int g_pre_cap = getenv("DSVCU_PRE_GRID") ? atoi(getenv("DSVCU_PRE_GRID")) : 0; /* experiments: cap the prepass grid */
-static int g_me_smem = getenv("DSVCU_ME_SMEM") ? atoi(getenv("DSVCU_ME_SMEM")) : 0; /* experiments: pad the search kernel's shared memory to limit co-residency */
+#ifdef DSVCU_DIAG
+/* diagnostics build only (-DDSVCU_DIAG): experiment knobs, never in the product library */
+static int g_pre_cap = getenv("DSVCU_PRE_GRID") ? atoi(getenv("DSVCU_PRE_GRID")) : 0; /* cap the prepass grid */
+static int g_me_smem = getenv("DSVCU_ME_SMEM") ? atoi(getenv("DSVCU_ME_SMEM")) : 0; /* pad the search kernel's shared memory */
+#else
+static const int g_pre_cap = 0, g_me_smem = 0;
+#endif
 static long long g_launches = 0; /* kernels launched by every context of this process */
 
 static int
@@ -418,7 +423,7 @@ dsvcu_timer_stop_ms(dsvcu_ctx *c, float *ms)
     return 0;
 }
 
-#if defined(ME_TIMING) && !defined(DSVCU_EMU)
+#if defined(DSVCU_DIAG) && defined(ME_TIMING) && !defined(DSVCU_EMU)
 /* Diagnostics build only: what does ONE extra warp per SM see while the encoder
  * instances run?  mode 0: a dependent integer chain in a hot loop (issue
  * arbitration only); mode 1: a dependent chain of L2 loads (ld.cg pointer chase
@@ -1748,7 +1753,7 @@ uniform_carveout(int device)
 {
 #ifndef DSVCU_EMU
     static int done[64];
-    static const int pct = getenv("DSVCU_CARVEOUT") ? atoi(getenv("DSVCU_CARVEOUT")) : 58;
+    static const int pct = 58;
     if (device < 0 || device >= 64 || done[device] || pct < 0) return 0;
 #define CARVE(k) CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct))
     CARVE(k_compact_count);

@@ -103,6 +103,8 @@ size_t dsv_rle_wr_end(DSV_RLEWR *r); /* returns byte length */
 /* writes one plane: [32-bit length][SEG dc][24-bit count][(run,value)...][0x55] */
 void dsv_hzcc_write_plane(DSV_BITWR *bw, const dsvcu_symbol *syms, int nsyms, int dc, int w, int h);
 int dsv_hzcc_pack_plane(const dsvcu_symbol *syms, int nsyms, int dc, int w, int h, uint8_t *out, int cap);
+int dsv_hzcc_unpack_plane(const uint8_t *bits, int len, dsvcu_symbol *syms, int cap, int w, int h, int level_start[5],
+                          int *dc);
 /* parses one plane into `syms` (capacity `cap`); fills level_start[5] and *dc.
  * returns the symbol count, or -1 when the plane is corrupt (bad length / EOP) */
 int dsv_hzcc_read_plane(DSV_BITRD *br, dsvcu_symbol *syms, int cap, int w, int h, int level_start[5], int *dc);

@@ -14,6 +14,7 @@
  */
 #include <string.h>
 #include "dsv_host.h"
+#include <stdlib.h>
 #include "dsv_bits_inl.h"
 
 void
@@ -190,5 +191,23 @@ dsv_hzcc_pack_plane(const dsvcu_symbol *syms, int nsyms, int dc, int w, int h, u
         memcpy(out, bw.buf, (size_t) n);
     }
     dsv_bw_free(&bw);
+    return n;
+}
+
+/* test hook, mirror of dsv_hzcc_pack_plane: parses one serialised plane (as the
+ * reference's dsv_encode_plane wrote it) into the ordered symbol list */
+int
+dsv_hzcc_unpack_plane(const uint8_t *bits, int len, dsvcu_symbol *syms, int cap, int w, int h, int level_start[5], int *dc)
+{
+    DSV_BITRD br;
+    uint8_t *copy = calloc((size_t) len + 32, 1);
+    int n;
+    if (!copy) {
+        return -1;
+    }
+    memcpy(copy, bits, (size_t) len);
+    dsv_br_init(&br, copy, (size_t) len);
+    n = dsv_hzcc_read_plane(&br, syms, cap, w, h, level_start, dc);
+    free(copy);
     return n;
 }

@@ -370,3 +370,51 @@ refop_intra_filter(const refop_cfg *c, int q, const uint8_t *blockdata, uint8_t 
     dsv_frame_ref_dec(f);
     return 0;
 }
+
+/* the decoder's half of a coefficient plane: `bits`/`len` as refop_encode_plane
+ * produced them -> de-quantised coefficients (dsv_decode_plane, hzcc.c:616-649,
+ * into a zeroed plane like dsv_decoder.c:506-519).  Returns dsv_decode_plane's
+ * success flag. */
+int
+refop_decode_plane(const refop_cfg *c, int plane, int q, const uint8_t *bits, int len, const uint8_t *blockdata,
+                   const DSV_MV *mvs, int32_t *coefs_out)
+{
+    DSV_PARAMS prm;
+    DSV_FMETA fm;
+    DSV_COEFS k[3];
+    DSV_BS bs;
+    uint8_t *copy;
+    int ok;
+    mk_params(c, &prm);
+    dsv_mk_coefs(k, c->subsamp, c->w, c->h);
+    memset(&fm, 0, sizeof(fm));
+    fm.params = &prm;
+    fm.blockdata = (uint8_t *) blockdata;
+    fm.mvs = (DSV_MV *) mvs;
+    fm.cur_plane = (uint8_t) plane;
+    fm.isP = (uint8_t) c->isP;
+    fm.fnum = c->fnum;
+    copy = calloc((size_t) len + 64, 1);
+    memcpy(copy, bits, (size_t) len);
+    dsv_bs_init(&bs, copy);
+    ok = dsv_decode_plane(&bs, &k[plane], q, &fm);
+    memcpy(coefs_out, k[plane].data, (size_t) k[plane].width * k[plane].height * sizeof(int32_t));
+    free(copy);
+    dsv_free(k[0].data);
+    return ok;
+}
+
+/* one plane of dsv_extend_frame's result WITH its 32-px border (frame.c:357-434):
+ * out must hold (h + 64) * stride bytes; returns the stride */
+int
+refop_extend_plane(const refop_cfg *c, const uint8_t *yuv, int plane, uint8_t *out, int *pw, int *ph)
+{
+    DSV_FRAME *f = frame_from_yuv(c, yuv, 1);
+    DSV_PLANE *pl = &f->planes[plane];
+    int stride = pl->stride;
+    *pw = pl->w;
+    *ph = pl->h;
+    memcpy(out, pl->data - DSV_FRAME_BORDER * stride - DSV_FRAME_BORDER, (size_t) stride * (pl->h + 2 * DSV_FRAME_BORDER));
+    dsv_frame_ref_dec(f);
+    return stride;
+}

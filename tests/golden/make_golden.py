@@ -4,7 +4,8 @@
 
 The reference ships no golden vectors, so the fixtures are
 outputs of the reference itself on the deterministic synthetic clips of
-tools/synth_y4m.py: md5 of the input y4m, of the .dsv the reference encoder
+tools/synth_y4m.py (kind="tri": integer arithmetic only, so the input bytes are
+the same on every machine and the test can insist on them): md5 of the input y4m, of the .dsv the reference encoder
 writes, and of the y4m the reference decoder writes from it.  Run in a container
 that has /root/reference:   python tests/golden/make_golden.py
 """
@@ -25,6 +26,7 @@ CASES = [
     ("cif444", 352, 288, 6, "444", 30, ["-qp=50", "-gop=5"]),
     ("cif444ll", 352, 288, 4, "444", 30, ["-qp=100"]),
     ("cif_cqp", 352, 288, 6, "420", 30, ["-qp=45", "-rc_mode=2", "-effort=5"]),
+    ("oddchroma", 354, 290, 5, "420", 30, ["-qp=60", "-gop=48"]),
 ]
 
 
@@ -36,7 +38,7 @@ def main():
     assert util.have_ref(), "build oracle/_ref first (make -C oracle ref)"
     out = {}
     for name, w, h, n, fmt, fps, args in CASES:
-        y4m = util.clip("golden_" + name, w, h, n, fmt, fps=fps)
+        y4m = util.clip("golden_" + name, w, h, n, fmt, fps=fps, kind="tri")
         dsv = util.ref_encode(y4m, args, "golden")
         dec = util.ref_decode(dsv)
         out[name] = {"w": w, "h": h, "frames": n, "fmt": fmt, "fps": fps, "args": args,

@@ -29,10 +29,39 @@ def _canvas(w, h, rng, noise_amp):
     return luma, cb, cr
 
 
-def frames(w, h, nfr, fmt="420", seed=1234, noise=24.0, sensor=3, cut=40):
-    """Yield (Y, U, V) uint8 arrays for nfr frames."""
+def _tri(v, period, amp):
+    """integer triangle wave of v: values in [-amp, amp], exact on every platform"""
+    p = np.mod(v, 2 * period)
+    t = np.where(p < period, p, 2 * period - p)  # 0 .. period
+    return (2 * amp * t) // period - amp
+
+
+def _canvas_int(w, h, rng, noise_amp):
+    """the same kind of content as _canvas from integer arithmetic only (no libm):
+    used for the committed golden fixtures, whose input must be bit-identical on
+    every machine"""
+    cw, ch = w * 2 + 256, h * 2 + 256
+    x = np.arange(cw, dtype=np.int64)[None, :]
+    y = np.arange(ch, dtype=np.int64)[:, None]
+    luma = 128 + (_tri(x, 58, 60) * _tri(y + 18, 36, 64)) // 64 + _tri(x + y, 17, 30)
+    na = int(noise_amp)
+    if na > 0:
+        n = rng.integers(-na, na + 1, size=(ch + 1, cw + 1), dtype=np.int64)
+        luma = luma + (n[:-1, :-1] + n[1:, :-1] + n[:-1, 1:] + n[1:, 1:] + 2 * na * 4) // 4 - 2 * na
+    cb = 128 + _tri(x, 83, 50) + 0 * y
+    cr = 128 + _tri(y + 32, 64, 50) + 0 * x
+    return luma.astype(np.float64), cb.astype(np.float64), cr.astype(np.float64)
+
+
+def frames(w, h, nfr, fmt="420", seed=1234, noise=24.0, sensor=3, cut=40, kind="sin"):
+    """Yield (Y, U, V) uint8 arrays for nfr frames.  kind="tri": integer-only
+    canvas (platform-independent bytes); every later step is exact in float64
+    (sums of integers, /4 and /2 of integers, rint)."""
+    if (w | h) & 1 and fmt in ("420", "422"):
+        raise ValueError("odd luma dimensions are not valid input for the reference CLI (dsv_main.c:622) "
+                         "and not supported by this generator")
     rng = np.random.default_rng(seed)
-    luma, cb, cr = _canvas(w, h, rng, noise)
+    luma, cb, cr = (_canvas_int if kind == "tri" else _canvas)(w, h, rng, noise)
     ch_h, ch_w = luma.shape
     sub = 2 if fmt == "420" else 1
     for t in range(nfr):
