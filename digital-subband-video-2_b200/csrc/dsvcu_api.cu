@@ -45,9 +45,8 @@ static int uniform_carveout(int device);
 #ifdef DSVCU_DIAG
 /* diagnostics build only (-DDSVCU_DIAG): experiment knobs, never in the product library */
 static int g_pre_cap = getenv("DSVCU_PRE_GRID") ? atoi(getenv("DSVCU_PRE_GRID")) : 0; /* cap the prepass grid */
-static int g_me_smem = getenv("DSVCU_ME_SMEM") ? atoi(getenv("DSVCU_ME_SMEM")) : 0; /* pad the search kernel's shared memory */
 #else
-static const int g_pre_cap = 0, g_me_smem = 0;
+static const int g_pre_cap = 0;
 #endif
 static long long g_launches = 0; /* kernels launched by every context of this process */
 
@@ -1594,24 +1593,24 @@ dsvcu_hme(dsvcu_ctx *c, const dsvcu_fmeta *fm, const dsvcu_hme_params *hp, dsvcu
             /* everything a block needs that does not depend on its same-level
              * neighbours, for all blocks at once */
             int cols = (fm->nblocks_h + step - 1) / step;
-            int pctas = (cols * rows + ME_WARPS_PER_CTA - 1) / ME_WARPS_PER_CTA;
+            int pctas = (cols * rows + ME_PRE_GROUPS - 1) / ME_PRE_GROUPS;
 #ifdef DSVCU_EMU
             pctas = 1;
 #endif
             if (pctas > 148 * 8) pctas = 148 * 8;
             if (g_pre_cap > 0 && pctas > g_pre_cap) pctas = g_pre_cap;
-            DSVCU_LAUNCH(k_me_prepass, pctas, ME_WARPS_PER_CTA * 32, 0, c->stream, A);
+            DSVCU_LAUNCH(k_me_prepass, pctas, ME_PRE_THREADS, 0, c->stream, A);
             CK_LAUNCH(c);
         }
-        /* one warp per block row; CTA k only waits for CTA k-1, dispatched first */
-        ctas = (rows + ME_WARPS_PER_CTA - 1) / ME_WARPS_PER_CTA;
+        /* four block rows per warp; CTA k only waits for CTA k-1, dispatched first */
+        ctas = (rows + ME_LVL_ROWS - 1) / ME_LVL_ROWS;
 #ifndef DSVCU_EMU
-        if (g_me_smem > 0 && !c->me_smem_set) {
-            CK(cudaFuncSetAttribute(k_me_level, cudaFuncAttributeMaxDynamicSharedMemorySize, g_me_smem));
+        if (!c->me_smem_set) {
+            CK(cudaFuncSetAttribute(k_me_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(MeLvlShared)));
             c->me_smem_set = 1;
         }
 #endif
-        DSVCU_LAUNCH(k_me_level, ctas, ME_WARPS_PER_CTA * 32, g_me_smem, c->stream, A);
+        DSVCU_LAUNCH(k_me_level, ctas, ME_LVL_WARPS * 32, sizeof(MeLvlShared), c->stream, A);
         CK_LAUNCH(c);
         if (lvl != 0) {
             DSVCU_LAUNCH(k_me_global, 1, 256, 0, c->stream, c->d_mvf[lvl], fm->nblocks_h, fm->nblocks_v, lvl, c->d_me);
@@ -1650,6 +1649,14 @@ dsvcu_hme_fetch(dsvcu_ctx *c, void *mvs_out, int nblocks, int *intra_pct, int *s
     CK(dsvcu_d2h_async(c->h_mvs, c->d_mvs, (size_t) nblocks * sizeof(dsvcu_mv), c->stream));
     CK(ctx_wait(c));
     memcpy(mvs_out, c->h_mvs, (size_t) nblocks * sizeof(dsvcu_mv));
+#if defined(ME_COUNT) && defined(DSVCU_EMU)
+    {
+        static const char *nm[8] = { "blocks", "decision landed on S", "metric look-ups", "  measured on demand", "sub-pel passes on demand",
+                                     "reference statistics on demand", "max-sub-block metrics on demand", "intra error sums on demand" };
+        for (int k = 0; k < 8; k++) fprintf(stderr, "  [me level 0 wavefront] %-34s %8ld\n", nm[k], g_me_cnt[k]);
+        memset(g_me_cnt, 0, sizeof(g_me_cnt));
+    }
+#endif
     elig = c->h_me[4] ? c->h_me[4] : 1;
     *intra_pct = (c->h_me[2] * 100) / nblocks;
     *scene_change_blocks = c->h_me[3] * 100 / elig;

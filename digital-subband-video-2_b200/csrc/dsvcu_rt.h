@@ -116,6 +116,7 @@ dsvcu_emu_need_smem(size_t n)
 
 using std::max;
 using std::min;
+struct uint4 { unsigned x, y, z, w; };
 
 static inline int dsvcu_malloc_(void **pp, size_t n) { *pp = calloc(1, n ? n : 1); return *pp ? 0 : 2; }
 #define dsvcu_malloc(pp, n) dsvcu_malloc_((void **) (pp), (n))

@@ -33,8 +33,12 @@
 /* residency targets (CTAs per SM) the register allocation is held to: with many
  * encoder instances on one GPU the register file is what runs out first */
 #ifndef ME_MIN_CTAS
-#define ME_MIN_CTAS 2
+#define ME_MIN_CTAS 4
 #endif
+/* the prepass runs four blocks per warp (groups of ME_PRE_G lanes, k_hme_body.cuh) */
+#define ME_PRE_G 8
+#define ME_PRE_THREADS 128
+#define ME_PRE_GROUPS (ME_PRE_THREADS / ME_PRE_G)
 #ifndef ME_PRE_MIN_CTAS
 #define ME_PRE_MIN_CTAS 4
 #endif
@@ -44,6 +48,16 @@
 #ifndef ME_POLL_NS
 #define ME_POLL_NS 256 /* back-off between polls of the row above (a block takes ~30 us) */
 #endif
+/* ME_COUNT (host emulation only, diagnostics): how much pixel work is left in the
+ * dependent wavefront pass at level 0, i.e. how often the prepass' speculation hit */
+#if defined(ME_COUNT) && defined(DSVCU_EMU)
+static long g_me_cnt[16];
+static int g_me_in_wave = 0;
+#define ME_CNT(k) (g_me_in_wave ? (void) g_me_cnt[k]++ : (void) 0)
+#else
+#define ME_CNT(k) ((void) 0)
+#endif
+enum { MEC_BLOCKS, MEC_AT_S, MEC_EVAL, MEC_EVAL_MISS, MEC_SUBPEL, MEC_REFSTATS, MEC_MAXSUB, MEC_ERR_INTRA, MEC_BLOCK_AVG };
 #define ME_BORDER 32
 #define ME_MAXLVL 5
 #define SP_SZ 16
@@ -72,28 +86,6 @@ struct MeArgs {
     int b2sr;          /* (256 * (q*q >> 12) * blk_w * blk_h) / (width * height), dsv.c:370 */
     struct MePre *pre; /* per-block results of k_me_prepass for this level */
 };
-
-#ifdef DSVCU_EMU
-#define ME_LANE 0
-#define ME_NL 1
-#define ME_WARP ((int) blockIdx.x)
-#define ME_NWARPS ((int) gridDim.x)
-#define ME_WIC 0
-DSVCU_DEV int me_wsum(int v) { return v; }
-DSVCU_DEV unsigned me_wsumu(unsigned v) { return v; }
-DSVCU_DEV int me_wor(int v) { return v; }
-DSVCU_DEV unsigned me_wmaxu(unsigned v) { return v; }
-#else
-#define ME_LANE ((int) (threadIdx.x & 31))
-#define ME_NL 32
-#define ME_WARP ((int) ((blockIdx.x * blockDim.x + threadIdx.x) >> 5))
-#define ME_NWARPS ((int) ((gridDim.x * blockDim.x) >> 5))
-#define ME_WIC ((int) (threadIdx.x >> 5))
-DSVCU_DEV int me_wsum(int v) { return __reduce_add_sync(0xffffffffu, v); }
-DSVCU_DEV unsigned me_wsumu(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
-DSVCU_DEV int me_wor(int v) { return (int) __reduce_or_sync(0xffffffffu, (unsigned) v); }
-DSVCU_DEV unsigned me_wmaxu(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
-#endif
 
 DSVCU_HD int me_abs(int v) { return v < 0 ? -v : v; }
 DSVCU_HD int me_sqr(int v) { return v * v; }
@@ -157,6 +149,17 @@ DSVCU_DEV int me_gshift(int w)
     return w == 16 ? 2 : (w == 8 ? 1 : (w == 32 ? 3 : (w == 4 ? 0 : -1)));
 }
 
+/* index of the lowest set bit (x != 0) */
+DSVCU_DEV int
+me_ctz(unsigned x)
+{
+#ifndef DSVCU_EMU
+    return __ffs((int) x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+
 /* floor(sqrt(n)): what the reference's digit-by-digit iisqrt (hme.c:99-124)
  * returns; here from the hardware square root plus an exact integer fix-up
  * (checked against the digit-by-digit form over the full 32-bit range at
@@ -170,813 +173,32 @@ me_isqrt(unsigned n)
     return r;
 }
 
-struct MePsy {
-    int err_w, tex_w, avg_w;
-};
-
-/* one 2x2 cell of the psycho-visual metric (METR_CALC, hme.c:126-134) */
-DSVCU_DEV unsigned
-me_cell(int a1, int a2, int a3, int a4, int b1, int b2, int b3, int b4, const MePsy &p)
-{
-    int s0 = (int) me_uavg4(a1, a2, a3, a4), s1 = (int) me_uavg4(b1, b2, b3, b4);
-    int se = (int) me_uavg4(me_abs(a1 - b1), me_abs(a2 - b2), me_abs(a3 - b3), me_abs(a4 - b4));
-    int ta = (int) me_uavg4(me_abs(a1 - a2), me_abs(a2 - a3), me_abs(a3 - a4), me_abs(a4 - a1));
-    int tb = (int) me_uavg4(me_abs(b1 - b2), me_abs(b2 - b3), me_abs(b3 - b4), me_abs(b4 - b1));
-    unsigned acc = 0;
-    acc += (unsigned) (me_sqr(se) << p.err_w);
-    acc += (unsigned) (me_sqr(ta - tb) << p.tex_w);
-    acc += (unsigned) (me_sqr(s0 - s1) << p.avg_w);
-    return acc;
-}
-
-/* the same on packed cells A = (a1,a2,a3,a4), B = (b1,b2,b3,b4) */
-DSVCU_DEV unsigned
-me_cell4(uint32_t A, uint32_t B, const MePsy &p)
-{
-    int s0 = (int) ((me_dot4(A, ME_ONES, 2)) >> 2), s1 = (int) ((me_dot4(B, ME_ONES, 2)) >> 2);
-    int se = (int) ((me_dot4(me_absdiff4(A, B), ME_ONES, 2)) >> 2);
-    int ta = (int) ((me_dot4(me_absdiff4(A, me_perm(A, A, 0x0321)), ME_ONES, 2)) >> 2);
-    int tb = (int) ((me_dot4(me_absdiff4(B, me_perm(B, B, 0x0321)), ME_ONES, 2)) >> 2);
-    unsigned acc = (unsigned) (me_sqr(se) << p.err_w);
-    acc += (unsigned) (me_sqr(ta - tb) << p.tex_w);
-    acc += (unsigned) (me_sqr(s0 - s1) << p.avg_w);
-    return acc;
-}
-
-/* raw accumulator of the psy metric over w x h (umetr_wxh, hme.c:191-196) */
-DSVCU_DEV unsigned
-me_umetr(const uint8_t *a, int as, const uint8_t *b, int bs, int w, int h, const MePsy &p)
-{
-    int cw = w / 2, ch = h / 2, n = cw * ch;
-    unsigned acc = 0;
-    const int gs = me_gshift(w);
-    if (gs >= 0) {
-        /* one work item = 4 pixels x 2 rows = two 2x2 cells */
-        const int ng = ch << gs, gm = (1 << gs) - 1;
-        /* the source block is word-aligned at every level whose block origin is
-         * a multiple of 4 (always at level 0): one load instead of two per word */
-        const bool al = ((((uintptr_t) a) | (unsigned) as) & 3) == 0;
-        for (int g = ME_LANE; g < ng; g += ME_NL) {
-            int y = (g >> gs) * 2, x = (g & gm) * 4;
-            uint32_t a0 = al ? me_ld4a(a + y * as + x) : me_ld4(a + y * as + x);
-            uint32_t a1 = al ? me_ld4a(a + (y + 1) * as + x) : me_ld4(a + (y + 1) * as + x);
-            uint32_t b0 = me_ld4(b + y * bs + x), b1 = me_ld4(b + (y + 1) * bs + x);
-            acc += me_cell4(me_perm(a0, a1, 0x5410), me_perm(b0, b1, 0x5410), p);
-            acc += me_cell4(me_perm(a0, a1, 0x7632), me_perm(b0, b1, 0x7632), p);
-        }
-        return me_wsumu(acc);
-    }
-    for (int k = ME_LANE; k < n; k += ME_NL) {
-        int j = k / cw, i = k - j * cw;
-        const uint8_t *pa = a + (2 * j) * as + 2 * i, *pb = b + (2 * j) * bs + 2 * i;
-        acc += me_cell(pa[0], pa[1], pa[as], pa[as + 1], pb[0], pb[1], pb[bs], pb[bs + 1], p);
-    }
-    return me_wsumu(acc);
-}
-
-/* fastmetr (hme.c:271-306): sqrt-normalised */
-DSVCU_DEV unsigned
-me_metr(const uint8_t *a, int as, const uint8_t *b, int bs, int w, int h, const MePsy &p)
-{
-    if (w == 0 || h == 0) return 0x7fffffffu;
-    unsigned acc = me_umetr(a, as, b, bs, w, h, p);
-    return me_isqrt(acc) * (unsigned) w * (unsigned) h / (unsigned) me_avg2(w, h);
-}
-
-/* SSE over w x h (hme.c:198-242) */
-DSVCU_DEV unsigned
-me_sse(const uint8_t *a, int as, const uint8_t *b, int bs, int w, int h)
-{
-    if (w == 0 || h == 0) return 0x7fffffffu;
-    unsigned acc = 0;
-    int n = w * h;
-    const int gs = me_gshift(w);
-    if (gs >= 0) {
-        const int ng = h << gs, gm = (1 << gs) - 1;
-        const bool al = ((((uintptr_t) a) | (unsigned) as) & 3) == 0;
-        for (int g = ME_LANE; g < ng; g += ME_NL) {
-            int y = g >> gs, x = (g & gm) * 4;
-            uint32_t sa = al ? me_ld4a(a + y * as + x) : me_ld4(a + y * as + x);
-            uint32_t d = me_absdiff4(sa, me_ld4(b + y * bs + x));
-            acc = me_dot4(d, d, acc);
-        }
-        return me_wsumu(acc);
-    }
-    for (int k = ME_LANE; k < n; k += ME_NL) {
-        int j = k / w, i = k - j * w;
-        int d = (int) a[j * as + i] - (int) b[j * bs + i];
-        acc += (unsigned) (d * d);
-    }
-    return me_wsumu(acc);
-}
-
-DSVCU_DEV unsigned
-me_hier_metr(int level, const uint8_t *a, int as, const uint8_t *b, int bs, int w, int h, const MePsy &p)
-{
-    if (level > 1) return me_sse(a, as, b, bs, w, h);
-    return me_metr(a, as, b, bs, w, h, p);
-}
-
-/* ---- MV field helpers (dsv.c:324-447) ---- */
-
-/* entries of the level being built are written by other warps: bypass L1 */
-DSVCU_DEV void
-me_ldmv(const dsvcu_mv *p, int *x, int *y, unsigned *fl)
-{
-#ifndef DSVCU_EMU
-    int w = *(volatile const int *) p;
-    *x = (int16_t) (w & 0xffff);
-    *y = (int16_t) (w >> 16);
-    if (fl) *fl = *((volatile const unsigned *) p + 1);
-#else
-    *x = p->x;
-    *y = p->y;
-    if (fl) *fl = p->flags;
-#endif
-}
-
-DSVCU_DEV int
-me_grad_pick(int left, int top, int topleft)
-{
-    int g = left + top - topleft;
-    return (me_abs(g - left) < me_abs(g - top)) ? left : top;
-}
-
-DSVCU_DEV void
-me_movec_pred(const dsvcu_mv *vecs, int nbh, int x, int y, int *px, int *py)
-{
-    int lx = 0, ly = 0, tx = 0, ty = 0, dx = 0, dy = 0;
-    const dsvcu_mv *c = vecs + x + y * nbh;
-    if (x > 0) {
-        me_ldmv(c - 1, &lx, &ly, NULL);
-    }
-    if (y > 0) {
-        me_ldmv(c - nbh, &tx, &ty, NULL);
-        if (x > 0) {
-            me_ldmv(c - nbh - 1, &dx, &dy, NULL);
-        }
-    }
-    *px = me_grad_pick(lx, tx, dx);
-    *py = me_grad_pick(ly, ty, dy);
-}
-
-DSVCU_DEV int
-me_seg_len(int v)
-{
-    /* 2 * floor(log2(|v| + 1)) + 2 */
-    if (v < 0) v = -v;
-    v++;
-#ifndef DSVCU_EMU
-    return (31 - __clz(v)) * 2 + 2;
-#else
-    return (31 - __builtin_clz((unsigned) v)) * 2 + 2;
-#endif
-}
-
-/* mv_cost (hme.c:354-366) on top of dsv_mv_cost (dsv.c:357-374) */
-/* the predictor of a block depends only on its left / top / top-left
- * neighbours, which are final before the block starts: computed once per block
- * (MePred) instead of inside every rate term */
-struct MePred {
-    int x, y;
-};
-
-DSVCU_DEV int
-me_mv_cost(const MeArgs &A, const MePred &pr, int mx, int my, int level)
-{
-    int px = pr.x, py = pr.y, bits, b2sr, q = A.quant;
-    int sqr = level > 1;
-    bits = me_seg_len(mx - px) + me_seg_len(my - py);
-    b2sr = A.b2sr;
-    bits += bits * b2sr >> 7;
-    if (sqr) bits *= bits;
-    bits = min(bits, 1 << 19);
-    if (sqr) return bits * (q * q >> 12) >> (12 - 2);
-    return 3 * bits * q >> 12;
-}
-
-DSVCU_DEV int
-me_neighbordif(const dsvcu_mv *vecs, int nbh, int x, int y)
-{
-    const dsvcu_mv *c = vecs + x + y * nbh;
-    int cx, cy, nx, ny;
-    unsigned nf;
-    me_ldmv(c, &cx, &cy, NULL);
-    int lx = cx, ly = cy, tx = cx, ty = cy;
-    if (me_abs(cx) < 2 && me_abs(cy) < 2) return 0;
-    if (x > 0) {
-        me_ldmv(c - 1, &nx, &ny, &nf);
-        if ((nx | ny) != 0 && !(nf & MVF_SKIP)) {
-            lx = nx;
-            ly = ny;
-        }
-    }
-    if (y > 0) {
-        me_ldmv(c - nbh, &nx, &ny, &nf);
-        if ((nx | ny) != 0 && !(nf & MVF_SKIP)) {
-            tx = nx;
-            ty = ny;
-        }
-    }
-    return (me_abs(lx - cx) + me_abs(ly - cy) + me_abs(tx - cx) + me_abs(ty - cy)) / 3;
-}
-
-/* ---- block statistics (hme.c:492-775); every lane returns the same value ---- */
-
-DSVCU_DEV int
-me_block_avg(const uint8_t *a, int as, int w, int h)
-{
-    int s = 0, n = w * h;
-    const int gs = me_gshift(w);
-    if (gs >= 0) {
-        const int ng = h << gs, gm = (1 << gs) - 1;
-        unsigned u = 0;
-        for (int g = ME_LANE; g < ng; g += ME_NL) {
-            u = me_dot4(me_ld4(a + (g >> gs) * as + (g & gm) * 4), ME_ONES, u);
-        }
-        return me_wsum((int) u) / (w * h);
-    }
-    for (int k = ME_LANE; k < n; k += ME_NL) {
-        int j = k / w, i = k - j * w;
-        s += a[j * as + i];
-    }
-    return me_wsum(s) / (w * h);
-}
-
-/* sums of horizontal / vertical absolute gradients (block_tex core) */
-DSVCU_DEV void
-me_grad_sums(const uint8_t *a, int as, int w, int h, unsigned *psh, unsigned *psv, int *psum)
-{
-    unsigned sh = 0, sv = 0;
-    int s = 0, n = w * h;
-    const int gs = me_gshift(w);
-    if (gs >= 0) {
-        const int ng = h << gs, gm = (1 << gs) - 1;
-        unsigned us = 0;
-        for (int g = ME_LANE; g < ng; g += ME_NL) {
-            int y = g >> gs, x = (g & gm) * 4;
-            const uint8_t *p = a + y * as + x;
-            uint32_t c = me_ld4(p);
-            uint32_t dl = me_absdiff4(c, me_ld4(p - 1));
-            us = me_dot4(c, ME_ONES, us);
-            if (x == 0) dl &= 0xffffff00u; /* column 0 has no left neighbour */
-            sh = me_dot4(dl, ME_ONES, sh);
-            if (y > 0) sv = me_dot4(me_absdiff4(c, me_ld4(p - as)), ME_ONES, sv);
-        }
-        *psh = me_wsumu(sh);
-        *psv = me_wsumu(sv);
-        *psum = me_wsum((int) us);
-        return;
-    }
-    for (int k = ME_LANE; k < n; k += ME_NL) {
-        int j = k / w, i = k - j * w;
-        int px = a[j * as + i];
-        s += px;
-        if (i > 0) sh += (unsigned) me_abs(px - a[j * as + i - 1]);
-        if (j > 0) sv += (unsigned) me_abs(px - a[(j - 1) * as + i]);
-    }
-    *psh = me_wsumu(sh);
-    *psv = me_wsumu(sv);
-    *psum = me_wsum(s);
-}
-
-DSVCU_DEV unsigned
-me_block_tex(const uint8_t *a, int as, int w, int h)
-{
-    unsigned sh, sv;
-    int s;
-    me_grad_sums(a, as, w, h, &sh, &sv, &s);
-    return max(sh, sv);
-}
-
-DSVCU_DEV int
-me_abs_dev(const uint8_t *a, int as, int w, int h, int mean)
-{
-    int var = 0, n = w * h;
-    const int gs = me_gshift(w);
-    if (gs >= 0 && mean >= 0 && mean <= 255) {
-        const int ng = h << gs, gm = (1 << gs) - 1;
-        const uint32_t m4 = (uint32_t) mean * ME_ONES;
-        unsigned u = 0;
-        for (int g = ME_LANE; g < ng; g += ME_NL) {
-            u = me_dot4(me_absdiff4(me_ld4(a + (g >> gs) * as + (g & gm) * 4), m4), ME_ONES, u);
-        }
-        return me_wsum((int) u);
-    }
-    for (int k = ME_LANE; k < n; k += ME_NL) {
-        int j = k / w, i = k - j * w;
-        var += me_abs((int) a[j * as + i] - mean);
-    }
-    return me_wsum(var);
-}
-
-DSVCU_DEV int
-me_block_var(const uint8_t *a, int as, int w, int h, unsigned *avg)
-{
-    int s = me_block_avg(a, as, w, h);
-    *avg = (unsigned) s;
-    return me_abs_dev(a, as, w, h, s);
-}
-
-DSVCU_DEV int
-me_block_detail(const uint8_t *a, int as, int w, int h, unsigned *avg)
-{
-    unsigned sh, sv;
-    int s, var, tex;
-    me_grad_sums(a, as, w, h, &sh, &sv, &s);
-    s /= (w * h);
-    *avg = (unsigned) s;
-    var = me_abs_dev(a, as, w, h, s) >> 1;
-    tex = (int) max(sh, sv) - var;
-    return var + max(tex, 0);
-}
-
-DSVCU_DEV int
-me_quant_tex(const uint8_t *a, int as, int w, int h)
-{
-    unsigned sh = 0, sv = 0;
-    int n = w * h;
-    const int gs = me_gshift(w);
-    if (gs >= 0) {
-        const int ng = h << gs, gm = (1 << gs) - 1;
-        for (int g = ME_LANE; g < ng; g += ME_NL) {
-            int y = g >> gs, x = (g & gm) * 4;
-            const uint8_t *p = a + y * as + x;
-            uint32_t c = (me_ld4(p) >> 4) & 0x0f0f0f0fu;
-            uint32_t dr = me_absdiff4(c, (me_ld4(p + 1) >> 4) & 0x0f0f0f0fu);
-            if (x == w - 4) dr &= 0x00ffffffu; /* last column has no right neighbour */
-            sh = me_dot4(dr, dr, sh);
-            if (y > 0) {
-                uint32_t du = me_absdiff4(c, (me_ld4(p - as) >> 4) & 0x0f0f0f0fu);
-                sv = me_dot4(du, du, sv);
-            }
-        }
-        sh = me_wsumu(sh);
-        sv = me_wsumu(sv);
-        return (int) (me_isqrt(max(sh, sv)) / (unsigned) me_avg2(w, h));
-    }
-    for (int k = ME_LANE; k < n; k += ME_NL) {
-        int j = k / w, i = k - j * w;
-        int px = a[j * as + i] >> 4;
-        if (i < w - 1) {
-            int d = px - (a[j * as + i + 1] >> 4);
-            sh += (unsigned) (d * d);
-        }
-        if (j > 0) {
-            int d = px - (a[(j - 1) * as + i] >> 4);
-            sv += (unsigned) (d * d);
-        }
-    }
-    sh = me_wsumu(sh);
-    sv = me_wsumu(sv);
-    return (int) (me_isqrt(max(sh, sv)) / (unsigned) me_avg2(w, h));
-}
-
-/* 16-bin histograms are built in per-warp shared memory */
-DSVCU_DEV void
-me_hist_clear(int *hist)
-{
-    for (int k = ME_LANE; k < 16; k += ME_NL) hist[k] = 0;
-    DSVCU_SYNCWARP();
-}
-
-DSVCU_DEV unsigned
-me_block_hist_var(const uint8_t *a, int as, int w, int h, int *hist)
-{
-    unsigned avg, quant16, var = 0;
-    int n = w * h;
-    const int gs = me_gshift(w);
-    me_hist_clear(hist);
-    avg = (unsigned) me_block_avg(a, as, w, h);
-    if (avg == 0) avg = 1;
-    quant16 = ((1u << 3) << 16) / avg;
-    if (gs >= 0) {
-        const int ng = h << gs, gm = (1 << gs) - 1;
-        for (int g = ME_LANE; g < ng; g += ME_NL) {
-            uint32_t c = me_ld4(a + (g >> gs) * as + (g & gm) * 4);
-            for (int k = 0; k < 4; k++) {
-                unsigned hi = ((c >> (8 * k)) & 255u) * quant16 >> 16;
-                atomicAdd(&hist[hi > 15 ? 15 : hi], 1);
-            }
-        }
-    } else {
-        for (int k = ME_LANE; k < n; k += ME_NL) {
-            int j = k / w, i = k - j * w;
-            int hi = (int) (a[j * as + i] * quant16 >> 16);
-            atomicAdd(&hist[hi < 0 ? 0 : (hi > 15 ? 15 : hi)], 1);
-        }
-    }
-    DSVCU_SYNCWARP();
-    avg = 0;
-    for (int x = 0; x < 16; x++) avg += (unsigned) hist[x];
-    avg /= 16;
-    for (int x = 0; x < 16; x++) var += ((unsigned) hist[x] - avg) * ((unsigned) hist[x] - avg);
-    DSVCU_SYNCWARP();
-    return (var * 16 * 16) / (unsigned) (16 * w * h * w * h);
-}
-
-DSVCU_DEV int
-me_block_peaks(const uint8_t *a, int as, int w, int h, int *hist, int bavg)
-{
-    int avg = bavg, maxv = 0, npeaks = 0, quant16, cw, ch, n;
-    me_hist_clear(hist);
-    if (avg == 0) avg = 1;
-    quant16 = ((1 << 3) << 16) / avg;
-    cw = w / 2;
-    ch = h / 2;
-    n = cw * ch;
-    {
-        const int gs = me_gshift(w);
-        if (gs >= 0) {
-            const int ng = ch << gs, gm = (1 << gs) - 1;
-            for (int g = ME_LANE; g < ng; g += ME_NL) {
-                int y = (g >> gs) * 2, x = (g & gm) * 4;
-                uint32_t r0 = me_ld4(a + y * as + x), r1 = me_ld4(a + (y + 1) * as + x);
-                int d0 = (int) (me_dot4(me_perm(r0, r1, 0x5410), ME_ONES, 2) >> 2);
-                int d1 = (int) (me_dot4(me_perm(r0, r1, 0x7632), ME_ONES, 2) >> 2);
-                atomicAdd(&hist[min(d0 * quant16 >> 16, 15)], 1);
-                atomicAdd(&hist[min(d1 * quant16 >> 16, 15)], 1);
-            }
-        } else {
-            for (int k = ME_LANE; k < n; k += ME_NL) {
-                int j = k / cw, i = k - j * cw;
-                const uint8_t *p = a + (2 * j) * as + 2 * i;
-                int ds = (int) me_uavg4(p[0], p[1], p[as], p[as + 1]);
-                int hi = ds * quant16 >> 16;
-                atomicAdd(&hist[min(hi, 15)], 1);
-            }
-        }
-    }
-    DSVCU_SYNCWARP();
-    avg = 0;
-    for (int x = 0; x < 16; x++) {
-        maxv = max(maxv, hist[x]);
-        avg += hist[x];
-    }
-    avg /= 16;
-    maxv >>= 2;
-    for (int x = 0; x < 16; x++) {
-        int c = hist[x], is_peak = 1;
-        if (x > 0) is_peak &= (c > hist[x - 1]);
-        if (x < 15) is_peak &= (c > hist[x + 1]);
-        is_peak &= (c > maxv) || (c > avg);
-        npeaks += is_peak;
-    }
-    DSVCU_SYNCWARP();
-    return npeaks;
-}
-
-DSVCU_DEV void
-me_c_average(const MePlane *pl, int x, int y, int w, int h, int *uavg, int *vavg)
-{
-    int su = 0, sv = 0, n = w * h;
-    const int gs = me_gshift(w);
-    if (gs >= 0) {
-        const int ng = h << gs, gm = (1 << gs) - 1;
-        unsigned uu = 0, uv = 0;
-        for (int g = ME_LANE; g < ng; g += ME_NL) {
-            int j = g >> gs, i = (g & gm) * 4;
-            uu = me_dot4(me_ld4(pl[1].data + (y + j) * pl[1].stride + x + i), ME_ONES, uu);
-            uv = me_dot4(me_ld4(pl[2].data + (y + j) * pl[2].stride + x + i), ME_ONES, uv);
-        }
-        su = (int) uu;
-        sv = (int) uv;
-    } else {
-        for (int k = ME_LANE; k < n; k += ME_NL) {
-            int j = k / w, i = k - j * w;
-            su += pl[1].data[(y + j) * pl[1].stride + x + i];
-            sv += pl[2].data[(y + j) * pl[2].stride + x + i];
-        }
-    }
-    su = me_wsum(su);
-    sv = me_wsum(sv);
-    /* w*h == 0 divides by zero in the reference too; callers never pass it */
-    *uavg = su / (w * h);
-    *vavg = sv / (w * h);
-}
-
-struct MeChroma {
-    int nature, hifreq, greyish, skinnish;
-};
-
-DSVCU_DEV void
-me_chroma_analysis(MeChroma *c, int y, int u, int v)
-{
-    c->nature = u < 128 && v < 160;
-    c->greyish = me_abs(u - 128) < 8 && me_abs(v - 128) < 8;
-    c->skinnish = (y > 80) && (y < 230) && me_abs(u - 108) < 24 && me_abs(v - 148) < 24;
-    c->hifreq = (u > 160) && !c->greyish && !c->skinnish;
-}
-
-DSVCU_DEV int
-me_invalid_block(int fw, int fh, int bx, int by, int bw, int bh, int pad)
-{
-    return (bx - pad) < -ME_BORDER || (by - pad) < -ME_BORDER || (bx + bw + pad) >= (fw + ME_BORDER) ||
-           (by + bh + pad) >= (fh + ME_BORDER);
-}
-
-/* max over the four quadrants of the raw psy metric, luma + both chroma planes
- * (yuv_max_subblock_err, hme.c:368-411) */
-DSVCU_DEV void
-me_yuv_max_sub(unsigned out[3], const MePlane *sp, const MePlane *rp, int bx, int by, int brx, int bry, int bw, int bh,
-               int cbx, int cby, int cbrx, int cbry, int cbw, int cbh, const MePsy &psy)
-{
-    bw /= 2;
-    bh /= 2;
-    cbw /= 2;
-    cbh /= 2;
-    for (int z = 0; z < 3; z++) {
-        unsigned sub[4] = { 0, 0, 0, 0 };
-        int pos = 0;
-        for (int g = 0; g <= bh; g += (bh + !bh)) {
-            for (int f = 0; f <= bw; f += (bw + !bw)) {
-                const uint8_t *s = sp[z].data + (by + g) * sp[z].stride + bx + f;
-                const uint8_t *r = rp[z].data + (bry + g) * rp[z].stride + brx + f;
-                if (pos < 4) sub[pos] = me_umetr(s, sp[z].stride, r, rp[z].stride, bw, bh, psy);
-                pos++;
-            }
-        }
-        bx = cbx;
-        by = cby;
-        brx = cbrx;
-        bry = cbry;
-        bw = cbw;
-        bh = cbh;
-        out[z] = max(max(sub[0], sub[1]), max(sub[2], sub[3]));
-    }
-}
-
-/* calc_EPRM (hme.c:452-490): does MV / intra(ref avg) / intra(src avg)
- * prediction clip anywhere in the block?  OR over pixels == the early-out scan */
-DSVCU_DEV void
-me_calc_eprm(const uint8_t *src, int ss, const uint8_t *mvr, int rs, int avg_src, int avg_ref, int w, int h, int *eprmi,
-             int *eprmd, int *eprmr)
-{
-    int ci = 0, cd = 0, cr = 0, n = w * h;
-    avg_src -= 128;
-    avg_ref -= 128;
-    {
-        const int gs = me_gshift(w);
-        if (gs >= 0) {
-            const int ng = h << gs, gm = (1 << gs) - 1;
-            for (int g = ME_LANE; g < ng; g += ME_NL) {
-                int j = g >> gs, i = (g & gm) * 4;
-                uint32_t sw = me_ld4(src + j * ss + i), rw = me_ld4(mvr + j * rs + i);
-                for (int k = 0; k < 4; k++) {
-                    int s = (int) ((sw >> (8 * k)) & 255u);
-                    cr |= ((s - (int) ((rw >> (8 * k)) & 255u)) + 128) & ~0xff;
-                    ci |= (s - avg_ref) & ~0xff;
-                    cd |= (s - avg_src) & ~0xff;
-                }
-            }
-        } else {
-            for (int k = ME_LANE; k < n; k += ME_NL) {
-                int j = k / w, i = k - j * w;
-                int s = src[j * ss + i];
-                cr |= ((s - (int) mvr[j * rs + i]) + 128) & ~0xff;
-                ci |= (s - avg_ref) & ~0xff;
-                cd |= (s - avg_src) & ~0xff;
-            }
-        }
-    }
-    *eprmi = me_wor(ci != 0);
-    *eprmd = me_wor(cd != 0);
-    *eprmr = me_wor(cr != 0);
-}
-
-/* ---- sub-pel refinement (hme.c:777-837, :1051-1164) ---- */
-
 #define ME_HPF(a, b, c, d) ((5 * ((b) + (c))) - ((a) + (d)))
-
-/* Half-pel image (34 x 34, HP_STRIDE) of the 17 x 17 window at r, as the
- * reference's hpel() builds it (hme.c:787-813).  The reference then expands it
- * to a 68 x 68 quarter-pel image by bilinear averaging (qpel(), :815-837) of
- * which the search samples 7 x 256 points; here those points are averaged from
- * the half-pel image on the fly (me_qsample), same arithmetic. */
 #define ME_WIN (SP_DIM + 3) /* full-pel window rows/cols -1 .. SP_DIM+1 */
-DSVCU_DEV void
-me_interp(uint8_t *tmph, uint8_t *win, int16_t *hbuf, const uint8_t *r, int rs)
-{
-    /* stage the full-pel window once */
-    for (int k = ME_LANE; k < ME_WIN * ME_WIN; k += ME_NL) {
-        int j = k / ME_WIN, i = k - j * ME_WIN;
-        win[k] = r[(j - 1) * rs + i - 1];
-    }
-    DSVCU_SYNCWARP();
-    /* horizontal half-pel sums for rows -1 .. SP_DIM+1 */
-    for (int k = ME_LANE; k < ME_WIN * SP_DIM; k += ME_NL) {
-        int j = k / SP_DIM, i = k - j * SP_DIM;
-        const uint8_t *p = win + j * ME_WIN + i + 1;
-        hbuf[k] = (int16_t) ME_HPF(p[-1], p[0], p[1], p[2]);
-    }
-    DSVCU_SYNCWARP();
-    for (int k = ME_LANE; k < SP_DIM * SP_DIM; k += ME_NL) {
-        int j = k / SP_DIM, i = k - j * SP_DIM;
-        const uint8_t *p = win + (j + 1) * ME_WIN + i + 1;
-        uint8_t *d = tmph + (2 * j) * HP_STRIDE + 2 * i;
-        int c = ME_HPF(hbuf[k], hbuf[k + SP_DIM], hbuf[k + 2 * SP_DIM], hbuf[k + 3 * SP_DIM]);
-        d[0] = p[0];
-        d[1] = (uint8_t) me_u8((ME_HPF(p[-1], p[0], p[1], p[2]) + 4) >> 3);
-        d[HP_STRIDE] = (uint8_t) me_u8((ME_HPF(p[-ME_WIN], p[0], p[ME_WIN], p[2 * ME_WIN]) + 4) >> 3);
-        d[HP_STRIDE + 1] = (uint8_t) me_u8((c + 32) >> 6);
-    }
-    DSVCU_SYNCWARP();
-}
-
-/* quarter-pel sample (qx, qy) of the image the reference's qpel() would build:
- * a, avg2(a,b), avg2(a,c) or avg4(a,b,c,e) by the parity of (qx, qy).  All four
- * cases are (a + h[ox] + h[oy*S] + h[ox + oy*S] + 2) >> 2 with ox, oy the parity
- * bits ((2a+2b+2)>>2 == (a+b+1)>>1), so the sample is branch-free. */
-DSVCU_DEV int
-me_qsample(const uint8_t *tmph, int qx, int qy)
-{
-    const uint8_t *h0 = tmph + (qy >> 1) * HP_STRIDE + (qx >> 1);
-    int ox = qx & 1, oy = (qy & 1) * HP_STRIDE;
-    return (h0[0] + h0[ox] + h0[oy] + h0[ox + oy] + 2) >> 2;
-}
-
-/* psy metric of the 16 x 16 source window against the quarter-pel image at
- * offset (tx, ty) quarter pels (qpsad, hme.c:244-269) */
-DSVCU_DEV unsigned
-me_qpsad(const uint8_t *a, int as, const uint8_t *tmph, int tx, int ty, const MePsy &psy)
-{
-    unsigned acc = 0;
-    for (int g = ME_LANE; g < (SP_SZ / 2) * (SP_SZ / 4); g += ME_NL) {
-        /* one work item = 4 source pixels x 2 rows = two cells */
-        int y = (g >> 2) * 2, x = (g & 3) * 4;
-        uint32_t a0 = me_ld4(a + y * as + x), a1 = me_ld4(a + (y + 1) * as + x);
-        int qx = 4 + tx + 4 * x, qy = 4 + ty + 4 * y;
-        uint32_t B0 = (uint32_t) me_qsample(tmph, qx, qy) | ((uint32_t) me_qsample(tmph, qx + 4, qy) << 8) |
-                      ((uint32_t) me_qsample(tmph, qx, qy + 4) << 16) | ((uint32_t) me_qsample(tmph, qx + 4, qy + 4) << 24);
-        uint32_t B1 = (uint32_t) me_qsample(tmph, qx + 8, qy) | ((uint32_t) me_qsample(tmph, qx + 12, qy) << 8) |
-                      ((uint32_t) me_qsample(tmph, qx + 8, qy + 4) << 16) | ((uint32_t) me_qsample(tmph, qx + 12, qy + 4) << 24);
-        acc += me_cell4(me_perm(a0, a1, 0x5410), B0, psy);
-        acc += me_cell4(me_perm(a0, a1, 0x7632), B1, psy);
-    }
-    acc = me_wsumu(acc);
-    return me_isqrt(acc) * (unsigned) SP_SZ * (unsigned) SP_SZ / (unsigned) SP_SZ;
-}
-
-/* cell metric with the source-side terms (mean s0, texture ta) precomputed */
-DSVCU_DEV unsigned
-me_cell4_pre(uint32_t A, int s0, int ta, uint32_t B, const MePsy &p)
-{
-    int s1 = (int) ((me_dot4(B, ME_ONES, 2)) >> 2);
-    int se = (int) ((me_dot4(me_absdiff4(A, B), ME_ONES, 2)) >> 2);
-    int tb = (int) ((me_dot4(me_absdiff4(B, me_perm(B, B, 0x0321)), ME_ONES, 2)) >> 2);
-    unsigned acc = (unsigned) (me_sqr(se) << p.err_w);
-    acc += (unsigned) (me_sqr(ta - tb) << p.tex_w);
-    acc += (unsigned) (me_sqr(s0 - s1) << p.avg_w);
-    return acc;
-}
-
-/* me_qpsad for up to 7 offsets in one pass over the source window: the source
- * cells are loaded (and their own terms computed) once, and the offsets give
- * independent accumulation chains */
 #define ME_MAXSP 7
-DSVCU_DEV void
-me_qpsad_multi(const uint8_t *a, int as, const uint8_t *tmph, int nv, const int *tx, const int *ty, const MePsy &psy,
-               unsigned *out)
-{
-    unsigned acc[ME_MAXSP];
-    for (int v = 0; v < ME_MAXSP; v++) acc[v] = 0;
-    for (int g = ME_LANE; g < (SP_SZ / 2) * (SP_SZ / 4); g += ME_NL) {
-        int y = (g >> 2) * 2, x = (g & 3) * 4;
-        uint32_t a0 = me_ld4(a + y * as + x), a1 = me_ld4(a + (y + 1) * as + x);
-        uint32_t A0 = me_perm(a0, a1, 0x5410), A1 = me_perm(a0, a1, 0x7632);
-        int s00 = (int) (me_dot4(A0, ME_ONES, 2) >> 2), s01 = (int) (me_dot4(A1, ME_ONES, 2) >> 2);
-        int ta0 = (int) (me_dot4(me_absdiff4(A0, me_perm(A0, A0, 0x0321)), ME_ONES, 2) >> 2);
-        int ta1 = (int) (me_dot4(me_absdiff4(A1, me_perm(A1, A1, 0x0321)), ME_ONES, 2) >> 2);
-#ifndef DSVCU_EMU
-#pragma unroll
-#endif
-        for (int v = 0; v < ME_MAXSP; v++) {
-            if (v < nv) {
-                int qx = 4 + tx[v] + 4 * x, qy = 4 + ty[v] + 4 * y;
-                uint32_t B0 = (uint32_t) me_qsample(tmph, qx, qy) | ((uint32_t) me_qsample(tmph, qx + 4, qy) << 8) |
-                              ((uint32_t) me_qsample(tmph, qx, qy + 4) << 16) |
-                              ((uint32_t) me_qsample(tmph, qx + 4, qy + 4) << 24);
-                uint32_t B1 = (uint32_t) me_qsample(tmph, qx + 8, qy) | ((uint32_t) me_qsample(tmph, qx + 12, qy) << 8) |
-                              ((uint32_t) me_qsample(tmph, qx + 8, qy + 4) << 16) |
-                              ((uint32_t) me_qsample(tmph, qx + 12, qy + 4) << 24);
-                acc[v] += me_cell4_pre(A0, s00, ta0, B0, psy) + me_cell4_pre(A1, s01, ta1, B1, psy);
-            }
-        }
-    }
-    for (int v = 0; v < ME_MAXSP; v++) {
-        if (v < nv) out[v] = me_isqrt(me_wsumu(acc[v])) * (unsigned) SP_SZ * (unsigned) SP_SZ / (unsigned) SP_SZ;
-    }
-}
-
 #define ME_MEMO 32
-struct MeScratch {
-    uint8_t tmph[(2 + HP_STRIDE) * (2 + HP_STRIDE)];
-    uint8_t win[ME_WIN * ME_WIN + 16];
-    int16_t hbuf[(SP_DIM + 3) * SP_DIM + 4];
-    int hist[16];
-    /* full-pel metric memo of the current block: position -> raw metric */
-    short memo_x[ME_MEMO], memo_y[ME_MEMO];
-    unsigned memo_v[ME_MEMO];
-    /* the block's prepass record, fetched from global memory in one batch */
-    uint32_t pre_words[160];
-};
-
-/* Sub-pel refinement, split in two.  me_subpel_measure: everything that depends
- * only on the full-pel position -- the four neighbour SSEs that order the
- * search (hme.c:1084-1136), the half-pel image and the metric at the <= 7 test
- * offsets in the reference's order (:1137-1160).  me_subpel_decide: the scalar
- * part that needs the block's running best score and rate predictor. */
-struct MeSubpel {
-    int nv;
-    int tx[ME_MAXSP], ty[ME_MAXSP];
-    unsigned sc[ME_MAXSP];
-};
-
-DSVCU_DEV void
-me_subpel_measure(const MeArgs &A, MeScratch *S, MeSubpel *M, int fpelx, int fpely, int bx, int by, int bw, int bh,
-                  const MePsy &psy)
-{
-    const MePlane &sp = A.src[0], &rp = A.ref[0];
-    unsigned quad[4], ms1, ms2;
-    int pri[2], sec[2], diag[2], xx, yy, nv = 0;
-    const int ddx[4] = { 1, -1, 0, 0 }, ddy[4] = { 0, 0, 1, -1 };
-    {
-        const uint8_t *s = sp.data + by * sp.stride + bx;
-        for (int n = 0; n < 4; n++) {
-            const uint8_t *r = rp.data + (by + fpely + ddy[n]) * rp.stride + bx + fpelx + ddx[n];
-            quad[n] = me_sse(s, sp.stride, r, rp.stride, bw, bh);
-        }
-    }
-    xx = bx + ((bw >> 1) - ((SP_SZ + 1) / 2));
-    yy = by + ((bh >> 1) - ((SP_SZ + 1) / 2));
-    me_interp(S->tmph, S->win, S->hbuf, rp.data + (yy + fpely - 1) * rp.stride + xx + fpelx - 1, rp.stride);
-
-    pri[0] = 0; pri[1] = -1;
-    sec[0] = -1; sec[1] = 0;
-    ms1 = quad[1];
-    ms2 = quad[3];
-    if (quad[3] >= quad[2]) {
-        pri[0] = 0; pri[1] = 1;
-        ms2 = quad[2];
-    }
-    if (quad[1] >= quad[0]) {
-        sec[0] = 1; sec[1] = 0;
-        ms1 = quad[0];
-    }
-    if (ms2 > ms1) {
-        int t0 = sec[0], t1 = sec[1];
-        sec[0] = pri[0]; sec[1] = pri[1];
-        pri[0] = t0; pri[1] = t1;
-    }
-    diag[0] = pri[0] + sec[0];
-    diag[1] = pri[1] + sec[1];
-    /* test order of the reference: half then quarter steps along pri, sec,
-     * diag, then pri + diag */
-    for (int n = 0; n <= 6; n++) {
-        int t[2];
-        if (n == 6) {
-            t[0] = pri[0] + diag[0];
-            t[1] = pri[1] + diag[1];
-        } else {
-            int hp = !(n & 1);
-            const int *tv = (n >> 1) == 0 ? pri : ((n >> 1) == 1 ? sec : diag);
-            t[0] = tv[0] * (1 << hp);
-            t[1] = tv[1] * (1 << hp);
-        }
-        if (((t[0] | t[1]) & 1) && A.effort < 8) continue;
-        M->tx[nv] = t[0];
-        M->ty[nv] = t[1];
-        nv++;
-    }
-    M->nv = nv;
-    me_qpsad_multi(sp.data + yy * sp.stride + xx, sp.stride, S->tmph, nv, M->tx, M->ty, psy, M->sc);
-}
-
-DSVCU_DEV unsigned
-me_subpel_decide(const MeArgs &A, const MeSubpel *M, int *outx, int *outy, int fpelx, int fpely, const MePred &pr,
-                 unsigned best, int bw, int bh)
-{
-    int yarea = bw * bh, bestv[2] = { 0, 0 };
-    int area_ratio = 8 * (SP_SZ * SP_SZ) / yarea, iarea_ratio = 8 * yarea / (SP_SZ * SP_SZ);
-    best = best * (unsigned) area_ratio >> 3;
-    for (int n = 0; n < M->nv; n++) {
-        unsigned score = M->sc[n] + (unsigned) me_mv_cost(A, pr, fpelx * 4 + M->tx[n], fpely * 4 + M->ty[n], 0);
-        if (best > score) {
-            best = score;
-            bestv[0] = M->tx[n];
-            bestv[1] = M->ty[n];
-        }
-    }
-    *outx = bestv[0];
-    *outy = bestv[1];
-    return best * (unsigned) iarea_ratio >> 3;
-}
+#define ME_PRE_WORDS 256
 
 /* ---- neighbour-independent part of a block, computed for every block of a
- * level in parallel by k_me_prepass and consumed by the wavefront ---- */
+ * level in parallel by k_me_prepass and consumed by the wavefront.
+ *
+ * Besides what is neighbour-independent by construction (source statistics,
+ * the non-spatial candidates and their metrics) the record carries a
+ * SPECULATION: the prepass guesses the block's final full-pel vector S (the
+ * best measured candidate by raw metric, followed through the reference's
+ * descent with an assumed predictor) and computes everything the mode decision
+ * needs AT S -- second sub-pel pass, reference-side statistics, the sub-block
+ * metrics of the no-transmit test, the reference-side half of the intra test.
+ * The wavefront uses those numbers when its real decision lands on S and falls
+ * back to computing them on demand when it does not, so the speculation only
+ * moves work out of the dependency chain; results are identical either way. ---- */
 #define ME_PRE_NB 20 /* temporal (<= 9) + global + parent inliers (<= 9) */
 #define ME_PRE_NM 32
-struct MePre {
+#define ME_SV_RS 1    /* reference-side statistics at S */
+#define ME_SV_BSUB 2  /* sub-block metrics at S (no-transmit test) */
+#define ME_SV_ZSUB 4  /* sub-block metrics at the zero vector (skip test) */
+#define ME_SV_INTRA 8 /* reference quadrant means at S (+ per-quadrant error sums where the gate passes) */
+struct __align__(16) MePre {
     unsigned var_src, avg_src;
     int motion_bias, psy_pack; /* err_w | tex_w << 8 | avg_w << 16 */
     int lax, lay, has_list, nb;
@@ -985,1049 +207,194 @@ struct MePre {
     short bx[ME_PRE_NB], by[ME_PRE_NB]; /* non-spatial candidates after (lax, lay), raw units */
     short mx[ME_PRE_NM], my[ME_PRE_NM]; /* positions already measured ... */
     unsigned mv[ME_PRE_NM];             /* ... and their raw metric */
-    /* level 0: statistics of the block against the reference at (lax, lay) [0]
-     * and at the zero vector [1] (what the mode decision needs once the final
-     * vector is known), source-side quadrant statistics for the intra test,
-     * chroma texture of the source block */
-    int rs_valid[2];
-    unsigned rs_ogrerr[2], rs_var[2], rs_avg[2];
-    int rs_u[2], rs_v[2], rs_eprm[2]; /* eprm: bit0 i, bit1 d, bit2 r */
-    unsigned q_detail[4], q_avg[4];
+    /* level 0 only from here on */
+    int sx, sy, s_valid;                /* speculated full-pel vector, ME_SV_* bits */
+    unsigned rs_ogrerr, rs_var, rs_avg; /* statistics against the reference at S */
+    int rs_u, rs_v, rs_eprm;            /* eprm: bit0 i, bit1 d, bit2 r */
+    unsigned bsub[3], zsub[3];          /* raw max-sub-block metrics at S / at zero */
+    unsigned q_detail[4], q_avg[4];     /* source-side quadrant statistics (intra test) */
+    unsigned qa_sub[4];                 /* mean of the reference quadrants at S */
+    int qi_mask;                        /* quadrants whose error sums below are valid (ratio == 32) */
+    unsigned qi_sub[4], qi_src[4], qi_inter[4];
+    /* the inter error of a quadrant depends on the sub-pel gain `ratio` cell by cell
+     * (hme.c:839-889): ratio-independent part + the 16 per-cell mean absolute errors
+     * of each 8x8 quadrant let the wavefront rebuild it for any ratio */
+    int qi_cells;                       /* 1: qi_rest / qi_ae are filled (16x16 blocks) */
+    unsigned qi_rest[4];
+    uint8_t qi_ae[64];
     int utex, vtex;
-    /* level 0: sub-pel measurements around the parent-average position (lax, lay) */
-    int sp_valid, sp_nv;
-    signed char sp_tx[ME_MAXSP + 1], sp_ty[ME_MAXSP + 1];
-    unsigned sp_sc[ME_MAXSP];
+    /* sub-pel measurements: [0] around the parent average (lax, lay), [1] around S */
+    int sp_valid[2], sp_nv[2];
+    signed char sp_tx[2][ME_MAXSP + 1], sp_ty[2][ME_MAXSP + 1];
+    unsigned sp_sc[2][ME_MAXSP];
+    int pad_[3]; /* sizeof(MePre) is a multiple of 16: the wavefront fetches a record in 16-byte words */
 };
 
-/* ---- intra sub-block tests (hme.c:839-1049) ---- */
-
-DSVCU_DEV void
-me_err_intra(const uint8_t *a, int as, const uint8_t *b, int bs, int avg_sb, int avg_src, int w, int h, unsigned *intra_err,
-             unsigned *intrasrc_err, unsigned *inter_err, const MePsy &psy, int ratio)
-{
-    unsigned isb = 0, isrc = 0, inter = 0;
-    int cw = w / 2, ch = h / 2, n = cw * ch;
-    const int gs = me_gshift(w);
-    if (gs >= 0 && avg_sb >= 0 && avg_sb <= 255 && avg_src >= 0 && avg_src <= 255) {
-        const int ng = ch << gs, gm = (1 << gs) - 1;
-        const uint32_t sb4 = (uint32_t) avg_sb * ME_ONES, sr4 = (uint32_t) avg_src * ME_ONES;
-        for (int g = ME_LANE; g < ng; g += ME_NL) {
-            int y = (g >> gs) * 2, x = (g & gm) * 4;
-            uint32_t a0 = me_ld4(a + y * as + x), a1 = me_ld4(a + (y + 1) * as + x);
-            uint32_t b0 = me_ld4(b + y * bs + x), b1 = me_ld4(b + (y + 1) * bs + x);
-            for (int c = 0; c < 2; c++) {
-                uint32_t A = me_perm(a0, a1, c ? 0x7632 : 0x5410), B = me_perm(b0, b1, c ? 0x7632 : 0x5410);
-                int s0 = (int) (me_dot4(A, ME_ONES, 2) >> 2), s1 = (int) (me_dot4(B, ME_ONES, 2) >> 2);
-                int ae = (int) (me_dot4(me_absdiff4(A, B), ME_ONES, 2) >> 2);
-                int ta = (int) (me_dot4(me_absdiff4(A, me_perm(A, A, 0x0321)), ME_ONES, 2) >> 2);
-                int tb = (int) (me_dot4(me_absdiff4(B, me_perm(B, B, 0x0321)), ME_ONES, 2) >> 2);
-                inter += (unsigned) (me_sqr(ae) * ratio >> (5 - psy.err_w));
-                inter += (unsigned) (me_sqr(ta - tb) << psy.tex_w);
-                inter += (unsigned) (me_sqr(s0 - s1) << psy.avg_w);
-                ae = (int) (me_dot4(me_absdiff4(A, sb4), ME_ONES, 2) >> 2);
-                isb += (unsigned) (me_sqr(ae) << psy.err_w);
-                isb += (unsigned) (me_sqr(ta) << psy.tex_w);
-                isb += (unsigned) (me_sqr(s0 - avg_sb) << (psy.avg_w + 1));
-                ae = (int) (me_dot4(me_absdiff4(A, sr4), ME_ONES, 2) >> 2);
-                isrc += (unsigned) (me_sqr(ae) << psy.err_w);
-                isrc += (unsigned) (me_sqr(ta) << psy.tex_w);
-                isrc += (unsigned) (me_sqr(s0 - avg_src) << (psy.avg_w + 1));
-            }
-        }
-        *intra_err = me_wsumu(isb);
-        *intrasrc_err = me_wsumu(isrc);
-        *inter_err = me_wsumu(inter) * (unsigned) ratio >> 5;
-        return;
-    }
-    for (int k = ME_LANE; k < n; k += ME_NL) {
-        int j = k / cw, i = k - j * cw;
-        const uint8_t *pa = a + (2 * j) * as + 2 * i, *pb = b + (2 * j) * bs + 2 * i;
-        int a1 = pa[0], a2 = pa[1], a3 = pa[as], a4 = pa[as + 1];
-        int b1 = pb[0], b2 = pb[1], b3 = pb[bs], b4 = pb[bs + 1];
-        int s0 = (int) me_uavg4(a1, a2, a3, a4), s1 = (int) me_uavg4(b1, b2, b3, b4);
-        int ae, ta, tb;
-        ae = (int) me_uavg4(me_abs(a1 - b1), me_abs(a2 - b2), me_abs(a3 - b3), me_abs(a4 - b4));
-        ta = (int) me_uavg4(me_abs(a1 - a2), me_abs(a2 - a3), me_abs(a3 - a4), me_abs(a4 - a1));
-        tb = (int) me_uavg4(me_abs(b1 - b2), me_abs(b2 - b3), me_abs(b3 - b4), me_abs(b4 - b1));
-        inter += (unsigned) (me_sqr(ae) * ratio >> (5 - psy.err_w));
-        inter += (unsigned) (me_sqr(ta - tb) << psy.tex_w);
-        inter += (unsigned) (me_sqr(s0 - s1) << psy.avg_w);
-        ae = (int) me_uavg4(me_abs(a1 - avg_sb), me_abs(a2 - avg_sb), me_abs(a3 - avg_sb), me_abs(a4 - avg_sb));
-        isb += (unsigned) (me_sqr(ae) << psy.err_w);
-        isb += (unsigned) (me_sqr(ta) << psy.tex_w);
-        isb += (unsigned) (me_sqr(s0 - avg_sb) << (psy.avg_w + 1));
-        ae = (int) me_uavg4(me_abs(a1 - avg_src), me_abs(a2 - avg_src), me_abs(a3 - avg_src), me_abs(a4 - avg_src));
-        isrc += (unsigned) (me_sqr(ae) << psy.err_w);
-        isrc += (unsigned) (me_sqr(ta) << psy.tex_w);
-        isrc += (unsigned) (me_sqr(s0 - avg_src) << (psy.avg_w + 1));
-    }
-    *intra_err = me_wsumu(isb);
-    *intrasrc_err = me_wsumu(isrc);
-    *inter_err = me_wsumu(inter) * (unsigned) ratio >> 5;
-}
-
-struct MeMv { /* working copy of the block's DSV_MV */
-    int x, y;
-    unsigned flags;
-    unsigned err, dc, submask;
-};
-
-DSVCU_DEV void
-me_test_intra_y(const MeArgs &A, const MePre *P, const dsvcu_mv *refmv, MeMv *mv, const uint8_t *srcd, int ss, const uint8_t *refd, int rs,
-                int detail_src, int avg_src, int neidif, unsigned ratio, int bw, int bh)
-{
-    int sbw = bw / 2, sbh = bh / 2, bit_index = 0, nsub = 0;
-    unsigned avg_tot = 0, err_sub = 0, err_src = 0;
-    MePsy psy;
-    int rx = refmv ? refmv->x : mv->x, ry = refmv ? refmv->y : mv->y;
-    if ((mv->x | mv->y) != 0 && neidif < 3 && me_abs(rx - mv->x) < 3 && me_abs(ry - mv->y) < 3) return;
-    if (sbw == 0 || sbh == 0) return;
-    psy.err_w = 0;
-    psy.tex_w = 1;
-    psy.avg_w = 2;
-    detail_src += detail_src / max(neidif, 1);
-    for (int g = 0; g <= sbh; g += (sbh + !sbh)) {
-        for (int f = 0; f <= sbw; f += (sbw + !sbw)) {
-            const uint8_t *src_d = srcd + f + g * ss, *mvr_d = refd + f + g * rs;
-            unsigned avg_local, avg_sub, local_detail, dcd, sub_err, src_err, intererr;
-            int dc, lo, hi, lerp, sub_better, src_better;
-            if (bit_index < 4 && !(mv->submask & (1u << bit_index))) {
-                avg_sub = (unsigned) me_block_avg(mvr_d, rs, sbw, sbh);
-                local_detail = P->q_detail[bit_index]; /* source-side, from the prepass */
-                avg_local = P->q_avg[bit_index];
-                dcd = (unsigned) me_abs((int) avg_local - (int) avg_sub) + 2;
-                if (!(local_detail > ((dcd * dcd * (unsigned) bw * (unsigned) bh * ratio) >> 5))) {
-                    dc = (int) (avg_local + (unsigned) avg_src * 3 + 2) >> 2;
-                    me_err_intra(src_d, ss, mvr_d, rs, (int) avg_sub, dc, sbw, sbh, &sub_err, &src_err, &intererr, psy,
-                                 (int) ratio);
-                    lo = me_avg2(detail_src, (int) local_detail);
-                    hi = detail_src;
-                    lerp = (lo * (32 - A.psyscale) + hi * A.psyscale) >> 5;
-                    local_detail = (unsigned) max(lerp, lo);
-                    sub_better = (sub_err + local_detail) < intererr;
-                    src_better = (src_err + local_detail) < intererr;
-                    if (sub_better || src_better) {
-                        mv->submask |= (1u << bit_index);
-                        err_src += src_err;
-                        err_sub += sub_err;
-                        avg_tot += (sub_err < src_err) ? avg_sub : (unsigned) dc;
-                        nsub++;
-                        detail_src = detail_src * 4 / 5;
-                    }
-                }
-            }
-            bit_index++;
-        }
-    }
-    if (mv->submask) {
-        mv->flags |= MVF_INTRA;
-        mv->dc = (err_src < err_sub) ? ((avg_tot / (unsigned) nsub) | 0x100u) : 0;
-    }
-}
-
-DSVCU_DEV void
-me_test_intra_c(const MeArgs &A, MeMv *mv, unsigned mad, unsigned detail_src, unsigned avg_src, int cbx, int cby, int cbmx,
-                int cbmy, int cbw, int cbh)
-{
-    int sbw = cbw / 2, sbh = cbh / 2, bit_index = 0;
-    unsigned thr, avg_ramp;
-    if (A.effort < 6) return;
-    thr = (mv->flags & MVF_INTRA) ? detail_src : detail_src * detail_src;
-    if (sbw == 0 || sbh == 0 || mad <= thr || thr > 64 || (me_abs(mv->x) < 4 && me_abs(mv->y) < 4)) return;
-    avg_ramp = avg_src * avg_src >> 8;
-    for (int g = 0; g <= sbh; g += (sbh + !sbh)) {
-        for (int f = 0; f <= sbw; f += (sbw + !sbw)) {
-            if (bit_index < 4 && !(mv->submask & (1u << bit_index))) {
-                int us, vs, um, vm;
-                unsigned dif;
-                me_c_average(A.src, cbx + f, cby + g, sbw, sbh, &us, &vs);
-                me_c_average(A.ref, cbmx + f, cbmy + g, sbw, sbh, &um, &vm);
-                dif = (unsigned) (me_sqr(us - um) + me_sqr(vs - vm)) * avg_ramp >> 8;
-                if (dif > thr) mv->submask |= (1u << bit_index);
-            }
-            bit_index++;
-        }
-    }
-    if (mv->submask) mv->flags |= MVF_INTRA;
-}
-
-static_assert(sizeof(MePre) % 4 == 0 && sizeof(MePre) <= 160 * 4, "MePre must fit MeScratch::pre_words");
-
-/* Full-pel metric memo.  The candidate scan and the descent probe overlapping
- * positions, and k_me_prepass has already measured the neighbour-independent
- * candidates; the value is a pure function of the position (the reference
- * recomputes it).  Entries live in per-warp shared memory, one per lane, so a
- * lookup is one compare + ballot. */
-DSVCU_DEV int
-me_memo_find(const MeScratch *S, int n, int dx, int dy)
-{
-#ifndef DSVCU_EMU
-    int l = ME_LANE;
-    unsigned hit = __ballot_sync(0xffffffffu, l < n && S->memo_x[l] == dx && S->memo_y[l] == dy);
-    return hit ? __ffs(hit) - 1 : -1;
-#else
-    for (int k = 0; k < n; k++) {
-        if (S->memo_x[k] == dx && S->memo_y[k] == dy) return k;
-    }
-    return -1;
-#endif
-}
-
-DSVCU_DEV void
-me_memo_add(MeScratch *S, int &n, int dx, int dy, unsigned v)
-{
-    if (n < ME_MEMO) {
-        if (ME_LANE == 0) {
-            S->memo_x[n] = (short) dx;
-            S->memo_y[n] = (short) dy;
-            S->memo_v[n] = v;
-        }
-        n++;
-        DSVCU_SYNCWARP();
-    }
-}
-
-DSVCU_DEV unsigned
-me_eval(MeScratch *S, int &mn, int level, const uint8_t *srcd, int ss, const MePlane &rp, int bx, int by, int dx, int dy, int bw,
-        int bh, const MePsy &psy)
-{
-    int k = me_memo_find(S, mn, dx, dy);
-    if (k >= 0) return S->memo_v[k];
-    unsigned sc = me_hier_metr(level, srcd, ss, rp.data + (by + dy) * rp.stride + bx + dx, rp.stride, bw, bh, psy);
-    me_memo_add(S, mn, dx, dy, sc);
-    return sc;
-}
-
-/* source-block statistics -> metric weights and motion bias (hme.c:1445-1481) */
-DSVCU_DEV void
-me_src_stats(const MeArgs &A, MeScratch *S, const uint8_t *srcd, int ss, int bw, int bh, int gx, int gy, unsigned *pvar,
-             unsigned *pavg, int *pbias, MePsy *ppsy)
-{
-    MePsy psy;
-    unsigned var_src = 0, avg_src = 0;
-    int motion_bias = A.y_w * A.y_h;
-    psy.err_w = 2;
-    psy.tex_w = 1;
-    psy.avg_w = 0;
-    if (A.level <= 1) {
-        int tvar;
-        var_src = (unsigned) me_block_detail(srcd, ss, bw, bh, &avg_src);
-        tvar = (int) (var_src + (var_src >> 10) * (var_src >> 10));
-        tvar = ((int) (8u * (unsigned) tvar * (unsigned) A.quant) >> 9) / (bw * bh);
-        if (tvar) {
-            int hvar = (int) me_block_hist_var(srcd, ss, bw, bh, S->hist);
-            int qtex = me_quant_tex(srcd, ss, bw, bh);
-            int npeaks = me_block_peaks(srcd, ss, bw, bh, S->hist, (int) avg_src);
-            motion_bias += tvar * (hvar - qtex) * npeaks;
-        }
-        motion_bias = max(motion_bias, 0) / (2 + (me_abs(gx) + me_abs(gy)));
-        if (var_src <= (unsigned) (8 * bw * bh * A.quant >> 9)) {
-            psy.err_w = 2;
-            psy.tex_w = 1;
-            psy.avg_w = 2;
-            motion_bias = 0;
-        } else {
-            psy.err_w = 1;
-            psy.tex_w = 2;
-            psy.avg_w = 1;
-        }
-        if (var_src > (unsigned) (24 * bw * bh)) psy.avg_w = 0;
-    }
-    *pvar = var_src;
-    *pavg = avg_src;
-    *pbias = motion_bias;
-    *ppsy = psy;
-}
-
-/* candidates that do not depend on same-level neighbours: parent average with
- * outlier rejection (find_inliers, hme.c:1258-1298), temporal neighbours of the
- * previous picture's field (:1229-1256), global motion, parent inliers.
- * Returns has_list (the reference only builds the list when the parent level
- * gave at least one vector); values are raw (before the >> level) */
-DSVCU_DEV int
-me_nonspatial(const MeArgs &A, int i, int j, int gx, int gy, int *plax, int *play, int *bx, int *by, int *pnb)
-{
-    const int step = 1 << A.level, nxb = A.nxb, nyb = A.nyb;
-    int nb = 0;
-    *plax = 0;
-    *play = 0;
-    *pnb = 0;
-    if (!A.parent) return 0;
-    const int pt[18] = { 0, 0, -2, 0, 2, 0, 0, -2, 0, 2, -2, -2, 2, 2, 2, -2, -2, 2 };
-    int pmask = ~((step << 1) - 1);
-    int pi = i & pmask, pj = j & pmask;
-    int lx[9], ly[9], npar = 0, sumx = 0, sumy = 0;
-    for (int m = 0; m < 9; m++) {
-        int x = pi + pt[2 * m] * step, y = pj + pt[2 * m + 1] * step;
-        if (x >= 0 && x < nxb && y >= 0 && y < nyb) {
-            const dsvcu_mv *pmv = A.parent + x + y * nxb;
-            lx[npar] = pmv->x;
-            ly[npar] = pmv->y;
-            sumx += pmv->x;
-            sumy += pmv->y;
-            npar++;
-        }
-    }
-    if (!npar) return 0;
-    int dist[9], keep[9], nl = 0, avgd = 0, ssd = 0, thresh, ax = 0, ay = 0;
-    int lax = sumx / npar, lay = sumy / npar;
-    for (int m = 0; m < npar; m++) {
-        dist[m] = me_sqr(lx[m] - lax) + me_sqr(ly[m] - lay);
-        avgd += dist[m];
-    }
-    avgd /= npar;
-    for (int m = 0; m < npar; m++) ssd += me_sqr(dist[m] - avgd);
-    thresh = avgd + (int) me_isqrt((unsigned) (ssd / npar));
-    for (int m = 0; m < npar; m++) {
-        if (dist[m] <= thresh) {
-            ax += lx[m];
-            ay += ly[m];
-            keep[nl++] = m;
-        }
-    }
-    if (nl) {
-        lax = ax / nl;
-        lay = ay / nl;
-    }
-    *plax = lax;
-    *play = lay;
-    if (A.ref_mvf) {
-        const int rectx[9] = { 0, 1, -1, 0, 0, -1, 1, -1, 1 };
-        const int recty[9] = { 0, 0, 0, 1, -1, -1, -1, 1, 1 };
-        for (int k = 0; k < 9; k++) {
-            int rx = i + rectx[k] * step, ry = j + recty[k] * step;
-            if (rx < 0 || ry < 0 || rx >= nxb || ry >= nyb) continue;
-            bx[nb] = me_sar_r2(A.ref_mvf[rx + ry * nxb].x);
-            by[nb] = me_sar_r2(A.ref_mvf[rx + ry * nxb].y);
-            nb++;
-        }
-    }
-    bx[nb] = gx;
-    by[nb] = gy;
-    nb++;
-    for (int m = 0; m < nl; m++) {
-        bx[nb] = lx[keep[m]];
-        by[nb] = ly[keep[m]];
-        nb++;
-    }
-    *pnb = nb;
-    return 1;
-}
-
-/* statistics of a block against the reference at full-pel offset (fx, fy):
- * metric against the ORIGINAL reference picture, detail + mean of the
- * prediction, chroma means, EPRM clipping tests (hme.c:1640-1690) */
-struct MeRefStats {
-    unsigned ogrerr, var_ref, avg_ref;
-    int u, v, eprm;
-};
-
-DSVCU_DEV void
-me_ref_stats(const MeArgs &A, MeRefStats *R, const uint8_t *srcd, int i, int j, int bx, int by, int bw, int bh, int fx, int fy,
-             int avg_src, const MePsy &psy)
-{
-    const MePlane &sp = A.src[0], &rp = A.ref[0];
-    const uint8_t *refd = rp.data + (by + fy) * rp.stride + bx + fx;
-    const uint8_t *ogrd = A.ogr.data + (by + fy) * A.ogr.stride + bx + fx;
-    int e0, e1, e2;
-    R->ogrerr = me_metr(srcd, sp.stride, ogrd, A.ogr.stride, bw, bh, psy);
-    R->var_ref = (unsigned) me_block_detail(refd, rp.stride, bw, bh, &R->avg_ref);
-    me_c_average(A.ref, i * (A.y_w >> A.hs) + (fx >> A.hs), j * (A.y_h >> A.vs) + (fy >> A.vs), bw >> A.hs, bh >> A.vs, &R->u,
-                 &R->v);
-    me_calc_eprm(srcd, sp.stride, refd, rp.stride, avg_src, (int) R->avg_ref, bw, bh, &e0, &e1, &e2);
-    R->eprm = (e0 ? 1 : 0) | (e1 ? 2 : 0) | (e2 ? 4 : 0);
-}
-
-/* neighbour-independent half of refine_level's block loop, all blocks of the
- * level in parallel (one warp per block) */
-/* ME_PHASE: optional CTA barrier between the phases of the prepass, so that the
- * eight warps of a CTA walk the same stretch of this very long kernel at the
- * same time and share its instruction fetches (`ps` is CTA-uniform) */
-#if defined(ME_PRE_PHASE_SYNC) && !defined(DSVCU_EMU)
-#define ME_PHASE()            \
-    do {                      \
-        if (ps) __syncthreads(); \
-    } while (0)
-#else
-#define ME_PHASE() ((void) 0)
-#endif
-
-DSVCU_DEV void
-me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j, bool ps)
-{
-    (void) ps;
-    const int level = A.level;
-    const MePlane &sp = A.src[0], &rp = A.ref[0];
-    const int gx = A.gxy[0], gy = A.gxy[1];
-    int bx = (i * A.y_w) >> level, by = (j * A.y_h) >> level;
-    MePre *P = A.pre + i + j * A.nxb;
-    if (bx >= sp.w || by >= sp.h) return;
-    const uint8_t *srcd = sp.data + by * sp.stride + bx;
-    int bw = min(sp.w - bx, A.y_w), bh = min(sp.h - by, A.y_h);
-    unsigned var_src, avg_src, zoscore;
-    int motion_bias, lax, lay, nb, cbx[ME_PRE_NB], cby[ME_PRE_NB], has, mn = 0, uavg = 0, vavg = 0;
-    MePsy psy;
-    me_src_stats(A, S, srcd, sp.stride, bw, bh, gx, gy, &var_src, &avg_src, &motion_bias, &psy);
-    has = me_nonspatial(A, i, j, gx, gy, &lax, &lay, cbx, cby, &nb);
-    ME_PHASE();
-    /* measure zero, the parent average and the list (valid, distinct positions) */
-    for (int k = -2; k < (has ? nb : 0); k++) {
-        int dx, dy;
-        if (k == -2) {
-            dx = 0;
-            dy = 0;
-        } else if (k == -1) {
-            if (!has) continue;
-            dx = (int16_t) lax >> level;
-            dy = (int16_t) lay >> level;
-        } else {
-            dx = (int16_t) cbx[k] >> level;
-            dy = (int16_t) cby[k] >> level;
-        }
-        if (me_invalid_block(rp.w, rp.h, bx + dx, by + dy, bw, bh, 0)) continue;
-        if (mn >= ME_PRE_NM) break;
-        (void) me_eval(S, mn, level, srcd, sp.stride, rp, bx, by, dx, dy, bw, bh, psy);
-    }
-    if (has) {
-        /* the descent starts at the best candidate, most often the parent
-         * average: measure its eight neighbours too */
-        const int nx[8] = { 1, -1, 0, 0, -1, 1, -1, 1 }, ny[8] = { 0, 0, 1, -1, -1, -1, 1, 1 };
-        int cxl = (int16_t) lax >> level, cyl = (int16_t) lay >> level;
-        for (int k = 0; k < 8 && mn < ME_PRE_NM; k++) {
-            if (me_invalid_block(rp.w, rp.h, bx + cxl + nx[k], by + cyl + ny[k], bw, bh, 0)) continue;
-            (void) me_eval(S, mn, level, srcd, sp.stride, rp, bx, by, cxl + nx[k], cyl + ny[k], bw, bh, psy);
-        }
-    }
-    ME_PHASE();
-    zoscore = me_metr(srcd, sp.stride, A.ogr.data + by * A.ogr.stride + bx, A.ogr.stride, bw, bh, psy);
-    MeRefStats rs[2];
-    int rs_valid[2] = { 0, 0 }, utex = 0, vtex = 0;
-    unsigned q_detail[4] = { 0, 0, 0, 0 }, q_avg[4] = { 0, 0, 0, 0 };
-    if (level == 0) {
-        int qn = 0, sbw = bw / 2, sbh = bh / 2;
-        int cbw = bw >> A.hs, cbh = bh >> A.vs, cbx = i * (A.y_w >> A.hs), cby = j * (A.y_h >> A.vs);
-        if (!me_invalid_block(rp.w, rp.h, bx + lax, by + lay, bw, bh, 0)) {
-            me_ref_stats(A, &rs[0], srcd, i, j, bx, by, bw, bh, lax, lay, (int) avg_src, psy);
-            rs_valid[0] = 1;
-        }
-        ME_PHASE();
-        if (lax | lay) {
-            me_ref_stats(A, &rs[1], srcd, i, j, bx, by, bw, bh, 0, 0, (int) avg_src, psy);
-            rs_valid[1] = 1;
-        }
-        ME_PHASE();
-        if (sbw && sbh) {
-            for (int g = 0; g <= sbh; g += (sbh + !sbh)) {
-                for (int f = 0; f <= sbw; f += (sbw + !sbw)) {
-                    if (qn < 4) q_detail[qn] = (unsigned) me_block_detail(srcd + f + g * sp.stride, sp.stride, sbw, sbh, &q_avg[qn]);
-                    qn++;
-                }
-            }
-        }
-        if (cbw > 0 && cbh > 0) {
-            utex = (int) me_block_tex(A.src[1].data + cby * A.src[1].stride + cbx, A.src[1].stride, cbw, cbh);
-            vtex = (int) me_block_tex(A.src[2].data + cby * A.src[2].stride + cbx, A.src[2].stride, cbw, cbh);
-        }
-    }
-    ME_PHASE();
-    MeSubpel M;
-    int sp_valid = 0;
-    M.nv = 0;
-    if (level == 0) {
-        me_c_average(A.src, i * (A.y_w >> A.hs), j * (A.y_h >> A.vs), bw >> A.hs, bh >> A.vs, &uavg, &vavg);
-        /* the first sub-pel pass of the reference is always around (lax, lay) */
-        if (A.effort >= 4 && !me_invalid_block(rp.w, rp.h, bx + lax, by + lay, bw, bh, 4)) {
-            me_subpel_measure(A, S, &M, lax, lay, bx, by, bw, bh, psy);
-            sp_valid = 1;
-        }
-    }
-    DSVCU_SYNCWARP();
-    if (ME_LANE == 0) {
-        for (int k = 0; k < 2; k++) {
-            P->rs_valid[k] = rs_valid[k];
-            if (rs_valid[k]) {
-                P->rs_ogrerr[k] = rs[k].ogrerr;
-                P->rs_var[k] = rs[k].var_ref;
-                P->rs_avg[k] = rs[k].avg_ref;
-                P->rs_u[k] = rs[k].u;
-                P->rs_v[k] = rs[k].v;
-                P->rs_eprm[k] = rs[k].eprm;
-            }
-        }
-        for (int k = 0; k < 4; k++) {
-            P->q_detail[k] = q_detail[k];
-            P->q_avg[k] = q_avg[k];
-        }
-        P->utex = utex;
-        P->vtex = vtex;
-        P->sp_valid = sp_valid;
-        P->sp_nv = M.nv;
-        for (int k = 0; k < M.nv; k++) {
-            P->sp_tx[k] = (signed char) M.tx[k];
-            P->sp_ty[k] = (signed char) M.ty[k];
-            P->sp_sc[k] = M.sc[k];
-        }
-        P->var_src = var_src;
-        P->avg_src = avg_src;
-        P->motion_bias = motion_bias;
-        P->psy_pack = psy.err_w | (psy.tex_w << 8) | (psy.avg_w << 16);
-        P->lax = lax;
-        P->lay = lay;
-        P->has_list = has;
-        P->nb = nb;
-        P->zoscore = zoscore;
-        P->uavg = uavg;
-        P->vavg = vavg;
-        P->nm = mn;
-        for (int k = 0; k < nb; k++) {
-            P->bx[k] = (short) cbx[k];
-            P->by[k] = (short) cby[k];
-        }
-    }
-    for (int k = ME_LANE; k < mn; k += ME_NL) {
-        P->mx[k] = S->memo_x[k];
-        P->my[k] = S->memo_y[k];
-        P->mv[k] = S->memo_v[k];
-    }
-    DSVCU_SYNCWARP();
-}
-
-/* ---- one block of refine_level (hme.c:1413-1823) ---- */
+static_assert(sizeof(MePre) % 16 == 0 && sizeof(MePre) <= ME_PRE_WORDS * 4, "MePre: whole 16-byte words, must fit the staging area");
 
 #define ME_MAXCAND 40
 
-DSVCU_DEV void
-me_block(const MeArgs &A, MeScratch *S, int i, int j, int *acc_local)
-{
-    const int level = A.level, step = 1 << level;
-    const MePlane &sp = A.src[0], &rp = A.ref[0];
-    const int nxb = A.nxb, nyb = A.nyb;
-    int bx = (i * A.y_w) >> level, by = (j * A.y_h) >> level;
-    dsvcu_mv *out = A.mvf + i + j * nxb;
-    int cx[ME_MAXCAND], cy[ME_MAXCAND], n = 0;
-    int bw, bh, dx, dy, lax = 0, lay = 0, motion_bias, good_enough = 0;
-    unsigned best, score_zero, score, best_score, qthresh, var_src = 0, avg_src = 0;
-    MePsy psy;
-    const uint8_t *srcd;
-
-    psy.err_w = 2;
-    psy.tex_w = 1;
-    psy.avg_w = 0;
-    if (bx >= sp.w || by >= sp.h) {
-        return; /* field is zero-initialised: inter, zero vector */
-    }
-    srcd = sp.data + by * sp.stride + bx;
-    bw = min(sp.w - bx, A.y_w);
-    bh = min(sp.h - by, A.y_h);
-    MePred pred;
-    int mn = 0; /* entries in the block's metric memo */
-    /* one coalesced batch of loads (a single L2 round trip) instead of a miss
-     * per touched line of the record */
-    {
-        const uint32_t *g = (const uint32_t *) (A.pre + i + j * nxb);
-        for (int k = ME_LANE; k < (int) (sizeof(MePre) / 4); k += ME_NL) S->pre_words[k] = g[k];
-        DSVCU_SYNCWARP();
-    }
-    const MePre *P = (const MePre *) S->pre_words;
-    me_movec_pred(A.mvf, nxb, i, j, &pred.x, &pred.y);
-    /* neighbour-independent results of k_me_prepass: statistics, metric weights,
-     * the non-spatial candidates and their metrics (memo seed) */
-    var_src = P->var_src;
-    avg_src = P->avg_src;
-    motion_bias = P->motion_bias;
-    psy.err_w = P->psy_pack & 255;
-    psy.tex_w = (P->psy_pack >> 8) & 255;
-    psy.avg_w = (P->psy_pack >> 16) & 255;
-    mn = P->nm;
-    for (int k = ME_LANE; k < mn; k += ME_NL) {
-        S->memo_x[k] = P->mx[k];
-        S->memo_y[k] = P->my[k];
-        S->memo_v[k] = P->mv[k];
-    }
-    DSVCU_SYNCWARP();
-    cx[n] = 0;
-    cy[n] = 0;
-    n++;
-    if (P->has_list) {
-        const int nb = P->nb;
-        lax = P->lax;
-        lay = P->lay;
-        cx[n] = lax;
-        cy[n] = lay;
-        n++;
-        /* spatial predictions (hme.c:1202-1227); vectors pass through the
-         * qpel->fpel rounding whatever unit they are stored in */
-        if (level == 0) {
-            cx[n] = me_sar_r2(pred.x);
-            cy[n] = me_sar_r2(pred.y);
-            n++;
-        }
-        if (i > 0) {
-            int mx_, my_;
-            me_ldmv(A.mvf + (i - step) + j * nxb, &mx_, &my_, NULL);
-            cx[n] = me_sar_r2(mx_);
-            cy[n] = me_sar_r2(my_);
-            n++;
-        }
-        if (j > 0) {
-            int mx_, my_;
-            me_ldmv(A.mvf + i + (j - step) * nxb, &mx_, &my_, NULL);
-            cx[n] = me_sar_r2(mx_);
-            cy[n] = me_sar_r2(my_);
-            n++;
-        }
-        if (i > 0 && j > 0) {
-            int mx_, my_;
-            me_ldmv(A.mvf + (i - step) + (j - step) * nxb, &mx_, &my_, NULL);
-            cx[n] = me_sar_r2(mx_);
-            cy[n] = me_sar_r2(my_);
-            n++;
-        }
-        /* temporal neighbours, global motion, parent inliers (from the prepass) */
-        for (int k = 0; k < nb; k++) {
-            cx[n] = P->bx[k];
-            cy[n] = P->by[k];
-            n++;
-        }
-    }
-    /* candidates live in int16 fields in the reference */
-    for (int k = 0; k < n; k++) {
-        cx[k] = (int16_t) cx[k] >> level;
-        cy[k] = (int16_t) cy[k] >> level;
-    }
-    {
-        /* remove_dupes (hme.c:1166-1183) keeps the FIRST occurrence of every
-         * position, then the candidates are scored in list order.  On the device
-         * each lane holds one candidate (n <= 32): duplicates are found with one
-         * match instruction and the survivors are visited in lane order. */
-        int bestx = cx[0], besty = cy[0];
-        best_score = score_zero = 0xffffffffu;
-#ifndef DSVCU_EMU
-        const int lane = ME_LANE;
-        const int myx = lane < n ? cx[lane] : 0, myy = lane < n ? cy[lane] : 0;
-        const unsigned key = lane < n ? (((unsigned) myx << 16) | ((unsigned) myy & 0xffffu)) : (0x7fff0000u | (unsigned) lane);
-        const unsigned same = __match_any_sync(0xffffffffu, key);
-        unsigned keep = __ballot_sync(0xffffffffu, lane < n && (__ffs(same) - 1) == lane);
-        for (; keep; keep &= keep - 1) {
-            const int srcl = __ffs(keep) - 1;
-            dx = __shfl_sync(0xffffffffu, myx, srcl);
-            dy = __shfl_sync(0xffffffffu, myy, srcl);
-#else
-        {
-            int newn = 1;
-            for (int a = 1; a < n; a++) {
-                int b;
-                for (b = 0; b < newn; b++) {
-                    if (cx[a] == cx[b] && cy[a] == cy[b]) break;
-                }
-                if (b == newn) {
-                    cx[newn] = cx[a];
-                    cy[newn] = cy[a];
-                    newn++;
-                }
-            }
-            n = newn;
-        }
-        for (int k = 0; k < n; k++) {
-            dx = cx[k];
-            dy = cy[k];
-#endif
-            if (me_invalid_block(rp.w, rp.h, bx + dx, by + dy, bw, bh, 0)) continue;
-            score = me_eval(S, mn, level, srcd, sp.stride, rp, bx, by, dx, dy, bw, bh, psy);
-            if (dx == 0 && dy == 0) score_zero = score;
-            score += (unsigned) me_mv_cost(A, pred, dx * step * 4, dy * step * 4, level);
-            if (dx == lax && dy == lay) score = (unsigned) max((int) score - (motion_bias >> level), 0);
-            if (best_score > score) {
-                best_score = score;
-                bestx = dx;
-                besty = dy;
-            }
-        }
-        dx = bestx;
-        dy = besty;
-    }
-    best = best_score;
-    qthresh = (unsigned) (A.quant * bw * bh >> 11);
-    {
-        unsigned zoscore = P->zoscore;
-        if (me_abs(dx) <= 1 && me_abs(dy) <= 1) qthresh *= 2;
-        if (zoscore < qthresh) {
-            best = (level == 0) ? score_zero : 0;
-            dx = 0;
-            dy = 0;
-            good_enough = 1;
-        }
-    }
-    if (!good_enough) {
-        /* refine_best_fpel_cand (hme.c:1300-1370) */
-        const int rectx[9] = { 0, 1, -1, 0, 0, -1, 1, -1, 1 };
-        const int recty[9] = { 0, 0, 0, 1, -1, -1, -1, 1, 1 };
-        unsigned metr[4] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu };
-        int again = 1;
-        while (again) {
-            int tvx, tvy;
-            again = 0;
-            for (int k = 0; k < 5; k++) {
-                tvx = dx + rectx[k];
-                tvy = dy + recty[k];
-                if (me_invalid_block(rp.w, rp.h, bx + tvx, by + tvy, bw, bh, 0)) continue;
-                score = me_eval(S, mn, level, srcd, sp.stride, rp, bx, by, tvx, tvy, bw, bh, psy);
-                if (k >= 1) metr[k - 1] = score;
-                if (level == 0 && !tvx && !tvy && score <= qthresh) {
-                    dx = tvx;
-                    dy = tvy;
-                    best = score;
-                    good_enough = 1;
-                    break;
-                }
-                score += (unsigned) me_mv_cost(A, pred, tvx * step * 4, tvy * step * 4, level);
-                if (best > score) {
-                    best = score;
-                    dx = tvx;
-                    dy = tvy;
-                    again = 1;
-                    break;
-                }
-            }
-            if (again || good_enough) continue;
-            tvx = dx + rectx[(metr[0] <= metr[1]) ? 1 : 2];
-            tvy = dy + recty[(metr[2] <= metr[3]) ? 3 : 4];
-            if (me_invalid_block(rp.w, rp.h, bx + tvx, by + tvy, bw, bh, 0)) break;
-            score = me_eval(S, mn, level, srcd, sp.stride, rp, bx, by, tvx, tvy, bw, bh, psy);
-            score += (unsigned) me_mv_cost(A, pred, tvx * step * 4, tvy * step * 4, level);
-            if (best > score) {
-                best = score;
-                dx = tvx;
-                dy = tvy;
-                again = 1;
-            }
-        }
-    }
-
-    MeMv mv;
-    mv.x = dx * step;
-    mv.y = dy * step;
-    mv.flags = 0;
-    mv.err = 0;
-    mv.dc = 0;
-    mv.submask = 0;
-
-    if (level == 0) {
-        int fpelx = mv.x, fpely = mv.y, subx = 0, suby = 0;
-        unsigned yarea = (unsigned) (bw * bh), best_fp;
-        if (fpelx == lax && fpely == lay) best += (unsigned) motion_bias;
-        best_fp = best;
-        if (A.effort >= 4) {
-            int tried_la = 0;
-            MeSubpel M;
-            if (!me_invalid_block(rp.w, rp.h, bx + lax, by + lay, bw, bh, 4)) {
-                /* measured by the prepass; only the decision is left */
-                if (best_fp != 0) {
-                    M.nv = P->sp_nv;
-                    for (int k = 0; k < M.nv; k++) {
-                        M.tx[k] = P->sp_tx[k];
-                        M.ty[k] = P->sp_ty[k];
-                        M.sc[k] = P->sp_sc[k];
-                    }
-                    best = me_subpel_decide(A, &M, &subx, &suby, lax, lay, pred, best_fp, bw, bh);
-                } else {
-                    best = best_fp;
-                }
-                tried_la = 1;
-                if (subx | suby) {
-                    fpelx = lax;
-                    fpely = lay;
-                }
-            }
-            /* the reference repeats the refinement around the full-pel winner;
-             * when that is the position just tried (and nothing was found) the
-             * second pass would recompute the very same numbers */
-            if (!(subx | suby) && !good_enough && !(tried_la && fpelx == lax && fpely == lay) &&
-                !me_invalid_block(rp.w, rp.h, bx + fpelx, by + fpely, bw, bh, 4)) {
-                if (best_fp != 0) {
-                    me_subpel_measure(A, S, &M, fpelx, fpely, bx, by, bw, bh, psy);
-                    best = me_subpel_decide(A, &M, &subx, &suby, fpelx, fpely, pred, best_fp, bw, bh);
-                } else {
-                    best = best_fp;
-                }
-            }
-        }
-        mv.x = fpelx * 4 + subx;
-        mv.y = fpely * 4 + suby;
-        /* publish the vector now: the neighbour difference below reads it */
-        if (ME_LANE == 0) {
-            out->x = (int16_t) mv.x;
-            out->y = (int16_t) mv.y;
-            out->flags = 0;
-        }
-        DSVCU_SYNCWARP();
-        {
-            const uint8_t *refd = rp.data + (by + fpely) * rp.stride + bx + fpelx;
-            unsigned var_ref, avg_ref, mad, ogrerr, ogrmad, avg_y_dif, avg_c_dif;
-            int uavg_src, vavg_src, uavg_ref, vavg_ref, cbx, cby, cbw, cbh, cbmx, cbmy;
-            int eprmi, eprmd, eprmr, neidif, oob, ipolvar, dv, skipped = 0;
-            unsigned skipt = ((unsigned) A.quant * (unsigned) A.quant) >> 19;
-            unsigned ratio = 1 << 5, chroma_ratio;
-            MeChroma cpsy;
-            const dsvcu_mv *refmv = A.ref_mvf ? A.ref_mvf + i + j * nxb : NULL;
-
-            if ((mv.x | mv.y) & 3) ratio = (best << 5) / (best_fp + !best_fp);
-            {
-                /* reference-side statistics at the chosen position: from the
-                 * prepass when that position is the parent average or zero */
-                int slot = (fpelx == lax && fpely == lay && P->rs_valid[0]) ? 0
-                         : ((fpelx | fpely) == 0 && P->rs_valid[1]) ? 1 : -1;
-                MeRefStats rs;
-                if (slot >= 0) {
-                    rs.ogrerr = P->rs_ogrerr[slot];
-                    rs.var_ref = P->rs_var[slot];
-                    rs.avg_ref = P->rs_avg[slot];
-                    rs.u = P->rs_u[slot];
-                    rs.v = P->rs_v[slot];
-                    rs.eprm = P->rs_eprm[slot];
-                } else {
-                    me_ref_stats(A, &rs, srcd, i, j, bx, by, bw, bh, fpelx, fpely, (int) avg_src, psy);
-                }
-                ogrerr = rs.ogrerr;
-                var_ref = rs.var_ref;
-                avg_ref = rs.avg_ref;
-                uavg_ref = rs.u;
-                vavg_ref = rs.v;
-                eprmi = rs.eprm & 1;
-                eprmd = (rs.eprm >> 1) & 1;
-                eprmr = (rs.eprm >> 2) & 1;
-            }
-            ogrmad = (ogrerr + yarea / 2) / yarea;
-            ogrmad = ogrmad * ratio >> 5;
-            mad = (best + yarea / 2) / yarea;
-            dv = (int) min(ratio, 32u);
-            ipolvar = (int) ((var_src * (unsigned) dv + var_ref * (unsigned) (32 - dv)) >> 5);
-            dv = me_abs((int) var_src - ipolvar);
-            if ((var_src > 16 * yarea) && (var_src < 32 * yarea)) mv.flags |= MVF_MAINTAIN;
-
-            cbx = i * (A.y_w >> A.hs);
-            cby = j * (A.y_h >> A.vs);
-            cbmx = cbx + (fpelx >> A.hs);
-            cbmy = cby + (fpely >> A.vs);
-            cbw = bw >> A.hs;
-            cbh = bh >> A.vs;
-            chroma_ratio = ((unsigned) (cbw * cbh) << 4) / yarea;
-            uavg_src = P->uavg;
-            vavg_src = P->vavg;
-            me_chroma_analysis(&cpsy, (int) avg_src, uavg_src, vavg_src);
-            avg_y_dif = (unsigned) me_abs((int) avg_src - (int) avg_ref);
-            avg_c_dif = (unsigned) me_avg2(me_abs(uavg_src - uavg_ref), me_abs(vavg_src - vavg_ref));
-            {   /* outofbounds (hme.c:413-424) */
-                int limx = ((nxb - 1) * A.y_w) - 1, limy = ((nyb - 1) * A.y_h) - 1;
-                int px = i * A.y_w + (mv.x >> 2), py = j * A.y_h + (mv.y >> 2);
-                oob = (px < 0 || py < 0 || px >= limx || py >= limy);
-            }
-            neidif = me_neighbordif(A.mvf, nxb, i, j);
-
-            if ((good_enough || (mv.x | mv.y) == 0) && A.skip_thresh >= 0 && !A.lossless) {
-                unsigned cth, sth = skipt * yarea, zsub[3];
-                sth += 4 * var_src;
-                sth += yarea * (unsigned) A.skip_thresh;
-                if (A.quant < (1 << 10)) sth = sth * (unsigned) A.quant >> 10;
-                if (avg_y_dif <= 2) sth = max(sth, 3 * (yarea + var_src));
-                sth = max(sth, yarea);
-                if (good_enough) sth *= 2;
-                me_yuv_max_sub(zsub, A.src, A.ref, bx, by, bx, by, bw, bh, cbx, cby, cbx, cby, cbw, cbh, psy);
-                cth = (chroma_ratio * sth * max(skipt, 1u) >> (4 + 1));
-                zsub[0] = zsub[0] * ratio >> 5;
-                zsub[1] = zsub[1] * ratio >> 5;
-                zsub[2] = zsub[2] * ratio >> 5;
-                zsub[0] += (unsigned) me_sqr((int) avg_src - (int) avg_ref) * yarea;
-                if (zsub[0] <= sth && zsub[1] <= cth && zsub[2] <= cth) {
-                    mv.flags |= MVF_SKIP;
-                    mv.x = 0;
-                    mv.y = 0;
-                    mv.err = 0;
-                    skipped = 1;
-                }
-            }
-            if (!skipped) {
-                if (!oob && !A.lossless) {
-                    int y_pre = (avg_y_dif <= 2), c_pre = !cpsy.greyish && (avg_c_dif <= 2);
-                    if (y_pre || c_pre) {
-                        unsigned bsub[3], xth = skipt * yarea;
-                        int utex, vtex, carea = 4 * cbw * cbh;
-                        me_yuv_max_sub(bsub, A.src, A.ref, bx, by, bx + fpelx, by + fpely, bw, bh, cbx, cby, cbmx, cbmy, cbw,
-                                       cbh, psy);
-                        xth += (unsigned) ipolvar;
-                        xth = (unsigned) max((int) xth - ((int) yarea * neidif * 2), 0);
-                        xth = xth * (unsigned) A.quant >> 12;
-                        xth = xth < 32 ? 32 : (xth > yarea * 4 ? yarea * 4 : xth);
-                        bsub[0] = bsub[0] * ratio >> 5;
-                        bsub[1] = bsub[1] * ratio >> 5;
-                        bsub[2] = bsub[2] * ratio >> 5;
-                        if (y_pre && bsub[0] < 4 * xth) mv.flags |= MVF_NOXMITY;
-                        utex = P->utex;
-                        vtex = P->vtex;
-                        c_pre &= (utex > carea || vtex > carea);
-                        xth = chroma_ratio * xth >> 4;
-                        if (c_pre && bsub[1] < xth && bsub[2] < xth) mv.flags |= MVF_NOXMITC;
-                    }
-                    if ((unsigned) dv < (var_src / 4)) mv.flags |= MVF_SIMCMPLX;
-                }
-                me_test_intra_y(A, P, refmv, &mv, srcd, sp.stride, refd, rp.stride, ipolvar, (int) avg_src, neidif, ratio, bw,
-                                bh);
-                me_test_intra_c(A, &mv, mad, (unsigned) (ipolvar / (bw * bh)), avg_src, cbx, cby, cbmx, cbmy, cbw, cbh);
-                if (!(mv.flags & MVF_NOXMITY)) {
-                    mv.err = mad & 0xffff;
-                    acc_local[3] += (int) mad;
-                }
-                acc_local[1] += (ogrmad > 11) + (avg_c_dif >= 32);
-            }
-            if (best > 0) acc_local[2]++;
-            if (mv.flags & MVF_INTRA) {
-                int merged = (mv.dc & 0x100) ? eprmd : eprmi;
-                if (mv.submask != 15) merged |= eprmr;
-                if (merged) mv.flags |= MVF_EPRM;
-                acc_local[0]++;
-                mv.x = fpelx * 4;
-                mv.y = fpely * 4;
-            } else {
-                int merged = eprmr;
-                if (mv.submask) merged |= eprmi;
-                if (merged) mv.flags |= MVF_EPRM;
-            }
-            if (mv.flags & (MVF_INTRA | MVF_EPRM)) mv.flags &= ~(unsigned) MVF_SIMCMPLX;
-        }
-    }
-    if (ME_LANE == 0) {
-        out->x = (int16_t) mv.x;
-        out->y = (int16_t) mv.y;
-        out->flags = mv.flags;
-        out->err = (uint16_t) mv.err;
-        out->dc = (uint16_t) mv.dc;
-        out->submask = (uint8_t) mv.submask;
-    }
-    DSVCU_SYNCWARP();
+/* ---- the per-block functions, for one warp per block and for four blocks per warp ---- */
+#define ME_G 32
+namespace meg32 {
+#include "k_hme_body.cuh"
 }
+#undef ME_G
+#define ME_G ME_PRE_G
+namespace meg8 {
+#include "k_hme_body.cuh"
+}
+#undef ME_G
 
-/* neighbour-independent half of every block of a level: one warp per block */
-DSVCU_KERNEL void __launch_bounds__(ME_WARPS_PER_CTA * 32, ME_PRE_MIN_CTAS)
+/* lane / group bookkeeping of the kernels below (the host emulation runs one "lane" per CTA) */
+#ifdef DSVCU_EMU
+#define ME_KLANE 0
+#define ME_WIC 0
+#define ME_WARP ((int) blockIdx.x)
+#define ME_NWARPS ((int) gridDim.x)
+#define ME_GRP(g) ((int) blockIdx.x)
+#define ME_NGRPS(g) ((int) gridDim.x)
+#define ME_GIC(g) 0
+#else
+#define ME_KLANE ((int) (threadIdx.x & 31))
+#define ME_WIC ((int) (threadIdx.x >> 5))
+#define ME_WARP ((int) ((blockIdx.x * blockDim.x + threadIdx.x) >> 5))
+#define ME_NWARPS ((int) ((gridDim.x * blockDim.x) >> 5))
+#define ME_GRP(g) ((int) ((blockIdx.x * blockDim.x + threadIdx.x) / (g)))
+#define ME_NGRPS(g) ((int) ((gridDim.x * blockDim.x) / (g)))
+#define ME_GIC(g) ((int) (threadIdx.x / (g)))
+#endif
+
+/* neighbour-independent half of every block of a level: ME_PRE_G lanes per block,
+ * four blocks (consecutive in a block row) per warp */
+DSVCU_KERNEL void __launch_bounds__(ME_PRE_THREADS, ME_PRE_MIN_CTAS)
 k_me_prepass(MeArgs A)
 {
-    DSVCU_SHARED MeScratch scratch[ME_WARPS_PER_CTA];
-    MeScratch *S = &scratch[ME_WIC];
+    DSVCU_SHARED meg8::MeScratch scratch[ME_PRE_GROUPS];
+    meg8::MeScratch *S = &scratch[ME_GIC(ME_PRE_G)];
     const int step = 1 << A.level;
     const int cols = (A.nxb + step - 1) / step, rows = (A.nyb + step - 1) / step;
-#if defined(ME_PRE_PHASE_SYNC) && !defined(DSVCU_EMU)
-    for (int base = (int) blockIdx.x * ME_WARPS_PER_CTA; base < cols * rows; base += (int) gridDim.x * ME_WARPS_PER_CTA) {
-        const int b = base + ME_WIC;
-        const int r = b / cols, c = b - r * cols;
-        const bool live = b < cols * rows && ((c * step * A.y_w) >> A.level) < A.src[0].w &&
-                          ((r * step * A.y_h) >> A.level) < A.src[0].h;
-        const bool ps = __syncthreads_and(live);
-        if (live) me_prepass_block(A, S, c * step, r * step, ps);
-    }
-#else
-    for (int b = ME_WARP; b < cols * rows; b += ME_NWARPS) {
+    for (int b = ME_GRP(ME_PRE_G); b < cols * rows; b += ME_NGRPS(ME_PRE_G)) {
         int r = b / cols, c = b - r * cols;
-        me_prepass_block(A, S, c * step, r * step, false);
+        meg8::me_prepass_block(A, S, c * step, r * step);
     }
-#endif
 }
 
-/* Wavefront over the block rows of one pyramid level: one warp per row, a CTA
- * owns ME_WARPS_PER_CTA consecutive rows.  Row r may start block c once row r-1
- * has finished block c (left / top / top-left dependencies).
- * Hand-offs inside a CTA go through shared-memory progress words and
- * block-scope fences; the last row of a CTA also publishes through global memory
- * (device-scope fence) for the first row of the next CTA.  The vector field
- * itself is read with volatile loads (me_ldmv), i.e. from L2. */
-#if defined(ME_TIMING) && !defined(DSVCU_EMU)
-/* diagnostics build only: [0] cycles in me_block, [1] cycles waiting for the row above, [2] blocks (level 0) */
-__device__ unsigned long long g_me_dbg[4];
+/* Wavefront over the block rows of one pyramid level.  Block (i, j) needs the
+ * final vectors of its left, top and top-left neighbours, so row
+ * r may work on block c once row r-1 has finished block c.
+ *
+ * Since the prepass took the pixel work out of this pass, a block is mostly
+ * scalar decisions, and what limits the whole encoder is how many warps (and
+ * registers) the wavefronts of all the instances on the GPU keep resident while
+ * they wait for each other.  So a warp owns ME_LVL_RPW = 4 consecutive rows, one
+ * group of ME_LVL_G = 8 lanes each, in SKEWED LOCKSTEP: at warp-step t the group
+ * of row g works on column t - g, which is exactly the dependency between the
+ * rows of a warp -- no flags inside a warp, one __syncwarp per step, and the four
+ * groups mostly walk the same instructions together.  Only the first row of a warp
+ * waits for a progress word: shared memory between the warps of a CTA, global
+ * memory (+ device-scope fence) between CTAs.  The vector field itself is read
+ * with volatile loads (me_ldmv), i.e. from L2.  1080p level 0: 68 rows = 17 warps
+ * in 5 CTAs, against 68 warps in 9 CTAs for one warp per row. */
+#ifndef ME_LVL_G
+#define ME_LVL_G 32 /* lanes per block row in the wavefront: 32 (one row per warp) or ME_PRE_G (four rows per warp) */
 #endif
+#if ME_LVL_G == 32
+#define ME_LVL_NS meg32
+#else
+#define ME_LVL_NS meg8
+#endif
+#define ME_LVL_RPW (32 / ME_LVL_G)
+#ifndef ME_LVL_WARPS
+#define ME_LVL_WARPS (ME_LVL_G == 32 ? 8 : 4)
+#endif
+#define ME_LVL_ROWS (ME_LVL_WARPS * ME_LVL_RPW) /* rows per CTA */
+struct MeLvlShared {
+    ME_LVL_NS::MeScratch scratch[ME_LVL_ROWS];
+    __align__(16) uint32_t pre_words[ME_LVL_ROWS][ME_PRE_WORDS];
+    int sprog[ME_LVL_WARPS];
+};
 
-DSVCU_KERNEL void __launch_bounds__(ME_WARPS_PER_CTA * 32, ME_MIN_CTAS)
+DSVCU_KERNEL void __launch_bounds__(ME_LVL_WARPS * 32, ME_LVL_G == 32 ? 2 : 4)
 k_me_level(MeArgs A)
 {
-    DSVCU_SHARED MeScratch scratch[ME_WARPS_PER_CTA];
-    DSVCU_SHARED int sprog[ME_WARPS_PER_CTA];
+    DSVCU_DYN_SMEM(MeLvlShared, sh);
     const int step = 1 << A.level;
     int acc_local[4] = { 0, 0, 0, 0 };
 #ifndef DSVCU_EMU
-    const int lr = ME_WIC;
-    const int row = (int) blockIdx.x * ME_WARPS_PER_CTA + lr;
-    MeScratch *S = &scratch[lr];
-    if (threadIdx.x < ME_WARPS_PER_CTA) sprog[threadIdx.x] = 0;
+    const int wic = ME_WIC, g = ME_KLANE / ME_LVL_G;   /* warp in CTA, row group in warp */
+    const int lr = wic * ME_LVL_RPW + g;                /* row in CTA */
+    const int row = (int) blockIdx.x * ME_LVL_ROWS + lr;
+    const int cols = (A.nxb + step - 1) / step;
+    ME_LVL_NS::MeScratch *S = &sh->scratch[lr];
+    if (threadIdx.x < ME_LVL_WARPS) sh->sprog[threadIdx.x] = 0;
     __syncthreads();
-    if (row < A.nrows) {
-        const bool above_global = (lr == 0), pub_global = (lr == ME_WARPS_PER_CTA - 1);
-        volatile const int *above = above_global ? (volatile const int *) (A.progress + row - 1)
-                                                 : (volatile const int *) (sprog + lr - 1);
-        const int j = row * step;
-        int seen = (row == 0) ? 0x7fffffff : 0;
-        int col = 0;
-#if defined(ME_TIMING)
-        long long tw = 0, tb = 0;
-#endif
-        for (int i = 0; i < A.nxb; i += step, col++) {
-            const int need = col + 1;
-#if defined(ME_TIMING)
-            long long c0 = clock64();
-#endif
-            if (seen < need) {
-                while ((seen = *above) < need) {
-                    /* leave the issue slots to warps that have work: a row that polls
-                     * shared memory without pausing takes a third of its scheduler
-                     * from the row it is waiting for */
-                    __nanosleep(above_global ? ME_POLL_NS : ME_POLL_NS_CTA);
+    {
+        /* the row above the warp's first row: previous warp of the CTA, or the last
+         * warp of the previous CTA (its progress word is published globally) */
+        const int wrow0 = (int) blockIdx.x * ME_LVL_ROWS + wic * ME_LVL_RPW;
+        const bool above_global = (wic == 0), pub_global = (wic == ME_LVL_WARPS - 1);
+        volatile const int *above = above_global ? (volatile const int *) (A.progress + (int) blockIdx.x - 1)
+                                                 : (volatile const int *) (sh->sprog + wic - 1);
+        int seen = (wrow0 == 0) ? 0x7fffffff : 0;
+        if (wrow0 < A.nrows) {
+            for (int t = 0; t < cols + ME_LVL_RPW - 1; t++) {
+                const int col = t - g;
+                const bool active = row < A.nrows && col >= 0 && col < cols;
+                /* the warp's first row is the only one that depends on another warp */
+                if (g == 0 && active && seen < col + 1) {
+                    while ((seen = *above) < col + 1) {
+                        __nanosleep(above_global ? ME_POLL_NS : ME_POLL_NS_CTA);
+                    }
+                    if (above_global) {
+                        __threadfence();
+                    } else {
+                        __threadfence_block();
+                    }
                 }
-                if (above_global) {
+                __syncwarp();
+                if (active) ME_LVL_NS::me_block(A, S, sh->pre_words[lr], col * step, row * step, acc_local);
+                /* vectors of this step must be visible before the next step's readers
+                 * (the other groups of the warp, then the next warp / CTA) */
+                if (pub_global) {
                     __threadfence();
                 } else {
                     __threadfence_block();
                 }
+                __syncwarp();
+                if (g == ME_LVL_RPW - 1 && active && (ME_KLANE % ME_LVL_G) == 0) {
+                    *(volatile int *) (sh->sprog + wic) = col + 1;
+                    if (pub_global) *(volatile int *) (A.progress + (int) blockIdx.x) = col + 1;
+                }
             }
-#if defined(ME_TIMING)
-            long long c1 = clock64();
-#endif
-            me_block(A, S, i, j, acc_local);
-#if defined(ME_TIMING)
-            tw += c1 - c0;
-            tb += clock64() - c1;
-#endif
-            if (pub_global) {
-                __threadfence();
-            } else {
-                __threadfence_block();
-            }
-            __syncwarp();
-            if (ME_LANE == 0) {
-                *(volatile int *) (sprog + lr) = col + 1;
-                if (pub_global) *(volatile int *) (A.progress + row) = col + 1;
-            }
-        }
-#if defined(ME_TIMING)
-        if (ME_LANE == 0 && A.level == 0) {
-            atomicAdd(&g_me_dbg[0], (unsigned long long) tb);
-            atomicAdd(&g_me_dbg[1], (unsigned long long) tw);
-            atomicAdd(&g_me_dbg[2], (unsigned long long) col);
-        }
-#endif
-    }
-#else
-    MeScratch *S = &scratch[0];
-    (void) sprog;
-    for (int lr = 0; lr < ME_WARPS_PER_CTA; lr++) {
-        int row = (int) blockIdx.x * ME_WARPS_PER_CTA + lr;
-        if (row >= A.nrows) continue;
-        for (int i = 0; i < A.nxb; i += step) {
-            me_block(A, S, i, row * step, acc_local);
         }
     }
-#endif
-    if (ME_LANE == 0 && A.level == 0) {
+    if ((ME_KLANE % ME_LVL_G) == 0 && A.level == 0) {
         for (int k = 0; k < 4; k++) {
             if (acc_local[k]) atomicAdd(&A.acc[k], acc_local[k]);
         }
     }
+#else
+    ME_LVL_NS::MeScratch *S = &sh->scratch[0];
+    for (int lr = 0; lr < ME_LVL_ROWS; lr++) {
+        int row = (int) blockIdx.x * ME_LVL_ROWS + lr;
+        if (row >= A.nrows) continue;
+        for (int i = 0; i < A.nxb; i += step) {
+#if defined(ME_COUNT)
+            g_me_in_wave = (A.level == 0);
+#endif
+            ME_LVL_NS::me_block(A, S, sh->pre_words[0], i, row * step, acc_local);
+#if defined(ME_COUNT)
+            g_me_in_wave = 0;
+#endif
+        }
+    }
+    if (A.level == 0) {
+        for (int k = 0; k < 4; k++) {
+            if (acc_local[k]) atomicAdd(&A.acc[k], acc_local[k]);
+        }
+    }
+#endif
 }
 
 /* global_motion (hme.c:1973-1999): average vector of a level, x2 */
@@ -2069,6 +436,7 @@ struct IaArgs {
 DSVCU_KERNEL void __launch_bounds__(ME_WARPS_PER_CTA * 32)
 k_intra_analysis(IaArgs A)
 {
+    using namespace meg32;
     DSVCU_SHARED int hists[ME_WARPS_PER_CTA][16];
     int *hist = hists[ME_WIC];
     const int total = A.nxb * A.nyb;
@@ -2138,7 +506,7 @@ k_intra_analysis(IaArgs A)
             if (maintain) flags |= MVF_MAINTAIN;
             if (keep_hf) flags |= MVF_SKIP;
         }
-        if (ME_LANE == 0) {
+        if (ME_KLANE == 0) {
             dsvcu_mv *o = A.out + b;
             o->x = 0;
             o->y = 0;
