@@ -197,6 +197,10 @@ def load(emu=False):
         "dsvcu_pyramid_destroy": (None, [vp, vp]),
         "dsvcu_pyramid_build": (ip, [vp, vp, vp]),
         "dsvcu_pyramid_level": (vp, [vp, ip]),
+        "dsvcu_extend_pyramid": (ip, [vp, vp, vp]),
+        "dsvcu_set_side": (ip, [vp, vp, vp, ip]),
+        "dsvcu_mvs_swap_prev": (ip, [vp, ip]),
+        "dsvcu_sub_pred_from": (ip, [vp, P(DSVCU_FMETA), vp, vp, vp, vp]),
         "dsvcu_set_prev_mvs": (ip, [vp, vp, ip]),
         "dsvcu_mvs_to_prev": (ip, [vp, ip]),
         "dsvcu_hme": (ip, [vp, P(DSVCU_FMETA), P(DSVCU_HME_PARAMS), vp, vp, vp, vp, vp, vp]),

@@ -105,8 +105,14 @@ struct dsvcu_ctx {
     int cw[3], ch[3]; /* coefficient plane dims */
     long long launches;
     /* side information */
-    uint8_t *d_blockdata;
-    dsvcu_mv *d_mvs;
+    /* two blocks [vector field | blockdata]: the current picture's side information and
+     * the previous picture's field (dsvcu_mvs_swap_prev exchanges them) */
+    uint8_t *d_side[2];
+    uint8_t *h_side;      /* pinned staging for one block */
+    size_t side_mv_bytes, side_bytes;
+    int side_cur;
+    uint8_t *d_blockdata; /* = d_side[side_cur] + side_mv_bytes */
+    dsvcu_mv *d_mvs;      /* = d_side[side_cur] */
     int nblk_cap;
     /* transform scratch: two LL ping-pong planes per coefficient plane (the
      * three planes of a picture are transformed by the same launches) */
@@ -128,7 +134,11 @@ struct dsvcu_ctx {
     cudaEvent_t marks[DSVCU_MARKS];
 #endif
     /* motion estimation */
-    dsvcu_mv *d_mvf[ME_MAXLVL + 1]; /* [0] aliases d_mvs */
+    dsvcu_mv *d_mvf[ME_MAXLVL + 1]; /* [0] aliases d_mvs; [1..] live in d_me_zero */
+    uint8_t *d_me_zero;             /* everything the search wants zeroed per picture: one memset */
+    size_t me_zero_bytes;
+    int *d_me_prog[ME_MAXLVL + 1];  /* per-level wavefront progress words */
+    int me_prog_cap;
     dsvcu_mv *d_prev_mvf;
     int mvf_cap;
     MePre *d_pre; /* per-block prepass records of the level being searched */
@@ -280,7 +290,9 @@ dsvcu_ctx_create(dsvcu_ctx **out, int device, int width, int height, int subsamp
     }
     c->progress_cap = height / 4 + 64;
     CK(dsvcu_malloc(&c->d_progress, (size_t) c->progress_cap * sizeof(int)));
-    CK(dsvcu_malloc(&c->d_me, 16 * sizeof(int)));
+    CK(dsvcu_malloc(&c->d_me_zero, 256)); /* d_me until the search sizes its block (ensure_mvf) */
+    c->d_me = (int *) c->d_me_zero;
+    c->me_zero_bytes = 256;
     CK(dsvcu_malloc_host(&c->h_me, 16 * sizeof(int)));
     CK(dsvcu_malloc(&c->d_lavg, 4 * sizeof(int)));
     CK(dsvcu_malloc_host(&c->h_lavg, 4 * sizeof(int)));
@@ -313,14 +325,11 @@ dsvcu_ctx_destroy(dsvcu_ctx *c)
         dsvcu_free_host(c->h_syms[i]);
     }
     dsvcu_free_dev(c->d_progress);
-    if (c->d_blockdata) dsvcu_free_dev(c->d_blockdata);
-    if (c->d_mvs) dsvcu_free_dev(c->d_mvs);
-    for (i = 1; i <= ME_MAXLVL; i++) {
-        if (c->d_mvf[i]) dsvcu_free_dev(c->d_mvf[i]);
-    }
-    if (c->d_prev_mvf) dsvcu_free_dev(c->d_prev_mvf);
+    if (c->d_side[0]) dsvcu_free_dev(c->d_side[0]);
+    if (c->d_side[1]) dsvcu_free_dev(c->d_side[1]);
+    if (c->h_side) dsvcu_free_host(c->h_side);
     if (c->d_pre) dsvcu_free_dev(c->d_pre);
-    dsvcu_free_dev(c->d_me);
+    if (c->d_me_zero) dsvcu_free_dev(c->d_me_zero);
     dsvcu_free_host(c->h_me);
     dsvcu_free_dev(c->d_lavg);
     dsvcu_free_host(c->h_lavg);
@@ -693,18 +702,34 @@ dsvcu_coefs_download(dsvcu_ctx *c, dsvcu_coefs *k, int plane, int32_t *dst)
 
 /* --------------------------------------------------------- side information */
 
+static void
+side_point(dsvcu_ctx *c)
+{
+    c->d_mvs = (dsvcu_mv *) c->d_side[c->side_cur];
+    c->d_blockdata = c->d_side[c->side_cur] + c->side_mv_bytes;
+    c->d_prev_mvf = (dsvcu_mv *) c->d_side[c->side_cur ^ 1];
+}
+
 static int
 ensure_blocks(dsvcu_ctx *c, int n)
 {
+    int i;
     if (n <= c->nblk_cap) return 0;
-    if (c->d_blockdata) dsvcu_free_dev(c->d_blockdata);
-    if (c->d_mvs) dsvcu_free_dev(c->d_mvs);
-    c->d_blockdata = NULL;
-    c->d_mvs = NULL;
-    CK(dsvcu_malloc(&c->d_blockdata, (size_t) n + 64));
-    CK(dsvcu_malloc(&c->d_mvs, ((size_t) n + 4) * sizeof(dsvcu_mv)));
-    CK(dsvcu_memset_async(c->d_blockdata, 0, (size_t) n + 64, c->stream));
-    CK(dsvcu_memset_async(c->d_mvs, 0, ((size_t) n + 4) * sizeof(dsvcu_mv), c->stream));
+    for (i = 0; i < 2; i++) {
+        if (c->d_side[i]) dsvcu_free_dev(c->d_side[i]);
+        c->d_side[i] = NULL;
+    }
+    if (c->h_side) dsvcu_free_host(c->h_side);
+    c->h_side = NULL;
+    c->side_mv_bytes = ((((size_t) n + 4) * sizeof(dsvcu_mv)) + 255) & ~(size_t) 255;
+    c->side_bytes = c->side_mv_bytes + (((size_t) n + 64 + 255) & ~(size_t) 255);
+    for (i = 0; i < 2; i++) {
+        CK(dsvcu_malloc(&c->d_side[i], c->side_bytes));
+        CK(dsvcu_memset_async(c->d_side[i], 0, c->side_bytes, c->stream));
+    }
+    CK(dsvcu_malloc_host(&c->h_side, c->side_bytes));
+    c->side_cur = 0;
+    side_point(c);
     c->nblk_cap = n;
     return 0;
 }
@@ -722,6 +747,37 @@ dsvcu_set_mvs(dsvcu_ctx *c, const void *mvs, int n)
 {
     if (ensure_blocks(c, n)) return -1;
     CK(dsvcu_h2d_async(c->d_mvs, mvs, (size_t) n * sizeof(dsvcu_mv), c->stream));
+    return 0;
+}
+
+/* dsvcu_set_blockdata + dsvcu_set_mvs (mvs may be NULL) as ONE copy from pinned
+ * staging.  The staging block is reused: the caller must not call this again
+ * before the previous copy has left the host, i.e. before its next wait on the
+ * context (every picture waits for its symbols / its output). */
+extern "C" int
+dsvcu_set_side(dsvcu_ctx *c, const uint8_t *bd, const void *mvs, int n)
+{
+    if (ensure_blocks(c, n)) return -1;
+    memcpy(c->h_side + c->side_mv_bytes, bd, (size_t) n);
+    if (mvs) {
+        memcpy(c->h_side, mvs, (size_t) n * sizeof(dsvcu_mv));
+        CK(dsvcu_h2d_async(c->d_side[c->side_cur], c->h_side, c->side_mv_bytes + (size_t) n, c->stream));
+    } else {
+        CK(dsvcu_h2d_async(c->d_blockdata, c->h_side + c->side_mv_bytes, (size_t) n, c->stream));
+    }
+    return 0;
+}
+
+/* The current vector field becomes "the previous picture's field" (DSV_HME.ref_mvf)
+ * by exchanging the two side-information blocks: no copy.  The current field and
+ * blockdata are undefined afterwards -- call it after the picture's last operator
+ * that reads them has been queued. */
+extern "C" int
+dsvcu_mvs_swap_prev(dsvcu_ctx *c, int nblocks)
+{
+    if (ensure_blocks(c, nblocks)) return -1;
+    c->side_cur ^= 1;
+    side_point(c);
     return 0;
 }
 
@@ -1222,6 +1278,8 @@ bmc_fill(BmcArgs *A, dsvcu_ctx *c, const dsvcu_fmeta *fm, dsvcu_frame *ref, dsvc
         if (res) {
             P->res = res->p[i].data;
             P->res_stride = res->p[i].stride;
+            P->src = P->res;
+            P->src_stride = P->res_stride;
             P->w = res->p[i].w;
             P->h = res->p[i].h;
         }
@@ -1347,6 +1405,29 @@ dsvcu_sub_pred(dsvcu_ctx *c, const dsvcu_fmeta *fm, dsvcu_frame *pred, dsvcu_fra
 {
     BmcArgs A;
     bmc_fill(&A, c, fm, ref, pred, resd, NULL, 0);
+    DSVCU_LAUNCH(k_predict, dim3(fm->nblocks_h * fm->nblocks_v, 3, 1), BMC_THREADS, 0, c->stream, A);
+    CK_LAUNCH(c);
+    return 0;
+}
+
+/* dsv_sub_pred with the source picture read from `src` and the residual written
+ * to `resd`: no clone of the source into the residual frame beforehand
+ * (dsv_encoder.c:1292).  Like the reference's subtract(), the kernel works on whole
+ * blocks, i.e. also on the border columns / rows the block grid covers past the
+ * picture edge -- source pixels there come from the padded source's border, and
+ * the residual written there is what the forward transform reads for the one
+ * extra column of an odd-width chroma plane (sbt.c:807). */
+extern "C" int
+dsvcu_sub_pred_from(dsvcu_ctx *c, const dsvcu_fmeta *fm, dsvcu_frame *pred, dsvcu_frame *resd, dsvcu_frame *ref,
+                    dsvcu_frame *src)
+{
+    BmcArgs A;
+    int i;
+    bmc_fill(&A, c, fm, ref, pred, resd, NULL, 0);
+    for (i = 0; i < 3; i++) {
+        A.pl[i].src = src->p[i].data;
+        A.pl[i].src_stride = src->p[i].stride;
+    }
     DSVCU_LAUNCH(k_predict, dim3(fm->nblocks_h * fm->nblocks_v, 3, 1), BMC_THREADS, 0, c->stream, A);
     CK_LAUNCH(c);
     return 0;
@@ -1482,17 +1563,49 @@ dsvcu_pyramid_level(dsvcu_pyramid *p, int level)
     return (level >= 1 && level <= p->levels) ? p->f[level] : NULL;
 }
 
+/* border of `base` (all its planes when extend_base, else taken as already
+ * extended) + every level of the pyramid, in two launches (k_frame.cuh) */
+static int
+pyramid_run(dsvcu_ctx *c, dsvcu_pyramid *p, dsvcu_frame *base, int extend_base)
+{
+    PyrArgs A;
+    int i, tiles;
+    memset(&A, 0, sizeof(A));
+    for (i = 0; i < base->nplanes; i++) {
+        A.base[i].data = base->p[i].data;
+        A.base[i].stride = base->p[i].stride;
+        A.base[i].w = base->p[i].w;
+        A.base[i].h = base->p[i].h;
+    }
+    A.nbase = extend_base ? base->nplanes : 0;
+    A.levels = p ? p->levels : 0;
+    for (i = 1; i <= A.levels; i++) {
+        A.lv[i].data = p->f[i]->p[0].data;
+        A.lv[i].stride = p->f[i]->p[0].stride;
+        A.lv[i].w = p->f[i]->p[0].w;
+        A.lv[i].h = p->f[i]->p[0].h;
+    }
+    if (A.levels > 0) {
+        tiles = ((base->p[0].w + PYR_TILE - 1) / PYR_TILE) * ((base->p[0].h + PYR_TILE - 1) / PYR_TILE);
+        DSVCU_LAUNCH(k_pyr_interior, tiles, 256, 0, c->stream, A);
+        CK_LAUNCH(c);
+    }
+    DSVCU_LAUNCH(k_pyr_borders, 1, 1024, 0, c->stream, A);
+    CK_LAUNCH(c);
+    return 0;
+}
+
 extern "C" int
 dsvcu_pyramid_build(dsvcu_ctx *c, dsvcu_pyramid *p, dsvcu_frame *base)
 {
-    dsvcu_frame *prev = base;
-    int i;
-    for (i = 1; i <= p->levels; i++) {
-        if (dsvcu_ds2x_luma(c, p->f[i], prev)) return -1;
-        if (dsvcu_extend_frame(c, p->f[i], 1)) return -1;
-        prev = p->f[i];
-    }
-    return 0;
+    return pyramid_run(c, p, base, 0);
+}
+
+/* dsv_extend_frame(base) followed by mk_pyramid(base) */
+extern "C" int
+dsvcu_extend_pyramid(dsvcu_ctx *c, dsvcu_frame *base, dsvcu_pyramid *p)
+{
+    return pyramid_run(c, p, base, 1);
 }
 
 static int
@@ -1501,16 +1614,30 @@ ensure_mvf(dsvcu_ctx *c, int nblk)
     int i;
     if (ensure_blocks(c, nblk)) return -1;
     if (nblk <= c->mvf_cap) return 0;
-    for (i = 1; i <= ME_MAXLVL; i++) {
-        if (c->d_mvf[i]) dsvcu_free_dev(c->d_mvf[i]);
-        CK(dsvcu_malloc(&c->d_mvf[i], ((size_t) nblk + 4) * sizeof(dsvcu_mv)));
+    /* one block: [d_me (16 ints)] [progress words of every level] [vector fields of levels 1..5] */
+    {
+        const size_t mvf_bytes = (((size_t) nblk + 4) * sizeof(dsvcu_mv) + 255) & ~(size_t) 255;
+        const int prog_cap = c->height / 8 + 64; /* rows of 16-px blocks at level 0, with room */
+        const size_t prog_bytes = (((size_t) prog_cap * sizeof(int)) + 255) & ~(size_t) 255;
+        size_t off = 256;
+        if (c->d_me_zero) dsvcu_free_dev(c->d_me_zero);
+        c->d_me_zero = NULL;
+        c->me_zero_bytes = 256 + (ME_MAXLVL + 1) * prog_bytes + ME_MAXLVL * mvf_bytes;
+        CK(dsvcu_malloc(&c->d_me_zero, c->me_zero_bytes));
+        c->d_me = (int *) c->d_me_zero;
+        for (i = 0; i <= ME_MAXLVL; i++) {
+            c->d_me_prog[i] = (int *) (c->d_me_zero + off);
+            off += prog_bytes;
+        }
+        c->me_prog_cap = prog_cap;
+        for (i = 1; i <= ME_MAXLVL; i++) {
+            c->d_mvf[i] = (dsvcu_mv *) (c->d_me_zero + off);
+            off += mvf_bytes;
+        }
     }
-    if (c->d_prev_mvf) dsvcu_free_dev(c->d_prev_mvf);
     if (c->d_pre) dsvcu_free_dev(c->d_pre);
     c->d_pre = NULL;
     CK(dsvcu_malloc(&c->d_pre, ((size_t) nblk + 4) * sizeof(MePre)));
-    CK(dsvcu_malloc(&c->d_prev_mvf, ((size_t) nblk + 4) * sizeof(dsvcu_mv)));
-    CK(dsvcu_memset_async(c->d_prev_mvf, 0, ((size_t) nblk + 4) * sizeof(dsvcu_mv), c->stream));
     c->mvf_cap = nblk;
     return 0;
 }
@@ -1541,7 +1668,9 @@ dsvcu_hme(dsvcu_ctx *c, const dsvcu_fmeta *fm, const dsvcu_hme_params *hp, dsvcu
     if (ensure_mvf(c, nblk)) return -1;
     c->me_nblk = nblk;
     c->d_mvf[0] = c->d_mvs;
-    CK(dsvcu_memset_async(c->d_me, 0, 16 * sizeof(int), c->stream));
+    /* accumulators, progress words and the fields of levels 1..n in one go, level 0's field apart */
+    CK(dsvcu_memset_async(c->d_me_zero, 0, c->me_zero_bytes, c->stream));
+    CK(dsvcu_memset_async(c->d_mvs, 0, (size_t) nblk * sizeof(dsvcu_mv), c->stream));
     for (lvl = hp->pyramid_levels; lvl >= 0; lvl--) {
         MeArgs A;
         int step = 1 << lvl, rows, ctas;
@@ -1579,14 +1708,11 @@ dsvcu_hme(dsvcu_ctx *c, const dsvcu_fmeta *fm, const dsvcu_hme_params *hp, dsvcu
         A.acc = c->d_me + 2;
         rows = (fm->nblocks_v + step - 1) / step;
         A.nrows = rows;
-        if (rows > c->progress_cap) {
-            dsvcu_free_dev(c->d_progress);
-            c->progress_cap = rows + 64;
-            CK(dsvcu_malloc(&c->d_progress, (size_t) c->progress_cap * sizeof(int)));
+        if (rows > c->me_prog_cap) {
+            snprintf(g_err, sizeof(g_err), "motion search: %d block rows exceed the progress table", rows);
+            return -1;
         }
-        A.progress = c->d_progress;
-        CK(dsvcu_memset_async(c->d_progress, 0, (size_t) rows * sizeof(int), c->stream));
-        CK(dsvcu_memset_async(c->d_mvf[lvl], 0, (size_t) nblk * sizeof(dsvcu_mv), c->stream));
+        A.progress = c->d_me_prog[lvl];
         A.pre = c->d_pre;
         A.b2sr = (256 * (hp->quant * hp->quant >> 12) * fm->blk_w * fm->blk_h) / (c->width * c->height);
         {
@@ -1784,6 +1910,8 @@ uniform_carveout(int device)
     CARVE(k_sbt_fwd);
     CARVE(k_sbt_inv);
     CARVE(k_luma_avg);
+    CARVE(k_pyr_interior);
+    CARVE(k_pyr_borders);
 #undef CARVE
     done[device] = 1;
 #else

@@ -28,8 +28,10 @@ struct BmcPlane {
     int ref_stride;
     uint8_t *pred;      /* encoder: prediction plane (written); decoder: unused */
     int pred_stride;
-    uint8_t *res;       /* residual plane: encoder in/out; decoder input */
+    uint8_t *res;       /* residual plane: encoder output; decoder input */
     int res_stride;
+    const uint8_t *src; /* encoder: source picture plane (may be the residual plane itself: in place) */
+    int src_stride;
     uint8_t *out;       /* decoder: reconstructed output plane */
     int out_stride;
     int w, h;           /* plane size */
@@ -202,7 +204,7 @@ k_predict(BmcArgs A)
             int r = k / bw, q = k - r * bw;
             int p = prd[r * BMC_MAXB + q];
             uint8_t *rp = P.res + (y + r) * P.res_stride + x + q;
-            int s = *rp, o;
+            int s = P.src[(y + r) * P.src_stride + x + q], o;
             P.pred[(y + r) * P.pred_stride + x + q] = (uint8_t) p;
             if (A.lossless) {
                 o = (s - p + 128) & 0xff;

@@ -933,8 +933,7 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
     for (i = 0; i < 3; i++) {
         GPU(dsvcu_frame_upload(g->ctx, src, i, frame->planes[i].data, frame->planes[i].stride));
     }
-    GPU(dsvcu_extend_frame(g->ctx, src, 0));
-    GPU(dsvcu_pyramid_build(g->ctx, g->src_pyr[g->cur], src));
+    GPU(dsvcu_extend_pyramid(g->ctx, src, g->src_pyr[g->cur]));
 
     if (enc->force_metadata || ((enc->prev_gop + (DSV_FNUM) enc->gop) <= fnum)) {
         gop_start = 1;
@@ -1034,25 +1033,23 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
 
     PROF_MARK(g, PH_SIDEINFO);
     /* ---- pixel pipeline (device), queued in one go ---- */
-    GPU(dsvcu_set_blockdata(g->ctx, enc->blockdata, nblk));
-    if (p->has_ref) {
-        GPU(dsvcu_set_mvs(g->ctx, g->mvs, nblk));
-    }
-    if (tried_motion) {
-        /* the field as the host left it is the next picture's temporal
-         * predictor (DSV_HME.ref_mvf = reference picture's final_mvs) */
-        if (!p->has_ref) {
-            GPU(dsvcu_set_prev_mvs(g->ctx, g->mvs, nblk));
-        } else {
-            GPU(dsvcu_mvs_to_prev(g->ctx, nblk));
-        }
+    GPU(dsvcu_set_side(g->ctx, enc->blockdata, p->has_ref ? g->mvs : NULL, nblk));
+    if (tried_motion && !p->has_ref) {
+        /* a picture that went through the search but is coded intra: the field as the
+         * host left it is the next picture's temporal predictor
+         * (DSV_HME.ref_mvf = reference picture's final_mvs) */
+        GPU(dsvcu_set_prev_mvs(g->ctx, g->mvs, nblk));
     }
     if (g_prof > 1 && p->has_ref) dsvcu_mark(g->ctx, 3);
-    GPU(dsvcu_frame_copy(g->ctx, rec, src));
+    /* the reference clones the padded source into the residual frame and works in
+     * place (dsv_encoder.c:1292); here an intra picture is transformed straight
+     * from the source, a predicted one has its residual written into `rec` */
     if (p->has_ref) {
-        GPU(dsvcu_sub_pred(g->ctx, &fm, g->pred, rec, ref_rec));
+        GPU(dsvcu_sub_pred_from(g->ctx, &fm, g->pred, rec, ref_rec, src));
+        GPU(dsvcu_fwd_sbt_frame(g->ctx, rec, g->coefs, &fm, 7));
+    } else {
+        GPU(dsvcu_fwd_sbt_frame(g->ctx, src, g->coefs, &fm, 7));
     }
-    GPU(dsvcu_fwd_sbt_frame(g->ctx, rec, g->coefs, &fm, 7));
     GPU(dsvcu_quant_frame(g->ctx, g->coefs, quant, &fm, 7));
     GPU(dsvcu_inv_sbt_frame(g->ctx, rec, g->coefs, quant, &fm, 7));
     if (!p->has_ref) {
@@ -1064,12 +1061,16 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
         if (g_prof > 1) dsvcu_mark(g->ctx, 5);
     }
     if (p->is_ref) {
-        GPU(dsvcu_extend_frame(g->ctx, rec, 0));
-        GPU(dsvcu_pyramid_build(g->ctx, g->ref_pyr, rec));
+        GPU(dsvcu_extend_pyramid(g->ctx, rec, g->ref_pyr));
     }
     if (g_prof > 1 && p->has_ref) {
         dsvcu_mark(g->ctx, 6);
         g->marks_live = 1;
+    }
+    if (tried_motion && p->has_ref) {
+        /* every reader of this picture's field is queued: it becomes the next
+         * picture's temporal predictor by exchanging buffers, not by copying */
+        GPU(dsvcu_mvs_swap_prev(g->ctx, nblk));
     }
 
     PROF_MARK(g, PH_QUEUE);

@@ -84,6 +84,9 @@ int dsvcu_coefs_download(dsvcu_ctx *ctx, dsvcu_coefs *c, int plane, int32_t *dst
 /* per-frame block side information (reference DSV_FMETA.blockdata / .mvs) */
 int dsvcu_set_blockdata(dsvcu_ctx *ctx, const uint8_t *blockdata, int nblocks);
 int dsvcu_set_mvs(dsvcu_ctx *ctx, const void *dsv_mv_array, int nblocks);
+/* both in one host-to-device copy through pinned staging (dsv_mv_array may be NULL);
+ * not to be called again before the next wait on the context */
+int dsvcu_set_side(dsvcu_ctx *ctx, const uint8_t *blockdata, const void *dsv_mv_array, int nblocks);
 
 /* ---- subband transforms ---- */
 /* dsv_fwd_sbt, reference sbt.c:847-886 (dsv_internal.h:112) */
@@ -117,6 +120,10 @@ int dsvcu_scan_layout(int w, int h, int part_start[5]);
 /* ---- motion compensation, reconstruction, filters ---- */
 /* dsv_sub_pred, reference bmc.c:1057-1070 */
 int dsvcu_sub_pred(dsvcu_ctx *ctx, const dsvcu_fmeta *fm, dsvcu_frame *pred, dsvcu_frame *resd, dsvcu_frame *ref);
+/* the same with the source read from `src` and the residual written to `resd`
+ * (saves cloning the source into the residual frame, dsv_encoder.c:1292) */
+int dsvcu_sub_pred_from(dsvcu_ctx *ctx, const dsvcu_fmeta *fm, dsvcu_frame *pred, dsvcu_frame *resd, dsvcu_frame *ref,
+                        dsvcu_frame *src);
 /* dsv_add_pred, reference bmc.c:1093-1111 */
 int dsvcu_add_pred(dsvcu_ctx *ctx, const dsvcu_fmeta *fm, int q, dsvcu_frame *resd, dsvcu_frame *out,
                    dsvcu_frame *ref, int do_filter);
@@ -141,6 +148,9 @@ int dsvcu_pyramid_create(dsvcu_ctx *ctx, dsvcu_pyramid **out, int levels);
 void dsvcu_pyramid_destroy(dsvcu_ctx *ctx, dsvcu_pyramid *p);
 /* mk_pyramid, reference dsv_encoder.c:493-516 (ds2x + luma border per level) */
 int dsvcu_pyramid_build(dsvcu_ctx *ctx, dsvcu_pyramid *p, dsvcu_frame *base);
+/* dsv_extend_frame(base) + mk_pyramid(base) fused: the border of every plane of
+ * `base`, then all pyramid levels with their borders, in two launches */
+int dsvcu_extend_pyramid(dsvcu_ctx *ctx, dsvcu_frame *base, dsvcu_pyramid *p);
 dsvcu_frame *dsvcu_pyramid_level(dsvcu_pyramid *p, int level); /* 1..n */
 
 typedef struct {
@@ -154,6 +164,10 @@ typedef struct {
 int dsvcu_set_prev_mvs(dsvcu_ctx *ctx, const void *dsv_mv_array, int nblocks);
 /* ... or from the device's current MV array (after dsvcu_hme / dsvcu_set_mvs) */
 int dsvcu_mvs_to_prev(dsvcu_ctx *ctx, int nblocks);
+/* ... or without a copy: the current array BECOMES the previous picture's field and the
+ * current array / blockdata are undefined afterwards (call after the picture's last
+ * operator that reads them has been queued) */
+int dsvcu_mvs_swap_prev(dsvcu_ctx *ctx, int nblocks);
 /* dsv_hme, reference hme.c:2001-2016 (struct DSV_HME, dsv_encoder.h:202-213).
  * Leaves the final field on the device as the current MV array (as if
  * dsvcu_set_mvs had been called with it). */

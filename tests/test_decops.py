@@ -161,7 +161,17 @@ def _extend_and_pyramid(geom, emu):
             d = np.argwhere(a != b)
             assert len(d) == 0, "plane %d: %d border/pixel bytes differ, first at row %d col %d" % (
                 p, len(d), d[0][0] - 32, d[0][1] - 32)
-        pyr = D.pyramid(f)
+        # the fused form (border of every plane + all levels in two launches) on a frame
+        # that has NOT been extended must give the same borders and the same pyramid
+        f2 = D.frame(fr[1], extend=False)
+        pyr = C.c_void_p()
+        D.ck(D.lib.dsvcu_pyramid_create(D.ctx, C.byref(pyr), cfg.pyr))
+        D._pyr.append(pyr)
+        D.ck(D.lib.dsvcu_extend_pyramid(D.ctx, f2, pyr))
+        for p in range(3):
+            a, gw, gh, gs = _bordered(D, f, p)
+            b, _, _, _ = _bordered(D, f2, p)
+            assert np.array_equal(a[:, :gw + 64], b[:, :gw + 64]), "fused extension, plane %d" % p
         for lvl in range(1, cfg.pyr + 1):
             pf = D.lib.dsvcu_pyramid_level(pyr, lvl)
             got, gw, gh, gs = _bordered(D, C.c_void_p(pf), 0)
