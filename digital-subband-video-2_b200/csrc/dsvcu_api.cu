@@ -45,8 +45,16 @@ static int uniform_carveout(int device);
 #ifdef DSVCU_DIAG
 /* diagnostics build only (-DDSVCU_DIAG): experiment knobs, never in the product library */
 static int g_pre_cap = getenv("DSVCU_PRE_GRID") ? atoi(getenv("DSVCU_PRE_GRID")) : 0; /* cap the prepass grid */
+/* DSVCU_SKIP (bit mask): leave out whole kernel families to see what caps the many-instance
+ * throughput (results are garbage, timing only): 1 transforms, 2 quantiser, 4 predict, 8 reconstruct,
+ * 16 loop / intra filter, 32 border + pyramid, 64 search prepass, 128 search wavefront */
+static int g_skip = getenv("DSVCU_SKIP") ? atoi(getenv("DSVCU_SKIP")) : 0;
+static int g_sbt_cap = getenv("DSVCU_SBT_CTAS") ? atoi(getenv("DSVCU_SBT_CTAS")) : 0; /* CTAs per plane and transform launch */
+static int g_grid_cap = getenv("DSVCU_GRID_CAP") ? atoi(getenv("DSVCU_GRID_CAP")) : 0; /* grid_for() ceiling */
+#define DIAG_SKIP(bit) (g_skip & (bit))
 #else
-static const int g_pre_cap = 0;
+static const int g_pre_cap = 0, g_sbt_cap = 0, g_grid_cap = 0;
+#define DIAG_SKIP(bit) 0
 #endif
 static long long g_launches = 0; /* kernels launched by every context of this process */
 
@@ -190,6 +198,7 @@ grid_for(int total, int threads)
     int g = (total + threads - 1) / threads;
     if (g < 1) g = 1;
     if (g > 148 * 16) g = 148 * 16;
+    if (g_grid_cap > 0 && g > g_grid_cap) g = g_grid_cap;
     return g;
 }
 
@@ -900,7 +909,7 @@ sbt_run(dsvcu_ctx *c, dsvcu_frame *fr, dsvcu_coefs *k, int q, const dsvcu_fmeta 
         if (tail[p] - 1 > maxbig) maxbig = tail[p] - 1;
     }
     /* stages: forward = levels 1..maxbig then the tails; inverse = the tails then maxbig..1 */
-    if (!mask) return 0;
+    if (!mask || DIAG_SKIP(1)) return 0;
     for (stage = 0; stage <= maxbig; stage++) {
         const int is_tail = fwd ? (stage == maxbig) : (stage == 0);
         int ctas = 0;
@@ -932,6 +941,7 @@ sbt_run(dsvcu_ctx *c, dsvcu_frame *fr, dsvcu_coefs *k, int q, const dsvcu_fmeta 
                 }
                 n = 1;
                 P->ncta = sbt_level_ctas(&P->L[0], P->f[0]);
+                if (g_sbt_cap > 0 && P->ncta > g_sbt_cap) P->ncta = g_sbt_cap;
             }
             P->nlev = n;
             P->first_cta = ctas;
@@ -1124,6 +1134,13 @@ quant_run(dsvcu_ctx *c, dsvcu_coefs *k, int q, const dsvcu_fmeta *fm, int mask)
         if (mask & (1 << i)) pl[n++] = i;
     }
     if (!n) return 0;
+    if (DIAG_SKIP(2)) {
+        for (i = 0; i < n; i++) c->h_meta[pl[i]] = 0;
+#ifndef DSVCU_EMU
+        for (i = 0; i < n; i++) CK(cudaEventRecord(c->ev_sym[pl[i]], c->stream));
+#endif
+        return 0;
+    }
     memset(&CJ, 0, sizeof(CJ));
     gmax = 1;
     for (i = 0; i < n; i++) {
@@ -1326,7 +1343,7 @@ run_filter_job(dsvcu_ctx *c, FiltJob *J, int nplanes)
         bands += (F->nrows + FILT_G - 1) / FILT_G;
     }
     J->nplanes = nplanes;
-    if (!ctas) return 0;
+    if (!ctas || DIAG_SKIP(16)) return 0;
     if (smem > 200 * 1024) {
         snprintf(g_err, sizeof(g_err), "picture too wide for the filter schedule");
         return -1;
@@ -1423,6 +1440,7 @@ dsvcu_sub_pred_from(dsvcu_ctx *c, const dsvcu_fmeta *fm, dsvcu_frame *pred, dsvc
 {
     BmcArgs A;
     int i;
+    if (DIAG_SKIP(4)) return 0;
     bmc_fill(&A, c, fm, ref, pred, resd, NULL, 0);
     for (i = 0; i < 3; i++) {
         A.pl[i].src = src->p[i].data;
@@ -1449,6 +1467,7 @@ dsvcu_add_res(dsvcu_ctx *c, const dsvcu_fmeta *fm, int q, dsvcu_frame *resd, dsv
 {
     BmcArgs A;
     bmc_fill(&A, c, fm, NULL, pred, resd, NULL, 0);
+    if (!DIAG_SKIP(8))
     DSVCU_LAUNCH(k_reconstruct, dim3(fm->nblocks_h * fm->nblocks_v, 3, 1), BMC_THREADS, 0, c->stream, A);
     CK_LAUNCH(c);
     return loop_filters(c, fm, q, resd, do_filter);
@@ -1570,6 +1589,7 @@ pyramid_run(dsvcu_ctx *c, dsvcu_pyramid *p, dsvcu_frame *base, int extend_base)
 {
     PyrArgs A;
     int i, tiles;
+    if (DIAG_SKIP(32)) return 0;
     memset(&A, 0, sizeof(A));
     for (i = 0; i < base->nplanes; i++) {
         A.base[i].data = base->p[i].data;
@@ -1590,7 +1610,7 @@ pyramid_run(dsvcu_ctx *c, dsvcu_pyramid *p, dsvcu_frame *base, int extend_base)
         DSVCU_LAUNCH(k_pyr_interior, tiles, 256, 0, c->stream, A);
         CK_LAUNCH(c);
     }
-    DSVCU_LAUNCH(k_pyr_borders, 1, 1024, 0, c->stream, A);
+    DSVCU_LAUNCH(k_pyr_borders, 1, PYR_BORDER_THREADS, 0, c->stream, A);
     CK_LAUNCH(c);
     return 0;
 }
@@ -1725,6 +1745,7 @@ dsvcu_hme(dsvcu_ctx *c, const dsvcu_fmeta *fm, const dsvcu_hme_params *hp, dsvcu
 #endif
             if (pctas > 148 * 8) pctas = 148 * 8;
             if (g_pre_cap > 0 && pctas > g_pre_cap) pctas = g_pre_cap;
+            if (!DIAG_SKIP(64))
             DSVCU_LAUNCH(k_me_prepass, pctas, ME_PRE_THREADS, 0, c->stream, A);
             CK_LAUNCH(c);
         }
@@ -1736,6 +1757,7 @@ dsvcu_hme(dsvcu_ctx *c, const dsvcu_fmeta *fm, const dsvcu_hme_params *hp, dsvcu
             c->me_smem_set = 1;
         }
 #endif
+        if (!DIAG_SKIP(128))
         DSVCU_LAUNCH(k_me_level, ctas, ME_LVL_WARPS * 32, sizeof(MeLvlShared), c->stream, A);
         CK_LAUNCH(c);
         if (lvl != 0) {
@@ -1886,7 +1908,10 @@ uniform_carveout(int device)
 {
 #ifndef DSVCU_EMU
     static int done[64];
-    static const int pct = 58;
+#ifndef DSVCU_CARVEOUT_PCT
+#define DSVCU_CARVEOUT_PCT 58
+#endif
+    static const int pct = DSVCU_CARVEOUT_PCT;
     if (device < 0 || device >= 64 || done[device] || pct < 0) return 0;
 #define CARVE(k) CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct))
     CARVE(k_compact_count);

@@ -143,6 +143,9 @@ k_ds2x(uint8_t *dst, int ds, int dw, int dh, const uint8_t *src, int ss)
  * Same arithmetic as k_ds2x / k_extend, bit-identical planes and borders. */
 #define PYR_MAXLVL 5
 #define PYR_TILE 64
+#ifndef PYR_BORDER_THREADS
+#define PYR_BORDER_THREADS 1024
+#endif
 struct PyrArgs {
     ExtPlane base[3]; /* [0] = luma = pyramid level 0 */
     int nbase;        /* planes of the base picture to extend first (0: already extended) */
@@ -207,7 +210,7 @@ k_pyr_interior(PyrArgs A)
     }
 }
 
-DSVCU_KERNEL void __launch_bounds__(1024)
+DSVCU_KERNEL void __launch_bounds__(PYR_BORDER_THREADS)
 k_pyr_borders(PyrArgs A)
 {
     for (int p = 0; p < A.nbase; p++) {

@@ -37,7 +37,9 @@
 #endif
 /* the prepass runs four blocks per warp (groups of ME_PRE_G lanes, k_hme_body.cuh) */
 #define ME_PRE_G 8
+#ifndef ME_PRE_THREADS
 #define ME_PRE_THREADS 128
+#endif
 #define ME_PRE_GROUPS (ME_PRE_THREADS / ME_PRE_G)
 #ifndef ME_PRE_MIN_CTAS
 #define ME_PRE_MIN_CTAS 4
