@@ -199,6 +199,7 @@ def load(emu=False):
         "dsvcu_pyramid_level": (vp, [vp, ip]),
         "dsvcu_extend_pyramid": (ip, [vp, vp, vp]),
         "dsvcu_set_side": (ip, [vp, vp, vp, ip]),
+        "dsvcu_hme_counters": (ip, [vp, P(C.c_longlong)]),
         "dsvcu_mvs_swap_prev": (ip, [vp, ip]),
         "dsvcu_sub_pred_from": (ip, [vp, P(DSVCU_FMETA), vp, vp, vp, vp]),
         "dsvcu_set_prev_mvs": (ip, [vp, vp, ip]),

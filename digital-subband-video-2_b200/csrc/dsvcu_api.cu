@@ -116,7 +116,8 @@ struct dsvcu_ctx {
     /* two blocks [vector field | blockdata]: the current picture's side information and
      * the previous picture's field (dsvcu_mvs_swap_prev exchanges them) */
     uint8_t *d_side[2];
-    uint8_t *h_side;      /* pinned staging for one block */
+    uint8_t *h_side;      /* pinned staging for one block (= h_side_set[stage_cur]) */
+    uint8_t *h_side_set[2];
     size_t side_mv_bytes, side_bytes;
     int side_cur;
     uint8_t *d_blockdata; /* = d_side[side_cur] + side_mv_bytes */
@@ -131,7 +132,15 @@ struct dsvcu_ctx {
     int *d_meta;          /* [0..2] nsyms, [3..5] dc */
     int *h_meta;          /* pinned mirror */
     dsvcu_sym *d_syms[3];
-    dsvcu_sym *h_syms[3]; /* pinned */
+    dsvcu_sym *h_syms[3]; /* pinned (= h_syms_set[stage_cur]) */
+    /* Host staging comes in two sets so that a caller may fill the next picture's symbols and
+     * side information while the copies of the previous picture are still in flight
+     * (dsvcu_staging_flip); callers that wait for every picture only ever use set 0 */
+    dsvcu_sym *h_syms_set[2][3];
+    int stage_cur;
+#ifndef DSVCU_EMU
+    cudaEvent_t ev_stage[2]; /* last host-to-device copy out of the set has completed */
+#endif
     int sym_cap[3];
     int *d_progress;
     int progress_cap;
@@ -295,7 +304,8 @@ dsvcu_ctx_create(dsvcu_ctx **out, int device, int width, int height, int subsamp
     for (i = 0; i < 3; i++) {
         c->sym_cap[i] = c->cw[i] * c->ch[i] + 8;
         CK(dsvcu_malloc(&c->d_syms[i], (size_t) c->sym_cap[i] * sizeof(dsvcu_sym)));
-        CK(dsvcu_malloc_host(&c->h_syms[i], (size_t) c->sym_cap[i] * sizeof(dsvcu_sym)));
+        CK(dsvcu_malloc_host(&c->h_syms_set[0][i], (size_t) c->sym_cap[i] * sizeof(dsvcu_sym)));
+        c->h_syms[i] = c->h_syms_set[0][i];
     }
     c->progress_cap = height / 4 + 64;
     CK(dsvcu_malloc(&c->d_progress, (size_t) c->progress_cap * sizeof(int)));
@@ -331,7 +341,8 @@ dsvcu_ctx_destroy(dsvcu_ctx *c)
     dsvcu_free_host(c->h_meta);
     for (i = 0; i < 3; i++) {
         dsvcu_free_dev(c->d_syms[i]);
-        dsvcu_free_host(c->h_syms[i]);
+        dsvcu_free_host(c->h_syms_set[0][i]);
+        if (c->h_syms_set[1][i]) dsvcu_free_host(c->h_syms_set[1][i]);
     }
     dsvcu_free_dev(c->d_progress);
     if (c->d_side[0]) dsvcu_free_dev(c->d_side[0]);
@@ -728,7 +739,10 @@ ensure_blocks(dsvcu_ctx *c, int n)
         if (c->d_side[i]) dsvcu_free_dev(c->d_side[i]);
         c->d_side[i] = NULL;
     }
-    if (c->h_side) dsvcu_free_host(c->h_side);
+    for (i = 0; i < 2; i++) {
+        if (c->h_side_set[i]) dsvcu_free_host(c->h_side_set[i]);
+        c->h_side_set[i] = NULL;
+    }
     c->h_side = NULL;
     c->side_mv_bytes = ((((size_t) n + 4) * sizeof(dsvcu_mv)) + 255) & ~(size_t) 255;
     c->side_bytes = c->side_mv_bytes + (((size_t) n + 64 + 255) & ~(size_t) 255);
@@ -736,7 +750,9 @@ ensure_blocks(dsvcu_ctx *c, int n)
         CK(dsvcu_malloc(&c->d_side[i], c->side_bytes));
         CK(dsvcu_memset_async(c->d_side[i], 0, c->side_bytes, c->stream));
     }
-    CK(dsvcu_malloc_host(&c->h_side, c->side_bytes));
+    CK(dsvcu_malloc_host(&c->h_side_set[0], c->side_bytes));
+    CK(dsvcu_malloc_host(&c->h_side_set[1], c->side_bytes));
+    c->h_side = c->h_side_set[c->stage_cur];
     c->side_cur = 0;
     side_point(c);
     c->nblk_cap = n;
@@ -774,6 +790,9 @@ dsvcu_set_side(dsvcu_ctx *c, const uint8_t *bd, const void *mvs, int n)
     } else {
         CK(dsvcu_h2d_async(c->d_blockdata, c->h_side + c->side_mv_bytes, (size_t) n, c->stream));
     }
+#ifndef DSVCU_EMU
+    if (c->ev_stage[c->stage_cur]) CK(cudaEventRecord(c->ev_stage[c->stage_cur], c->stream));
+#endif
     return 0;
 }
 
@@ -1223,6 +1242,30 @@ dsvcu_fetch_symbols(dsvcu_ctx *c, int plane, const dsvcu_symbol **syms, int *nsy
     return 0;
 }
 
+/* Switch to the other set of host staging buffers (symbols, side information) and wait until
+ * the device has finished copying out of it.  A decoder that calls this at the start of
+ * every picture may parse picture n + 1 while picture n is still being copied / decoded. */
+extern "C" int
+dsvcu_staging_flip(dsvcu_ctx *c)
+{
+    int i;
+    c->stage_cur ^= 1;
+    for (i = 0; i < 3; i++) {
+        if (!c->h_syms_set[c->stage_cur][i]) {
+            CK(dsvcu_malloc_host(&c->h_syms_set[c->stage_cur][i], (size_t) c->sym_cap[i] * sizeof(dsvcu_sym)));
+        }
+        c->h_syms[i] = c->h_syms_set[c->stage_cur][i];
+    }
+    if (c->h_side_set[c->stage_cur]) c->h_side = c->h_side_set[c->stage_cur];
+#ifndef DSVCU_EMU
+    for (i = 0; i < 2; i++) {
+        if (!c->ev_stage[i]) CK(cudaEventCreateWithFlags(&c->ev_stage[i], cudaEventDisableTiming | cudaEventBlockingSync));
+    }
+    CK(cudaEventSynchronize(c->ev_stage[c->stage_cur])); /* never recorded = complete */
+#endif
+    return 0;
+}
+
 extern "C" dsvcu_symbol *
 dsvcu_symbol_staging(dsvcu_ctx *c, int plane, int *capacity)
 {
@@ -1245,6 +1288,9 @@ dsvcu_dequant_plane(dsvcu_ctx *c, dsvcu_coefs *k, int plane, int q, const dsvcu_
     c->h_syms[plane][nsyms].pos = 0;
     c->h_syms[plane][nsyms].v = dc;
     CK(dsvcu_h2d_async(c->d_syms[plane], c->h_syms[plane], (size_t) (nsyms + 1) * sizeof(dsvcu_sym), c->stream));
+#ifndef DSVCU_EMU
+    if (c->ev_stage[c->stage_cur]) CK(cudaEventRecord(c->ev_stage[c->stage_cur], c->stream));
+#endif
     if (nsyms > 0) {
         quant_level_geom(&Q, c, k, plane, qf, fm, -1, part);
         Q.syms = c->d_syms[plane];
@@ -1809,6 +1855,16 @@ dsvcu_hme_fetch(dsvcu_ctx *c, void *mvs_out, int nblocks, int *intra_pct, int *s
     *intra_pct = (c->h_me[2] * 100) / nblocks;
     *scene_change_blocks = c->h_me[3] * 100 / elig;
     *avg_err = (int) ((unsigned) c->h_me[5] / (unsigned) nblocks);
+    return 0;
+}
+
+/* work counters of the last dsvcu_hme (valid after dsvcu_hme_fetch): [0] full-block metric
+ * evaluations (SSE at levels > 1, the psycho-visual metric below), [1] sub-pel position metrics */
+extern "C" int
+dsvcu_hme_counters(dsvcu_ctx *c, long long out[2])
+{
+    out[0] = c->h_me[8];
+    out[1] = c->h_me[9];
     return 0;
 }
 

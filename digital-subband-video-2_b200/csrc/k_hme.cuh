@@ -82,7 +82,7 @@ struct MeArgs {
     int level, quant, effort, lossless, skip_thresh;
     int hs, vs, vid_w, vid_h, psyscale;
     const int *gxy; /* global motion from the level above */
-    int *acc;       /* [0] nintra [1] ndiff [2] eligible [3] total_err */
+    int *acc;       /* [0] nintra [1] ndiff [2] eligible [3] total_err; [6] full-block metric evaluations [7] sub-pel position metrics (all levels) */
     int *progress;
     int nrows;
     int b2sr;          /* (256 * (q*q >> 12) * blk_w * blk_h) / (width * height), dsv.c:370 */

@@ -748,6 +748,8 @@ struct MeScratch {
     /* full-pel metric memo of the current block: position -> raw metric */
     short memo_x[ME_MEMO], memo_y[ME_MEMO];
     unsigned memo_v[ME_MEMO];
+    /* work counters of the current block (lane 0): full-block metric evaluations, sub-pel position metrics */
+    int n_evals, n_subpel;
 };
 
 /* Sub-pel refinement, split in two.  me_subpel_measure: everything that depends
@@ -819,6 +821,10 @@ me_subpel_measure(const MeArgs &A, MeScratch *S, MeSubpel *M, int fpelx, int fpe
         nv++;
     }
     M->nv = nv;
+    if (ME_LANE == 0) {
+        S->n_evals += 4;     /* the four neighbour SSEs that order the search */
+        S->n_subpel += nv;
+    }
     me_qpsad_multi(sp.data + yy * sp.stride + xx, sp.stride, S->tmph, nv, M->tx, M->ty, psy, M->sc);
 }
 
@@ -1088,6 +1094,7 @@ me_eval(MeScratch *S, int &mn, int level, const uint8_t *srcd, int ss, const MeP
     if (k >= 0) return S->memo_v[k];
     ME_CNT(MEC_EVAL_MISS);
     unsigned sc = me_hier_metr(level, srcd, ss, rp.data + (by + dy) * rp.stride + bx + dx, rp.stride, bw, bh, psy);
+    if (ME_LANE == 0) S->n_evals++;
     me_memo_add(S, mn, dx, dy, sc);
     return sc;
 }
@@ -1282,6 +1289,7 @@ me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j)
     unsigned var_src, avg_src, zoscore;
     int motion_bias, lax, lay, nb, cbx[ME_PRE_NB], cby[ME_PRE_NB], has, mn = 0, uavg = 0, vavg = 0;
     MePsy psy;
+    if (ME_LANE == 0) S->n_evals = S->n_subpel = 0;
     me_src_stats(A, S, srcd, sp.stride, bw, bh, gx, gy, &var_src, &avg_src, &motion_bias, &psy);
     has = me_nonspatial(A, i, j, gx, gy, &lax, &lay, cbx, cby, &nb);
     /* measure zero, the parent average and the list (valid, distinct positions) */
@@ -1448,6 +1456,8 @@ me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j)
     }
     ME_SYNC();
     if (ME_LANE == 0) {
+        if (S->n_evals) atomicAdd(&A.acc[6], S->n_evals);
+        if (S->n_subpel) atomicAdd(&A.acc[7], S->n_subpel);
         P->sx = sx;
         P->sy = sy;
         P->s_valid = s_valid;
@@ -1538,6 +1548,7 @@ me_block(const MeArgs &A, MeScratch *S, uint32_t *pre_words, int i, int j, int *
     bh = min(sp.h - by, A.y_h);
     MePred pred;
     int mn = 0; /* entries in the block's metric memo */
+    if (ME_LANE == 0) S->n_evals = S->n_subpel = 0;
     /* one coalesced batch of loads (a single L2 round trip) instead of a miss
      * per touched line of the record */
     {
@@ -1931,6 +1942,8 @@ me_block(const MeArgs &A, MeScratch *S, uint32_t *pre_words, int i, int j, int *
         }
     }
     if (ME_LANE == 0) {
+        if (S->n_evals) atomicAdd(&A.acc[6], S->n_evals);
+        if (S->n_subpel) atomicAdd(&A.acc[7], S->n_subpel);
         out->x = (int16_t) mv.x;
         out->y = (int16_t) mv.y;
         out->flags = mv.flags;

@@ -44,6 +44,29 @@ dsv_dec_direct_output(uint8_t *dst)
     tls_direct_out = dst;
 }
 
+/* set by the whole-stream drivers: pictures decoded by this thread are NOT waited for;
+ * dsv_dec returns as soon as the picture's work is queued (its frame, written straight to
+ * the caller's memory, is complete after dsv_dec_flush).  Host parsing of picture n + 1
+ * then overlaps the device work of picture n. */
+static __thread int tls_async = 0;
+
+void
+dsv_dec_set_async(int on)
+{
+    tls_async = on;
+}
+
+int
+dsv_dec_flush(DSV_DECODER *d)
+{
+    DEC_STATE *s = (DEC_STATE *) d->ref;
+    if (s && s->ctx && dsvcu_sync(s->ctx)) {
+        DSV_ERROR(("dsv_dec_flush: %s", dsvcu_last_error()));
+        return -1;
+    }
+    return 0;
+}
+
 static void
 state_free(DEC_STATE *s)
 {
@@ -415,10 +438,11 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
 
     p->temporal_mc = isP ? (int) DSV_TEMPORAL_MC(fno) : 0;
     dsv_fmeta_from_params(&fm, p, isP, fno);
-    GPU(dsvcu_set_blockdata(s->ctx, s->blockdata, nblk));
-    if (isP) {
-        GPU(dsvcu_set_mvs(s->ctx, s->mvs, nblk));
+    if (tls_async && tls_direct_out) {
+        /* the previous picture may still be reading the staging set just used */
+        GPU(dsvcu_staging_flip(s->ctx));
     }
+    GPU(dsvcu_set_side(s->ctx, s->blockdata, isP ? s->mvs : NULL, nblk));
 
     /* intra pictures are reconstructed straight into the output picture;
      * inter pictures into the residual frame, then predicted + added */
@@ -463,7 +487,9 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
     for (i = 0; i < 3; i++) {
         GPU(dsvcu_frame_download(s->ctx, dst, i, host->planes[i].data, host->planes[i].stride));
     }
-    GPU(dsvcu_sync(s->ctx));
+    if (!(tls_async && tls_direct_out)) {
+        GPU(dsvcu_sync(s->ctx));
+    }
     if (is_ref) {
         s->cur ^= 1;
         s->have_ref = 1;

@@ -21,6 +21,8 @@
 /* internal hooks of dsv_enc.c / dsv_dec.c */
 void dsv_enc_recycle(DSV_ENCODER *from, DSV_ENCODER *to);
 void dsv_dec_direct_output(uint8_t *dst);
+void dsv_dec_set_async(int on);
+int dsv_dec_flush(DSV_DECODER *d);
 
 static __thread int tls_device = -1;
 
@@ -600,6 +602,8 @@ static int
 decode_range(DSV_DECODER *dec, const uint8_t *d, const PKT *pk, int first, int last, uint8_t *dst, size_t fsz)
 {
     int i, nfr = 0;
+    /* pictures are queued without waiting: parsing the next packet overlaps the device work */
+    dsv_dec_set_async(1);
     for (i = first; i < last; i++) {
         DSV_BUF b;
         DSV_FRAME *fr = NULL;
@@ -625,6 +629,10 @@ decode_range(DSV_DECODER *dec, const uint8_t *d, const PKT *pk, int first, int l
             nfr++;
             dsv_frame_ref_dec(fr);
         }
+    }
+    dsv_dec_set_async(0);
+    if (dsv_dec_flush(dec)) {
+        return 0;
     }
     return nfr;
 }

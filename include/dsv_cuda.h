@@ -111,6 +111,10 @@ int dsvcu_fetch_symbols(dsvcu_ctx *ctx, int plane, const dsvcu_symbol **syms, in
  * list is in scan order; level_start[0..4] = index of the first symbol of the
  * LL part, level 0, 1, 2 and the end.  Zero-fills the plane first. */
 dsvcu_symbol *dsvcu_symbol_staging(dsvcu_ctx *ctx, int plane, int *capacity);
+/* the staging buffers (symbols, dsvcu_set_side) exist twice: switch to the other set, waiting
+ * until the device has copied everything out of it.  Lets a decoder parse the next picture
+ * while the previous one is still in flight; pointers from dsvcu_symbol_staging are per set. */
+int dsvcu_staging_flip(dsvcu_ctx *ctx);
 int dsvcu_dequant_plane(dsvcu_ctx *ctx, dsvcu_coefs *c, int plane, int q, const dsvcu_fmeta *fm,
                         int nsyms, const int level_start[5], int dc);
 /* number of scan positions of a plane and the first scan position of each
@@ -178,6 +182,9 @@ int dsvcu_hme(dsvcu_ctx *ctx, const dsvcu_fmeta *fm, const dsvcu_hme_params *hp,
  * dsv_hme returns (intra %, scene-change blocks %, average error) */
 int dsvcu_hme_fetch(dsvcu_ctx *ctx, void *mvs_out, int nblocks, int *intra_pct, int *scene_change_blocks,
                     int *avg_err);
+/* work counters of the last dsvcu_hme, valid after dsvcu_hme_fetch: [0] full-block metric
+ * evaluations, [1] sub-pel position metrics (the unit SURVEY section 8d asks the search to be measured in) */
+int dsvcu_hme_counters(dsvcu_ctx *ctx, long long out[2]);
 /* dsv_intra_analysis, reference hme.c:1835-1971; result via dsvcu_hme_fetch-like copy */
 int dsvcu_intra_analysis(dsvcu_ctx *ctx, const dsvcu_fmeta *fm, dsvcu_frame *src, void *mvs_out, int nblocks);
 /* the same in two halves: queue the kernel + copy, then wait and read */
