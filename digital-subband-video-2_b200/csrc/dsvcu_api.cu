@@ -1794,6 +1794,17 @@ dsvcu_hme(dsvcu_ctx *c, const dsvcu_fmeta *fm, const dsvcu_hme_params *hp, dsvcu
             if (!DIAG_SKIP(64))
             DSVCU_LAUNCH(k_me_prepass, pctas, ME_PRE_THREADS, 0, c->stream, A);
             CK_LAUNCH(c);
+            if (lvl == 0 && fm->effort >= 4) {
+                /* the two sub-pel measurements of every block, one warp each */
+                int sctas = (2 * nblk + ME_SP_WARPS - 1) / ME_SP_WARPS;
+#ifdef DSVCU_EMU
+                sctas = 1;
+#endif
+                if (sctas > 148 * 8) sctas = 148 * 8;
+                if (!DIAG_SKIP(64))
+                DSVCU_LAUNCH(k_me_subpel, sctas, ME_SP_WARPS * 32, 0, c->stream, A);
+                CK_LAUNCH(c);
+            }
         }
         /* four block rows per warp; CTA k only waits for CTA k-1, dispatched first */
         ctas = (rows + ME_LVL_ROWS - 1) / ME_LVL_ROWS;
@@ -1982,6 +1993,7 @@ uniform_carveout(int device)
     CARVE(k_me_global);
     CARVE(k_me_level);
     CARVE(k_me_prepass);
+    CARVE(k_me_subpel);
     CARVE(k_post_sharpen);
     CARVE(k_predict);
     CARVE(k_quant_hf);

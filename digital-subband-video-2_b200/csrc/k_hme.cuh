@@ -42,7 +42,7 @@
 #endif
 #define ME_PRE_GROUPS (ME_PRE_THREADS / ME_PRE_G)
 #ifndef ME_PRE_MIN_CTAS
-#define ME_PRE_MIN_CTAS 4
+#define ME_PRE_MIN_CTAS 8
 #endif
 #ifndef ME_POLL_NS_CTA
 #define ME_POLL_NS_CTA 128 /* same, for rows whose predecessor is in the same CTA */
@@ -275,10 +275,38 @@ k_me_prepass(MeArgs A)
     DSVCU_SHARED meg8::MeScratch scratch[ME_PRE_GROUPS];
     meg8::MeScratch *S = &scratch[ME_GIC(ME_PRE_G)];
     const int step = 1 << A.level;
+    if (ME_KLANE % ME_PRE_G == 0) S->ip = NULL; /* no sub-pel measurement in here: k_me_subpel */
+#ifndef DSVCU_EMU
+    __syncwarp();
+#endif
     const int cols = (A.nxb + step - 1) / step, rows = (A.nyb + step - 1) / step;
     for (int b = ME_GRP(ME_PRE_G); b < cols * rows; b += ME_NGRPS(ME_PRE_G)) {
         int r = b / cols, c = b - r * cols;
         meg8::me_prepass_block(A, S, c * step, r * step);
+    }
+}
+
+/* The sub-pel measurements of level 0 (half-pel image of a 17 x 17 window + the metric at
+ * up to seven quarter-pel offsets, hme.c:1051-1164), two per block: around the parent
+ * average and around the speculated winner.  One warp per measurement: 289 interpolated
+ * samples and 7 x 32 metric work items keep all 32 lanes busy, which the 8-lane groups of
+ * the prepass could not -- and without the interpolation scratch the prepass fits three
+ * times as many blocks per SM. */
+#define ME_SP_WARPS 8
+DSVCU_KERNEL void __launch_bounds__(ME_SP_WARPS * 32)
+k_me_subpel(MeArgs A)
+{
+    DSVCU_SHARED meg32::MeInterp interp[ME_SP_WARPS];
+    DSVCU_SHARED meg32::MeScratch scratch[ME_SP_WARPS];
+    meg32::MeScratch *S = &scratch[ME_WIC];
+    const int ntask = 2 * A.nxb * A.nyb;
+    if (ME_KLANE == 0) S->ip = &interp[ME_WIC];
+#ifndef DSVCU_EMU
+    __syncwarp();
+#endif
+    for (int t = ME_WARP; t < ntask; t += ME_NWARPS) {
+        const int b = t >> 1;
+        meg32::me_subpel_task(A, S, b % A.nxb, b / A.nxb, t & 1);
     }
 }
 
@@ -312,6 +340,7 @@ k_me_prepass(MeArgs A)
 #endif
 #define ME_LVL_ROWS (ME_LVL_WARPS * ME_LVL_RPW) /* rows per CTA */
 struct MeLvlShared {
+    ME_LVL_NS::MeInterp interp[ME_LVL_ROWS];
     ME_LVL_NS::MeScratch scratch[ME_LVL_ROWS];
     __align__(16) uint32_t pre_words[ME_LVL_ROWS][ME_PRE_WORDS];
     int sprog[ME_LVL_WARPS];
@@ -329,6 +358,7 @@ k_me_level(MeArgs A)
     const int row = (int) blockIdx.x * ME_LVL_ROWS + lr;
     const int cols = (A.nxb + step - 1) / step;
     ME_LVL_NS::MeScratch *S = &sh->scratch[lr];
+    if ((ME_KLANE % ME_LVL_G) == 0) S->ip = &sh->interp[lr];
     if (threadIdx.x < ME_LVL_WARPS) sh->sprog[threadIdx.x] = 0;
     __syncthreads();
     {
@@ -378,6 +408,7 @@ k_me_level(MeArgs A)
     }
 #else
     ME_LVL_NS::MeScratch *S = &sh->scratch[0];
+    S->ip = &sh->interp[0];
     for (int lr = 0; lr < ME_LVL_ROWS; lr++) {
         int row = (int) blockIdx.x * ME_LVL_ROWS + lr;
         if (row >= A.nrows) continue;

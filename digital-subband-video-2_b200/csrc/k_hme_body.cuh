@@ -740,10 +740,15 @@ me_qpsad_multi(const uint8_t *a, int as, const uint8_t *tmph, int nv, const sign
     }
 }
 
-struct MeScratch {
+/* scratch of one sub-pel measurement (half-pel image and its staging) */
+struct MeInterp {
     uint8_t tmph[(2 + HP_STRIDE) * (2 + HP_STRIDE)];
     uint8_t win[ME_WIN * ME_WIN + 16];
     int16_t hbuf[(SP_DIM + 3) * SP_DIM + 4];
+};
+
+struct MeScratch {
+    MeInterp *ip; /* NULL where no sub-pel measurement can happen (the prepass) */
     int hist[16];
     /* full-pel metric memo of the current block: position -> raw metric */
     short memo_x[ME_MEMO], memo_y[ME_MEMO];
@@ -781,7 +786,7 @@ me_subpel_measure(const MeArgs &A, MeScratch *S, MeSubpel *M, int fpelx, int fpe
     }
     xx = bx + ((bw >> 1) - ((SP_SZ + 1) / 2));
     yy = by + ((bh >> 1) - ((SP_SZ + 1) / 2));
-    me_interp(S->tmph, S->win, S->hbuf, rp.data + (yy + fpely - 1) * rp.stride + xx + fpelx - 1, rp.stride);
+    me_interp(S->ip->tmph, S->ip->win, S->ip->hbuf, rp.data + (yy + fpely - 1) * rp.stride + xx + fpelx - 1, rp.stride);
 
     pri[0] = 0; pri[1] = -1;
     sec[0] = -1; sec[1] = 0;
@@ -825,7 +830,7 @@ me_subpel_measure(const MeArgs &A, MeScratch *S, MeSubpel *M, int fpelx, int fpe
         S->n_evals += 4;     /* the four neighbour SSEs that order the search */
         S->n_subpel += nv;
     }
-    me_qpsad_multi(sp.data + yy * sp.stride + xx, sp.stride, S->tmph, nv, M->tx, M->ty, psy, M->sc);
+    me_qpsad_multi(sp.data + yy * sp.stride + xx, sp.stride, S->ip->tmph, nv, M->tx, M->ty, psy, M->sc);
 }
 
 /* The reference walks the offsets in order and keeps a strictly better score,
@@ -1369,9 +1374,6 @@ me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j)
     unsigned qi_sub[4] = { 0, 0, 0, 0 }, qi_src[4] = { 0, 0, 0, 0 }, qi_inter[4] = { 0, 0, 0, 0 }, qi_rest[4] = { 0, 0, 0, 0 };
     const int qi_cells = (bw == 16 && bh == 16); /* 8x8 quadrants: 16 cells each */
     unsigned bsub[3] = { 0, 0, 0 }, zsub[3] = { 0, 0, 0 };
-    MeSubpel M[2];
-    int sp_valid[2] = { 0, 0 };
-    M[0].nv = M[1].nv = 0;
     if (level == 0) {
         const int sbw = bw / 2, sbh = bh / 2;
         const int cbw = bw >> A.hs, cbh = bh >> A.vs, ccx = i * (A.y_w >> A.hs), ccy = j * (A.y_h >> A.vs);
@@ -1441,18 +1443,8 @@ me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j)
             me_yuv_max_sub(zsub, A.src, A.ref, bx, by, bx, by, bw, bh, ccx, ccy, ccx, ccy, cbw, cbh, psy);
             s_valid |= ME_SV_ZSUB;
         }
-            if (A.effort >= 4) {
-            /* the first sub-pel pass of the reference is always around (lax, lay);
-             * the second one around the full-pel winner */
-            if (!me_invalid_block(rp.w, rp.h, bx + lax, by + lay, bw, bh, 4)) {
-                me_subpel_measure(A, S, &M[0], lax, lay, bx, by, bw, bh, psy);
-                sp_valid[0] = 1;
-            }
-            if ((sx != lax || sy != lay) && !me_invalid_block(rp.w, rp.h, bx + sx, by + sy, bw, bh, 4)) {
-                me_subpel_measure(A, S, &M[1], sx, sy, bx, by, bw, bh, psy);
-                sp_valid[1] = 1;
-            }
-        }
+            /* the sub-pel measurements around (lax, lay) and around S are taken by k_me_subpel,
+         * one warp per measurement, once this kernel has written (lax, lay) and S */
     }
     ME_SYNC();
     if (ME_LANE == 0) {
@@ -1486,15 +1478,8 @@ me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j)
         P->qi_cells = qi_cells;
         P->utex = utex;
         P->vtex = vtex;
-        for (int z = 0; z < 2; z++) {
-            P->sp_valid[z] = sp_valid[z];
-            P->sp_nv[z] = M[z].nv;
-            for (int k = 0; k < M[z].nv; k++) {
-                P->sp_tx[z][k] = M[z].tx[k];
-                P->sp_ty[z][k] = M[z].ty[k];
-                P->sp_sc[z][k] = M[z].sc[k];
-            }
-        }
+        P->sp_valid[0] = P->sp_valid[1] = 0; /* set by k_me_subpel */
+        P->sp_nv[0] = P->sp_nv[1] = 0;
         P->var_src = var_src;
         P->avg_src = avg_src;
         P->motion_bias = motion_bias;
@@ -1516,6 +1501,43 @@ me_prepass_block(const MeArgs &A, MeScratch *S, int i, int j)
         P->mx[k] = S->memo_x[k];
         P->my[k] = S->memo_y[k];
         P->mv[k] = S->memo_v[k];
+    }
+    ME_SYNC();
+}
+
+/* One sub-pel measurement of the level-0 prepass record of block (i, j): slot 0 around
+ * the parent average (the reference's first pass, always taken), slot 1 around the
+ * speculated winner S when that is another position (its second pass). */
+DSVCU_DEV void
+me_subpel_task(const MeArgs &A, MeScratch *S, int i, int j, int slot)
+{
+    const MePlane &sp = A.src[0], &rp = A.ref[0];
+    MePre *P = A.pre + i + j * A.nxb;
+    const int bx = i * A.y_w, by = j * A.y_h;
+    if (bx >= sp.w || by >= sp.h) return;
+    const int bw = min(sp.w - bx, A.y_w), bh = min(sp.h - by, A.y_h);
+    const int lax = P->lax, lay = P->lay, sx = P->sx, sy = P->sy;
+    const int fx = slot ? sx : lax, fy = slot ? sy : lay;
+    MePsy psy;
+    MeSubpel M;
+    if (slot && sx == lax && sy == lay) return;
+    if (me_invalid_block(rp.w, rp.h, bx + fx, by + fy, bw, bh, 4)) return;
+    psy.err_w = P->psy_pack & 255;
+    psy.tex_w = (P->psy_pack >> 8) & 255;
+    psy.avg_w = (P->psy_pack >> 16) & 255;
+    if (ME_LANE == 0) S->n_evals = S->n_subpel = 0;
+    ME_SYNC();
+    me_subpel_measure(A, S, &M, fx, fy, bx, by, bw, bh, psy);
+    if (ME_LANE == 0) {
+        atomicAdd(&A.acc[6], S->n_evals);
+        atomicAdd(&A.acc[7], S->n_subpel);
+        P->sp_nv[slot] = M.nv;
+        for (int k = 0; k < M.nv; k++) {
+            P->sp_tx[slot][k] = M.tx[k];
+            P->sp_ty[slot][k] = M.ty[k];
+            P->sp_sc[slot][k] = M.sc[k];
+        }
+        P->sp_valid[slot] = 1;
     }
     ME_SYNC();
 }
