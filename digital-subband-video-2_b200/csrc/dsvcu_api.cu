@@ -1651,13 +1651,17 @@ pyramid_run(dsvcu_ctx *c, dsvcu_pyramid *p, dsvcu_frame *base, int extend_base)
         A.lv[i].w = p->f[i]->p[0].w;
         A.lv[i].h = p->f[i]->p[0].h;
     }
-    if (A.levels > 0) {
-        tiles = ((base->p[0].w + PYR_TILE - 1) / PYR_TILE) * ((base->p[0].h + PYR_TILE - 1) / PYR_TILE);
-        DSVCU_LAUNCH(k_pyr_interior, tiles, 256, 0, c->stream, A);
+    tiles = A.levels > 0 ? ((base->p[0].w + PYR_TILE - 1) / PYR_TILE) * ((base->p[0].h + PYR_TILE - 1) / PYR_TILE) : 0;
+    A.ntiles = tiles;
+    if (tiles > 0 || A.nbase > 0) {
+        /* tiles of the base picture, then (when asked to) 16 CTAs for the base picture's border */
+        DSVCU_LAUNCH(k_pyr_interior, tiles + (A.nbase > 0 ? 16 : 0), 256, 0, c->stream, A);
         CK_LAUNCH(c);
     }
-    DSVCU_LAUNCH(k_pyr_borders, 1, PYR_BORDER_THREADS, 0, c->stream, A);
-    CK_LAUNCH(c);
+    if (A.levels > 0) {
+        DSVCU_LAUNCH(k_pyr_borders, 1, PYR_BORDER_THREADS, 0, c->stream, A);
+        CK_LAUNCH(c);
+    }
     return 0;
 }
 

@@ -39,6 +39,26 @@ fr_strip(const uint8_t *p, int d, int n, int g)
     return rem ? sum / rem : 0;
 }
 
+/* `n` copies of byte v at p (n = 32 or 4 here), with the widest stores the address allows:
+ * planes start 16-byte aligned and strides are multiples of 16, so the left border and
+ * every 4-column group are aligned; the right border is when the width is */
+DSVCU_DEV void
+fr_fill(uint8_t *p, int v, int n)
+{
+    const uint32_t w4 = (uint32_t) v * 0x01010101u;
+    const uintptr_t a = (uintptr_t) p;
+    if (n == FR_BORDER && (a & 15) == 0) {
+        uint4 q;
+        q.x = q.y = q.z = q.w = w4;
+        ((uint4 *) p)[0] = q;
+        ((uint4 *) p)[1] = q;
+    } else if ((a & 3) == 0 && (n & 3) == 0) {
+        for (int i = 0; i < n / 4; i++) ((uint32_t *) p)[i] = w4;
+    } else {
+        for (int i = 0; i < n; i++) p[i] = (uint8_t) v;
+    }
+}
+
 /* border of one plane; work items: h rows (left+right), ceil(w/4) column groups
  * (top+bottom), 4 corners; item k of `total` is done by caller-chosen threads */
 DSVCU_DEV void
@@ -51,22 +71,16 @@ fr_extend_item(const ExtPlane &P, int k)
         int l = fr_strip(P.data, s, h, j / 4);
         int r = fr_strip(P.data + (w - 1), s, h, j / 4);
         uint8_t *line = P.data + (size_t) j * s;
-        for (int i = 0; i < FR_BORDER; i++) {
-            line[i - FR_BORDER] = (uint8_t) l;
-            line[w + i] = (uint8_t) r;
-        }
+        fr_fill(line - FR_BORDER, l, FR_BORDER);
+        fr_fill(line + w, r, FR_BORDER);
     } else if (k < h + ngc) {
         int g = k - h;
         int t = fr_strip(P.data, 1, w, g);
         int b = fr_strip(P.data + (size_t) (h - 1) * s, 1, w, g);
         int x0 = g * 4, x1 = min(w, x0 + 4);
         for (int j = 0; j < FR_BORDER; j++) {
-            uint8_t *top = P.data - (size_t) (j + 1) * s;
-            uint8_t *bot = P.data + (size_t) (h + j) * s;
-            for (int x = x0; x < x1; x++) {
-                top[x] = (uint8_t) t;
-                bot[x] = (uint8_t) b;
-            }
+            fr_fill(P.data - (size_t) (j + 1) * s + x0, t, x1 - x0);
+            fr_fill(P.data + (size_t) (h + j) * s + x0, b, x1 - x0);
         }
     } else {
         /* corners average the two adjacent strip ends (frame.c:377-380);
@@ -88,10 +102,7 @@ fr_extend_item(const ExtPlane &P, int k)
             v = (bs1 + rs1 + 1) >> 1; cx = w; cy = h;
         }
         for (int j = 0; j < FR_BORDER; j++) {
-            uint8_t *o = P.data + (ptrdiff_t) (cy + j) * s + cx;
-            for (int i = 0; i < FR_BORDER; i++) {
-                o[i] = (uint8_t) v;
-            }
+            fr_fill(P.data + (ptrdiff_t) (cy + j) * s + cx, v, FR_BORDER);
         }
     }
 }
@@ -149,6 +160,7 @@ k_ds2x(uint8_t *dst, int ds, int dw, int dh, const uint8_t *src, int ss)
 struct PyrArgs {
     ExtPlane base[3]; /* [0] = luma = pyramid level 0 */
     int nbase;        /* planes of the base picture to extend first (0: already extended) */
+    int ntiles;       /* k_pyr_interior: CTAs [0, ntiles) are tiles, the rest extend the base planes */
     int levels;
     ExtPlane lv[PYR_MAXLVL + 1]; /* [1..levels] */
 };
@@ -173,6 +185,16 @@ k_pyr_interior(PyrArgs A)
     uint8_t (*t)[PYR_TILE * PYR_TILE] = (uint8_t (*)[PYR_TILE * PYR_TILE]) tw;
     const ExtPlane &B = A.base[0];
     const int tiles_x = (B.w + PYR_TILE - 1) / PYR_TILE;
+    if ((int) blockIdx.x >= A.ntiles) {
+        /* the CTAs behind the tiles: border of the base picture's planes (reads interior
+         * pixels, writes border pixels: independent of the tiles) */
+        const int e = (int) blockIdx.x - A.ntiles, ne = (int) gridDim.x - A.ntiles;
+        for (int p = 0; p < A.nbase; p++) {
+            const int total = fr_extend_items(A.base[p]);
+            for (int k = e * DSVCU_NTH + DSVCU_TID; k < total; k += ne * DSVCU_NTH) fr_extend_item(A.base[p], k);
+        }
+        return;
+    }
     const int tx = (int) blockIdx.x % tiles_x, ty = (int) blockIdx.x / tiles_x;
     const int x0 = tx * PYR_TILE, y0 = ty * PYR_TILE;
     /* level 0 tile, word-wise (tile rows are 4-byte aligned: stride and the 32-px border are multiples of 4) */
@@ -213,11 +235,7 @@ k_pyr_interior(PyrArgs A)
 DSVCU_KERNEL void __launch_bounds__(PYR_BORDER_THREADS)
 k_pyr_borders(PyrArgs A)
 {
-    for (int p = 0; p < A.nbase; p++) {
-        const int total = fr_extend_items(A.base[p]);
-        PAR_FOR(k, total) fr_extend_item(A.base[p], k);
-    }
-    DSVCU_SYNC();
+    /* (the base picture's border was written by the extra CTAs of k_pyr_interior) */
     for (int l = 1; l <= A.levels; l++) {
         const ExtPlane &S = (l == 1) ? A.base[0] : A.lv[l - 1];
         const ExtPlane &D = A.lv[l];

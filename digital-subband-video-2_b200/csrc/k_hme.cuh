@@ -36,7 +36,9 @@
 #define ME_MIN_CTAS 4
 #endif
 /* the prepass runs four blocks per warp (groups of ME_PRE_G lanes, k_hme_body.cuh) */
+#ifndef ME_PRE_G
 #define ME_PRE_G 8
+#endif
 #ifndef ME_PRE_THREADS
 #define ME_PRE_THREADS 128
 #endif
