@@ -1514,7 +1514,8 @@ dsvcu_add_res(dsvcu_ctx *c, const dsvcu_fmeta *fm, int q, dsvcu_frame *resd, dsv
     BmcArgs A;
     bmc_fill(&A, c, fm, NULL, pred, resd, NULL, 0);
     if (!DIAG_SKIP(8))
-    DSVCU_LAUNCH(k_reconstruct, dim3(fm->nblocks_h * fm->nblocks_v, 3, 1), BMC_THREADS, 0, c->stream, A);
+    DSVCU_LAUNCH(k_reconstruct, dim3(grid_for(fm->nblocks_h * fm->nblocks_v * fm->blk_h * (fm->blk_w / 16 > 0 ? fm->blk_w / 16 : 1), REC_THREADS), 3, 1),
+                 REC_THREADS, 0, c->stream, A);
     CK_LAUNCH(c);
     return loop_filters(c, fm, q, resd, do_filter);
 }

@@ -236,31 +236,62 @@ k_predict(BmcArgs A)
     }
 }
 
-/* encoder-side reconstruct: res = pred (+) res, in place (dsv_add_res, bmc.c:1072-1090) */
-DSVCU_KERNEL void __launch_bounds__(BMC_THREADS)
-k_reconstruct(BmcArgs A)
+/* encoder-side reconstruct: res = pred (+) res, in place (dsv_add_res, bmc.c:1072-1090).
+ * Pure per-pixel arithmetic steered by the block's flags: one thread per 16-byte segment of a
+ * block row (8 / 4 bytes where a chroma block is narrower), 16-byte loads and stores -- planes
+ * start 16-byte aligned, strides are multiples of 16, block widths powers of two.  Like the
+ * reference it works on whole blocks, i.e. also on the border columns / rows the block grid
+ * covers past the picture edge. */
+#define REC_THREADS 256
+
+DSVCU_HD uint32_t
+bmc_rec4(uint32_t p4, uint32_t s4, int lossless, int plain)
 {
-    const int c = (int) blockIdx.y;
-    const BmcPlane P = A.pl[c];
-    const int bi = (int) blockIdx.x % A.nbh, bj = (int) blockIdx.x / A.nbh;
-    const dsvcu_mv mv = A.mvs[bi + bj * A.nbh];
-    const int bw = A.blk_w >> P.sh, bh = A.blk_h >> P.sv;
-    const int x = bi * bw, y = bj * bh;
-    const int intra = mv.flags & MVF_INTRA, skip = mv.flags & MVF_SKIP, eprm = mv.flags & MVF_EPRM;
-    const int plain = !eprm || (!intra && skip);
-    PAR_FOR(k, bw * bh) {
-        int r = k / bw, q = k - r * bw;
-        int p = P.pred[(y + r) * P.pred_stride + x + q];
-        uint8_t *rp = P.res + (y + r) * P.res_stride + x + q;
-        int s = *rp, o;
-        if (A.lossless) {
+    uint32_t o4 = 0;
+    for (int k = 0; k < 4; k++) {
+        const int p = (int) ((p4 >> (8 * k)) & 255u), s = (int) ((s4 >> (8 * k)) & 255u);
+        int o;
+        if (lossless) {
             o = (p + s - 128) & 0xff;
         } else if (plain) {
             o = bmc_u8(p + s - 128);
         } else {
             o = bmc_u8(p + (s - 128) * 2);
         }
-        *rp = (uint8_t) o;
+        o4 |= (uint32_t) o << (8 * k);
+    }
+    return o4;
+}
+
+DSVCU_KERNEL void __launch_bounds__(REC_THREADS)
+k_reconstruct(BmcArgs A)
+{
+    const int c = (int) blockIdx.y;
+    const BmcPlane P = A.pl[c];
+    const int bw = A.blk_w >> P.sh, bh = A.blk_h >> P.sv;
+    const int seg = bw >= 16 ? 16 : bw;            /* bytes per work item: 16, 8 or 4 */
+    const int segs_row = (A.nbh * bw) / seg, rows = A.nbv * bh;
+    const int total = segs_row * rows;
+    for (int k = (int) blockIdx.x * DSVCU_NTH + DSVCU_TID; k < total; k += (int) gridDim.x * DSVCU_NTH) {
+        const int row = k / segs_row, x = (k - row * segs_row) * seg;
+        const dsvcu_mv *mvp = A.mvs + (x / bw) + (row / bh) * A.nbh;
+        const unsigned flags = mvp->flags;
+        const int intra = flags & MVF_INTRA, skip = flags & MVF_SKIP, eprm = flags & MVF_EPRM;
+        const int plain = !eprm || (!intra && skip);
+        const uint8_t *pp = P.pred + (ptrdiff_t) row * P.pred_stride + x;
+        uint8_t *rp = P.res + (ptrdiff_t) row * P.res_stride + x;
+        if (seg == 16) {
+            uint4 p = *(const uint4 *) pp, s = *(const uint4 *) rp, o;
+            o.x = bmc_rec4(p.x, s.x, A.lossless, plain);
+            o.y = bmc_rec4(p.y, s.y, A.lossless, plain);
+            o.z = bmc_rec4(p.z, s.z, A.lossless, plain);
+            o.w = bmc_rec4(p.w, s.w, A.lossless, plain);
+            *(uint4 *) rp = o;
+        } else {
+            for (int i = 0; i < seg; i += 4) {
+                *(uint32_t *) (rp + i) = bmc_rec4(*(const uint32_t *) (pp + i), *(const uint32_t *) (rp + i), A.lossless, plain);
+            }
+        }
     }
 }
 

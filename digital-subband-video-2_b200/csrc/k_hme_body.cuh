@@ -630,10 +630,10 @@ me_calc_eprm(const uint8_t *src, int ss, const uint8_t *mvr, int rs, int avg_src
 DSVCU_DEV void
 me_interp(uint8_t *tmph, uint8_t *win, int16_t *hbuf, const uint8_t *r, int rs)
 {
-    /* stage the full-pel window once */
-    for (int k = ME_LANE; k < ME_WIN * ME_WIN; k += ME_NL) {
-        int j = k / ME_WIN, i = k - j * ME_WIN;
-        win[k] = r[(j - 1) * rs + i - 1];
+    /* stage the full-pel window once: ME_WIN = 20 bytes per row = five (unaligned) words */
+    for (int k = ME_LANE; k < ME_WIN * (ME_WIN / 4); k += ME_NL) {
+        int j = k / (ME_WIN / 4), i = (k - j * (ME_WIN / 4)) * 4;
+        *(uint32_t *) (win + j * ME_WIN + i) = me_ld4(r + (j - 1) * rs + i - 1);
     }
     ME_SYNC();
     /* horizontal half-pel sums for rows -1 .. SP_DIM+1 */
@@ -666,6 +666,18 @@ me_qsample(const uint8_t *tmph, int qx, int qy)
     const uint8_t *h0 = tmph + (qy >> 1) * HP_STRIDE + (qx >> 1);
     int ox = qx & 1, oy = (qy & 1) * HP_STRIDE;
     return (h0[0] + h0[ox] + h0[oy] + h0[ox + oy] + 2) >> 2;
+}
+
+/* me_qsample at a position whose parity bits are known: ox in {0, 1}, oy in {0, HP_STRIDE}.
+ * Both even = the half-pel sample itself ((4a + 2) >> 2 == a), one odd = the average of two
+ * ((2a + 2b + 2) >> 2 == (a + b + 1) >> 1): one, two or four loads instead of always four. */
+DSVCU_DEV int
+me_qs(const uint8_t *h0, int ox, int oy)
+{
+    if (!(ox | oy)) return h0[0];
+    if (!oy) return (h0[0] + h0[1] + 1) >> 1;
+    if (!ox) return (h0[0] + h0[oy] + 1) >> 1;
+    return (h0[0] + h0[1] + h0[oy] + h0[1 + oy] + 2) >> 2;
 }
 
 /* psy metric of the 16 x 16 source window against the quarter-pel image at
@@ -724,13 +736,15 @@ me_qpsad_multi(const uint8_t *a, int as, const uint8_t *tmph, int nv, const sign
 #endif
         for (int v = 0; v < ME_MAXSP; v++) {
             if (v < nv) {
-                int qx = 4 + tx[v] + 4 * x, qy = 4 + ty[v] + 4 * y;
-                uint32_t B0 = (uint32_t) me_qsample(tmph, qx, qy) | ((uint32_t) me_qsample(tmph, qx + 4, qy) << 8) |
-                              ((uint32_t) me_qsample(tmph, qx, qy + 4) << 16) |
-                              ((uint32_t) me_qsample(tmph, qx + 4, qy + 4) << 24);
-                uint32_t B1 = (uint32_t) me_qsample(tmph, qx + 8, qy) | ((uint32_t) me_qsample(tmph, qx + 12, qy) << 8) |
-                              ((uint32_t) me_qsample(tmph, qx + 8, qy + 4) << 16) |
-                              ((uint32_t) me_qsample(tmph, qx + 12, qy + 4) << 24);
+                /* the eight samples of this work item: quarter-pel positions 4 apart = half-pel
+                 * image positions 2 apart, all with the offset's parity (uniform over the lanes) */
+                const int qx = 4 + tx[v] + 4 * x, qy = 4 + ty[v] + 4 * y;
+                const int ox = qx & 1, oy = (qy & 1) * HP_STRIDE;
+                const uint8_t *h0 = tmph + (qy >> 1) * HP_STRIDE + (qx >> 1), *h1 = h0 + 2 * HP_STRIDE;
+                uint32_t B0 = (uint32_t) me_qs(h0, ox, oy) | ((uint32_t) me_qs(h0 + 2, ox, oy) << 8) |
+                              ((uint32_t) me_qs(h1, ox, oy) << 16) | ((uint32_t) me_qs(h1 + 2, ox, oy) << 24);
+                uint32_t B1 = (uint32_t) me_qs(h0 + 4, ox, oy) | ((uint32_t) me_qs(h0 + 6, ox, oy) << 8) |
+                              ((uint32_t) me_qs(h1 + 4, ox, oy) << 16) | ((uint32_t) me_qs(h1 + 6, ox, oy) << 24);
                 acc[v] += me_cell4_pre(A0, s00, ta0, B0, psy) + me_cell4_pre(A1, s01, ta1, B1, psy);
             }
         }
@@ -741,7 +755,7 @@ me_qpsad_multi(const uint8_t *a, int as, const uint8_t *tmph, int nv, const sign
 }
 
 /* scratch of one sub-pel measurement (half-pel image and its staging) */
-struct MeInterp {
+struct __align__(16) MeInterp {
     uint8_t tmph[(2 + HP_STRIDE) * (2 + HP_STRIDE)];
     uint8_t win[ME_WIN * ME_WIN + 16];
     int16_t hbuf[(SP_DIM + 3) * SP_DIM + 4];
