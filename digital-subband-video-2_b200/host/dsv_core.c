@@ -283,12 +283,43 @@ dsv_yuv_write(FILE *out, int fno, DSV_PLANE *p)
     return dsv_yuv_write_seq(out, p);
 }
 
+/* packed UYVY 4:2:2 (2 bytes per pixel: U Y V Y) -> planar Y, U, V (reference dsv.c:142-176) */
+static int
+read_uyvy(FILE *in, uint8_t *o, int w, int h)
+{
+    uint8_t *yp = o, *up = o + (size_t) w * h, *vp = up + (size_t) (w / 2) * h;
+    size_t row = (size_t) w * 2;
+    uint8_t *line = malloc(row ? row : 1);
+    int i, j, ok = 0;
+    if (!line) {
+        return -1;
+    }
+    for (j = 0; j < h; j++) {
+        const uint8_t *t = line;
+        if (fread(line, 1, row, in) != row) {
+            ok = -1;
+            break;
+        }
+        for (i = 0; i < w / 2; i++, t += 4) {
+            *up++ = t[0];
+            *yp++ = t[1];
+            *vp++ = t[2];
+            *yp++ = t[3];
+        }
+    }
+    free(line);
+    return ok;
+}
+
 int
 dsv_yuv_read_seq(FILE *in, uint8_t *o, int w, int h, int subsamp)
 {
     size_t n = yuv_frame_bytes(w, h, subsamp);
     if (!in) {
         return -1;
+    }
+    if (subsamp == DSV_SUBSAMP_UYVY) {
+        return read_uyvy(in, o, w, h);
     }
     if (fread(o, 1, n, in) != n) {
         return -1;

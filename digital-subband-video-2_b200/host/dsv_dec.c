@@ -355,6 +355,97 @@ dsv_get_metadata(DSV_DECODER *d)
         }                                                      \
     } while (0)
 
+/* ---- debug overlay on the OUTPUT copy of a picture (the reference picture stays clean),
+ * reference dsv_decoder.c:243-350: block grid, markers for stable / skipped and
+ * "maintain" blocks, motion vectors as lines, intra sub-block dots.  Pure host drawing. */
+#define OVL_SHADE 255
+
+static void
+ovl_put(DSV_PLANE *lp, int x, int y, int v)
+{
+    if (x >= 0 && y >= 0 && x < lp->w && y < lp->h) {
+        lp->data[(size_t) y * lp->stride + x] = (uint8_t) v;
+    }
+}
+
+/* Bresenham line from the block centre along the (quarter-pel valued) vector */
+static void
+ovl_vector(DSV_PLANE *lp, int x0, int y0, int vx, int vy, int bw, int bh)
+{
+    int x1, y1, dx, dy, sx, sy, err;
+    x0 += bw / 2;
+    y0 += bh / 2;
+    x1 = x0 + vx;
+    y1 = y0 + vy;
+    dx = abs(x1 - x0);
+    dy = abs(y1 - y0);
+    sx = x0 < x1 ? 1 : -1;
+    sy = y0 < y1 ? 1 : -1;
+    err = dx - dy;
+    ovl_put(lp, x0, y0, OVL_SHADE);
+    while (x0 != x1 || y0 != y1) {
+        int e2;
+        ovl_put(lp, x0, y0, OVL_SHADE);
+        e2 = 2 * err;
+        if (e2 > -dy) {
+            err -= dy;
+            x0 += sx;
+        }
+        if (e2 < dx) {
+            err += dx;
+            y0 += sy;
+        }
+    }
+}
+
+static void
+overlay_info(DSV_FRAME *f, const DSV_PARAMS *p, const uint8_t *blockdata, const DSV_MV *mvs, int mode)
+{
+    DSV_PLANE *lp = &f->planes[0];
+    const int bw = p->blk_w, bh = p->blk_h;
+    int i, j, k;
+    for (j = 0; j < p->nblocks_v; j++) {
+        const int y = j * bh;
+        /* the reference fills the whole line including the stride padding; only the
+         * visible part exists in a tightly packed output frame */
+        memset(lp->data + (size_t) y * lp->stride, OVL_SHADE, (size_t) MIN(lp->stride, lp->w));
+        for (i = 0; i < p->nblocks_h; i++) {
+            const int x = i * bw, idx = i + j * p->nblocks_h;
+            const DSV_MV *mv = mvs ? &mvs[idx] : NULL;
+            for (k = y; k < y + bh && k < lp->h; k++) {
+                ovl_put(lp, x, k, OVL_SHADE);
+            }
+            if (mode & DSV_DRAW_STABHQ) {
+                const int a = x + bw / 2, b = y + bh / 2;
+                if (blockdata[idx] & (DSV_IS_SKIP | DSV_IS_STABLE)) {
+                    for (k = -bw / 4; k <= bw / 4; k++) {
+                        ovl_put(lp, a + k, b, (k & 1) * 255);
+                    }
+                }
+                if (blockdata[idx] & DSV_IS_MAINTAIN) {
+                    for (k = -bh / 4; k <= bh / 4; k++) {
+                        ovl_put(lp, a, b + k, (k & 1) * 255);
+                    }
+                }
+            }
+            if (mv && (mode & DSV_DRAW_MOVECS) && !(blockdata[idx] & DSV_IS_SKIP)) {
+                ovl_vector(lp, x, y, mv->u.mv.x, mv->u.mv.y, bw, bh);
+            }
+            if (mv && (mode & DSV_DRAW_IBLOCK)) {
+                static const int qx[4] = { 1, 3, 1, 3 }, qy[4] = { 1, 1, 3, 3 };
+                static const int bit[4] = { DSV_MASK_INTRA00, DSV_MASK_INTRA01, DSV_MASK_INTRA10, DSV_MASK_INTRA11 };
+                for (k = 0; k < 4; k++) {
+                    if (mv->submask & bit[k]) {
+                        /* unlike the other marks the reference writes these unchecked; blocks that
+                         * overhang the picture are clipped here */
+                        ovl_put(lp, x + bw * qx[k] / 4, y + bh * qy[k] / 4, OVL_SHADE);
+                    }
+                }
+            }
+        }
+    }
+}
+
 static int
 decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FRAME **out, DSV_FNUM *fn)
 {
@@ -487,15 +578,15 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
     for (i = 0; i < 3; i++) {
         GPU(dsvcu_frame_download(s->ctx, dst, i, host->planes[i].data, host->planes[i].stride));
     }
-    if (!(tls_async && tls_direct_out)) {
-        GPU(dsvcu_sync(s->ctx));
+    if (!(tls_async && tls_direct_out) || d->draw_info) {
+        GPU(dsvcu_sync(s->ctx)); /* (the overlay below is drawn into the finished host copy) */
     }
     if (is_ref) {
         s->cur ^= 1;
         s->have_ref = 1;
     }
     if (d->draw_info) {
-        DSV_WARNING(("draw_info overlays are not implemented in the B200 build"));
+        overlay_info(host, p, s->blockdata, isP ? s->mvs : NULL, d->draw_info);
     }
     *out = host;
     return DSV_DEC_OK;

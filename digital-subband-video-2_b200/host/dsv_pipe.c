@@ -131,8 +131,8 @@ pct_or_auto(int pct)
 
 /* option table -> encoder configuration, as the CLI does it
  * (reference dsv_main.c:573-723) */
-static void
-configure_encoder(DSV_ENCODER *enc, const dsv_enc_opts *o)
+void
+dsv_enc_configure(DSV_ENCODER *enc, const dsv_enc_opts *o)
 {
     DSV_META md;
     int fps, bps;
@@ -272,7 +272,7 @@ dsv_encode_buffer(const dsv_enc_opts *o, const uint8_t *yuv, int nframes, int ex
     BYTES b;
     int r;
     memset(&b, 0, sizeof(b));
-    configure_encoder(&enc, o);
+    dsv_enc_configure(&enc, o);
     r = run_encoder(&enc, o, yuv, nframes, !o->noeos || (exhausted && nframes > 0), &b);
     dsv_enc_free(&enc);
     if (r) {
@@ -447,7 +447,7 @@ encode_chunk(WORKER *w, void *arg, int k)
     /* a fresh encoder per chunk (frame numbers, rate control and block
      * statistics restart, parallel_encode_yuv.sh:34-41), but the device
      * buffers of the worker's previous encoder are handed over */
-    configure_encoder(&enc, j->o);
+    dsv_enc_configure(&enc, j->o);
     if (w->have_enc) {
         dsv_enc_recycle(&w->enc_keep, &enc);
         dsv_enc_free(&w->enc_keep);
@@ -757,6 +757,17 @@ dsv_pool_decode(dsv_pool *pl, const uint8_t *dsv, size_t len, uint8_t *dst, size
         return -1;
     }
     return pool_decode(pl, dsv, len, dst, dst_cap, 0, NULL, &n, nframes, meta);
+}
+
+/* the same into pinned memory allocated by the call (dsv_pinned_free) */
+int
+dsv_pool_decode_alloc(dsv_pool *pl, const uint8_t *dsv, size_t len, uint8_t **yuv, size_t *yuv_len, int *nframes,
+                      DSV_META *meta)
+{
+    if (!pl || !yuv) {
+        return -1;
+    }
+    return pool_decode(pl, dsv, len, NULL, 0, 1, yuv, yuv_len, nframes, meta);
 }
 
 int

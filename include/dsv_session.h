@@ -17,6 +17,7 @@
 #include <stddef.h>
 #include <stdint.h>
 #include "dsv.h"
+#include "dsv_encoder.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -41,6 +42,9 @@ typedef struct {
 } dsv_enc_opts;
 
 void dsv_enc_opts_default(dsv_enc_opts *o, int w, int h, int fmt, int fps_num, int fps_den);
+/* dsv_enc_init + the CLI's way of turning the option table into a DSV_ENCODER
+ * configuration (dsv_main.c:573-723); dsv_enc_start / dsv_enc then work as usual */
+void dsv_enc_configure(DSV_ENCODER *enc, const dsv_enc_opts *o);
 
 /* the CUDA device used by encoder / decoder instances created by the calling
  * thread from now on (default: $DSV_CUDA_DEVICE or 0) */
@@ -77,6 +81,10 @@ int dsv_pool_encode(dsv_pool *pool, const dsv_enc_opts *o, const uint8_t *yuv, i
 /* frames are written to caller memory `dst` (host, pinned or DEVICE) */
 int dsv_pool_decode(dsv_pool *pool, const uint8_t *dsv, size_t len, uint8_t *dst, size_t dst_cap, int *nframes,
                     DSV_META *meta);
+
+/* the same with the frames in pinned memory allocated by the call (dsv_pinned_free) */
+int dsv_pool_decode_alloc(dsv_pool *pool, const uint8_t *dsv, size_t len, uint8_t **yuv, size_t *yuv_len, int *nframes,
+                          DSV_META *meta);
 
 /* `dsv2 d`: decodes a stream into packed frames.  *yuv is malloc'ed (or pinned
  * when `pinned` != 0: free with dsv_pinned_free). */
