@@ -475,6 +475,52 @@ def cpu_baseline_sample():
             "decode_value": round(GOP / dd, 3)}
 
 
+def single_stream_configs(P, lib):
+    """BASELINE configs 1-4 (frame-serial: one encoder / decoder instance, they cannot be sharded
+    bit-exactly), bounded lengths: our single-instance frames/s through the public buffer API from
+    HOST memory, next to the single-core reference on the same clip, with byte parity."""
+    import util
+    import ops
+    out = []
+    cases = [("1: CIF 352x288 4:2:0, -qp=60 -gop=48", 352, 288, 60, "420", 30, ["-qp=60", "-gop=48"], dict(qp=60, gop=48)),
+             ("2: 1280x720 4:2:0 50 fps, -gop=250 -effort=10", 1280, 720, 50, "420", 50, ["-gop=250", "-effort=10"],
+              dict(gop=250, effort=10)),
+             ("3: 1920x1080 4:2:0 CRF, -qp=60 -gop=48", 1920, 1080, 48, "420", 30, ["-qp=60", "-gop=48"], dict(qp=60, gop=48)),
+             ("4: 1920x1080 4:4:4 lossless, -qp=100", 1920, 1080, 8, "444", 30, ["-qp=100"], dict(qp=100))]
+    for name, w, h, n, fmt, fps, rargs, over in cases:
+        try:
+            y4m = util.clip("bench_cfg%s" % name[0], w, h, n, fmt, fps=fps)
+            _, _, fr = util.read_y4m(y4m)
+            yuv = b"".join(ops.yuv_bytes(f) for f in fr)
+            o = P.enc_opts(w, h, P.SUBSAMP_420 if fmt == "420" else P.SUBSAMP_444, (fps, 1), **over)
+            P.encode_frames(o, yuv[:len(yuv) // n * min(n, 4)], min(n, 4))  # warm-up: contexts, clocks
+            t0 = time.perf_counter()
+            dsv = P.encode_frames(o, yuv, n)
+            te = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            _, nfr, dec = P.decode_frames(dsv)
+            td = time.perf_counter() - t0
+            rout = "/dev/shm/dsv2_bench_cfg%s.dsv" % name[0]
+            t0 = time.perf_counter()
+            r = subprocess.run([REF_BIN, "e", "-y", "-inp=" + y4m, "-out=" + rout, "-y4m=1"] + rargs, stdout=subprocess.DEVNULL,
+                               stderr=subprocess.DEVNULL)
+            tre = time.perf_counter() - t0
+            ryuv = "/dev/shm/dsv2_bench_cfg%s.yuv" % name[0]
+            t0 = time.perf_counter()
+            subprocess.run([REF_BIN, "d", "-y", "-inp=" + rout, "-out=" + ryuv], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            trd = time.perf_counter() - t0
+            ok_e = open(rout, "rb").read() == dsv
+            ok_d = open(ryuv, "rb").read() == dec
+            os.unlink(ryuv)
+            out.append({"config": name, "frames": n, "encode_fps": round(n / te, 2), "decode_fps": round(nfr / td, 2),
+                        "reference_1core_encode_fps": round(n / tre, 2), "reference_1core_decode_fps": round(n / trd, 2),
+                        "encode_speedup": round(tre / te, 1), "decode_speedup": round(trd / td, 1),
+                        "parity": {"encode": ok_e, "decode": ok_d}, "reference_exit": r.returncode})
+        except Exception as e:
+            out.append({"config": name, "error": str(e)})
+    return out
+
+
 def run_own(args):
     import numpy as np
     import torch
@@ -644,7 +690,7 @@ def run_own(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    kern, me, batched = [], None, []
+    kern, me, batched, single = [], None, [], []
     cpu = None
     if world == 1 and not args.no_micro:
         try:
@@ -656,6 +702,11 @@ def run_own(args):
         except Exception as e:
             log("batched microbench failed:", e)
         cpu = cpu_baseline_sample()
+        try:
+            single = single_stream_configs(P, lib) if os.path.exists(REF_BIN) else []
+        except Exception as e:
+            log("single-stream configs failed:", e)
+            single = []
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(1000 * dt / args.steps, 3), "higher_is_better": True,
@@ -707,6 +758,8 @@ def run_own(args):
             best_b = max(batched, key=lambda k: k["frac"])
             line["roofline"]["hbm_family_best"] = {"kernel": best_b["kernel"], "achieved": best_b["achieved_gbs"], "peak": peak,
                                                     "unit": "GB/s", "frac": best_b["frac"]}
+    if single:
+        line["single_stream_configs"] = single
     if cpu is not None:
         line["cpu_baseline"] = cpu
     emit(line)

@@ -1394,12 +1394,13 @@ run_filter_job(dsvcu_ctx *c, FiltJob *J, int nplanes)
         snprintf(g_err, sizeof(g_err), "picture too wide for the filter schedule");
         return -1;
     }
-    if (bands > c->progress_cap) {
+    if (bands + 1 > c->progress_cap) {
         dsvcu_free_dev(c->d_progress);
         c->progress_cap = bands + 64;
         CK(dsvcu_malloc(&c->d_progress, (size_t) c->progress_cap * sizeof(int)));
     }
-    CK(dsvcu_memset_async(c->d_progress, 0, (size_t) bands * sizeof(int), c->stream));
+    CK(dsvcu_memset_async(c->d_progress, 0, (size_t) (bands + 1) * sizeof(int), c->stream));
+    J->ticket = c->d_progress + bands;
     bands = 0;
     for (i = 0; i < nplanes; i++) {
         J->p[i].progress = c->d_progress + bands;
@@ -1779,11 +1780,12 @@ dsvcu_hme(dsvcu_ctx *c, const dsvcu_fmeta *fm, const dsvcu_hme_params *hp, dsvcu
         A.acc = c->d_me + 2;
         rows = (fm->nblocks_v + step - 1) / step;
         A.nrows = rows;
-        if (rows > c->me_prog_cap) {
+        if (rows >= c->me_prog_cap) {
             snprintf(g_err, sizeof(g_err), "motion search: %d block rows exceed the progress table", rows);
             return -1;
         }
         A.progress = c->d_me_prog[lvl];
+        A.ticket = c->d_me_prog[lvl] + c->me_prog_cap - 1; /* last word of the level's (zeroed) progress region */
         A.pre = c->d_pre;
         A.b2sr = (256 * (hp->quant * hp->quant >> 12) * fm->blk_w * fm->blk_h) / (c->width * c->height);
         {

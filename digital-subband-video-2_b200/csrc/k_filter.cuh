@@ -67,6 +67,7 @@ struct FiltArgs {
 struct FiltJob {
     FiltArgs p[3];
     int nplanes;
+    int *ticket; /* zeroed before the launch: CTAs take their logical index from it (see k_filter_skew) */
 };
 
 #ifdef DSVCU_EMU
@@ -833,14 +834,26 @@ DSVCU_KERNEL void __launch_bounds__(FILT_THREADS)
 k_filter_skew(FiltJob J)
 {
     DSVCU_DYN_SMEM(uint8_t, smem);
+    /* A CTA waits for the band above, which belongs to the CTA with the next lower index.  The
+     * logical index is a ticket drawn at entry, not blockIdx: whoever holds ticket k started after
+     * the holders of 0..k-1, so a waiting CTA only ever waits for CTAs that are already running
+     * (or done), whatever order the hardware dispatches blocks in. */
+#ifndef DSVCU_EMU
+    __shared__ int s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(J.ticket, 1);
+    __syncthreads();
+    const int bid = s_ticket;
+#else
+    const int bid = (int) blockIdx.x;
+#endif
     int pl = 0;
-    while (pl + 1 < J.nplanes && (int) blockIdx.x >= J.p[pl + 1].first_cta) pl++;
+    while (pl + 1 < J.nplanes && bid >= J.p[pl + 1].first_cta) pl++;
     const FiltArgs &A = J.p[pl];
     const int ncols = A.ncols, nrows = A.nrows;
     int *done = (int *) (smem + FILT_CELLS * FT_BYTES);
     int *btab = done + FILT_WPC; /* chroma: one word per block; luma/intra: FBlk */
 #ifndef DSVCU_EMU
-    const int cta = (int) blockIdx.x - A.first_cta;
+    const int cta = bid - A.first_cta;
     const int lane = (int) (threadIdx.x & 31), warp = (int) (threadIdx.x >> 5);
     const int grp = lane / FILT_LPC;
     const int nbands = (nrows + FILT_G - 1) / FILT_G;
@@ -938,7 +951,7 @@ k_filter_skew(FiltJob J)
 #else
     (void) done;
     (void) btab;
-    if ((int) blockIdx.x != A.first_cta) return; /* emulation: the plane's first CTA walks it in raster order */
+    if (bid != A.first_cta) return; /* emulation: the plane's first CTA walks it in raster order */
     for (int row = 0; row < nrows; row++) {
         for (int i = 0; i < ncols; i++) {
             if (A.mode == FILT_MODE_CHROMA) {

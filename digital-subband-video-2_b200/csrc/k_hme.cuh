@@ -86,6 +86,7 @@ struct MeArgs {
     const int *gxy; /* global motion from the level above */
     int *acc;       /* [0] nintra [1] ndiff [2] eligible [3] total_err; [6] full-block metric evaluations [7] sub-pel position metrics (all levels) */
     int *progress;
+    int *ticket;       /* zeroed per launch: wavefront CTAs draw their logical index from it */
     int nrows;
     int b2sr;          /* (256 * (q*q >> 12) * blk_w * blk_h) / (width * height), dsv.c:370 */
     struct MePre *pre; /* per-block results of k_me_prepass for this level */
@@ -346,6 +347,7 @@ struct MeLvlShared {
     ME_LVL_NS::MeScratch scratch[ME_LVL_ROWS];
     __align__(16) uint32_t pre_words[ME_LVL_ROWS][ME_PRE_WORDS];
     int sprog[ME_LVL_WARPS];
+    int cta;
 };
 
 DSVCU_KERNEL void __launch_bounds__(ME_LVL_WARPS * 32, ME_LVL_G == 32 ? 2 : 4)
@@ -355,9 +357,14 @@ k_me_level(MeArgs A)
     const int step = 1 << A.level;
     int acc_local[4] = { 0, 0, 0, 0 };
 #ifndef DSVCU_EMU
+    /* CTA k waits for CTA k - 1; k is a ticket drawn at entry, not blockIdx, so a waiting CTA only
+     * waits for CTAs that have already started, whatever the dispatch order */
+    if (threadIdx.x == 0) sh->cta = atomicAdd(A.ticket, 1);
+    __syncthreads();
+    const int cta = sh->cta;
     const int wic = ME_WIC, g = ME_KLANE / ME_LVL_G;   /* warp in CTA, row group in warp */
     const int lr = wic * ME_LVL_RPW + g;                /* row in CTA */
-    const int row = (int) blockIdx.x * ME_LVL_ROWS + lr;
+    const int row = cta * ME_LVL_ROWS + lr;
     const int cols = (A.nxb + step - 1) / step;
     ME_LVL_NS::MeScratch *S = &sh->scratch[lr];
     if ((ME_KLANE % ME_LVL_G) == 0) S->ip = &sh->interp[lr];
@@ -366,9 +373,9 @@ k_me_level(MeArgs A)
     {
         /* the row above the warp's first row: previous warp of the CTA, or the last
          * warp of the previous CTA (its progress word is published globally) */
-        const int wrow0 = (int) blockIdx.x * ME_LVL_ROWS + wic * ME_LVL_RPW;
+        const int wrow0 = cta * ME_LVL_ROWS + wic * ME_LVL_RPW;
         const bool above_global = (wic == 0), pub_global = (wic == ME_LVL_WARPS - 1);
-        volatile const int *above = above_global ? (volatile const int *) (A.progress + (int) blockIdx.x - 1)
+        volatile const int *above = above_global ? (volatile const int *) (A.progress + cta - 1)
                                                  : (volatile const int *) (sh->sprog + wic - 1);
         int seen = (wrow0 == 0) ? 0x7fffffff : 0;
         if (wrow0 < A.nrows) {
@@ -398,7 +405,7 @@ k_me_level(MeArgs A)
                 __syncwarp();
                 if (g == ME_LVL_RPW - 1 && active && (ME_KLANE % ME_LVL_G) == 0) {
                     *(volatile int *) (sh->sprog + wic) = col + 1;
-                    if (pub_global) *(volatile int *) (A.progress + (int) blockIdx.x) = col + 1;
+                    if (pub_global) *(volatile int *) (A.progress + cta) = col + 1;
                 }
             }
         }
