@@ -1469,7 +1469,7 @@ dsvcu_sub_pred(dsvcu_ctx *c, const dsvcu_fmeta *fm, dsvcu_frame *pred, dsvcu_fra
 {
     BmcArgs A;
     bmc_fill(&A, c, fm, ref, pred, resd, NULL, 0);
-    DSVCU_LAUNCH(k_predict, dim3(fm->nblocks_h * fm->nblocks_v, 3, 1), BMC_THREADS, 0, c->stream, A);
+    DSVCU_LAUNCH(k_predict, dim3(fm->nblocks_h * fm->nblocks_v, 1, 1), BMC_THREADS, 0, c->stream, A);
     CK_LAUNCH(c);
     return 0;
 }
@@ -1493,7 +1493,7 @@ dsvcu_sub_pred_from(dsvcu_ctx *c, const dsvcu_fmeta *fm, dsvcu_frame *pred, dsvc
         A.pl[i].src = src->p[i].data;
         A.pl[i].src_stride = src->p[i].stride;
     }
-    DSVCU_LAUNCH(k_predict, dim3(fm->nblocks_h * fm->nblocks_v, 3, 1), BMC_THREADS, 0, c->stream, A);
+    DSVCU_LAUNCH(k_predict, dim3(fm->nblocks_h * fm->nblocks_v, 1, 1), BMC_THREADS, 0, c->stream, A);
     CK_LAUNCH(c);
     return 0;
 }
@@ -1504,7 +1504,7 @@ dsvcu_add_pred(dsvcu_ctx *c, const dsvcu_fmeta *fm, int q, dsvcu_frame *resd, ds
 {
     BmcArgs A;
     bmc_fill(&A, c, fm, ref, NULL, resd, out, 1);
-    DSVCU_LAUNCH(k_predict, dim3(fm->nblocks_h * fm->nblocks_v, 3, 1), BMC_THREADS, 0, c->stream, A);
+    DSVCU_LAUNCH(k_predict, dim3(fm->nblocks_h * fm->nblocks_v, 1, 1), BMC_THREADS, 0, c->stream, A);
     CK_LAUNCH(c);
     return loop_filters(c, fm, q, out, do_filter);
 }

@@ -74,11 +74,14 @@ k_predict(BmcArgs A)
     DSVCU_SHARED uint8_t prd[BMC_MAXB * BMC_MAXB];
     DSVCU_SHARED int sums[4];
 
-    const int c = (int) blockIdx.y;
+    /* a CTA owns one motion block and walks its planes: a third of the CTAs of a launch per
+     * (block, plane), which was dominated by CTA start-up for 8x8 chroma blocks */
+    for (int c = (int) blockIdx.y; c < 3; c += (int) gridDim.y) {
     const BmcPlane P = A.pl[c];
     const int bi = (int) blockIdx.x % A.nbh, bj = (int) blockIdx.x / A.nbh;
     const dsvcu_mv mv = A.mvs[bi + bj * A.nbh];
     const int bw = A.blk_w >> P.sh, bh = A.blk_h >> P.sv;
+    const int lbw = bw >= 32 ? 5 : (bw >= 16 ? 4 : (bw >= 8 ? 3 : (bw >= 4 ? 2 : (bw >= 2 ? 1 : 0))));
     const int x = bi * bw, y = bj * bh;
     const int limx = (P.w - bw) + BMC_BORDER - 1;
     const int limy = (P.h - bh) + BMC_BORDER - 1;
@@ -92,7 +95,7 @@ k_predict(BmcArgs A)
         px = bmc_clampi(px, -BMC_BORDER, limx);
         py = bmc_clampi(py, -BMC_BORDER, limy);
         PAR_FOR(k, bw * bh) {
-            int r = k / bw, q = k - r * bw;
+            int r = k >> lbw, q = k & (bw - 1); /* bw is a power of two */
             win[r * WS + q] = P.ref[(py + r) * P.ref_stride + px + q];
         }
         PAR_FOR(k, 4) { sums[k] = 0; }
@@ -104,7 +107,7 @@ k_predict(BmcArgs A)
             /* per-quadrant (or whole-block) sums; integer sums are order-free */
             int part[4] = { 0, 0, 0, 0 };
             PAR_FOR(k, bw * bh) {
-                int r = k / bw, q = k - r * bw;
+                int r = k >> lbw, q = k & (bw - 1); /* bw is a power of two */
                 int qi = whole ? 0 : ((r >= sbh) * 2 + (q >= sbw));
                 part[qi] += win[r * WS + q];
             }
@@ -114,7 +117,7 @@ k_predict(BmcArgs A)
         }
         DSVCU_SYNC();
         PAR_FOR(k, bw * bh) {
-            int r = k / bw, q = k - r * bw;
+            int r = k >> lbw, q = k & (bw - 1); /* bw is a power of two */
             int qi = (r >= sbh) * 2 + (q >= sbw);
             int v;
             if (whole) {
@@ -131,7 +134,7 @@ k_predict(BmcArgs A)
             px = bmc_clampi(px, -BMC_BORDER, limx);
             py = bmc_clampi(py, -BMC_BORDER, limy);
             PAR_FOR(k, bw * bh) {
-                int r = k / bw, q = k - r * bw;
+                int r = k >> lbw, q = k & (bw - 1); /* bw is a power of two */
                 prd[r * BMC_MAXB + q] = P.ref[(py + r) * P.ref_stride + px + q];
             }
         } else {
@@ -143,13 +146,14 @@ k_predict(BmcArgs A)
             int dx = mv.x & 3, dy = mv.y & 3;
             int dqtx = large || !(dx & 1) || (A.tmc & 1);
             int dqty = large || !(dy & 1) || (A.tmc & 1);
-            PAR_FOR(k, (bh + 3) * (bw + 3)) {
-                int r = k / (bw + 3), q = k - r * (bw + 3);
-                win[r * WS + q] = P.ref[(py + r) * P.ref_stride + px + q];
+            /* window rows are WS = 36 apart: index it as (row, column) of a 64-wide grid, no division */
+            PAR_FOR(k, (bh + 3) * 64) {
+                int r = k >> 6, q = k & 63;
+                if (q < bw + 3) win[r * WS + q] = P.ref[(py + r) * P.ref_stride + px + q];
             }
             DSVCU_SYNC();
             PAR_FOR(k, (bh + 3) * bw) {
-                int r = k / bw, q = k - r * bw;
+                int r = k >> lbw, q = k & (bw - 1); /* bw is a power of two */
                 const uint8_t *s = win + r * WS + q;
                 int a = s[0], b = s[1], cc = s[2], d = s[3];
                 int f = dqtx ? HPF_A(a, b, cc, d) : HPF_B(a, b, cc, d);
@@ -157,7 +161,7 @@ k_predict(BmcArgs A)
             }
             DSVCU_SYNC();
             PAR_FOR(k, bh * bw) {
-                int r = k / bw, q = k - r * bw;
+                int r = k >> lbw, q = k & (bw - 1); /* bw is a power of two */
                 const int16_t *s = tmp + r * BMC_MAXB + q;
                 int a = s[0], b = s[BMC_MAXB], cc = s[2 * BMC_MAXB], d = s[3 * BMC_MAXB];
                 int f = dqty ? HPF_A(a, b, cc, d) : HPF_B(a, b, cc, d);
@@ -175,20 +179,20 @@ k_predict(BmcArgs A)
             int f0 = (hf - dx) * (vf - dy), f1 = dx * (vf - dy);
             int f2 = (hf - dx) * dy, f3 = dx * dy;
             int sf = hbits + vbits, af = 1 << (sf - 1);
-            PAR_FOR(k, (bh + 1) * (bw + 1)) {
-                int r = k / (bw + 1), q = k - r * (bw + 1);
-                win[r * WS + q] = P.ref[(py + r) * P.ref_stride + px + q];
+            PAR_FOR(k, (bh + 1) * 64) {
+                int r = k >> 6, q = k & 63;
+                if (q < bw + 1) win[r * WS + q] = P.ref[(py + r) * P.ref_stride + px + q];
             }
             DSVCU_SYNC();
             PAR_FOR(k, bh * bw) {
-                int r = k / bw, q = k - r * bw;
+                int r = k >> lbw, q = k & (bw - 1); /* bw is a power of two */
                 const uint8_t *s = win + r * WS + q;
                 prd[r * BMC_MAXB + q] =
                     (uint8_t) ((f0 * s[0] + f1 * s[1] + f2 * s[WS] + f3 * s[WS + 1] + af) >> sf);
             }
         } else {
             PAR_FOR(k, bw * bh) {
-                int r = k / bw, q = k - r * bw;
+                int r = k >> lbw, q = k & (bw - 1); /* bw is a power of two */
                 prd[r * BMC_MAXB + q] = P.ref[(py + r) * P.ref_stride + px + q];
             }
         }
@@ -201,7 +205,7 @@ k_predict(BmcArgs A)
         const int noxmit = !intra && (skip || (c == 0 && (mv.flags & MVF_NOXMITY)) ||
                                       (c != 0 && (mv.flags & MVF_NOXMITC)));
         PAR_FOR(k, bw * bh) {
-            int r = k / bw, q = k - r * bw;
+            int r = k >> lbw, q = k & (bw - 1); /* bw is a power of two */
             int p = prd[r * BMC_MAXB + q];
             uint8_t *rp = P.res + (y + r) * P.res_stride + x + q;
             int s = P.src[(y + r) * P.src_stride + x + q], o;
@@ -221,7 +225,7 @@ k_predict(BmcArgs A)
         /* decoder: out = prediction + residual (bmc.c:925-987) */
         const int plain = !eprm || (!intra && skip);
         PAR_FOR(k, bw * bh) {
-            int r = k / bw, q = k - r * bw;
+            int r = k >> lbw, q = k & (bw - 1); /* bw is a power of two */
             int p = prd[r * BMC_MAXB + q];
             int s = P.res[(y + r) * P.res_stride + x + q], o;
             if (A.lossless) {
@@ -233,6 +237,8 @@ k_predict(BmcArgs A)
             }
             P.out[(y + r) * P.out_stride + x + q] = (uint8_t) o;
         }
+    }
+    DSVCU_SYNC(); /* the staging arrays are reused by the next plane */
     }
 }
 
