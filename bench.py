@@ -477,28 +477,55 @@ def cpu_baseline_sample():
 
 def single_stream_configs(P, lib):
     """BASELINE configs 1-4 (frame-serial: one encoder / decoder instance, they cannot be sharded
-    bit-exactly), bounded lengths: our single-instance frames/s through the public buffer API from
-    HOST memory, next to the single-core reference on the same clip, with byte parity."""
+    bit-exactly), bounded lengths: our single-instance frames/s through the session API on a
+    persistent one-thread pool (contexts and device buffers exist, as in any long-running job), frames
+    in pinned HOST memory on both sides, next to the single-core reference on the same clip, with
+    byte parity.  The whole clip is one chunk, i.e. exactly one `dsv2 e` run without its final
+    end-of-stream packet."""
+    import torch
     import util
     import ops
     out = []
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
     cases = [("1: CIF 352x288 4:2:0, -qp=60 -gop=48", 352, 288, 60, "420", 30, ["-qp=60", "-gop=48"], dict(qp=60, gop=48)),
              ("2: 1280x720 4:2:0 50 fps, -gop=250 -effort=10", 1280, 720, 50, "420", 50, ["-gop=250", "-effort=10"],
               dict(gop=250, effort=10)),
              ("3: 1920x1080 4:2:0 CRF, -qp=60 -gop=48", 1920, 1080, 48, "420", 30, ["-qp=60", "-gop=48"], dict(qp=60, gop=48)),
              ("4: 1920x1080 4:4:4 lossless, -qp=100", 1920, 1080, 8, "444", 30, ["-qp=100"], dict(qp=100))]
+    devs = (C.c_int * 1)(torch.cuda.current_device())
     for name, w, h, n, fmt, fps, rargs, over in cases:
+        pool = None
         try:
             y4m = util.clip("bench_cfg%s" % name[0], w, h, n, fmt, fps=fps)
             _, _, fr = util.read_y4m(y4m)
             yuv = b"".join(ops.yuv_bytes(f) for f in fr)
-            o = P.enc_opts(w, h, P.SUBSAMP_420 if fmt == "420" else P.SUBSAMP_444, (fps, 1), **over)
-            P.encode_frames(o, yuv[:len(yuv) // n * min(n, 4)], min(n, 4))  # warm-up: contexts, clocks
+            fsz = len(yuv) // n
+            host = torch.frombuffer(bytearray(yuv), dtype=torch.uint8).pin_memory()
+            o = P.enc_opts(w, h, P.SUBSAMP_420 if fmt == "420" else P.SUBSAMP_444, (fps, 1), noeos=1, **over)
+            pool = lib.dsv_pool_create(1, devs, 1)
+            op, on = C.c_void_p(), C.c_size_t()
+
+            def enc(k):
+                if lib.dsv_pool_encode(pool, C.byref(o), C.c_void_p(host.data_ptr()), k, k, C.byref(op), C.byref(on)):
+                    raise RuntimeError("encode failed")
+                b = C.string_at(op, on.value)
+                libc.free(op)
+                return b
+            enc(min(n, 3))  # contexts, device buffers, clocks
             t0 = time.perf_counter()
-            dsv = P.encode_frames(o, yuv, n)
+            dsv = enc(n)
             te = time.perf_counter() - t0
+            dbuf = (C.c_uint8 * len(dsv)).from_buffer_copy(dsv)
+            dst = torch.empty(n * fsz, dtype=torch.uint8).pin_memory()
+            nf, meta = C.c_int(), P.DSV_META()
+
+            def dec():
+                if lib.dsv_pool_decode(pool, dbuf, len(dsv), C.c_void_p(dst.data_ptr()), n * fsz, C.byref(nf), C.byref(meta)):
+                    raise RuntimeError("decode failed")
+            dec()
             t0 = time.perf_counter()
-            _, nfr, dec = P.decode_frames(dsv)
+            dec()
             td = time.perf_counter() - t0
             rout = "/dev/shm/dsv2_bench_cfg%s.dsv" % name[0]
             t0 = time.perf_counter()
@@ -509,15 +536,20 @@ def single_stream_configs(P, lib):
             t0 = time.perf_counter()
             subprocess.run([REF_BIN, "d", "-y", "-inp=" + rout, "-out=" + ryuv], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             trd = time.perf_counter() - t0
-            ok_e = open(rout, "rb").read() == dsv
-            ok_d = open(ryuv, "rb").read() == dec
+            ref = open(rout, "rb").read()
+            # the reference run reached the end of its input and appended the 14-byte end-of-stream packet
+            ok_e = ref[:len(dsv)] == dsv and len(ref) - len(dsv) in (0, 14)
+            ok_d = open(ryuv, "rb").read() == dst.numpy().tobytes()
             os.unlink(ryuv)
-            out.append({"config": name, "frames": n, "encode_fps": round(n / te, 2), "decode_fps": round(nfr / td, 2),
+            out.append({"config": name, "frames": n, "encode_fps": round(n / te, 2), "decode_fps": round(nf.value / td, 2),
                         "reference_1core_encode_fps": round(n / tre, 2), "reference_1core_decode_fps": round(n / trd, 2),
                         "encode_speedup": round(tre / te, 1), "decode_speedup": round(trd / td, 1),
-                        "parity": {"encode": ok_e, "decode": ok_d}, "reference_exit": r.returncode})
+                        "parity": {"encode": ok_e, "decode": ok_d}})
         except Exception as e:
             out.append({"config": name, "error": str(e)})
+        finally:
+            if pool:
+                lib.dsv_pool_destroy(pool)
     return out
 
 
@@ -731,9 +763,10 @@ def run_own(args):
             ncu = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_summary.json")))
         except Exception:
             pass
-        l0n = ncu.get("k_me_level_L0", {})
-        prn = ncu.get("k_me_prepass_L0", {})
-        inst = (l0n.get("warp_instructions") or 0) + (prn.get("warp_instructions") or 0)
+        l0n = ncu.get("me_level_L0", {})
+        prn = ncu.get("me_prepass_L0", {})
+        spn = ncu.get("me_subpel", {})
+        inst = (l0n.get("warp_instructions") or 0) + (prn.get("warp_instructions") or 0) + (spn.get("warp_instructions") or 0)
         sm_mhz = (clk.summary() or {}).get("sm_mhz") or 1965
         issue_peak = 148 * 4 * sm_mhz * 1e6  # warp instructions per second the GPU can issue
         line["roofline"] = {
@@ -741,12 +774,11 @@ def run_own(args):
             "achieved": round(me["block_metric_evals_per_s"] / 1e6, 2), "unit": "M block-metric evaluations/s (one instance)",
             "peak": None, "frac": None,
             "issue_slot_pct": round(100.0 * inst / max(me["ms_per_frame"] * 1e-3 * issue_peak, 1e-9), 2) if inst else None,
-            "issue_slot_note": "warp instructions of the level-0 prepass + wavefront launches (ncu, profiles/r2_ncu_summary.json) / "
+            "issue_slot_note": "warp instructions of the level-0 prepass + sub-pel + wavefront launches (ncu, profiles/r2_ncu_summary.json) / "
                                "(live CUDA-event time of dsvcu_hme x 148 SMs x 4 schedulers x sampled SM clock)",
             "ms_per_picture_live": me["ms_per_frame"],
             "hbm": {"achieved": me["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": me["frac"],
-                    "traffic": int(l0n.get("dram_bytes_read", 0) + l0n.get("dram_bytes_write", 0) +
-                                   prn.get("dram_bytes_read", 0) + prn.get("dram_bytes_write", 0)) or None,
+                    "traffic": int(sum(k.get("dram_bytes_read", 0) + k.get("dram_bytes_write", 0) for k in (l0n, prn, spn))) or None,
                     "peak_source": src_peak},
             "note": "dominant kernel family by device time is the motion search: the prepass is issue / latency bound "
                     "(no HBM pressure: one picture and its pyramids sit in L2), the wavefront is bound by the dependency "
@@ -754,6 +786,13 @@ def run_own(args):
                     "one stream: launch-latency bound) and 'kernels_batched' (>= 64 pictures in flight: bandwidth)"}
         line["kernels"] = kern
         if batched:
+            tmap = {"fwd_sbt": "sbt_fwd_L1", "inv_sbt": "sbt_inv_L1", "predict": "predict", "reconstruct": "reconstruct",
+                    "quantise": "quant_hf_L2"}
+            for k in batched:
+                for key, nm in tmap.items():
+                    if k["kernel"].startswith(key) and nm in ncu:
+                        k["traffic_dominant_launch"] = int(ncu[nm].get("dram_bytes_read", 0) + ncu[nm].get("dram_bytes_write", 0))
+                        k["traffic_note"] = "dram bytes of the largest launch of the family (ncu, profiles/r2_ncu_%s.txt)" % nm
             line["kernels_batched"] = batched
             best_b = max(batched, key=lambda k: k["frac"])
             line["roofline"]["hbm_family_best"] = {"kernel": best_b["kernel"], "achieved": best_b["achieved_gbs"], "peak": peak,

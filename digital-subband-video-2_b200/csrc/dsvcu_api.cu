@@ -206,7 +206,9 @@ grid_for(int total, int threads)
 {
     int g = (total + threads - 1) / threads;
     if (g < 1) g = 1;
-    if (g > 148 * 16) g = 148 * 16;
+    /* four CTAs per SM and a grid-stride loop inside: per-element kernels with grids of thousands of
+     * short CTAs spend their time starting CTAs (measured: +2.5 % encoder throughput against 16 per SM) */
+    if (g > 148 * 4) g = 148 * 4;
     if (g_grid_cap > 0 && g > g_grid_cap) g = g_grid_cap;
     return g;
 }
