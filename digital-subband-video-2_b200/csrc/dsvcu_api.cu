@@ -250,12 +250,12 @@ coef_dims(int subsamp, int w, int h, int cw[3], int ch[3])
     ch[1] = ch[2] = chei;
 }
 
+static int ctx_init(dsvcu_ctx *c, int device, int width, int height, int subsamp);
+
 extern "C" int
 dsvcu_ctx_create(dsvcu_ctx **out, int device, int width, int height, int subsamp)
 {
     dsvcu_ctx *c;
-    int i;
-    size_t maxplane;
     *out = NULL;
 #ifndef DSVCU_EMU
     {
@@ -275,6 +275,22 @@ dsvcu_ctx_create(dsvcu_ctx **out, int device, int width, int height, int subsamp
 #endif
     c = (dsvcu_ctx *) calloc(1, sizeof(*c));
     if (!c) return -1;
+    if (ctx_init(c, device, width, height, subsamp)) {
+        dsvcu_ctx_destroy(c); /* releases whatever was created before the failure */
+#ifndef DSVCU_EMU
+        cudaGetLastError(); /* destroying handles that were never created leaves a sticky-looking error behind */
+#endif
+        return -1;
+    }
+    *out = c;
+    return 0;
+}
+
+static int
+ctx_init(dsvcu_ctx *c, int device, int width, int height, int subsamp)
+{
+    int i;
+    size_t maxplane;
     c->device = device;
     c->width = width;
     c->height = height;
@@ -318,7 +334,6 @@ dsvcu_ctx_create(dsvcu_ctx **out, int device, int width, int height, int subsamp
     CK(dsvcu_malloc(&c->d_lavg, 4 * sizeof(int)));
     CK(dsvcu_malloc_host(&c->h_lavg, 4 * sizeof(int)));
     *c->h_lavg = 255;
-    *out = c;
     return 0;
 }
 

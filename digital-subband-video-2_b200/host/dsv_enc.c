@@ -190,6 +190,16 @@ dsv_enc_recycle(DSV_ENCODER *from, DSV_ENCODER *to)
         }                                                      \
     } while (0)
 
+/* the same once the picture's bit writer exists: it is released on the way out */
+#define GPU_BW(call)                                           \
+    do {                                                       \
+        if (call) {                                            \
+            DSV_ERROR(("%s: %s", #call, dsvcu_last_error())); \
+            dsv_bw_free(&bw);                                  \
+            return -1;                                         \
+        }                                                      \
+    } while (0)
+
 /* ------------------------------------------------- quality -> quantiser */
 
 /* piecewise-exponential curve sampled every 10 quality points
@@ -1033,35 +1043,35 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
 
     PROF_MARK(g, PH_SIDEINFO);
     /* ---- pixel pipeline (device), queued in one go ---- */
-    GPU(dsvcu_set_side(g->ctx, enc->blockdata, p->has_ref ? g->mvs : NULL, nblk));
+    GPU_BW(dsvcu_set_side(g->ctx, enc->blockdata, p->has_ref ? g->mvs : NULL, nblk));
     if (tried_motion && !p->has_ref) {
         /* a picture that went through the search but is coded intra: the field as the
          * host left it is the next picture's temporal predictor
          * (DSV_HME.ref_mvf = reference picture's final_mvs) */
-        GPU(dsvcu_set_prev_mvs(g->ctx, g->mvs, nblk));
+        GPU_BW(dsvcu_set_prev_mvs(g->ctx, g->mvs, nblk));
     }
     if (g_prof > 1 && p->has_ref) dsvcu_mark(g->ctx, 3);
     /* the reference clones the padded source into the residual frame and works in
      * place (dsv_encoder.c:1292); here an intra picture is transformed straight
      * from the source, a predicted one has its residual written into `rec` */
     if (p->has_ref) {
-        GPU(dsvcu_sub_pred_from(g->ctx, &fm, g->pred, rec, ref_rec, src));
-        GPU(dsvcu_fwd_sbt_frame(g->ctx, rec, g->coefs, &fm, 7));
+        GPU_BW(dsvcu_sub_pred_from(g->ctx, &fm, g->pred, rec, ref_rec, src));
+        GPU_BW(dsvcu_fwd_sbt_frame(g->ctx, rec, g->coefs, &fm, 7));
     } else {
-        GPU(dsvcu_fwd_sbt_frame(g->ctx, src, g->coefs, &fm, 7));
+        GPU_BW(dsvcu_fwd_sbt_frame(g->ctx, src, g->coefs, &fm, 7));
     }
-    GPU(dsvcu_quant_frame(g->ctx, g->coefs, quant, &fm, 7));
-    GPU(dsvcu_inv_sbt_frame(g->ctx, rec, g->coefs, quant, &fm, 7));
+    GPU_BW(dsvcu_quant_frame(g->ctx, g->coefs, quant, &fm, 7));
+    GPU_BW(dsvcu_inv_sbt_frame(g->ctx, rec, g->coefs, quant, &fm, 7));
     if (!p->has_ref) {
-        GPU(dsvcu_intra_filter(g->ctx, quant, &fm, 0, rec, enc->do_intra_filter));
+        GPU_BW(dsvcu_intra_filter(g->ctx, quant, &fm, 0, rec, enc->do_intra_filter));
     }
     if (p->has_ref) {
         if (g_prof > 1) dsvcu_mark(g->ctx, 4);
-        GPU(dsvcu_add_res(g->ctx, &fm, quant, rec, g->pred, inter_filter));
+        GPU_BW(dsvcu_add_res(g->ctx, &fm, quant, rec, g->pred, inter_filter));
         if (g_prof > 1) dsvcu_mark(g->ctx, 5);
     }
     if (p->is_ref) {
-        GPU(dsvcu_extend_pyramid(g->ctx, rec, g->ref_pyr));
+        GPU_BW(dsvcu_extend_pyramid(g->ctx, rec, g->ref_pyr));
     }
     if (g_prof > 1 && p->has_ref) {
         dsvcu_mark(g->ctx, 6);
@@ -1070,7 +1080,7 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
     if (tried_motion && p->has_ref) {
         /* every reader of this picture's field is queued: it becomes the next
          * picture's temporal predictor by exchanging buffers, not by copying */
-        GPU(dsvcu_mvs_swap_prev(g->ctx, nblk));
+        GPU_BW(dsvcu_mvs_swap_prev(g->ctx, nblk));
     }
 
     PROF_MARK(g, PH_QUEUE);
@@ -1078,7 +1088,7 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
     for (i = 0; i < 3; i++) {
         const dsvcu_symbol *syms;
         int nsym, dc, cw, ch;
-        GPU(dsvcu_fetch_symbols(g->ctx, i, &syms, &nsym, &dc));
+        GPU_BW(dsvcu_fetch_symbols(g->ctx, i, &syms, &nsym, &dc));
         PROF_MARK(g, PH_SYM_WAIT);
         dsvcu_coefs_plane_dims(g->coefs, i, &cw, &ch);
         dsv_hzcc_write_plane(&bw, syms, nsym, dc, cw, ch);
@@ -1089,9 +1099,9 @@ encode_picture(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_FNUM fnum, DSV_BUF *out, 
     if (enc->frame_callback) {
         DSV_FRAME *hrec = dsv_mk_frame(g->subsamp, g->w, g->h, 0);
         for (i = 0; i < 3; i++) {
-            GPU(dsvcu_frame_download(g->ctx, rec, i, hrec->planes[i].data, hrec->planes[i].stride));
+            GPU_BW(dsvcu_frame_download(g->ctx, rec, i, hrec->planes[i].data, hrec->planes[i].stride));
         }
-        GPU(dsvcu_sync(g->ctx));
+        GPU_BW(dsvcu_sync(g->ctx));
         enc->frame_callback(&enc->vidmeta, frame, hrec);
         dsv_frame_ref_dec(hrec);
     }
