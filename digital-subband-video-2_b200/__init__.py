@@ -106,6 +106,10 @@ class DSVCU_SYMBOL(C.Structure):
     _fields_ = [("pos", C.c_uint32), ("v", C.c_int32)]
 
 
+class DSVCU_PLANE_BITS(C.Structure):
+    _fields_ = [("bits", C.c_void_p), ("len", C.c_uint32), ("w", C.c_int), ("h", C.c_int)]
+
+
 def lib_path(emu=False):
     if emu:
         return os.path.join(_ROOT, "tests", "_emu", "libdsv2cuda_emu.so")
@@ -184,6 +188,12 @@ def load(emu=False):
         "dsvcu_fetch_symbols": (ip, [vp, ip, P(P(DSVCU_SYMBOL)), P(ip), P(ip)]),
         "dsvcu_symbol_staging": (P(DSVCU_SYMBOL), [vp, ip, P(ip)]),
         "dsvcu_dequant_plane": (ip, [vp, vp, ip, ip, P(DSVCU_FMETA), ip, P(ip), ip]),
+        "dsv_set_device_entropy_decode": (ip, [ip]),
+        "dsvcu_parse_begin": (ip, [vp, P(DSVCU_PLANE_BITS), ip]),
+        "dsvcu_parse_end": (ip, [vp, ip, P(ip)]),
+        "dsvcu_parse_planes": (ip, [vp, P(DSVCU_PLANE_BITS), ip, P(ip)]),
+        "dsvcu_parsed_count": (ip, [vp, ip, ip]),
+        "dsvcu_dequant_parsed": (ip, [vp, vp, ip, P(DSVCU_FMETA), ip, ip]),
         "dsvcu_scan_layout": (ip, [ip, ip, P(ip)]),
         "dsvcu_sub_pred": (ip, [vp, P(DSVCU_FMETA), vp, vp, vp]),
         "dsvcu_add_pred": (ip, [vp, P(DSVCU_FMETA), ip, vp, vp, vp, ip]),

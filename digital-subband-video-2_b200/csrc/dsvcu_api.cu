@@ -9,6 +9,7 @@
 #include "dsvcu_rt.h"
 #include "k_sbt.cuh"
 #include "k_quant.cuh"
+#include "k_hzcc.cuh"
 #include "k_bmc.cuh"
 #include "k_filter.cuh"
 #include "k_frame.cuh"
@@ -66,6 +67,13 @@ fail(const char *what, int code)
 #else
     snprintf(g_err, sizeof(g_err), "%s: error %d", what, code);
 #endif
+    return -1;
+}
+
+static int
+fail_msg(const char *what)
+{
+    snprintf(g_err, sizeof(g_err), "%s", what);
     return -1;
 }
 
@@ -142,6 +150,27 @@ struct dsvcu_ctx {
     cudaEvent_t ev_stage[2]; /* last host-to-device copy out of the set has completed */
 #endif
     int sym_cap[3];
+    /* device-side entropy decode of batches of pictures (dsvcu_parse_begin / _end): two sets,
+     * so that the planes of the next batch are parsed (on `pstream`) while the pictures of
+     * the current one are reconstructed */
+    struct ParseSet {
+        uint8_t *h_bits, *d_bits; /* gathered plane bytes: pinned staging and device copy */
+        size_t bits_cap;
+        dsvcu_sym *d_syms;        /* one slot per (run, value) pair the plane headers announce */
+        size_t syms_cap;
+        HzSpan *h_spans, *d_spans;
+        int *h_meta, *d_meta;     /* HZ_META_WORDS per plane */
+        int spans_cap, n;
+        int pending;              /* begun, result not collected yet */
+#ifndef DSVCU_EMU
+        cudaEvent_t ev_parsed;    /* meta words of the batch are in pinned memory */
+        cudaEvent_t ev_consumed;  /* last de-quantiser launch that read the set's symbols */
+#endif
+    } pset[2];
+    int pset_last;
+#ifndef DSVCU_EMU
+    cudaStream_t pstream;
+#endif
     int *d_progress;
     int progress_cap;
     int me_smem_set;
@@ -337,6 +366,24 @@ ctx_init(dsvcu_ctx *c, int device, int width, int height, int subsamp)
     return 0;
 }
 
+static void
+parse_set_free(dsvcu_ctx *c, int i)
+{
+    dsvcu_ctx::ParseSet *S = &c->pset[i];
+    if (S->h_bits) dsvcu_free_host(S->h_bits);
+    if (S->d_bits) dsvcu_free_dev(S->d_bits);
+    if (S->d_syms) dsvcu_free_dev(S->d_syms);
+    if (S->h_spans) dsvcu_free_host(S->h_spans);
+    if (S->d_spans) dsvcu_free_dev(S->d_spans);
+    if (S->h_meta) dsvcu_free_host(S->h_meta);
+    if (S->d_meta) dsvcu_free_dev(S->d_meta);
+#ifndef DSVCU_EMU
+    if (S->ev_parsed) cudaEventDestroy(S->ev_parsed);
+    if (S->ev_consumed) cudaEventDestroy(S->ev_consumed);
+#endif
+    memset(S, 0, sizeof(*S));
+}
+
 extern "C" void
 dsvcu_ctx_destroy(dsvcu_ctx *c)
 {
@@ -344,6 +391,7 @@ dsvcu_ctx_destroy(dsvcu_ctx *c)
     if (!c) return;
 #ifndef DSVCU_EMU
     cudaSetDevice(c->device);
+    if (c->pstream) cudaStreamSynchronize(c->pstream);
     cudaStreamSynchronize(c->stream);
 #endif
     for (i = 0; i < 3; i++) {
@@ -361,6 +409,10 @@ dsvcu_ctx_destroy(dsvcu_ctx *c)
         dsvcu_free_host(c->h_syms_set[0][i]);
         if (c->h_syms_set[1][i]) dsvcu_free_host(c->h_syms_set[1][i]);
     }
+    for (i = 0; i < 2; i++) parse_set_free(c, i);
+#ifndef DSVCU_EMU
+    if (c->pstream) cudaStreamDestroy(c->pstream);
+#endif
     dsvcu_free_dev(c->d_progress);
     if (c->d_side[0]) dsvcu_free_dev(c->d_side[0]);
     if (c->d_side[1]) dsvcu_free_dev(c->d_side[1]);
@@ -1334,6 +1386,246 @@ dsvcu_dequant_plane(dsvcu_ctx *c, dsvcu_coefs *k, int plane, int q, const dsvcu_
     }
     /* dst->data[0] = LL (hzcc.c:634) */
     CK(dsvcu_d2d_async(k->data[plane], &c->d_syms[plane][nsyms].v, sizeof(int), c->stream));
+    return 0;
+}
+
+
+/* ---- entropy decode on the device (k_hzcc.cuh) ----
+ *
+ * dsvcu_parse_begin: `n` serialised coefficient planes (each starting at its 32-bit length
+ * word) are gathered into pinned memory, copied to the device and parsed by one launch, one
+ * warp per plane, on the context's parse stream -- beside whatever the context's main stream
+ * is doing.  Returns the set (0 / 1) the batch lives in.  dsvcu_parse_end waits for that set:
+ * ok[i] = 1: plane i was well-formed and its symbols are resident (dsvcu_dequant_parsed);
+ * ok[i] = 0: the caller must parse that plane on the host, which reproduces the reference's
+ * handling of damaged planes.  A set's symbols stay valid until the set is begun again, i.e.
+ * for two batches. */
+
+/* the number of (run, value) pairs a plane announces: [len32][SEG dc][align][count24] */
+static uint32_t
+plane_pair_count(const uint8_t *p, uint32_t len)
+{
+    uint32_t bit = 32, v = 1;
+    const uint32_t nbits = len * 8u;
+#define PBIT(b) ((b) < nbits ? (p[(b) >> 3] >> (7 - ((b) & 7))) & 1u : 1u)
+    while (!PBIT(bit)) { /* (0 d)* 1 */
+        v = (v << 1) | PBIT(bit + 1);
+        bit += 2;
+        if (bit > 32 + 66) return 0;
+    }
+    bit++;
+    if (v != 1) bit++; /* sign of a nonzero DC */
+#undef PBIT
+    bit = (bit + 7) & ~7u;
+    if (bit + 24 > nbits) return 0;
+    return ((uint32_t) p[bit >> 3] << 16) | ((uint32_t) p[(bit >> 3) + 1] << 8) | p[(bit >> 3) + 2];
+}
+
+extern "C" int
+dsvcu_parse_begin(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n)
+{
+    size_t total = 0, nsyms = 0, at = 0, sat = 0;
+    int i, set = 0;
+    HzJob J;
+    dsvcu_ctx::ParseSet *S;
+
+    if (n <= 0) return fail_msg("dsvcu_parse_begin: no planes");
+    /* the set that was begun longer ago; never one whose result has not been collected */
+    if (c->pset[0].pending && c->pset[1].pending) return fail_msg("dsvcu_parse_begin: two batches already in flight");
+    set = c->pset[0].pending ? 1 : (c->pset[1].pending ? 0 : (c->pset_last ^ 1));
+    S = &c->pset[set];
+    for (i = 0; i < n; i++) {
+        if (pl[i].len < 8 || pl[i].len > 0x3fffffffu || !pl[i].bits) return fail_msg("dsvcu_parse_begin: bad plane");
+        total += ((size_t) pl[i].len + 7) & ~(size_t) 7;
+    }
+    if (total + 16 > 0xffffffffu / 8) return fail_msg("dsvcu_parse_begin: batch too large");
+#ifndef DSVCU_EMU
+    if (!c->pstream) CK(cudaStreamCreateWithFlags(&c->pstream, cudaStreamNonBlocking));
+    if (!S->ev_parsed) {
+        CK(cudaEventCreateWithFlags(&S->ev_parsed, cudaEventDisableTiming | cudaEventBlockingSync));
+        CK(cudaEventCreateWithFlags(&S->ev_consumed, cudaEventDisableTiming));
+    }
+    /* de-quantiser launches of the batch that used this set last may still be queued */
+    CK(cudaStreamWaitEvent(c->pstream, S->ev_consumed, 0));
+#endif
+    if (total + 16 > S->bits_cap || n > S->spans_cap) {
+        /* (growing frees memory that queued work may still read) */
+        CK(ctx_wait(c));
+#ifndef DSVCU_EMU
+        CK(cudaStreamSynchronize(c->pstream));
+#endif
+        if (total + 16 > S->bits_cap) {
+            const size_t cap = total + total / 4 + 4096;
+            if (S->h_bits) dsvcu_free_host(S->h_bits);
+            if (S->d_bits) dsvcu_free_dev(S->d_bits);
+            S->h_bits = S->d_bits = NULL;
+            S->bits_cap = 0;
+            CK(dsvcu_malloc_host(&S->h_bits, cap));
+            CK(dsvcu_malloc(&S->d_bits, cap));
+            S->bits_cap = cap;
+        }
+        if (n > S->spans_cap) {
+            const int cap = n + 16;
+            if (S->h_spans) dsvcu_free_host(S->h_spans);
+            if (S->d_spans) dsvcu_free_dev(S->d_spans);
+            if (S->h_meta) dsvcu_free_host(S->h_meta);
+            if (S->d_meta) dsvcu_free_dev(S->d_meta);
+            S->h_spans = S->d_spans = NULL;
+            S->h_meta = S->d_meta = NULL;
+            S->spans_cap = 0;
+            CK(dsvcu_malloc_host(&S->h_spans, (size_t) cap * sizeof(HzSpan)));
+            CK(dsvcu_malloc(&S->d_spans, (size_t) cap * sizeof(HzSpan)));
+            CK(dsvcu_malloc_host(&S->h_meta, (size_t) cap * HZ_META_WORDS * sizeof(int)));
+            CK(dsvcu_malloc(&S->d_meta, (size_t) cap * HZ_META_WORDS * sizeof(int)));
+            S->spans_cap = cap;
+        }
+    }
+    for (i = 0; i < n; i++) {
+        HzSpan *sp = &S->h_spans[i];
+        const size_t padded = ((size_t) pl[i].len + 7) & ~(size_t) 7;
+        int part[5];
+        uint32_t pairs = plane_pair_count(pl[i].bits, pl[i].len);
+        /* a pair takes two bits or more and lands on a scan position of its own: anything
+         * beyond that is a damaged plane, which the kernel will refuse */
+        const uint32_t most = (uint32_t) dsvcu_scan_layout(pl[i].w, pl[i].h, part);
+        if (pairs > most || (size_t) pairs > (size_t) pl[i].len * 4) pairs = 0;
+        memcpy(S->h_bits + at, pl[i].bits, pl[i].len);
+        memset(S->h_bits + at + pl[i].len, 0, padded - pl[i].len);
+        sp->off = (uint32_t) at;
+        sp->len = pl[i].len;
+        sp->w = pl[i].w;
+        sp->h = pl[i].h;
+        sp->sym_base = (uint32_t) sat;
+        sp->sym_cap = pairs;
+        at += padded;
+        sat += pairs;
+    }
+    nsyms = sat;
+    if (nsyms + 1 > S->syms_cap) {
+        const size_t cap = nsyms + nsyms / 4 + 4096;
+        CK(ctx_wait(c));
+#ifndef DSVCU_EMU
+        CK(cudaStreamSynchronize(c->pstream));
+#endif
+        if (S->d_syms) dsvcu_free_dev(S->d_syms);
+        S->d_syms = NULL;
+        S->syms_cap = 0;
+        CK(dsvcu_malloc(&S->d_syms, cap * sizeof(dsvcu_sym)));
+        S->syms_cap = cap;
+    }
+    memset(S->h_bits + at, 0, 16);
+#ifndef DSVCU_EMU
+    const cudaStream_t ps = c->pstream;
+#else
+    const dsvcu_stream_t ps = 0;
+#endif
+    CK(dsvcu_h2d_async(S->d_bits, S->h_bits, at + 16, ps));
+    CK(dsvcu_h2d_async(S->d_spans, S->h_spans, (size_t) n * sizeof(HzSpan), ps));
+    J.bits = S->d_bits;
+    J.spans = S->d_spans;
+    J.nspans = n;
+    J.syms = S->d_syms;
+    J.meta = S->d_meta;
+#ifndef DSVCU_EMU
+    DSVCU_LAUNCH(k_hzcc_parse, (n + HZ_WARPS - 1) / HZ_WARPS, HZ_WARPS * 32, 0, ps, J);
+#else
+    DSVCU_LAUNCH(k_hzcc_parse, n, 32, 0, ps, J);
+#endif
+    CK_LAUNCH(c);
+    CK(dsvcu_d2h_async(S->h_meta, S->d_meta, (size_t) n * HZ_META_WORDS * sizeof(int), ps));
+#ifndef DSVCU_EMU
+    CK(cudaEventRecord(S->ev_parsed, ps));
+#endif
+    S->n = n;
+    S->pending = 1;
+    c->pset_last = set;
+    return set;
+}
+
+extern "C" int
+dsvcu_parse_end(dsvcu_ctx *c, int set, int *ok)
+{
+    dsvcu_ctx::ParseSet *S;
+    int i;
+    if (set < 0 || set > 1 || !c->pset[set].n) return fail_msg("dsvcu_parse_end: no such batch");
+    S = &c->pset[set];
+    if (S->pending) {
+#ifndef DSVCU_EMU
+        CK(cudaEventSynchronize(S->ev_parsed));
+#endif
+        S->pending = 0;
+    }
+    for (i = 0; i < S->n; i++) ok[i] = S->h_meta[i * HZ_META_WORDS + HZ_META_OK] == 1;
+    return 0;
+}
+
+/* both halves in one call: the batch is set 0 or 1 (returned) */
+extern "C" int
+dsvcu_parse_planes(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n, int *ok)
+{
+    const int set = dsvcu_parse_begin(c, pl, n);
+    if (set < 0) return -1;
+    if (dsvcu_parse_end(c, set, ok)) return -1;
+    return set;
+}
+
+/* number of symbols the device parser found in plane `span` of a collected batch (tests) */
+extern "C" int
+dsvcu_parsed_count(dsvcu_ctx *c, int set, int span)
+{
+    const dsvcu_ctx::ParseSet *S;
+    if (set < 0 || set > 1) return -1;
+    S = &c->pset[set];
+    if (S->pending || span < 0 || span >= S->n || S->h_meta[span * HZ_META_WORDS + HZ_META_OK] != 1) return -1;
+    return S->h_meta[span * HZ_META_WORDS + HZ_META_NSYM];
+}
+
+/* de-quantise the three planes of one picture from spans first_span .. first_span + 2 of a
+ * collected batch (all three must have been ok): the counterpart of three
+ * dsvcu_dequant_plane calls, 7 launches, nothing crosses the bus */
+extern "C" int
+dsvcu_dequant_parsed(dsvcu_ctx *c, dsvcu_coefs *k, int q, const dsvcu_fmeta *fm, int set, int first_span)
+{
+    DequantJob J;
+    const dsvcu_ctx::ParseSet *S;
+    int part[3][5], p, l, wave, most = 0;
+    const int qf = q * 3 / 2;
+
+    if (set < 0 || set > 1) return fail_msg("dsvcu_dequant_parsed: no such batch");
+    S = &c->pset[set];
+    if (S->pending || first_span < 0 || first_span + 3 > S->n) return fail_msg("dsvcu_dequant_parsed: no such planes");
+    for (p = 0; p < 3; p++) {
+        const HzSpan *sp = &S->h_spans[first_span + p];
+        const int *m = S->h_meta + (first_span + p) * HZ_META_WORDS;
+        if (m[HZ_META_OK] != 1 || sp->w != k->w[p] || sp->h != k->h[p]) {
+            return fail_msg("dsvcu_dequant_parsed: plane was not parsed for this geometry");
+        }
+        dsvcu_scan_layout(k->w[p], k->h[p], part[p]);
+        CK(dsvcu_memset_async(k->data[p], 0, (size_t) k->w[p] * k->h[p] * sizeof(int32_t), c->stream));
+        J.meta[p] = S->d_meta + (first_span + p) * HZ_META_WORDS;
+        J.lfq[p] = fm->lossless ? 1 : lfquant(qf, p, fm);
+        if (m[HZ_META_NSYM] > most) most = m[HZ_META_NSYM];
+    }
+    /* grid for the fullest level of the fullest plane (grid-stride loops inside) */
+    const int grid = grid_for(most > 0 ? most : 1, 256 * 4);
+    for (l = -1; l < 3; l++) {
+        for (p = 0; p < 3; p++) {
+            quant_level_geom(&J.Q[p], c, k, p, qf, fm, l, part[p]);
+            J.Q[p].syms = S->d_syms + S->h_spans[first_span + p].sym_base;
+        }
+        if (l < 0) {
+            DSVCU_LAUNCH(k_dequant_ll_m, dim3(grid, 3, 1), 256, 0, c->stream, J);
+            CK_LAUNCH(c);
+            continue;
+        }
+        for (wave = 0; wave < (fm->lossless ? 1 : 2); wave++) {
+            DSVCU_LAUNCH(k_dequant_hf_m, dim3(grid, 3, 1), 256, 0, c->stream, J, wave);
+            CK_LAUNCH(c);
+        }
+    }
+#ifndef DSVCU_EMU
+    CK(cudaEventRecord(S->ev_consumed, c->stream));
+#endif
     return 0;
 }
 

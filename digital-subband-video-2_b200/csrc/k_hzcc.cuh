@@ -1,0 +1,352 @@
+/*
+ * k_hzcc.cuh -- entropy decode of coefficient planes on the device.
+ *
+ * Replaces the bit-parsing half of reference src/hzcc.c: dsv_decode_plane
+ * (:585-649) / hzcc_dec (:450-583) with the codes of src/bs.c (interleaved
+ * exp-Golomb :96-137, adaptive Rice :237-251): a serialised plane
+ *   [32-bit byte length][SEG dc][align][24-bit pair count][align]
+ *   [(UEG run, value)...][align][0x55]
+ * becomes the ordered list of (scan position, value) symbols that the
+ * de-quantiser kernels (k_quant.cuh) scatter -- the same list the host parser
+ * (host/dsv_hzcc.c) produces.
+ *
+ * A plane is one serial chain (every code length depends on the previous
+ * code, the Rice parameter adapts per symbol), but planes are independent and
+ * pictures carry no entropy-coder state: one warp per plane, all planes of
+ * a batch of pictures (a closed GOP) in one launch on a stream of its own, so
+ * that the chains run beside the reconstruction of the pictures before them.
+ * Off the host this removes ~70 % of the CPU time of a decoded picture.
+ *
+ * The kernel accepts only what a well-formed encoder writes.  Anything else
+ * (truncated plane, bad end marker, position overflow, oversized Rice
+ * parameter, ...) clears the plane's `ok` word and the host parser -- which
+ * reproduces the reference's behaviour on damaged input -- decodes that picture
+ * instead.
+ */
+#ifndef K_HZCC_CUH
+#define K_HZCC_CUH
+
+#include "dsvcu_rt.h"
+#include "k_quant.cuh"
+#ifndef DSVCU_EMU
+#define HZT_FN __host__ __device__ __forceinline__ static
+#define HZT_CLZ32(v) hzt_clz32_(v)
+__host__ __device__ __forceinline__ static int
+hzt_clz32_(uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+    return __clz((int) v);
+#else
+    return v ? __builtin_clz(v) : 32;
+#endif
+}
+#endif
+#include "hz_table.h"
+
+#define HZ_EOP 0x55
+#define HZ_META_WORDS 8 /* nsym, level_start[0..4], dc, ok */
+#define HZ_META_NSYM 0
+#define HZ_META_LS 1
+#define HZ_META_DC 6
+#define HZ_META_OK 7
+
+struct HzSpan {
+    uint32_t off;      /* first byte of the plane (its length word) in the batch buffer; multiple of 8 */
+    uint32_t len;      /* bytes available to this plane: 4 + declared length */
+    int w, h;          /* coefficient plane size */
+    uint32_t sym_base; /* first symbol slot of this plane */
+    uint32_t sym_cap;
+};
+
+struct HzJob {
+    const uint8_t *bits; /* batch buffer, 16 zero bytes behind the last plane */
+    const HzSpan *spans;
+    int nspans;
+    dsvcu_sym *syms;
+    int *meta; /* HZ_META_WORDS per span */
+};
+
+/* big-endian bit reader: `win` holds the next `n` bits left-aligned (zeros below them); the
+ * bytes behind them start at buf[nb], and the word at buf[nb] is already in `nxt` (loaded one
+ * refill ahead, so that its latency is not on the dependent chain) */
+struct HzRd {
+    const uint8_t *buf;
+    uint32_t nb;  /* next byte to enter the window */
+    uint32_t end; /* bytes in the plane (reads beyond see zeros) */
+    uint64_t win;
+    int n;
+    uint32_t nxt;
+};
+
+DSVCU_DEV uint32_t
+hz_be32(const uint8_t *p)
+{
+#ifndef DSVCU_EMU
+    return __byte_perm(*(const uint32_t *) p, 0, 0x0123);
+#else
+    return ((uint32_t) p[0] << 24) | ((uint32_t) p[1] << 16) | ((uint32_t) p[2] << 8) | p[3];
+#endif
+}
+
+DSVCU_DEV int
+hz_clz32(uint32_t v)
+{
+#ifndef DSVCU_EMU
+    return __clz((int) v);
+#else
+    return v ? __builtin_clz(v) : 32;
+#endif
+}
+
+DSVCU_DEV uint32_t
+hz_word(const HzRd &r, uint32_t at) /* `at` is a multiple of 4; the batch buffer is padded */
+{
+    return at < r.end ? hz_be32(r.buf + at) : 0u;
+}
+
+DSVCU_DEV void
+hz_open(HzRd &r, const uint8_t *buf, uint32_t len)
+{
+    r.buf = buf;
+    r.end = len;
+    r.win = ((uint64_t) hz_word(r, 0) << 32) | hz_word(r, 4);
+    r.n = 64;
+    r.nb = 8;
+    r.nxt = hz_word(r, 8);
+}
+
+/* at least 32 valid bits in the window (written without a branch: the refill is a handful of
+ * predicated instructions, a branch costs a reconvergence point on the dependent chain) */
+DSVCU_DEV void
+hz_fill(HzRd &r)
+{
+    const bool take = r.n <= 32;
+    const uint32_t nb = r.nb + 4;
+    const uint64_t add = (uint64_t) r.nxt << ((32 - r.n) & 63);
+    r.win |= take ? add : 0;
+    const uint32_t w = (take && nb < r.end) ? hz_be32(r.buf + nb) : 0u;
+    r.nxt = take ? w : r.nxt;
+    r.nb = take ? nb : r.nb;
+    r.n += take ? 32 : 0;
+}
+
+DSVCU_DEV void
+hz_skip(HzRd &r, int k)
+{
+    r.win <<= k;
+    r.n -= k;
+}
+
+/* bits consumed so far, from the start of the plane */
+DSVCU_DEV uint32_t
+hz_pos(const HzRd &r)
+{
+    return r.nb * 8u - (uint32_t) r.n;
+}
+
+DSVCU_DEV uint32_t
+hz_bits(HzRd &r, int k) /* 0 <= k <= 32 */
+{
+    hz_fill(r);
+    if (k == 0) return 0;
+    uint32_t v = (uint32_t) (r.win >> (64 - k));
+    hz_skip(r, k);
+    return v;
+}
+
+DSVCU_DEV void
+hz_align(HzRd &r)
+{
+    hz_skip(r, r.n & 7); /* the window ends on a byte boundary */
+}
+
+#define HZ_BAD 0xffffffffu
+
+/* interleaved exp-Golomb (bs.c:96-137): (0 d)* 1 -- any length; HZ_BAD when the code runs
+ * off the plane */
+DSVCU_DEV uint32_t
+hz_ueg(HzRd &r)
+{
+    uint32_t v = 1;
+    for (;;) {
+        hz_fill(r);
+        const uint32_t top = (uint32_t) (r.win >> 32);
+        const uint32_t stops = top & 0xAAAAAAAAu;
+        if (stops == 0) { /* 16 pairs, no terminator yet */
+            v = (v << 16) | hzt_even_bits(top);
+            hz_skip(r, 32);
+            if (r.nb > r.end + 16) return HZ_BAD;
+            continue;
+        }
+        const int pairs = hz_clz32(stops) >> 1;
+        if (pairs) v = (v << pairs) | hzt_even_bits(top >> (32 - 2 * pairs));
+        hz_skip(r, 2 * pairs + 1);
+        return v - 1;
+    }
+}
+
+DSVCU_DEV int
+hz_seg(HzRd &r)
+{
+    int v = (int) hz_ueg(r);
+    if (v && hz_bits(r, 1)) return -v;
+    return v;
+}
+
+/* nonzero value of the LL part (bs.c: UEG of |v| - 1, then the sign) */
+DSVCU_DEV int
+hz_neg(HzRd &r)
+{
+    const int v = (int) hz_ueg(r) + 1;
+    return hz_bits(r, 1) ? -v : v;
+}
+
+/* adaptive Rice (bs.c:237-251); k <= 24 is checked by the caller */
+DSVCU_DEV int
+hz_nrice(HzRd &r, int *rk, int k)
+{
+    uint32_t q, uv;
+    hz_fill(r);
+    const uint32_t top = (uint32_t) (r.win >> 32);
+    const int z = hz_clz32(top);
+    if (z + 1 + k <= 32) { /* the whole code is in the upper half of the window */
+        const uint32_t rest = top << z << 1;
+        q = (uint32_t) z;
+        uv = (q << k) | ((rest >> 1) >> (31 - k));
+        hz_skip(r, z + 1 + k);
+    } else {
+        q = 0;
+        for (;;) {
+            hz_fill(r);
+            const uint32_t t = (uint32_t) (r.win >> 32);
+            if (t == 0) {
+                q += 32;
+                hz_skip(r, 32);
+                if (r.nb > r.end + 16) break;
+                continue;
+            }
+            const int n = hz_clz32(t);
+            q += (uint32_t) n;
+            hz_skip(r, n + 1);
+            break;
+        }
+        uv = (q << k) | hz_bits(r, k);
+    }
+    *rk += q ? 1 : -(*rk > 0);
+    uv += 1;
+    return (int) (uv >> 1) ^ -(int) (uv & 1);
+}
+
+/* scan-order partition of a plane (same as dsvcu_scan_layout) */
+DSVCU_DEV int
+hz_layout(int w, int h, int part[5])
+{
+    int pos = ((w + 7) >> 3) * ((h + 7) >> 3);
+    part[0] = 0;
+    for (int l = 0; l < 3; l++) {
+        part[1 + l] = pos;
+        pos += 3 * ((w + (1 << (3 - l)) - 1) >> (3 - l)) * ((h + (1 << (3 - l)) - 1) >> (3 - l));
+    }
+    part[4] = pos;
+    return pos;
+}
+
+/* one plane; returns 1 when it was well-formed.  `tab`: HZT_ROWS rows of HZT_SIZE entries */
+DSVCU_DEV int
+hz_parse_plane(const HzJob &J, const HzSpan &S, int *meta, const uint32_t *tab)
+{
+    HzRd r;
+    int part[5];
+    const uint32_t total = (uint32_t) hz_layout(S.w, S.h, part);
+    dsvcu_sym *out = J.syms + S.sym_base;
+    hz_open(r, J.bits + S.off, S.len);
+    const uint32_t plen = hz_bits(r, 32);
+    if (!(plen > 0 && (uint64_t) plen < (uint64_t) S.w * (uint64_t) S.h * sizeof(int32_t) * 2) || plen + 4 != S.len) {
+        return 0;
+    }
+    const int dc = hz_seg(r);
+    hz_align(r);
+    const uint32_t runs = hz_bits(r, 24);
+    hz_align(r);
+    if (runs > S.sym_cap) return 0; /* (the host sized the symbol slots from this very field) */
+    /* the parts of the scan in turn: LL (l = -1), then levels 0..2; `bound` = first position
+     * behind the part, `ls` = index of the first symbol of each part.  Every step of the
+     * chain is  value of this pair, run of the next pair: one table look-up where both codes
+     * fit into HZT_BITS bits (nearly always), the general readers otherwise. */
+    int n = 0, l = -1, vk = 0, ls1 = 0, ls2 = 0, ls3 = 0;
+    uint32_t cur = 0, bound = (uint32_t) part[1];
+    uint32_t run = runs ? hz_ueg(r) : 0;
+    for (uint32_t i = 0; i < runs; i++) {
+        const uint32_t pos = cur + run;
+        if (run > 0x3fffffffu) return 0;
+        while (pos >= bound) {
+            if (pos >= total) return 0;
+            l++;
+            if (l == 0) ls1 = n;
+            if (l == 1) ls2 = n;
+            if (l == 2) ls3 = n;
+            bound = l < 2 ? (uint32_t) part[l + 2] : total;
+        }
+        const int k = l < 0 ? HZT_ROW_LL : vk >> (3 + l);
+        int v;
+        uint32_t e = 0;
+        hz_fill(r);
+        if ((l < 0 || k < HZT_KMAX) && i + 1 < runs) e = tab[k * HZT_SIZE + (uint32_t) (r.win >> (64 - HZT_BITS))];
+        if (HZT_LEN(e)) {
+            hz_skip(r, HZT_LEN(e));
+            v = HZT_VAL(e);
+            run = HZT_RUN(e);
+            if (l >= 0) vk += HZT_QNZ(e) ? 1 : -(vk > 0);
+        } else {
+            if (l < 0) {
+                v = hz_neg(r);
+            } else {
+                if (k > 24) return 0;
+                v = hz_nrice(r, &vk, k);
+            }
+            run = i + 1 < runs ? hz_ueg(r) : 0;
+        }
+        if (pos != 0) {
+            dsvcu_sym sy;
+            sy.pos = pos;
+            sy.v = v;
+            out[n++] = sy;
+        }
+        cur = pos + 1;
+    }
+    /* a pair whose bits end at or behind the declared length is the host parser's business
+     * (bit positions only grow: looking once, here, is the same as looking after every pair) */
+    if ((hz_pos(r) >> 3) >= S.len) return 0;
+    if (l < 0) ls1 = n;
+    if (l < 1) ls2 = n;
+    if (l < 2) ls3 = n;
+    hz_align(r);
+    if (hz_bits(r, 8) != HZ_EOP || hz_pos(r) > S.len * 8u) return 0;
+    meta[HZ_META_NSYM] = n;
+    meta[HZ_META_LS + 0] = 0;
+    meta[HZ_META_LS + 1] = ls1;
+    meta[HZ_META_LS + 2] = ls2;
+    meta[HZ_META_LS + 3] = ls3;
+    meta[HZ_META_LS + 4] = n;
+    meta[HZ_META_DC] = dc;
+    return 1;
+}
+
+/* One chain per warp (lane 0 walks it; a chain is latency-bound and wants a scheduler slot,
+ * not lanes), HZ_WARPS chains per CTA sharing the prefix table in shared memory (40 KB). */
+#define HZ_WARPS 8
+
+DSVCU_KERNEL void __launch_bounds__(HZ_WARPS * 32)
+k_hzcc_parse(HzJob J)
+{
+    DSVCU_SHARED uint32_t tab[HZT_ROWS * HZT_SIZE];
+    PAR_FOR(i, HZT_ROWS * HZT_SIZE) tab[i] = hzt_entry((uint32_t) i & (HZT_SIZE - 1), i >> HZT_BITS);
+    DSVCU_SYNC();
+    const int per_cta = DSVCU_NTH >= 32 ? DSVCU_NTH >> 5 : 1;
+    const int s = (int) blockIdx.x * per_cta + (DSVCU_TID >> 5);
+    if ((DSVCU_TID & 31) != 0 || s >= J.nspans) return;
+    int *meta = J.meta + s * HZ_META_WORDS;
+    meta[HZ_META_OK] = hz_parse_plane(J, J.spans[s], meta, tab);
+}
+
+#endif /* K_HZCC_CUH */

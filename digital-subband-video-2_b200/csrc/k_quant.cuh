@@ -376,47 +376,92 @@ k_compact_scatter(CompactJob J)
 /* ------------------------------------------------------------- decoder */
 
 /* LL part (hzcc.c:520-533; lossless :479-492) */
-DSVCU_KERNEL void __launch_bounds__(256)
-k_dequant_ll(QuantLevel Q, int qp)
+DSVCU_DEV void
+q_dequant_ll_one(const QuantLevel &Q, int qp, dsvcu_sym sy)
 {
-    for (int k = Q.sym_begin + (int) blockIdx.x * DSVCU_NTH + DSVCU_TID; k < Q.sym_end; k += (int) gridDim.x * DSVCU_NTH) {
-        dsvcu_sym sy = Q.syms[k];
-        int y = (int) sy.pos / Q.w, x = (int) sy.pos - y * Q.w;
-        int v = sy.v;
-        if (!Q.lossless) {
-            v = Q.isP ? q_deq_d(v, qp) : q_deq_s(v, qp);
-        }
-        Q.coefs[y * Q.fw + x] = v;
+    int y = (int) sy.pos / Q.w, x = (int) sy.pos - y * Q.w;
+    int v = sy.v;
+    if (!Q.lossless) {
+        v = Q.isP ? q_deq_d(v, qp) : q_deq_s(v, qp);
     }
+    Q.coefs[y * Q.fw + x] = v;
 }
 
 /* levels 0..2 (hzcc.c:534-581).  wave 0 skips aliased-parent elements, wave 1
  * handles only those. */
+DSVCU_DEV void
+q_dequant_hf_one(const QuantLevel &Q, int wave, dsvcu_sym sy)
+{
+    const int area = Q.w * Q.h;
+    int rel = (int) sy.pos - Q.band[0].scan_base;
+    int s = rel / area;
+    rel -= s * area;
+    const QuantBand B = Q.band[s];
+    int y = rel / Q.w, x = rel - y * Q.w;
+    int v = sy.v;
+    if (!Q.lossless) {
+        int al = q_parent_aliased(Q, B, x, y);
+        if (al != wave) {
+            return;
+        }
+        int flags = Q.blockdata[((y * Q.dby) >> 14) * Q.nbh + ((x * Q.dbx) >> 14)];
+        int parc = Q.coefs[(B.poy + (y >> 1)) * Q.fw + B.pox + (x >> 1)];
+        int tmq = Q.isP ? q_tmq_p(B.qp, flags, parc) : q_tmq_i(B.qp, flags, parc, Q.l);
+        v = q_deq_d(v, tmq);
+    } else if (wave) {
+        return;
+    }
+    Q.coefs[(B.oy + y) * Q.fw + B.ox + x] = v;
+}
+
+/* one plane, symbol range given by the host (symbols parsed on the host) */
+DSVCU_KERNEL void __launch_bounds__(256)
+k_dequant_ll(QuantLevel Q, int qp)
+{
+    for (int k = Q.sym_begin + (int) blockIdx.x * DSVCU_NTH + DSVCU_TID; k < Q.sym_end; k += (int) gridDim.x * DSVCU_NTH) {
+        q_dequant_ll_one(Q, qp, Q.syms[k]);
+    }
+}
+
 DSVCU_KERNEL void __launch_bounds__(256)
 k_dequant_hf(QuantLevel Q)
 {
-    const int area = Q.w * Q.h;
     for (int k = Q.sym_begin + (int) blockIdx.x * DSVCU_NTH + DSVCU_TID; k < Q.sym_end; k += (int) gridDim.x * DSVCU_NTH) {
-        dsvcu_sym sy = Q.syms[k];
-        int rel = (int) sy.pos - Q.band[0].scan_base;
-        int s = rel / area;
-        rel -= s * area;
-        const QuantBand B = Q.band[s];
-        int y = rel / Q.w, x = rel - y * Q.w;
-        int v = sy.v;
-        if (!Q.lossless) {
-            int al = q_parent_aliased(Q, B, x, y);
-            if (al != Q.wave) {
-                continue;
-            }
-            int flags = Q.blockdata[((y * Q.dby) >> 14) * Q.nbh + ((x * Q.dbx) >> 14)];
-            int parc = Q.coefs[(B.poy + (y >> 1)) * Q.fw + B.pox + (x >> 1)];
-            int tmq = Q.isP ? q_tmq_p(B.qp, flags, parc) : q_tmq_i(B.qp, flags, parc, Q.l);
-            v = q_deq_d(v, tmq);
-        } else if (Q.wave) {
-            continue;
-        }
-        Q.coefs[(B.oy + y) * Q.fw + B.ox + x] = v;
+        q_dequant_hf_one(Q, Q.wave, Q.syms[k]);
+    }
+}
+
+/* The planes of a picture whose symbols were parsed on the device (k_hzcc.cuh): blockIdx.y
+ * selects the plane, the symbol ranges of the levels and the DC are read from the parser's
+ * meta words {count, level_start[5], dc, ok} -- the host never sees them. */
+struct DequantJob {
+    QuantLevel Q[3];
+    int lfq[3];
+    const int *meta[3];
+};
+
+DSVCU_KERNEL void __launch_bounds__(256)
+k_dequant_ll_m(DequantJob J)
+{
+    const QuantLevel &Q = J.Q[blockIdx.y];
+    const int *meta = J.meta[blockIdx.y];
+    const int begin = meta[1], end = meta[2], qp = J.lfq[blockIdx.y];
+    for (int k = begin + (int) blockIdx.x * DSVCU_NTH + DSVCU_TID; k < end; k += (int) gridDim.x * DSVCU_NTH) {
+        q_dequant_ll_one(Q, qp, Q.syms[k]);
+    }
+    if (blockIdx.x == 0 && DSVCU_TID == 0) {
+        Q.coefs[0] = meta[6]; /* dst->data[0] = LL (hzcc.c:634); no symbol sits at position 0 */
+    }
+}
+
+DSVCU_KERNEL void __launch_bounds__(256)
+k_dequant_hf_m(DequantJob J, int wave)
+{
+    const QuantLevel &Q = J.Q[blockIdx.y];
+    const int *meta = J.meta[blockIdx.y];
+    const int begin = meta[2 + Q.l], end = meta[3 + Q.l];
+    for (int k = begin + (int) blockIdx.x * DSVCU_NTH + DSVCU_TID; k < end; k += (int) gridDim.x * DSVCU_NTH) {
+        q_dequant_hf_one(Q, wave, Q.syms[k]);
     }
 }
 

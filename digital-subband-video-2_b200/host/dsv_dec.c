@@ -14,8 +14,49 @@
  */
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
+#include <time.h>
 #include "dsv_host.h"
 #include "../../include/dsv_decoder.h"
+
+/* optional thread-CPU phase accounting (DSV_PROFILE=1): where one decoder instance's host
+ * thread spends its time, summed over pictures and printed by dsv_dec_free */
+static int g_prof = -1;
+enum { DP_SIDE, DP_PLANES, DP_QUEUE, DP_TAIL, DP_PREPARSE, DP_N };
+static const char *dp_name[DP_N] = { "header + side information", "coefficient planes (parse)",
+                                     "queue device work", "download + wait",
+                                     "batch entropy decode on the device (gather + wait)" };
+static double
+cpu_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+static double
+wall_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+#define DPROF_START(s)                \
+    do {                              \
+        if (g_prof > 0) {             \
+            (s)->ph_t0 = cpu_ms();    \
+            (s)->ph_w0 = wall_ms();   \
+        }                             \
+    } while (0)
+#define DPROF(s, ph)                              \
+    do {                                          \
+        if (g_prof > 0) {                         \
+            double t_ = cpu_ms(), w_ = wall_ms(); \
+            (s)->ph_ms[ph] += t_ - (s)->ph_t0;    \
+            (s)->ph_wall[ph] += w_ - (s)->ph_w0;  \
+            (s)->ph_t0 = t_;                      \
+            (s)->ph_w0 = w_;                      \
+        }                                         \
+    } while (0)
 
 typedef struct {
     DSV_IMAGE img; /* first member: DSV_DECODER.ref points at this object */
@@ -29,6 +70,19 @@ typedef struct {
     uint8_t *blockdata;
     DSV_MV *mvs;
     int nblk_cap;
+    double ph_ms[DP_N], ph_t0, ph_wall[DP_N], ph_w0;
+    int ph_frames;
+    /* batches of pictures whose coefficient planes are entropy-decoded on the device ahead of
+     * time (dsv_dec_preparse), one per parse set of the context: first span of picture i in
+     * the batch, or -1 where the host parses */
+    struct {
+        int *first;
+        int n, cap;
+        int nspans;  /* planes handed to the device */
+        int cset;    /* the context's parse set they went to */
+        int pending; /* launched, result not looked at yet */
+    } pre[2];
+    int pre_last;
 } DEC_STATE;
 
 int dsv_get_thread_device(void);
@@ -56,10 +110,18 @@ dsv_dec_set_async(int on)
     tls_async = on;
 }
 
+static int preparse_collect(DEC_STATE *s, int set);
+
 int
 dsv_dec_flush(DSV_DECODER *d)
 {
     DEC_STATE *s = (DEC_STATE *) d->ref;
+    int set;
+    /* a batch of planes that was sent ahead and is not wanted any more */
+    for (set = 0; s && s->ctx && set < 2; set++) {
+        (void) preparse_collect(s, set);
+        s->pre[set].n = 0;
+    }
     if (s && s->ctx && dsvcu_sync(s->ctx)) {
         DSV_ERROR(("dsv_dec_flush: %s", dsvcu_last_error()));
         return -1;
@@ -67,11 +129,33 @@ dsv_dec_flush(DSV_DECODER *d)
     return 0;
 }
 
+/* set by the whole-stream drivers before dsv_dec: the packet is picture `idx` of the batch
+ * that dsv_dec_preparse put into `set` (idx -1: parse the planes on the host) */
+static __thread int tls_parsed = -1, tls_parsed_set = 0;
+
+void
+dsv_dec_use_parsed(int set, int idx)
+{
+    tls_parsed_set = set & 1;
+    tls_parsed = idx;
+}
+
 static void
 state_free(DEC_STATE *s)
 {
     if (!s) {
         return;
+    }
+    if (g_prof > 0 && s->ph_frames) {
+        int i;
+        char line[1024];
+        int at = snprintf(line, sizeof(line), "[dsv_dec profile] %d pictures, host thread CPU (wall) ms per picture:",
+                          s->ph_frames);
+        for (i = 0; i < DP_N && at < (int) sizeof(line) - 96; i++) {
+            at += snprintf(line + at, sizeof(line) - (size_t) at, " %s %.3f (%.3f);", dp_name[i],
+                           s->ph_ms[i] / s->ph_frames, s->ph_wall[i] / s->ph_frames);
+        }
+        fprintf(stderr, "%s\n", line);
     }
     if (s->ctx) {
         dsvcu_sync(s->ctx);
@@ -83,6 +167,8 @@ state_free(DEC_STATE *s)
     }
     free(s->blockdata);
     free(s->mvs);
+    free(s->pre[0].first);
+    free(s->pre[1].first);
     free(s);
 }
 
@@ -456,8 +542,15 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
     DSV_FRAME *host;
     DSV_FNUM fno;
     int stats[DSV_MAX_STAT];
-    int i, nblk, quant, is_ref, do_filter, isP, good_planes = 0;
+    int i, nblk, quant, is_ref, do_filter, isP, good_planes = 0, on_device = 0;
 
+    if (g_prof < 0) {
+        g_prof = getenv("DSV_PROFILE") ? atoi(getenv("DSV_PROFILE")) : 0;
+    }
+    DPROF_START(s);
+    if (g_prof > 0) {
+        s->ph_frames++;
+    }
     memset(p, 0, sizeof(*p));
     p->vidmeta = meta;
     p->has_ref = DSV_PT_HAS_REF(pkt_type);
@@ -533,17 +626,34 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
         /* the previous picture may still be reading the staging set just used */
         GPU(dsvcu_staging_flip(s->ctx));
     }
+    DPROF(s, DP_SIDE);
     GPU(dsvcu_set_side(s->ctx, s->blockdata, isP ? s->mvs : NULL, nblk));
+    DPROF(s, DP_QUEUE);
 
     /* intra pictures are reconstructed straight into the output picture;
      * inter pictures into the residual frame, then predicted + added */
     dst = s->pic[s->cur];
     ref = s->pic[s->cur ^ 1];
-    for (i = 0; i < 3; i++) {
+    if (tls_parsed >= 0 && tls_parsed < s->pre[tls_parsed_set].n && s->pre[tls_parsed_set].first[tls_parsed] >= 0) {
+        if (preparse_collect(s, tls_parsed_set)) {
+            return DSV_DEC_ERROR;
+        }
+        DPROF(s, DP_PREPARSE);
+    }
+    if (tls_parsed >= 0 && tls_parsed < s->pre[tls_parsed_set].n && s->pre[tls_parsed_set].first[tls_parsed] >= 0) {
+        /* the symbols of all three planes are already on the device */
+        GPU(dsvcu_dequant_parsed(s->ctx, s->coefs, quant, &fm, s->pre[tls_parsed_set].cset,
+                                 s->pre[tls_parsed_set].first[tls_parsed]));
+        DPROF(s, DP_QUEUE);
+        good_planes = 7;
+        on_device = 1;
+    }
+    for (i = 0; i < 3 && !on_device; i++) {
         int cap, nsym, lstart[5], dc, cw, ch;
         dsvcu_symbol *st = dsvcu_symbol_staging(s->ctx, i, &cap);
         dsvcu_coefs_plane_dims(s->coefs, i, &cw, &ch);
         nsym = dsv_hzcc_read_plane(br, st, cap - 1, cw, ch, lstart, &dc);
+        DPROF(s, DP_PLANES);
         if (nsym < 0) {
             DSV_ERROR(("decoding error in plane %d", i));
             /* the reference leaves a fresh (zeroed) residual plane here */
@@ -551,6 +661,7 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
             continue;
         }
         GPU(dsvcu_dequant_plane(s->ctx, s->coefs, i, quant, &fm, nsym, lstart, dc));
+        DPROF(s, DP_QUEUE);
         good_planes |= 1 << i;
     }
     /* the planes that decoded go through the inverse transform together */
@@ -570,6 +681,7 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
         GPU(dsvcu_extend_frame(s->ctx, dst, 0));
     }
 
+    DPROF(s, DP_QUEUE);
     if (tls_direct_out) {
         host = dsv_load_planar_frame(meta->subsamp, tls_direct_out, meta->width, meta->height);
     } else {
@@ -581,6 +693,7 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
     if (!(tls_async && tls_direct_out) || d->draw_info) {
         GPU(dsvcu_sync(s->ctx)); /* (the overlay below is drawn into the finished host copy) */
     }
+    DPROF(s, DP_TAIL);
     if (is_ref) {
         s->cur ^= 1;
         s->have_ref = 1;
@@ -590,6 +703,186 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
     }
     *out = host;
     return DSV_DEC_OK;
+}
+
+/* Where the three coefficient planes of a picture packet start, found without decoding
+ * anything: every sub-stream in front of them is length-prefixed.  Mirrors the reading order
+ * of decode_picture; returns -1 for anything unusual (the packet is then parsed the normal
+ * way, which knows what to do with damaged input). */
+static int
+locate_planes(const DEC_STATE *s, const uint8_t *pkt, size_t len, dsvcu_plane_bits out[3])
+{
+    DSV_BITRD br;
+    const uint8_t *p;
+    size_t n, at;
+    int type, isP, i, nsub;
+
+    if (len < 64) {
+        return -1;
+    }
+    /* the reader looks ahead 8 bytes; nothing in front of the planes may come that close to the end */
+    dsv_br_init(&br, pkt, len - 8);
+    type = read_packet_hdr(&br);
+    if (type < 0 || !DSV_PT_IS_PIC(type)) {
+        return -1;
+    }
+    isP = DSV_PT_HAS_REF(type);
+    dsv_br_align(&br);
+    (void) dsv_br_bits(&br, 32);
+    dsv_br_align(&br);
+    if (dsv_br_ueg(&br) > 2 || dsv_br_ueg(&br) > 2) {
+        return -1;
+    }
+    dsv_br_align(&br);
+    (void) dsv_br_bits(&br, 3); /* stable + (maintain, ringing | mode, eprm) */
+    (void) dsv_br_bit(&br);     /* do_filter */
+    (void) dsv_br_bits(&br, DSV_MAX_QP_BITS);
+    if (dsv_br_bit(&br)) {
+        (void) dsv_br_bits(&br, 15);
+    }
+    dsv_br_align(&br);
+    /* stability; then motion (five sub-streams) or ringing + maintain */
+    nsub = 1 + (isP ? DSV_SUB_NSUB : 2);
+    for (i = 0; i < nsub; i++) {
+        if (!isP || i < 2) {
+            dsv_br_align(&br);
+        }
+        if (open_substream(&br, &p, &n)) {
+            return -1;
+        }
+    }
+    dsv_br_align(&br);
+    at = dsv_br_byte(&br);
+    for (i = 0; i < 3; i++) {
+        size_t plen;
+        int cw, ch;
+        if (at + 4 > len) {
+            return -1;
+        }
+        plen = ((size_t) pkt[at] << 24) | ((size_t) pkt[at + 1] << 16) | ((size_t) pkt[at + 2] << 8) | pkt[at + 3];
+        if (plen == 0 || plen > len - at - 4) {
+            return -1;
+        }
+        dsvcu_coefs_plane_dims(s->coefs, i, &cw, &ch);
+        out[i].bits = pkt + at;
+        out[i].len = (uint32_t) (4 + plen);
+        out[i].w = cw;
+        out[i].h = ch;
+        at += 4 + plen;
+    }
+    return 0;
+}
+
+/* Pictures above this size keep their planes on the host: a plane is one serial chain, which
+ * a device thread walks an order of magnitude slower than a core does.  What matters on the
+ * device is that the chains of a batch run side by side and beside the reconstruction of the
+ * pictures in front of them; one very long chain (the intra picture of a GOP) would only
+ * make everything behind it wait. */
+#define PREPARSE_MAX_PICTURE_BYTES (160 * 1024)
+
+/* Entropy-decode the coefficient planes of the next `n` picture packets on the device, in
+ * one launch on the context's parse stream (they carry no coder state from one to the
+ * next).  Does not wait: the result is collected when the first picture of the batch that
+ * needs it is decoded.  The driver announces picture i of the batch with
+ * dsv_dec_use_parsed(set, i) before handing its packet to dsv_dec; pictures whose planes were
+ * not located, are too long or turn out not to be well-formed are parsed on the host as usual.
+ * Needs the metadata packet to have been seen.  Returns the set (0 / 1) the batch occupies,
+ * -1 on a device error (nothing is pending then). */
+int
+dsv_dec_preparse(DSV_DECODER *d, const uint8_t *const *pkt, const size_t *len, int n)
+{
+    DEC_STATE *s;
+    dsvcu_plane_bits *pl;
+    int i, m = 0, set;
+
+    if (!d->got_metadata || n <= 0) {
+        return -1;
+    }
+    s = state_get(d);
+    if (!s) {
+        return -1;
+    }
+    if (g_prof < 0) {
+        g_prof = getenv("DSV_PROFILE") ? atoi(getenv("DSV_PROFILE")) : 0;
+    }
+    DPROF_START(s);
+    pl = malloc((size_t) n * 3 * sizeof(*pl));
+    if (!pl) {
+        return -1;
+    }
+    /* the slot that is not waiting for its result; failing that the older one */
+    set = s->pre[0].pending ? 1 : (s->pre[1].pending ? 0 : (s->pre_last ^ 1));
+    if (s->pre[set].pending) {
+        free(pl);
+        return -1;
+    }
+    s->pre[set].n = 0;
+    if (n > s->pre[set].cap) {
+        free(s->pre[set].first);
+        s->pre[set].first = malloc((size_t) n * sizeof(int));
+        s->pre[set].cap = s->pre[set].first ? n : 0;
+        if (!s->pre[set].first) {
+            free(pl);
+            return -1;
+        }
+    }
+    for (i = 0; i < n; i++) {
+        s->pre[set].first[i] = -1;
+        if (len[i] <= PREPARSE_MAX_PICTURE_BYTES && locate_planes(s, pkt[i], len[i], pl + m) == 0) {
+            s->pre[set].first[i] = m;
+            m += 3;
+        }
+    }
+    s->pre[set].nspans = m;
+    if (m) {
+        const int got = dsvcu_parse_begin(s->ctx, pl, m);
+        if (got < 0) {
+            DSV_ERROR(("dsv_dec_preparse: %s", dsvcu_last_error()));
+            free(pl);
+            return -1;
+        }
+        s->pre[set].cset = got;
+        s->pre[set].pending = 1;
+    }
+    s->pre[set].n = n;
+    s->pre_last = set;
+    free(pl);
+    DPROF(s, DP_PREPARSE);
+    return set;
+}
+
+/* is a batch still on its way (begun, not collected)? */
+int
+dsv_dec_preparse_pending(DSV_DECODER *d, int set)
+{
+    DEC_STATE *s = d->ref ? (DEC_STATE *) d->ref : NULL;
+    return s ? s->pre[set & 1].pending : 0;
+}
+
+/* wait for the batch in `set` and strike the pictures that the device parser refused */
+static int
+preparse_collect(DEC_STATE *s, int set)
+{
+    int *ok, i;
+    if (!s->pre[set].pending) {
+        return 0;
+    }
+    s->pre[set].pending = 0;
+    ok = malloc((size_t) s->pre[set].nspans * sizeof(int));
+    if (!ok || dsvcu_parse_end(s->ctx, s->pre[set].cset, ok)) {
+        DSV_ERROR(("dsv_dec_preparse: %s", ok ? dsvcu_last_error() : "out of memory"));
+        free(ok);
+        s->pre[set].n = 0;
+        return -1;
+    }
+    for (i = 0; i < s->pre[set].n; i++) {
+        const int f = s->pre[set].first[i];
+        if (f >= 0 && !(ok[f] && ok[f + 1] && ok[f + 2])) {
+            s->pre[set].first[i] = -1;
+        }
+    }
+    free(ok);
+    return 0;
 }
 
 int

@@ -13,9 +13,24 @@
  * value = NEG in the LL part, adaptive Rice with damping 3+level elsewhere.
  */
 #include <string.h>
+#include <pthread.h>
 #include "dsv_host.h"
 #include <stdlib.h>
 #include "dsv_bits_inl.h"
+#include "../csrc/hz_table.h"
+
+/* joint (value, next run) prefix table, see csrc/hz_table.h: 40 KB, built on first use */
+static uint32_t hz_tab[HZT_ROWS * HZT_SIZE];
+static pthread_once_t hz_tab_once = PTHREAD_ONCE_INIT;
+
+static void
+hz_tab_build(void)
+{
+    int i;
+    for (i = 0; i < HZT_ROWS * HZT_SIZE; i++) {
+        hz_tab[i] = hzt_entry((uint32_t) i & (HZT_SIZE - 1), i >> HZT_BITS);
+    }
+}
 
 void
 dsv_hzcc_write_plane(DSV_BITWR *bw, const dsvcu_symbol *syms, int nsyms, int dc, int w, int h)
@@ -103,6 +118,7 @@ dsv_hzcc_read_plane(DSV_BITRD *br, dsvcu_symbol *syms, int cap, int w, int h, in
     int runs, truncated = 0;
     unsigned cur = 0, run;
 
+    pthread_once(&hz_tab_once, hz_tab_build);
     total = dsvcu_scan_layout(w, h, part);
     for (i = 0; i < 5; i++) {
         level_start[i] = 0;
@@ -127,9 +143,11 @@ dsv_hzcc_read_plane(DSV_BITRD *br, dsvcu_symbol *syms, int cap, int w, int h, in
      * the declared plane length is dropped together with everything after it */
     {
         DSV_FR r;
+        size_t lenbits;
         r.buf = br->buf;
         r.len = br->len;
         r.pos = br->pos;
+        lenbits = r.len * 8;
         run = (runs-- > 0) ? dsv_fr_ueg(&r) : UINT_MAX;
         while (run != UINT_MAX) {
             unsigned pos = cur + run;
@@ -141,8 +159,33 @@ dsv_hzcc_read_plane(DSV_BITRD *br, dsvcu_symbol *syms, int cap, int w, int h, in
                 l++;
                 level_start[l + 1] = n;
             }
-            v = (l < 0) ? dsv_fr_neg(&r) : dsv_fr_nrice(&r, &vk, 3 + l);
-            run = (runs-- > 0) ? dsv_fr_ueg(&r) : UINT_MAX;
+            /* value of this pair + run of the next: one look-up where both codes fit into
+             * HZT_BITS bits, the general readers otherwise (same bits, same result) */
+            {
+                const int row = l < 0 ? HZT_ROW_LL : vk >> (3 + l);
+                uint32_t e = 0;
+                /* (the general readers see zeros once a code STARTS behind the end of the buffer:
+                 * the table is only asked while both codes start inside it) */
+                if (runs > 0 && (l < 0 || row < HZT_KMAX) && r.pos + HZT_BITS < lenbits) {
+                    e = hz_tab[row * HZT_SIZE + (uint32_t) (dsv_fr_peek(&r) >> (64 - HZT_BITS))];
+                }
+                if (HZT_LEN(e)) {
+                    r.pos += (size_t) HZT_LEN(e);
+                    v = HZT_VAL(e);
+                    run = HZT_RUN(e);
+                    runs--;
+                    if (l >= 0) {
+                        if (HZT_QNZ(e)) {
+                            vk++;
+                        } else if (vk > 0) {
+                            vk--;
+                        }
+                    }
+                } else {
+                    v = (l < 0) ? dsv_fr_neg(&r) : dsv_fr_nrice(&r, &vk, 3 + l);
+                    run = (runs-- > 0) ? dsv_fr_ueg(&r) : UINT_MAX;
+                }
+            }
             if ((r.pos >> 3) >= limit) {
                 truncated = 1;
                 break;

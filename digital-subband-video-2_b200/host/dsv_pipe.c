@@ -23,6 +23,9 @@ void dsv_enc_recycle(DSV_ENCODER *from, DSV_ENCODER *to);
 void dsv_dec_direct_output(uint8_t *dst);
 void dsv_dec_set_async(int on);
 int dsv_dec_flush(DSV_DECODER *d);
+int dsv_dec_preparse(DSV_DECODER *d, const uint8_t *const *pkt, const size_t *len, int n);
+void dsv_dec_use_parsed(int set, int idx);
+int dsv_dec_preparse_pending(DSV_DECODER *d, int set);
 
 static __thread int tls_device = -1;
 
@@ -596,38 +599,104 @@ probe_meta(const uint8_t *d, const PKT *pk, int npk, DSV_META *meta)
     return have ? 0 : -1;
 }
 
+/* pictures per device-side entropy decode (dsv_dec_preparse): a closed GOP or two */
+#define PREPARSE_MAX_PICS 64
+#define PREPARSE_MAX_BYTES ((size_t) 24 << 20)
+
+static volatile int g_device_entropy = 1;
+
+int
+dsv_set_device_entropy_decode(int on)
+{
+    const int was = g_device_entropy;
+    g_device_entropy = !!on;
+    return was;
+}
+
+typedef struct {
+    int begin, end; /* packets [begin, end), all of them pictures */
+    int slot;       /* where dsv_dec_preparse put them; -1: the host parses */
+} BATCH;
+
+/* hand the coefficient planes of the pictures from packet `from` on (up to the next packet
+ * that is not a picture) to the device parser */
+static void
+batch_begin(DSV_DECODER *dec, const uint8_t *d, const PKT *pk, int from, int last, BATCH *b)
+{
+    const uint8_t *bp[PREPARSE_MAX_PICS];
+    size_t bl[PREPARSE_MAX_PICS], bytes = 0;
+    int j, n = 0;
+    for (j = from; j < last && n < PREPARSE_MAX_PICS && DSV_PT_IS_PIC(pk[j].type); j++) {
+        if (n && bytes + pk[j].len > PREPARSE_MAX_BYTES) {
+            break;
+        }
+        bp[n] = d + pk[j].off;
+        bl[n] = pk[j].len;
+        bytes += pk[j].len;
+        n++;
+    }
+    b->begin = from;
+    b->end = j;
+    /* on a device error the host parser takes over (and will report it) */
+    b->slot = (dec->got_metadata && g_device_entropy) ? dsv_dec_preparse(dec, bp, bl, n) : -1;
+}
+
 /* decode packets [first, last) with `dec`; frames are written to dst one after
  * the other.  returns the number of frames written */
 static int
 decode_range(DSV_DECODER *dec, const uint8_t *d, const PKT *pk, int first, int last, uint8_t *dst, size_t fsz)
 {
-    int i, nfr = 0;
+    BATCH cur, nxt;
+    int i, nfr = 0, cur_k = 0, have_next = 0;
+    cur.begin = cur.end = first;
+    cur.slot = nxt.slot = -1;
     /* pictures are queued without waiting: parsing the next packet overlaps the device work */
     dsv_dec_set_async(1);
     for (i = first; i < last; i++) {
         DSV_BUF b;
         DSV_FRAME *fr = NULL;
         DSV_FNUM fn;
-        int code;
+        int code, is_pic = DSV_PT_IS_PIC(pk[i].type);
+        if (is_pic && i >= cur.end) {
+            if (have_next && nxt.begin == i) {
+                cur = nxt;
+            } else {
+                batch_begin(dec, d, pk, i, last, &cur);
+            }
+            have_next = 0;
+            cur_k = 0;
+        }
         dsv_mk_buf(&b, (int) pk[i].len);
         memcpy(b.data, d + pk[i].off, pk[i].len);
-        if (DSV_PT_IS_PIC(pk[i].type)) {
+        if (is_pic) {
             /* never arm a direct copy for a geometry other than the one dst was sized for */
             if (dec->got_metadata &&
                 frame_bytes(dec->vidmeta.width, dec->vidmeta.height, dec->vidmeta.subsamp) != fsz) {
                 DSV_ERROR(("picture packet with unexpected geometry: segment abandoned"));
+                dsv_buf_free(&b);
                 break;
             }
             dsv_dec_direct_output(dst + (size_t) nfr * fsz);
+            dsv_dec_use_parsed(cur.slot, cur.slot >= 0 ? cur_k : -1);
+            cur_k++;
         }
         code = dsv_dec(dec, &b, &fr, &fn);
         dsv_dec_direct_output(NULL);
+        dsv_dec_use_parsed(0, -1);
         if (code == DSV_DEC_EOS) {
             break;
         }
         if (code == DSV_DEC_OK && fr) {
             nfr++;
             dsv_frame_ref_dec(fr);
+        }
+        /* one batch ahead: as soon as the result of the current batch has been collected, the
+         * planes of the pictures behind it go to the device, to be parsed while the current
+         * ones are reconstructed */
+        if (is_pic && !have_next && cur.end < last && DSV_PT_IS_PIC(pk[cur.end].type) &&
+            (cur.slot < 0 || !dsv_dec_preparse_pending(dec, cur.slot))) {
+            batch_begin(dec, d, pk, cur.end, last, &nxt);
+            have_next = 1;
         }
     }
     dsv_dec_set_async(0);

@@ -117,6 +117,33 @@ dsvcu_symbol *dsvcu_symbol_staging(dsvcu_ctx *ctx, int plane, int *capacity);
 int dsvcu_staging_flip(dsvcu_ctx *ctx);
 int dsvcu_dequant_plane(dsvcu_ctx *ctx, dsvcu_coefs *c, int plane, int q, const dsvcu_fmeta *fm,
                         int nsyms, const int level_start[5], int dc);
+/* Entropy decode on the device: the bit-parsing half of dsv_decode_plane (reference
+ * hzcc.c:450-583, :585-649; codes of bs.c:96-137, :237-251) for a BATCH of planes -- typically
+ * the 3 x N planes of the N pictures of a closed GOP, which carry no entropy-coder state from
+ * one to the next.  pl[i].bits points at plane i's 32-bit length word, pl[i].len = 4 + that
+ * length, (w, h) = dsvcu_coefs_plane_dims.
+ *   dsvcu_parse_begin  gathers, uploads and launches on the context's parse stream (beside the
+ *                      work queued on its main stream) and returns the set (0 or 1) the batch
+ *                      occupies; at most two batches exist at a time, a set's symbols live
+ *                      until the set is begun again.
+ *   dsvcu_parse_end    waits for the batch.  ok[i] = 1: symbols are resident on the device;
+ *                      ok[i] = 0: not a well-formed plane, parse it on the host
+ *                      (dsvcu_dequant_plane) -- the host parser reproduces the reference's
+ *                      handling of damaged planes.
+ *   dsvcu_parse_planes both in one call; returns the set. */
+typedef struct {
+    const uint8_t *bits;
+    uint32_t len;
+    int w, h;
+} dsvcu_plane_bits;
+int dsvcu_parse_begin(dsvcu_ctx *ctx, const dsvcu_plane_bits *pl, int n);
+int dsvcu_parse_end(dsvcu_ctx *ctx, int set, int *ok);
+int dsvcu_parse_planes(dsvcu_ctx *ctx, const dsvcu_plane_bits *pl, int n, int *ok);
+/* symbols found in plane `span` of a collected batch, -1 if it was not ok */
+int dsvcu_parsed_count(dsvcu_ctx *ctx, int set, int span);
+/* the three planes of one picture, parsed as spans first_span .. first_span + 2 of a collected
+ * batch: zero-fill + de-quantise (hzcc.c:450-583) without the symbols leaving the device */
+int dsvcu_dequant_parsed(dsvcu_ctx *ctx, dsvcu_coefs *c, int q, const dsvcu_fmeta *fm, int set, int first_span);
 /* number of scan positions of a plane and the first scan position of each
  * HZCC part (LL, level 0, 1, 2, end) -- the host coder needs them */
 int dsvcu_scan_layout(int w, int h, int part_start[5]);

@@ -82,6 +82,13 @@ int dsv_pool_encode(dsv_pool *pool, const dsv_enc_opts *o, const uint8_t *yuv, i
 int dsv_pool_decode(dsv_pool *pool, const uint8_t *dsv, size_t len, uint8_t *dst, size_t dst_cap, int *nframes,
                     DSV_META *meta);
 
+/* Where the whole-stream decoders (dsv_pool_decode*, dsv_decode_*) entropy-decode the
+ * coefficient planes: 1 (default) = on the device, in batches of pictures one batch ahead of
+ * the reconstruction (csrc/k_hzcc.cuh; pictures above 160 KB and planes the device parser does
+ * not accept stay on the host); 0 = all of them on the host threads.  Same output either way.
+ * Process-wide; returns the previous setting. */
+int dsv_set_device_entropy_decode(int on);
+
 /* the same with the frames in pinned memory allocated by the call (dsv_pinned_free) */
 int dsv_pool_decode_alloc(dsv_pool *pool, const uint8_t *dsv, size_t len, uint8_t **yuv, size_t *yuv_len, int *nframes,
                           DSV_META *meta);

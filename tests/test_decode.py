@@ -39,3 +39,32 @@ def test_decode_emulated_kernels(case):
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_decode_gpu(case):
     _run(case, emu=False)
+
+
+def _whole_stream_vs_packetwise(emu):
+    """dsv_decode_sharded hands the coefficient planes to the device parser (k_hzcc_parse)
+    in batches of up to 64 pictures, one batch ahead of the reconstruction; dsv_dec() packet by
+    packet parses on the host.  Both against the reference decoder, on a segment of several
+    batches (150 pictures, one metadata packet) with intra pictures in the middle of a batch."""
+    w, h, n = 96, 64, 150
+    y4m = util.clip("manybatches", w, h, n, "420")
+    dsv = util.ref_encode(y4m, ["-qp=40", "-gop=35"], "ref")
+    data = open(dsv, "rb").read()
+    _, _, ref = util.read_y4m(util.ref_decode(dsv))
+    P = util.pkg()
+    meta, nfr, whole = P.decode_frames(data, emu=emu)
+    assert nfr == n
+    _, packetwise = P.decode_stream(data, emu=emu)
+    util.assert_same_frames(packetwise, ref, w, h)
+    assert whole == b"".join(b"".join(f) for f in packetwise)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+def test_whole_stream_device_parser_emulated():
+    util.ensure_emu()
+    _whole_stream_vs_packetwise(True)
+
+
+@pytest.mark.gpu
+def test_whole_stream_device_parser_gpu():
+    _whole_stream_vs_packetwise(False)

@@ -13,6 +13,7 @@ import ops
 import util
 from test_encops import GEOM, BIG, _frames, _cfg, _rand_blockdata, _mvs_for, _blockdata_from_mvs
 
+P = util.pkg()
 need_ref = pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
 ODDC = [("oddchroma", 354, 290, "420"), ("oddchroma2", 226, 150, "420")]  # chroma 177x145, 113x75
 
@@ -83,6 +84,7 @@ def _dequant(geom, emu, isP, q):
         D.set_mvs(mvs)
         fm = cfg.fmeta()
         k = D.coefs()
+        wants, counts = [], []
         for p in range(3):
             deq, bits = planes[p]
             cw, ch = D.coef_dims(k, p)
@@ -104,6 +106,57 @@ def _dequant(geom, emu, isP, q):
             d = np.nonzero(got != want)[0]
             assert len(d) == 0, "plane %d: %d coefficients differ, first at %d (x=%d y=%d) got %d want %d" % (
                 p, len(d), d[0], d[0] % cw, d[0] // cw, got[d[0]], want[d[0]])
+            wants.append(want)
+            counts.append(n)
+        # the same bytes through the device parser (k_hzcc_parse): a batch of two "pictures"
+        # (the three planes twice), de-quantised without the symbols leaving the device
+        keep = [ops._buf(planes[p][1]) for p in range(3)]
+        pl = (P.DSVCU_PLANE_BITS * 6)()
+        for i in range(6):
+            cw, ch = D.coef_dims(k, i % 3)
+            pl[i].bits = C.cast(keep[i % 3], C.c_void_p)
+            pl[i].len = len(planes[i % 3][1])
+            pl[i].w, pl[i].h = cw, ch
+        okv = (C.c_int * 6)()
+        # two batches in flight at once (the decoder parses one batch ahead): the first one
+        # holds the planes in reverse order
+        plr = (P.DSVCU_PLANE_BITS * 3)()
+        for i in range(3):
+            plr[i].bits, plr[i].len, plr[i].w, plr[i].h = pl[2 - i].bits, pl[2 - i].len, pl[2 - i].w, pl[2 - i].h
+        set_r = lib.dsvcu_parse_begin(D.ctx, plr, 3)
+        set_f = lib.dsvcu_parse_begin(D.ctx, pl, 6)
+        assert sorted((set_r, set_f)) == [0, 1], lib.dsvcu_last_error()
+        assert lib.dsvcu_parse_begin(D.ctx, pl, 6) < 0  # a third one has nowhere to go
+        okr = (C.c_int * 3)()
+        D.ck(lib.dsvcu_parse_end(D.ctx, set_r, okr))
+        D.ck(lib.dsvcu_parse_end(D.ctx, set_f, okv))
+        assert list(okv) == [1] * 6 and list(okr) == [1] * 3
+        assert [lib.dsvcu_parsed_count(D.ctx, set_f, i) for i in range(6)] == counts * 2
+        assert [lib.dsvcu_parsed_count(D.ctx, set_r, i) for i in range(3)] == counts[::-1]
+        for first in (3, 0):
+            D.ck(lib.dsvcu_dequant_parsed(D.ctx, k, q, C.byref(fm), set_f, first))
+            for p in range(3):
+                cw, ch = D.coef_dims(k, p)
+                got = D.coefs_download(k, p).reshape(-1)
+                d = np.nonzero(got != wants[p])[0]
+                assert len(d) == 0, "device-parsed plane %d: %d coefficients differ, first at %d got %d want %d" % (
+                    p, len(d), d[0], got[d[0]], wants[p][d[0]])
+        if D.coef_dims(k, 0) != D.coef_dims(k, 2):  # planes of another geometry are refused
+            assert lib.dsvcu_dequant_parsed(D.ctx, k, q, C.byref(fm), set_r, 0) != 0
+        # damaged planes are handed back to the host parser: cut short, end marker gone, length word wrong
+        bits = planes[0][1]
+        cw, ch = D.coef_dims(k, 0)
+        bad = [bits[:len(bits) // 2], bits[:-1] + b"\x54", bits[:3] + bytes([bits[3] ^ 1]) + bits[4:],
+               bits[:12] + bytes(len(bits) - 12)]
+        keep2 = [ops._buf(b) for b in bad]
+        pl2 = (P.DSVCU_PLANE_BITS * len(bad))()
+        for i, b in enumerate(bad):
+            pl2[i].bits = C.cast(keep2[i], C.c_void_p)
+            pl2[i].len = len(b)
+            pl2[i].w, pl2[i].h = cw, ch
+        ok2 = (C.c_int * len(bad))()
+        assert lib.dsvcu_parse_planes(D.ctx, pl2, len(bad), ok2) >= 0, lib.dsvcu_last_error()
+        assert list(ok2) == [0] * len(bad)
     finally:
         D.close()
 
@@ -246,3 +299,82 @@ def test_intra_filter_gpu(geom, q):
 @pytest.mark.parametrize("geom", GEOM + ODDC + BIG, ids=[g[0] for g in GEOM + ODDC + BIG])
 def test_extend_and_pyramid_gpu(geom):
     _extend_and_pyramid(geom, False)
+
+
+def _parser_fuzz(emu, rounds, w=96, h=64):
+    """Random symbol lists of every flavour (dense / sparse, tiny / huge magnitudes, so that the
+    Rice parameter wanders through and beyond the rows of the prefix table, runs longer than the
+    table knows) written by the host coder; the device parser (k_hzcc_parse) and the host parser
+    must put the same coefficients into the planes (lossless de-quantiser: coefficient = value)."""
+    cfg = _cfg(w, h, "444", isP=0, fnum=0, lossless=1)
+    D = ops.Dev(cfg, emu)
+    lib = D.lib
+    rng = np.random.default_rng(1234)
+    try:
+        fm = cfg.fmeta()
+        assert fm.lossless == 1
+        k = D.coefs()
+        cw, ch = D.coef_dims(k, 0)
+        part = (C.c_int * 5)()
+        total = lib.dsvcu_scan_layout(cw, ch, part)
+        for rnd in range(rounds):
+            blobs, syms_all = [], []
+            for p in range(3):
+                while True:
+                    density = [0.002, 0.05, 0.4, 0.95][int(rng.integers(0, 4))]
+                    npos = max(1, int(total * density))
+                    pos = np.sort(rng.choice(np.arange(1, total), size=min(npos, total - 1), replace=False)).astype(np.uint32)
+                    scale = [1, 3, 40, 300, 3000][int(rng.integers(0, 5))]
+                    mag = 1 + np.floor(rng.exponential(scale, size=len(pos))).astype(np.int64)
+                    val = (mag * rng.choice([-1, 1], size=len(pos))).astype(np.int32)
+                    if rnd % 3 == 0 and len(pos) > 4:   # a stretch of small values between large ones
+                        val[len(val) // 3:len(val) // 2] = np.sign(val[len(val) // 3:len(val) // 2])
+                    sy = np.zeros(len(pos), dtype=[("pos", np.uint32), ("v", np.int32)])
+                    sy["pos"], sy["v"] = pos, val
+                    dc = int(rng.integers(-500, 500))
+                    out = (C.c_uint8 * (len(pos) * 600 + 4096))()
+                    n = lib.dsv_hzcc_pack_plane(sy.ctypes.data_as(C.c_void_p), len(sy), dc, cw, ch, out, len(out))
+                    assert n > 0
+                    if n - 4 < cw * ch * 8:   # (longer planes are refused by every parser: hzcc.c:600)
+                        break
+                blobs.append(bytes(out[:n]))
+                syms_all.append((sy, dc))
+            keep = [ops._buf(b) for b in blobs]
+            pl = (P.DSVCU_PLANE_BITS * 3)()
+            for i in range(3):
+                pl[i].bits = C.cast(keep[i], C.c_void_p)
+                pl[i].len = len(blobs[i])
+                pl[i].w, pl[i].h = cw, ch
+            okv = (C.c_int * 3)()
+            st = lib.dsvcu_parse_planes(D.ctx, pl, 3, okv)
+            assert st >= 0 and list(okv) == [1, 1, 1], (rnd, list(okv))
+            assert [lib.dsvcu_parsed_count(D.ctx, st, i) for i in range(3)] == [len(s[0]) for s in syms_all]
+            D.ck(lib.dsvcu_dequant_parsed(D.ctx, k, 60, C.byref(fm), st, 0))
+            got = [D.coefs_download(k, p).reshape(-1).copy() for p in range(3)]
+            for p in range(3):
+                cap = C.c_int()
+                stg = lib.dsvcu_symbol_staging(D.ctx, p, C.byref(cap))
+                lstart = (C.c_int * 5)()
+                dcv = C.c_int()
+                n = lib.dsv_hzcc_unpack_plane(ops._buf(blobs[p]), len(blobs[p]), stg, cap.value - 1, cw, ch, lstart, C.byref(dcv))
+                assert n == len(syms_all[p][0]) and dcv.value == syms_all[p][1]
+                host_syms = np.ctypeslib.as_array(C.cast(stg, C.POINTER(C.c_int32)), shape=(n, 2)).copy()
+                assert (host_syms[:, 0].astype(np.uint32) == syms_all[p][0]["pos"]).all()
+                assert (host_syms[:, 1] == syms_all[p][0]["v"]).all()
+                D.ck(lib.dsvcu_dequant_plane(D.ctx, k, p, 60, C.byref(fm), n, lstart, dcv.value))
+                want = D.coefs_download(k, p).reshape(-1)
+                d = np.nonzero(got[p] != want)[0]
+                assert len(d) == 0, "round %d plane %d: %d coefficients differ, first at %d got %d want %d" % (
+                    rnd, p, len(d), d[0], got[p][d[0]], want[d[0]])
+    finally:
+        D.close()
+
+
+def test_device_parser_fuzz_emulated():
+    util.ensure_emu()
+    _parser_fuzz(True, 12)
+
+
+@pytest.mark.gpu
+def test_device_parser_fuzz_gpu():
+    _parser_fuzz(False, 12)

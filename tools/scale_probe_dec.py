@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""decode throughput vs host threads"""
+"""decode throughput vs host threads.  usage: scale_probe_dec.py THREADS[,THREADS..] [MODES]
+MODES: 1 = entropy decode on the device (default), 0 = on the host, e.g. 0,1"""
 import ctypes as C, os, sys, time
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
@@ -27,7 +28,9 @@ print("encode 32 threads: %.1f fps" % (nfr / (time.perf_counter() - t0)), flush=
 dsv = (C.c_uint8 * outn.value).from_buffer_copy(C.string_at(out, outn.value))
 lib.dsv_pool_destroy(pool)
 nf, meta = C.c_int(), P.DSV_META()
-for threads in [int(t) for t in sys.argv[1].split(",")]:
+modes = [int(m) for m in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1]
+for threads, mode in [(int(t), m) for t in sys.argv[1].split(",") for m in modes]:
+    lib.dsv_set_device_entropy_decode(mode)
     pool = lib.dsv_pool_create(threads, devs, 1)
     for rep in range(3):
         t0 = time.perf_counter()
@@ -38,5 +41,5 @@ for threads in [int(t) for t in sys.argv[1].split(",")]:
         t0 = time.perf_counter()
         lib.dsv_pool_decode(pool, dsv, len(dsv), C.c_void_p(host.data_ptr()), nfr * bench.FRAME_BYTES, C.byref(nf), C.byref(meta))
         dth = time.perf_counter() - t0
-    print("threads %2d: decode %7.1f fps to HBM, %7.1f fps to pinned host (%.2f ms/frame/stream)" % (threads, nfr / dt, nfr / dth, 1000 * dt * threads / nfr), flush=True)
+    print("threads %2d, entropy decode on the %s: decode %7.1f fps to HBM, %7.1f fps to pinned host (%.2f ms/frame/stream)" % (threads, "device" if mode else "host", nfr / dt, nfr / dth, 1000 * dt * threads / nfr), flush=True)
     lib.dsv_pool_destroy(pool)
