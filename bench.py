@@ -575,6 +575,10 @@ def run_own(args):
     threads = args.threads or max(2, min(32, 8 * cores // max(1, world)))
     chunks = args.chunks or threads
     nframes = chunks * GOP
+    # where the decoder parses its coefficient planes (dsv_session.h): the ranks of one box share
+    # its cores, which the library cannot see from inside one process
+    dev_entropy = 1 if threads * world > cores else 0
+    lib.dsv_set_device_entropy_decode(dev_entropy)
 
     distinct = DISTINCT
     # rank 0 generates (and caches on tmpfs) the synthetic chunks, the others read the cache
@@ -752,7 +756,8 @@ def run_own(args):
         "e2e": {"value": round(e2e, 3), "unit": "frames/s", "h2d_bytes_per_step": nframes * FRAME_BYTES,
                 "d2h_bytes_per_step": int(stream_bytes)},
         "decode": {"value": round(dvalue, 3), "e2e": round(de2e, 3), "unit": "frames/s",
-                   "d2h_bytes_per_step_e2e": nframes * FRAME_BYTES, "first_frame_checksum": chk},
+                   "d2h_bytes_per_step_e2e": nframes * FRAME_BYTES, "first_frame_checksum": chk,
+                   "entropy_decode": "device (k_hzcc_parse; intra pictures on the host)" if dev_entropy else "host threads"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "parity": parity,

@@ -325,9 +325,12 @@ def encode_frames(opts, yuv, nframes, emu=False, exhausted=True, chunk=0, thread
     return _take(lib, out, n)
 
 
-def decode_frames(data, emu=False, threads=1, devices=None):
-    """Decode .dsv bytes -> (DSV_META, nframes, packed planar frames bytes)."""
+def decode_frames(data, emu=False, threads=1, devices=None, device_entropy=1):
+    """Decode .dsv bytes -> (DSV_META, nframes, packed planar frames bytes).
+    device_entropy: dsv_set_device_entropy_decode() for this call (1 = coefficient planes are
+    entropy-decoded by k_hzcc_parse, 0 = by the host threads, -1 = the library decides)."""
     lib = load(emu)
+    lib.dsv_set_device_entropy_decode(device_entropy)
     out, n, nfr, meta = C.c_void_p(), C.c_size_t(), C.c_int(), DSV_META()
     devs = devices or [0]
     arr = (C.c_int * len(devs))(*devs)

@@ -78,16 +78,6 @@ struct HzRd {
     uint32_t nxt;
 };
 
-DSVCU_DEV uint32_t
-hz_be32(const uint8_t *p)
-{
-#ifndef DSVCU_EMU
-    return __byte_perm(*(const uint32_t *) p, 0, 0x0123);
-#else
-    return ((uint32_t) p[0] << 24) | ((uint32_t) p[1] << 16) | ((uint32_t) p[2] << 8) | p[3];
-#endif
-}
-
 DSVCU_DEV int
 hz_clz32(uint32_t v)
 {
@@ -98,10 +88,22 @@ hz_clz32(uint32_t v)
 #endif
 }
 
+/* the raw (little-endian as loaded) word at byte `at`, a multiple of 4; the batch buffer is
+ * padded, reads behind the plane see zeros */
 DSVCU_DEV uint32_t
-hz_word(const HzRd &r, uint32_t at) /* `at` is a multiple of 4; the batch buffer is padded */
+hz_raw(const HzRd &r, uint32_t at)
 {
-    return at < r.end ? hz_be32(r.buf + at) : 0u;
+    return at < r.end ? *(const uint32_t *) (r.buf + at) : 0u;
+}
+
+DSVCU_DEV uint32_t
+hz_swap(uint32_t w)
+{
+#ifndef DSVCU_EMU
+    return __byte_perm(w, 0, 0x0123);
+#else
+    return __builtin_bswap32(w);
+#endif
 }
 
 DSVCU_DEV void
@@ -109,25 +111,24 @@ hz_open(HzRd &r, const uint8_t *buf, uint32_t len)
 {
     r.buf = buf;
     r.end = len;
-    r.win = ((uint64_t) hz_word(r, 0) << 32) | hz_word(r, 4);
+    r.win = ((uint64_t) hz_swap(hz_raw(r, 0)) << 32) | hz_swap(hz_raw(r, 4));
     r.n = 64;
     r.nb = 8;
-    r.nxt = hz_word(r, 8);
+    r.nxt = hz_raw(r, 8);
 }
 
-/* at least 32 valid bits in the window (written without a branch: the refill is a handful of
- * predicated instructions, a branch costs a reconvergence point on the dependent chain) */
+/* at least 32 valid bits in the window.  The word that enters was loaded at the previous
+ * refill and is not touched before this one (not even byte-swapped): its latency stays off
+ * the dependent chain. */
 DSVCU_DEV void
 hz_fill(HzRd &r)
 {
-    const bool take = r.n <= 32;
-    const uint32_t nb = r.nb + 4;
-    const uint64_t add = (uint64_t) r.nxt << ((32 - r.n) & 63);
-    r.win |= take ? add : 0;
-    const uint32_t w = (take && nb < r.end) ? hz_be32(r.buf + nb) : 0u;
-    r.nxt = take ? w : r.nxt;
-    r.nb = take ? nb : r.nb;
-    r.n += take ? 32 : 0;
+    if (r.n <= 32) {
+        r.win |= (uint64_t) hz_swap(r.nxt) << (32 - r.n);
+        r.nb += 4;
+        r.n += 32;
+        r.nxt = hz_raw(r, r.nb);
+    }
 }
 
 DSVCU_DEV void
@@ -251,9 +252,34 @@ hz_layout(int w, int h, int part[5])
     return pos;
 }
 
+/* the prefix table lives in shared memory; on the device it is addressed through its 32-bit
+ * shared-window address, held in a register for the whole walk (the compiler otherwise rebuilds
+ * the window base from a special register in front of every look-up, on the dependent chain) */
+#ifndef DSVCU_EMU
+typedef uint32_t hz_tab_t;
+DSVCU_DEV hz_tab_t
+hz_tab_ref(const uint32_t *tab)
+{
+    uint32_t a = (uint32_t) __cvta_generic_to_shared(tab), kept;
+    asm volatile("mov.u32 %0, %1;" : "=r"(kept) : "r"(a)); /* opaque: not rematerialised */
+    return kept;
+}
+DSVCU_DEV uint32_t
+hz_tab_at(hz_tab_t tab, uint32_t idx)
+{
+    uint32_t e;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(tab + idx * 4u));
+    return e;
+}
+#else
+typedef const uint32_t *hz_tab_t;
+DSVCU_DEV hz_tab_t hz_tab_ref(const uint32_t *tab) { return tab; }
+DSVCU_DEV uint32_t hz_tab_at(hz_tab_t tab, uint32_t idx) { return tab[idx]; }
+#endif
+
 /* one plane; returns 1 when it was well-formed.  `tab`: HZT_ROWS rows of HZT_SIZE entries */
 DSVCU_DEV int
-hz_parse_plane(const HzJob &J, const HzSpan &S, int *meta, const uint32_t *tab)
+hz_parse_plane(const HzJob &J, const HzSpan &S, int *meta, const hz_tab_t tab)
 {
     HzRd r;
     int part[5];
@@ -276,9 +302,9 @@ hz_parse_plane(const HzJob &J, const HzSpan &S, int *meta, const uint32_t *tab)
     int n = 0, l = -1, vk = 0, ls1 = 0, ls2 = 0, ls3 = 0;
     uint32_t cur = 0, bound = (uint32_t) part[1];
     uint32_t run = runs ? hz_ueg(r) : 0;
+    if (run > 0x3fffffffu) return 0;
     for (uint32_t i = 0; i < runs; i++) {
         const uint32_t pos = cur + run;
-        if (run > 0x3fffffffu) return 0;
         while (pos >= bound) {
             if (pos >= total) return 0;
             l++;
@@ -291,7 +317,7 @@ hz_parse_plane(const HzJob &J, const HzSpan &S, int *meta, const uint32_t *tab)
         int v;
         uint32_t e = 0;
         hz_fill(r);
-        if ((l < 0 || k < HZT_KMAX) && i + 1 < runs) e = tab[k * HZT_SIZE + (uint32_t) (r.win >> (64 - HZT_BITS))];
+        if ((l < 0 || k < HZT_KMAX) && i + 1 < runs) e = hz_tab_at(tab, (uint32_t) k * HZT_SIZE + (uint32_t) (r.win >> (64 - HZT_BITS)));
         if (HZT_LEN(e)) {
             hz_skip(r, HZT_LEN(e));
             v = HZT_VAL(e);
@@ -305,12 +331,18 @@ hz_parse_plane(const HzJob &J, const HzSpan &S, int *meta, const uint32_t *tab)
                 v = hz_nrice(r, &vk, k);
             }
             run = i + 1 < runs ? hz_ueg(r) : 0;
+            if (run > 0x3fffffffu) return 0; /* (runs out of the table are small) */
         }
         if (pos != 0) {
-            dsvcu_sym sy;
-            sy.pos = pos;
-            sy.v = v;
-            out[n++] = sy;
+#ifndef DSVCU_EMU
+            /* (the slots are 8-byte aligned: cudaMalloc base, 8-byte elements) */
+            *(uint2 *) (out + n) = make_uint2(pos, (uint32_t) v);
+            n++;
+#else
+            out[n].pos = pos;
+            out[n].v = v;
+            n++;
+#endif
         }
         cur = pos + 1;
     }
@@ -346,7 +378,7 @@ k_hzcc_parse(HzJob J)
     const int s = (int) blockIdx.x * per_cta + (DSVCU_TID >> 5);
     if ((DSVCU_TID & 31) != 0 || s >= J.nspans) return;
     int *meta = J.meta + s * HZ_META_WORDS;
-    meta[HZ_META_OK] = hz_parse_plane(J, J.spans[s], meta, tab);
+    meta[HZ_META_OK] = hz_parse_plane(J, J.spans[s], meta, hz_tab_ref(tab));
 }
 
 #endif /* K_HZCC_CUH */

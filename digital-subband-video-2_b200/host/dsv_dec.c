@@ -773,12 +773,15 @@ locate_planes(const DEC_STATE *s, const uint8_t *pkt, size_t len, dsvcu_plane_bi
     return 0;
 }
 
-/* Pictures above this size keep their planes on the host: a plane is one serial chain, which
- * a device thread walks an order of magnitude slower than a core does.  What matters on the
- * device is that the chains of a batch run side by side and beside the reconstruction of the
- * pictures in front of them; one very long chain (the intra picture of a GOP) would only
- * make everything behind it wait. */
-#define PREPARSE_MAX_PICTURE_BYTES (160 * 1024)
+/* Pictures above this size keep their planes on the host.  A plane is one serial chain; a
+ * device thread walks it at about 5 cycles per instruction, ~0.2 us per (run, value) pair
+ * (measured, profiles/r2_ncu_hzcc_parse.txt) -- ten times slower than a core.  What the device
+ * offers is that all chains of a batch run side by side, beside the reconstruction of the
+ * pictures in front of them, and cost the host nothing; the batch is ready when its longest
+ * chain is.  64 KB is about 75 000 pairs = 15 ms: the time the host needs for the intra picture
+ * that leads the GOP (1080p, qp 60: 550 KB, 11 ms).  Longer chains (the intra picture, the
+ * pictures behind a scene cut) would only make every picture of the batch wait for them. */
+#define PREPARSE_MAX_PICTURE_BYTES (64 * 1024)
 
 /* Entropy-decode the coefficient planes of the next `n` picture packets on the device, in
  * one launch on the context's parse stream (they carry no coder state from one to the

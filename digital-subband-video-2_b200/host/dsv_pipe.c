@@ -10,9 +10,14 @@
  * on one of the GPUs, so several chunks are in flight per GPU and their kernels
  * overlap.  There is no exchange between chunks, hence no collective.
  */
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
 #include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include "dsv_host.h"
 #include "../../include/dsv_encoder.h"
 #include "../../include/dsv_decoder.h"
@@ -603,14 +608,38 @@ probe_meta(const uint8_t *d, const PKT *pk, int npk, DSV_META *meta)
 #define PREPARSE_MAX_PICS 64
 #define PREPARSE_MAX_BYTES ((size_t) 24 << 20)
 
-static volatile int g_device_entropy = 1;
+static volatile int g_device_entropy = -1;
 
 int
 dsv_set_device_entropy_decode(int on)
 {
     const int was = g_device_entropy;
-    g_device_entropy = !!on;
+    g_device_entropy = on < 0 ? -1 : !!on;
     return was;
+}
+
+/* cores this process may run on */
+static int
+host_cores(void)
+{
+    cpu_set_t set;
+    long n;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) {
+        return CPU_COUNT(&set);
+    }
+    n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n > 0 ? (int) n : 1;
+}
+
+/* The setting in effect for a job of `nthreads` decoder instances.  A plane is a serial
+ * chain that a core walks an order of magnitude faster than a device thread; the device wins
+ * by walking thousands of them at once and by leaving the cores alone.  So, left to itself,
+ * the library parses on the device exactly when the instances outnumber the cores. */
+static int
+device_entropy_for(int nthreads)
+{
+    const int g = g_device_entropy;
+    return g < 0 ? nthreads > host_cores() : g;
 }
 
 typedef struct {
@@ -621,7 +650,7 @@ typedef struct {
 /* hand the coefficient planes of the pictures from packet `from` on (up to the next packet
  * that is not a picture) to the device parser */
 static void
-batch_begin(DSV_DECODER *dec, const uint8_t *d, const PKT *pk, int from, int last, BATCH *b)
+batch_begin(DSV_DECODER *dec, const uint8_t *d, const PKT *pk, int from, int last, int on_device, BATCH *b)
 {
     const uint8_t *bp[PREPARSE_MAX_PICS];
     size_t bl[PREPARSE_MAX_PICS], bytes = 0;
@@ -638,13 +667,14 @@ batch_begin(DSV_DECODER *dec, const uint8_t *d, const PKT *pk, int from, int las
     b->begin = from;
     b->end = j;
     /* on a device error the host parser takes over (and will report it) */
-    b->slot = (dec->got_metadata && g_device_entropy) ? dsv_dec_preparse(dec, bp, bl, n) : -1;
+    b->slot = (dec->got_metadata && on_device) ? dsv_dec_preparse(dec, bp, bl, n) : -1;
 }
 
 /* decode packets [first, last) with `dec`; frames are written to dst one after
  * the other.  returns the number of frames written */
 static int
-decode_range(DSV_DECODER *dec, const uint8_t *d, const PKT *pk, int first, int last, uint8_t *dst, size_t fsz)
+decode_range(DSV_DECODER *dec, const uint8_t *d, const PKT *pk, int first, int last, uint8_t *dst, size_t fsz,
+             int on_device)
 {
     BATCH cur, nxt;
     int i, nfr = 0, cur_k = 0, have_next = 0;
@@ -661,7 +691,7 @@ decode_range(DSV_DECODER *dec, const uint8_t *d, const PKT *pk, int first, int l
             if (have_next && nxt.begin == i) {
                 cur = nxt;
             } else {
-                batch_begin(dec, d, pk, i, last, &cur);
+                batch_begin(dec, d, pk, i, last, on_device, &cur);
             }
             have_next = 0;
             cur_k = 0;
@@ -695,7 +725,7 @@ decode_range(DSV_DECODER *dec, const uint8_t *d, const PKT *pk, int first, int l
          * ones are reconstructed */
         if (is_pic && !have_next && cur.end < last && DSV_PT_IS_PIC(pk[cur.end].type) &&
             (cur.slot < 0 || !dsv_dec_preparse_pending(dec, cur.slot))) {
-            batch_begin(dec, d, pk, cur.end, last, &nxt);
+            batch_begin(dec, d, pk, cur.end, last, on_device, &nxt);
             have_next = 1;
         }
     }
@@ -723,6 +753,7 @@ typedef struct {
     uint8_t *dst;
     size_t fsz;
     int *seg_done; /* frames actually decoded per segment */
+    int device_entropy;
 } DEC_JOB;
 
 static void
@@ -730,7 +761,7 @@ decode_segment(WORKER *w, void *arg, int k)
 {
     DEC_JOB *j = arg;
     j->seg_done[k] = decode_range(&w->dec, j->d, j->pk, j->seg_first[k], j->seg_last[k],
-                                  j->dst + (size_t) j->seg_frame0[k] * j->fsz, j->fsz);
+                                  j->dst + (size_t) j->seg_frame0[k] * j->fsz, j->fsz, j->device_entropy);
 }
 
 /* frames are written to `dst` (host, pinned or DEVICE memory) when it is given
@@ -782,6 +813,7 @@ pool_decode(dsv_pool *pl, const uint8_t *dsv, size_t len, uint8_t *dst, size_t d
     job.d = dsv;
     job.pk = pk;
     job.fsz = frame_bytes(md.width, md.height, md.subsamp);
+    job.device_entropy = device_entropy_for(pl->nthreads);
     if (dst) {
         if (dst_cap < job.fsz * (size_t) total) {
             ok = 0;

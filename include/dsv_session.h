@@ -83,10 +83,12 @@ int dsv_pool_decode(dsv_pool *pool, const uint8_t *dsv, size_t len, uint8_t *dst
                     DSV_META *meta);
 
 /* Where the whole-stream decoders (dsv_pool_decode*, dsv_decode_*) entropy-decode the
- * coefficient planes: 1 (default) = on the device, in batches of pictures one batch ahead of
- * the reconstruction (csrc/k_hzcc.cuh; pictures above 160 KB and planes the device parser does
- * not accept stay on the host); 0 = all of them on the host threads.  Same output either way.
- * Process-wide; returns the previous setting. */
+ * coefficient planes: 1 = on the device, in batches of pictures one batch ahead of the
+ * reconstruction (csrc/k_hzcc.cuh; pictures above 64 KB and planes the device parser does
+ * not accept stay on the host); 0 = all of them on the host threads; -1 (default) = on the
+ * device when the pool has more decoder instances than the process has cores (a process that
+ * shares its cores with others -- one rank per GPU -- knows better and says so).  Same output
+ * either way.  Process-wide; returns the previous setting. */
 int dsv_set_device_entropy_decode(int on);
 
 /* the same with the frames in pinned memory allocated by the call (dsv_pinned_free) */

@@ -52,11 +52,12 @@ def _whole_stream_vs_packetwise(emu):
     data = open(dsv, "rb").read()
     _, _, ref = util.read_y4m(util.ref_decode(dsv))
     P = util.pkg()
-    meta, nfr, whole = P.decode_frames(data, emu=emu)
-    assert nfr == n
     _, packetwise = P.decode_stream(data, emu=emu)
     util.assert_same_frames(packetwise, ref, w, h)
-    assert whole == b"".join(b"".join(f) for f in packetwise)
+    for device_entropy in (1, 0, -1):
+        meta, nfr, whole = P.decode_frames(data, emu=emu, device_entropy=device_entropy)
+        assert nfr == n
+        assert whole == b"".join(b"".join(f) for f in packetwise), "device_entropy=%d" % device_entropy
 
 
 @pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")

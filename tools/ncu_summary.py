@@ -7,7 +7,7 @@ import collections, glob, json, os, subprocess, sys
 sys.path.insert(0, "/opt/nvidia/nsight-compute/2025.2.1/extras/python")
 import ncu_report
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
-CSRC = os.path.join(ROOT, "digital-subband-video-2_b200", "csrc")
+CSRC = os.environ.get("NCU_SRC") or os.path.join(ROOT, "digital-subband-video-2_b200", "csrc")
 tag, rnd = sys.argv[1], sys.argv[2]
 IN = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out")
 OUT = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "profiles")
