@@ -575,9 +575,8 @@ def run_own(args):
     threads = args.threads or max(2, min(32, 8 * cores // max(1, world)))
     chunks = args.chunks or threads
     nframes = chunks * GOP
-    # where the decoder parses its coefficient planes (dsv_session.h): the ranks of one box share
-    # its cores, which the library cannot see from inside one process
-    dev_entropy = 1 if threads * world > cores else 0
+    # the decoder parses its coefficient planes on the device (dsv_session.h; the library's default)
+    dev_entropy = 1
     lib.dsv_set_device_entropy_decode(dev_entropy)
 
     distinct = DISTINCT

@@ -189,8 +189,9 @@ def load(emu=False):
         "dsvcu_symbol_staging": (P(DSVCU_SYMBOL), [vp, ip, P(ip)]),
         "dsvcu_dequant_plane": (ip, [vp, vp, ip, ip, P(DSVCU_FMETA), ip, P(ip), ip]),
         "dsv_set_device_entropy_decode": (ip, [ip]),
-        "dsvcu_parse_begin": (ip, [vp, P(DSVCU_PLANE_BITS), ip]),
-        "dsvcu_parse_end": (ip, [vp, ip, P(ip)]),
+        "dsv_set_device_entropy_limits": (None, [C.c_long, C.c_long, ip]),
+        "dsvcu_parse_begin": (ip, [vp, P(DSVCU_PLANE_BITS), ip, ip]),
+        "dsvcu_parse_end": (ip, [vp, ip, ip, P(ip)]),
         "dsvcu_parse_planes": (ip, [vp, P(DSVCU_PLANE_BITS), ip, P(ip)]),
         "dsvcu_parsed_count": (ip, [vp, ip, ip]),
         "dsvcu_dequant_parsed": (ip, [vp, vp, ip, P(DSVCU_FMETA), ip, ip]),
@@ -328,7 +329,7 @@ def encode_frames(opts, yuv, nframes, emu=False, exhausted=True, chunk=0, thread
 def decode_frames(data, emu=False, threads=1, devices=None, device_entropy=1):
     """Decode .dsv bytes -> (DSV_META, nframes, packed planar frames bytes).
     device_entropy: dsv_set_device_entropy_decode() for this call (1 = coefficient planes are
-    entropy-decoded by k_hzcc_parse, 0 = by the host threads, -1 = the library decides)."""
+    entropy-decoded by k_hzcc_parse, 0 = by the host threads, -1 = the library's default, which is 1)."""
     lib = load(emu)
     lib.dsv_set_device_entropy_decode(device_entropy)
     out, n, nfr, meta = C.c_void_p(), C.c_size_t(), C.c_int(), DSV_META()

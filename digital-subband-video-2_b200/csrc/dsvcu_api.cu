@@ -161,15 +161,17 @@ struct dsvcu_ctx {
         HzSpan *h_spans, *d_spans;
         int *h_meta, *d_meta;     /* HZ_META_WORDS per plane */
         int spans_cap, n;
-        int pending;              /* begun, result not collected yet */
+        int n_early;              /* planes [0, n_early) are part 0 of the batch, the rest part 1 */
+        int pending[2];           /* part begun, result not collected yet */
 #ifndef DSVCU_EMU
-        cudaEvent_t ev_parsed;    /* meta words of the batch are in pinned memory */
+        cudaEvent_t ev_parsed[2]; /* meta words of the part are in pinned memory */
+        cudaEvent_t ev_bits;      /* plane bytes and descriptors are on the device */
         cudaEvent_t ev_consumed;  /* last de-quantiser launch that read the set's symbols */
 #endif
     } pset[2];
     int pset_last;
 #ifndef DSVCU_EMU
-    cudaStream_t pstream;
+    cudaStream_t pstream, pstream2; /* part 0 / part 1 of a batch */
 #endif
     int *d_progress;
     int progress_cap;
@@ -378,7 +380,9 @@ parse_set_free(dsvcu_ctx *c, int i)
     if (S->h_meta) dsvcu_free_host(S->h_meta);
     if (S->d_meta) dsvcu_free_dev(S->d_meta);
 #ifndef DSVCU_EMU
-    if (S->ev_parsed) cudaEventDestroy(S->ev_parsed);
+    if (S->ev_parsed[0]) cudaEventDestroy(S->ev_parsed[0]);
+    if (S->ev_parsed[1]) cudaEventDestroy(S->ev_parsed[1]);
+    if (S->ev_bits) cudaEventDestroy(S->ev_bits);
     if (S->ev_consumed) cudaEventDestroy(S->ev_consumed);
 #endif
     memset(S, 0, sizeof(*S));
@@ -392,6 +396,7 @@ dsvcu_ctx_destroy(dsvcu_ctx *c)
 #ifndef DSVCU_EMU
     cudaSetDevice(c->device);
     if (c->pstream) cudaStreamSynchronize(c->pstream);
+    if (c->pstream2) cudaStreamSynchronize(c->pstream2);
     cudaStreamSynchronize(c->stream);
 #endif
     for (i = 0; i < 3; i++) {
@@ -412,6 +417,7 @@ dsvcu_ctx_destroy(dsvcu_ctx *c)
     for (i = 0; i < 2; i++) parse_set_free(c, i);
 #ifndef DSVCU_EMU
     if (c->pstream) cudaStreamDestroy(c->pstream);
+    if (c->pstream2) cudaStreamDestroy(c->pstream2);
 #endif
     dsvcu_free_dev(c->d_progress);
     if (c->d_side[0]) dsvcu_free_dev(c->d_side[0]);
@@ -1393,9 +1399,13 @@ dsvcu_dequant_plane(dsvcu_ctx *c, dsvcu_coefs *k, int plane, int q, const dsvcu_
 /* ---- entropy decode on the device (k_hzcc.cuh) ----
  *
  * dsvcu_parse_begin: `n` serialised coefficient planes (each starting at its 32-bit length
- * word) are gathered into pinned memory, copied to the device and parsed by one launch, one
- * warp per plane, on the context's parse stream -- beside whatever the context's main stream
- * is doing.  Returns the set (0 / 1) the batch lives in.  dsvcu_parse_end waits for that set:
+ * word) are gathered into pinned memory, copied to the device and parsed, one warp per plane,
+ * on the context's parse streams -- beside whatever the context's main stream is doing.  The
+ * batch comes in two parts with a launch, a stream and a completion event each: planes
+ * [0, n_early) and the rest.  A part is ready when its LONGEST chain is, so the caller puts
+ * the planes it needs first and that are short into part 0 and the long ones (pictures behind
+ * a scene cut, needed late) into part 1.  Returns the set (0 / 1) the batch lives in.
+ * dsvcu_parse_end waits for one part of that set and reports its planes:
  * ok[i] = 1: plane i was well-formed and its symbols are resident (dsvcu_dequant_parsed);
  * ok[i] = 0: the caller must parse that plane on the host, which reproduces the reference's
  * handling of damaged planes.  A set's symbols stay valid until the set is begun again, i.e.
@@ -1421,8 +1431,14 @@ plane_pair_count(const uint8_t *p, uint32_t len)
     return ((uint32_t) p[bit >> 3] << 16) | ((uint32_t) p[(bit >> 3) + 1] << 8) | p[(bit >> 3) + 2];
 }
 
+static int
+parse_set_pending(const dsvcu_ctx *c, int set)
+{
+    return c->pset[set].pending[0] || c->pset[set].pending[1];
+}
+
 extern "C" int
-dsvcu_parse_begin(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n)
+dsvcu_parse_begin(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n, int n_early)
 {
     size_t total = 0, nsyms = 0, at = 0, sat = 0;
     int i, set = 0;
@@ -1431,8 +1447,9 @@ dsvcu_parse_begin(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n)
 
     if (n <= 0) return fail_msg("dsvcu_parse_begin: no planes");
     /* the set that was begun longer ago; never one whose result has not been collected */
-    if (c->pset[0].pending && c->pset[1].pending) return fail_msg("dsvcu_parse_begin: two batches already in flight");
-    set = c->pset[0].pending ? 1 : (c->pset[1].pending ? 0 : (c->pset_last ^ 1));
+    if (n_early < 0 || n_early > n) return fail_msg("dsvcu_parse_begin: bad split");
+    if (parse_set_pending(c, 0) && parse_set_pending(c, 1)) return fail_msg("dsvcu_parse_begin: two batches already in flight");
+    set = parse_set_pending(c, 0) ? 1 : (parse_set_pending(c, 1) ? 0 : (c->pset_last ^ 1));
     S = &c->pset[set];
     for (i = 0; i < n; i++) {
         if (pl[i].len < 8 || pl[i].len > 0x3fffffffu || !pl[i].bits) return fail_msg("dsvcu_parse_begin: bad plane");
@@ -1441,8 +1458,11 @@ dsvcu_parse_begin(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n)
     if (total + 16 > 0xffffffffu / 8) return fail_msg("dsvcu_parse_begin: batch too large");
 #ifndef DSVCU_EMU
     if (!c->pstream) CK(cudaStreamCreateWithFlags(&c->pstream, cudaStreamNonBlocking));
-    if (!S->ev_parsed) {
-        CK(cudaEventCreateWithFlags(&S->ev_parsed, cudaEventDisableTiming | cudaEventBlockingSync));
+    if (!c->pstream2) CK(cudaStreamCreateWithFlags(&c->pstream2, cudaStreamNonBlocking));
+    if (!S->ev_consumed) {
+        CK(cudaEventCreateWithFlags(&S->ev_parsed[0], cudaEventDisableTiming | cudaEventBlockingSync));
+        CK(cudaEventCreateWithFlags(&S->ev_parsed[1], cudaEventDisableTiming | cudaEventBlockingSync));
+        CK(cudaEventCreateWithFlags(&S->ev_bits, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&S->ev_consumed, cudaEventDisableTiming));
     }
     /* de-quantiser launches of the batch that used this set last may still be queued */
@@ -1453,6 +1473,7 @@ dsvcu_parse_begin(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n)
         CK(ctx_wait(c));
 #ifndef DSVCU_EMU
         CK(cudaStreamSynchronize(c->pstream));
+        CK(cudaStreamSynchronize(c->pstream2));
 #endif
         if (total + 16 > S->bits_cap) {
             const size_t cap = total + total / 4 + 4096;
@@ -1506,6 +1527,7 @@ dsvcu_parse_begin(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n)
         CK(ctx_wait(c));
 #ifndef DSVCU_EMU
         CK(cudaStreamSynchronize(c->pstream));
+        CK(cudaStreamSynchronize(c->pstream2));
 #endif
         if (S->d_syms) dsvcu_free_dev(S->d_syms);
         S->d_syms = NULL;
@@ -1522,50 +1544,68 @@ dsvcu_parse_begin(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n)
     CK(dsvcu_h2d_async(S->d_bits, S->h_bits, at + 16, ps));
     CK(dsvcu_h2d_async(S->d_spans, S->h_spans, (size_t) n * sizeof(HzSpan), ps));
     J.bits = S->d_bits;
-    J.spans = S->d_spans;
-    J.nspans = n;
     J.syms = S->d_syms;
-    J.meta = S->d_meta;
 #ifndef DSVCU_EMU
-    DSVCU_LAUNCH(k_hzcc_parse, (n + HZ_WARPS - 1) / HZ_WARPS, HZ_WARPS * 32, 0, ps, J);
+    CK(cudaEventRecord(S->ev_bits, ps));
+    CK(cudaStreamWaitEvent(c->pstream2, S->ev_bits, 0));
+#endif
+    for (int part = 0; part < 2; part++) {
+        const int first = part ? n_early : 0, cnt = part ? n - n_early : n_early;
+#ifndef DSVCU_EMU
+        const cudaStream_t st = part ? c->pstream2 : c->pstream;
 #else
-    DSVCU_LAUNCH(k_hzcc_parse, n, 32, 0, ps, J);
+        const dsvcu_stream_t st = 0;
 #endif
-    CK_LAUNCH(c);
-    CK(dsvcu_d2h_async(S->h_meta, S->d_meta, (size_t) n * HZ_META_WORDS * sizeof(int), ps));
+        S->pending[part] = 0;
+        if (!cnt) continue;
+        J.spans = S->d_spans + first;
+        J.nspans = cnt;
+        J.meta = S->d_meta + first * HZ_META_WORDS;
 #ifndef DSVCU_EMU
-    CK(cudaEventRecord(S->ev_parsed, ps));
+        DSVCU_LAUNCH(k_hzcc_parse, (cnt + HZ_WARPS - 1) / HZ_WARPS, HZ_WARPS * 32, 0, st, J);
+#else
+        DSVCU_LAUNCH(k_hzcc_parse, cnt, 32, 0, st, J);
 #endif
+        CK_LAUNCH(c);
+        CK(dsvcu_d2h_async(S->h_meta + first * HZ_META_WORDS, S->d_meta + first * HZ_META_WORDS,
+                           (size_t) cnt * HZ_META_WORDS * sizeof(int), st));
+#ifndef DSVCU_EMU
+        CK(cudaEventRecord(S->ev_parsed[part], st));
+#endif
+        S->pending[part] = 1;
+    }
     S->n = n;
-    S->pending = 1;
+    S->n_early = n_early;
     c->pset_last = set;
     return set;
 }
 
 extern "C" int
-dsvcu_parse_end(dsvcu_ctx *c, int set, int *ok)
+dsvcu_parse_end(dsvcu_ctx *c, int set, int part, int *ok)
 {
     dsvcu_ctx::ParseSet *S;
     int i;
-    if (set < 0 || set > 1 || !c->pset[set].n) return fail_msg("dsvcu_parse_end: no such batch");
+    if (set < 0 || set > 1 || part < 0 || part > 1 || !c->pset[set].n) return fail_msg("dsvcu_parse_end: no such batch");
     S = &c->pset[set];
-    if (S->pending) {
+    if (S->pending[part]) {
 #ifndef DSVCU_EMU
-        CK(cudaEventSynchronize(S->ev_parsed));
+        CK(cudaEventSynchronize(S->ev_parsed[part]));
 #endif
-        S->pending = 0;
+        S->pending[part] = 0;
     }
-    for (i = 0; i < S->n; i++) ok[i] = S->h_meta[i * HZ_META_WORDS + HZ_META_OK] == 1;
+    for (i = part ? S->n_early : 0; i < (part ? S->n : S->n_early); i++) {
+        ok[i] = S->h_meta[i * HZ_META_WORDS + HZ_META_OK] == 1;
+    }
     return 0;
 }
 
-/* both halves in one call: the batch is set 0 or 1 (returned) */
+/* a batch of one part, begun and collected in one call: the batch is set 0 or 1 (returned) */
 extern "C" int
 dsvcu_parse_planes(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n, int *ok)
 {
-    const int set = dsvcu_parse_begin(c, pl, n);
+    const int set = dsvcu_parse_begin(c, pl, n, n);
     if (set < 0) return -1;
-    if (dsvcu_parse_end(c, set, ok)) return -1;
+    if (dsvcu_parse_end(c, set, 0, ok)) return -1;
     return set;
 }
 
@@ -1576,7 +1616,7 @@ dsvcu_parsed_count(dsvcu_ctx *c, int set, int span)
     const dsvcu_ctx::ParseSet *S;
     if (set < 0 || set > 1) return -1;
     S = &c->pset[set];
-    if (S->pending || span < 0 || span >= S->n || S->h_meta[span * HZ_META_WORDS + HZ_META_OK] != 1) return -1;
+    if (S->pending[span >= S->n_early] || span < 0 || span >= S->n || S->h_meta[span * HZ_META_WORDS + HZ_META_OK] != 1) return -1;
     return S->h_meta[span * HZ_META_WORDS + HZ_META_NSYM];
 }
 
@@ -1593,7 +1633,9 @@ dsvcu_dequant_parsed(dsvcu_ctx *c, dsvcu_coefs *k, int q, const dsvcu_fmeta *fm,
 
     if (set < 0 || set > 1) return fail_msg("dsvcu_dequant_parsed: no such batch");
     S = &c->pset[set];
-    if (S->pending || first_span < 0 || first_span + 3 > S->n) return fail_msg("dsvcu_dequant_parsed: no such planes");
+    if (first_span < 0 || first_span + 3 > S->n || S->pending[first_span >= S->n_early] || S->pending[first_span + 2 >= S->n_early]) {
+        return fail_msg("dsvcu_dequant_parsed: no such planes");
+    }
     for (p = 0; p < 3; p++) {
         const HzSpan *sp = &S->h_spans[first_span + p];
         const int *m = S->h_meta + (first_span + p) * HZ_META_WORDS;

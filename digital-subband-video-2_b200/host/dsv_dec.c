@@ -72,6 +72,7 @@ typedef struct {
     int nblk_cap;
     double ph_ms[DP_N], ph_t0, ph_wall[DP_N], ph_w0;
     int ph_frames;
+    int ph_where[3]; /* pictures parsed by the device (part 0, part 1) and by the host */
     /* batches of pictures whose coefficient planes are entropy-decoded on the device ahead of
      * time (dsv_dec_preparse), one per parse set of the context: first span of picture i in
      * the batch, or -1 where the host parses */
@@ -79,8 +80,9 @@ typedef struct {
         int *first;
         int n, cap;
         int nspans;  /* planes handed to the device */
+        int nearly;  /* of which part 0 (short planes, needed first); the rest is part 1 */
         int cset;    /* the context's parse set they went to */
-        int pending; /* launched, result not looked at yet */
+        int pending[2]; /* part launched, result not looked at yet */
     } pre[2];
     int pre_last;
 } DEC_STATE;
@@ -110,7 +112,7 @@ dsv_dec_set_async(int on)
     tls_async = on;
 }
 
-static int preparse_collect(DEC_STATE *s, int set);
+static int preparse_collect(DEC_STATE *s, int set, int part);
 
 int
 dsv_dec_flush(DSV_DECODER *d)
@@ -119,7 +121,8 @@ dsv_dec_flush(DSV_DECODER *d)
     int set;
     /* a batch of planes that was sent ahead and is not wanted any more */
     for (set = 0; s && s->ctx && set < 2; set++) {
-        (void) preparse_collect(s, set);
+        (void) preparse_collect(s, set, 0);
+        (void) preparse_collect(s, set, 1);
         s->pre[set].n = 0;
     }
     if (s && s->ctx && dsvcu_sync(s->ctx)) {
@@ -155,7 +158,8 @@ state_free(DEC_STATE *s)
             at += snprintf(line + at, sizeof(line) - (size_t) at, " %s %.3f (%.3f);", dp_name[i],
                            s->ph_ms[i] / s->ph_frames, s->ph_wall[i] / s->ph_frames);
         }
-        fprintf(stderr, "%s\n", line);
+        fprintf(stderr, "%s planes parsed on the device for %d + %d pictures (part 0 + part 1), on the host for %d\n",
+                line, s->ph_where[0], s->ph_where[1], s->ph_where[2]);
     }
     if (s->ctx) {
         dsvcu_sync(s->ctx);
@@ -635,7 +639,8 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
     dst = s->pic[s->cur];
     ref = s->pic[s->cur ^ 1];
     if (tls_parsed >= 0 && tls_parsed < s->pre[tls_parsed_set].n && s->pre[tls_parsed_set].first[tls_parsed] >= 0) {
-        if (preparse_collect(s, tls_parsed_set)) {
+        if (preparse_collect(s, tls_parsed_set,
+                             s->pre[tls_parsed_set].first[tls_parsed] >= s->pre[tls_parsed_set].nearly)) {
             return DSV_DEC_ERROR;
         }
         DPROF(s, DP_PREPARSE);
@@ -647,6 +652,9 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
         DPROF(s, DP_QUEUE);
         good_planes = 7;
         on_device = 1;
+        s->ph_where[s->pre[tls_parsed_set].first[tls_parsed] >= s->pre[tls_parsed_set].nearly]++;
+    } else {
+        s->ph_where[2]++;
     }
     for (i = 0; i < 3 && !on_device; i++) {
         int cap, nsym, lstart[5], dc, cw, ch;
@@ -773,30 +781,44 @@ locate_planes(const DEC_STATE *s, const uint8_t *pkt, size_t len, dsvcu_plane_bi
     return 0;
 }
 
-/* Pictures above this size keep their planes on the host.  A plane is one serial chain; a
- * device thread walks it at about 5 cycles per instruction, ~0.2 us per (run, value) pair
- * (measured, profiles/r2_ncu_hzcc_parse.txt) -- ten times slower than a core.  What the device
- * offers is that all chains of a batch run side by side, beside the reconstruction of the
- * pictures in front of them, and cost the host nothing; the batch is ready when its longest
- * chain is.  64 KB is about 75 000 pairs = 15 ms: the time the host needs for the intra picture
- * that leads the GOP (1080p, qp 60: 550 KB, 11 ms).  Longer chains (the intra picture, the
- * pictures behind a scene cut) would only make every picture of the batch wait for them. */
-#define PREPARSE_MAX_PICTURE_BYTES (64 * 1024)
+/* Which pictures go to the device parser.  A plane is one serial chain; a device thread walks
+ * it at about 5 cycles per instruction, ~0.2 us per (run, value) pair (measured,
+ * profiles/r2_ncu_hzcc_parse.txt) -- ten times slower than a core.  What the device offers is
+ * that all chains of a batch run side by side, beside the reconstruction of the pictures in
+ * front of them, and cost the host nothing; a part of the batch is ready when its longest
+ * chain is.  Pictures up to 64 KB (about 75 000 pairs = 15 ms, the time the host needs for
+ * the intra picture that leads the GOP: 1080p, qp 60: 550 KB, 11 ms) form part 0.  Longer ones
+ * up to 256 KB (the pictures behind a scene cut) form part 1, which only they wait for; if
+ * they lead the batch they stay on the host, like anything longer (the intra picture). */
+#define PREPARSE_EARLY_BYTES (64 * 1024)
+#define PREPARSE_LATE_BYTES (256 * 1024)
+#define PREPARSE_LATE_FROM 8 /* a long chain needs the time of this many pictures in front of it */
+static volatile size_t g_early_bytes = PREPARSE_EARLY_BYTES, g_late_bytes = PREPARSE_LATE_BYTES;
+static volatile int g_late_from = PREPARSE_LATE_FROM;
+
+/* the three limits above, process-wide (include/dsv_session.h); 0 / negative = default */
+void
+dsv_set_device_entropy_limits(long early_bytes, long late_bytes, int late_from)
+{
+    g_early_bytes = early_bytes > 0 ? (size_t) early_bytes : PREPARSE_EARLY_BYTES;
+    g_late_bytes = late_bytes > 0 ? (size_t) late_bytes : PREPARSE_LATE_BYTES;
+    g_late_from = late_from >= 0 ? late_from : PREPARSE_LATE_FROM;
+}
 
 /* Entropy-decode the coefficient planes of the next `n` picture packets on the device, in
- * one launch on the context's parse stream (they carry no coder state from one to the
- * next).  Does not wait: the result is collected when the first picture of the batch that
- * needs it is decoded.  The driver announces picture i of the batch with
- * dsv_dec_use_parsed(set, i) before handing its packet to dsv_dec; pictures whose planes were
- * not located, are too long or turn out not to be well-formed are parsed on the host as usual.
- * Needs the metadata packet to have been seen.  Returns the set (0 / 1) the batch occupies,
+ * one batch on the context's parse streams (they carry no coder state from one to the
+ * next).  Does not wait: the result is collected when the first picture that needs it is
+ * decoded.  The driver announces picture i of the batch with dsv_dec_use_parsed(set, i)
+ * before handing its packet to dsv_dec; pictures whose planes were not located, are too
+ * long or turn out not to be well-formed are parsed on the host as usual.  Needs the
+ * metadata packet to have been seen.  Returns the set (0 / 1) the batch occupies,
  * -1 on a device error (nothing is pending then). */
 int
 dsv_dec_preparse(DSV_DECODER *d, const uint8_t *const *pkt, const size_t *len, int n)
 {
     DEC_STATE *s;
     dsvcu_plane_bits *pl;
-    int i, m = 0, set;
+    int i, m = 0, set, part;
 
     if (!d->got_metadata || n <= 0) {
         return -1;
@@ -814,11 +836,13 @@ dsv_dec_preparse(DSV_DECODER *d, const uint8_t *const *pkt, const size_t *len, i
         return -1;
     }
     /* the slot that is not waiting for its result; failing that the older one */
-    set = s->pre[0].pending ? 1 : (s->pre[1].pending ? 0 : (s->pre_last ^ 1));
-    if (s->pre[set].pending) {
+#define SLOT_BUSY(k) (s->pre[k].pending[0] || s->pre[k].pending[1])
+    set = SLOT_BUSY(0) ? 1 : (SLOT_BUSY(1) ? 0 : (s->pre_last ^ 1));
+    if (SLOT_BUSY(set)) {
         free(pl);
         return -1;
     }
+#undef SLOT_BUSY
     s->pre[set].n = 0;
     if (n > s->pre[set].cap) {
         free(s->pre[set].first);
@@ -831,21 +855,31 @@ dsv_dec_preparse(DSV_DECODER *d, const uint8_t *const *pkt, const size_t *len, i
     }
     for (i = 0; i < n; i++) {
         s->pre[set].first[i] = -1;
-        if (len[i] <= PREPARSE_MAX_PICTURE_BYTES && locate_planes(s, pkt[i], len[i], pl + m) == 0) {
-            s->pre[set].first[i] = m;
-            m += 3;
+    }
+    for (part = 0; part < 2; part++) {
+        for (i = 0; i < n; i++) {
+            const int mine = part ? (len[i] > g_early_bytes && len[i] <= g_late_bytes && i >= g_late_from)
+                                  : len[i] <= g_early_bytes;
+            if (mine && locate_planes(s, pkt[i], len[i], pl + m) == 0) {
+                s->pre[set].first[i] = m;
+                m += 3;
+            }
+        }
+        if (!part) {
+            s->pre[set].nearly = m;
         }
     }
     s->pre[set].nspans = m;
     if (m) {
-        const int got = dsvcu_parse_begin(s->ctx, pl, m);
+        const int got = dsvcu_parse_begin(s->ctx, pl, m, s->pre[set].nearly);
         if (got < 0) {
             DSV_ERROR(("dsv_dec_preparse: %s", dsvcu_last_error()));
             free(pl);
             return -1;
         }
         s->pre[set].cset = got;
-        s->pre[set].pending = 1;
+        s->pre[set].pending[0] = s->pre[set].nearly > 0;
+        s->pre[set].pending[1] = m > s->pre[set].nearly;
     }
     s->pre[set].n = n;
     s->pre_last = set;
@@ -854,25 +888,26 @@ dsv_dec_preparse(DSV_DECODER *d, const uint8_t *const *pkt, const size_t *len, i
     return set;
 }
 
-/* is a batch still on its way (begun, not collected)? */
+/* is the first part of a batch still on its way (begun, not collected)? */
 int
 dsv_dec_preparse_pending(DSV_DECODER *d, int set)
 {
     DEC_STATE *s = d->ref ? (DEC_STATE *) d->ref : NULL;
-    return s ? s->pre[set & 1].pending : 0;
+    return s ? s->pre[set & 1].pending[0] : 0;
 }
 
-/* wait for the batch in `set` and strike the pictures that the device parser refused */
+/* wait for one part of the batch in `set` and strike the pictures that the device parser
+ * refused */
 static int
-preparse_collect(DEC_STATE *s, int set)
+preparse_collect(DEC_STATE *s, int set, int part)
 {
     int *ok, i;
-    if (!s->pre[set].pending) {
+    if (!s->pre[set].pending[part]) {
         return 0;
     }
-    s->pre[set].pending = 0;
+    s->pre[set].pending[part] = 0;
     ok = malloc((size_t) s->pre[set].nspans * sizeof(int));
-    if (!ok || dsvcu_parse_end(s->ctx, s->pre[set].cset, ok)) {
+    if (!ok || dsvcu_parse_end(s->ctx, s->pre[set].cset, part, ok)) {
         DSV_ERROR(("dsv_dec_preparse: %s", ok ? dsvcu_last_error() : "out of memory"));
         free(ok);
         s->pre[set].n = 0;
@@ -880,7 +915,7 @@ preparse_collect(DEC_STATE *s, int set)
     }
     for (i = 0; i < s->pre[set].n; i++) {
         const int f = s->pre[set].first[i];
-        if (f >= 0 && !(ok[f] && ok[f + 1] && ok[f + 2])) {
+        if (f >= 0 && (f >= s->pre[set].nearly) == part && !(ok[f] && ok[f + 1] && ok[f + 2])) {
             s->pre[set].first[i] = -1;
         }
     }

@@ -10,14 +10,9 @@
  * on one of the GPUs, so several chunks are in flight per GPU and their kernels
  * overlap.  There is no exchange between chunks, hence no collective.
  */
-#ifndef _GNU_SOURCE
-#define _GNU_SOURCE
-#endif
 #include <pthread.h>
-#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
-#include <unistd.h>
 #include "dsv_host.h"
 #include "../../include/dsv_encoder.h"
 #include "../../include/dsv_decoder.h"
@@ -608,38 +603,18 @@ probe_meta(const uint8_t *d, const PKT *pk, int npk, DSV_META *meta)
 #define PREPARSE_MAX_PICS 64
 #define PREPARSE_MAX_BYTES ((size_t) 24 << 20)
 
-static volatile int g_device_entropy = -1;
+/* 1: the coefficient planes of the whole-stream decoders are entropy-decoded on the device
+ * (measured on one B200 + 16 cores, 1080p: 1 / 8 / 32 instances 678 / 4716 / 10 514 frames/s
+ * against 647 / 4260 / 9575 with the host parser; with 4 cores for 32 instances 5781 against
+ * 3545); 0: on the host threads */
+static volatile int g_device_entropy = 1;
 
 int
 dsv_set_device_entropy_decode(int on)
 {
     const int was = g_device_entropy;
-    g_device_entropy = on < 0 ? -1 : !!on;
+    g_device_entropy = on < 0 ? 1 : !!on;
     return was;
-}
-
-/* cores this process may run on */
-static int
-host_cores(void)
-{
-    cpu_set_t set;
-    long n;
-    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) {
-        return CPU_COUNT(&set);
-    }
-    n = sysconf(_SC_NPROCESSORS_ONLN);
-    return n > 0 ? (int) n : 1;
-}
-
-/* The setting in effect for a job of `nthreads` decoder instances.  A plane is a serial
- * chain that a core walks an order of magnitude faster than a device thread; the device wins
- * by walking thousands of them at once and by leaving the cores alone.  So, left to itself,
- * the library parses on the device exactly when the instances outnumber the cores. */
-static int
-device_entropy_for(int nthreads)
-{
-    const int g = g_device_entropy;
-    return g < 0 ? nthreads > host_cores() : g;
 }
 
 typedef struct {
@@ -813,7 +788,7 @@ pool_decode(dsv_pool *pl, const uint8_t *dsv, size_t len, uint8_t *dst, size_t d
     job.d = dsv;
     job.pk = pk;
     job.fsz = frame_bytes(md.width, md.height, md.subsamp);
-    job.device_entropy = device_entropy_for(pl->nthreads);
+    job.device_entropy = g_device_entropy;
     if (dst) {
         if (dst_cap < job.fsz * (size_t) total) {
             ok = 0;

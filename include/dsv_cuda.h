@@ -122,22 +122,26 @@ int dsvcu_dequant_plane(dsvcu_ctx *ctx, dsvcu_coefs *c, int plane, int q, const 
  * the 3 x N planes of the N pictures of a closed GOP, which carry no entropy-coder state from
  * one to the next.  pl[i].bits points at plane i's 32-bit length word, pl[i].len = 4 + that
  * length, (w, h) = dsvcu_coefs_plane_dims.
- *   dsvcu_parse_begin  gathers, uploads and launches on the context's parse stream (beside the
- *                      work queued on its main stream) and returns the set (0 or 1) the batch
- *                      occupies; at most two batches exist at a time, a set's symbols live
- *                      until the set is begun again.
- *   dsvcu_parse_end    waits for the batch.  ok[i] = 1: symbols are resident on the device;
- *                      ok[i] = 0: not a well-formed plane, parse it on the host
- *                      (dsvcu_dequant_plane) -- the host parser reproduces the reference's
- *                      handling of damaged planes.
- *   dsvcu_parse_planes both in one call; returns the set. */
+ *   dsvcu_parse_begin  gathers, uploads and launches on the context's parse streams (beside
+ *                      the work queued on its main stream) and returns the set (0 or 1) the
+ *                      batch occupies; at most two batches exist at a time, a set's symbols
+ *                      live until the set is begun again.  The batch has two parts, planes
+ *                      [0, n_early) and [n_early, n), each with a launch and a completion of
+ *                      its own: a part is ready when its longest plane is, so short planes
+ *                      that are needed first go into part 0, long ones needed late into part 1.
+ *   dsvcu_parse_end    waits for one part (0 / 1) of the batch.  ok[i] = 1: symbols of plane i
+ *                      are resident on the device; ok[i] = 0: not a well-formed plane, parse
+ *                      it on the host (dsvcu_dequant_plane) -- the host parser reproduces the
+ *                      reference's handling of damaged planes.  Only the entries of that part
+ *                      are written.
+ *   dsvcu_parse_planes one part, begun and collected in one call; returns the set. */
 typedef struct {
     const uint8_t *bits;
     uint32_t len;
     int w, h;
 } dsvcu_plane_bits;
-int dsvcu_parse_begin(dsvcu_ctx *ctx, const dsvcu_plane_bits *pl, int n);
-int dsvcu_parse_end(dsvcu_ctx *ctx, int set, int *ok);
+int dsvcu_parse_begin(dsvcu_ctx *ctx, const dsvcu_plane_bits *pl, int n, int n_early);
+int dsvcu_parse_end(dsvcu_ctx *ctx, int set, int part, int *ok);
 int dsvcu_parse_planes(dsvcu_ctx *ctx, const dsvcu_plane_bits *pl, int n, int *ok);
 /* symbols found in plane `span` of a collected batch, -1 if it was not ok */
 int dsvcu_parsed_count(dsvcu_ctx *ctx, int set, int span);

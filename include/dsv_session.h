@@ -83,13 +83,18 @@ int dsv_pool_decode(dsv_pool *pool, const uint8_t *dsv, size_t len, uint8_t *dst
                     DSV_META *meta);
 
 /* Where the whole-stream decoders (dsv_pool_decode*, dsv_decode_*) entropy-decode the
- * coefficient planes: 1 = on the device, in batches of pictures one batch ahead of the
- * reconstruction (csrc/k_hzcc.cuh; pictures above 64 KB and planes the device parser does
- * not accept stay on the host); 0 = all of them on the host threads; -1 (default) = on the
- * device when the pool has more decoder instances than the process has cores (a process that
- * shares its cores with others -- one rank per GPU -- knows better and says so).  Same output
- * either way.  Process-wide; returns the previous setting. */
+ * coefficient planes: 1 (default; any negative value restores it) = on the device, in batches
+ * of pictures one batch ahead of the reconstruction (csrc/k_hzcc.cuh; long pictures and planes
+ * the device parser does not accept stay on the host, see dsv_set_device_entropy_limits);
+ * 0 = all of them on the host threads.  Same output either way.  Process-wide; returns the
+ * previous setting. */
 int dsv_set_device_entropy_decode(int on);
+/* Which pictures of a batch the device parser takes (host/dsv_dec.c, dsv_dec_preparse):
+ * packets up to early_bytes (default 64 KB) are parsed together and wanted first; longer ones
+ * up to late_bytes (256 KB) form a second part that only they wait for, unless they are among
+ * the first late_from (8) pictures of the batch; everything else stays on the host.
+ * 0 (late_from: negative) restores a default.  Process-wide. */
+void dsv_set_device_entropy_limits(long early_bytes, long late_bytes, int late_from);
 
 /* the same with the frames in pinned memory allocated by the call (dsv_pinned_free) */
 int dsv_pool_decode_alloc(dsv_pool *pool, const uint8_t *dsv, size_t len, uint8_t **yuv, size_t *yuv_len, int *nframes,
