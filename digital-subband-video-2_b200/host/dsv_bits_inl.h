@@ -229,4 +229,48 @@ done:
     return (int) (uv >> 1) ^ -(int) (uv & 1);
 }
 
+static inline unsigned
+dsv_fr_bit(DSV_FR *r)
+{
+    unsigned b = (unsigned) (dsv_fr_peek(r) >> 63);
+    r->pos++;
+    return b;
+}
+
+static inline int
+dsv_fr_seg(DSV_FR *r)
+{
+    int v = (int) dsv_fr_ueg(r);
+    if (v && dsv_fr_bit(r)) {
+        return -v;
+    }
+    return v;
+}
+
+/* zero-bit run-length reader (dsv_rle_rd_get of dsv_bits.c, reference bs.c:277-330) */
+typedef struct {
+    DSV_FR r;
+    int nz;
+} DSV_FRLE;
+
+static inline void
+dsv_frle_init(DSV_FRLE *e, const uint8_t *buf, size_t len)
+{
+    e->r.buf = buf;
+    e->r.len = len;
+    e->r.pos = 0;
+    e->nz = 0;
+}
+
+static inline int
+dsv_frle_get(DSV_FRLE *e)
+{
+    if (e->nz == 0) {
+        e->nz = (int) dsv_fr_ueg(&e->r);
+        return e->nz == 0;
+    }
+    e->nz--;
+    return e->nz == 0;
+}
+
 #endif /* DSV_BITS_INL_H */

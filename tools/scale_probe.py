@@ -6,7 +6,10 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench, util
 import torch
-P = util.pkg(); lib = P.load()
+P = util.pkg()
+if os.environ.get("DSV2CUDA_LIB"):  # a variant build (tools/gpu_filtvar.sh)
+    P.lib_path = lambda emu=False, _p=os.environ["DSV2CUDA_LIB"]: _p
+lib = P.load()
 data = bench.synth_chunks(2)
 GOPN = int(os.environ.get("GOPN", "24"))
 for threads in [int(t) for t in sys.argv[1].split(",")]:
