@@ -148,10 +148,84 @@ dsv_hzcc_read_plane(DSV_BITRD *br, dsvcu_symbol *syms, int cap, int w, int h, in
         r.len = br->len;
         r.pos = br->pos;
         lenbits = r.len * 8;
+        size_t safe_bytes;
+        int idle = 0;
+        /* bytes of the buffer a burst (below) may have loaded: every code it reads then starts
+         * and ends well inside both the buffer and the declared plane */
+        safe_bytes = r.len < limit ? r.len : limit;
+        safe_bytes = safe_bytes > 16 ? safe_bytes - 16 : 0;
         run = (runs-- > 0) ? dsv_fr_ueg(&r) : UINT_MAX;
         while (run != UINT_MAX) {
-            unsigned pos = cur + run;
+            unsigned pos;
             int v;
+            /* Burst: while the pairs stay inside one part of the scan, inside the table
+             * (both codes within HZT_BITS bits, Rice parameter below HZT_KMAX) and away from
+             * the end of the data, they are read from a 64-bit window held in a register --
+             * one table look-up and one shift per pair, no memory access on the dependent
+             * chain except the look-up.  Whatever ends the burst is handled by the general
+             * code below, one pair at a time, exactly as before. */
+            if (idle > 0) {
+                idle--;
+            } else if (runs > 0 && (r.pos >> 3) + 8 <= safe_bytes) {
+                const unsigned bnd = (unsigned) (l < 2 ? part[l + 2] : total);
+                const uint8_t *next = r.buf + (r.pos >> 3) + 8;
+                const uint8_t *const stop = r.buf + safe_bytes;
+                uint64_t win;
+                int nbits = 64 - (int) (r.pos & 7), got = 0;
+                {
+                    uint64_t w8;
+                    memcpy(&w8, next - 8, 8);
+#if !(defined(__BYTE_ORDER__) && (__BYTE_ORDER__ == __ORDER_BIG_ENDIAN__))
+                    w8 = __builtin_bswap64(w8);
+#endif
+                    win = w8 << (r.pos & 7);
+                }
+                for (;;) {
+                    unsigned row;
+                    uint32_t e;
+                    pos = cur + run;
+                    if (pos >= bnd || pos < cur || runs <= 0 || next > stop) {
+                        break;
+                    }
+                    if (nbits < 32) {
+                        uint32_t w4;
+                        memcpy(&w4, next, 4);
+#if !(defined(__BYTE_ORDER__) && (__BYTE_ORDER__ == __ORDER_BIG_ENDIAN__))
+                        w4 = __builtin_bswap32(w4);
+#endif
+                        win |= (uint64_t) w4 << (32 - nbits);
+                        next += 4;
+                        nbits += 32;
+                    }
+                    row = l < 0 ? (unsigned) HZT_ROW_LL : (unsigned) (vk >> (3 + l));
+                    if (row >= HZT_ROWS || (l >= 0 && row >= HZT_KMAX)) {
+                        break;
+                    }
+                    e = hz_tab[row * HZT_SIZE + (uint32_t) (win >> (64 - HZT_BITS))];
+                    if (!HZT_LEN(e)) {
+                        break;
+                    }
+                    win <<= HZT_LEN(e);
+                    nbits -= HZT_LEN(e);
+                    runs--;
+                    if (l >= 0) {
+                        vk += HZT_QNZ(e) ? 1 : -(vk > 0);
+                    }
+                    if (n < cap && pos != 0) {
+                        syms[n].pos = pos;
+                        syms[n].v = HZT_VAL(e);
+                        n++;
+                    }
+                    cur = pos + 1;
+                    run = HZT_RUN(e);
+                    got++;
+                }
+                r.pos = (size_t) (next - r.buf) * 8 - (size_t) nbits;
+                if (got < 4) {
+                    idle = 32; /* not table country (large values): do not keep setting up windows */
+                }
+            }
+            pos = cur + run;
             if (pos >= (unsigned) total || pos < cur) {
                 break;
             }
