@@ -190,8 +190,9 @@ def load(emu=False):
         "dsvcu_dequant_plane": (ip, [vp, vp, ip, ip, P(DSVCU_FMETA), ip, P(ip), ip]),
         "dsv_set_device_entropy_decode": (ip, [ip]),
         "dsv_set_device_entropy_limits": (None, [C.c_long, C.c_long, ip]),
-        "dsvcu_parse_begin": (ip, [vp, P(DSVCU_PLANE_BITS), ip, ip]),
-        "dsvcu_parse_end": (ip, [vp, ip, ip, P(ip)]),
+        "dsvcu_parse_begin": (ip, [vp, P(DSVCU_PLANE_BITS), ip, ip, vp, ip, ip]),
+        "dsvcu_parse_end": (ip, [vp, ip, ip, P(ip), P(ip)]),
+        "dsvcu_set_side_parsed": (ip, [vp, ip, ip, ip]),
         "dsvcu_parse_planes": (ip, [vp, P(DSVCU_PLANE_BITS), ip, P(ip)]),
         "dsvcu_parsed_count": (ip, [vp, ip, ip]),
         "dsvcu_dequant_parsed": (ip, [vp, vp, ip, P(DSVCU_FMETA), ip, ip]),

@@ -162,6 +162,12 @@ struct dsvcu_ctx {
         int *h_meta, *d_meta;     /* HZ_META_WORDS per plane */
         int spans_cap, n;
         int n_early;              /* planes [0, n_early) are part 0 of the batch, the rest part 1 */
+        /* side information of the batch's inter pictures (k_hzcc.cuh, hz_parse_side) */
+        HzSide *h_sides, *d_sides;
+        int *h_side_ok, *d_side_ok;
+        uint8_t *d_side_out;      /* one block [vector field | block flags] per picture */
+        size_t side_out_cap, side_stride;
+        int sides_cap, nsd, nsd_early;
         int pending[2];           /* part begun, result not collected yet */
 #ifndef DSVCU_EMU
         cudaEvent_t ev_parsed[2]; /* meta words of the part are in pinned memory */
@@ -379,6 +385,11 @@ parse_set_free(dsvcu_ctx *c, int i)
     if (S->d_spans) dsvcu_free_dev(S->d_spans);
     if (S->h_meta) dsvcu_free_host(S->h_meta);
     if (S->d_meta) dsvcu_free_dev(S->d_meta);
+    if (S->h_sides) dsvcu_free_host(S->h_sides);
+    if (S->d_sides) dsvcu_free_dev(S->d_sides);
+    if (S->h_side_ok) dsvcu_free_host(S->h_side_ok);
+    if (S->d_side_ok) dsvcu_free_dev(S->d_side_ok);
+    if (S->d_side_out) dsvcu_free_dev(S->d_side_out);
 #ifndef DSVCU_EMU
     if (S->ev_parsed[0]) cudaEventDestroy(S->ev_parsed[0]);
     if (S->ev_parsed[1]) cudaEventDestroy(S->ev_parsed[1]);
@@ -1438,14 +1449,30 @@ parse_set_pending(const dsvcu_ctx *c, int set)
 }
 
 extern "C" int
-dsvcu_parse_begin(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n, int n_early)
+dsvcu_parse_begin(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n, int n_early, const dsvcu_side_bits *sd, int nsd,
+                  int nsd_early)
 {
     size_t total = 0, nsyms = 0, at = 0, sat = 0;
-    int i, set = 0;
+    int i, set = 0, max_blk = 0;
     HzJob J;
     dsvcu_ctx::ParseSet *S;
 
     if (n <= 0) return fail_msg("dsvcu_parse_begin: no planes");
+    if (!sd) nsd = nsd_early = 0;
+    if (nsd < 0 || nsd_early < 0 || nsd_early > nsd) return fail_msg("dsvcu_parse_begin: bad split");
+    for (i = 0; i < nsd; i++) {
+        int k;
+        if (!sd[i].base || sd[i].base_len > 0x0fffffffu || sd[i].nbh <= 0 || sd[i].nbv <= 0 ||
+            (size_t) sd[i].nbh * sd[i].nbv > 0x00ffffffu) {
+            return fail_msg("dsvcu_parse_begin: bad side information");
+        }
+        for (k = 0; k < HZ_SIDE_NSUB; k++) {
+            if ((size_t) sd[i].off[k] + sd[i].len[k] > sd[i].base_len) return fail_msg("dsvcu_parse_begin: bad side information");
+        }
+        if (sd[i].nbh * sd[i].nbv > max_blk) max_blk = sd[i].nbh * sd[i].nbv;
+        total += (((size_t) sd[i].base_len + 7) & ~(size_t) 7) + 16;
+    }
+    if (max_blk && ensure_blocks(c, max_blk)) return -1;
     /* the set that was begun longer ago; never one whose result has not been collected */
     if (n_early < 0 || n_early > n) return fail_msg("dsvcu_parse_begin: bad split");
     if (parse_set_pending(c, 0) && parse_set_pending(c, 1)) return fail_msg("dsvcu_parse_begin: two batches already in flight");
@@ -1501,6 +1528,37 @@ dsvcu_parse_begin(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n, int n_early)
             S->spans_cap = cap;
         }
     }
+    if (nsd > S->sides_cap || (size_t) nsd * c->side_bytes > S->side_out_cap) {
+        CK(ctx_wait(c));
+#ifndef DSVCU_EMU
+        CK(cudaStreamSynchronize(c->pstream));
+        CK(cudaStreamSynchronize(c->pstream2));
+#endif
+        if (nsd > S->sides_cap) {
+            const int cap = nsd + 16;
+            if (S->h_sides) dsvcu_free_host(S->h_sides);
+            if (S->d_sides) dsvcu_free_dev(S->d_sides);
+            if (S->h_side_ok) dsvcu_free_host(S->h_side_ok);
+            if (S->d_side_ok) dsvcu_free_dev(S->d_side_ok);
+            S->h_sides = S->d_sides = NULL;
+            S->h_side_ok = S->d_side_ok = NULL;
+            S->sides_cap = 0;
+            CK(dsvcu_malloc_host(&S->h_sides, (size_t) cap * sizeof(HzSide)));
+            CK(dsvcu_malloc(&S->d_sides, (size_t) cap * sizeof(HzSide)));
+            CK(dsvcu_malloc_host(&S->h_side_ok, (size_t) cap * sizeof(int)));
+            CK(dsvcu_malloc(&S->d_side_ok, (size_t) cap * sizeof(int)));
+            S->sides_cap = cap;
+        }
+        if ((size_t) nsd * c->side_bytes > S->side_out_cap) {
+            const size_t cap = (size_t) (nsd + 8) * c->side_bytes;
+            if (S->d_side_out) dsvcu_free_dev(S->d_side_out);
+            S->d_side_out = NULL;
+            S->side_out_cap = 0;
+            CK(dsvcu_malloc(&S->d_side_out, cap));
+            S->side_out_cap = cap;
+        }
+    }
+    S->side_stride = c->side_bytes;
     for (i = 0; i < n; i++) {
         HzSpan *sp = &S->h_spans[i];
         const size_t padded = ((size_t) pl[i].len + 7) & ~(size_t) 7;
@@ -1520,6 +1578,23 @@ dsvcu_parse_begin(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n, int n_early)
         sp->sym_cap = pairs;
         at += padded;
         sat += pairs;
+    }
+    for (i = 0; i < nsd; i++) {
+        HzSide *D = &S->h_sides[i];
+        const size_t padded = (((size_t) sd[i].base_len + 7) & ~(size_t) 7) + 16;
+        int k;
+        memcpy(S->h_bits + at, sd[i].base, sd[i].base_len);
+        memset(S->h_bits + at + sd[i].base_len, 0, padded - sd[i].base_len);
+        for (k = 0; k < HZ_SIDE_NSUB; k++) {
+            D->off[k] = (uint32_t) at + sd[i].off[k];
+            D->len[k] = sd[i].len[k];
+        }
+        D->nbh = sd[i].nbh;
+        D->nbv = sd[i].nbv;
+        D->flips = sd[i].flips;
+        D->out_off = (uint32_t) ((size_t) i * c->side_bytes);
+        D->mv_bytes = (uint32_t) c->side_mv_bytes;
+        at += padded;
     }
     nsyms = sat;
     if (nsyms + 1 > S->syms_cap) {
@@ -1543,32 +1618,41 @@ dsvcu_parse_begin(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n, int n_early)
 #endif
     CK(dsvcu_h2d_async(S->d_bits, S->h_bits, at + 16, ps));
     CK(dsvcu_h2d_async(S->d_spans, S->h_spans, (size_t) n * sizeof(HzSpan), ps));
+    if (nsd) CK(dsvcu_h2d_async(S->d_sides, S->h_sides, (size_t) nsd * sizeof(HzSide), ps));
     J.bits = S->d_bits;
     J.syms = S->d_syms;
+    J.side_out = S->d_side_out;
 #ifndef DSVCU_EMU
     CK(cudaEventRecord(S->ev_bits, ps));
     CK(cudaStreamWaitEvent(c->pstream2, S->ev_bits, 0));
 #endif
     for (int part = 0; part < 2; part++) {
         const int first = part ? n_early : 0, cnt = part ? n - n_early : n_early;
+        const int sfirst = part ? nsd_early : 0, scnt = part ? nsd - nsd_early : nsd_early;
 #ifndef DSVCU_EMU
         const cudaStream_t st = part ? c->pstream2 : c->pstream;
 #else
         const dsvcu_stream_t st = 0;
 #endif
         S->pending[part] = 0;
-        if (!cnt) continue;
+        if (!cnt && !scnt) continue;
         J.spans = S->d_spans + first;
         J.nspans = cnt;
         J.meta = S->d_meta + first * HZ_META_WORDS;
+        J.sides = S->d_sides + sfirst;
+        J.nsides = scnt;
+        J.side_ok = S->d_side_ok + sfirst;
 #ifndef DSVCU_EMU
-        DSVCU_LAUNCH(k_hzcc_parse, (cnt + HZ_WARPS - 1) / HZ_WARPS, HZ_WARPS * 32, 0, st, J);
+        DSVCU_LAUNCH(k_hzcc_parse, (cnt + scnt + HZ_WARPS - 1) / HZ_WARPS, HZ_WARPS * 32, 0, st, J);
 #else
-        DSVCU_LAUNCH(k_hzcc_parse, cnt, 32, 0, st, J);
+        DSVCU_LAUNCH(k_hzcc_parse, cnt + scnt, 32, 0, st, J);
 #endif
         CK_LAUNCH(c);
-        CK(dsvcu_d2h_async(S->h_meta + first * HZ_META_WORDS, S->d_meta + first * HZ_META_WORDS,
-                           (size_t) cnt * HZ_META_WORDS * sizeof(int), st));
+        if (cnt) {
+            CK(dsvcu_d2h_async(S->h_meta + first * HZ_META_WORDS, S->d_meta + first * HZ_META_WORDS,
+                               (size_t) cnt * HZ_META_WORDS * sizeof(int), st));
+        }
+        if (scnt) CK(dsvcu_d2h_async(S->h_side_ok + sfirst, S->d_side_ok + sfirst, (size_t) scnt * sizeof(int), st));
 #ifndef DSVCU_EMU
         CK(cudaEventRecord(S->ev_parsed[part], st));
 #endif
@@ -1576,12 +1660,14 @@ dsvcu_parse_begin(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n, int n_early)
     }
     S->n = n;
     S->n_early = n_early;
+    S->nsd = nsd;
+    S->nsd_early = nsd_early;
     c->pset_last = set;
     return set;
 }
 
 extern "C" int
-dsvcu_parse_end(dsvcu_ctx *c, int set, int part, int *ok)
+dsvcu_parse_end(dsvcu_ctx *c, int set, int part, int *ok, int *side_ok)
 {
     dsvcu_ctx::ParseSet *S;
     int i;
@@ -1596,17 +1682,39 @@ dsvcu_parse_end(dsvcu_ctx *c, int set, int part, int *ok)
     for (i = part ? S->n_early : 0; i < (part ? S->n : S->n_early); i++) {
         ok[i] = S->h_meta[i * HZ_META_WORDS + HZ_META_OK] == 1;
     }
+    for (i = part ? S->nsd_early : 0; side_ok && i < (part ? S->nsd : S->nsd_early); i++) {
+        side_ok[i] = S->h_side_ok[i] == 1;
+    }
     return 0;
 }
 
-/* a batch of one part, begun and collected in one call: the batch is set 0 or 1 (returned) */
+/* a batch of one part without side information, begun and collected in one call: the batch is
+ * set 0 or 1 (returned) */
 extern "C" int
 dsvcu_parse_planes(dsvcu_ctx *c, const dsvcu_plane_bits *pl, int n, int *ok)
 {
-    const int set = dsvcu_parse_begin(c, pl, n, n);
+    const int set = dsvcu_parse_begin(c, pl, n, n, NULL, 0, 0);
     if (set < 0) return -1;
-    if (dsvcu_parse_end(c, set, 0, ok)) return -1;
+    if (dsvcu_parse_end(c, set, 0, ok, NULL)) return -1;
     return set;
+}
+
+/* the vector field and block flags of picture `side` of a collected batch become the
+ * context's current side information: the counterpart of dsvcu_set_side, device to device */
+extern "C" int
+dsvcu_set_side_parsed(dsvcu_ctx *c, int set, int side, int nblocks)
+{
+    const dsvcu_ctx::ParseSet *S;
+    if (set < 0 || set > 1) return fail_msg("dsvcu_set_side_parsed: no such batch");
+    S = &c->pset[set];
+    if (side < 0 || side >= S->nsd || S->pending[side >= S->nsd_early] || S->h_side_ok[side] != 1 ||
+        nblocks != S->h_sides[side].nbh * S->h_sides[side].nbv || S->side_stride != c->side_bytes) {
+        return fail_msg("dsvcu_set_side_parsed: no such picture");
+    }
+    if (ensure_blocks(c, nblocks)) return -1;
+    CK(dsvcu_d2d_async(c->d_side[c->side_cur], S->d_side_out + (size_t) side * S->side_stride,
+                       c->side_mv_bytes + (size_t) nblocks, c->stream));
+    return 0;
 }
 
 /* number of symbols the device parser found in plane `span` of a collected batch (tests) */

@@ -58,12 +58,34 @@ struct HzSpan {
     uint32_t sym_cap;
 };
 
+/* The side information of one inter picture (reference dsv_decoder.c: decode_stability_blocks,
+ * decode_motion; spec B.2.3.1, B.2.3.4): six length-prefixed sub-streams -- skip bits, then
+ * mode bits, vector x, vector y, intra sub-block masks + DC, EPRM bits -- decoded into the
+ * picture's vector field and block flags, in the layout dsvcu_set_side uploads. */
+#define HZ_SIDE_NSUB 6
+#define HZ_SIDE_SKIP 0 /* then the five of DSV_SUB_*: mode, x, y, sbim, eprm */
+
+struct HzSide {
+    uint32_t off[HZ_SIDE_NSUB]; /* first byte of each sub-stream in the batch buffer (multiples of 4 apart
+                                 * from the base: see `shift`) */
+    uint32_t len[HZ_SIDE_NSUB]; /* its coded length in bytes; the readers may look 8 bytes further */
+    int nbh, nbv;               /* blocks per row / column */
+    int flips;                  /* bit i: the bits of RLE stream i are stored inverted (0 skip, 1 mode, 2 eprm) */
+    uint32_t out_off;           /* this picture's block of `side_out` */
+    uint32_t mv_bytes;          /* size of the vector part of that block; the flags follow it */
+};
+
 struct HzJob {
     const uint8_t *bits; /* batch buffer, 16 zero bytes behind the last plane */
     const HzSpan *spans;
     int nspans;
     dsvcu_sym *syms;
     int *meta; /* HZ_META_WORDS per span */
+    /* side-information chains of the batch part, handled by the warps behind the planes' */
+    const HzSide *sides;
+    int nsides;
+    uint8_t *side_out;
+    int *side_ok;
 };
 
 /* big-endian bit reader: `win` holds the next `n` bits left-aligned (zeros below them); the
@@ -364,8 +386,163 @@ hz_parse_plane(const HzJob &J, const HzSpan &S, int *meta, const hz_tab_t tab)
     return 1;
 }
 
+/* ---- side information ---- */
+
+/* a reader over an arbitrarily aligned sub-stream: the window is filled from the 4-byte word
+ * that holds the first byte, and the bits in front of it are dropped */
+DSVCU_DEV void
+hz_open_at(HzRd &r, const uint8_t *base, uint32_t off, uint32_t len)
+{
+    const uint32_t a = off & ~3u, lead = off & 3u;
+    hz_open(r, base + a, len + lead);
+    hz_skip(r, (int) lead * 8);
+}
+
+/* bits consumed from the start of the SUB-STREAM (hz_open_at) */
+DSVCU_DEV uint32_t
+hz_pos_at(const HzRd &r, uint32_t off)
+{
+    return hz_pos(r) - (off & 3u) * 8u;
+}
+
+struct HzRle {
+    HzRd r;
+    uint32_t nz;
+};
+
+/* dsv_rle_rd_get (bs.c:277-330): zero-bit run lengths in exp-Golomb */
+DSVCU_DEV int
+hz_rle_get(HzRle &e)
+{
+    if (e.nz == 0) {
+        e.nz = hz_ueg(e.r);
+        return e.nz == 0;
+    }
+    e.nz--;
+    return e.nz == 0;
+}
+
+DSVCU_DEV int
+hz_iabs(int v)
+{
+    return v < 0 ? -v : v;
+}
+
+DSVCU_DEV int
+hz_grad_pick(int left, int top, int topleft) /* dsv.c:324-331 */
+{
+    const int g = left + top - topleft;
+    return hz_iabs(g - left) < hz_iabs(g - top) ? left : top;
+}
+
+#define HZ_BD_STABLE 1
+#define HZ_BD_SKIP 4
+#define HZ_BD_INTRA 16
+#define HZ_BD_EPRM_BIT 5
+#define HZ_MVF_INTRA 1u
+#define HZ_MVF_EPRM 2u
+#define HZ_MVF_SKIP 8u
+
+/* One picture: the walk of host/dsv_dec.c read_stability + read_motion.  Returns 1 when no
+ * reader went past the end of its sub-stream (what happens behind it depends on how the
+ * host's reader is positioned; such pictures are the host's business). */
+DSVCU_DEV int
+hz_parse_side(const HzJob &J, const HzSide &D)
+{
+    dsvcu_mv *mvs = (dsvcu_mv *) (J.side_out + D.out_off);
+    uint8_t *bd = J.side_out + D.out_off + D.mv_bytes;
+    const int nbh = D.nbh, nbv = D.nbv;
+    HzRle skip, mode, eprm;
+    HzRd rx, ry, rb;
+    hz_open_at(skip.r, J.bits, D.off[0], D.len[0] + 8);
+    hz_open_at(mode.r, J.bits, D.off[1], D.len[1] + 8);
+    hz_open_at(rx, J.bits, D.off[2], D.len[2] + 8);
+    hz_open_at(ry, J.bits, D.off[3], D.len[3] + 8);
+    hz_open_at(rb, J.bits, D.off[4], D.len[4] + 8);
+    hz_open_at(eprm.r, J.bits, D.off[5], D.len[5] + 8);
+    skip.nz = mode.nz = eprm.nz = 0;
+    const int f_skip = D.flips & 1, f_mode = (D.flips >> 1) & 1, f_eprm = (D.flips >> 2) & 1;
+    for (int j = 0; j < nbv; j++) {
+        for (int i = 0; i < nbh; i++) {
+            const int idx = i + j * nbh;
+            dsvcu_mv m;
+            m.x = m.y = 0;
+            m.flags = 0;
+            m.err = 0;
+            m.dc = 0;
+            m.submask = 0;
+            m.pad_[0] = m.pad_[1] = m.pad_[2] = 0;
+            if (hz_rle_get(skip) ^ f_skip) {
+                m.flags = HZ_MVF_SKIP;
+                mvs[idx] = m;
+                bd[idx] = (uint8_t) (HZ_BD_SKIP | HZ_BD_STABLE);
+                continue;
+            }
+            const int md = hz_rle_get(mode) ^ f_mode, ep = hz_rle_get(eprm) ^ f_eprm;
+            int flags = ep << HZ_BD_EPRM_BIT;
+            m.flags = (md ? HZ_MVF_INTRA : 0u) | (ep ? HZ_MVF_EPRM : 0u);
+            /* predictor from the left, top and top-left vectors (dsv_movec_pred, dsv.c:333-357) */
+            int lx = 0, ly = 0, tx = 0, ty = 0, dx = 0, dy = 0;
+            dsvcu_mv L, T;
+            L.x = L.y = 0;
+            L.flags = 0;
+            T = L;
+            if (i > 0) {
+                L = mvs[idx - 1];
+                lx = L.x;
+                ly = L.y;
+            }
+            if (j > 0) {
+                T = mvs[idx - nbh];
+                tx = T.x;
+                ty = T.y;
+                if (i > 0) {
+                    const dsvcu_mv Q = mvs[idx - nbh - 1];
+                    dx = Q.x;
+                    dy = Q.y;
+                }
+            }
+            int px = hz_grad_pick(lx, tx, dx), py = hz_grad_pick(ly, ty, dy);
+            if (md) {
+                px = (px + 2) >> 2;
+                py = (py + 2) >> 2;
+            }
+            int vx = (int16_t) (hz_seg(rx) + px), vy = (int16_t) (hz_seg(ry) + py);
+            if (md) {
+                vx = (int16_t) (vx * 4); /* intra vectors are full-pel */
+                vy = (int16_t) (vy * 4);
+                m.submask = hz_bits(rb, 1) ? (uint8_t) 15 : (uint8_t) hz_bits(rb, 4);
+                m.dc = hz_bits(rb, 1) ? (uint16_t) (hz_bits(rb, 8) | 0x100u) : (uint16_t) 0;
+                flags |= HZ_BD_INTRA;
+            }
+            m.x = (int16_t) vx;
+            m.y = (int16_t) vy;
+            mvs[idx] = m;
+            /* dsv_neighbordif (dsv.c:359-407): distance to the left and top vectors */
+            if (!(hz_iabs(vx) < 2 && hz_iabs(vy) < 2)) {
+                int ax = vx, ay = vy, bx = vx, by = vy;
+                if (i > 0 && (L.x | L.y) != 0 && !(L.flags & HZ_MVF_SKIP)) {
+                    ax = L.x;
+                    ay = L.y;
+                }
+                if (j > 0 && (T.x | T.y) != 0 && !(T.flags & HZ_MVF_SKIP)) {
+                    bx = T.x;
+                    by = T.y;
+                }
+                const int nd = hz_iabs(ax - vx) + hz_iabs(ay - vy) + hz_iabs(bx - vx) + hz_iabs(by - vy);
+                if (nd / 3 > 8) flags |= HZ_BD_STABLE;
+            }
+            bd[idx] = (uint8_t) flags;
+        }
+    }
+    return hz_pos_at(skip.r, D.off[0]) <= D.len[0] * 8u && hz_pos_at(mode.r, D.off[1]) <= D.len[1] * 8u &&
+           hz_pos_at(rx, D.off[2]) <= D.len[2] * 8u && hz_pos_at(ry, D.off[3]) <= D.len[3] * 8u &&
+           hz_pos_at(rb, D.off[4]) <= D.len[4] * 8u && hz_pos_at(eprm.r, D.off[5]) <= D.len[5] * 8u;
+}
+
 /* One chain per warp (lane 0 walks it; a chain is latency-bound and wants a scheduler slot,
- * not lanes), HZ_WARPS chains per CTA sharing the prefix table in shared memory (40 KB). */
+ * not lanes), HZ_WARPS chains per CTA sharing the prefix table in shared memory (40 KB).
+ * Chains 0 .. nspans-1 are coefficient planes, the nsides behind them side information. */
 #define HZ_WARPS 8
 
 DSVCU_KERNEL void __launch_bounds__(HZ_WARPS * 32)
@@ -376,7 +553,11 @@ k_hzcc_parse(HzJob J)
     DSVCU_SYNC();
     const int per_cta = DSVCU_NTH >= 32 ? DSVCU_NTH >> 5 : 1;
     const int s = (int) blockIdx.x * per_cta + (DSVCU_TID >> 5);
-    if ((DSVCU_TID & 31) != 0 || s >= J.nspans) return;
+    if ((DSVCU_TID & 31) != 0 || s >= J.nspans + J.nsides) return;
+    if (s >= J.nspans) {
+        J.side_ok[s - J.nspans] = hz_parse_side(J, J.sides[s - J.nspans]);
+        return;
+    }
     int *meta = J.meta + s * HZ_META_WORDS;
     meta[HZ_META_OK] = hz_parse_plane(J, J.spans[s], meta, hz_tab_ref(tab));
 }

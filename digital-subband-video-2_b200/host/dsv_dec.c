@@ -75,11 +75,14 @@ typedef struct {
     double ph_ms[DP_N], ph_t0, ph_wall[DP_N], ph_w0;
     int ph_frames;
     int ph_where[3]; /* pictures parsed by the device (part 0, part 1) and by the host */
+    int ph_side_dev; /* pictures whose side information was decoded on the device too */
     /* batches of pictures whose coefficient planes are entropy-decoded on the device ahead of
      * time (dsv_dec_preparse), one per parse set of the context: first span of picture i in
      * the batch, or -1 where the host parses */
     struct {
         int *first;
+        int *side;   /* index of the picture's side information in the batch, or -1 (host) */
+        int nsides, nsides_early;
         int n, cap;
         int nspans;  /* planes handed to the device */
         int nearly;  /* of which part 0 (short planes, needed first); the rest is part 1 */
@@ -160,8 +163,8 @@ state_free(DEC_STATE *s)
             at += snprintf(line + at, sizeof(line) - (size_t) at, " %s %.3f (%.3f);", dp_name[i],
                            s->ph_ms[i] / s->ph_frames, s->ph_wall[i] / s->ph_frames);
         }
-        fprintf(stderr, "%s planes parsed on the device for %d + %d pictures (part 0 + part 1), on the host for %d\n",
-                line, s->ph_where[0], s->ph_where[1], s->ph_where[2]);
+        fprintf(stderr, "%s planes parsed on the device for %d + %d pictures (part 0 + part 1; side information of %d), "
+                "on the host for %d\n", line, s->ph_where[0], s->ph_where[1], s->ph_side_dev, s->ph_where[2]);
     }
     if (s->ctx) {
         dsvcu_sync(s->ctx);
@@ -175,6 +178,8 @@ state_free(DEC_STATE *s)
     free(s->mvs);
     free(s->pre[0].first);
     free(s->pre[1].first);
+    free(s->pre[0].side);
+    free(s->pre[1].side);
     free(s);
 }
 
@@ -549,7 +554,7 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
     DSV_FRAME *host;
     DSV_FNUM fno;
     int stats[DSV_MAX_STAT];
-    int i, nblk, quant, is_ref, do_filter, isP, good_planes = 0, on_device = 0;
+    int i, nblk, quant, is_ref, do_filter, isP, good_planes = 0, on_device = 0, planes_dev, side_dev;
 
     if (g_prof < 0) {
         g_prof = getenv("DSV_PROFILE") ? atoi(getenv("DSV_PROFILE")) : 0;
@@ -603,52 +608,64 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
     p->reserved = dsv_br_bit(br) ? (int) dsv_br_bits(br, 15) : 0;
     dsv_br_align(br);
 
-    if (nblk > s->nblk_cap) {
-        free(s->blockdata);
-        free(s->mvs);
-        s->blockdata = malloc((size_t) nblk);
-        s->mvs = malloc((size_t) nblk * sizeof(DSV_MV));
-        s->nblk_cap = nblk;
-        if (!s->blockdata || !s->mvs) {
-            free(s->blockdata);
-            free(s->mvs);
-            s->blockdata = NULL;
-            s->mvs = NULL;
-            s->nblk_cap = 0;
-            return DSV_DEC_ERROR;
-        }
-    }
-    memset(s->blockdata, 0, (size_t) nblk);
-    memset(s->mvs, 0, (size_t) nblk * sizeof(DSV_MV));
-    if (read_stability(br, s->blockdata, nblk, isP, stats) ||
-        (isP ? read_motion(br, p, s->blockdata, s->mvs, stats) : read_intra_meta(br, s->blockdata, nblk, stats))) {
-        DSV_ERROR(("side information runs past the end of the packet"));
-        return DSV_DEC_ERROR;
-    }
-    dsv_br_align(br);
-
-    p->temporal_mc = isP ? (int) DSV_TEMPORAL_MC(fno) : 0;
-    dsv_fmeta_from_params(&fm, p, isP, fno);
-    if (tls_async && tls_direct_out) {
-        /* the previous picture may still be reading the staging set just used */
-        GPU(dsvcu_staging_flip(s->ctx));
-    }
-    DPROF(s, DP_SIDE);
-    GPU(dsvcu_set_side(s->ctx, s->blockdata, isP ? s->mvs : NULL, nblk));
-    DPROF(s, DP_QUEUE);
-
-    /* intra pictures are reconstructed straight into the output picture;
-     * inter pictures into the residual frame, then predicted + added */
-    dst = s->pic[s->cur];
-    ref = s->pic[s->cur ^ 1];
+    /* planes (and, for an inter picture, side information) that went ahead to the device parser */
     if (tls_parsed >= 0 && tls_parsed < s->pre[tls_parsed_set].n && s->pre[tls_parsed_set].first[tls_parsed] >= 0) {
+        DPROF(s, DP_SIDE);
         if (preparse_collect(s, tls_parsed_set,
                              s->pre[tls_parsed_set].first[tls_parsed] >= s->pre[tls_parsed_set].nearly)) {
             return DSV_DEC_ERROR;
         }
         DPROF(s, DP_PREPARSE);
     }
-    if (tls_parsed >= 0 && tls_parsed < s->pre[tls_parsed_set].n && s->pre[tls_parsed_set].first[tls_parsed] >= 0) {
+    planes_dev = tls_parsed >= 0 && tls_parsed < s->pre[tls_parsed_set].n && s->pre[tls_parsed_set].first[tls_parsed] >= 0;
+    side_dev = planes_dev && isP && !d->draw_info && s->pre[tls_parsed_set].side[tls_parsed] >= 0;
+
+    if (!side_dev) {
+        if (nblk > s->nblk_cap) {
+            free(s->blockdata);
+            free(s->mvs);
+            s->blockdata = malloc((size_t) nblk);
+            s->mvs = malloc((size_t) nblk * sizeof(DSV_MV));
+            s->nblk_cap = nblk;
+            if (!s->blockdata || !s->mvs) {
+                free(s->blockdata);
+                free(s->mvs);
+                s->blockdata = NULL;
+                s->mvs = NULL;
+                s->nblk_cap = 0;
+                return DSV_DEC_ERROR;
+            }
+        }
+        memset(s->blockdata, 0, (size_t) nblk);
+        memset(s->mvs, 0, (size_t) nblk * sizeof(DSV_MV));
+        if (read_stability(br, s->blockdata, nblk, isP, stats) ||
+            (isP ? read_motion(br, p, s->blockdata, s->mvs, stats) : read_intra_meta(br, s->blockdata, nblk, stats))) {
+            DSV_ERROR(("side information runs past the end of the packet"));
+            return DSV_DEC_ERROR;
+        }
+        dsv_br_align(br);
+    }
+
+    p->temporal_mc = isP ? (int) DSV_TEMPORAL_MC(fno) : 0;
+    dsv_fmeta_from_params(&fm, p, isP, fno);
+    if (tls_async && tls_direct_out && !(side_dev && planes_dev)) {
+        /* the previous picture may still be reading the staging set just used */
+        GPU(dsvcu_staging_flip(s->ctx));
+    }
+    DPROF(s, DP_SIDE);
+    if (side_dev) {
+        /* vector field and block flags were decoded on the device, with the planes */
+        GPU(dsvcu_set_side_parsed(s->ctx, s->pre[tls_parsed_set].cset, s->pre[tls_parsed_set].side[tls_parsed], nblk));
+    } else {
+        GPU(dsvcu_set_side(s->ctx, s->blockdata, isP ? s->mvs : NULL, nblk));
+    }
+    DPROF(s, DP_QUEUE);
+
+    /* intra pictures are reconstructed straight into the output picture;
+     * inter pictures into the residual frame, then predicted + added */
+    dst = s->pic[s->cur];
+    ref = s->pic[s->cur ^ 1];
+    if (planes_dev) {
         /* the symbols of all three planes are already on the device */
         GPU(dsvcu_dequant_parsed(s->ctx, s->coefs, quant, &fm, s->pre[tls_parsed_set].cset,
                                  s->pre[tls_parsed_set].first[tls_parsed]));
@@ -656,6 +673,7 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
         good_planes = 7;
         on_device = 1;
         s->ph_where[s->pre[tls_parsed_set].first[tls_parsed] >= s->pre[tls_parsed_set].nearly]++;
+        s->ph_side_dev += side_dev;
     } else {
         s->ph_where[2]++;
     }
@@ -721,13 +739,16 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
  * of decode_picture; returns -1 for anything unusual (the packet is then parsed the normal
  * way, which knows what to do with damaged input). */
 static int
-locate_planes(const DEC_STATE *s, const uint8_t *pkt, size_t len, dsvcu_plane_bits out[3])
+locate_planes(const DEC_STATE *s, const DSV_META *meta, const uint8_t *pkt, size_t len, dsvcu_plane_bits out[3],
+              dsvcu_side_bits *side)
 {
     DSV_BITRD br;
     const uint8_t *p;
     size_t n, at;
-    int type, isP, i, nsub;
+    unsigned ex, ey;
+    int type, isP, i, nsub, stats;
 
+    side->base = NULL;
     if (len < 64) {
         return -1;
     }
@@ -741,12 +762,14 @@ locate_planes(const DEC_STATE *s, const uint8_t *pkt, size_t len, dsvcu_plane_bi
     dsv_br_align(&br);
     (void) dsv_br_bits(&br, 32);
     dsv_br_align(&br);
-    if (dsv_br_ueg(&br) > 2 || dsv_br_ueg(&br) > 2) {
+    ex = dsv_br_ueg(&br);
+    ey = dsv_br_ueg(&br);
+    if (ex > 2 || ey > 2) {
         return -1;
     }
     dsv_br_align(&br);
-    (void) dsv_br_bits(&br, 3); /* stable + (maintain, ringing | mode, eprm) */
-    (void) dsv_br_bit(&br);     /* do_filter */
+    stats = (int) dsv_br_bits(&br, 3); /* stable + (maintain, ringing | mode, eprm), first bit on top */
+    (void) dsv_br_bit(&br);            /* do_filter */
     (void) dsv_br_bits(&br, DSV_MAX_QP_BITS);
     if (dsv_br_bit(&br)) {
         (void) dsv_br_bits(&br, 15);
@@ -761,9 +784,25 @@ locate_planes(const DEC_STATE *s, const uint8_t *pkt, size_t len, dsvcu_plane_bi
         if (open_substream(&br, &p, &n)) {
             return -1;
         }
+        if (isP) {
+            if (i == 0) {
+                side->base = p;
+            }
+            side->off[i] = (uint32_t) (p - side->base);
+            side->len[i] = (uint32_t) n;
+        }
     }
     dsv_br_align(&br);
     at = dsv_br_byte(&br);
+    if (isP) {
+        /* skip bits, then DSV_SUB_MODE, _MV_X, _MV_Y, _SBIM, _EPRM in the order they are stored;
+         * the readers look up to 8 bytes past a sub-stream (into the planes that follow) */
+        side->base_len = (uint32_t) ((size_t) (pkt + at - side->base) + 8);
+        side->nbh = DSV_UDIV_ROUND_UP(meta->width, 16 << ex);
+        side->nbv = DSV_UDIV_ROUND_UP(meta->height, 16 << ey);
+        /* a statistic bit equal to DSV_ZERO_MARKER (1) says the bits of that stream are stored inverted */
+        side->flips = ((stats >> 2) & 1) | (((stats >> 1) & 1) << 1) | ((stats & 1) << 2);
+    }
     for (i = 0; i < 3; i++) {
         size_t plen;
         int cw, ch;
@@ -821,7 +860,8 @@ dsv_dec_preparse(DSV_DECODER *d, const uint8_t *const *pkt, const size_t *len, i
 {
     DEC_STATE *s;
     dsvcu_plane_bits *pl;
-    int i, m = 0, set, part;
+    dsvcu_side_bits *sd, one;
+    int i, m = 0, ms = 0, set, part;
 
     if (!d->got_metadata || n <= 0) {
         return -1;
@@ -835,7 +875,10 @@ dsv_dec_preparse(DSV_DECODER *d, const uint8_t *const *pkt, const size_t *len, i
     }
     DPROF_START(s);
     pl = malloc((size_t) n * 3 * sizeof(*pl));
-    if (!pl) {
+    sd = malloc((size_t) n * sizeof(*sd));
+    if (!pl || !sd) {
+        free(pl);
+        free(sd);
         return -1;
     }
     /* the slot that is not waiting for its result; failing that the older one */
@@ -843,41 +886,57 @@ dsv_dec_preparse(DSV_DECODER *d, const uint8_t *const *pkt, const size_t *len, i
     set = SLOT_BUSY(0) ? 1 : (SLOT_BUSY(1) ? 0 : (s->pre_last ^ 1));
     if (SLOT_BUSY(set)) {
         free(pl);
+        free(sd);
         return -1;
     }
 #undef SLOT_BUSY
     s->pre[set].n = 0;
     if (n > s->pre[set].cap) {
         free(s->pre[set].first);
+        free(s->pre[set].side);
         s->pre[set].first = malloc((size_t) n * sizeof(int));
-        s->pre[set].cap = s->pre[set].first ? n : 0;
-        if (!s->pre[set].first) {
+        s->pre[set].side = malloc((size_t) n * sizeof(int));
+        s->pre[set].cap = (s->pre[set].first && s->pre[set].side) ? n : 0;
+        if (!s->pre[set].cap) {
+            free(s->pre[set].first);
+            free(s->pre[set].side);
+            s->pre[set].first = s->pre[set].side = NULL;
             free(pl);
+            free(sd);
             return -1;
         }
     }
     for (i = 0; i < n; i++) {
-        s->pre[set].first[i] = -1;
+        s->pre[set].first[i] = s->pre[set].side[i] = -1;
     }
     for (part = 0; part < 2; part++) {
         for (i = 0; i < n; i++) {
             const int mine = part ? (len[i] > g_early_bytes && len[i] <= g_late_bytes && i >= g_late_from)
                                   : len[i] <= g_early_bytes;
-            if (mine && locate_planes(s, pkt[i], len[i], pl + m) == 0) {
+            if (mine && locate_planes(s, &d->vidmeta, pkt[i], len[i], pl + m, &one) == 0) {
                 s->pre[set].first[i] = m;
                 m += 3;
+                /* the picture's side information rides along (not when the overlay wants the
+                 * vectors on the host) */
+                if (one.base && !d->draw_info) {
+                    s->pre[set].side[i] = ms;
+                    sd[ms++] = one;
+                }
             }
         }
         if (!part) {
             s->pre[set].nearly = m;
+            s->pre[set].nsides_early = ms;
         }
     }
     s->pre[set].nspans = m;
+    s->pre[set].nsides = ms;
     if (m) {
-        const int got = dsvcu_parse_begin(s->ctx, pl, m, s->pre[set].nearly);
+        const int got = dsvcu_parse_begin(s->ctx, pl, m, s->pre[set].nearly, sd, ms, s->pre[set].nsides_early);
         if (got < 0) {
             DSV_ERROR(("dsv_dec_preparse: %s", dsvcu_last_error()));
             free(pl);
+            free(sd);
             return -1;
         }
         s->pre[set].cset = got;
@@ -887,6 +946,7 @@ dsv_dec_preparse(DSV_DECODER *d, const uint8_t *const *pkt, const size_t *len, i
     s->pre[set].n = n;
     s->pre_last = set;
     free(pl);
+    free(sd);
     DPROF(s, DP_PREPARSE);
     return set;
 }
@@ -904,22 +964,29 @@ dsv_dec_preparse_pending(DSV_DECODER *d, int set)
 static int
 preparse_collect(DEC_STATE *s, int set, int part)
 {
-    int *ok, i;
+    int *ok, *sok, i;
     if (!s->pre[set].pending[part]) {
         return 0;
     }
     s->pre[set].pending[part] = 0;
-    ok = malloc((size_t) s->pre[set].nspans * sizeof(int));
-    if (!ok || dsvcu_parse_end(s->ctx, s->pre[set].cset, part, ok)) {
+    ok = malloc((size_t) (s->pre[set].nspans + s->pre[set].nsides + 1) * sizeof(int));
+    sok = ok ? ok + s->pre[set].nspans : NULL;
+    if (!ok || dsvcu_parse_end(s->ctx, s->pre[set].cset, part, ok, sok)) {
         DSV_ERROR(("dsv_dec_preparse: %s", ok ? dsvcu_last_error() : "out of memory"));
         free(ok);
         s->pre[set].n = 0;
         return -1;
     }
     for (i = 0; i < s->pre[set].n; i++) {
-        const int f = s->pre[set].first[i];
-        if (f >= 0 && (f >= s->pre[set].nearly) == part && !(ok[f] && ok[f + 1] && ok[f + 2])) {
-            s->pre[set].first[i] = -1;
+        const int f = s->pre[set].first[i], sd = s->pre[set].side[i];
+        if (f >= 0 && (f >= s->pre[set].nearly) == part) {
+            if (!(ok[f] && ok[f + 1] && ok[f + 2])) {
+                s->pre[set].first[i] = -1;
+            }
+            /* (a picture's side information is in the part its planes are in) */
+            if (sd >= 0 && !sok[sd]) {
+                s->pre[set].side[i] = -1;
+            }
         }
     }
     free(ok);

@@ -140,8 +140,27 @@ typedef struct {
     uint32_t len;
     int w, h;
 } dsvcu_plane_bits;
-int dsvcu_parse_begin(dsvcu_ctx *ctx, const dsvcu_plane_bits *pl, int n, int n_early);
-int dsvcu_parse_end(dsvcu_ctx *ctx, int set, int part, int *ok);
+/* Side information of an inter picture for the same batch (reference dsv_decoder.c:
+ * decode_stability_blocks :77-101, decode_motion :137-222; spec B.2.3.1, B.2.3.4): `base` points
+ * into the packet, at or in front of the first of the six sub-streams' data -- skip bits, mode
+ * bits, vector x, vector y, intra sub-block masks + DC, EPRM bits -- and base_len bytes are
+ * copied (they must reach 8 bytes past the last sub-stream: the readers look that far);
+ * off[k] / len[k] = start (relative to base) and coded length of sub-stream k; flips: bit 0 / 1 /
+ * 2 = the skip / mode / EPRM bits are stored inverted.  side_ok[i] = 0: a reader ran past the
+ * end of its sub-stream -- decode that picture's side information on the host. */
+typedef struct {
+    const uint8_t *base;
+    uint32_t base_len;
+    uint32_t off[6], len[6];
+    int nbh, nbv;
+    int flips;
+} dsvcu_side_bits;
+int dsvcu_parse_begin(dsvcu_ctx *ctx, const dsvcu_plane_bits *pl, int n, int n_early, const dsvcu_side_bits *sd,
+                      int nsd, int nsd_early);
+int dsvcu_parse_end(dsvcu_ctx *ctx, int set, int part, int *ok, int *side_ok);
+/* picture `side` of a collected batch: its vector field and block flags become the context's
+ * current side information (what dsvcu_set_side uploads), device to device */
+int dsvcu_set_side_parsed(dsvcu_ctx *ctx, int set, int side, int nblocks);
 int dsvcu_parse_planes(dsvcu_ctx *ctx, const dsvcu_plane_bits *pl, int n, int *ok);
 /* symbols found in plane `span` of a collected batch, -1 if it was not ok */
 int dsvcu_parsed_count(dsvcu_ctx *ctx, int set, int span);

@@ -123,16 +123,16 @@ def _dequant(geom, emu, isP, q):
         plr = (P.DSVCU_PLANE_BITS * 3)()
         for i in range(3):
             plr[i].bits, plr[i].len, plr[i].w, plr[i].h = pl[2 - i].bits, pl[2 - i].len, pl[2 - i].w, pl[2 - i].h
-        set_r = lib.dsvcu_parse_begin(D.ctx, plr, 3, 3)
-        set_f = lib.dsvcu_parse_begin(D.ctx, pl, 6, 2)  # in two parts: planes 0-1, planes 2-5
+        set_r = lib.dsvcu_parse_begin(D.ctx, plr, 3, 3, None, 0, 0)
+        set_f = lib.dsvcu_parse_begin(D.ctx, pl, 6, 2, None, 0, 0)  # in two parts: planes 0-1, planes 2-5
         assert sorted((set_r, set_f)) == [0, 1], lib.dsvcu_last_error()
-        assert lib.dsvcu_parse_begin(D.ctx, pl, 6, 6) < 0  # a third one has nowhere to go
+        assert lib.dsvcu_parse_begin(D.ctx, pl, 6, 6, None, 0, 0) < 0  # a third one has nowhere to go
         okr = (C.c_int * 3)()
-        D.ck(lib.dsvcu_parse_end(D.ctx, set_r, 0, okr))
-        D.ck(lib.dsvcu_parse_end(D.ctx, set_f, 1, okv))
+        D.ck(lib.dsvcu_parse_end(D.ctx, set_r, 0, okr, None))
+        D.ck(lib.dsvcu_parse_end(D.ctx, set_f, 1, okv, None))
         assert list(okv) == [0, 0, 1, 1, 1, 1]  # (only the entries of the part are written)
         assert lib.dsvcu_dequant_parsed(D.ctx, k, q, C.byref(fm), set_f, 0) != 0  # part 0 not collected yet
-        D.ck(lib.dsvcu_parse_end(D.ctx, set_f, 0, okv))
+        D.ck(lib.dsvcu_parse_end(D.ctx, set_f, 0, okv, None))
         assert list(okv) == [1] * 6 and list(okr) == [1] * 3
         assert [lib.dsvcu_parsed_count(D.ctx, set_f, i) for i in range(6)] == counts * 2
         assert [lib.dsvcu_parsed_count(D.ctx, set_r, i) for i in range(3)] == counts[::-1]
