@@ -1751,11 +1751,14 @@ dsvcu_dequant_parsed(dsvcu_ctx *c, dsvcu_coefs *k, int q, const dsvcu_fmeta *fm,
             return fail_msg("dsvcu_dequant_parsed: plane was not parsed for this geometry");
         }
         dsvcu_scan_layout(k->w[p], k->h[p], part[p]);
-        CK(dsvcu_memset_async(k->data[p], 0, (size_t) k->w[p] * k->h[p] * sizeof(int32_t), c->stream));
         J.meta[p] = S->d_meta + (first_span + p) * HZ_META_WORDS;
         J.lfq[p] = fm->lossless ? 1 : lfquant(qf, p, fm);
         if (m[HZ_META_NSYM] > most) most = m[HZ_META_NSYM];
     }
+    /* the three planes are one allocation (dsvcu_coefs_create): one zero-fill */
+    CK(dsvcu_memset_async(k->alloc, 0,
+                          ((size_t) k->w[0] * k->h[0] + (size_t) k->w[1] * k->h[1] + (size_t) k->w[2] * k->h[2]) * sizeof(int32_t),
+                          c->stream));
     /* grid for the fullest level of the fullest plane (grid-stride loops inside) */
     const int grid = grid_for(most > 0 ? most : 1, 256 * 4);
     for (l = -1; l < 3; l++) {
