@@ -1,10 +1,11 @@
 #!/bin/bash
-# round-2 checkpoint: the whole GPU test suite, the default bench line, the launch list
+# round-2 checkpoint: GPU tests (all, or the files given), the default bench line, the launch list
 cd "$GRAFT_REPO_ROOT" || exit 1
 export CUDA_DEVICE_MAX_CONNECTIONS=32
 O=gpurun_out
 TAG=${1:-ck}
-timeout 1500 python -m pytest tests -x -q -m gpu > $O/gputest_$TAG.log 2>&1
+TESTS=${2:-tests}
+timeout 1500 python -m pytest $TESTS -x -q -m gpu > $O/gputest_$TAG.log 2>&1
 echo "pytest rc=$?"; tail -3 $O/gputest_$TAG.log
 timeout 900 python bench.py > $O/bench_$TAG.json 2> $O/bench_$TAG.log
 echo "bench rc=$?"; tail -c 600 $O/bench_$TAG.json | head -c 300; echo
