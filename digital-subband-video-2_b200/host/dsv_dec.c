@@ -823,28 +823,81 @@ locate_planes(const DEC_STATE *s, const DSV_META *meta, const uint8_t *pkt, size
     return 0;
 }
 
-/* Which pictures go to the device parser.  A plane is one serial chain; a device thread walks
- * it at about 5 cycles per instruction, ~0.2 us per (run, value) pair (measured,
+/* Which pictures go to the device parser, and into which part of the batch.
+ *
+ * A plane is one serial chain; a device thread walks it at about 5 cycles per instruction,
+ * ~0.2 us per (run, value) pair = ~0.25 us per byte of picture (measured,
  * profiles/r2_ncu_hzcc_parse.txt) -- ten times slower than a core.  What the device offers is
  * that all chains of a batch run side by side, beside the reconstruction of the pictures in
- * front of them, and cost the host nothing; a part of the batch is ready when its longest
- * chain is.  Pictures up to 64 KB (about 75 000 pairs = 15 ms, the time the host needs for
- * the intra picture that leads the GOP: 1080p, qp 60: 550 KB, 11 ms) form part 0.  Longer ones
- * up to 256 KB (the pictures behind a scene cut) form part 1, which only they wait for; if
- * they lead the batch they stay on the host, like anything longer (the intra picture). */
-#define PREPARSE_EARLY_BYTES (64 * 1024)
-#define PREPARSE_LATE_BYTES (256 * 1024)
-#define PREPARSE_LATE_FROM 8 /* a long chain needs the time of this many pictures in front of it */
-static volatile size_t g_early_bytes = PREPARSE_EARLY_BYTES, g_late_bytes = PREPARSE_LATE_BYTES;
-static volatile int g_late_from = PREPARSE_LATE_FROM;
+ * front of them, and cost the host nothing.  A part of the batch is ready when its LONGEST
+ * chain is, so a picture belongs on the device if its chain is over by the time the decoder
+ * gets to it -- which is a question of how much work lies in front of it in the batch:
+ *
+ *   the walk below keeps a clock t (ms from the start of the batch): a picture parsed on the
+ *   host advances it by its parse time (~0.025 us per byte) or by the time the device needs
+ *   to reconstruct a picture, whichever is longer; a picture parsed on the device by the
+ *   reconstruction time.  The first picture whose chain is over at t (+ half a millisecond)
+ *   opens part 0 and fixes its deadline; later pictures join part 0 if their chain meets that
+ *   deadline, part 1 if it is over by the time they are reached (and not longer than the chain
+ *   that opened part 1, whose waiters would otherwise wait for it), else they stay on the host.
+ *
+ * 1080p, qp 60, GOP of 48: the intra picture (550 KB: 137 ms on the device, 11 ms on a core)
+ * stays on the host, the P pictures (50 KB: 10-12 ms) are part 0 and ready when the host is
+ * done with the intra picture, the 100-190 KB pictures behind a scene cut at picture 40 are
+ * part 1.  CIF: the 25 KB intra picture (6 ms) at the head of a stream stays on the host --
+ * the 2 KB pictures behind it are ready in half a millisecond --, the one that leads the
+ * second GOP goes to part 1.
+ * dsv_set_device_entropy_limits replaces the model by fixed sizes. */
+#define PREPARSE_DEV_MS_PER_BYTE 0.25e-3
+#define PREPARSE_HOST_MS_PER_BYTE 0.025e-3
+#define PREPARSE_SLACK_MS 0.5
+static volatile size_t g_early_bytes = 0, g_late_bytes = 0;
+static volatile int g_late_from = 0;
 
-/* the three limits above, process-wide (include/dsv_session.h); 0 / negative = default */
+/* fixed limits instead of the model (include/dsv_session.h): packets up to early_bytes form
+ * part 0, longer ones up to late_bytes part 1 unless they are among the first late_from
+ * pictures of the batch; early_bytes <= 0 restores the model */
 void
 dsv_set_device_entropy_limits(long early_bytes, long late_bytes, int late_from)
 {
-    g_early_bytes = early_bytes > 0 ? (size_t) early_bytes : PREPARSE_EARLY_BYTES;
-    g_late_bytes = late_bytes > 0 ? (size_t) late_bytes : PREPARSE_LATE_BYTES;
-    g_late_from = late_from >= 0 ? late_from : PREPARSE_LATE_FROM;
+    g_early_bytes = early_bytes > 0 ? (size_t) early_bytes : 0;
+    g_late_bytes = late_bytes > 0 ? (size_t) late_bytes : 0;
+    g_late_from = late_from > 0 ? late_from : 0;
+}
+
+/* cls[i] = 0 / 1: picture i goes into part 0 / 1 of the device batch, 2: the host parses it */
+static void
+preparse_classify(const size_t *len, int n, int width, int height, uint8_t *cls)
+{
+    const double t_pic = 0.3 + (double) width * height * 0.55e-6; /* reconstruction of one picture, ms */
+    double t = 0, dl0 = -1, dl1 = -1;
+    int i;
+    for (i = 0; i < n; i++) {
+        const double chain = (double) len[i] * PREPARSE_DEV_MS_PER_BYTE;
+        if (g_early_bytes) {
+            cls[i] = len[i] <= g_early_bytes ? 0 : ((len[i] <= g_late_bytes && i >= g_late_from) ? 1 : 2);
+            continue;
+        }
+        if (dl0 < 0 && chain <= t + PREPARSE_SLACK_MS) {
+            dl0 = t + PREPARSE_SLACK_MS;
+        }
+        if (dl0 >= 0 && chain <= dl0) {
+            cls[i] = 0;
+        } else if (chain + PREPARSE_SLACK_MS <= t && (dl1 < 0 || chain <= dl1)) {
+            if (dl1 < 0) {
+                dl1 = chain;
+            }
+            cls[i] = 1;
+        } else {
+            cls[i] = 2;
+        }
+        if (cls[i] == 2) {
+            const double hp = (double) len[i] * PREPARSE_HOST_MS_PER_BYTE;
+            t += hp > t_pic ? hp : t_pic;
+        } else {
+            t += t_pic;
+        }
+    }
 }
 
 /* Entropy-decode the coefficient planes of the next `n` picture packets on the device, in
@@ -861,6 +914,7 @@ dsv_dec_preparse(DSV_DECODER *d, const uint8_t *const *pkt, const size_t *len, i
     DEC_STATE *s;
     dsvcu_plane_bits *pl;
     dsvcu_side_bits *sd, one;
+    uint8_t *cls;
     int i, m = 0, ms = 0, set, part;
 
     if (!d->got_metadata || n <= 0) {
@@ -909,10 +963,16 @@ dsv_dec_preparse(DSV_DECODER *d, const uint8_t *const *pkt, const size_t *len, i
     for (i = 0; i < n; i++) {
         s->pre[set].first[i] = s->pre[set].side[i] = -1;
     }
+    cls = malloc((size_t) n);
+    if (!cls) {
+        free(pl);
+        free(sd);
+        return -1;
+    }
+    preparse_classify(len, n, d->vidmeta.width, d->vidmeta.height, cls);
     for (part = 0; part < 2; part++) {
         for (i = 0; i < n; i++) {
-            const int mine = part ? (len[i] > g_early_bytes && len[i] <= g_late_bytes && i >= g_late_from)
-                                  : len[i] <= g_early_bytes;
+            const int mine = cls[i] == part;
             if (mine && locate_planes(s, &d->vidmeta, pkt[i], len[i], pl + m, &one) == 0) {
                 s->pre[set].first[i] = m;
                 m += 3;
@@ -929,6 +989,7 @@ dsv_dec_preparse(DSV_DECODER *d, const uint8_t *const *pkt, const size_t *len, i
             s->pre[set].nsides_early = ms;
         }
     }
+    free(cls);
     s->pre[set].nspans = m;
     s->pre[set].nsides = ms;
     if (m) {

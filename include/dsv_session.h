@@ -89,11 +89,13 @@ int dsv_pool_decode(dsv_pool *pool, const uint8_t *dsv, size_t len, uint8_t *dst
  * 0 = all of them on the host threads.  Same output either way.  Process-wide; returns the
  * previous setting. */
 int dsv_set_device_entropy_decode(int on);
-/* Which pictures of a batch the device parser takes (host/dsv_dec.c, dsv_dec_preparse):
- * packets up to early_bytes (default 64 KB) are parsed together and wanted first; longer ones
- * up to late_bytes (256 KB) form a second part that only they wait for, unless they are among
- * the first late_from (8) pictures of the batch; everything else stays on the host.
- * 0 (late_from: negative) restores a default.  Process-wide. */
+/* Which pictures of a batch the device parser takes (host/dsv_dec.c, preparse_classify).  By
+ * default a small model decides from the picture sizes whether a picture's chain is over by
+ * the time the decoder reaches it.  With early_bytes > 0 fixed sizes are used instead: packets
+ * up to early_bytes are parsed together and wanted first; longer ones up to late_bytes form a
+ * second part that only they wait for, unless they are among the first late_from pictures of
+ * the batch; everything else stays on the host.  early_bytes <= 0 restores the model.
+ * Process-wide. */
 void dsv_set_device_entropy_limits(long early_bytes, long late_bytes, int late_from);
 
 /* the same with the frames in pinned memory allocated by the call (dsv_pinned_free) */

@@ -57,9 +57,9 @@ def _whole_stream_vs_packetwise(emu):
     lib = P.load(emu)
     sizes = sorted(len(p) for p in P.split_packets(data)[1:])
     try:
-        # default limits (everything is "short" here); then limits that send the larger half of
-        # the pictures into the second part of their batch and keep the largest on the host
-        for limits in ((0, 0, -1), (sizes[len(sizes) // 2], sizes[-8], 2)):
+        # the size model; limits that send the larger half of the pictures into the second part
+        # of their batch and keep the largest on the host; everything in the first part
+        for limits in ((0, 0, 0), (sizes[len(sizes) // 2], sizes[-8], 2), (1 << 30, 0, 0)):
             lib.dsv_set_device_entropy_limits(*limits)
             for device_entropy in (1, 0, -1):
                 meta, nfr, whole = P.decode_frames(data, emu=emu, device_entropy=device_entropy)
@@ -67,7 +67,7 @@ def _whole_stream_vs_packetwise(emu):
                 assert whole == b"".join(b"".join(f) for f in packetwise), "device_entropy=%d limits %r" % (
                     device_entropy, limits)
     finally:
-        lib.dsv_set_device_entropy_limits(0, 0, -1)
+        lib.dsv_set_device_entropy_limits(0, 0, 0)
 
 
 @pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
