@@ -193,6 +193,7 @@ def load(emu=False):
         "dsvcu_parse_begin": (ip, [vp, P(DSVCU_PLANE_BITS), ip, ip, vp, ip, ip]),
         "dsvcu_parse_end": (ip, [vp, ip, ip, P(ip), P(ip)]),
         "dsvcu_set_side_parsed": (ip, [vp, ip, ip, ip]),
+        "dsvcu_parse_ready": (ip, [vp, ip, ip]),
         "dsvcu_parse_planes": (ip, [vp, P(DSVCU_PLANE_BITS), ip, P(ip)]),
         "dsvcu_parsed_count": (ip, [vp, ip, ip]),
         "dsvcu_dequant_parsed": (ip, [vp, vp, ip, P(DSVCU_FMETA), ip, ip]),

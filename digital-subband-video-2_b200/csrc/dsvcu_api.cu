@@ -1688,6 +1688,38 @@ dsvcu_parse_end(dsvcu_ctx *c, int set, int part, int *ok, int *side_ok)
     return 0;
 }
 
+#ifdef DSVCU_EMU
+static int g_emu_not_ready_every, g_emu_ready_calls;
+extern "C" void
+dsvcu_emu_parse_not_ready(int every)
+{
+    g_emu_not_ready_every = every;
+    g_emu_ready_calls = 0;
+}
+#endif
+
+/* has part `part` of the batch in `set` been parsed?  1: yes (dsvcu_parse_end will not wait),
+ * 0: still running, -1: no such batch */
+extern "C" int
+dsvcu_parse_ready(dsvcu_ctx *c, int set, int part)
+{
+    dsvcu_ctx::ParseSet *S;
+    if (set < 0 || set > 1 || part < 0 || part > 1 || !c->pset[set].n) return fail_msg("dsvcu_parse_ready: no such batch");
+    S = &c->pset[set];
+    if (!S->pending[part]) return 1;
+#ifdef DSVCU_EMU
+    /* test hook of the emulation build: every n-th question is answered "not yet" */
+    if (g_emu_not_ready_every > 0 && ++g_emu_ready_calls % g_emu_not_ready_every == 0) return 0;
+#else
+    {
+        const cudaError_t e = cudaEventQuery(S->ev_parsed[part]);
+        if (e == cudaErrorNotReady) return 0;
+        if (e != cudaSuccess) return fail("dsvcu_parse_ready", (int) e);
+    }
+#endif
+    return 1;
+}
+
 /* a batch of one part without side information, begun and collected in one call: the batch is
  * set 0 or 1 (returned) */
 extern "C" int

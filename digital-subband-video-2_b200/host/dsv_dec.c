@@ -76,6 +76,7 @@ typedef struct {
     int ph_frames;
     int ph_where[3]; /* pictures parsed by the device (part 0, part 1) and by the host */
     int ph_side_dev; /* pictures whose side information was decoded on the device too */
+    int ph_stolen;   /* pictures sent to the device parser that the host parsed because it got there first */
     /* batches of pictures whose coefficient planes are entropy-decoded on the device ahead of
      * time (dsv_dec_preparse), one per parse set of the context: first span of picture i in
      * the batch, or -1 where the host parses */
@@ -164,7 +165,8 @@ state_free(DEC_STATE *s)
                            s->ph_ms[i] / s->ph_frames, s->ph_wall[i] / s->ph_frames);
         }
         fprintf(stderr, "%s planes parsed on the device for %d + %d pictures (part 0 + part 1; side information of %d), "
-                "on the host for %d\n", line, s->ph_where[0], s->ph_where[1], s->ph_side_dev, s->ph_where[2]);
+                "on the host for %d (%d of them because the device parser was not through yet)\n", line, s->ph_where[0],
+                s->ph_where[1], s->ph_side_dev, s->ph_where[2], s->ph_stolen);
     }
     if (s->ctx) {
         dsvcu_sync(s->ctx);
@@ -554,7 +556,7 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
     DSV_FRAME *host;
     DSV_FNUM fno;
     int stats[DSV_MAX_STAT];
-    int i, nblk, quant, is_ref, do_filter, isP, good_planes = 0, on_device = 0, planes_dev, side_dev;
+    int i, nblk, quant, is_ref, do_filter, isP, good_planes = 0, on_device = 0, planes_dev, side_dev, stolen = 0;
 
     if (g_prof < 0) {
         g_prof = getenv("DSV_PROFILE") ? atoi(getenv("DSV_PROFILE")) : 0;
@@ -610,14 +612,23 @@ decode_picture(DSV_DECODER *d, DEC_STATE *s, DSV_BITRD *br, int pkt_type, DSV_FR
 
     /* planes (and, for an inter picture, side information) that went ahead to the device parser */
     if (tls_parsed >= 0 && tls_parsed < s->pre[tls_parsed_set].n && s->pre[tls_parsed_set].first[tls_parsed] >= 0) {
+        const int part = s->pre[tls_parsed_set].first[tls_parsed] >= s->pre[tls_parsed_set].nearly;
         DPROF(s, DP_SIDE);
-        if (preparse_collect(s, tls_parsed_set,
-                             s->pre[tls_parsed_set].first[tls_parsed] >= s->pre[tls_parsed_set].nearly)) {
+        /* Never wait for the device parser: if this picture's part of the batch is not through
+         * yet, the picture is parsed here and now (the device's copy of it goes unused) -- the
+         * host thread has nothing better to do, and the device, which runs behind the host,
+         * gets its next picture sooner.  A host that is short of cores runs behind the parser
+         * and finds its pictures ready. */
+        if (s->pre[tls_parsed_set].pending[part] && dsvcu_parse_ready(s->ctx, s->pre[tls_parsed_set].cset, part) == 0) {
+            stolen = 1;
+            s->ph_stolen++;
+        } else if (preparse_collect(s, tls_parsed_set, part)) {
             return DSV_DEC_ERROR;
         }
         DPROF(s, DP_PREPARSE);
     }
-    planes_dev = tls_parsed >= 0 && tls_parsed < s->pre[tls_parsed_set].n && s->pre[tls_parsed_set].first[tls_parsed] >= 0;
+    planes_dev = !stolen && tls_parsed >= 0 && tls_parsed < s->pre[tls_parsed_set].n &&
+                 s->pre[tls_parsed_set].first[tls_parsed] >= 0;
     side_dev = planes_dev && isP && !d->draw_info && s->pre[tls_parsed_set].side[tls_parsed] >= 0;
 
     if (!side_dev) {

@@ -158,6 +158,8 @@ typedef struct {
 int dsvcu_parse_begin(dsvcu_ctx *ctx, const dsvcu_plane_bits *pl, int n, int n_early, const dsvcu_side_bits *sd,
                       int nsd, int nsd_early);
 int dsvcu_parse_end(dsvcu_ctx *ctx, int set, int part, int *ok, int *side_ok);
+/* 1: that part of the batch has been parsed (dsvcu_parse_end will not wait), 0: still running */
+int dsvcu_parse_ready(dsvcu_ctx *ctx, int set, int part);
 /* picture `side` of a collected batch: its vector field and block flags become the context's
  * current side information (what dsvcu_set_side uploads), device to device */
 int dsvcu_set_side_parsed(dsvcu_ctx *ctx, int set, int side, int nblocks);

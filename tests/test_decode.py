@@ -1,5 +1,7 @@
 """Whole-stream decode parity: dsv_dec() of the B200 library vs the reference
 decoder (oracle/_ref/dsv2 d) on streams produced by the reference encoder."""
+import ctypes as C
+
 import pytest
 
 import util
@@ -66,8 +68,18 @@ def _whole_stream_vs_packetwise(emu):
                 assert nfr == n
                 assert whole == b"".join(b"".join(f) for f in packetwise), "device_entropy=%d limits %r" % (
                     device_entropy, limits)
+        if emu:
+            # the host takes over pictures whose part of the batch is "not through yet"
+            # (emulation-only hook: every second / third question is answered that way)
+            for every in (2, 3):
+                lib.dsvcu_emu_parse_not_ready.argtypes = [C.c_int]
+                lib.dsvcu_emu_parse_not_ready(every)
+                meta, nfr, whole = P.decode_frames(data, emu=emu, device_entropy=1)
+                assert nfr == n and whole == b"".join(b"".join(f) for f in packetwise), "not ready every %d" % every
     finally:
         lib.dsv_set_device_entropy_limits(0, 0, 0)
+        if emu:
+            lib.dsvcu_emu_parse_not_ready(0)
 
 
 @pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
