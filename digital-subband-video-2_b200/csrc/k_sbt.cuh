@@ -220,6 +220,18 @@ sbt_inv_lift_tile(const SbtLevel &L, int32_t *t, int tile_x, int tile_y)
             t[ty * SBT_SW + tx] -= sbt_lo_term<F>(t + ty * SBT_SW, 1, X0, X, sw, ring);
         }
     }
+    if (sw == 1 && tile_x == 0) {
+        /* A line of ONE sample: the reference still executes "v[0] -= v[s] >> 1" (sbt.c:199, :221,
+         * :296) and, with the rows filtered in place in the coefficient plane (inv_2d, :462-473),
+         * v[s] is the plane's coefficient at column 1 of that row -- a sample of a finer level's
+         * HL band that no coarser level has touched yet.  (Pictures 8 or more times as tall as
+         * wide get here.  The same thing in a COLUMN of one sample reads scratch memory of another
+         * level: DESIGN.md, known divergences.) */
+        PAR_FOR(k, SBT_TH) {
+            int ty = k + SBT_HALO, Y = Y0 + ty;
+            if (Y < sh) t[ty * SBT_SW + SBT_HALO] -= L.bands[Y * fw + 1] >> 1;
+        }
+    }
     DSVCU_SYNC();
     PAR_FOR(k, SBT_TH * (SBT_SW / 2)) {
         int ty = k / (SBT_SW / 2) + SBT_HALO, tx = (k % (SBT_SW / 2)) * 2 + 1;
@@ -308,6 +320,15 @@ sbt_fwd_lift_tile(const SbtLevel &L, int32_t *t, int tile_x, int tile_y)
                 ring = L.blockdata[bc + br * L.nbh] & BD_RINGING;
             }
             t[ty * SBT_SW + tx] += sbt_lo_term<F>(t + ty * SBT_SW, 1, X0, X, sw, ring);
+        }
+    }
+    if (sw == 1 && tile_x == 0) {
+        /* a row of ONE sample: "v[0] += v[s] >> 1" (sbt.c:199, :221) with v = the coefficient plane
+         * itself (fwd_2d, :449-460): v[s] is column 1 of the row, the HL band the level that went
+         * from two columns to one has already written (see sbt_inv_lift_tile) */
+        PAR_FOR(k, SBT_SH) {
+            int Y = Y0 + k;
+            if (Y >= 0 && Y < sh) t[k * SBT_SW + SBT_HALO] += L.out_bands[Y * fw + 1] >> 1;
         }
     }
     DSVCU_SYNC();

@@ -44,14 +44,18 @@ CASES = [
     ("c422q", 176, 144, 5, "422", 30, ["-qp=30", "-gop=2"], dict(qp=30, gop=2), {}),
     ("c411", 352, 288, 5, "411", 30, ["-qp=60"], dict(qp=60), {}),
     ("c410", 352, 288, 5, "410", 30, ["-qp=60"], dict(qp=60), {}),
+    # 8 and 16 times as tall as wide: lifting levels meet ROWS of one sample, where the reference adds
+    # the neighbouring coefficient of the plane (sbt.c:199, :221 with v = the plane itself) -- lossless
+    # (every plane), intra chroma (CC levels) and P pictures
+    ("tall_ll444", 64, 512, 3, "444", 30, ["-qp=100"], dict(qp=100), {}),
+    ("tall_420", 64, 512, 4, "420", 30, ["-qp=55", "-gop=3"], dict(qp=55, gop=3), {}),
+    ("tall16_422", 32, 512, 3, "422", 30, ["-qp=40"], dict(qp=40), {}),
 ]
 BIG = [
     ("fhd_b32", 1920, 1080, 3, "420", 30, ["-qp=50", "-bszx=1", "-bszy=1"], dict(qp=50, bszx=1, bszy=1), {}),
     ("hd_static", 1280, 720, 4, "420", 50, ["-qp=70"], dict(qp=70), dict(noise=0.0, sensor=0)),
-    # wider than 1280 and not "mostly square": 32 x 16 blocks (dsv_encoder.c:1203-1209).  Aspect ratios of 8:1
-    # and beyond are NOT covered: there a lifting level meets a 1-sample dimension and the reference's
-    # DO_SIMPLE_LO / DO_5_TAP_LO read v[s] outside the line (sbt.c:199, :221), i.e. stale scratch memory from
-    # earlier calls -- its own encoder and decoder disagree on such input.
+    # wider than 1280 and not "mostly square": 32 x 16 blocks (dsv_encoder.c:1203-1209).  8 times as wide as
+    # tall and beyond is NOT covered: see test_wide_pictures_reference_disagrees_with_itself below.
     ("wide_32x16", 1536, 384, 3, "420", 30, ["-qp=60"], dict(qp=60), {}),
 ]
 FMT = {"420": 0x5, "444": 0x0, "422": 0x4, "411": 0x8, "410": 0xA}
@@ -93,3 +97,28 @@ def test_option_emulated(case):
 @pytest.mark.parametrize("case", CASES + BIG, ids=[c[0] for c in CASES + BIG])
 def test_option_gpu(case):
     _run(case, False)
+
+
+@need_ref
+def test_wide_pictures_reference_disagrees_with_itself():
+    """DESIGN.md section 4, known divergences.  8 or more times as wide as tall, a lifting level meets
+    COLUMNS of one sample and the reference's "v[0] op v[s] >> 1" (sbt.c:199, :221) reads the row below in
+    its scratch buffer, which another level left there -- a different one in the encoder than in the
+    decoder.  Shown here with the reference alone: its lossless 4:4:4 round trip is the identity at 4:1
+    and is not at 8:1.  This build reads a zero there, so its own lossless round trip stays the identity;
+    bit parity with the reference is neither possible nor meaningful for such pictures."""
+    util.ensure_emu()
+    P = util.pkg()
+    for w, h, consistent in ((512, 128, True), (512, 64, False)):
+        y4m = util.clip("aspect", w, h, 3, "444")
+        _, _, src = util.read_y4m(y4m)
+        want = b"".join(ops.yuv_bytes(f) for f in src)
+        dsv = util.ref_encode(y4m, ["-qp=100"], "ref")
+        _, _, dec = util.read_y4m(util.ref_decode(dsv))
+        assert (b"".join(ops.yuv_bytes(f) for f in dec) == want) == consistent, (w, h)
+        o = P.enc_opts(w, h, FMT["444"], (30, 1), emu=True, qp=100)
+        ours = P.encode_frames(o, want, 3, emu=True)
+        _, n, back = P.decode_frames(ours, emu=True)
+        assert n == 3 and back == want, "own lossless round trip %dx%d" % (w, h)
+        if consistent:
+            assert ours == open(dsv, "rb").read()
