@@ -1708,8 +1708,10 @@ dsvcu_parse_ready(dsvcu_ctx *c, int set, int part)
     S = &c->pset[set];
     if (!S->pending[part]) return 1;
 #ifdef DSVCU_EMU
-    /* test hook of the emulation build: every n-th question is answered "not yet" */
+    /* test hook of the emulation build: every n-th question is answered "not yet"; -1: every
+     * question about the second part of a batch */
     if (g_emu_not_ready_every > 0 && ++g_emu_ready_calls % g_emu_not_ready_every == 0) return 0;
+    if (g_emu_not_ready_every < 0 && part == 1) return 0;
 #else
     {
         const cudaError_t e = cudaEventQuery(S->ev_parsed[part]);

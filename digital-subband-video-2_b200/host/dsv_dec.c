@@ -946,15 +946,14 @@ dsv_dec_preparse(DSV_DECODER *d, const uint8_t *const *pkt, const size_t *len, i
         free(sd);
         return -1;
     }
-    /* the slot that is not waiting for its result; failing that the older one */
-#define SLOT_BUSY(k) (s->pre[k].pending[0] || s->pre[k].pending[1])
-    set = SLOT_BUSY(0) ? 1 : (SLOT_BUSY(1) ? 0 : (s->pre_last ^ 1));
-    if (SLOT_BUSY(set)) {
-        free(pl);
-        free(sd);
-        return -1;
-    }
-#undef SLOT_BUSY
+    /* The slots alternate: the one used last holds the batch the decoder is working on (or
+     * about to), the other one the batch before it, which is done with.  A part of THAT batch
+     * may never have been collected -- its pictures were all parsed on the host because they
+     * were reached before the parser was through -- so it is collected now, which at worst
+     * waits for a chain that has had two batches' time. */
+    set = s->pre_last ^ 1;
+    (void) preparse_collect(s, set, 0);
+    (void) preparse_collect(s, set, 1);
     s->pre[set].n = 0;
     if (n > s->pre[set].cap) {
         free(s->pre[set].first);

@@ -70,12 +70,16 @@ def _whole_stream_vs_packetwise(emu):
                     device_entropy, limits)
         if emu:
             # the host takes over pictures whose part of the batch is "not through yet"
-            # (emulation-only hook: every second / third question is answered that way)
-            for every in (2, 3):
-                lib.dsvcu_emu_parse_not_ready.argtypes = [C.c_int]
-                lib.dsvcu_emu_parse_not_ready(every)
-                meta, nfr, whole = P.decode_frames(data, emu=emu, device_entropy=1)
-                assert nfr == n and whole == b"".join(b"".join(f) for f in packetwise), "not ready every %d" % every
+            # (emulation-only hook: every n-th question is answered that way; 1 = always, so
+            # parts stay uncollected until their slot is needed again)
+            lib.dsvcu_emu_parse_not_ready.argtypes = [C.c_int]
+            for limits in ((0, 0, 0), (sizes[len(sizes) // 2], sizes[-8], 2), (sizes[len(sizes) // 4], sizes[-2], 0)):
+                lib.dsv_set_device_entropy_limits(*limits)
+                for every in (1, 2, 3, 5, -1):  # (-1: the second part of every batch is never through)
+                    lib.dsvcu_emu_parse_not_ready(every)
+                    meta, nfr, whole = P.decode_frames(data, emu=emu, device_entropy=1)
+                    assert nfr == n and whole == b"".join(b"".join(f) for f in packetwise), "not ready every %d, limits %r" % (
+                        every, limits)
     finally:
         lib.dsv_set_device_entropy_limits(0, 0, 0)
         if emu:
@@ -91,3 +95,35 @@ def test_whole_stream_device_parser_emulated():
 @pytest.mark.gpu
 def test_whole_stream_device_parser_gpu():
     _whole_stream_vs_packetwise(False)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+def test_uncollected_part_does_not_cost_the_next_batches_their_slot():
+    """A part of a batch that nobody waited for (all its pictures were parsed on the host, because
+    they were reached first) is still pending when its slot comes round again, two batches later --
+    while the batch in the other slot is the one being decoded.  Batches of 64 pictures; with
+    fixed limits (second part: intra-sized packets at least 50 pictures into their batch) only the
+    second batch of this clip has a second part, which the emulation hook keeps "not through"."""
+    util.ensure_emu()
+    w, h, n = 96, 64, 200
+    y4m = util.clip("slots", w, h, n, "420")
+    dsv = util.ref_encode(y4m, ["-qp=40", "-gop=48"], "ref")
+    data = open(dsv, "rb").read()
+    P = util.pkg()
+    lib = P.load(True)
+    _, packetwise = P.decode_stream(data, emu=True)
+    want = b"".join(b"".join(f) for f in packetwise)
+    pk = [p for p in P.split_packets(data)[1:] if len(p) > 20]
+    intra = min(len(p) for p in pk if not (p[5] & 1))
+    assert max(len(p) for p in pk if p[5] & 1) < intra
+    late = [[i for i in range(b, min(b + 64, len(pk))) if len(pk[i]) >= intra and i - b >= 50] for b in range(0, len(pk), 64)]
+    assert len(late) >= 4 and not late[0] and late[1] and not late[2], late
+    lib.dsvcu_emu_parse_not_ready.argtypes = [C.c_int]
+    try:
+        lib.dsv_set_device_entropy_limits(intra - 1, 1 << 30, 50)
+        lib.dsvcu_emu_parse_not_ready(-1)
+        meta, nfr, whole = P.decode_frames(data, emu=True, device_entropy=1)
+        assert nfr == n and whole == want
+    finally:
+        lib.dsv_set_device_entropy_limits(0, 0, 0)
+        lib.dsvcu_emu_parse_not_ready(0)
