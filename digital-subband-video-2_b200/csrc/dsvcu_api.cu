@@ -1715,7 +1715,10 @@ dsvcu_parse_ready(dsvcu_ctx *c, int set, int part)
 #else
     {
         const cudaError_t e = cudaEventQuery(S->ev_parsed[part]);
-        if (e == cudaErrorNotReady) return 0;
+        if (e == cudaErrorNotReady) {
+            (void) cudaGetLastError(); /* "not ready" is an answer, not an error: keep it away from CK_LAUNCH */
+            return 0;
+        }
         if (e != cudaSuccess) return fail("dsvcu_parse_ready", (int) e);
     }
 #endif
