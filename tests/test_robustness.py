@@ -183,3 +183,60 @@ def test_corrupt_side_information_lengths_are_contained():
             P.decode_frames(bytes(d), emu=True)
     finally:
         lib.dsv_set_log_level(1)
+
+
+def _device_vs_host_parser(emu, rounds, seed):
+    """Whatever is in a picture packet, the whole-stream decoder must produce the same frames
+    with the coefficient planes and side information parsed on the device (k_hzcc_parse, which
+    refuses what it does not trust) and with everything parsed by the host threads: random
+    damage to the payload of random pictures of a 150-picture stream (single bits, bytes, short
+    stretches; the packet headers and links stay intact)."""
+    import random
+    P = util.pkg()
+    lib = P.load(emu)
+    lib.dsv_set_log_level(0)
+    dsv = util.ref_encode(util.clip("manybatches", 96, 64, 150, "420"), ["-qp=40", "-gop=35"], "ref")
+    data = bytearray(open(dsv, "rb").read())
+    pk = P.split_packets(bytes(data))
+    offs, o = [], 0
+    for p in pk:
+        offs.append(o)
+        o += len(p)
+    rng = random.Random(seed)
+    try:
+        for it in range(rounds):
+            d = bytearray(data)
+            for _ in range(rng.randint(1, 6)):
+                k = rng.randrange(1, len(pk) - 1)
+                if len(pk[k]) < 40:
+                    continue
+                pos = offs[k] + rng.randrange(14, len(pk[k]))
+                mode = rng.randrange(3)
+                if mode == 0:
+                    d[pos] ^= 1 << rng.randrange(8)
+                elif mode == 1:
+                    d[pos] = rng.randrange(256)
+                else:
+                    for j in range(pos, min(pos + rng.randint(1, 12), offs[k] + len(pk[k]))):
+                        d[j] = rng.randrange(256)
+            got = []
+            for device_entropy in (0, 1):
+                try:
+                    _, nfr, frames = P.decode_frames(bytes(d), emu=emu, device_entropy=device_entropy)
+                    got.append((nfr, frames))
+                except RuntimeError as e:
+                    got.append(("error", str(e)))
+            assert got[0] == got[1], "round %d: host parser %r frames, device parser %r" % (it, got[0][0], got[1][0])
+    finally:
+        lib.dsv_set_log_level(1)
+
+
+@need_ref
+def test_device_and_host_parser_agree_on_damaged_streams_emulated():
+    util.ensure_emu()
+    _device_vs_host_parser(True, 40, 11)
+
+
+@pytest.mark.gpu
+def test_device_and_host_parser_agree_on_damaged_streams_gpu():
+    _device_vs_host_parser(False, 40, 12)
